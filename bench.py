@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- 31-mer count_kmer throughput (queries/s) on B200, per the driver contract.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3]
+
+A "step" is one pass of the hot path (pack + backward-search kernels) over one batch of
+synthetic k-mer queries.  Default workload = BASELINE.json configs[1]: 1 M synthetic
+150-bp reads (151 Msymbol BWT), 5 M random + 5 M read-sampled 31-mers, one B200.
+With N > 1 (torchrun, one rank per GPU) every rank holds a replica of the index and its
+own batch of the same size (weak scaling, no data-path collective); the only
+torch.distributed traffic is the barrier and the max-over-ranks of the timings.
+
+One JSON line on stdout (rank 0).  Everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "cfg2": dict(reads=1_000_000, read_len=150, coverage=30.0, error=0.0, n_read=5_000_000, n_random=5_000_000, k=31,
+                 name="configs[1]: 1M synthetic 150bp reads (151 Msymbol BWT), 5M random + 5M read-sampled 31-mers"),
+    # BASELINE.json configs[2]
+    "cfg3": dict(reads=10_000_000, read_len=150, coverage=30.0, error=0.01, n_read=100_000_000, n_random=0, k=31,
+                 name="configs[2]: 10M synthetic 150bp reads with 1% errors (1.51 Gsymbol BWT), 100M read-sampled 31-mers"),
+    # small shape for plumbing checks
+    "tiny": dict(reads=20_000, read_len=150, coverage=30.0, error=0.01, n_read=100_000, n_random=100_000, k=31,
+                 name="tiny: 20k reads, 200k 31-mers (plumbing check, not a bench line)"),
+}
+METRIC = "count_kmer_31mer_queries_per_sec"
+UNIT = "queries/s"
+BLOCK_BYTES = 128
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def build_workload(cfg: dict, device, rank: int):
+    """Synthetic reads -> BWT -> RLE bytes (host) and this rank's query batch (device)."""
+    import torch
+    from harness import bwt_build, synth
+    t0 = time.time()
+    reads = synth.make_reads(cfg["reads"], cfg["read_len"], cfg["coverage"], cfg["error"], device=device)
+    rle, total = bwt_build.build_rle_bwt(reads)
+    rle_host = rle.cpu().numpy()
+    del rle
+    queries = synth.make_queries(reads, cfg["k"], cfg["n_read"], cfg["n_random"], seed_offset=1000 * rank)
+    del reads
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+    log(f"[rank {rank}] workload built in {time.time() - t0:.1f}s: {total} symbols, {rle_host.size} RLE bytes, "
+        f"{queries.shape[0]} queries")
+    return rle_host, total, queries
+
+
+def cpu_reference_leg(orc, q_host, k, threads, target_s, label):
+    """Times the oracle's count_kmer loop on a bounded prefix of the batch."""
+    n = q_host.shape[0]
+    probe = min(n, 50_000)
+    t0 = time.perf_counter()
+    orc.count_kmers_fixed(q_host[:probe], k, threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    m = int(min(n, max(probe, probe / dt * target_s)))
+    t0 = time.perf_counter()
+    counts = orc.count_kmers_fixed(q_host[:m], k, threads=threads)
+    dt = time.perf_counter() - t0
+    log(f"[cpu] {label}: {m} queries in {dt:.2f}s on {threads} thread(s) -> {m / dt:,.0f} q/s")
+    return m / dt, m, counts
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's own CPU algorithm (oracle port; the Rust crate cannot be
+    built in this image) on this box's host cores, all threads, bounded samples of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import oracle as O
+    dev = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")  # GPU only manufactures the inputs
+    rle_host, total, queries = build_workload(cfg, dev, 0)
+    q_host = queries.cpu().numpy()
+    del queries
+    orc = O.RleBWT()
+    orc.load_vector(rle_host)
+    cores = os.cpu_count() or 1
+    k = cfg["k"]
+    n = q_host.shape[0]
+    probe = min(n, 100_000)
+    t0 = time.perf_counter()
+    orc.count_kmers_fixed(q_host[:probe], k, threads=cores)
+    rate = probe / max(time.perf_counter() - t0, 1e-6)
+    per_step = int(min(n, max(probe, rate * 4.0)))  # ~4 s of CPU work per step
+    times = []
+    for s in range(args.warmup + args.steps):
+        a = (s * per_step) % max(1, n - per_step + 1)
+        t0 = time.perf_counter()
+        orc.count_kmers_fixed(q_host[a:a + per_step], k, threads=cores)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    total_t = sum(times)
+    value = per_step * len(times) / total_t
+    sample = f"{per_step} of the workload's {n} queries per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": cfg["name"], "bwt_symbols": total, "k": k, "queries_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, cfg):
+    import numpy as np
+    import torch
+
+    import rust_msbwt_b200 as M
+    from oracle import oracle as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    k = cfg["k"]
+    rle_host, total, queries = build_workload(cfg, dev, rank)
+    n = queries.shape[0]
+    t0 = time.time()
+    bwt = M.RleBWT.new(devices=[local])
+    bwt.load_vector(rle_host)
+    log(f"[rank {rank}] index resident: {bwt.index_bytes / 1e6:.1f} MB in {time.time() - t0:.1f}s")
+
+    stream = torch.cuda.current_stream().cuda_stream
+    words = M.packed_words(k)
+    d_packed = torch.empty(words * n, dtype=torch.int64, device=dev)
+    d_out = torch.empty(n, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(1, dtype=torch.int32, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > L2: evicts index + queries between steps
+
+    def step(ev=None):
+        d_status.zero_()
+        bwt.pack_kmers_device(queries.data_ptr(), k, n, d_packed.data_ptr(), d_status.data_ptr(), stream)
+        if ev:
+            ev[0].record()
+        bwt.count_kmers_packed_device(d_packed.data_ptr(), k, n, d_out.data_ptr(), stream)
+        if ev:
+            ev[1].record()
+
+    # ---- value: kernel-only, inputs resident in HBM ----
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = M.launch_count()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s & 1)               # L2 flush between timed iterations (not inside the event spans)
+        ev[s][0].record()
+        step((ev[s][1], ev[s][2]))
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = M.launch_count() - launches0
+    step_ms = [ev[s][0].elapsed_time(ev[s][2]) for s in range(args.steps)]
+    kern_ms = [ev[s][1].elapsed_time(ev[s][2]) for s in range(args.steps)]
+    total_ms = max_over_ranks(sum(step_ms))
+    clocks = sampler.stop() if rank == 0 else None
+    assert int(d_status.item()) == 0
+    value = world * n * args.steps / (total_ms / 1e3)
+    checksum = int(d_out.sum().item())
+
+    # ---- e2e: the drop-in C-ABI call with HOST buffers (pinned), H2D + D2H inside ----
+    q_pinned = torch.empty((n, k), dtype=torch.uint8, pin_memory=True)
+    q_pinned.copy_(queries)
+    out_pinned = torch.empty(n, dtype=torch.int64, pin_memory=True)
+    q_np, out_np = q_pinned.numpy(), out_pinned.numpy().view(np.uint64)
+    lib = M.load_library()
+    import ctypes
+
+    def e2e_step():
+        rc = lib.msbwt_count_kmers_fixed(bwt.handle, ctypes.c_void_p(q_np.ctypes.data), k, n,
+                                         ctypes.c_void_p(out_np.ctypes.data))
+        assert rc == 0, lib.msbwt_last_error()
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * n * args.steps / e2e_s
+    assert int(out_np.astype(np.int64).sum()) == checksum, "host-path and device-path results differ"
+
+    # ---- parity + CPU baseline + algorithmic bytes (rank 0, bounded samples) ----
+    cpu_baseline = roofline = None
+    extra = {}
+    if rank == 0:
+        q_host = q_np
+        orc = O.RleBWT()
+        orc.load_vector(rle_host)
+        cores = os.cpu_count() or 1
+        got = d_out.cpu().numpy().view(np.uint64)
+        if world == 1:
+            v1, m1, c1 = cpu_reference_leg(orc, q_host, k, 1, 8.0, "single thread")
+            assert (got[:m1] == c1).all(), "GPU counts differ from the CPU oracle"
+            vN, mN, cN = cpu_reference_leg(orc, q_host, k, cores, 8.0, "all-core static split")
+            assert (got[:mN] == cN).all(), "GPU counts differ from the CPU oracle"
+            cpu_baseline = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": f"first {m1} of {n} queries, single thread (the reference's loop)",
+                            "allcore": {"value": vN, "cores": cores, "sample": f"first {mN} of {n} queries"},
+                            "parity_checked_queries": max(m1, mN)}
+        else:
+            m = min(n, 200_000)
+            assert (got[:m] == orc.count_kmers_fixed(q_host[:m], k, threads=cores)).all()
+        # algorithmic bytes: steps the reference executes x distinct 128-B blocks per step
+        ms = min(n, 1_000_000)
+        steps, two = orc.count_kmers_stats(q_host[:ms], k, 8)
+        packed_q = 8 * words
+        bytes_per_query = (steps + two) * BLOCK_BYTES / ms + packed_q + 8
+        peak, peak_src = measured_peak_gbs()
+        kern_s = statistics.mean(kern_ms) / 1e3
+        achieved = bytes_per_query * n / kern_s / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "count_kmers_packed_kernel", "kernel_ms": 1e3 * kern_s,
+                    "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": steps / ms,
+                    "two_block_step_share": two / max(1, steps), "peak_source": peak_src,
+                    "stats_sample": f"first {ms} of {n} queries (oracle replay)"}
+        # gather microbenchmark: what random 128-B reads sustain on this box (K4)
+        try:
+            gb = torch.empty(2 << 30, dtype=torch.uint8, device=dev)
+            sink = torch.zeros(1, dtype=torch.int64, device=dev)
+            res = {}
+            for gran in (32, 64, 128):
+                ng = 1 << 26
+                for it in range(3):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    M.gather_bench(local, gb.data_ptr(), gb.numel(), gran, ng, 1234 + it, sink.data_ptr(), stream)
+                    e1.record()
+                    torch.cuda.synchronize()
+                res[gran] = ng * gran / (e0.elapsed_time(e1) / 1e3) / 1e9
+            roofline["gather_gbs"] = {str(g): v for g, v in res.items()}
+            roofline["frac_of_gather128"] = achieved / res[128]
+            del gb
+        except Exception as e:  # measurement aid only
+            log("gather microbench failed:", e)
+        extra = {"kernel_share_of_step": statistics.mean(kern_ms) / statistics.mean(step_ms)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "bwt_symbols": total, "index_bytes": bwt.index_bytes, "k": k,
+                       "queries_per_gpu_per_step": n, "parallelism": f"replica x{world}, query batch sharded",
+                       "l2": "L2 flushed (512 MB fill) between timed iterations; query batch (n*k bytes) exceeds L2",
+                       "seeds": "torch Philox 0x5EED0001.. (harness/synth.py)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * k, "d2h_bytes_per_step": n * 8,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "wall_s_timed_region": wall,
+            "checksum": checksum,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default=os.environ.get("MSBWT_BENCH_WORKLOAD", "cfg2"))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+/*
+ * msbwt_gpu.h -- C ABI of the B200-native FM-index query engine for msbwt2's
+ * run-length-encoded multi-string BWT.
+ *
+ * This is the drop-in boundary for ONE path of HudsonAlpha/rust-msbwt: the
+ * `BWT` trait surface that `RleBWT` implements (src/msbwt_core.rs:28-162,
+ * src/rle_bwt.rs:44-322) plus the batched `count_kmers` entry point.  A Rust
+ * `extern "C"` module binds exactly these symbols (see INTEGRATION.md and
+ * rust/src/gpu_ffi.rs).  Plain pointers and sizes only; the caller owns every
+ * buffer it passes; the opaque handle owns the device-resident index replicas.
+ *
+ * There is no CPU fallback: if no CUDA device is usable, create fails with
+ * MSBWT_ENODEV.
+ *
+ * Symbol alphabet (src/msbwt_core.rs:4-14): $=0 A=1 C=2 G=3 N=4 T=5, one symbol
+ * per byte in every `syms` argument, exactly the `&[u8]` the reference takes.
+ *
+ * Thread-safety: a handle is immutable after create.  Concurrent query calls on
+ * one handle are allowed; calls that target the same device serialise on an
+ * internal per-device mutex (they share that device's staging workspace).
+ * create/destroy must not race with queries on the same handle.
+ */
+#ifndef MSBWT_GPU_H
+#define MSBWT_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSBWT_ABI_VERSION 1
+
+/* Return codes.  The reference panics where we return EINVAL / EFORMAT; the
+ * Rust shim turns those back into panics to keep trait behaviour
+ * (src/msbwt_core.rs:127, src/rle_bwt.rs:91-93,115-125). */
+enum msbwt_status {
+    MSBWT_OK = 0,
+    MSBWT_EINVAL = 1,  /* symbol >= 6, l > h, h > total_size, NULL where data is required */
+    MSBWT_EIO = 2,     /* open / short read / size mismatch: where the reference returns io::Error
+                          (src/rle_bwt.rs:84,101-112,128-147) */
+    MSBWT_EFORMAT = 3, /* malformed .npy header or RLE symbol >= 6: where the reference panics */
+    MSBWT_ECUDA = 4,   /* a CUDA call failed; msbwt_last_error() has the CUDA string */
+    MSBWT_ENOMEM = 5,
+    MSBWT_ENODEV = 6   /* no usable CUDA device (there is no CPU fallback) */
+};
+
+typedef struct msbwt_index msbwt_index;
+
+/* ---- construction: RleBWT::new + BWT::load_vector / load_numpy_file ---- */
+
+/* Replaces `RleBWT::new()` + `load_vector(Vec<u8>)` (src/rle_bwt.rs:59-66,297-299).
+ * `rle` is the msbwt RLE byte stream (byte = sym | digit<<3, consecutive equal-sym
+ * bytes are little-endian base-32 digits of one run).  The bytes are consumed
+ * during the call (re-laid-out into the device block image) and not retained.
+ * `devices`/`ndev`: CUDA ordinals to replicate the index on; ndev == 0 means the
+ * calling thread's current device.  Returns NULL and sets *err on failure. */
+msbwt_index *msbwt_index_create_from_rle(const uint8_t *rle, uint64_t len,
+                                         const int *devices, int ndev, int *err);
+
+/* Replaces `load_numpy_file` (src/rle_bwt.rs:81-155).  Same acceptance rules:
+ * npy magic/version are not checked, header length is bytes 8..9 little-endian,
+ * the data offset is rounded up to 16, dtype/fortran_order are ignored,
+ * `shape[0]` must equal the remaining file size. */
+msbwt_index *msbwt_index_create_from_npy(const char *path, const int *devices, int ndev, int *err);
+
+/* Same as create_from_rle with explicit layout knobs (testing / tuning):
+ * `superblock_shift` = log2(blocks per superblock), 0 selects the default (24:
+ * 2^32 symbols per superblock).  The reference's only tuning knob, `bin_power`
+ * (RleBWT::with_bin_power, src/rle_bwt.rs:309-322), has no effect on results
+ * and no equivalent here: the device block covers 256 symbols, the reference's
+ * default bin. */
+msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
+                                   uint32_t superblock_shift, int *err);
+
+void msbwt_index_destroy(msbwt_index *idx);
+
+/* ---- accessors: get_total_size / get_symbol_count (src/rle_bwt.rs:172-193) ---- */
+uint64_t msbwt_total_size(const msbwt_index *idx);
+uint64_t msbwt_symbol_count(const msbwt_index *idx, uint8_t sym); /* 0 for sym >= 6 */
+/* start_index[sym] (the C array, src/rle_bwt.rs:374-381); total_size for sym >= 6 */
+uint64_t msbwt_start_index(const msbwt_index *idx, uint8_t sym);
+int msbwt_device_count(const msbwt_index *idx);
+int msbwt_device_ordinal(const msbwt_index *idx, int slot);
+uint64_t msbwt_index_bytes(const msbwt_index *idx); /* device bytes per replica */
+
+/* ---- queries from HOST buffers (the drop-in calls) ---- */
+
+/* Batched BWT::count_kmer (src/msbwt_core.rs:125-161): query i is
+ * syms[offsets[i] .. offsets[i+1]); out[i] = count.  An empty query counts
+ * total_size.  Any symbol >= 6 anywhere in the batch -> MSBWT_EINVAL (the reference
+ * asserts, src/msbwt_core.rs:127) and the contents of `out` are unspecified: symbols
+ * are checked on the device while the batch streams through, never silently accepted.
+ * The batch is split across the handle's devices. */
+int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, const uint64_t *offsets,
+                      uint64_t n, uint64_t *out);
+
+/* Fixed-length form: query i is syms[i*k .. (i+1)*k).  This is the fast path. */
+int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n,
+                            uint64_t *out);
+
+/* Batched BWT::constrain_range (src/rle_bwt.rs:202-287): for each i,
+ * [out_l, out_h) = [C[sym]+rank(sym,l), C[sym]+rank(sym,h)).  The reference's
+ * version is `unsafe` and unchecked; here sym >= 6, l > h or h > total_size
+ * -> MSBWT_EINVAL with outputs untouched. */
+int msbwt_constrain_ranges(const msbwt_index *idx, const uint8_t *sym, const uint64_t *l,
+                           const uint64_t *h, uint64_t n, uint64_t *out_l, uint64_t *out_h);
+
+/* ---- queries on DEVICE buffers (zero-copy callers, kernel-only timing) ----
+ * `slot` indexes the handle's device list; all pointers must be device memory on
+ * that device; `stream` is a cudaStream_t (NULL = legacy default stream).  The
+ * call is asynchronous; `d_status` (device uint32, may be NULL) receives 0 or
+ * MSBWT_EINVAL when a symbol >= 6 was seen (in which case d_out is unspecified). */
+int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, const uint8_t *d_syms,
+                                   uint32_t k, uint64_t n, uint64_t *d_out, uint32_t *d_status,
+                                   void *stream);
+int msbwt_constrain_ranges_device(const msbwt_index *idx, int slot, const uint8_t *d_sym,
+                                  const uint64_t *d_l, const uint64_t *d_h, uint64_t n,
+                                  uint64_t *d_out_l, uint64_t *d_out_h, void *stream);
+
+/* The two stages of msbwt_count_kmers_fixed_device as separate calls, for callers that keep
+ * packed k-mers resident (and for timing the search kernel on its own):
+ *   pack : n*k symbol bytes -> msbwt_packed_words(k)*n u64 words (word-major: word w of query
+ *          q at d_packed[w*n + q]; 21 three-bit symbols per word, the k-mer's LAST symbol in
+ *          the top bits because backward search consumes it first), validating symbols;
+ *   count: the backward search over packed k-mers. */
+uint32_t msbwt_packed_words(uint32_t k);
+int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const uint8_t *d_syms, uint32_t k,
+                            uint64_t n, uint64_t *d_packed, uint32_t *d_status, void *stream);
+int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot, const uint64_t *d_packed,
+                                    uint32_t k, uint64_t n, uint64_t *d_out, void *stream);
+
+/* Number of kernel launches the library has issued so far (all devices). */
+uint64_t msbwt_launch_count(void);
+
+/* ---- measurement aid: random-gather roofline microbenchmark ----
+ * Issues n_gathers independent, uniformly random, `granule`-byte-aligned reads of
+ * `granule` bytes (32, 64 or 128) over `d_buf` (buf_bytes, device memory) on `stream`. */
+int msbwt_gather_bench(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,
+                       uint64_t n_gathers, uint64_t seed, uint64_t *d_sink, void *stream);
+
+/* ---- inspection: the host-side block image (no device needed) ----
+ * Builds the layout.h block image of `rle` exactly as create does and copies it out so
+ * tests can check the loader without a GPU.  Call with blocks == NULL to size:
+ * *nblocks blocks of 32 u32 words, *n_super rows of 8 u64 in cbase. */
+int msbwt_debug_build_image(const uint8_t *rle, uint64_t len, uint32_t superblock_shift,
+                            uint64_t *nblocks, uint32_t *n_super, uint32_t *blocks, uint64_t *cbase);
+
+/* ---- pinned host buffers for callers that want full copy/compute overlap ---- */
+void *msbwt_host_alloc(size_t bytes);
+void msbwt_host_free(void *p);
+
+/* Thread-local description of the last failure in the calling thread ("" if none). */
+const char *msbwt_last_error(void);
+int msbwt_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSBWT_GPU_H */

@@ -31,16 +31,33 @@ class OracleIoError(OSError):
     """The reference returns `Err(io::Error)` here."""
 
 
+def _cpu_signature() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force: bool = False) -> str:
-    """Compile the C restatement in place (gcc; seconds)."""
+    """Compile the C restatement in place (gcc -O3 -march=native; seconds).  The library is
+    rebuilt when the sources are newer or when it was built on a different CPU model
+    (-march=native code from the build container must not run on the GPU box's host)."""
     src = os.path.join(_HERE, "msbwt_oracle.c")
     hdr = os.path.join(_HERE, "msbwt_oracle.h")
-    stale = (not os.path.exists(_SO)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr))
-    if stale and not os.path.exists(src):
-        stale = False
+    tag = _SO + ".cpu"
+    sig = _cpu_signature()
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr))
+    try:
+        stale = stale or open(tag).read() != sig
+    except OSError:
+        stale = True
     if force or stale:
-        subprocess.check_call(["make", "-s", "-C", _HERE, "libmsbwt_oracle.so"])
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "libmsbwt_oracle.so"])
+        with open(tag, "w") as f:
+            f.write(sig)
     return _SO
 
 

@@ -1,0 +1,521 @@
+// capi.cu -- the C ABI declared in include/msbwt_gpu.h: handle management, device
+// replicas, host<->device staging pipelines and the multi-GPU batch split.
+//
+// Reference surface being replaced: the `BWT` trait as implemented by `RleBWT`
+// (src/msbwt_core.rs:28-162, src/rle_bwt.rs:44-322).  There is no CPU fallback
+// anywhere in this file: every query entry point ends in a kernel launch.
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "../../include/msbwt_gpu.h"
+#include "engine.h"
+
+using namespace msbwt;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? MSBWT_ENOMEM : MSBWT_ECUDA,             \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// per-device staging for the host-buffer entry points: two lanes so that the copy-in of
+// chunk c+1 overlaps the kernels of chunk c
+struct Lane {
+    cudaStream_t stream = nullptr;
+    DevBuf in_a, in_b, in_c, packed, out_a, out_b;
+};
+
+struct Replica {
+    int device = -1;
+    uint4 *d_blocks = nullptr;
+    uint64_t *d_cbase = nullptr;
+    IndexView view{};
+    std::mutex mu;
+    Lane lane[2];
+    DevBuf dev_packed;       // scratch for the *_device entry points
+    uint32_t *d_status = nullptr;  // [0,1]: per-lane flags; [2]: device entry points
+    uint32_t *h_status = nullptr;  // pinned mirror
+
+    ~Replica() {
+        if (device < 0) return;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(device);
+        for (auto &ln : lane) {
+            if (ln.stream) cudaStreamDestroy(ln.stream);
+            ln.in_a.release(); ln.in_b.release(); ln.in_c.release();
+            ln.packed.release(); ln.out_a.release(); ln.out_b.release();
+        }
+        dev_packed.release();
+        if (d_status) cudaFree(d_status);
+        if (h_status) cudaFreeHost(h_status);
+        if (d_blocks) cudaFree(d_blocks);
+        if (d_cbase) cudaFree(d_cbase);
+        cudaSetDevice(cur);
+    }
+};
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+constexpr uint64_t kChunkQueries = 1ull << 21;  // host-path pipeline granularity
+constexpr uint64_t kChunkBytes = 1ull << 27;
+
+}  // namespace
+
+struct msbwt_index {
+    uint64_t total = 0;
+    uint64_t counts[kAlphabet] = {0, 0, 0, 0, 0, 0};
+    uint64_t start[kAlphabet] = {0, 0, 0, 0, 0, 0};
+    uint64_t bytes_per_replica = 0;
+    std::vector<std::unique_ptr<Replica>> reps;
+};
+
+namespace {
+
+int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(MSBWT_ENODEV, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    std::vector<int> devs;
+    if (ndev <= 0 || !devices) {
+        int cur = 0;
+        CU_TRY(cudaGetDevice(&cur));
+        devs.push_back(cur);
+    } else {
+        devs.assign(devices, devices + ndev);
+    }
+    for (int d : devs)
+        if (d < 0 || d >= count) return fail(MSBWT_ENODEV, "device ordinal " + std::to_string(d) + " out of range");
+
+    idx->total = img.total;
+    for (int s = 0; s < kAlphabet; s++) { idx->counts[s] = img.counts[s]; idx->start[s] = img.start[s]; }
+    const size_t block_bytes = img.blocks.size() * sizeof(uint32_t);
+    const size_t cbase_bytes = img.cbase.size() * sizeof(uint64_t);
+    idx->bytes_per_replica = block_bytes + cbase_bytes;
+
+    for (int d : devs) {
+        DeviceGuard guard(d);
+        auto rep = std::make_unique<Replica>();
+        rep->device = d;
+        CU_TRY(cudaMalloc((void **)&rep->d_blocks, block_bytes));
+        CU_TRY(cudaMalloc((void **)&rep->d_cbase, cbase_bytes));
+        CU_TRY(cudaMemcpy(rep->d_blocks, img.blocks.data(), block_bytes, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(rep->d_cbase, img.cbase.data(), cbase_bytes, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMalloc((void **)&rep->d_status, 4 * sizeof(uint32_t)));
+        CU_TRY(cudaMemset(rep->d_status, 0, 4 * sizeof(uint32_t)));
+        CU_TRY(cudaHostAlloc((void **)&rep->h_status, 4 * sizeof(uint32_t), cudaHostAllocDefault));
+        for (auto &ln : rep->lane) CU_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        rep->view.blocks = rep->d_blocks;
+        rep->view.cbase = rep->d_cbase;
+        rep->view.total = img.total;
+        rep->view.nblocks = img.nblocks;
+        rep->view.n_super = img.n_super;
+        rep->view.sb_shift = img.sb_shift;
+        idx->reps.push_back(std::move(rep));
+    }
+    return MSBWT_OK;
+}
+
+msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices, int ndev, uint32_t sb_shift,
+                           int *err) {
+    g_last_error.clear();
+    int rc;
+    std::string why;
+    auto idx = std::make_unique<msbwt_index>();
+    {
+        HostImage img;
+        rc = build_image_from_rle(rle, len, sb_shift, img, why);
+        if (rc == MSBWT_OK) rc = upload(idx.get(), img, devices, ndev);
+        else fail(rc, why);
+    }
+    if (err) *err = rc;
+    if (rc != MSBWT_OK) return nullptr;
+    return idx.release();
+}
+
+// one device's share of a host batch
+struct Slice { uint64_t begin, end; };
+
+Slice slice_for(uint64_t n, size_t d, size_t ndev) { return {n * d / ndev, n * (d + 1) / ndev}; }
+
+int check_status_flags(msbwt_index const *idx, const char *what) {
+    for (auto &rep : idx->reps)
+        if (rep->h_status[0] | rep->h_status[1])
+            return fail(MSBWT_EINVAL, std::string(what) + ": symbol >= 6 or range out of bounds in the batch");
+    return MSBWT_OK;
+}
+
+}  // namespace
+
+// ================================================================ construction
+
+extern "C" msbwt_index *msbwt_index_create_from_rle(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
+                                                   int *err) {
+    return create_common(rle, len, devices, ndev, 0, err);
+}
+
+extern "C" msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
+                                             uint32_t superblock_shift, int *err) {
+    return create_common(rle, len, devices, ndev, superblock_shift, err);
+}
+
+extern "C" msbwt_index *msbwt_index_create_from_npy(const char *path, const int *devices, int ndev, int *err) {
+    g_last_error.clear();
+    std::vector<uint8_t> payload;
+    std::string why;
+    int rc = read_npy_payload(path, payload, why);
+    if (rc != MSBWT_OK) {
+        fail(rc, why);
+        if (err) *err = rc;
+        return nullptr;
+    }
+    return create_common(payload.data(), payload.size(), devices, ndev, 0, err);
+}
+
+extern "C" void msbwt_index_destroy(msbwt_index *idx) { delete idx; }
+
+// ================================================================ accessors
+
+extern "C" uint64_t msbwt_total_size(const msbwt_index *idx) { return idx ? idx->total : 0; }
+extern "C" uint64_t msbwt_symbol_count(const msbwt_index *idx, uint8_t sym) {
+    return (idx && sym < kAlphabet) ? idx->counts[sym] : 0;
+}
+extern "C" uint64_t msbwt_start_index(const msbwt_index *idx, uint8_t sym) {
+    if (!idx) return 0;
+    return sym < kAlphabet ? idx->start[sym] : idx->total;
+}
+extern "C" int msbwt_device_count(const msbwt_index *idx) { return idx ? (int)idx->reps.size() : 0; }
+extern "C" int msbwt_device_ordinal(const msbwt_index *idx, int slot) {
+    return (idx && slot >= 0 && slot < (int)idx->reps.size()) ? idx->reps[slot]->device : -1;
+}
+extern "C" uint64_t msbwt_index_bytes(const msbwt_index *idx) { return idx ? idx->bytes_per_replica : 0; }
+extern "C" uint64_t msbwt_launch_count(void) { return g_launches.load(); }
+extern "C" const char *msbwt_last_error(void) { return g_last_error.c_str(); }
+extern "C" int msbwt_abi_version(void) { return MSBWT_ABI_VERSION; }
+
+extern "C" void *msbwt_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        g_last_error = "cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void msbwt_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ================================================================ device-buffer entry points
+
+extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, const uint8_t *d_syms, uint32_t k,
+                                              uint64_t n, uint64_t *d_out, uint32_t *d_status, void *stream) {
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
+    if (n && (!d_out || (k && !d_syms))) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (!n) return MSBWT_OK;
+    Replica &rep = *idx->reps[slot];
+    std::lock_guard<std::mutex> lock(rep.mu);
+    DeviceGuard guard(rep.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(rep.dev_packed.reserve(n * words_for_k(k) * sizeof(uint64_t)));
+    uint32_t *flag = d_status ? d_status : rep.d_status + 2;
+    CU_TRY(cudaMemsetAsync(flag, 0, sizeof(uint32_t), st));
+    if (k) {
+        CU_TRY(launch_pack_fixed(d_syms, k, n, rep.dev_packed.as<uint64_t>(), flag, st));
+        g_launches++;
+    }
+    CU_TRY(launch_count_packed(rep.device, rep.view, rep.dev_packed.as<uint64_t>(), k, n, d_out, st));
+    g_launches++;
+    return MSBWT_OK;
+}
+
+extern "C" uint32_t msbwt_packed_words(uint32_t k) { return words_for_k(k); }
+
+extern "C" int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const uint8_t *d_syms, uint32_t k, uint64_t n,
+                                       uint64_t *d_packed, uint32_t *d_status, void *stream) {
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
+    if (n && k && (!d_syms || !d_packed || !d_status)) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (!n || !k) return MSBWT_OK;
+    Replica &rep = *idx->reps[slot];
+    DeviceGuard guard(rep.device);
+    CU_TRY(launch_pack_fixed(d_syms, k, n, d_packed, d_status, (cudaStream_t)stream));
+    g_launches++;
+    return MSBWT_OK;
+}
+
+extern "C" int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot, const uint64_t *d_packed, uint32_t k,
+                                               uint64_t n, uint64_t *d_out, void *stream) {
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
+    if (n && (!d_out || (k && !d_packed))) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (!n) return MSBWT_OK;
+    Replica &rep = *idx->reps[slot];
+    DeviceGuard guard(rep.device);
+    CU_TRY(launch_count_packed(rep.device, rep.view, d_packed, k, n, d_out, (cudaStream_t)stream));
+    g_launches++;
+    return MSBWT_OK;
+}
+
+extern "C" int msbwt_constrain_ranges_device(const msbwt_index *idx, int slot, const uint8_t *d_sym,
+                                             const uint64_t *d_l, const uint64_t *d_h, uint64_t n,
+                                             uint64_t *d_out_l, uint64_t *d_out_h, void *stream) {
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
+    if (n && (!d_sym || !d_l || !d_h || !d_out_l || !d_out_h)) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (!n) return MSBWT_OK;
+    Replica &rep = *idx->reps[slot];
+    DeviceGuard guard(rep.device);
+    CU_TRY(launch_constrain_ranges(rep.device, rep.view, d_sym, d_l, d_h, n, d_out_l, d_out_h, (cudaStream_t)stream));
+    g_launches++;
+    return MSBWT_OK;
+}
+
+// ================================================================ host-buffer entry points
+
+extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n,
+                                       uint64_t *out) {
+    g_last_error.clear();
+    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
+    if (n && (!out || (k && !syms))) return fail(MSBWT_EINVAL, "NULL host buffer");
+    if (!n) return MSBWT_OK;
+    const size_t ndev = idx->reps.size();
+    const uint32_t words = words_for_k(k);
+    uint64_t chunk = kChunkQueries;
+    if (k && chunk * k > kChunkBytes) chunk = std::max<uint64_t>(1, kChunkBytes / k);
+
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
+
+    uint64_t max_chunks = 0;
+    for (size_t d = 0; d < ndev; d++) {
+        Replica &rep = *idx->reps[d];
+        DeviceGuard guard(rep.device);
+        const Slice sl = slice_for(n, d, ndev);
+        const uint64_t len = sl.end - sl.begin;
+        const uint64_t c = std::min(chunk, len);
+        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
+        for (auto &ln : rep.lane) {
+            CU_TRY(ln.in_a.reserve(std::max<uint64_t>(1, c * k)));
+            CU_TRY(ln.packed.reserve(std::max<uint64_t>(1, c * words * sizeof(uint64_t))));
+            CU_TRY(ln.out_a.reserve(std::max<uint64_t>(1, c * sizeof(uint64_t))));
+        }
+        CU_TRY(cudaMemsetAsync(rep.d_status, 0, 2 * sizeof(uint32_t), rep.lane[0].stream));
+        CU_TRY(cudaStreamSynchronize(rep.lane[0].stream));
+    }
+    // chunks are issued round-robin over devices so every GPU always has work queued
+    for (uint64_t c = 0; c < max_chunks; c++) {
+        for (size_t d = 0; d < ndev; d++) {
+            Replica &rep = *idx->reps[d];
+            const Slice sl = slice_for(n, d, ndev);
+            const uint64_t b = sl.begin + c * chunk;
+            if (b >= sl.end) continue;
+            const uint64_t m = std::min(chunk, sl.end - b);
+            DeviceGuard guard(rep.device);
+            Lane &ln = rep.lane[c & 1];
+            if (k) {
+                CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + b * k, m * k, cudaMemcpyHostToDevice, ln.stream));
+                CU_TRY(launch_pack_fixed(ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(),
+                                         rep.d_status + (c & 1), ln.stream));
+                g_launches++;
+            }
+            CU_TRY(launch_count_packed(rep.device, rep.view, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
+                                       ln.stream));
+            g_launches++;
+            CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+        }
+    }
+    for (auto &rep : idx->reps) {
+        DeviceGuard guard(rep->device);
+        CU_TRY(cudaStreamSynchronize(rep->lane[0].stream));
+        CU_TRY(cudaStreamSynchronize(rep->lane[1].stream));
+        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    return check_status_flags(idx, "count_kmers_fixed");
+}
+
+extern "C" int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, const uint64_t *offsets, uint64_t n,
+                                 uint64_t *out) {
+    g_last_error.clear();
+    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
+    if (!n) return MSBWT_OK;
+    if (!out || !offsets) return fail(MSBWT_EINVAL, "NULL host buffer");
+    for (uint64_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(MSBWT_EINVAL, "offsets must be non-decreasing");
+    if (offsets[n] > offsets[0] && !syms) return fail(MSBWT_EINVAL, "NULL host buffer");
+    const size_t ndev = idx->reps.size();
+
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
+    for (auto &rep : idx->reps) {
+        DeviceGuard guard(rep->device);
+        CU_TRY(cudaMemsetAsync(rep->d_status, 0, 2 * sizeof(uint32_t), rep->lane[0].stream));
+        CU_TRY(cudaStreamSynchronize(rep->lane[0].stream));
+    }
+    // per device: walk its slice in chunks bounded in both queries and symbol bytes
+    std::vector<uint64_t> cursor(ndev);
+    std::vector<uint64_t> round(ndev, 0);
+    for (size_t d = 0; d < ndev; d++) cursor[d] = slice_for(n, d, ndev).begin;
+    for (bool any = true; any;) {
+        any = false;
+        for (size_t d = 0; d < ndev; d++) {
+            const Slice sl = slice_for(n, d, ndev);
+            uint64_t b = cursor[d];
+            if (b >= sl.end) continue;
+            any = true;
+            uint64_t e = std::min(sl.end, b + kChunkQueries);
+            if (offsets[e] - offsets[b] > kChunkBytes) {
+                // largest e with offsets[e]-offsets[b] <= kChunkBytes, at least one query
+                const uint64_t *hi = std::upper_bound(offsets + b, offsets + e + 1, offsets[b] + kChunkBytes);
+                e = std::max<uint64_t>(b + 1, (uint64_t)(hi - offsets) - 1);
+            }
+            const uint64_t m = e - b, nbytes = offsets[e] - offsets[b];
+            Replica &rep = *idx->reps[d];
+            DeviceGuard guard(rep.device);
+            Lane &ln = rep.lane[round[d] & 1];
+            CU_TRY(cudaStreamSynchronize(ln.stream));  // buffers may be regrown below
+            CU_TRY(ln.in_a.reserve(std::max<uint64_t>(1, nbytes)));
+            CU_TRY(ln.in_b.reserve((m + 1) * sizeof(uint64_t)));
+            CU_TRY(ln.out_a.reserve(m * sizeof(uint64_t)));
+            if (nbytes) CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + offsets[b], nbytes, cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(cudaMemcpyAsync(ln.in_b.p, offsets + b, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
+            // the kernel indexes syms with absolute offsets: bias the base pointer instead of rewriting them
+            const uint8_t *biased = ln.in_a.as<uint8_t>() - offsets[b];
+            CU_TRY(launch_count_bytes(rep.device, rep.view, biased, ln.in_b.as<uint64_t>(), m, ln.out_a.as<uint64_t>(),
+                                      rep.d_status + (round[d] & 1), ln.stream));
+            g_launches++;
+            CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+            cursor[d] = e;
+            round[d]++;
+        }
+    }
+    for (auto &rep : idx->reps) {
+        DeviceGuard guard(rep->device);
+        CU_TRY(cudaStreamSynchronize(rep->lane[0].stream));
+        CU_TRY(cudaStreamSynchronize(rep->lane[1].stream));
+        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    return check_status_flags(idx, "count_kmers");
+}
+
+extern "C" int msbwt_constrain_ranges(const msbwt_index *idx, const uint8_t *sym, const uint64_t *l,
+                                      const uint64_t *h, uint64_t n, uint64_t *out_l, uint64_t *out_h) {
+    g_last_error.clear();
+    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
+    if (!n) return MSBWT_OK;
+    if (!sym || !l || !h || !out_l || !out_h) return fail(MSBWT_EINVAL, "NULL host buffer");
+    const size_t ndev = idx->reps.size();
+    const uint64_t chunk = kChunkQueries;
+
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
+
+    // validation first (the reference's constrain_range is unchecked; we refuse bad input
+    // before any output is written)
+    for (uint64_t i = 0; i < n; i++)
+        if (sym[i] >= kAlphabet || l[i] > h[i] || h[i] > idx->total)
+            return fail(MSBWT_EINVAL, "constrain_ranges: item " + std::to_string(i) + " has sym >= 6, l > h or h > total_size");
+
+    uint64_t max_chunks = 0;
+    for (size_t d = 0; d < ndev; d++) {
+        Replica &rep = *idx->reps[d];
+        DeviceGuard guard(rep.device);
+        const Slice sl = slice_for(n, d, ndev);
+        const uint64_t len = sl.end - sl.begin, c = std::max<uint64_t>(1, std::min(chunk, len));
+        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
+        for (auto &ln : rep.lane) {
+            CU_TRY(cudaStreamSynchronize(ln.stream));
+            CU_TRY(ln.in_a.reserve(c));
+            CU_TRY(ln.in_b.reserve(c * sizeof(uint64_t)));
+            CU_TRY(ln.in_c.reserve(c * sizeof(uint64_t)));
+            CU_TRY(ln.out_a.reserve(c * sizeof(uint64_t)));
+            CU_TRY(ln.out_b.reserve(c * sizeof(uint64_t)));
+        }
+    }
+    for (uint64_t c = 0; c < max_chunks; c++) {
+        for (size_t d = 0; d < ndev; d++) {
+            Replica &rep = *idx->reps[d];
+            const Slice sl = slice_for(n, d, ndev);
+            const uint64_t b = sl.begin + c * chunk;
+            if (b >= sl.end) continue;
+            const uint64_t m = std::min(chunk, sl.end - b);
+            DeviceGuard guard(rep.device);
+            Lane &ln = rep.lane[c & 1];
+            CU_TRY(cudaMemcpyAsync(ln.in_a.p, sym + b, m, cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(cudaMemcpyAsync(ln.in_b.p, l + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(cudaMemcpyAsync(ln.in_c.p, h + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(launch_constrain_ranges(rep.device, rep.view, ln.in_a.as<uint8_t>(), ln.in_b.as<uint64_t>(),
+                                           ln.in_c.as<uint64_t>(), m, ln.out_a.as<uint64_t>(), ln.out_b.as<uint64_t>(),
+                                           ln.stream));
+            g_launches++;
+            CU_TRY(cudaMemcpyAsync(out_l + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+            CU_TRY(cudaMemcpyAsync(out_h + b, ln.out_b.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+        }
+    }
+    for (auto &rep : idx->reps) {
+        DeviceGuard guard(rep->device);
+        CU_TRY(cudaStreamSynchronize(rep->lane[0].stream));
+        CU_TRY(cudaStreamSynchronize(rep->lane[1].stream));
+    }
+    return MSBWT_OK;
+}
+
+// ================================================================ inspection
+
+extern "C" int msbwt_debug_build_image(const uint8_t *rle, uint64_t len, uint32_t superblock_shift, uint64_t *nblocks,
+                                       uint32_t *n_super, uint32_t *blocks, uint64_t *cbase) {
+    g_last_error.clear();
+    if (!nblocks || !n_super) return fail(MSBWT_EINVAL, "NULL size outputs");
+    HostImage img;
+    std::string why;
+    int rc = build_image_from_rle(rle, len, superblock_shift, img, why);
+    if (rc != MSBWT_OK) return fail(rc, why);
+    *nblocks = img.nblocks;
+    *n_super = img.n_super;
+    if (blocks) memcpy(blocks, img.blocks.data(), img.blocks.size() * sizeof(uint32_t));
+    if (cbase) memcpy(cbase, img.cbase.data(), img.cbase.size() * sizeof(uint64_t));
+    return MSBWT_OK;
+}
+
+// ================================================================ measurement aid
+
+extern "C" int msbwt_gather_bench(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,
+                                  uint64_t n_gathers, uint64_t seed, uint64_t *d_sink, void *stream) {
+    if (!d_buf || !d_sink) return fail(MSBWT_EINVAL, "NULL device buffer");
+    DeviceGuard guard(device);
+    CU_TRY(launch_gather(device, d_buf, buf_bytes, granule, n_gathers, seed, d_sink, (cudaStream_t)stream));
+    g_launches++;
+    return MSBWT_OK;
+}

@@ -1,0 +1,48 @@
+// engine.h -- internal interface between the C ABI (capi.cu), the host-side layout
+// builder (loader.cu) and the kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "layout.h"
+
+namespace msbwt {
+
+constexpr int kCountThreads = 256;
+
+inline uint32_t words_for_k(uint32_t k) { return k ? (k + kSymsPerWord - 1) / kSymsPerWord : 1; }
+
+// ---- loader.cu: RLE byte stream / .npy -> host block image ----
+struct HostImage {
+    std::vector<uint32_t> blocks;  // nblocks * 32 words
+    std::vector<uint64_t> cbase;   // n_super * 8
+    uint64_t counts[kAlphabet] = {0, 0, 0, 0, 0, 0};
+    uint64_t start[kAlphabet] = {0, 0, 0, 0, 0, 0};
+    uint64_t total = 0;
+    uint64_t nblocks = 0;
+    uint32_t n_super = 0;
+    uint32_t sb_shift = kDefaultSuperShift;
+};
+
+// return an msbwt_status; on failure `why` explains
+int build_image_from_rle(const uint8_t *rle, uint64_t len, uint32_t sb_shift, HostImage &img, std::string &why);
+int read_npy_payload(const char *path, std::vector<uint8_t> &payload, std::string &why);
+
+// ---- kernels.cu ----
+cudaError_t launch_pack_fixed(const uint8_t *d_syms, uint32_t k, uint64_t n, uint64_t *d_packed,
+                              uint32_t *d_status, cudaStream_t st);
+cudaError_t launch_count_packed(int device, const IndexView &ix, const uint64_t *d_packed, uint32_t k,
+                                uint64_t n, uint64_t *d_out, cudaStream_t st);
+cudaError_t launch_count_bytes(int device, const IndexView &ix, const uint8_t *d_syms,
+                               const uint64_t *d_offsets, uint64_t n, uint64_t *d_out, uint32_t *d_status,
+                               cudaStream_t st);
+cudaError_t launch_constrain_ranges(int device, const IndexView &ix, const uint8_t *d_sym, const uint64_t *d_l,
+                                    const uint64_t *d_h, uint64_t n, uint64_t *d_out_l, uint64_t *d_out_h,
+                                    cudaStream_t st);
+cudaError_t launch_gather(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,
+                          uint64_t n_gathers, uint64_t seed, uint64_t *d_sink, cudaStream_t st);
+
+}  // namespace msbwt

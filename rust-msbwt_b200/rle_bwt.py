@@ -1,0 +1,332 @@
+"""Host-side mirror of the reference's `RleBWT` (src/rle_bwt.rs:14-322) and `BWT` trait
+(src/msbwt_core.rs:28-162) over the C ABI in include/msbwt_gpu.h.
+
+Same method names, argument meaning and error behaviour as the reference:
+
+    RleBWT.new() / RleBWT.with_bin_power(p)    src/rle_bwt.rs:297-322
+    load_vector(rle_bytes)                     src/rle_bwt.rs:59-66
+    load_numpy_file(path)                      src/rle_bwt.rs:81-155  (OSError where the reference
+                                               returns io::Error, MsbwtError where it panics)
+    get_symbol_count(sym) / get_total_size()   src/rle_bwt.rs:172-193
+    constrain_range(sym, BWTRange)             src/rle_bwt.rs:202-287
+    count_kmer(kmer)                           src/msbwt_core.rs:125-161 (symbol >= 6 raises, as the
+                                               reference's assert panics)
+    count_kmers(kmers)                         the batched entry point BASELINE.json adds
+
+Every query goes to the CUDA library; there is no CPU path here.  If the library or a
+CUDA device is missing the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmsbwt_b200.so")
+
+OK, EINVAL, EIO, EFORMAT, ECUDA, ENOMEM, ENODEV = range(7)
+_NAMES = {EINVAL: "EINVAL", EIO: "EIO", EFORMAT: "EFORMAT", ECUDA: "ECUDA", ENOMEM: "ENOMEM", ENODEV: "ENODEV"}
+
+# string_util.rs:3-32 / 6-9 / 12
+_STOI = np.full(256, 4, dtype=np.uint8)
+for _c, _v in (("$", 0), ("A", 1), ("C", 2), ("G", 3), ("N", 4), ("T", 5), ("a", 1), ("c", 2), ("g", 3), ("n", 4), ("t", 5)):
+    _STOI[ord(_c)] = _v
+_ITOS = np.frombuffer(b"$ACGNT", dtype=np.uint8)
+_COMPLEMENT = np.array([0, 5, 3, 2, 4, 1], dtype=np.uint8)
+
+
+def convert_stoi(seq: str | bytes) -> np.ndarray:
+    """string_util.rs:63-67"""
+    raw = seq.encode() if isinstance(seq, str) else bytes(seq)
+    return _STOI[np.frombuffer(raw, dtype=np.uint8)]
+
+
+def convert_itos(iseq) -> str:
+    """string_util.rs:80-88"""
+    return _ITOS[np.asarray(iseq, dtype=np.uint8)].tobytes().decode()
+
+
+def reverse_complement_i(seq) -> np.ndarray:
+    """string_util.rs:45-50"""
+    return _COMPLEMENT[np.asarray(seq, dtype=np.uint8)[::-1]]
+
+
+class MsbwtError(RuntimeError):
+    """A failure the reference would have panicked on (or a CUDA failure)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+@dataclass(frozen=True)
+class BWTRange:
+    """msbwt_core.rs:18-24: half-open [l, h)."""
+    l: int = 0
+    h: int = 0
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen libmsbwt_b200.so (built in-tree by build.py).  Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise MsbwtError(ENODEV, f"{_LIB_PATH} is missing: run `python rust-msbwt_b200/build.py` "
+                                 "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(_LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    ip = C.POINTER(C.c_int)
+    sig = {
+        "msbwt_index_create_from_rle": (vp, [vp, u64, ip, i32, ip]),
+        "msbwt_index_create_from_npy": (vp, [C.c_char_p, ip, i32, ip]),
+        "msbwt_index_create_ex": (vp, [vp, u64, ip, i32, u32, ip]),
+        "msbwt_index_destroy": (None, [vp]),
+        "msbwt_total_size": (u64, [vp]),
+        "msbwt_symbol_count": (u64, [vp, C.c_uint8]),
+        "msbwt_start_index": (u64, [vp, C.c_uint8]),
+        "msbwt_device_count": (i32, [vp]),
+        "msbwt_device_ordinal": (i32, [vp, i32]),
+        "msbwt_index_bytes": (u64, [vp]),
+        "msbwt_count_kmers": (i32, [vp, vp, vp, u64, vp]),
+        "msbwt_count_kmers_fixed": (i32, [vp, vp, u32, u64, vp]),
+        "msbwt_constrain_ranges": (i32, [vp, vp, vp, vp, u64, vp, vp]),
+        "msbwt_count_kmers_fixed_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
+        "msbwt_constrain_ranges_device": (i32, [vp, i32, vp, vp, vp, u64, vp, vp, vp]),
+        "msbwt_packed_words": (u32, [u32]),
+        "msbwt_pack_kmers_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
+        "msbwt_count_kmers_packed_device": (i32, [vp, i32, vp, u32, u64, vp, vp]),
+        "msbwt_launch_count": (u64, []),
+        "msbwt_gather_bench": (i32, [i32, vp, u64, u32, u64, u64, vp, vp]),
+        "msbwt_debug_build_image": (i32, [vp, u64, u32, C.POINTER(u64), C.POINTER(u32), vp, vp]),
+        "msbwt_host_alloc": (vp, [C.c_size_t]),
+        "msbwt_host_free": (None, [vp]),
+        "msbwt_last_error": (C.c_char_p, []),
+        "msbwt_abi_version": (i32, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex",
+    "msbwt_index_destroy", "msbwt_total_size", "msbwt_symbol_count", "msbwt_start_index",
+    "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_count_kmers",
+    "msbwt_count_kmers_fixed", "msbwt_constrain_ranges", "msbwt_count_kmers_fixed_device",
+    "msbwt_constrain_ranges_device", "msbwt_packed_words", "msbwt_pack_kmers_device",
+    "msbwt_count_kmers_packed_device", "msbwt_launch_count", "msbwt_gather_bench", "msbwt_debug_build_image",
+    "msbwt_host_alloc",
+    "msbwt_host_free", "msbwt_last_error", "msbwt_abi_version",
+)
+
+
+def _check(rc: int, what: str) -> None:
+    if rc == OK:
+        return
+    msg = (load_library().msbwt_last_error() or b"").decode(errors="replace")
+    if rc == EIO:
+        raise OSError(f"{what}: {msg}")  # the reference returns Err(io::Error) here
+    raise MsbwtError(rc, f"{what}: {msg}")
+
+
+def _u8(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint8))
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+def _p(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+class RleBWT:
+    """GPU-resident `RleBWT`.  `devices`: CUDA ordinals to replicate the index on
+    (None = the current device); batches are split across them (no collective)."""
+
+    def __init__(self, bin_power: int = 8, devices: list[int] | None = None, superblock_shift: int = 0):
+        # bin_power is accepted for signature parity (src/rle_bwt.rs:309-322); it never
+        # changed results in the reference and has no counterpart in the device layout.
+        self.bin_power = bin_power
+        self._devices = list(devices) if devices else []
+        self._sb_shift = superblock_shift
+        self._h = None
+
+    @classmethod
+    def new(cls, **kw) -> "RleBWT":
+        return cls(8, **kw)
+
+    @classmethod
+    def with_bin_power(cls, bin_power: int, **kw) -> "RleBWT":
+        return cls(bin_power, **kw)
+
+    # -- lifetime
+    def close(self) -> None:
+        h, self._h = self._h, None
+        if h and _lib is not None:
+            _lib.msbwt_index_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev_args(self):
+        if not self._devices:
+            return None, 0
+        arr = (C.c_int * len(self._devices))(*self._devices)
+        return arr, len(self._devices)
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise MsbwtError(EINVAL, "no BWT loaded")
+        return self._h
+
+    # -- BWT trait
+    def load_vector(self, bwt) -> None:
+        L = load_library()
+        self.close()
+        a = _u8(bwt)
+        err = C.c_int(0)
+        devs, nd = self._dev_args()
+        h = L.msbwt_index_create_ex(_p(a), a.size, devs, nd, self._sb_shift, C.byref(err))
+        if not h:
+            _check(err.value or ECUDA, "load_vector")
+        self._h = h
+
+    def load_numpy_file(self, filename: str) -> None:
+        L = load_library()
+        self.close()
+        err = C.c_int(0)
+        devs, nd = self._dev_args()
+        h = L.msbwt_index_create_from_npy(os.fsencode(filename), devs, nd, C.byref(err))
+        if not h:
+            _check(err.value or ECUDA, "load_numpy_file")
+        self._h = h
+
+    def get_symbol_count(self, symbol: int) -> int:
+        return int(load_library().msbwt_symbol_count(self.handle, symbol))
+
+    def get_total_size(self) -> int:
+        return int(load_library().msbwt_total_size(self.handle))
+
+    def start_index(self, symbol: int) -> int:
+        return int(load_library().msbwt_start_index(self.handle, symbol))
+
+    def constrain_range(self, sym: int, input_range: BWTRange) -> BWTRange:
+        lo, hi = self.constrain_ranges([sym], [input_range.l], [input_range.h])
+        return BWTRange(int(lo[0]), int(hi[0]))
+
+    def count_kmer(self, kmer) -> int:
+        a = _u8(kmer).reshape(-1)
+        if a.size == 0:  # empty k-mer counts total_size (msbwt_core.rs:128-131,160)
+            return int(self.count_kmers([a])[0])
+        return int(self.count_kmers_fixed(a, a.size)[0])
+
+    # -- batched entry points
+    def count_kmers(self, kmers) -> np.ndarray:
+        """`count_kmers(&[Vec<u8>]) -> Vec<u64>`: variable-length batch."""
+        n = len(kmers)
+        lens = np.fromiter((len(q) for q in kmers), dtype=np.uint64, count=n)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(lens, out=offs[1:])
+        flat = _u8(np.concatenate([_u8(q).reshape(-1) for q in kmers])) if n and offs[-1] else np.zeros(1, np.uint8)
+        out = np.zeros(n, dtype=np.uint64)
+        _check(load_library().msbwt_count_kmers(self.handle, _p(flat), _p(offs), n, _p(out)), "count_kmers")
+        return out
+
+    def count_kmers_fixed(self, syms, k: int) -> np.ndarray:
+        """Fixed-k batch: `syms` is n*k symbols, row-major."""
+        a = _u8(syms).reshape(-1)
+        if k == 0:
+            raise MsbwtError(EINVAL, "count_kmers_fixed needs k > 0 (use count_kmers for empty k-mers)")
+        if a.size % k:
+            raise MsbwtError(EINVAL, "len(syms) is not a multiple of k")
+        n = a.size // k
+        out = np.zeros(n, dtype=np.uint64)
+        _check(load_library().msbwt_count_kmers_fixed(self.handle, _p(a), k, n, _p(out)), "count_kmers_fixed")
+        return out
+
+    def constrain_ranges(self, sym, l, h) -> tuple[np.ndarray, np.ndarray]:
+        s, lo, hi = _u8(sym).reshape(-1), _u64(l).reshape(-1), _u64(h).reshape(-1)
+        if not (s.size == lo.size == hi.size):
+            raise MsbwtError(EINVAL, "sym/l/h length mismatch")
+        out_l = np.zeros(s.size, dtype=np.uint64)
+        out_h = np.zeros(s.size, dtype=np.uint64)
+        _check(load_library().msbwt_constrain_ranges(self.handle, _p(s), _p(lo), _p(hi), s.size, _p(out_l), _p(out_h)),
+               "constrain_range")
+        return out_l, out_h
+
+    # -- device-buffer entry points (raw pointers: torch `.data_ptr()` / stream handles)
+    def count_kmers_fixed_device(self, d_syms: int, k: int, n: int, d_out: int, d_status: int = 0,
+                                 stream: int = 0, slot: int = 0) -> None:
+        _check(load_library().msbwt_count_kmers_fixed_device(self.handle, slot, d_syms, k, n, d_out, d_status or None,
+                                                             stream or None), "count_kmers_fixed_device")
+
+    def pack_kmers_device(self, d_syms: int, k: int, n: int, d_packed: int, d_status: int, stream: int = 0,
+                          slot: int = 0) -> None:
+        _check(load_library().msbwt_pack_kmers_device(self.handle, slot, d_syms, k, n, d_packed, d_status,
+                                                      stream or None), "pack_kmers_device")
+
+    def count_kmers_packed_device(self, d_packed: int, k: int, n: int, d_out: int, stream: int = 0,
+                                  slot: int = 0) -> None:
+        _check(load_library().msbwt_count_kmers_packed_device(self.handle, slot, d_packed, k, n, d_out,
+                                                              stream or None), "count_kmers_packed_device")
+
+    def constrain_ranges_device(self, d_sym: int, d_l: int, d_h: int, n: int, d_out_l: int, d_out_h: int,
+                                stream: int = 0, slot: int = 0) -> None:
+        _check(load_library().msbwt_constrain_ranges_device(self.handle, slot, d_sym, d_l, d_h, n, d_out_l, d_out_h,
+                                                            stream or None), "constrain_ranges_device")
+
+    @property
+    def index_bytes(self) -> int:
+        return int(load_library().msbwt_index_bytes(self.handle))
+
+    @property
+    def device_ordinals(self) -> list[int]:
+        L = load_library()
+        return [L.msbwt_device_ordinal(self.handle, i) for i in range(L.msbwt_device_count(self.handle))]
+
+
+def debug_build_image(rle, superblock_shift: int = 0) -> tuple[np.ndarray, np.ndarray]:
+    """Host-side block image (layout.h) of an RLE stream: (blocks[nblocks,32] u32, cbase[n_super,8] u64).
+    Inspection only; needs no device."""
+    L = load_library()
+    a = _u8(rle)
+    nb, ns = C.c_uint64(0), C.c_uint32(0)
+    _check(L.msbwt_debug_build_image(_p(a), a.size, superblock_shift, C.byref(nb), C.byref(ns), None, None), "image")
+    blocks = np.zeros((nb.value, 32), dtype=np.uint32)
+    cbase = np.zeros((ns.value, 8), dtype=np.uint64)
+    _check(L.msbwt_debug_build_image(_p(a), a.size, superblock_shift, C.byref(nb), C.byref(ns), _p(blocks), _p(cbase)),
+           "image")
+    return blocks, cbase
+
+
+def packed_words(k: int) -> int:
+    return int(load_library().msbwt_packed_words(k))
+
+
+def launch_count() -> int:
+    return int(load_library().msbwt_launch_count())
+
+
+def gather_bench(device: int, d_buf: int, buf_bytes: int, granule: int, n_gathers: int, seed: int, d_sink: int,
+                 stream: int = 0) -> None:
+    _check(load_library().msbwt_gather_bench(device, d_buf, buf_bytes, granule, n_gathers, seed, d_sink,
+                                             stream or None), "gather_bench")

@@ -1,0 +1,163 @@
+"""CPU checks of the product's host logic: the C ABI library loads and exports every
+symbol include/msbwt_gpu.h declares, the loader's block image (layout.h) encodes exact
+ranks (checked against the oracle through a numpy reading of the documented layout),
+the .npy reader accepts/rejects what the reference does, and without a GPU every
+query-capable constructor fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rust_msbwt_b200 as M
+from oracle import naive
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "msbwt_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(msbwt_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(M.library_path())
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/msbwt_gpu.h but not exported"
+    assert declared == set(M.EXPORTED_SYMBOLS)
+    assert M.load_library().msbwt_abi_version() == 1
+
+
+def image_rank(blocks, cbase, sb_shift, sym, pos):
+    """rank+C read off the block image exactly as layout.h documents it"""
+    blk, p = pos >> 8, pos & 255
+    w = blocks[blk]
+    cnt = 0
+    for j in range(8):
+        m = 0xFFFFFFFF
+        for b in range(3):
+            plane = int(w[j * 4 + 1 + b])
+            m &= plane if (sym >> b) & 1 else (~plane & 0xFFFFFFFF)
+        nb = min(max(p - 32 * j, 0), 32)
+        cnt += bin(m & ((1 << nb) - 1)).count("1")
+    return int(cbase[blk >> sb_shift][sym]) + int(w[sym * 4]) + cnt
+
+
+def random_rle(rng, nruns, big=False):
+    syms, counts, prev = [], [], -1
+    for _ in range(nruns):
+        s = int(rng.choice(6, p=[0.05, 0.27, 0.25, 0.25, 0.03, 0.15]))
+        if s == prev:
+            continue
+        prev = s
+        syms.append(s)
+        counts.append(int(rng.choice([1, 1, 2, 3, 7, 31, 32, 33, 255, 256, 257, 1025] if big else [1, 1, 1, 2, 3, 5, 9, 40])))
+    return O.encode_runs(syms, counts)
+
+
+@pytest.mark.parametrize("sb_shift", [0, 1, 3])
+@pytest.mark.parametrize("big", [False, True])
+def test_block_image_ranks_match_oracle(sb_shift, big):
+    rng = np.random.default_rng(99 + sb_shift + 10 * big)
+    rle = random_rle(rng, 900, big)
+    blocks, cbase = M.debug_build_image(rle, sb_shift)
+    orc = O.RleBWT()
+    orc.load_vector(rle)
+    n = orc.get_total_size()
+    shift = sb_shift or 24
+    assert blocks.shape[0] == (n >> 8) + 1
+    assert cbase.shape[0] == ((blocks.shape[0] - 1) >> shift) + 1
+    assert (blocks[:, 24] == 0).all() and (blocks[:, 28] == 0).all()
+    pos = sorted(set(rng.integers(0, n + 1, size=400).tolist() + [0, n, n - 1, 256, 255, 257]))
+    for s in range(6):
+        for a, b in zip(pos[:-1], pos[1:]):
+            want = orc.constrain_range(s, a, b)
+            assert (image_rank(blocks, cbase, shift, s, a), image_rank(blocks, cbase, shift, s, b)) == want
+
+
+def test_block_image_exact_multiple_of_256_and_empty():
+    rle = O.encode_runs([1, 2], [256, 256])
+    blocks, cbase = M.debug_build_image(rle)
+    assert blocks.shape == (3, 32)  # position N itself has a block
+    assert image_rank(blocks, cbase, 24, 2, 512) == 256 + 256
+    assert image_rank(blocks, cbase, 24, 1, 512) == 256
+    blocks, cbase = M.debug_build_image(np.zeros(0, np.uint8))
+    assert blocks.shape == (1, 32) and image_rank(blocks, cbase, 24, 3, 0) == 0
+
+
+def test_bad_rle_symbol_is_eformat():
+    with pytest.raises(M.MsbwtError) as e:
+        M.debug_build_image(np.array([9, 14], dtype=np.uint8))  # 14 = symbol 6
+    assert e.value.code == 3
+
+
+def test_string_util_mirror():
+    assert list(M.convert_stoi("ACGTN$acgtnx")) == [1, 2, 3, 5, 4, 0, 1, 2, 3, 5, 4, 4]
+    assert M.convert_itos([0, 1, 2, 3, 4, 5]) == "$ACGNT"
+    assert list(M.reverse_complement_i([0, 1, 2, 3, 4, 5])) == [1, 4, 2, 3, 5, 0]
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_a_device(two_string_npy):
+    b = M.RleBWT()
+    with pytest.raises(M.MsbwtError) as e:
+        b.load_vector(O.convert_to_vec(naive.naive_bwt(["ACGT", "TGCA"])))
+    assert e.value.code == 6  # ENODEV
+    with pytest.raises(M.MsbwtError) as e:
+        b.load_numpy_file(two_string_npy)
+    assert e.value.code == 6
+    with pytest.raises(M.MsbwtError):
+        b.count_kmer([1, 2])
+
+
+def test_npy_reader_error_classes_match_oracle(tmp_path, two_string_npy):
+    """Same acceptance classes as the reference's load_numpy_file (src/rle_bwt.rs:81-155):
+    io::Error -> OSError, panic -> MsbwtError(EFORMAT).  Checked through create_from_npy;
+    without a GPU a well-formed file gets as far as ENODEV."""
+    good = tmp_path / "good.npy"
+    O.save_bwt_numpy([9, 10], str(good))
+    raw = good.read_bytes()
+    cases = {
+        "missing.npy": None,
+        "short.npy": b"\x93NUMPY",
+        "trunc_hdr.npy": raw[:50],
+        "trunc_body.npy": raw[:-1],
+        "long_body.npy": raw + b"\x09",
+        "bad_json.npy": raw[:10] + b"[" + raw[11:],
+        "true.npy": raw.replace(b"False", b"True "),
+        "noshape.npy": raw.replace(b"'shape'", b"'shapx'"),
+        "nomagic.npy": b"XXXXXX" + raw[6:],
+        "badsym.npy": raw[:-1] + b"\x0e",
+    }
+    np.save(str(tmp_path / "np.npy"), np.array([9, 10, 11], dtype=np.uint8))
+    cases["np.npy"] = (tmp_path / "np.npy").read_bytes()
+    for name, data in cases.items():
+        p = tmp_path / name
+        if data is not None:
+            p.write_bytes(data)
+        orc = O.RleBWT()
+        try:
+            orc.load_numpy_file(str(p))
+            want = "ok"
+        except O.OracleIoError:
+            want = "io"
+        except O.OraclePanic:
+            want = "panic"
+        b = M.RleBWT()
+        try:
+            b.load_numpy_file(str(p))
+            got = "ok"
+        except OSError:
+            got = "io"
+        except M.MsbwtError as e:
+            got = {3: "panic", 6: "ok"}.get(e.code, f"code{e.code}")  # ENODEV == parsed fine, no device here
+        assert got == want, name

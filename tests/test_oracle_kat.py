@@ -284,3 +284,12 @@ def test_threads_split_matches_single():
     assert (v == a[:100]).all()
     steps, two = b.count_kmers_stats(qs, 6, 8)
     assert 0 < steps <= 5000 * 6 and 0 <= two <= steps
+
+
+def test_golden_fixture_matches_oracle(golden_dir):
+    z = np.load(f"{golden_dir}/reads30x_k31.npz")
+    b = O.RleBWT()
+    b.load_vector(z["rle"])
+    assert b.get_total_size() == int(z["total"])
+    assert (b.count_kmers_fixed(z["queries"], int(z["k"])) == z["counts"]).all()
+    assert (b.count_kmers_fixed(z["queries_k12"], 12) == z["counts_k12"]).all()
