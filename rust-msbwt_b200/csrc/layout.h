@@ -1,4 +1,4 @@
-// layout.h -- the device-resident block image of the BWT ("layout A").
+// layout.h -- the device-resident block image of the BWT.
 //
 // The reference keeps the RLE byte stream plus a sampled struct-of-arrays index
 // (`ref_index[]`, `fm_index[6][]`, one sample per 256 symbols: src/rle_bwt.rs:14-24,
@@ -6,44 +6,51 @@
 // constrain_range is exactly [C[s]+rank(s,l), C[s]+rank(s,h)) (SURVEY.md facts
 // table), so any exact rank structure is bit-exact.  Ours:
 //
-//   one 128-byte block per 256 BWT symbols (same stride as the reference's default
-//   bin), fetched by 8 lanes x one 16-byte ld.global.nc each.  Lane j's chunk is
+//   one 64-byte block per 128 BWT symbols, fetched by 4 lanes x one 16-byte
+//   ld.global.nc each (two 32-byte DRAM sectors: measured on B200, random 64-B reads
+//   sustain ~1.7x the access rate of random 128-B reads, and a step needs only the
+//   rank at two positions, not bandwidth).  Lane j's chunk is
 //
-//       u32 hdr_j | u32 plane0_j | u32 plane1_j | u32 plane2_j
+//       u32 ckpt_j | u32 plane0_j | u32 plane1_j | u32 plane2_j
 //
 //   plane_b_j bit i = bit b of the symbol at block offset 32*j + i  (3-bit symbols,
 //   bit-planes so a lane's 32 symbols are matched with 3 logic ops + 1 popc),
-//   hdr_0..hdr_5 = number of $,A,C,G,N,T before the block, relative to the block's
-//   superblock (u32); hdr_6/hdr_7 are zero.
+//   ckpt_0..ckpt_3 = number of A, C, G, T before the block, relative to the block's
+//   superblock (u32).  The rare symbols $ and N keep their checkpoints in a side
+//   array `aux[blk] = {u32 n$, u32 nN}` that only k-mers containing $ / N touch.
 //
 //   Positions past the end of the BWT in the last block hold symbol 7 (matches
-//   nothing).  There is always a block for position N itself (N>>8), so h == N needs
+//   nothing).  There is always a block for position N itself (N>>7), so h == N needs
 //   no special case.
 //
-//   A superblock is 2^sb_shift blocks (default 2^24 blocks = 2^32 symbols) so the
+//   A superblock is 2^sb_shift blocks (default 2^25 blocks = 2^32 symbols) so the
 //   per-block counters fit u32 for any N; `cbase[sb][s]` (u64, 8 per superblock) =
 //   C[s] + occurrences of s before the superblock.  rank+C for (s,pos) is
-//   cbase[blk>>sb_shift][s] + hdr_s + popc(match & below(pos&255)).
+//   cbase[blk>>sb_shift][s] + ckpt_s + popc(match & below(pos&127)).
 #pragma once
 #include <cstdint>
 
 namespace msbwt {
 
-constexpr int kBlockShift = 8;
+constexpr int kBlockShift = 7;
 constexpr int kBlockSyms = 1 << kBlockShift;
-constexpr int kBlockBytes = 128;
-constexpr int kLanesPerBlock = 8;     // 16 B per lane
-constexpr int kWordsPerBlock = 32;    // u32 words
+constexpr int kBlockBytes = 64;
+constexpr int kLanesPerBlock = 4;     // 16 B per lane
+constexpr int kWordsPerBlock = 16;    // u32 words
 constexpr int kAlphabet = 6;          // $ACGNT (src/msbwt_core.rs:4)
-constexpr int kDefaultSuperShift = 24;
+constexpr int kDefaultSuperShift = 25;
 constexpr int kSymsPerWord = 21;      // packed query word: 21 x 3-bit symbols, first-consumed symbol in the top bits
 constexpr int kMaxSuperInSmem = 64;
 
+// which lane of a block holds the checkpoint of symbol s (A=1,C=2,G=3,T=5); $/N use `aux`
+__host__ __device__ constexpr int ckpt_lane(int s) { return s == 5 ? 3 : s - 1; }
+
 struct IndexView {
-    const uint4 *blocks;     // nblocks * 8 uint4
+    const uint4 *blocks;     // nblocks * 4 uint4
+    const uint32_t *aux;     // nblocks * 2  ($, N checkpoints)
     const uint64_t *cbase;   // n_super * 8
     uint64_t total;          // N
-    uint64_t nblocks;        // (N >> 8) + 1
+    uint64_t nblocks;        // (N >> 7) + 1
     uint32_t n_super;
     uint32_t sb_shift;
 };

@@ -1,0 +1,33 @@
+// build.rs -- UNVERIFIED (no Rust toolchain in the build image).
+// Compiles the sm_100a engine into a static library with nvcc and links it.
+use std::{env, path::PathBuf, process::Command};
+
+fn main() {
+    let out = PathBuf::from(env::var("OUT_DIR").unwrap());
+    let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap());
+    let csrc = root.join("rust-msbwt_b200").join("csrc");
+    let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
+    let mut objs = vec![];
+    for f in ["capi.cu", "kernels.cu", "loader.cu"] {
+        let obj = out.join(f).with_extension("o");
+        let ok = Command::new(&nvcc)
+            .args(["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+                   "-Xcompiler", "-fPIC", "-c", "-o"])
+            .arg(&obj)
+            .arg(csrc.join(f))
+            .status()
+            .expect("nvcc not found: this crate feature has no CPU fallback")
+            .success();
+        assert!(ok, "nvcc failed on {f}");
+        println!("cargo:rerun-if-changed={}", csrc.join(f).display());
+        objs.push(obj);
+    }
+    let lib = out.join("libmsbwt_b200.a");
+    assert!(Command::new("ar").arg("crs").arg(&lib).args(&objs).status().unwrap().success());
+    let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());
+    println!("cargo:rustc-link-search=native={}", out.display());
+    println!("cargo:rustc-link-search=native={cuda}/lib64");
+    println!("cargo:rustc-link-lib=static=msbwt_b200");
+    println!("cargo:rustc-link-lib=dylib=cudart");
+    println!("cargo:rustc-link-lib=dylib=stdc++");
+}
