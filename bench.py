@@ -41,7 +41,8 @@ WORKLOADS = {
 }
 METRIC = "count_kmer_31mer_queries_per_sec"
 UNIT = "queries/s"
-BLOCK_BYTES = 128
+BLOCK_BYTES = 64      # layout.h: one 64-byte block per 128 symbols
+BLOCK_SHIFT = 7
 
 
 def log(*a):
@@ -318,9 +319,9 @@ def run_ours(args, cfg):
         else:
             m = min(n, 200_000)
             assert (got[:m] == orc.count_kmers_fixed(q_host[:m], k, threads=cores)).all()
-        # algorithmic bytes: steps the reference executes x distinct 128-B blocks per step
+        # algorithmic bytes: steps the reference executes x distinct 64-B index blocks per step
         ms = min(n, 1_000_000)
-        steps, two = orc.count_kmers_stats(q_host[:ms], k, 8)
+        steps, two = orc.count_kmers_stats(q_host[:ms], k, BLOCK_SHIFT)
         packed_q = 8 * words
         bytes_per_query = (steps + two) * BLOCK_BYTES / ms + packed_q + 8
         peak, peak_src = measured_peak_gbs()

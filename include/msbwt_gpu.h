@@ -66,11 +66,10 @@ msbwt_index *msbwt_index_create_from_rle(const uint8_t *rle, uint64_t len,
 msbwt_index *msbwt_index_create_from_npy(const char *path, const int *devices, int ndev, int *err);
 
 /* Same as create_from_rle with explicit layout knobs (testing / tuning):
- * `superblock_shift` = log2(blocks per superblock), 0 selects the default (24:
+ * `superblock_shift` = log2(blocks per superblock), 0 selects the default (25:
  * 2^32 symbols per superblock).  The reference's only tuning knob, `bin_power`
  * (RleBWT::with_bin_power, src/rle_bwt.rs:309-322), has no effect on results
- * and no equivalent here: the device block covers 256 symbols, the reference's
- * default bin. */
+ * and no equivalent here: the device block covers a fixed 128 symbols. */
 msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
                                    uint32_t superblock_shift, int *err);
 
@@ -142,10 +141,12 @@ int msbwt_gather_bench(int device, const void *d_buf, uint64_t buf_bytes, uint32
 
 /* ---- inspection: the host-side block image (no device needed) ----
  * Builds the layout.h block image of `rle` exactly as create does and copies it out so
- * tests can check the loader without a GPU.  Call with blocks == NULL to size:
- * *nblocks blocks of 32 u32 words, *n_super rows of 8 u64 in cbase. */
+ * tests can check the loader without a GPU.  Call with the array pointers NULL to size:
+ * *nblocks blocks of 16 u32 words, *nblocks pairs of u32 in aux, *n_super rows of 8 u64
+ * in cbase. */
 int msbwt_debug_build_image(const uint8_t *rle, uint64_t len, uint32_t superblock_shift,
-                            uint64_t *nblocks, uint32_t *n_super, uint32_t *blocks, uint64_t *cbase);
+                            uint64_t *nblocks, uint32_t *n_super, uint32_t *blocks, uint32_t *aux,
+                            uint64_t *cbase);
 
 /* ---- pinned host buffers for callers that want full copy/compute overlap ---- */
 void *msbwt_host_alloc(size_t bytes);

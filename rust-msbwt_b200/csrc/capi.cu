@@ -19,7 +19,13 @@ using namespace msbwt;
 namespace {
 
 thread_local std::string g_last_error;
+thread_local int g_call_launches = 0;
 std::atomic<uint64_t> g_launches{0};
+
+void flush_launches() {
+    g_launches += (uint64_t)g_call_launches;
+    g_call_launches = 0;
+}
 
 int fail(int code, const std::string &msg) {
     g_last_error = msg;
@@ -60,6 +66,7 @@ struct Lane {
 struct Replica {
     int device = -1;
     uint4 *d_blocks = nullptr;
+    uint32_t *d_aux = nullptr;
     uint64_t *d_cbase = nullptr;
     IndexView view{};
     std::mutex mu;
@@ -82,6 +89,7 @@ struct Replica {
         if (d_status) cudaFree(d_status);
         if (h_status) cudaFreeHost(h_status);
         if (d_blocks) cudaFree(d_blocks);
+        if (d_aux) cudaFree(d_aux);
         if (d_cbase) cudaFree(d_cbase);
         cudaSetDevice(cur);
     }
@@ -93,7 +101,7 @@ struct DeviceGuard {
     ~DeviceGuard() { cudaSetDevice(prev); }
 };
 
-constexpr uint64_t kChunkQueries = 1ull << 21;  // host-path pipeline granularity
+constexpr uint64_t kChunkQueries = 1ull << 20;  // host-path pipeline granularity
 constexpr uint64_t kChunkBytes = 1ull << 27;
 
 }  // namespace
@@ -129,7 +137,8 @@ int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev)
     for (int s = 0; s < kAlphabet; s++) { idx->counts[s] = img.counts[s]; idx->start[s] = img.start[s]; }
     const size_t block_bytes = img.blocks.size() * sizeof(uint32_t);
     const size_t cbase_bytes = img.cbase.size() * sizeof(uint64_t);
-    idx->bytes_per_replica = block_bytes + cbase_bytes;
+    const size_t aux_bytes = img.aux.size() * sizeof(uint32_t);
+    idx->bytes_per_replica = block_bytes + cbase_bytes + aux_bytes;
 
     for (int d : devs) {
         DeviceGuard guard(d);
@@ -137,6 +146,8 @@ int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev)
         rep->device = d;
         CU_TRY(cudaMalloc((void **)&rep->d_blocks, block_bytes));
         CU_TRY(cudaMalloc((void **)&rep->d_cbase, cbase_bytes));
+        CU_TRY(cudaMalloc((void **)&rep->d_aux, aux_bytes));
+        CU_TRY(cudaMemcpy(rep->d_aux, img.aux.data(), aux_bytes, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(rep->d_blocks, img.blocks.data(), block_bytes, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(rep->d_cbase, img.cbase.data(), cbase_bytes, cudaMemcpyHostToDevice));
         CU_TRY(cudaMalloc((void **)&rep->d_status, 4 * sizeof(uint32_t)));
@@ -145,6 +156,7 @@ int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev)
         for (auto &ln : rep->lane) CU_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
         rep->view.blocks = rep->d_blocks;
         rep->view.cbase = rep->d_cbase;
+        rep->view.aux = rep->d_aux;
         rep->view.total = img.total;
         rep->view.nblocks = img.nblocks;
         rep->view.n_super = img.n_super;
@@ -259,8 +271,8 @@ extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, 
         CU_TRY(launch_pack_fixed(d_syms, k, n, rep.dev_packed.as<uint64_t>(), flag, st));
         g_launches++;
     }
-    CU_TRY(launch_count_packed(rep.device, rep.view, rep.dev_packed.as<uint64_t>(), k, n, d_out, st));
-    g_launches++;
+    CU_TRY(launch_count_packed(rep.device, rep.view, rep.dev_packed.as<uint64_t>(), k, n, d_out, st, &g_call_launches));
+    flush_launches();
     return MSBWT_OK;
 }
 
@@ -285,8 +297,8 @@ extern "C" int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot,
     if (!n) return MSBWT_OK;
     Replica &rep = *idx->reps[slot];
     DeviceGuard guard(rep.device);
-    CU_TRY(launch_count_packed(rep.device, rep.view, d_packed, k, n, d_out, (cudaStream_t)stream));
-    g_launches++;
+    CU_TRY(launch_count_packed(rep.device, rep.view, d_packed, k, n, d_out, (cudaStream_t)stream, &g_call_launches));
+    flush_launches();
     return MSBWT_OK;
 }
 
@@ -298,8 +310,8 @@ extern "C" int msbwt_constrain_ranges_device(const msbwt_index *idx, int slot, c
     if (!n) return MSBWT_OK;
     Replica &rep = *idx->reps[slot];
     DeviceGuard guard(rep.device);
-    CU_TRY(launch_constrain_ranges(rep.device, rep.view, d_sym, d_l, d_h, n, d_out_l, d_out_h, (cudaStream_t)stream));
-    g_launches++;
+    CU_TRY(launch_constrain_ranges(rep.device, rep.view, d_sym, d_l, d_h, n, d_out_l, d_out_h, (cudaStream_t)stream, &g_call_launches));
+    flush_launches();
     return MSBWT_OK;
 }
 
@@ -352,8 +364,8 @@ extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *sy
                 g_launches++;
             }
             CU_TRY(launch_count_packed(rep.device, rep.view, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
-                                       ln.stream));
-            g_launches++;
+                                       ln.stream, &g_call_launches));
+            flush_launches();
             CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
         }
     }
@@ -414,8 +426,8 @@ extern "C" int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, co
             // the kernel indexes syms with absolute offsets: bias the base pointer instead of rewriting them
             const uint8_t *biased = ln.in_a.as<uint8_t>() - offsets[b];
             CU_TRY(launch_count_bytes(rep.device, rep.view, biased, ln.in_b.as<uint64_t>(), m, ln.out_a.as<uint64_t>(),
-                                      rep.d_status + (round[d] & 1), ln.stream));
-            g_launches++;
+                                      rep.d_status + (round[d] & 1), ln.stream, &g_call_launches));
+            flush_launches();
             CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
             cursor[d] = e;
             round[d]++;
@@ -478,8 +490,8 @@ extern "C" int msbwt_constrain_ranges(const msbwt_index *idx, const uint8_t *sym
             CU_TRY(cudaMemcpyAsync(ln.in_c.p, h + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
             CU_TRY(launch_constrain_ranges(rep.device, rep.view, ln.in_a.as<uint8_t>(), ln.in_b.as<uint64_t>(),
                                            ln.in_c.as<uint64_t>(), m, ln.out_a.as<uint64_t>(), ln.out_b.as<uint64_t>(),
-                                           ln.stream));
-            g_launches++;
+                                           ln.stream, &g_call_launches));
+            flush_launches();
             CU_TRY(cudaMemcpyAsync(out_l + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
             CU_TRY(cudaMemcpyAsync(out_h + b, ln.out_b.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
         }
@@ -495,7 +507,7 @@ extern "C" int msbwt_constrain_ranges(const msbwt_index *idx, const uint8_t *sym
 // ================================================================ inspection
 
 extern "C" int msbwt_debug_build_image(const uint8_t *rle, uint64_t len, uint32_t superblock_shift, uint64_t *nblocks,
-                                       uint32_t *n_super, uint32_t *blocks, uint64_t *cbase) {
+                                       uint32_t *n_super, uint32_t *blocks, uint32_t *aux, uint64_t *cbase) {
     g_last_error.clear();
     if (!nblocks || !n_super) return fail(MSBWT_EINVAL, "NULL size outputs");
     HostImage img;
@@ -505,6 +517,7 @@ extern "C" int msbwt_debug_build_image(const uint8_t *rle, uint64_t len, uint32_
     *nblocks = img.nblocks;
     *n_super = img.n_super;
     if (blocks) memcpy(blocks, img.blocks.data(), img.blocks.size() * sizeof(uint32_t));
+    if (aux) memcpy(aux, img.aux.data(), img.aux.size() * sizeof(uint32_t));
     if (cbase) memcpy(cbase, img.cbase.data(), img.cbase.size() * sizeof(uint64_t));
     return MSBWT_OK;
 }

@@ -12,12 +12,14 @@
 namespace msbwt {
 
 constexpr int kCountThreads = 256;
+constexpr int kCountMinCtas = 8;  // 8 x 256 threads = a full SM of warps; caps the kernels at 32 registers
 
 inline uint32_t words_for_k(uint32_t k) { return k ? (k + kSymsPerWord - 1) / kSymsPerWord : 1; }
 
 // ---- loader.cu: RLE byte stream / .npy -> host block image ----
 struct HostImage {
-    std::vector<uint32_t> blocks;  // nblocks * 32 words
+    std::vector<uint32_t> blocks;  // nblocks * 16 words
+    std::vector<uint32_t> aux;     // nblocks * 2 ($, N checkpoints)
     std::vector<uint64_t> cbase;   // n_super * 8
     uint64_t counts[kAlphabet] = {0, 0, 0, 0, 0, 0};
     uint64_t start[kAlphabet] = {0, 0, 0, 0, 0, 0};
@@ -34,14 +36,15 @@ int read_npy_payload(const char *path, std::vector<uint8_t> &payload, std::strin
 // ---- kernels.cu ----
 cudaError_t launch_pack_fixed(const uint8_t *d_syms, uint32_t k, uint64_t n, uint64_t *d_packed,
                               uint32_t *d_status, cudaStream_t st);
+// `launches` (optional) is incremented once per kernel launch issued
 cudaError_t launch_count_packed(int device, const IndexView &ix, const uint64_t *d_packed, uint32_t k,
-                                uint64_t n, uint64_t *d_out, cudaStream_t st);
+                                uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches);
 cudaError_t launch_count_bytes(int device, const IndexView &ix, const uint8_t *d_syms,
                                const uint64_t *d_offsets, uint64_t n, uint64_t *d_out, uint32_t *d_status,
-                               cudaStream_t st);
+                               cudaStream_t st, int *launches);
 cudaError_t launch_constrain_ranges(int device, const IndexView &ix, const uint8_t *d_sym, const uint64_t *d_l,
                                     const uint64_t *d_h, uint64_t n, uint64_t *d_out_l, uint64_t *d_out_h,
-                                    cudaStream_t st);
+                                    cudaStream_t st, int *launches);
 cudaError_t launch_gather(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,
                           uint64_t n_gathers, uint64_t seed, uint64_t *d_sink, cudaStream_t st);
 

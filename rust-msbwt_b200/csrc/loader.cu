@@ -34,7 +34,9 @@ struct ImageWriter {
             }
         }
         uint32_t *w = &img.blocks[blk * kWordsPerBlock];
-        for (int s = 0; s < kAlphabet; s++) w[s * 4] = (uint32_t)(running[s] - super_base[s]);
+        for (int s : {1, 2, 3, 5}) w[ckpt_lane(s) * 4] = (uint32_t)(running[s] - super_base[s]);
+        img.aux[blk * 2 + 0] = (uint32_t)(running[0] - super_base[0]);  // $
+        img.aux[blk * 2 + 1] = (uint32_t)(running[4] - super_base[4]);  // N
     }
 
     // set symbol `sym` at block offsets [off, off+take) of block blk
@@ -75,7 +77,7 @@ struct ImageWriter {
 int build_image_from_rle(const uint8_t *rle, uint64_t len, uint32_t sb_shift, HostImage &img, std::string &why) {
     if (len && !rle) { why = "rle is NULL"; return MSBWT_EINVAL; }
     if (sb_shift == 0) sb_shift = kDefaultSuperShift;
-    if (sb_shift > kDefaultSuperShift) { why = "superblock_shift > 24 would overflow the u32 block counters"; return MSBWT_EINVAL; }
+    if (sb_shift > (uint32_t)kDefaultSuperShift) { why = "superblock_shift > 25 would overflow the u32 block counters"; return MSBWT_EINVAL; }
 
     // pass 1: symbol totals (the C array) -- src/rle_bwt.rs:352-384
     uint8_t prev = 255;
@@ -103,6 +105,7 @@ int build_image_from_rle(const uint8_t *rle, uint64_t len, uint32_t sb_shift, Ho
     img.n_super = (uint32_t)(((img.nblocks - 1) >> sb_shift) + 1);
     try {
         img.blocks.assign(img.nblocks * kWordsPerBlock, 0u);
+        img.aux.assign(img.nblocks * 2, 0u);
         img.cbase.assign((size_t)img.n_super * 8, 0ull);
     } catch (const std::bad_alloc &) {
         why = "out of host memory for the block image";

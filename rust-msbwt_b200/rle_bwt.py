@@ -108,7 +108,7 @@ def load_library():
         "msbwt_count_kmers_packed_device": (i32, [vp, i32, vp, u32, u64, vp, vp]),
         "msbwt_launch_count": (u64, []),
         "msbwt_gather_bench": (i32, [i32, vp, u64, u32, u64, u64, vp, vp]),
-        "msbwt_debug_build_image": (i32, [vp, u64, u32, C.POINTER(u64), C.POINTER(u32), vp, vp]),
+        "msbwt_debug_build_image": (i32, [vp, u64, u32, C.POINTER(u64), C.POINTER(u32), vp, vp, vp]),
         "msbwt_host_alloc": (vp, [C.c_size_t]),
         "msbwt_host_free": (None, [vp]),
         "msbwt_last_error": (C.c_char_p, []),
@@ -304,18 +304,20 @@ class RleBWT:
         return [L.msbwt_device_ordinal(self.handle, i) for i in range(L.msbwt_device_count(self.handle))]
 
 
-def debug_build_image(rle, superblock_shift: int = 0) -> tuple[np.ndarray, np.ndarray]:
-    """Host-side block image (layout.h) of an RLE stream: (blocks[nblocks,32] u32, cbase[n_super,8] u64).
-    Inspection only; needs no device."""
+def debug_build_image(rle, superblock_shift: int = 0) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Host-side block image (layout.h) of an RLE stream:
+    (blocks[nblocks,16] u32, aux[nblocks,2] u32, cbase[n_super,8] u64).  Inspection only; needs no device."""
     L = load_library()
     a = _u8(rle)
     nb, ns = C.c_uint64(0), C.c_uint32(0)
-    _check(L.msbwt_debug_build_image(_p(a), a.size, superblock_shift, C.byref(nb), C.byref(ns), None, None), "image")
-    blocks = np.zeros((nb.value, 32), dtype=np.uint32)
-    cbase = np.zeros((ns.value, 8), dtype=np.uint64)
-    _check(L.msbwt_debug_build_image(_p(a), a.size, superblock_shift, C.byref(nb), C.byref(ns), _p(blocks), _p(cbase)),
+    _check(L.msbwt_debug_build_image(_p(a), a.size, superblock_shift, C.byref(nb), C.byref(ns), None, None, None),
            "image")
-    return blocks, cbase
+    blocks = np.zeros((nb.value, 16), dtype=np.uint32)
+    aux = np.zeros((nb.value, 2), dtype=np.uint32)
+    cbase = np.zeros((ns.value, 8), dtype=np.uint64)
+    _check(L.msbwt_debug_build_image(_p(a), a.size, superblock_shift, C.byref(nb), C.byref(ns), _p(blocks), _p(aux),
+                                     _p(cbase)), "image")
+    return blocks, aux, cbase
 
 
 def packed_words(k: int) -> int:

@@ -29,19 +29,23 @@ def test_library_exports_every_declared_symbol():
     assert M.load_library().msbwt_abi_version() == 1
 
 
-def image_rank(blocks, cbase, sb_shift, sym, pos):
+CKPT_LANE = {1: 0, 2: 1, 3: 2, 5: 3}  # layout.h: A,C,G,T checkpoints sit in lanes 0..3; $ / N in aux
+
+
+def image_rank(blocks, aux, cbase, sb_shift, sym, pos):
     """rank+C read off the block image exactly as layout.h documents it"""
-    blk, p = pos >> 8, pos & 255
+    blk, p = pos >> 7, pos & 127
     w = blocks[blk]
     cnt = 0
-    for j in range(8):
+    for j in range(4):
         m = 0xFFFFFFFF
         for b in range(3):
             plane = int(w[j * 4 + 1 + b])
             m &= plane if (sym >> b) & 1 else (~plane & 0xFFFFFFFF)
         nb = min(max(p - 32 * j, 0), 32)
         cnt += bin(m & ((1 << nb) - 1)).count("1")
-    return int(cbase[blk >> sb_shift][sym]) + int(w[sym * 4]) + cnt
+    ckpt = int(w[CKPT_LANE[sym] * 4]) if sym in CKPT_LANE else int(aux[blk][sym >> 2])
+    return int(cbase[blk >> sb_shift][sym]) + ckpt + cnt
 
 
 def random_rle(rng, nruns, big=False):
@@ -61,29 +65,29 @@ def random_rle(rng, nruns, big=False):
 def test_block_image_ranks_match_oracle(sb_shift, big):
     rng = np.random.default_rng(99 + sb_shift + 10 * big)
     rle = random_rle(rng, 900, big)
-    blocks, cbase = M.debug_build_image(rle, sb_shift)
+    blocks, aux, cbase = M.debug_build_image(rle, sb_shift)
     orc = O.RleBWT()
     orc.load_vector(rle)
     n = orc.get_total_size()
-    shift = sb_shift or 24
-    assert blocks.shape[0] == (n >> 8) + 1
+    shift = sb_shift or 25
+    assert blocks.shape[0] == aux.shape[0] == (n >> 7) + 1
     assert cbase.shape[0] == ((blocks.shape[0] - 1) >> shift) + 1
-    assert (blocks[:, 24] == 0).all() and (blocks[:, 28] == 0).all()
-    pos = sorted(set(rng.integers(0, n + 1, size=400).tolist() + [0, n, n - 1, 256, 255, 257]))
+    pos = sorted(set(rng.integers(0, n + 1, size=400).tolist() + [0, n, n - 1, 128, 127, 129, 256, 255, 257]))
     for s in range(6):
         for a, b in zip(pos[:-1], pos[1:]):
             want = orc.constrain_range(s, a, b)
-            assert (image_rank(blocks, cbase, shift, s, a), image_rank(blocks, cbase, shift, s, b)) == want
+            assert (image_rank(blocks, aux, cbase, shift, s, a), image_rank(blocks, aux, cbase, shift, s, b)) == want
 
 
 def test_block_image_exact_multiple_of_256_and_empty():
     rle = O.encode_runs([1, 2], [256, 256])
-    blocks, cbase = M.debug_build_image(rle)
-    assert blocks.shape == (3, 32)  # position N itself has a block
-    assert image_rank(blocks, cbase, 24, 2, 512) == 256 + 256
-    assert image_rank(blocks, cbase, 24, 1, 512) == 256
-    blocks, cbase = M.debug_build_image(np.zeros(0, np.uint8))
-    assert blocks.shape == (1, 32) and image_rank(blocks, cbase, 24, 3, 0) == 0
+    blocks, aux, cbase = M.debug_build_image(rle)
+    assert blocks.shape == (5, 16)  # position N itself has a block
+    assert image_rank(blocks, aux, cbase, 25, 2, 512) == 256 + 256
+    assert image_rank(blocks, aux, cbase, 25, 1, 512) == 256
+    assert image_rank(blocks, aux, cbase, 25, 0, 512) == 0 and image_rank(blocks, aux, cbase, 25, 4, 512) == 512
+    blocks, aux, cbase = M.debug_build_image(np.zeros(0, np.uint8))
+    assert blocks.shape == (1, 16) and image_rank(blocks, aux, cbase, 25, 3, 0) == 0
 
 
 def test_bad_rle_symbol_is_eformat():
