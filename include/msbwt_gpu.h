@@ -69,9 +69,14 @@ msbwt_index *msbwt_index_create_from_npy(const char *path, const int *devices, i
  * `superblock_shift` = log2(blocks per superblock), 0 selects the default (25:
  * 2^32 symbols per superblock).  The reference's only tuning knob, `bin_power`
  * (RleBWT::with_bin_power, src/rle_bwt.rs:309-322), has no effect on results
- * and no equivalent here: the device block covers a fixed 128 symbols. */
+ * and no equivalent here: the device block covers a fixed 128 symbols.
+ * `suffix_table_s`: depth of the suffix table -- the range after the first s backward-search
+ * steps, precomputed for all 4^s ACGT suffixes (the `kmer_cache` the reference author planned
+ * but never implemented, src/msbwt_core.rs:133-146); k-mers whose last s symbols are ACGT
+ * start from it, bit-exactly.  -1 = automatic (ceil(log4(N/32)), at most 13; the
+ * MSBWT_SUFFIX_TABLE_S environment variable overrides), 0 = none, 1..15 explicit. */
 msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
-                                   uint32_t superblock_shift, int *err);
+                                   uint32_t superblock_shift, int suffix_table_s, int *err);
 
 void msbwt_index_destroy(msbwt_index *idx);
 
@@ -82,7 +87,8 @@ uint64_t msbwt_symbol_count(const msbwt_index *idx, uint8_t sym); /* 0 for sym >
 uint64_t msbwt_start_index(const msbwt_index *idx, uint8_t sym);
 int msbwt_device_count(const msbwt_index *idx);
 int msbwt_device_ordinal(const msbwt_index *idx, int slot);
-uint64_t msbwt_index_bytes(const msbwt_index *idx); /* device bytes per replica */
+uint64_t msbwt_index_bytes(const msbwt_index *idx); /* device bytes per replica, suffix table included */
+int msbwt_suffix_table_s(const msbwt_index *idx);     /* suffix table depth in use (0 = none) */
 
 /* ---- queries from HOST buffers (the drop-in calls) ---- */
 
@@ -120,11 +126,13 @@ int msbwt_constrain_ranges_device(const msbwt_index *idx, int slot, const uint8_
 
 /* The two stages of msbwt_count_kmers_fixed_device as separate calls, for callers that keep
  * packed k-mers resident (and for timing the search kernel on its own):
- *   pack : n*k symbol bytes -> msbwt_packed_words(k)*n u64 words (word-major: word w of query
- *          q at d_packed[w*n + q]; 21 three-bit symbols per word, the k-mer's LAST symbol in
- *          the top bits because backward search consumes it first), validating symbols;
+ *   pack : n*k symbol bytes -> msbwt_packed_words(idx,k)*n u64 words (word-major: word w of
+ *          query q at d_packed[w*n + q]; 21 three-bit symbols per word, the k-mer's LAST symbol
+ *          in the top bits because backward search consumes it first; the trailing word(s)
+ *          hold the range the search starts from, looked up in the suffix table), validating
+ *          symbols;
  *   count: the backward search over packed k-mers. */
-uint32_t msbwt_packed_words(uint32_t k);
+uint32_t msbwt_packed_words(const msbwt_index *idx, uint32_t k);
 int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const uint8_t *d_syms, uint32_t k,
                             uint64_t n, uint64_t *d_packed, uint32_t *d_status, void *stream);
 int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot, const uint64_t *d_packed,
@@ -134,8 +142,9 @@ int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot, const uint
 uint64_t msbwt_launch_count(void);
 
 /* ---- measurement aid: random-gather roofline microbenchmark ----
- * Issues n_gathers independent, uniformly random, `granule`-byte-aligned reads of
- * `granule` bytes (32, 64 or 128) over `d_buf` (buf_bytes, device memory) on `stream`. */
+ * Issues n_gathers (< 2^31) independent, uniformly random, `granule`-byte-aligned reads of
+ * `granule` bytes (32, 64 or 128) over the largest power-of-two number of granules that
+ * fits in `d_buf` (buf_bytes, device memory) on `stream`. */
 int msbwt_gather_bench(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,
                        uint64_t n_gathers, uint64_t seed, uint64_t *d_sink, void *stream);
 

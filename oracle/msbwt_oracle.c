@@ -429,22 +429,38 @@ int orc_count_kmers(const orc_rle_bwt *b, const uint8_t *syms, const uint64_t *o
     return run_split(b, syms, offsets, 0, n, out, threads);
 }
 
-int orc_count_kmers_stats(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
-                          unsigned block_shift, uint64_t *steps, uint64_t *two_block_steps) {
-    uint64_t st = 0, tb = 0;
+int orc_count_kmers_stats_skip(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                               unsigned block_shift, uint32_t skip, uint64_t *steps,
+                               uint64_t *two_block_steps, uint64_t *table_hits) {
+    uint64_t st = 0, tb = 0, hits = 0;
     for (uint64_t i = 0; i < n; i++) {
         const uint8_t *q = syms + i * (uint64_t)k;
-        for (uint32_t t = 0; t < k; t++) if (q[t] >= ORC_VC_LEN) return ORC_PANIC_BAD_SYMBOL;
+        int eligible = skip > 0 && k >= skip;
+        for (uint32_t t = 0; t < k; t++) {
+            if (q[t] >= ORC_VC_LEN) return ORC_PANIC_BAD_SYMBOL;
+            if (t >= k - (eligible ? skip : 0) && !(q[t] == 1 || q[t] == 2 || q[t] == 3 || q[t] == 5)) eligible = 0;
+        }
+        hits += (uint64_t)eligible;
+        const uint32_t first_counted = eligible ? skip : 0;
         orc_range r = { 0, b->total_size };
-        for (uint32_t t = k; t-- > 0;) {
+        uint32_t done = 0;
+        for (uint32_t t = k; t-- > 0; done++) {
             if (r.h == r.l) break;
-            st++;
-            if ((r.l >> block_shift) != (r.h >> block_shift)) tb++;
+            if (done >= first_counted) {
+                st++;
+                if ((r.l >> block_shift) != (r.h >> block_shift)) tb++;
+            }
             r = orc_constrain_range(b, q[t], r);
         }
     }
     *steps = st; *two_block_steps = tb;
+    if (table_hits) *table_hits = hits;
     return ORC_OK;
+}
+
+int orc_count_kmers_stats(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                          unsigned block_shift, uint64_t *steps, uint64_t *two_block_steps) {
+    return orc_count_kmers_stats_skip(b, syms, k, n, block_shift, 0, steps, two_block_steps, NULL);
 }
 
 /* ---- bwt_converter.rs ---- */

@@ -93,6 +93,12 @@ int orc_count_kmers(const orc_rle_bwt *b, const uint8_t *syms, const uint64_t *o
  * `1<<block_shift`-symbol blocks (two_block_steps).  SURVEY.md section 8(d). */
 int orc_count_kmers_stats(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
                           unsigned block_shift, uint64_t *steps, uint64_t *two_block_steps);
+/* Same replay, but for an engine that answers the first `skip` steps of every k-mer whose
+ * last `skip` symbols are all ACGT from a precomputed suffix table: those steps are not
+ * counted, *table_hits counts the k-mers that took the shortcut. */
+int orc_count_kmers_stats_skip(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                               unsigned block_shift, uint32_t skip, uint64_t *steps,
+                               uint64_t *two_block_steps, uint64_t *table_hits);
 
 /* bwt_converter.rs:26-80 convert_to_vec: ASCII "$ACGNT"(+'\n') -> RLE bytes.
  * Returns number of bytes written (call with out==NULL to size), or

@@ -94,6 +94,7 @@ def lib():
         "orc_count_kmers_fixed": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, vp, C.c_int]),
         "orc_count_kmers": (C.c_int, [vp, vp, vp, C.c_uint64, vp, C.c_int]),
         "orc_count_kmers_stats": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, C.c_uint, u64p, u64p]),
+        "orc_count_kmers_stats_skip": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, C.c_uint, C.c_uint32, u64p, u64p, u64p]),
         "orc_convert_to_vec": (C.c_uint64, [vp, C.c_uint64, vp, C.c_uint64]),
         "orc_encode_runs": (C.c_uint64, [vp, vp, C.c_uint64, vp, C.c_uint64]),
         "orc_save_bwt_numpy": (C.c_int, [vp, C.c_uint64, C.c_char_p]),
@@ -252,6 +253,15 @@ class RleBWT:
         _raise(lib().orc_count_kmers(self._h, _ptr(flat), _ptr(offs), len(kmers), _ptr(out), threads),
                "count_kmers")
         return out
+
+    def count_kmers_stats_skip(self, syms, k: int, block_shift: int, skip: int) -> tuple[int, int, int]:
+        """(steps, two_block_steps, table_hits) for an engine whose suffix table answers the first `skip` steps."""
+        a = _u8(syms).reshape(-1)
+        n = a.size // k
+        st, tb, th = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _raise(lib().orc_count_kmers_stats_skip(self._h, _ptr(a), k, n, block_shift, skip, C.byref(st), C.byref(tb),
+                                                C.byref(th)), "count_kmers_stats_skip")
+        return int(st.value), int(tb.value), int(th.value)
 
     def count_kmers_stats(self, syms, k: int, block_shift: int = 8) -> tuple[int, int]:
         a = _u8(syms).reshape(-1)

@@ -17,7 +17,6 @@ from .rle_bwt import (  # noqa: F401
     debug_build_image,
     gather_bench,
     launch_count,
-    packed_words,
     EXPORTED_SYMBOLS,
     library_path,
     load_library,

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -67,6 +68,7 @@ struct Replica {
     int device = -1;
     uint4 *d_blocks = nullptr;
     uint32_t *d_aux = nullptr;
+    void *d_table = nullptr;
     uint64_t *d_cbase = nullptr;
     IndexView view{};
     std::mutex mu;
@@ -90,6 +92,7 @@ struct Replica {
         if (h_status) cudaFreeHost(h_status);
         if (d_blocks) cudaFree(d_blocks);
         if (d_aux) cudaFree(d_aux);
+        if (d_table) cudaFree(d_table);
         if (d_cbase) cudaFree(d_cbase);
         cudaSetDevice(cur);
     }
@@ -111,6 +114,7 @@ struct msbwt_index {
     uint64_t counts[kAlphabet] = {0, 0, 0, 0, 0, 0};
     uint64_t start[kAlphabet] = {0, 0, 0, 0, 0, 0};
     uint64_t bytes_per_replica = 0;
+    uint32_t table_s = 0;
     std::vector<std::unique_ptr<Replica>> reps;
 };
 
@@ -166,8 +170,58 @@ int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev)
     return MSBWT_OK;
 }
 
+// Suffix table (layout.h): level j+1 from level j with one constrain_range per entry, on the
+// replica's own device.  s < 0 picks ceil(log4(N / 32)) capped to kAutoMaxTableS: about the
+// depth at which a read set's BWT ranges stop being shared between unrelated k-mers.
+constexpr int kAutoMaxTableS = 13;
+
+int pick_table_s(uint64_t total, int requested) {
+    if (requested >= 0) return requested > kMaxTableS ? kMaxTableS : requested;
+    if (const char *env = getenv("MSBWT_SUFFIX_TABLE_S")) {
+        int v = atoi(env);
+        return v < 0 ? 0 : (v > kMaxTableS ? kMaxTableS : v);
+    }
+    int s = 0;
+    while (s < kAutoMaxTableS && (1ull << (2 * s)) < total / 32) s++;
+    return s;
+}
+
+int build_suffix_table(msbwt_index *idx, Replica &rep, int s) {
+    if (s <= 0) return MSBWT_OK;
+    DeviceGuard guard(rep.device);
+    const bool wide = index_is_wide(rep.view);
+    const size_t eb = wide ? 16 : 8;
+    const uint64_t entries = 1ull << (2 * s);
+    void *fin = nullptr, *tmp = nullptr;
+    CU_TRY(cudaMalloc(&fin, entries * eb));
+    if (cudaError_t e = cudaMalloc(&tmp, (entries / 4) * eb); e != cudaSuccess) {
+        cudaFree(fin);
+        return fail(MSBWT_ENOMEM, std::string("suffix table scratch: ") + cudaGetErrorString(e));
+    }
+    auto level_buf = [&](int j) { return ((s - j) % 2 == 0) ? fin : tmp; };
+    uint64_t root[2] = {0, rep.view.total};
+    uint32_t root32[2] = {0, (uint32_t)rep.view.total};
+    cudaError_t e = cudaMemcpy(level_buf(0), wide ? (const void *)root : (const void *)root32, eb, cudaMemcpyHostToDevice);
+    for (int j = 0; j < s && e == cudaSuccess; j++) {
+        e = launch_table_extend(rep.device, rep.view, level_buf(j), level_buf(j + 1), (uint32_t)(1ull << (2 * (j + 1))), nullptr);
+        g_launches++;
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(tmp);
+    if (e != cudaSuccess) {
+        cudaFree(fin);
+        return fail(MSBWT_ECUDA, std::string("suffix table build: ") + cudaGetErrorString(e));
+    }
+    rep.d_table = fin;
+    rep.view.table = fin;
+    rep.view.table_s = (uint32_t)s;
+    idx->table_s = (uint32_t)s;
+    idx->bytes_per_replica += (idx->reps[0].get() == &rep) ? entries * eb : 0;
+    return MSBWT_OK;
+}
+
 msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices, int ndev, uint32_t sb_shift,
-                           int *err) {
+                           int table_s, int *err) {
     g_last_error.clear();
     int rc;
     std::string why;
@@ -177,6 +231,13 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
         rc = build_image_from_rle(rle, len, sb_shift, img, why);
         if (rc == MSBWT_OK) rc = upload(idx.get(), img, devices, ndev);
         else fail(rc, why);
+    }
+    if (rc == MSBWT_OK) {
+        const int s = pick_table_s(idx->total, table_s);
+        for (auto &rep : idx->reps) {
+            rc = build_suffix_table(idx.get(), *rep, s);
+            if (rc != MSBWT_OK) break;
+        }
     }
     if (err) *err = rc;
     if (rc != MSBWT_OK) return nullptr;
@@ -201,12 +262,12 @@ int check_status_flags(msbwt_index const *idx, const char *what) {
 
 extern "C" msbwt_index *msbwt_index_create_from_rle(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
                                                    int *err) {
-    return create_common(rle, len, devices, ndev, 0, err);
+    return create_common(rle, len, devices, ndev, 0, -1, err);
 }
 
 extern "C" msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
-                                             uint32_t superblock_shift, int *err) {
-    return create_common(rle, len, devices, ndev, superblock_shift, err);
+                                             uint32_t superblock_shift, int suffix_table_s, int *err) {
+    return create_common(rle, len, devices, ndev, superblock_shift, suffix_table_s, err);
 }
 
 extern "C" msbwt_index *msbwt_index_create_from_npy(const char *path, const int *devices, int ndev, int *err) {
@@ -219,7 +280,7 @@ extern "C" msbwt_index *msbwt_index_create_from_npy(const char *path, const int 
         if (err) *err = rc;
         return nullptr;
     }
-    return create_common(payload.data(), payload.size(), devices, ndev, 0, err);
+    return create_common(payload.data(), payload.size(), devices, ndev, 0, -1, err);
 }
 
 extern "C" void msbwt_index_destroy(msbwt_index *idx) { delete idx; }
@@ -239,6 +300,7 @@ extern "C" int msbwt_device_ordinal(const msbwt_index *idx, int slot) {
     return (idx && slot >= 0 && slot < (int)idx->reps.size()) ? idx->reps[slot]->device : -1;
 }
 extern "C" uint64_t msbwt_index_bytes(const msbwt_index *idx) { return idx ? idx->bytes_per_replica : 0; }
+extern "C" int msbwt_suffix_table_s(const msbwt_index *idx) { return idx ? (int)idx->table_s : 0; }
 extern "C" uint64_t msbwt_launch_count(void) { return g_launches.load(); }
 extern "C" const char *msbwt_last_error(void) { return g_last_error.c_str(); }
 extern "C" int msbwt_abi_version(void) { return MSBWT_ABI_VERSION; }
@@ -264,28 +326,28 @@ extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, 
     std::lock_guard<std::mutex> lock(rep.mu);
     DeviceGuard guard(rep.device);
     cudaStream_t st = (cudaStream_t)stream;
-    CU_TRY(rep.dev_packed.reserve(n * words_for_k(k) * sizeof(uint64_t)));
+    CU_TRY(rep.dev_packed.reserve(n * packed_words_for(rep.view, k) * sizeof(uint64_t)));
     uint32_t *flag = d_status ? d_status : rep.d_status + 2;
     CU_TRY(cudaMemsetAsync(flag, 0, sizeof(uint32_t), st));
-    if (k) {
-        CU_TRY(launch_pack_fixed(d_syms, k, n, rep.dev_packed.as<uint64_t>(), flag, st));
-        g_launches++;
-    }
+    CU_TRY(launch_pack_seed(rep.view, d_syms, k, n, rep.dev_packed.as<uint64_t>(), flag, st));
+    g_launches++;
     CU_TRY(launch_count_packed(rep.device, rep.view, rep.dev_packed.as<uint64_t>(), k, n, d_out, st, &g_call_launches));
     flush_launches();
     return MSBWT_OK;
 }
 
-extern "C" uint32_t msbwt_packed_words(uint32_t k) { return words_for_k(k); }
+extern "C" uint32_t msbwt_packed_words(const msbwt_index *idx, uint32_t k) {
+    return (idx && !idx->reps.empty()) ? packed_words_for(idx->reps[0]->view, k) : 0;
+}
 
 extern "C" int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const uint8_t *d_syms, uint32_t k, uint64_t n,
                                        uint64_t *d_packed, uint32_t *d_status, void *stream) {
     if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
-    if (n && k && (!d_syms || !d_packed || !d_status)) return fail(MSBWT_EINVAL, "NULL device buffer");
-    if (!n || !k) return MSBWT_OK;
+    if (n && (!d_packed || !d_status || (k && !d_syms))) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (!n) return MSBWT_OK;
     Replica &rep = *idx->reps[slot];
     DeviceGuard guard(rep.device);
-    CU_TRY(launch_pack_fixed(d_syms, k, n, d_packed, d_status, (cudaStream_t)stream));
+    CU_TRY(launch_pack_seed(rep.view, d_syms, k, n, d_packed, d_status, (cudaStream_t)stream));
     g_launches++;
     return MSBWT_OK;
 }
@@ -293,7 +355,7 @@ extern "C" int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const u
 extern "C" int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot, const uint64_t *d_packed, uint32_t k,
                                                uint64_t n, uint64_t *d_out, void *stream) {
     if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
-    if (n && (!d_out || (k && !d_packed))) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (n && (!d_out || !d_packed)) return fail(MSBWT_EINVAL, "NULL device buffer");
     if (!n) return MSBWT_OK;
     Replica &rep = *idx->reps[slot];
     DeviceGuard guard(rep.device);
@@ -324,7 +386,7 @@ extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *sy
     if (n && (!out || (k && !syms))) return fail(MSBWT_EINVAL, "NULL host buffer");
     if (!n) return MSBWT_OK;
     const size_t ndev = idx->reps.size();
-    const uint32_t words = words_for_k(k);
+    const uint32_t words = packed_words_for(idx->reps[0]->view, k);
     uint64_t chunk = kChunkQueries;
     if (k && chunk * k > kChunkBytes) chunk = std::max<uint64_t>(1, kChunkBytes / k);
 
@@ -357,12 +419,10 @@ extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *sy
             const uint64_t m = std::min(chunk, sl.end - b);
             DeviceGuard guard(rep.device);
             Lane &ln = rep.lane[c & 1];
-            if (k) {
-                CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + b * k, m * k, cudaMemcpyHostToDevice, ln.stream));
-                CU_TRY(launch_pack_fixed(ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(),
-                                         rep.d_status + (c & 1), ln.stream));
-                g_launches++;
-            }
+            if (k) CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + b * k, m * k, cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(),
+                                    rep.d_status + (c & 1), ln.stream));
+            g_launches++;
             CU_TRY(launch_count_packed(rep.device, rep.view, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
                                        ln.stream, &g_call_launches));
             flush_launches();

@@ -12,6 +12,7 @@
 namespace msbwt {
 
 constexpr int kCountThreads = 256;
+constexpr int kCountMinCtasWide = 6;  // u64 positions need ~40 registers
 constexpr int kCountMinCtas = 8;  // 8 x 256 threads = a full SM of warps; caps the kernels at 32 registers
 
 inline uint32_t words_for_k(uint32_t k) { return k ? (k + kSymsPerWord - 1) / kSymsPerWord : 1; }
@@ -34,8 +35,13 @@ int build_image_from_rle(const uint8_t *rle, uint64_t len, uint32_t sb_shift, Ho
 int read_npy_payload(const char *path, std::vector<uint8_t> &payload, std::string &why);
 
 // ---- kernels.cu ----
-cudaError_t launch_pack_fixed(const uint8_t *d_syms, uint32_t k, uint64_t n, uint64_t *d_packed,
-                              uint32_t *d_status, cudaStream_t st);
+cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_t k, uint64_t n, uint64_t *d_packed,
+                             uint32_t *d_status, cudaStream_t st);
+cudaError_t launch_table_extend(int device, const IndexView &ix, const void *d_parent, void *d_child,
+                                uint32_t n_child, cudaStream_t st);
+bool index_is_wide(const IndexView &ix);
+// u64 words per query in the packed layout: symbol words + seed word(s)
+inline uint32_t packed_words_for(const IndexView &ix, uint32_t k) { return words_for_k(k) + (index_is_wide(ix) ? 2u : 1u); }
 // `launches` (optional) is incremented once per kernel launch issued
 cudaError_t launch_count_packed(int device, const IndexView &ix, const uint64_t *d_packed, uint32_t k,
                                 uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches);

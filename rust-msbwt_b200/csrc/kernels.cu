@@ -10,6 +10,8 @@
 // 32 symbols against the query symbol (3 LOP3 + POPC), and two shuffle-xor steps sum
 // the lanes (the l and h boundaries share the reduction, 16 bits each).  A warp
 // therefore advances 8 queries per instruction.
+#include <type_traits>
+
 #include "engine.h"
 
 namespace msbwt {
@@ -131,29 +133,57 @@ __device__ __forceinline__ void group_step(const IndexView &ix, const CBase<WIDE
     h = cb.at(bh, sym) + hh + (cnt >> 16);
 }
 
-// ---------------------------------------------------------------- K0: pack + validate
+// ---------------------------------------------------------------- K0: pack + validate + seed
 
-// One thread per (query, word).  Word w of query q holds symbols consumed at steps
-// 21w .. 21w+20 of the backward search (step t reads kmer[k-1-t]), first step in the
-// top 3 bits below bit 63.  Stored word-major: packed[w*n + q].
-__global__ void pack_fixed_kernel(const uint8_t *__restrict__ syms, uint32_t k, uint64_t n,
-                                  uint32_t words, uint64_t *__restrict__ packed,
-                                  uint32_t *__restrict__ status) {
-    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n * words) return;
-    const uint64_t q = tid % n;
-    const uint32_t w = (uint32_t)(tid / n);
+// Packed query layout (word-major, stride n): `words` symbol words, then the seed.
+// Word w of query q holds the symbols consumed at steps 21w .. 21w+20 of the backward search
+// (step t reads kmer[k-1-t]), first step in bits 62..60; bit 63 of word 0 says "the seed came
+// from the suffix table, the first table_s steps are already done".  The seed is the range
+// the search starts from: NARROW one word (l | h << 32), WIDE two words (l, h).
+// One thread per query: pack, validate (symbol >= 6 sets *status) and, when the last
+// table_s symbols are all ACGT, gather the seed range from the suffix table.
+template <bool WIDE>
+__global__ void pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, uint64_t n,
+                                 uint32_t words, uint64_t *__restrict__ packed, uint32_t *__restrict__ status) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
     const uint8_t *src = syms + q * k;
-    const uint32_t t0 = w * kSymsPerWord;
-    const uint32_t cnt = min((uint32_t)kSymsPerWord, k - t0);
-    uint64_t word = 0;
-    bool bad = false;
-    for (uint32_t i = 0; i < cnt; i++) {
-        const uint32_t s = src[k - 1 - (t0 + i)];
-        bad |= (s >= (uint32_t)kAlphabet);
-        word |= (uint64_t)(s & 7u) << (60 - 3 * i);
+    const uint32_t ts = ix.table_s;
+    bool bad = false, acgt = (ts != 0 && k >= ts);
+    uint64_t tidx = 0, word0 = 0;
+    for (uint32_t w = 0; w < words; w++) {
+        const uint32_t t0 = w * kSymsPerWord;
+        const uint32_t cnt = k > t0 ? min((uint32_t)kSymsPerWord, k - t0) : 0u;
+        uint64_t word = 0;
+        for (uint32_t i = 0; i < cnt; i++) {
+            const uint32_t sy = src[k - 1 - (t0 + i)];
+            bad |= (sy >= (uint32_t)kAlphabet);
+            word |= (uint64_t)(sy & 7u) << (60 - 3 * i);
+            if (t0 + i < ts) {
+                acgt &= ((0x2Eu >> (sy & 7u)) & 1u) != 0;                   // {1,2,3,5}
+                tidx = (tidx << 2) | ((sy - 1u - (sy >> 2)) & 3u);
+            }
+        }
+        if (w == 0) word0 = word; else packed[(uint64_t)w * n + q] = word;
     }
-    packed[(uint64_t)w * n + q] = word;
+    uint64_t lo = 0, hi = ix.total;
+    if (acgt && !bad) {
+        if constexpr (WIDE) {
+            const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(ix.table) + tidx);
+            lo = e.x; hi = e.y;
+        } else {
+            const uint2 e = __ldg(reinterpret_cast<const uint2 *>(ix.table) + tidx);
+            lo = e.x; hi = e.y;
+        }
+        word0 |= 1ull << 63;
+    }
+    packed[q] = word0;
+    if constexpr (WIDE) {
+        packed[(uint64_t)words * n + q] = lo;
+        packed[(uint64_t)(words + 1) * n + q] = hi;
+    } else {
+        packed[(uint64_t)words * n + q] = lo | (hi << 32);
+    }
     if (bad) atomicOr(status, 1u);
 }
 
@@ -163,12 +193,14 @@ constexpr int kGroupsPerCta = kCountThreads / kLanesPerBlock;
 
 // Persistent kernel: every 4-lane group owns a stream of queries (q, q+G, q+2G, ...)
 // and refills itself as soon as its current query is finished, so a warp's eight
-// groups never wait for each other's k-mers to end.  `packed`/`out` are already offset
-// to this launch's first query; `stride` is the word-major stride of `packed`.
+// groups never wait for each other's k-mers to end.  The next query's first word and
+// seed are loaded one query ahead so a refill never exposes memory latency.
+// `packed`/`out` are already offset to this launch's first query; `stride` is the
+// word-major stride of `packed`, `words` the number of symbol words per query.
 template <bool WIDE>
-__global__ void __launch_bounds__(kCountThreads, kCountMinCtas)
-count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, uint64_t stride, uint32_t k,
-                          uint32_t n, uint64_t *__restrict__ out) {
+__global__ void __launch_bounds__(kCountThreads, WIDE ? kCountMinCtasWide : kCountMinCtas)
+count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, uint64_t stride, uint32_t words,
+                          uint32_t k, uint32_t n, uint64_t *__restrict__ out) {
     using P = typename Pos<WIDE>::type;
     __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
     const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
@@ -177,17 +209,35 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, uin
     const uint32_t sub = threadIdx.x & (kLanesPerBlock - 1);
     const uint32_t groups = gridDim.x * kGroupsPerCta;
     uint32_t q = blockIdx.x * kGroupsPerCta + (threadIdx.x / kLanesPerBlock);
+    const uint64_t *seeds = packed + (uint64_t)words * stride;
+    const uint32_t ts = ix.table_s;
 
     P l = 0, h = 0;
-    uint64_t word = 0, next_word = 0;
+    uint64_t word = 0, next_word = 0, next_lo = 0;
+    [[maybe_unused]] uint64_t next_hi = 0;
     uint32_t rem = 0;   // symbols still to consume
     int shift = 60;     // bit offset of the next symbol in `word`
     uint32_t widx = 0;  // index of `word` within the query
+
+    auto prefetch = [&](uint32_t qq) {
+        next_word = ldg_stream(packed + qq, stream);
+        next_lo = ldg_stream(seeds + qq, stream);
+        if constexpr (WIDE) next_hi = ldg_stream(seeds + stride + qq, stream);
+    };
+    auto begin = [&]() {  // start the prefetched query
+        word = next_word;
+        if constexpr (WIDE) { l = next_lo; h = next_hi; } else { l = (uint32_t)next_lo; h = (uint32_t)(next_lo >> 32); }
+        const uint32_t done = (word >> 63) ? ts : 0u;  // steps already answered by the suffix table
+        rem = k - done;
+        shift = 60 - 3 * (int)done;
+        widx = 0;
+    };
+
     bool live = q < n;
     if (live) {
-        h = (P)ix.total; rem = k;
-        if (k) word = ldg_stream(packed + q, stream);
-        if (k && q + groups < n) next_word = ldg_stream(packed + q + groups, stream);
+        prefetch(q);
+        begin();
+        if (q + groups < n) prefetch(q + groups);
     }
 
     while (__any_sync(0xffffffffu, live)) {
@@ -197,9 +247,8 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, uin
             q += groups;
             live = q < n;
             if (live) {
-                l = 0; h = (P)ix.total; rem = k; shift = 60; widx = 0;
-                word = next_word;
-                if (k && q + groups < n) next_word = ldg_stream(packed + q + groups, stream);
+                begin();
+                if (q + groups < n) prefetch(q + groups);
             }
         }
         __syncwarp();
@@ -281,36 +330,75 @@ constrain_ranges_kernel(IndexView ix, const uint8_t *__restrict__ sym, const uin
     }
 }
 
+// ---------------------------------------------------------------- K3: suffix table levels
+
+// child[idx] = constrain_range(ACGT[idx & 3], parent[idx >> 2]); an empty parent stays empty
+// (count_kmer returns 0 as soon as the range is empty, msbwt_core.rs:151-153).
+template <bool WIDE>
+__global__ void __launch_bounds__(kCountThreads, kCountMinCtas)
+table_extend_kernel(IndexView ix, const void *__restrict__ parent_v, void *__restrict__ child_v, uint32_t n_child) {
+    using P = typename Pos<WIDE>::type;
+    using E = typename std::conditional<WIDE, ulonglong2, uint2>::type;
+    const E *parent = reinterpret_cast<const E *>(parent_v);
+    E *child = reinterpret_cast<E *>(child_v);
+    __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
+    const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
+    const uint64_t keep = policy_evict_last();
+    const uint32_t sub = threadIdx.x & (kLanesPerBlock - 1);
+    const uint32_t groups = gridDim.x * kGroupsPerCta;
+    const uint32_t g = blockIdx.x * kGroupsPerCta + (threadIdx.x / kLanesPerBlock);
+    const uint32_t warp_first = g - ((threadIdx.x / kLanesPerBlock) & 7u);
+    for (uint64_t it = 0; warp_first + it * groups < n_child; it++) {
+        const uint64_t i = g + it * groups;
+        bool live = i < n_child;
+        P a = 0, b = 0;
+        if (live) {
+            const E e = parent[i >> 2];
+            a = (P)e.x; b = (P)e.y;
+        }
+        const bool empty = (a == b);
+        const uint32_t sym = (0x5321u >> ((i & 3u) * 4u)) & 7u;  // A,C,G,T = 1,2,3,5
+        group_step<WIDE>(ix, cb, keep, sub, live && !empty, sym, a, b);
+        if (live && sub == 0) {
+            E e;
+            e.x = empty ? 0 : a; e.y = empty ? 0 : b;
+            child[i] = e;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- K4: gather roofline
 
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
-    z += 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {  // murmur3 finaliser
+    x ^= x >> 16; x *= 0x85EBCA6Bu;
+    x ^= x >> 13; x *= 0xC2B2AE35u;
+    return x ^ (x >> 16);
 }
 
 // LANES lanes x 16 B = one granule.  Every group issues independent random granule
-// reads, 4 in flight per lane, and xors what it read into a sink so nothing is elided.
+// reads, 8 in flight per lane, and xors what it read into a sink so nothing is elided.
+// The index stream is a 32-bit hash masked to a power-of-two granule count so that the
+// kernel stays far from issue-bound (a 64-bit modulo here would dominate).
 template <int LANES>
-__global__ void __launch_bounds__(256) gather_kernel(const uint4 *__restrict__ buf, uint64_t n_granules,
-                                                     uint64_t n_gathers, uint64_t seed,
+__global__ void __launch_bounds__(256) gather_kernel(const uint4 *__restrict__ buf, uint32_t granule_mask,
+                                                     uint32_t n_gathers, uint32_t seed,
                                                      uint64_t *__restrict__ sink) {
+    constexpr int kInFlight = 8;
     const uint32_t sub = threadIdx.x % LANES;
-    const uint64_t groups = (uint64_t)gridDim.x * (256 / LANES);
-    const uint64_t g = (uint64_t)blockIdx.x * (256 / LANES) + threadIdx.x / LANES;
+    const uint32_t groups = gridDim.x * (256 / LANES);
+    const uint32_t g = blockIdx.x * (256 / LANES) + threadIdx.x / LANES;
     uint32_t acc = 0;
-    for (uint64_t i = g; i < n_gathers; i += 4 * groups) {
-        uint4 v[4];
+    for (uint32_t i = g; i < n_gathers; i += kInFlight * groups) {
+        uint4 v[kInFlight];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint64_t j = i + (uint64_t)u * groups;
-            const uint64_t gi = mix64(j ^ seed) % n_granules;
+        for (int u = 0; u < kInFlight; u++) {
+            const uint32_t j = i + (uint32_t)u * groups;
+            const uint32_t gi = mix32(j ^ seed) & granule_mask;
             v[u] = make_uint4(0, 0, 0, 0);
-            if (j < n_gathers) v[u] = ldg_plain(buf + gi * LANES + sub);
+            if (j < n_gathers) v[u] = ldg_plain(buf + (size_t)gi * LANES + sub);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+        for (int u = 0; u < kInFlight; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
     }
     if (acc == 0x9E3779B9u) atomicAdd((unsigned long long *)sink, 1ull);  // practically never; defeats DCE
 }
@@ -345,26 +433,27 @@ static bool is_wide(const IndexView &ix) { return ix.n_super > 1 || (ix.total >>
 
 constexpr uint64_t kMaxPerLaunch = 1ull << 30;  // keeps q + groups inside u32
 
-cudaError_t launch_pack_fixed(const uint8_t *d_syms, uint32_t k, uint64_t n, uint64_t *d_packed,
-                              uint32_t *d_status, cudaStream_t st) {
+cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_t k, uint64_t n, uint64_t *d_packed,
+                             uint32_t *d_status, cudaStream_t st) {
+    if (!n) return cudaSuccess;
     const uint32_t words = words_for_k(k);
-    const uint64_t items = n * words;
-    if (!items) return cudaSuccess;
-    const unsigned blocks = (unsigned)((items + 255) / 256);
-    pack_fixed_kernel<<<blocks, 256, 0, st>>>(d_syms, k, n, words, d_packed, d_status);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (is_wide(ix)) pack_seed_kernel<true><<<blocks, 256, 0, st>>>(ix, d_syms, k, n, words, d_packed, d_status);
+    else pack_seed_kernel<false><<<blocks, 256, 0, st>>>(ix, d_syms, k, n, words, d_packed, d_status);
     return cudaGetLastError();
 }
 
 cudaError_t launch_count_packed(int device, const IndexView &ix, const uint64_t *d_packed, uint32_t k,
                                 uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches) {
+    const uint32_t words = words_for_k(k);
     for (uint64_t q0 = 0; q0 < n; q0 += kMaxPerLaunch) {
         const uint32_t m = (uint32_t)((n - q0) < kMaxPerLaunch ? (n - q0) : kMaxPerLaunch);
         if (is_wide(ix)) {
             const unsigned grid = persistent_grid(device, (const void *)count_kmers_packed_kernel<true>, kCountThreads, m, kGroupsPerCta);
-            count_kmers_packed_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_packed + q0, n, k, m, d_out + q0);
+            count_kmers_packed_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_packed + q0, n, words, k, m, d_out + q0);
         } else {
             const unsigned grid = persistent_grid(device, (const void *)count_kmers_packed_kernel<false>, kCountThreads, m, kGroupsPerCta);
-            count_kmers_packed_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_packed + q0, n, k, m, d_out + q0);
+            count_kmers_packed_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_packed + q0, n, words, k, m, d_out + q0);
         }
         if (launches) (*launches)++;
         cudaError_t e = cudaGetLastError();
@@ -372,6 +461,20 @@ cudaError_t launch_count_packed(int device, const IndexView &ix, const uint64_t 
     }
     return cudaSuccess;
 }
+
+cudaError_t launch_table_extend(int device, const IndexView &ix, const void *d_parent, void *d_child,
+                                uint32_t n_child, cudaStream_t st) {
+    if (is_wide(ix)) {
+        const unsigned grid = persistent_grid(device, (const void *)table_extend_kernel<true>, kCountThreads, n_child, kGroupsPerCta);
+        table_extend_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_parent, d_child, n_child);
+    } else {
+        const unsigned grid = persistent_grid(device, (const void *)table_extend_kernel<false>, kCountThreads, n_child, kGroupsPerCta);
+        table_extend_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_parent, d_child, n_child);
+    }
+    return cudaGetLastError();
+}
+
+bool index_is_wide(const IndexView &ix) { return is_wide(ix); }
 
 cudaError_t launch_count_bytes(int device, const IndexView &ix, const uint8_t *d_syms,
                                const uint64_t *d_offsets, uint64_t n, uint64_t *d_out, uint32_t *d_status,
@@ -413,14 +516,17 @@ cudaError_t launch_constrain_ranges(int device, const IndexView &ix, const uint8
 
 cudaError_t launch_gather(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,
                           uint64_t n_gathers, uint64_t seed, uint64_t *d_sink, cudaStream_t st) {
-    const uint64_t n_granules = buf_bytes / granule;
-    if (!n_granules || !n_gathers) return cudaErrorInvalidValue;
+    uint64_t n_granules = buf_bytes / granule;
+    if (!n_granules || !n_gathers || n_gathers >= (1ull << 31)) return cudaErrorInvalidValue;
+    while (n_granules & (n_granules - 1)) n_granules &= n_granules - 1;  // round down to a power of two
+    if (n_granules > (1ull << 31)) n_granules = 1ull << 31;
+    const uint32_t mask = (uint32_t)(n_granules - 1);
     const unsigned grid = (unsigned)sm_count(device) * 8u;
     const uint4 *buf = (const uint4 *)d_buf;
     switch (granule) {
-        case 32: gather_kernel<2><<<grid, 256, 0, st>>>(buf, n_granules, n_gathers, seed, d_sink); break;
-        case 64: gather_kernel<4><<<grid, 256, 0, st>>>(buf, n_granules, n_gathers, seed, d_sink); break;
-        case 128: gather_kernel<8><<<grid, 256, 0, st>>>(buf, n_granules, n_gathers, seed, d_sink); break;
+        case 32: gather_kernel<2><<<grid, 256, 0, st>>>(buf, mask, (uint32_t)n_gathers, (uint32_t)seed, d_sink); break;
+        case 64: gather_kernel<4><<<grid, 256, 0, st>>>(buf, mask, (uint32_t)n_gathers, (uint32_t)seed, d_sink); break;
+        case 128: gather_kernel<8><<<grid, 256, 0, st>>>(buf, mask, (uint32_t)n_gathers, (uint32_t)seed, d_sink); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

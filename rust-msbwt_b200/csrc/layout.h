@@ -45,14 +45,23 @@ constexpr int kMaxSuperInSmem = 64;
 // which lane of a block holds the checkpoint of symbol s (A=1,C=2,G=3,T=5); $/N use `aux`
 __host__ __device__ constexpr int ckpt_lane(int s) { return s == 5 ? 3 : s - 1; }
 
+// Suffix table (the reference author's planned-but-unimplemented `kmer_cache`,
+// src/msbwt_core.rs:133-146, src/rle_bwt.rs:332-346): table[idx] = the BWT range after the
+// first `table_s` backward-search steps, for every ACGT-only suffix; idx = the consumed
+// symbols as base-4 digits (A,C,G,T = 0..3), first consumed symbol most significant.
+// Entries are {u32 l, u32 h} when N < 2^32 (one superblock), {u64 l, u64 h} otherwise.
+constexpr int kMaxTableS = 15;
+
 struct IndexView {
     const uint4 *blocks;     // nblocks * 4 uint4
     const uint32_t *aux;     // nblocks * 2  ($, N checkpoints)
     const uint64_t *cbase;   // n_super * 8
+    const void *table;       // 4^table_s entries, or nullptr
     uint64_t total;          // N
     uint64_t nblocks;        // (N >> 7) + 1
     uint32_t n_super;
     uint32_t sb_shift;
+    uint32_t table_s;        // 0 = no table
 };
 
 }  // namespace msbwt

@@ -90,7 +90,7 @@ def load_library():
     sig = {
         "msbwt_index_create_from_rle": (vp, [vp, u64, ip, i32, ip]),
         "msbwt_index_create_from_npy": (vp, [C.c_char_p, ip, i32, ip]),
-        "msbwt_index_create_ex": (vp, [vp, u64, ip, i32, u32, ip]),
+        "msbwt_index_create_ex": (vp, [vp, u64, ip, i32, u32, i32, ip]),
         "msbwt_index_destroy": (None, [vp]),
         "msbwt_total_size": (u64, [vp]),
         "msbwt_symbol_count": (u64, [vp, C.c_uint8]),
@@ -103,7 +103,8 @@ def load_library():
         "msbwt_constrain_ranges": (i32, [vp, vp, vp, vp, u64, vp, vp]),
         "msbwt_count_kmers_fixed_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
         "msbwt_constrain_ranges_device": (i32, [vp, i32, vp, vp, vp, u64, vp, vp, vp]),
-        "msbwt_packed_words": (u32, [u32]),
+        "msbwt_packed_words": (u32, [vp, u32]),
+        "msbwt_suffix_table_s": (i32, [vp]),
         "msbwt_pack_kmers_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
         "msbwt_count_kmers_packed_device": (i32, [vp, i32, vp, u32, u64, vp, vp]),
         "msbwt_launch_count": (u64, []),
@@ -124,7 +125,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex",
     "msbwt_index_destroy", "msbwt_total_size", "msbwt_symbol_count", "msbwt_start_index",
-    "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_count_kmers",
+    "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_suffix_table_s", "msbwt_count_kmers",
     "msbwt_count_kmers_fixed", "msbwt_constrain_ranges", "msbwt_count_kmers_fixed_device",
     "msbwt_constrain_ranges_device", "msbwt_packed_words", "msbwt_pack_kmers_device",
     "msbwt_count_kmers_packed_device", "msbwt_launch_count", "msbwt_gather_bench", "msbwt_debug_build_image",
@@ -158,12 +159,14 @@ class RleBWT:
     """GPU-resident `RleBWT`.  `devices`: CUDA ordinals to replicate the index on
     (None = the current device); batches are split across them (no collective)."""
 
-    def __init__(self, bin_power: int = 8, devices: list[int] | None = None, superblock_shift: int = 0):
+    def __init__(self, bin_power: int = 8, devices: list[int] | None = None, superblock_shift: int = 0,
+                 suffix_table_s: int = -1):
         # bin_power is accepted for signature parity (src/rle_bwt.rs:309-322); it never
         # changed results in the reference and has no counterpart in the device layout.
         self.bin_power = bin_power
         self._devices = list(devices) if devices else []
         self._sb_shift = superblock_shift
+        self._table_s = suffix_table_s  # -1 auto, 0 none, 1..15 explicit (include/msbwt_gpu.h)
         self._h = None
 
     @classmethod
@@ -205,7 +208,7 @@ class RleBWT:
         a = _u8(bwt)
         err = C.c_int(0)
         devs, nd = self._dev_args()
-        h = L.msbwt_index_create_ex(_p(a), a.size, devs, nd, self._sb_shift, C.byref(err))
+        h = L.msbwt_index_create_ex(_p(a), a.size, devs, nd, self._sb_shift, self._table_s, C.byref(err))
         if not h:
             _check(err.value or ECUDA, "load_vector")
         self._h = h
@@ -294,6 +297,13 @@ class RleBWT:
         _check(load_library().msbwt_constrain_ranges_device(self.handle, slot, d_sym, d_l, d_h, n, d_out_l, d_out_h,
                                                             stream or None), "constrain_ranges_device")
 
+    def packed_words(self, k: int) -> int:
+        return int(load_library().msbwt_packed_words(self.handle, k))
+
+    @property
+    def suffix_table_s(self) -> int:
+        return int(load_library().msbwt_suffix_table_s(self.handle))
+
     @property
     def index_bytes(self) -> int:
         return int(load_library().msbwt_index_bytes(self.handle))
@@ -318,10 +328,6 @@ def debug_build_image(rle, superblock_shift: int = 0) -> tuple[np.ndarray, np.nd
     _check(L.msbwt_debug_build_image(_p(a), a.size, superblock_shift, C.byref(nb), C.byref(ns), _p(blocks), _p(aux),
                                      _p(cbase)), "image")
     return blocks, aux, cbase
-
-
-def packed_words(k: int) -> int:
-    return int(load_library().msbwt_packed_words(k))
 
 
 def launch_count() -> int:

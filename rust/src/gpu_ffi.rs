@@ -18,7 +18,7 @@ pub const MSBWT_ENODEV: c_int = 6;
 extern "C" {
     pub fn msbwt_index_create_from_rle(rle: *const u8, len: u64, devices: *const c_int, ndev: c_int, err: *mut c_int) -> *mut msbwt_index;
     pub fn msbwt_index_create_from_npy(path: *const c_char, devices: *const c_int, ndev: c_int, err: *mut c_int) -> *mut msbwt_index;
-    pub fn msbwt_index_create_ex(rle: *const u8, len: u64, devices: *const c_int, ndev: c_int, superblock_shift: u32, err: *mut c_int) -> *mut msbwt_index;
+    pub fn msbwt_index_create_ex(rle: *const u8, len: u64, devices: *const c_int, ndev: c_int, superblock_shift: u32, suffix_table_s: c_int, err: *mut c_int) -> *mut msbwt_index;
     pub fn msbwt_index_destroy(idx: *mut msbwt_index);
     pub fn msbwt_total_size(idx: *const msbwt_index) -> u64;
     pub fn msbwt_symbol_count(idx: *const msbwt_index, sym: u8) -> u64;
@@ -30,7 +30,8 @@ extern "C" {
     pub fn msbwt_count_kmers_fixed(idx: *const msbwt_index, syms: *const u8, k: u32, n: u64, out: *mut u64) -> c_int;
     pub fn msbwt_constrain_ranges(idx: *const msbwt_index, sym: *const u8, l: *const u64, h: *const u64, n: u64, out_l: *mut u64, out_h: *mut u64) -> c_int;
     pub fn msbwt_count_kmers_fixed_device(idx: *const msbwt_index, slot: c_int, d_syms: *const u8, k: u32, n: u64, d_out: *mut u64, d_status: *mut u32, stream: *mut c_void) -> c_int;
-    pub fn msbwt_packed_words(k: u32) -> u32;
+    pub fn msbwt_packed_words(idx: *const msbwt_index, k: u32) -> u32;
+    pub fn msbwt_suffix_table_s(idx: *const msbwt_index) -> c_int;
     pub fn msbwt_pack_kmers_device(idx: *const msbwt_index, slot: c_int, d_syms: *const u8, k: u32, n: u64, d_packed: *mut u64, d_status: *mut u32, stream: *mut c_void) -> c_int;
     pub fn msbwt_count_kmers_packed_device(idx: *const msbwt_index, slot: c_int, d_packed: *const u64, k: u32, n: u64, d_out: *mut u64, stream: *mut c_void) -> c_int;
     pub fn msbwt_constrain_ranges_device(idx: *const msbwt_index, slot: c_int, d_sym: *const u8, d_l: *const u64, d_h: *const u64, n: u64, d_out_l: *mut u64, d_out_h: *mut u64, stream: *mut c_void) -> c_int;

@@ -157,6 +157,31 @@ def test_random_streams_ranges_and_ragged_kmers(sb_shift):
     assert (g.count_kmers([]) == np.zeros(0, np.uint64)).all()
 
 
+@pytest.mark.parametrize("table_s", [0, 1, 2, 3, 5, 7])
+def test_suffix_table_depths_are_bit_exact(table_s):
+    """The suffix table (the reference's planned kmer_cache, msbwt_core.rs:133-146) must not change a
+    single count: k < s, k == s, k > s, k-mers with $ / N inside and outside the last s symbols."""
+    rng = np.random.default_rng(77)
+    reads = rng.choice(np.array([1, 2, 3, 4, 5], dtype=np.uint8), size=(300, 40), p=[0.28, 0.22, 0.22, 0.03, 0.25])
+    from harness import bwt_build
+    rle, _ = bwt_build.build_rle_bwt(torch.from_numpy(reads).cuda())
+    for sb in (0, 2):
+        g, o = both(rle.cpu().numpy(), suffix_table_s=table_s, superblock_shift=sb)
+        assert g.suffix_table_s == table_s
+        for k in (1, 2, 3, 4, 5, 6, 7, 8, 9, 22, 30):
+            a = reads[rng.integers(0, 300, 400)][:, 5:5 + k] if k <= 30 else None
+            b = rng.integers(0, 6, (300, k)).astype(np.uint8)
+            q = np.concatenate([a, b, rng.choice(np.array([1, 2, 3, 5], dtype=np.uint8), (300, k))])
+            assert (g.count_kmers_fixed(q, k) == o.count_kmers_fixed(q, k)).all(), (table_s, sb, k)
+        kmers = [rng.integers(0, 6, int(rng.integers(0, 12))).astype(np.uint8) for _ in range(500)]
+        assert (g.count_kmers(kmers) == o.count_kmers(kmers)).all()
+
+
+def test_automatic_suffix_table_is_on_for_real_sizes(midsize):
+    reads, g, o = midsize
+    assert g.suffix_table_s == 8  # ceil(log4(2.02e6 / 32))
+
+
 def test_empty_bwt():
     g, o = both(np.zeros(0, np.uint8))
     assert g.get_total_size() == 0
