@@ -146,12 +146,9 @@ def cpu_reference_leg(orc, q_host, k, threads, target_s, label):
     return m / dt, m, counts
 
 
-def run_reference(args, cfg):
-    """--impl reference: the reference's own CPU algorithm (oracle port; the Rust crate cannot be
-    built in this image) on this box's host cores, all threads, bounded samples of the same workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def reference_measure(args, cfg):
+    """The reference's own CPU algorithm (oracle port; the Rust crate cannot be built in this image)
+    on this box's host cores, all threads, bounded samples of the workload."""
     import torch
     from oracle import oracle as O
     dev = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")  # GPU only manufactures the inputs
@@ -178,58 +175,55 @@ def run_reference(args, cfg):
             times.append(dt)
     total_t = sum(times)
     value = per_step * len(times) / total_t
-    sample = f"{per_step} of the workload's {n} queries per step"
+    return {"value": value, "ms_per_step": 1e3 * total_t / len(times), "cores": cores, "per_step": per_step,
+            "n": n, "total": total, "k": k}
+
+
+def run_reference(args, cfgs):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = reference_measure(args, cfgs[0])
+    sample = f"{r['per_step']} of the workload's {r['n']} queries per step"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(times),
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": cfg["name"], "bwt_symbols": total, "k": k, "queries_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": cfgs[0]["name"], "bwt_symbols": r["total"], "k": r["k"],
+                   "queries_per_step": r["per_step"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    for extra in cfgs[1:]:
+        x = reference_measure(args, extra)
+        line.setdefault("other_workloads", []).append(
+            {"workload": extra["name"], "value": x["value"], "unit": UNIT, "cores": x["cores"],
+             "sample": f"{x['per_step']} of {x['n']} queries per step"})
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args, cfg):
+def measure_ours(args, cfg, ctx, primary: bool):
+    """One workload on this rank's GPU: kernel-only `value`, end-to-end C-ABI figure, parity check,
+    CPU baseline and roofline accounting (rank 0)."""
+    import ctypes
+
     import numpy as np
     import torch
 
     import rust_msbwt_b200 as M
     from oracle import oracle as O
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    rank, world, local, dev = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"]
+    barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
     k = cfg["k"]
     rle_host, total, queries = build_workload(cfg, dev, rank)
     n = queries.shape[0]
     t0 = time.time()
     bwt = M.RleBWT.new(devices=[local])
     bwt.load_vector(rle_host)
-    log(f"[rank {rank}] index resident: {bwt.index_bytes / 1e6:.1f} MB in {time.time() - t0:.1f}s")
+    log(f"[rank {rank}] index resident: {bwt.index_bytes / 1e6:.1f} MB (suffix table s={bwt.suffix_table_s}) "
+        f"in {time.time() - t0:.1f}s")
 
     stream = torch.cuda.current_stream().cuda_stream
     words = bwt.packed_words(k)        # symbol words + seed word(s)
@@ -257,7 +251,7 @@ def run_ours(args, cfg):
     if rank == 0:
         sampler.start()
     launches0 = M.launch_count()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
@@ -274,6 +268,7 @@ def run_ours(args, cfg):
     assert int(d_status.item()) == 0
     value = world * n * args.steps / (total_ms / 1e3)
     checksum = int(d_out.sum().item())
+    del flush
 
     # ---- e2e: the drop-in C-ABI call with HOST buffers (pinned), H2D + D2H inside ----
     q_pinned = torch.empty((n, k), dtype=torch.uint8, pin_memory=True)
@@ -281,7 +276,6 @@ def run_ours(args, cfg):
     out_pinned = torch.empty(n, dtype=torch.int64, pin_memory=True)
     q_np, out_np = q_pinned.numpy(), out_pinned.numpy().view(np.uint64)
     lib = M.load_library()
-    import ctypes
 
     def e2e_step():
         rc = lib.msbwt_count_kmers_fixed(bwt.handle, ctypes.c_void_p(q_np.ctypes.data), k, n,
@@ -299,9 +293,19 @@ def run_ours(args, cfg):
     e2e_value = world * n * args.steps / e2e_s
     assert int(out_np.astype(np.int64).sum()) == checksum, "host-path and device-path results differ"
 
+    res = {
+        "value": value, "ms_per_step": total_ms / args.steps,
+        "config": {"workload": cfg["name"], "bwt_symbols": total, "index_bytes": bwt.index_bytes, "k": k,
+                   "suffix_table_s": table_s, "kernel_lanes_per_query": bwt.kernel_lanes, "queries_per_gpu_per_step": n,
+                   "parallelism": f"replica x{world}, query batch sharded",
+                   "l2": "L2 flushed (512 MB fill) between timed iterations; query batch (n*k bytes) exceeds L2",
+                   "seeds": "torch Philox 0x5EED0001.. (harness/synth.py)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * k, "d2h_bytes_per_step": n * 8,
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "checksum": checksum,
+    }
+
     # ---- parity + CPU baseline + algorithmic bytes (rank 0, bounded samples) ----
-    cpu_baseline = roofline = None
-    extra = {}
     if rank == 0:
         q_host = q_np
         orc = O.RleBWT()
@@ -309,19 +313,21 @@ def run_ours(args, cfg):
         cores = os.cpu_count() or 1
         got = d_out.cpu().numpy().view(np.uint64)
         if world == 1:
-            v1, m1, c1 = cpu_reference_leg(orc, q_host, k, 1, 8.0, "single thread")
+            tgt = 8.0 if primary else 4.0
+            v1, m1, c1 = cpu_reference_leg(orc, q_host, k, 1, tgt, "single thread")
             assert (got[:m1] == c1).all(), "GPU counts differ from the CPU oracle"
-            vN, mN, cN = cpu_reference_leg(orc, q_host, k, cores, 8.0, "all-core static split")
+            vN, mN, cN = cpu_reference_leg(orc, q_host, k, cores, tgt, "all-core static split")
             assert (got[:mN] == cN).all(), "GPU counts differ from the CPU oracle"
-            cpu_baseline = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
-                            "sample": f"first {m1} of {n} queries, single thread (the reference's loop)",
-                            "allcore": {"value": vN, "cores": cores, "sample": f"first {mN} of {n} queries"},
-                            "parity_checked_queries": max(m1, mN)}
+            res["cpu_baseline"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                                   "sample": f"first {m1} of {n} queries, single thread (the reference's loop)",
+                                   "allcore": {"value": vN, "cores": cores, "sample": f"first {mN} of {n} queries"},
+                                   "parity_checked_queries": max(m1, mN)}
         else:
             m = min(n, 200_000)
             assert (got[:m] == orc.count_kmers_fixed(q_host[:m], k, threads=cores)).all()
-        # algorithmic bytes: steps the reference executes x distinct 64-B index blocks per step
-        # with the suffix table: the first table_s steps of an ACGT-suffixed k-mer are one 32-B table
+            res["cpu_baseline"] = None
+        # algorithmic bytes: steps the reference executes x distinct 64-B index blocks per step;
+        # with the suffix table the first table_s steps of an ACGT-suffixed k-mer are one 32-B table
         # sector instead of table_s block steps; the no-table figure is reported beside it
         ms = min(n, 1_000_000)
         steps0, two0 = orc.count_kmers_stats(q_host[:ms], k, BLOCK_SHIFT)
@@ -329,59 +335,107 @@ def run_ours(args, cfg):
         packed_q = 8 * words
         bytes_per_query = ((steps + two) * BLOCK_BYTES + hits * 32) / ms + packed_q + 8
         bytes_per_query_no_table = (steps0 + two0) * BLOCK_BYTES / ms + packed_q + 8
+        accesses_per_query = (steps + two + hits) / ms
         peak, peak_src = measured_peak_gbs()
         kern_s = statistics.mean(kern_ms) / 1e3
         achieved = bytes_per_query * n / kern_s / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "count_kmers_packed_kernel", "kernel_ms": 1e3 * kern_s,
-                    "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": steps / ms,
-                    "two_block_step_share": two / max(1, steps), "suffix_table_s": table_s,
-                    "table_hits_per_query": hits / ms,
-                    "no_table": {"algorithmic_bytes_per_query": bytes_per_query_no_table,
-                                 "mean_steps_per_query": steps0 / ms,
-                                 "achieved_if_counted_without_table": bytes_per_query_no_table * n / kern_s / 1e9}, "peak_source": peak_src,
-                    "stats_sample": f"first {ms} of {n} queries (oracle replay)"}
-        # gather microbenchmark: what random 128-B reads sustain on this box (K4)
+        res["roofline"] = {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "count_kmers_packed_kernel", "kernel_ms": 1e3 * kern_s,
+            "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": steps / ms,
+            "two_block_step_share": two / max(1, steps), "suffix_table_s": table_s,
+            "table_hits_per_query": hits / ms, "index_accesses_per_query": accesses_per_query,
+            "index_accesses_per_s": accesses_per_query * n / kern_s,
+            "no_table": {"algorithmic_bytes_per_query": bytes_per_query_no_table,
+                         "mean_steps_per_query": steps0 / ms,
+                         "achieved_if_counted_without_table": bytes_per_query_no_table * n / kern_s / 1e9},
+            "peak_source": peak_src, "stats_sample": f"first {ms} of {n} queries (oracle replay)"}
+        res["kernel_share_of_step"] = statistics.mean(kern_ms) / statistics.mean(step_ms)
+    del bwt, d_packed, d_out, queries, q_pinned, out_pinned
+    torch.cuda.empty_cache()
+    return res
+
+
+def gather_roofline(local, dev):
+    """K4: what independent random 32/64/128-B reads sustain on this box (2 GiB buffer, DRAM)."""
+    import torch
+
+    import rust_msbwt_b200 as M
+    stream = torch.cuda.current_stream().cuda_stream
+    gb = torch.empty(2 << 30, dtype=torch.uint8, device=dev)
+    sink = torch.zeros(1, dtype=torch.int64, device=dev)
+    res = {}
+    for gran in (32, 64, 128):
+        ng = 1 << 27
+        best = None
+        for it in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            M.gather_bench(local, gb.data_ptr(), gb.numel(), gran, ng, 1234 + it, sink.data_ptr(), stream)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        res[str(gran)] = {"gb_per_s": ng * gran / (best / 1e3) / 1e9, "reads_per_s": ng / (best / 1e3)}
+    del gb
+    return res
+
+
+def run_ours(args, cfgs):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = dict(rank=rank, world=world, local=local, dev=dev, barrier=barrier, max_over_ranks=max_over_ranks)
+    main_res = measure_ours(args, cfgs[0], ctx, primary=True)
+    others = [measure_ours(args, c, ctx, primary=False) for c in cfgs[1:]]
+    if rank == 0:
+        gather = None
         try:
-            gb = torch.empty(2 << 30, dtype=torch.uint8, device=dev)
-            sink = torch.zeros(1, dtype=torch.int64, device=dev)
-            res = {}
-            for gran in (32, 64, 128):
-                ng = 1 << 26
-                for it in range(3):
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    M.gather_bench(local, gb.data_ptr(), gb.numel(), gran, ng, 1234 + it, sink.data_ptr(), stream)
-                    e1.record()
-                    torch.cuda.synchronize()
-                res[gran] = ng * gran / (e0.elapsed_time(e1) / 1e3) / 1e9
-            roofline["gather_gbs"] = {str(g): v for g, v in res.items()}
-            roofline["frac_of_gather128"] = achieved / res[128]
-            del gb
+            gather = gather_roofline(local, dev)
         except Exception as e:  # measurement aid only
             log("gather microbench failed:", e)
-        extra = {"kernel_share_of_step": statistics.mean(kern_ms) / statistics.mean(step_ms)}
-
-    if rank == 0:
+        for r in [main_res] + others:
+            rf = r.get("roofline")
+            if rf and gather:
+                rf["gather_gbs"] = {g: v["gb_per_s"] for g, v in gather.items()}
+                rf["gather_reads_per_s"] = {g: v["reads_per_s"] for g, v in gather.items()}
+                rf["frac_of_gather64_access_rate"] = rf["index_accesses_per_s"] / gather["64"]["reads_per_s"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": cfg["name"], "bwt_symbols": total, "index_bytes": bwt.index_bytes, "k": k,
-                       "suffix_table_s": table_s,
-                       "queries_per_gpu_per_step": n, "parallelism": f"replica x{world}, query batch sharded",
-                       "l2": "L2 flushed (512 MB fill) between timed iterations; query batch (n*k bytes) exceeds L2",
-                       "seeds": "torch Philox 0x5EED0001.. (harness/synth.py)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * k, "d2h_bytes_per_step": n * 8,
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
-            "wall_s_timed_region": wall,
-            "checksum": checksum,
         }
-        line.update(extra)
+        for key in ("config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "wall_s_timed_region",
+                    "checksum", "kernel_share_of_step"):
+            line[key] = main_res.get(key)
+        if others:
+            line["other_workloads"] = [
+                {key: r.get(key) for key in ("value", "ms_per_step", "config", "e2e", "gpu_launches", "roofline",
+                                             "cpu_baseline", "checksum")} for r in others]
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -394,14 +448,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default=os.environ.get("MSBWT_BENCH_WORKLOAD", "cfg2"))
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["default"],
+                    default=os.environ.get("MSBWT_BENCH_WORKLOAD", "default"),
+                    help="default = configs[1] as the bench line, configs[2] (HBM-resident index) nested beside it")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    cfg = WORKLOADS[args.workload]
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)
+    cfgs = [WORKLOADS["cfg2"], WORKLOADS["cfg3"]] if args.workload == "default" else [WORKLOADS[args.workload]]
     if args.impl == "reference":
-        run_reference(args, cfg)
+        run_reference(args, cfgs)
     else:
-        run_ours(args, cfg)
+        run_ours(args, cfgs)
 
 
 if __name__ == "__main__":

@@ -89,6 +89,9 @@ int msbwt_device_count(const msbwt_index *idx);
 int msbwt_device_ordinal(const msbwt_index *idx, int slot);
 uint64_t msbwt_index_bytes(const msbwt_index *idx); /* device bytes per replica, suffix table included */
 int msbwt_suffix_table_s(const msbwt_index *idx);     /* suffix table depth in use (0 = none) */
+/* lanes per query of the search kernel chosen for this index: 1 = one thread per query (index
+ * L2-resident), 2 = a lane pair per query (index in HBM); MSBWT_LANES=1|2 overrides at create */
+int msbwt_kernel_lanes(const msbwt_index *idx);
 
 /* ---- queries from HOST buffers (the drop-in calls) ---- */
 
@@ -147,6 +150,11 @@ uint64_t msbwt_launch_count(void);
  * fits in `d_buf` (buf_bytes, device memory) on `stream`. */
 int msbwt_gather_bench(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,
                        uint64_t n_gathers, uint64_t seed, uint64_t *d_sink, void *stream);
+
+/* cudaLimitMaxL2FetchGranularity of `device` (bytes, 0 = query only).  Returns the value in
+ * effect afterwards, or a negative msbwt_status.  Measurement aid: on B200 an L2 miss of a
+ * 32/64-byte request fills a whole 128-byte line by default. */
+int msbwt_l2_fetch_granularity(int device, int bytes);
 
 /* ---- inspection: the host-side block image (no device needed) ----
  * Builds the layout.h block image of `rle` exactly as create does and copies it out so

@@ -17,6 +17,7 @@ from .rle_bwt import (  # noqa: F401
     debug_build_image,
     gather_bench,
     launch_count,
+    l2_fetch_granularity,
     EXPORTED_SYMBOLS,
     library_path,
     load_library,

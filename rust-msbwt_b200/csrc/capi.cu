@@ -69,6 +69,7 @@ struct Replica {
     uint4 *d_blocks = nullptr;
     uint32_t *d_aux = nullptr;
     void *d_table = nullptr;
+    int lanes = 1;           // kernel mapping: 1 = thread per query, 2 = lane pair per query (kernels.cu)
     uint64_t *d_cbase = nullptr;
     IndexView view{};
     std::mutex mu;
@@ -186,6 +187,15 @@ int pick_table_s(uint64_t total, int requested) {
     return s;
 }
 
+// Kernel mapping (kernels.cu): one thread per query while blocks + table are (mostly) L2-resident,
+// a lane pair per query -- one coalesced 64-byte request per block -- once they live in HBM.
+int pick_lanes(int device, uint64_t index_bytes) {
+    if (const char *env = getenv("MSBWT_LANES")) return atoi(env) == 2 ? 2 : 1;
+    int l2 = 0;
+    if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device) != cudaSuccess || l2 <= 0) l2 = 96 << 20;
+    return index_bytes > 2ull * (uint64_t)l2 ? 2 : 1;
+}
+
 int build_suffix_table(msbwt_index *idx, Replica &rep, int s) {
     if (s <= 0) return MSBWT_OK;
     DeviceGuard guard(rep.device);
@@ -237,6 +247,7 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
         for (auto &rep : idx->reps) {
             rc = build_suffix_table(idx.get(), *rep, s);
             if (rc != MSBWT_OK) break;
+            rep->lanes = pick_lanes(rep->device, idx->bytes_per_replica);
         }
     }
     if (err) *err = rc;
@@ -301,6 +312,7 @@ extern "C" int msbwt_device_ordinal(const msbwt_index *idx, int slot) {
 }
 extern "C" uint64_t msbwt_index_bytes(const msbwt_index *idx) { return idx ? idx->bytes_per_replica : 0; }
 extern "C" int msbwt_suffix_table_s(const msbwt_index *idx) { return idx ? (int)idx->table_s : 0; }
+extern "C" int msbwt_kernel_lanes(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->lanes : 0; }
 extern "C" uint64_t msbwt_launch_count(void) { return g_launches.load(); }
 extern "C" const char *msbwt_last_error(void) { return g_last_error.c_str(); }
 extern "C" int msbwt_abi_version(void) { return MSBWT_ABI_VERSION; }
@@ -331,7 +343,7 @@ extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, 
     CU_TRY(cudaMemsetAsync(flag, 0, sizeof(uint32_t), st));
     CU_TRY(launch_pack_seed(rep.view, d_syms, k, n, rep.dev_packed.as<uint64_t>(), flag, st));
     g_launches++;
-    CU_TRY(launch_count_packed(rep.device, rep.view, rep.dev_packed.as<uint64_t>(), k, n, d_out, st, &g_call_launches));
+    CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, rep.dev_packed.as<uint64_t>(), k, n, d_out, st, &g_call_launches));
     flush_launches();
     return MSBWT_OK;
 }
@@ -359,7 +371,7 @@ extern "C" int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot,
     if (!n) return MSBWT_OK;
     Replica &rep = *idx->reps[slot];
     DeviceGuard guard(rep.device);
-    CU_TRY(launch_count_packed(rep.device, rep.view, d_packed, k, n, d_out, (cudaStream_t)stream, &g_call_launches));
+    CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, d_packed, k, n, d_out, (cudaStream_t)stream, &g_call_launches));
     flush_launches();
     return MSBWT_OK;
 }
@@ -423,7 +435,7 @@ extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *sy
             CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(),
                                     rep.d_status + (c & 1), ln.stream));
             g_launches++;
-            CU_TRY(launch_count_packed(rep.device, rep.view, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
+            CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
                                        ln.stream, &g_call_launches));
             flush_launches();
             CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
@@ -562,6 +574,18 @@ extern "C" int msbwt_constrain_ranges(const msbwt_index *idx, const uint8_t *sym
         CU_TRY(cudaStreamSynchronize(rep->lane[1].stream));
     }
     return MSBWT_OK;
+}
+
+extern "C" int msbwt_l2_fetch_granularity(int device, int bytes) {
+    DeviceGuard guard(device);
+    if (bytes > 0) {
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+        if (e != cudaSuccess) return -fail(MSBWT_ECUDA, std::string("cudaDeviceSetLimit: ") + cudaGetErrorString(e));
+    }
+    size_t v = 0;
+    cudaError_t e = cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity);
+    if (e != cudaSuccess) return -fail(MSBWT_ECUDA, std::string("cudaDeviceGetLimit: ") + cudaGetErrorString(e));
+    return (int)v;
 }
 
 // ================================================================ inspection

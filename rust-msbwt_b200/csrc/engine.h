@@ -12,8 +12,9 @@
 namespace msbwt {
 
 constexpr int kCountThreads = 256;
-constexpr int kCountMinCtasWide = 6;  // u64 positions need ~40 registers
-constexpr int kCountMinCtas = 8;  // 8 x 256 threads = a full SM of warps; caps the kernels at 32 registers
+// resident CTAs per SM the kernels are compiled for (register budget = 65536 / (256 * min_ctas)):
+// one thread per query keeps two 64-byte blocks (32 registers) in flight, a lane pair half of that
+constexpr int min_ctas(bool wide, int lanes) { return lanes == 2 ? (wide ? 4 : 6) : (wide ? 3 : 4); }
 
 inline uint32_t words_for_k(uint32_t k) { return k ? (k + kSymsPerWord - 1) / kSymsPerWord : 1; }
 
@@ -43,7 +44,7 @@ bool index_is_wide(const IndexView &ix);
 // u64 words per query in the packed layout: symbol words + seed word(s)
 inline uint32_t packed_words_for(const IndexView &ix, uint32_t k) { return words_for_k(k) + (index_is_wide(ix) ? 2u : 1u); }
 // `launches` (optional) is incremented once per kernel launch issued
-cudaError_t launch_count_packed(int device, const IndexView &ix, const uint64_t *d_packed, uint32_t k,
+cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, const uint64_t *d_packed, uint32_t k,
                                 uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches);
 cudaError_t launch_count_bytes(int device, const IndexView &ix, const uint8_t *d_syms,
                                const uint64_t *d_offsets, uint64_t n, uint64_t *d_out, uint32_t *d_status,

@@ -2,14 +2,21 @@
 //
 // Replaces the reference's hot loop: BWT::count_kmer (src/msbwt_core.rs:125-161)
 // calling RleBWT::constrain_range (src/rle_bwt.rs:202-287) once per symbol.
-// Integer-only, random-gather (HBM sector / L2) bound; no tensor cores (nothing here
-// is a dense contraction).  See layout.h for the block format.
+// Integer-only, random-gather (HBM access rate / L2) bound; no tensor cores (nothing
+// here is a dense contraction).  See layout.h for the block format.
 //
-// Work mapping: 4 adjacent lanes form a group that owns one query at a time; the group
-// fetches a 64-byte block with one 128-bit ld.global.nc per lane, each lane matches its
-// 32 symbols against the query symbol (3 LOP3 + POPC), and two shuffle-xor steps sum
-// the lanes (the l and h boundaries share the reduction, 16 bits each).  A warp
-// therefore advances 8 queries per instruction.
+// Two work mappings over the same block image (template parameter LANES):
+//   LANES = 1  one thread per query: the thread reads both 32-byte halves of a block with
+//              two 256-bit ld.global.nc, matches 4 x 32 symbols (3 LOP3 each), masks and
+//              popcounts.  No shuffles.  ~4 warp instructions per query-step: the mapping
+//              for an L2-resident index, where issue slots are the limit.
+//   LANES = 2  a lane pair per query: each lane reads ONE half (one coalesced 64-byte
+//              request per block -- HBM serves ~39 G random requests/s whatever their
+//              size, so one request per rank matters more than instruction count), counts
+//              its 64 symbols, and three shuffles combine the pair.
+// In both, a lane (pair) whose k-mer ends refills itself from its own query stream, so
+// every lane of a warp stays busy.  (v1-v3 used 8- then 4-lane groups per query; ncu
+// showed them issue-bound at ~12 warp instructions per query-step -- profiles/.)
 #include <type_traits>
 
 #include "engine.h"
@@ -18,23 +25,21 @@ namespace msbwt {
 
 // ---------------------------------------------------------------- device helpers
 
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
 
-// index block chunk: read-only path, no L1 allocation, keep in L2
-__device__ __forceinline__ uint4 ldg_index(const uint4 *p, uint64_t pol) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p), "l"(pol));
+struct Half { uint32_t w[8]; };  // 32 bytes = one sector of a block
+
+// half an index block: read-only path, no L1 allocation, evict-last in L2 (256-bit load)
+__device__ __forceinline__ Half ldg_index256(const void *p) {
+    Half r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                   "=r"(r.w[7])
+                 : "l"(p));
     return r;
 }
 __device__ __forceinline__ uint4 ldg_plain(const uint4 *p) {
@@ -60,14 +65,6 @@ __device__ __forceinline__ uint32_t below_mask(int nbits) {
     int w = max(nbits, 0);
     asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0), "r"(w));
     return m;
-}
-
-// Occurrences, within this lane's 32 symbols, of the symbol selected by the
-// (x0,x1,x2) plane-inversion masks, restricted to block offsets < p.
-__device__ __forceinline__ uint32_t lane_count(const uint4 &c, uint32_t x0, uint32_t x1, uint32_t x2,
-                                               uint32_t p, uint32_t sub) {
-    uint32_t m = (c.y ^ x0) & (c.z ^ x1) & (c.w ^ x2);
-    return __popc(m & below_mask((int)p - (int)(sub << 5)));
 }
 
 template <bool WIDE> struct Pos { using type = uint32_t; };
@@ -101,36 +98,84 @@ __device__ __forceinline__ CBase<WIDE> stage_cbase(const IndexView &ix, uint64_t
     }
 }
 
-// One constrain_range for the 4-lane group this thread belongs to.  All 32 lanes of
-// the warp must call it together (the shuffles are warp-wide, segmented by 4).
-// `live` gates the loads; dead groups compute garbage that the caller discards.
-template <bool WIDE>
-__device__ __forceinline__ void group_step(const IndexView &ix, const CBase<WIDE> &cb, uint64_t keep, uint32_t sub,
-                                           bool live, uint32_t sym, typename Pos<WIDE>::type &l,
-                                           typename Pos<WIDE>::type &h) {
+// the 64 match bits of one half for the symbol selected by the plane-inversion masks
+__device__ __forceinline__ void match_half(const Half &v, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t &m0,
+                                           uint32_t &m1) {
+    m0 = (v.w[2] ^ x0) & (v.w[4] ^ x1) & (v.w[6] ^ x2);
+    m1 = (v.w[3] ^ x0) & (v.w[5] ^ x1) & (v.w[7] ^ x2);
+}
+
+// occurrences among 64 match bits at half offsets < p (p may be <= 0 or >= 64)
+__device__ __forceinline__ uint32_t count_below64(uint32_t m0, uint32_t m1, int p) {
+    return __popc(m0 & below_mask(p)) + __popc(m1 & below_mask(p - 32));
+}
+
+// One constrain_range: [l,h) -> [C[sym]+rank(sym,l), C[sym]+rank(sym,h)).
+// LANES == 1: the calling thread does all of it.  LANES == 2: the two lanes of a pair call
+// it together with identical (sym, l, h); `half` = lane & 1, `pair_mask` names the pair.
+template <bool WIDE, int LANES>
+__device__ __forceinline__ void rank_step(const IndexView &ix, const CBase<WIDE> &cb, uint32_t sym,
+                                          typename Pos<WIDE>::type &l, typename Pos<WIDE>::type &h,
+                                          uint32_t half = 0, uint32_t pair_mask = 0) {
     using P = typename Pos<WIDE>::type;
     const P bl = l >> kBlockShift, bh = h >> kBlockShift;
-    uint4 cl = make_uint4(0, 0, 0, 0), ch;
-    if (live) cl = ldg_index(ix.blocks + (size_t)bl * kLanesPerBlock + sub, keep);
-    ch = cl;
-    if (live && bh != bl) ch = ldg_index(ix.blocks + (size_t)bh * kLanesPerBlock + sub, keep);
-
-    const uint32_t x0 = (sym & 1u) ? 0u : ~0u, x1 = (sym & 2u) ? 0u : ~0u, x2 = (sym & 4u) ? 0u : ~0u;
-    uint32_t cnt = lane_count(cl, x0, x1, x2, (uint32_t)l & (kBlockSyms - 1), sub) |
-                   (lane_count(ch, x0, x1, x2, (uint32_t)h & (kBlockSyms - 1), sub) << 16);
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
-    const uint32_t src = (sym - 1u - (sym >> 2)) & 3u;  // ckpt_lane(sym) for A,C,G,T
-    uint32_t hl = __shfl_sync(0xffffffffu, cl.x, src, kLanesPerBlock);
-    uint32_t hh = __shfl_sync(0xffffffffu, ch.x, src, kLanesPerBlock);
-    if ((0x11u >> sym) & 1u) {  // $ or N: checkpoints live in the side array
-        if (live) {
-            hl = __ldg(ix.aux + (size_t)bl * 2 + (sym >> 2));
-            hh = __ldg(ix.aux + (size_t)bh * 2 + (sym >> 2));
+    const bool two = bh != bl;
+    const char *base = reinterpret_cast<const char *>(ix.blocks);
+    const uint32_t x0 = (sym & 1u) - 1u, x1 = ((sym >> 1) & 1u) - 1u, x2 = ((sym >> 2) & 1u) - 1u;  // 0 or ~0
+    const uint32_t slot = (sym - 1u - (sym >> 2)) & 3u;  // ckpt_slot(sym) for A,C,G,T
+    const int pl = (int)((uint32_t)l & (kBlockSyms - 1)), ph = (int)((uint32_t)h & (kBlockSyms - 1));
+    uint32_t ckl, ckh, cl, ch;
+    if constexpr (LANES == 1) {
+        // issue every load before the first use: up to four 32-byte sectors in flight per thread
+        const Half l0 = ldg_index256(base + (size_t)bl * kBlockBytes);
+        const Half l1 = ldg_index256(base + (size_t)bl * kBlockBytes + 32);
+        Half h0, h1;
+        if (two) {
+            h0 = ldg_index256(base + (size_t)bh * kBlockBytes);
+            h1 = ldg_index256(base + (size_t)bh * kBlockBytes + 32);
         }
+        uint32_t ml[4], mh[4];
+        match_half(l0, x0, x1, x2, ml[0], ml[1]);
+        match_half(l1, x0, x1, x2, ml[2], ml[3]);
+        const uint32_t lo = (slot & 1u) ? l0.w[1] : l0.w[0], hi = (slot & 1u) ? l1.w[1] : l1.w[0];
+        ckl = (slot & 2u) ? hi : lo;
+        ckh = ckl;
+#pragma unroll
+        for (int j = 0; j < 4; j++) mh[j] = ml[j];
+        if (two) {
+            match_half(h0, x0, x1, x2, mh[0], mh[1]);
+            match_half(h1, x0, x1, x2, mh[2], mh[3]);
+            const uint32_t lo2 = (slot & 1u) ? h0.w[1] : h0.w[0], hi2 = (slot & 1u) ? h1.w[1] : h1.w[0];
+            ckh = (slot & 2u) ? hi2 : lo2;
+        }
+        cl = count_below64(ml[0], ml[1], pl) + count_below64(ml[2], ml[3], pl - 64);
+        ch = count_below64(mh[0], mh[1], ph) + count_below64(mh[2], mh[3], ph - 64);
+    } else {
+        const Half a = ldg_index256(base + (size_t)bl * kBlockBytes + half * 32);
+        Half b;
+        if (two) b = ldg_index256(base + (size_t)bh * kBlockBytes + half * 32);
+        uint32_t ml0, ml1, mh0, mh1;
+        match_half(a, x0, x1, x2, ml0, ml1);
+        uint32_t cand_l = (slot & 1u) ? a.w[1] : a.w[0], cand_h = cand_l;
+        mh0 = ml0; mh1 = ml1;
+        if (two) {
+            match_half(b, x0, x1, x2, mh0, mh1);
+            cand_h = (slot & 1u) ? b.w[1] : b.w[0];
+        }
+        const int off = (int)half * 64;
+        uint32_t cnt = count_below64(ml0, ml1, pl - off) | (count_below64(mh0, mh1, ph - off) << 16);
+        cnt += __shfl_xor_sync(pair_mask, cnt, 1);
+        ckl = __shfl_sync(pair_mask, cand_l, slot >> 1, 2);  // the half that owns this symbol's checkpoint
+        ckh = __shfl_sync(pair_mask, cand_h, slot >> 1, 2);
+        cl = cnt & 0xffffu;
+        ch = cnt >> 16;
     }
-    l = cb.at(bl, sym) + hl + (cnt & 0xffffu);
-    h = cb.at(bh, sym) + hh + (cnt >> 16);
+    if ((0x11u >> sym) & 1u) {  // $ or N: checkpoints live in the side array
+        ckl = __ldg(ix.aux + (size_t)bl * 2 + (sym >> 2));
+        ckh = __ldg(ix.aux + (size_t)bh * 2 + (sym >> 2));
+    }
+    l = cb.at(bl, sym) + ckl + cl;
+    h = cb.at(bh, sym) + ckh + ch;
 }
 
 // ---------------------------------------------------------------- K0: pack + validate + seed
@@ -189,26 +234,26 @@ __global__ void pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms,
 
 // ---------------------------------------------------------------- K1: count_kmers
 
-constexpr int kGroupsPerCta = kCountThreads / kLanesPerBlock;
-
-// Persistent kernel: every 4-lane group owns a stream of queries (q, q+G, q+2G, ...)
-// and refills itself as soon as its current query is finished, so a warp's eight
-// groups never wait for each other's k-mers to end.  The next query's first word and
-// seed are loaded one query ahead so a refill never exposes memory latency.
-// `packed`/`out` are already offset to this launch's first query; `stride` is the
-// word-major stride of `packed`, `words` the number of symbol words per query.
-template <bool WIDE>
-__global__ void __launch_bounds__(kCountThreads, WIDE ? kCountMinCtasWide : kCountMinCtas)
+// Persistent kernel: every thread (LANES = 1) or lane pair (LANES = 2) owns a stream of
+// queries (q, q+T, q+2T, ...) and refills itself as soon as its current k-mer is finished.
+// The next query's first word and seed are loaded one query ahead so a refill never exposes
+// memory latency.  `packed`/`out` are already offset to this launch's first query; `stride`
+// is the word-major stride of `packed`, `words` the number of symbol words per query.
+template <bool WIDE, int LANES>
+__global__ void __launch_bounds__(kCountThreads, min_ctas(WIDE, LANES))
 count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, uint64_t stride, uint32_t words,
                           uint32_t k, uint32_t n, uint64_t *__restrict__ out) {
     using P = typename Pos<WIDE>::type;
     __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
     const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
-    const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
+    const uint64_t stream = policy_evict_first();
 
-    const uint32_t sub = threadIdx.x & (kLanesPerBlock - 1);
-    const uint32_t groups = gridDim.x * kGroupsPerCta;
-    uint32_t q = blockIdx.x * kGroupsPerCta + (threadIdx.x / kLanesPerBlock);
+    const uint32_t tid = blockIdx.x * kCountThreads + threadIdx.x;
+    const uint32_t owners = gridDim.x * kCountThreads / LANES;  // concurrent query streams
+    const uint32_t half = tid & (LANES - 1);
+    const uint32_t pair_mask = LANES == 2 ? (3u << (threadIdx.x & 30u)) : 0u;
+    uint32_t q = tid / LANES;
+    if (q >= n) return;
     const uint64_t *seeds = packed + (uint64_t)words * stride;
     const uint32_t ts = ix.table_s;
 
@@ -233,100 +278,74 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, uin
         widx = 0;
     };
 
-    bool live = q < n;
-    if (live) {
-        prefetch(q);
-        begin();
-        if (q + groups < n) prefetch(q + groups);
-    }
+    prefetch(q);
+    begin();
+    if (q + owners < n) prefetch(q + owners);
 
-    while (__any_sync(0xffffffffu, live)) {
+    for (;;) {
         // retire + refill (msbwt_core.rs:151-153,160: empty range or all symbols consumed)
-        while (live && (rem == 0 || l == h)) {
-            if (sub == 0) stg_stream(out + q, (uint64_t)(h - l), stream);
-            q += groups;
-            live = q < n;
-            if (live) {
-                begin();
-                if (q + groups < n) prefetch(q + groups);
-            }
+        while (rem == 0 || l == h) {
+            if (half == 0) stg_stream(out + q, (uint64_t)(h - l), stream);
+            q += owners;
+            if (q >= n) return;
+            begin();
+            if (q + owners < n) prefetch(q + owners);
         }
-        __syncwarp();
-        if (live && shift < 0) {  // next 21 symbols
+        if (shift < 0) {  // next 21 symbols
             widx++;
             word = ldg_stream(packed + (uint64_t)widx * stride + q, stream);
             shift = 60;
         }
-        const uint32_t sym = (uint32_t)(word >> (shift & 63)) & 7u;
-        P nl = l, nh = h;
-        group_step<WIDE>(ix, cb, keep, sub, live, sym, nl, nh);
-        if (live) { l = nl; h = nh; rem--; shift -= 3; }
+        const uint32_t sym = (uint32_t)(word >> shift) & 7u;
+        rank_step<WIDE, LANES>(ix, cb, sym, l, h, half, pair_mask);
+        rem--;
+        shift -= 3;
     }
 }
 
 // Variable-length form, symbols read straight from the caller's byte layout.
 template <bool WIDE>
-__global__ void __launch_bounds__(kCountThreads, kCountMinCtas)
+__global__ void __launch_bounds__(kCountThreads, min_ctas(WIDE, 1))
 count_kmers_bytes_kernel(IndexView ix, const uint8_t *__restrict__ syms, const uint64_t *__restrict__ offsets,
                          uint32_t n, uint64_t *__restrict__ out, uint32_t *__restrict__ status) {
     using P = typename Pos<WIDE>::type;
     __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
     const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
-    const uint64_t keep = policy_evict_last();
-
-    const uint32_t sub = threadIdx.x & (kLanesPerBlock - 1);
-    const uint32_t groups = gridDim.x * kGroupsPerCta;
-    uint32_t q = blockIdx.x * kGroupsPerCta + (threadIdx.x / kLanesPerBlock);
-
-    P l = 0, h = 0;
-    uint64_t beg = 0, cur = 0;  // cur: one past the next symbol to consume
-    bool live = q < n;
-    if (live) { h = (P)ix.total; beg = offsets[q]; cur = offsets[q + 1]; }
-
-    while (__any_sync(0xffffffffu, live)) {
-        while (live && (cur == beg || l == h)) {
-            if (sub == 0) out[q] = (uint64_t)(h - l);
-            q += groups;
-            live = q < n;
-            if (live) { l = 0; h = (P)ix.total; beg = offsets[q]; cur = offsets[q + 1]; }
+    const uint32_t threads = gridDim.x * kCountThreads;
+    uint32_t q = blockIdx.x * kCountThreads + threadIdx.x;
+    if (q >= n) return;
+    P l = 0, h = (P)ix.total;
+    uint64_t beg = offsets[q], cur = offsets[q + 1];  // cur: one past the next symbol to consume
+    for (;;) {
+        while (cur == beg || l == h) {
+            out[q] = (uint64_t)(h - l);
+            q += threads;
+            if (q >= n) return;
+            l = 0; h = (P)ix.total; beg = offsets[q]; cur = offsets[q + 1];
         }
-        __syncwarp();
-        uint32_t sym = 0;
-        if (live) {
-            sym = syms[cur - 1];
-            if (sym >= (uint32_t)kAlphabet) { atomicOr(status, 1u); sym = 0; }
-        }
-        P nl = l, nh = h;
-        group_step<WIDE>(ix, cb, keep, sub, live, sym, nl, nh);
-        if (live) { l = nl; h = nh; cur--; }
+        uint32_t sym = syms[cur - 1];
+        if (sym >= (uint32_t)kAlphabet) { atomicOr(status, 1u); sym = 0; }
+        rank_step<WIDE, 1>(ix, cb, sym, l, h);
+        cur--;
     }
 }
 
 // ---------------------------------------------------------------- K2: constrain_ranges
 
 template <bool WIDE>
-__global__ void __launch_bounds__(kCountThreads, kCountMinCtas)
+__global__ void __launch_bounds__(kCountThreads, min_ctas(WIDE, 1))
 constrain_ranges_kernel(IndexView ix, const uint8_t *__restrict__ sym, const uint64_t *__restrict__ l,
                         const uint64_t *__restrict__ h, uint32_t n, uint64_t *__restrict__ out_l,
                         uint64_t *__restrict__ out_h) {
     using P = typename Pos<WIDE>::type;
     __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
     const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
-    const uint64_t keep = policy_evict_last();
-    const uint32_t sub = threadIdx.x & (kLanesPerBlock - 1);
-    const uint32_t groups = gridDim.x * kGroupsPerCta;
-    const uint32_t q = blockIdx.x * kGroupsPerCta + (threadIdx.x / kLanesPerBlock);
-    // all eight groups of a warp must stay in the loop together (group_step shuffles warp-wide),
-    // so the trip count is decided by the warp's first group
-    const uint32_t warp_first = q - ((threadIdx.x / kLanesPerBlock) & 7u);
-    for (uint64_t it = 0; warp_first + it * groups < n; it++) {
-        const uint64_t i = q + it * groups;
-        const bool live = i < n;
-        P a = 0, b = 0;
-        uint32_t s = 0;
-        if (live) { a = (P)l[i]; b = (P)h[i]; s = sym[i]; }
-        group_step<WIDE>(ix, cb, keep, sub, live, s, a, b);
-        if (live && sub == 0) { out_l[i] = a; out_h[i] = b; }
+    const uint32_t threads = gridDim.x * kCountThreads;
+    for (uint64_t i = blockIdx.x * kCountThreads + threadIdx.x; i < n; i += threads) {
+        P a = (P)l[i], b = (P)h[i];
+        rank_step<WIDE, 1>(ix, cb, sym[i], a, b);
+        out_l[i] = a;
+        out_h[i] = b;
     }
 }
 
@@ -335,7 +354,7 @@ constrain_ranges_kernel(IndexView ix, const uint8_t *__restrict__ sym, const uin
 // child[idx] = constrain_range(ACGT[idx & 3], parent[idx >> 2]); an empty parent stays empty
 // (count_kmer returns 0 as soon as the range is empty, msbwt_core.rs:151-153).
 template <bool WIDE>
-__global__ void __launch_bounds__(kCountThreads, kCountMinCtas)
+__global__ void __launch_bounds__(kCountThreads, min_ctas(WIDE, 1))
 table_extend_kernel(IndexView ix, const void *__restrict__ parent_v, void *__restrict__ child_v, uint32_t n_child) {
     using P = typename Pos<WIDE>::type;
     using E = typename std::conditional<WIDE, ulonglong2, uint2>::type;
@@ -343,27 +362,18 @@ table_extend_kernel(IndexView ix, const void *__restrict__ parent_v, void *__res
     E *child = reinterpret_cast<E *>(child_v);
     __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
     const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
-    const uint64_t keep = policy_evict_last();
-    const uint32_t sub = threadIdx.x & (kLanesPerBlock - 1);
-    const uint32_t groups = gridDim.x * kGroupsPerCta;
-    const uint32_t g = blockIdx.x * kGroupsPerCta + (threadIdx.x / kLanesPerBlock);
-    const uint32_t warp_first = g - ((threadIdx.x / kLanesPerBlock) & 7u);
-    for (uint64_t it = 0; warp_first + it * groups < n_child; it++) {
-        const uint64_t i = g + it * groups;
-        bool live = i < n_child;
-        P a = 0, b = 0;
-        if (live) {
-            const E e = parent[i >> 2];
-            a = (P)e.x; b = (P)e.y;
+    const uint32_t threads = gridDim.x * kCountThreads;
+    for (uint64_t i = blockIdx.x * kCountThreads + threadIdx.x; i < n_child; i += threads) {
+        const E e = parent[i >> 2];
+        P a = (P)e.x, b = (P)e.y;
+        E o;
+        o.x = 0; o.y = 0;
+        if (a != b) {
+            const uint32_t sym = (0x5321u >> ((i & 3u) * 4u)) & 7u;  // A,C,G,T = 1,2,3,5
+            rank_step<WIDE, 1>(ix, cb, sym, a, b);
+            o.x = a; o.y = b;
         }
-        const bool empty = (a == b);
-        const uint32_t sym = (0x5321u >> ((i & 3u) * 4u)) & 7u;  // A,C,G,T = 1,2,3,5
-        group_step<WIDE>(ix, cb, keep, sub, live && !empty, sym, a, b);
-        if (live && sub == 0) {
-            E e;
-            e.x = empty ? 0 : a; e.y = empty ? 0 : b;
-            child[i] = e;
-        }
+        child[i] = o;
     }
 }
 
@@ -431,7 +441,7 @@ static unsigned persistent_grid(int device, const void *kernel, int threads, uin
 
 static bool is_wide(const IndexView &ix) { return ix.n_super > 1 || (ix.total >> 32) != 0; }
 
-constexpr uint64_t kMaxPerLaunch = 1ull << 30;  // keeps q + groups inside u32
+constexpr uint64_t kMaxPerLaunch = 1ull << 30;  // keeps q + threads inside u32
 
 cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_t k, uint64_t n, uint64_t *d_packed,
                              uint32_t *d_status, cudaStream_t st) {
@@ -443,20 +453,28 @@ cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_
     return cudaGetLastError();
 }
 
-cudaError_t launch_count_packed(int device, const IndexView &ix, const uint64_t *d_packed, uint32_t k,
+template <bool WIDE, int LANES>
+static cudaError_t launch_count_packed_t(int device, const IndexView &ix, const uint64_t *d_packed, uint64_t stride,
+                                         uint32_t words, uint32_t k, uint32_t m, uint64_t *d_out, cudaStream_t st) {
+    const unsigned grid = persistent_grid(device, (const void *)count_kmers_packed_kernel<WIDE, LANES>, kCountThreads,
+                                          m, kCountThreads / LANES);
+    count_kmers_packed_kernel<WIDE, LANES><<<grid, kCountThreads, 0, st>>>(ix, d_packed, stride, words, k, m, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, const uint64_t *d_packed, uint32_t k,
                                 uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches) {
     const uint32_t words = words_for_k(k);
     for (uint64_t q0 = 0; q0 < n; q0 += kMaxPerLaunch) {
         const uint32_t m = (uint32_t)((n - q0) < kMaxPerLaunch ? (n - q0) : kMaxPerLaunch);
-        if (is_wide(ix)) {
-            const unsigned grid = persistent_grid(device, (const void *)count_kmers_packed_kernel<true>, kCountThreads, m, kGroupsPerCta);
-            count_kmers_packed_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_packed + q0, n, words, k, m, d_out + q0);
-        } else {
-            const unsigned grid = persistent_grid(device, (const void *)count_kmers_packed_kernel<false>, kCountThreads, m, kGroupsPerCta);
-            count_kmers_packed_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_packed + q0, n, words, k, m, d_out + q0);
-        }
+        cudaError_t e;
+        if (is_wide(ix))
+            e = lanes == 2 ? launch_count_packed_t<true, 2>(device, ix, d_packed + q0, n, words, k, m, d_out + q0, st)
+                           : launch_count_packed_t<true, 1>(device, ix, d_packed + q0, n, words, k, m, d_out + q0, st);
+        else
+            e = lanes == 2 ? launch_count_packed_t<false, 2>(device, ix, d_packed + q0, n, words, k, m, d_out + q0, st)
+                           : launch_count_packed_t<false, 1>(device, ix, d_packed + q0, n, words, k, m, d_out + q0, st);
         if (launches) (*launches)++;
-        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -465,10 +483,10 @@ cudaError_t launch_count_packed(int device, const IndexView &ix, const uint64_t 
 cudaError_t launch_table_extend(int device, const IndexView &ix, const void *d_parent, void *d_child,
                                 uint32_t n_child, cudaStream_t st) {
     if (is_wide(ix)) {
-        const unsigned grid = persistent_grid(device, (const void *)table_extend_kernel<true>, kCountThreads, n_child, kGroupsPerCta);
+        const unsigned grid = persistent_grid(device, (const void *)table_extend_kernel<true>, kCountThreads, n_child, kCountThreads);
         table_extend_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_parent, d_child, n_child);
     } else {
-        const unsigned grid = persistent_grid(device, (const void *)table_extend_kernel<false>, kCountThreads, n_child, kGroupsPerCta);
+        const unsigned grid = persistent_grid(device, (const void *)table_extend_kernel<false>, kCountThreads, n_child, kCountThreads);
         table_extend_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_parent, d_child, n_child);
     }
     return cudaGetLastError();
@@ -482,10 +500,10 @@ cudaError_t launch_count_bytes(int device, const IndexView &ix, const uint8_t *d
     for (uint64_t q0 = 0; q0 < n; q0 += kMaxPerLaunch) {
         const uint32_t m = (uint32_t)((n - q0) < kMaxPerLaunch ? (n - q0) : kMaxPerLaunch);
         if (is_wide(ix)) {
-            const unsigned grid = persistent_grid(device, (const void *)count_kmers_bytes_kernel<true>, kCountThreads, m, kGroupsPerCta);
+            const unsigned grid = persistent_grid(device, (const void *)count_kmers_bytes_kernel<true>, kCountThreads, m, kCountThreads);
             count_kmers_bytes_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_syms, d_offsets + q0, m, d_out + q0, d_status);
         } else {
-            const unsigned grid = persistent_grid(device, (const void *)count_kmers_bytes_kernel<false>, kCountThreads, m, kGroupsPerCta);
+            const unsigned grid = persistent_grid(device, (const void *)count_kmers_bytes_kernel<false>, kCountThreads, m, kCountThreads);
             count_kmers_bytes_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_syms, d_offsets + q0, m, d_out + q0, d_status);
         }
         if (launches) (*launches)++;
@@ -501,10 +519,10 @@ cudaError_t launch_constrain_ranges(int device, const IndexView &ix, const uint8
     for (uint64_t q0 = 0; q0 < n; q0 += kMaxPerLaunch) {
         const uint32_t m = (uint32_t)((n - q0) < kMaxPerLaunch ? (n - q0) : kMaxPerLaunch);
         if (is_wide(ix)) {
-            const unsigned grid = persistent_grid(device, (const void *)constrain_ranges_kernel<true>, kCountThreads, m, kGroupsPerCta);
+            const unsigned grid = persistent_grid(device, (const void *)constrain_ranges_kernel<true>, kCountThreads, m, kCountThreads);
             constrain_ranges_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_sym + q0, d_l + q0, d_h + q0, m, d_out_l + q0, d_out_h + q0);
         } else {
-            const unsigned grid = persistent_grid(device, (const void *)constrain_ranges_kernel<false>, kCountThreads, m, kGroupsPerCta);
+            const unsigned grid = persistent_grid(device, (const void *)constrain_ranges_kernel<false>, kCountThreads, m, kCountThreads);
             constrain_ranges_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_sym + q0, d_l + q0, d_h + q0, m, d_out_l + q0, d_out_h + q0);
         }
         if (launches) (*launches)++;

@@ -6,18 +6,26 @@
 // constrain_range is exactly [C[s]+rank(s,l), C[s]+rank(s,h)) (SURVEY.md facts
 // table), so any exact rank structure is bit-exact.  Ours:
 //
-//   one 64-byte block per 128 BWT symbols, fetched by 4 lanes x one 16-byte
-//   ld.global.nc each (two 32-byte DRAM sectors: measured on B200, random 64-B reads
-//   sustain ~1.7x the access rate of random 128-B reads, and a step needs only the
-//   rank at two positions, not bandwidth).  Lane j's chunk is
+//   one 64-byte block per 128 BWT symbols, made of two self-contained 32-byte halves
+//   (half i covers block offsets 64i .. 64i+63):
 //
-//       u32 ckpt_j | u32 plane0_j | u32 plane1_j | u32 plane2_j
+//       word 0,1   u32 ckpt[2i], ckpt[2i+1]   two of the four checkpoints: occurrences of
+//                                             A, C (half 0) / G, T (half 1) before the BLOCK,
+//                                             relative to the block's superblock
+//       word 2,3   plane0 of symbols 64i..64i+31, 64i+32..64i+63  (bit 0 of each symbol)
+//       word 4,5   plane1 ...                                      (bit 1)
+//       word 6,7   plane2 ...                                      (bit 2)
 //
-//   plane_b_j bit i = bit b of the symbol at block offset 32*j + i  (3-bit symbols,
-//   bit-planes so a lane's 32 symbols are matched with 3 logic ops + 1 popc),
-//   ckpt_0..ckpt_3 = number of A, C, G, T before the block, relative to the block's
-//   superblock (u32).  The rare symbols $ and N keep their checkpoints in a side
-//   array `aux[blk] = {u32 n$, u32 nN}` that only k-mers containing $ / N touch.
+//   3-bit symbols as bit-planes: 32 symbols are matched against a query symbol with
+//   3 logic ops + 1 popc.  A half is exactly one 256-bit ld.global.nc / one 32-byte
+//   sector.  Two kernel mappings read it (kernels.cu): one thread per query (both
+//   halves, two loads) when the index is L2-resident, or a lane pair per query (one
+//   load per lane = one coalesced 64-byte request) when it lives in HBM.  Measured on
+//   B200 (profiles/): random reads of 32, 64 and 128 bytes all sustain ~39 G reads/s
+//   from HBM and 64-byte reads ~270 G reads/s from L2, so the block is sized by what a
+//   rank needs, not by bandwidth.
+//   The rare symbols $ and N keep their checkpoints in a side array
+//   `aux[blk] = {u32 n$, u32 nN}` that only k-mers containing $ / N touch.
 //
 //   Positions past the end of the BWT in the last block hold symbol 7 (matches
 //   nothing).  There is always a block for position N itself (N>>7), so h == N needs
@@ -35,15 +43,14 @@ namespace msbwt {
 constexpr int kBlockShift = 7;
 constexpr int kBlockSyms = 1 << kBlockShift;
 constexpr int kBlockBytes = 64;
-constexpr int kLanesPerBlock = 4;     // 16 B per lane
 constexpr int kWordsPerBlock = 16;    // u32 words
 constexpr int kAlphabet = 6;          // $ACGNT (src/msbwt_core.rs:4)
 constexpr int kDefaultSuperShift = 25;
 constexpr int kSymsPerWord = 21;      // packed query word: 21 x 3-bit symbols, first-consumed symbol in the top bits
 constexpr int kMaxSuperInSmem = 64;
 
-// which lane of a block holds the checkpoint of symbol s (A=1,C=2,G=3,T=5); $/N use `aux`
-__host__ __device__ constexpr int ckpt_lane(int s) { return s == 5 ? 3 : s - 1; }
+// index of symbol s's checkpoint within ckpt[4] (A=1,C=2,G=3,T=5); $/N use `aux`
+__host__ __device__ constexpr int ckpt_slot(int s) { return s == 5 ? 3 : s - 1; }
 
 // Suffix table (the reference author's planned-but-unimplemented `kmer_cache`,
 // src/msbwt_core.rs:133-146, src/rle_bwt.rs:332-346): table[idx] = the BWT range after the
@@ -53,7 +60,7 @@ __host__ __device__ constexpr int ckpt_lane(int s) { return s == 5 ? 3 : s - 1; 
 constexpr int kMaxTableS = 15;
 
 struct IndexView {
-    const uint4 *blocks;     // nblocks * 4 uint4
+    const uint4 *blocks;     // nblocks * 4 uint4 (64 B per block)
     const uint32_t *aux;     // nblocks * 2  ($, N checkpoints)
     const uint64_t *cbase;   // n_super * 8
     const void *table;       // 4^table_s entries, or nullptr

@@ -34,7 +34,10 @@ struct ImageWriter {
             }
         }
         uint32_t *w = &img.blocks[blk * kWordsPerBlock];
-        for (int s : {1, 2, 3, 5}) w[ckpt_lane(s) * 4] = (uint32_t)(running[s] - super_base[s]);
+        for (int s : {1, 2, 3, 5}) {
+            const int slot = ckpt_slot(s);  // half = slot >> 1, word = slot & 1
+            w[(slot >> 1) * 8 + (slot & 1)] = (uint32_t)(running[s] - super_base[s]);
+        }
         img.aux[blk * 2 + 0] = (uint32_t)(running[0] - super_base[0]);  // $
         img.aux[blk * 2 + 1] = (uint32_t)(running[4] - super_base[4]);  // N
     }
@@ -47,9 +50,10 @@ struct ImageWriter {
             const uint32_t lo = off > (j << 5) ? off - (j << 5) : 0;
             const uint32_t hi = end < ((j + 1) << 5) ? end - (j << 5) : 32;
             const uint32_t m = (hi == 32 ? ~0u : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-            if (sym & 1u) w[j * 4 + 1] |= m;
-            if (sym & 2u) w[j * 4 + 2] |= m;
-            if (sym & 4u) w[j * 4 + 3] |= m;
+            uint32_t *hw = w + (j >> 1) * 8 + (j & 1);  // half j/2, word j%2 within each plane pair
+            if (sym & 1u) hw[2] |= m;
+            if (sym & 2u) hw[4] |= m;
+            if (sym & 4u) hw[6] |= m;
         }
     }
 

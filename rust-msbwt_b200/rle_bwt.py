@@ -105,10 +105,12 @@ def load_library():
         "msbwt_constrain_ranges_device": (i32, [vp, i32, vp, vp, vp, u64, vp, vp, vp]),
         "msbwt_packed_words": (u32, [vp, u32]),
         "msbwt_suffix_table_s": (i32, [vp]),
+        "msbwt_kernel_lanes": (i32, [vp]),
         "msbwt_pack_kmers_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
         "msbwt_count_kmers_packed_device": (i32, [vp, i32, vp, u32, u64, vp, vp]),
         "msbwt_launch_count": (u64, []),
         "msbwt_gather_bench": (i32, [i32, vp, u64, u32, u64, u64, vp, vp]),
+        "msbwt_l2_fetch_granularity": (i32, [i32, i32]),
         "msbwt_debug_build_image": (i32, [vp, u64, u32, C.POINTER(u64), C.POINTER(u32), vp, vp, vp]),
         "msbwt_host_alloc": (vp, [C.c_size_t]),
         "msbwt_host_free": (None, [vp]),
@@ -125,10 +127,10 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex",
     "msbwt_index_destroy", "msbwt_total_size", "msbwt_symbol_count", "msbwt_start_index",
-    "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_suffix_table_s", "msbwt_count_kmers",
+    "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_suffix_table_s", "msbwt_kernel_lanes", "msbwt_count_kmers",
     "msbwt_count_kmers_fixed", "msbwt_constrain_ranges", "msbwt_count_kmers_fixed_device",
     "msbwt_constrain_ranges_device", "msbwt_packed_words", "msbwt_pack_kmers_device",
-    "msbwt_count_kmers_packed_device", "msbwt_launch_count", "msbwt_gather_bench", "msbwt_debug_build_image",
+    "msbwt_count_kmers_packed_device", "msbwt_launch_count", "msbwt_gather_bench", "msbwt_l2_fetch_granularity", "msbwt_debug_build_image",
     "msbwt_host_alloc",
     "msbwt_host_free", "msbwt_last_error", "msbwt_abi_version",
 )
@@ -305,6 +307,10 @@ class RleBWT:
         return int(load_library().msbwt_suffix_table_s(self.handle))
 
     @property
+    def kernel_lanes(self) -> int:
+        return int(load_library().msbwt_kernel_lanes(self.handle))
+
+    @property
     def index_bytes(self) -> int:
         return int(load_library().msbwt_index_bytes(self.handle))
 
@@ -328,6 +334,10 @@ def debug_build_image(rle, superblock_shift: int = 0) -> tuple[np.ndarray, np.nd
     _check(L.msbwt_debug_build_image(_p(a), a.size, superblock_shift, C.byref(nb), C.byref(ns), _p(blocks), _p(aux),
                                      _p(cbase)), "image")
     return blocks, aux, cbase
+
+
+def l2_fetch_granularity(device: int, nbytes: int = 0) -> int:
+    return int(load_library().msbwt_l2_fetch_granularity(device, nbytes))
 
 
 def launch_count() -> int:

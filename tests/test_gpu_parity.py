@@ -182,6 +182,27 @@ def test_automatic_suffix_table_is_on_for_real_sizes(midsize):
     assert g.suffix_table_s == 8  # ceil(log4(2.02e6 / 32))
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_both_kernel_mappings_are_bit_exact(lanes, monkeypatch, midsize, golden_dir):
+    """LANES=1 (thread per query) and LANES=2 (lane pair per query) over the same block image."""
+    from harness import synth
+    reads, _, o = midsize
+    monkeypatch.setenv("MSBWT_LANES", str(lanes))
+    for sb, ts in ((0, -1), (3, 5), (0, 0)):
+        g = M.RleBWT(superblock_shift=sb, suffix_table_s=ts)
+        g.load_vector(o.rle_bytes())
+        assert g.kernel_lanes == lanes
+        for k in (1, 12, 31, 50):
+            q = synth.make_queries(reads, k, 20001, 20000).cpu().numpy()
+            q[5, 0] = 4
+            q[7, k - 1] = 0
+            assert (g.count_kmers_fixed(q, k) == o.count_kmers_fixed(q, k, threads=8)).all(), (lanes, sb, ts, k)
+    z = np.load(f"{golden_dir}/reads30x_k31.npz")
+    g = M.RleBWT()
+    g.load_vector(z["rle"])
+    assert (g.count_kmers_fixed(z["queries"], 31) == z["counts"]).all()
+
+
 def test_empty_bwt():
     g, o = both(np.zeros(0, np.uint8))
     assert g.get_total_size() == 0

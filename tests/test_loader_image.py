@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert M.load_library().msbwt_abi_version() == 1
 
 
-CKPT_LANE = {1: 0, 2: 1, 3: 2, 5: 3}  # layout.h: A,C,G,T checkpoints sit in lanes 0..3; $ / N in aux
+CKPT_SLOT = {1: 0, 2: 1, 3: 2, 5: 3}  # layout.h: A,C in half 0 words 0,1; G,T in half 1 words 0,1; $ / N in aux
 
 
 def image_rank(blocks, aux, cbase, sb_shift, sym, pos):
@@ -40,11 +40,11 @@ def image_rank(blocks, aux, cbase, sb_shift, sym, pos):
     for j in range(4):
         m = 0xFFFFFFFF
         for b in range(3):
-            plane = int(w[j * 4 + 1 + b])
+            plane = int(w[(j >> 1) * 8 + 2 + 2 * b + (j & 1)])
             m &= plane if (sym >> b) & 1 else (~plane & 0xFFFFFFFF)
         nb = min(max(p - 32 * j, 0), 32)
         cnt += bin(m & ((1 << nb) - 1)).count("1")
-    ckpt = int(w[CKPT_LANE[sym] * 4]) if sym in CKPT_LANE else int(aux[blk][sym >> 2])
+    ckpt = int(w[(CKPT_SLOT[sym] >> 1) * 8 + (CKPT_SLOT[sym] & 1)]) if sym in CKPT_SLOT else int(aux[blk][sym >> 2])
     return int(cbase[blk >> sb_shift][sym]) + ckpt + cnt
 
 
