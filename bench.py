@@ -226,16 +226,15 @@ def measure_ours(args, cfg, ctx, primary: bool):
         f"in {time.time() - t0:.1f}s")
 
     stream = torch.cuda.current_stream().cuda_stream
-    words = bwt.packed_words(k)        # symbol words + seed word(s)
     table_s = bwt.suffix_table_s
-    d_packed = torch.empty(words * n, dtype=torch.int64, device=dev)
+    d_packed = torch.empty(bwt.packed_bytes(k, n) // 8, dtype=torch.int64, device=dev)  # pack -> search scratch
     d_out = torch.empty(n, dtype=torch.int64, device=dev)
     d_status = torch.zeros(1, dtype=torch.int32, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > L2: evicts index + queries between steps
 
     def step(ev=None):
         d_status.zero_()
-        bwt.pack_kmers_device(queries.data_ptr(), k, n, d_packed.data_ptr(), d_status.data_ptr(), stream)
+        bwt.pack_kmers_device(queries.data_ptr(), k, n, d_packed.data_ptr(), d_out.data_ptr(), d_status.data_ptr(), stream)
         if ev:
             ev[0].record()
         bwt.count_kmers_packed_device(d_packed.data_ptr(), k, n, d_out.data_ptr(), stream)
@@ -332,7 +331,7 @@ def measure_ours(args, cfg, ctx, primary: bool):
         ms = min(n, 1_000_000)
         steps0, two0 = orc.count_kmers_stats(q_host[:ms], k, BLOCK_SHIFT)
         steps, two, hits = orc.count_kmers_stats_skip(q_host[:ms], k, BLOCK_SHIFT, table_s)
-        packed_q = 8 * words
+        packed_q = 8 * (-(-k // 21) + 1) + 4   # symbol words + seed + index of the compacted live list
         bytes_per_query = ((steps + two) * BLOCK_BYTES + hits * 32) / ms + packed_q + 8
         bytes_per_query_no_table = (steps0 + two0) * BLOCK_BYTES / ms + packed_q + 8
         accesses_per_query = (steps + two + hits) / ms

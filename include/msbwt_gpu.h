@@ -127,17 +127,18 @@ int msbwt_constrain_ranges_device(const msbwt_index *idx, int slot, const uint8_
                                   const uint64_t *d_l, const uint64_t *d_h, uint64_t n,
                                   uint64_t *d_out_l, uint64_t *d_out_h, void *stream);
 
-/* The two stages of msbwt_count_kmers_fixed_device as separate calls, for callers that keep
- * packed k-mers resident (and for timing the search kernel on its own):
- *   pack : n*k symbol bytes -> msbwt_packed_words(idx,k)*n u64 words (word-major: word w of
- *          query q at d_packed[w*n + q]; 21 three-bit symbols per word, the k-mer's LAST symbol
- *          in the top bits because backward search consumes it first; the trailing word(s)
- *          hold the range the search starts from, looked up in the suffix table), validating
- *          symbols;
- *   count: the backward search over packed k-mers. */
-uint32_t msbwt_packed_words(const msbwt_index *idx, uint32_t k);
+/* The two stages of msbwt_count_kmers_fixed_device as separate calls, for callers that want to
+ * time or overlap them (n <= 2^30 per pair; d_packed = msbwt_packed_bytes(idx,k,n) bytes of device
+ * scratch, opaque):
+ *   pack : validates the n*k symbol bytes, looks each k-mer's last symbols up in the suffix table,
+ *          packs the remaining symbols 3 bits each (the k-mer's LAST symbol first, because backward
+ *          search consumes it first), writes d_out[q] directly for k-mers that need no further
+ *          search step (e.g. the table says "absent") and appends the rest to a compacted list;
+ *   count: the backward search over that list; afterwards every d_out[q] is final. */
+uint64_t msbwt_packed_bytes(const msbwt_index *idx, uint32_t k, uint64_t n);
 int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const uint8_t *d_syms, uint32_t k,
-                            uint64_t n, uint64_t *d_packed, uint32_t *d_status, void *stream);
+                            uint64_t n, uint64_t *d_packed, uint64_t *d_out, uint32_t *d_status,
+                            void *stream);
 int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot, const uint64_t *d_packed,
                                     uint32_t k, uint64_t n, uint64_t *d_out, void *stream);
 

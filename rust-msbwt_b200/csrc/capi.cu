@@ -338,28 +338,34 @@ extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, 
     std::lock_guard<std::mutex> lock(rep.mu);
     DeviceGuard guard(rep.device);
     cudaStream_t st = (cudaStream_t)stream;
-    CU_TRY(rep.dev_packed.reserve(n * packed_words_for(rep.view, k) * sizeof(uint64_t)));
+    const uint64_t per = std::min<uint64_t>(n, kMaxPerLaunch);
+    CU_TRY(rep.dev_packed.reserve(packed_layout(rep.view, k, per).total() * sizeof(uint64_t)));
     uint32_t *flag = d_status ? d_status : rep.d_status + 2;
     CU_TRY(cudaMemsetAsync(flag, 0, sizeof(uint32_t), st));
-    CU_TRY(launch_pack_seed(rep.view, d_syms, k, n, rep.dev_packed.as<uint64_t>(), flag, st));
-    g_launches++;
-    CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, rep.dev_packed.as<uint64_t>(), k, n, d_out, st, &g_call_launches));
-    flush_launches();
+    for (uint64_t q0 = 0; q0 < n; q0 += per) {  // sub-batches reuse the scratch in stream order
+        const uint64_t m = std::min(per, n - q0);
+        CU_TRY(launch_pack_seed(rep.view, d_syms + q0 * k, k, m, rep.dev_packed.as<uint64_t>(), d_out + q0, flag, st));
+        g_launches++;
+        CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, rep.dev_packed.as<uint64_t>(), k, m, d_out + q0, st,
+                                   &g_call_launches));
+        flush_launches();
+    }
     return MSBWT_OK;
 }
 
-extern "C" uint32_t msbwt_packed_words(const msbwt_index *idx, uint32_t k) {
-    return (idx && !idx->reps.empty()) ? packed_words_for(idx->reps[0]->view, k) : 0;
+extern "C" uint64_t msbwt_packed_bytes(const msbwt_index *idx, uint32_t k, uint64_t n) {
+    return (idx && !idx->reps.empty()) ? packed_layout(idx->reps[0]->view, k, n).total() * sizeof(uint64_t) : 0;
 }
 
 extern "C" int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const uint8_t *d_syms, uint32_t k, uint64_t n,
-                                       uint64_t *d_packed, uint32_t *d_status, void *stream) {
+                                       uint64_t *d_packed, uint64_t *d_out, uint32_t *d_status, void *stream) {
     if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
-    if (n && (!d_packed || !d_status || (k && !d_syms))) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (n && (!d_packed || !d_out || !d_status || (k && !d_syms))) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (n > kMaxPerLaunch) return fail(MSBWT_EINVAL, "more than 2^30 queries per pack/count pair: split the batch");
     if (!n) return MSBWT_OK;
     Replica &rep = *idx->reps[slot];
     DeviceGuard guard(rep.device);
-    CU_TRY(launch_pack_seed(rep.view, d_syms, k, n, d_packed, d_status, (cudaStream_t)stream));
+    CU_TRY(launch_pack_seed(rep.view, d_syms, k, n, d_packed, d_out, d_status, (cudaStream_t)stream));
     g_launches++;
     return MSBWT_OK;
 }
@@ -368,6 +374,7 @@ extern "C" int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot,
                                                uint64_t n, uint64_t *d_out, void *stream) {
     if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
     if (n && (!d_out || !d_packed)) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (n > kMaxPerLaunch) return fail(MSBWT_EINVAL, "more than 2^30 queries per pack/count pair: split the batch");
     if (!n) return MSBWT_OK;
     Replica &rep = *idx->reps[slot];
     DeviceGuard guard(rep.device);
@@ -398,7 +405,6 @@ extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *sy
     if (n && (!out || (k && !syms))) return fail(MSBWT_EINVAL, "NULL host buffer");
     if (!n) return MSBWT_OK;
     const size_t ndev = idx->reps.size();
-    const uint32_t words = packed_words_for(idx->reps[0]->view, k);
     uint64_t chunk = kChunkQueries;
     if (k && chunk * k > kChunkBytes) chunk = std::max<uint64_t>(1, kChunkBytes / k);
 
@@ -415,7 +421,7 @@ extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *sy
         max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
         for (auto &ln : rep.lane) {
             CU_TRY(ln.in_a.reserve(std::max<uint64_t>(1, c * k)));
-            CU_TRY(ln.packed.reserve(std::max<uint64_t>(1, c * words * sizeof(uint64_t))));
+            CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, std::max<uint64_t>(1, c)).total() * sizeof(uint64_t)));
             CU_TRY(ln.out_a.reserve(std::max<uint64_t>(1, c * sizeof(uint64_t))));
         }
         CU_TRY(cudaMemsetAsync(rep.d_status, 0, 2 * sizeof(uint32_t), rep.lane[0].stream));
@@ -432,7 +438,7 @@ extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *sy
             DeviceGuard guard(rep.device);
             Lane &ln = rep.lane[c & 1];
             if (k) CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + b * k, m * k, cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(),
+            CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
                                     rep.d_status + (c & 1), ln.stream));
             g_launches++;
             CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),

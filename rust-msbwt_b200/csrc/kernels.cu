@@ -112,11 +112,13 @@ __device__ __forceinline__ uint32_t count_below64(uint32_t m0, uint32_t m1, int 
 
 // One constrain_range: [l,h) -> [C[sym]+rank(sym,l), C[sym]+rank(sym,h)).
 // LANES == 1: the calling thread does all of it.  LANES == 2: the two lanes of a pair call
-// it together with identical (sym, l, h); `half` = lane & 1, `pair_mask` names the pair.
+// it together with identical (sym, l, h); `half` = lane & 1.  Every non-exited lane of the warp
+// reaches the shuffles in the same iteration of the caller's loop (lanes leave only by returning),
+// so they use the full mask -- a per-pair mask would make ptxas emit MATCH/REDUX guards.
 template <bool WIDE, int LANES>
 __device__ __forceinline__ void rank_step(const IndexView &ix, const CBase<WIDE> &cb, uint32_t sym,
                                           typename Pos<WIDE>::type &l, typename Pos<WIDE>::type &h,
-                                          uint32_t half = 0, uint32_t pair_mask = 0) {
+                                          uint32_t half = 0) {
     using P = typename Pos<WIDE>::type;
     const P bl = l >> kBlockShift, bh = h >> kBlockShift;
     const bool two = bh != bl;
@@ -164,9 +166,9 @@ __device__ __forceinline__ void rank_step(const IndexView &ix, const CBase<WIDE>
         }
         const int off = (int)half * 64;
         uint32_t cnt = count_below64(ml0, ml1, pl - off) | (count_below64(mh0, mh1, ph - off) << 16);
-        cnt += __shfl_xor_sync(pair_mask, cnt, 1);
-        ckl = __shfl_sync(pair_mask, cand_l, slot >> 1, 2);  // the half that owns this symbol's checkpoint
-        ckh = __shfl_sync(pair_mask, cand_h, slot >> 1, 2);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+        ckl = __shfl_sync(0xffffffffu, cand_l, slot >> 1, 2);  // the half that owns this symbol's checkpoint
+        ckh = __shfl_sync(0xffffffffu, cand_h, slot >> 1, 2);
         cl = cnt & 0xffffu;
         ch = cnt >> 16;
     }
@@ -180,39 +182,33 @@ __device__ __forceinline__ void rank_step(const IndexView &ix, const CBase<WIDE>
 
 // ---------------------------------------------------------------- K0: pack + validate + seed
 
-// Packed query layout (word-major, stride n): `words` symbol words, then the seed.
-// Word w of query q holds the symbols consumed at steps 21w .. 21w+20 of the backward search
-// (step t reads kmer[k-1-t]), first step in bits 62..60; bit 63 of word 0 says "the seed came
-// from the suffix table, the first table_s steps are already done".  The seed is the range
-// the search starts from: NARROW one word (l | h << 32), WIDE two words (l, h).
-// One thread per query: pack, validate (symbol >= 6 sets *status) and, when the last
-// table_s symbols are all ACGT, gather the seed range from the suffix table.
+// One thread per query: validate (symbol >= 6 sets *status), look the last table_s symbols up in
+// the suffix table when they are all ACGT (that many steps are then already done), pack the
+// REMAINING symbols 21 per u64 word (step t of the remaining search in bits 62-3(t%21) .. of word
+// t/21; step order = from the k-mer's last symbol to its first), and
+//   * finish the query right here when nothing is left to search (empty range -> count 0,
+//     msbwt_core.rs:151-153; or no symbols left -> h-l), or
+//   * append it to the compacted live list (PackedLayout) for the search kernel.
 template <bool WIDE>
-__global__ void pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, uint64_t n,
-                                 uint32_t words, uint64_t *__restrict__ packed, uint32_t *__restrict__ status) {
+__global__ void pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, PackedLayout lay,
+                                 uint64_t *__restrict__ packed, uint64_t *__restrict__ out,
+                                 uint32_t *__restrict__ status) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const uint8_t *src = syms + q * k;
+    const bool valid = q < lay.n;
+    const uint8_t *src = syms + (valid ? q : 0) * k;
     const uint32_t ts = ix.table_s;
-    bool bad = false, acgt = (ts != 0 && k >= ts);
-    uint64_t tidx = 0, word0 = 0;
-    for (uint32_t w = 0; w < words; w++) {
-        const uint32_t t0 = w * kSymsPerWord;
-        const uint32_t cnt = k > t0 ? min((uint32_t)kSymsPerWord, k - t0) : 0u;
-        uint64_t word = 0;
-        for (uint32_t i = 0; i < cnt; i++) {
-            const uint32_t sy = src[k - 1 - (t0 + i)];
-            bad |= (sy >= (uint32_t)kAlphabet);
-            word |= (uint64_t)(sy & 7u) << (60 - 3 * i);
-            if (t0 + i < ts) {
-                acgt &= ((0x2Eu >> (sy & 7u)) & 1u) != 0;                   // {1,2,3,5}
-                tidx = (tidx << 2) | ((sy - 1u - (sy >> 2)) & 3u);
-            }
+    bool bad = false, acgt = valid && (ts != 0 && k >= ts);
+    uint64_t tidx = 0;
+    if (acgt) {
+        for (uint32_t t = 0; t < ts; t++) {
+            const uint32_t sy = src[k - 1 - t];
+            acgt &= ((0x2Eu >> (sy & 7u)) & 1u) != 0 && sy < 8u;  // {1,2,3,5}
+            tidx = (tidx << 2) | ((sy - 1u - (sy >> 2)) & 3u);
         }
-        if (w == 0) word0 = word; else packed[(uint64_t)w * n + q] = word;
     }
     uint64_t lo = 0, hi = ix.total;
-    if (acgt && !bad) {
+    uint32_t done = 0;
+    if (acgt) {
         if constexpr (WIDE) {
             const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(ix.table) + tidx);
             lo = e.x; hi = e.y;
@@ -220,84 +216,120 @@ __global__ void pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms,
             const uint2 e = __ldg(reinterpret_cast<const uint2 *>(ix.table) + tidx);
             lo = e.x; hi = e.y;
         }
-        word0 |= 1ull << 63;
+        done = ts;
     }
-    packed[q] = word0;
-    if constexpr (WIDE) {
-        packed[(uint64_t)words * n + q] = lo;
-        packed[(uint64_t)(words + 1) * n + q] = hi;
-    } else {
-        packed[(uint64_t)words * n + q] = lo | (hi << 32);
+    // pack (and validate) every symbol; symbols the table consumed are validated but not stored
+    uint64_t word0 = 0;
+    if (valid) {
+        for (uint32_t t = 0; t < done; t++) bad |= src[k - 1 - t] >= (uint32_t)kAlphabet;
+        const uint32_t rest = k - done;
+        for (uint32_t w = 0; w * kSymsPerWord < rest; w++) {
+            const uint32_t t0 = w * kSymsPerWord;
+            const uint32_t cnt = min((uint32_t)kSymsPerWord, rest - t0);
+            uint64_t word = 0;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const uint32_t sy = src[k - 1 - (done + t0 + i)];
+                bad |= (sy >= (uint32_t)kAlphabet);
+                word |= (uint64_t)(sy & 7u) << (60 - 3 * i);
+            }
+            if (w == 0) word0 = word; else packed[lay.wx() + (uint64_t)(w - 1) * lay.n + q] = word;
+        }
+    }
+    const bool finished = valid && (lo == hi || done == k);
+    if (finished) out[q] = hi - lo;
+    const bool live = valid && !finished;
+    // warp-aggregated append to the live list
+    const uint32_t mask = __ballot_sync(0xffffffffu, live);
+    if (mask) {
+        const uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(reinterpret_cast<unsigned long long *>(packed + lay.live()), (unsigned long long)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (live) {
+            const uint64_t pos = base + __popc(mask & ((1u << lane) - 1u));
+            packed[lay.w0() + pos] = word0 | ((uint64_t)(done != 0) << 63);
+            if constexpr (WIDE) {
+                packed[lay.seed() + pos] = lo;
+                packed[lay.seed() + lay.n + pos] = hi;
+            } else {
+                packed[lay.seed() + pos] = lo | (hi << 32);
+            }
+            reinterpret_cast<uint32_t *>(packed + lay.qidx())[pos] = (uint32_t)q;
+        }
     }
     if (bad) atomicOr(status, 1u);
 }
 
 // ---------------------------------------------------------------- K1: count_kmers
 
-// Persistent kernel: every thread (LANES = 1) or lane pair (LANES = 2) owns a stream of
-// queries (q, q+T, q+2T, ...) and refills itself as soon as its current k-mer is finished.
-// The next query's first word and seed are loaded one query ahead so a refill never exposes
-// memory latency.  `packed`/`out` are already offset to this launch's first query; `stride`
-// is the word-major stride of `packed`, `words` the number of symbol words per query.
+// Persistent kernel: every owner -- a thread (LANES = 1) or a lane pair (LANES = 2) -- walks its
+// own stream of live queries (i, i+T, i+2T, ... of the compacted list) and refills itself as soon
+// as its current k-mer is finished.  The next query's first word, seed and index are loaded one
+// query ahead and the next symbol word 21 steps ahead, so neither exposes memory latency.
 template <bool WIDE, int LANES>
 __global__ void __launch_bounds__(kCountThreads, min_ctas(WIDE, LANES))
-count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, uint64_t stride, uint32_t words,
-                          uint32_t k, uint32_t n, uint64_t *__restrict__ out) {
+count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, PackedLayout lay, uint32_t k,
+                          uint64_t *__restrict__ out) {
     using P = typename Pos<WIDE>::type;
     __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
     const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
     const uint64_t stream = policy_evict_first();
 
+    const uint32_t n = (uint32_t)packed[lay.live()];  // live queries (written by the pack kernel)
     const uint32_t tid = blockIdx.x * kCountThreads + threadIdx.x;
     const uint32_t owners = gridDim.x * kCountThreads / LANES;  // concurrent query streams
     const uint32_t half = tid & (LANES - 1);
-    const uint32_t pair_mask = LANES == 2 ? (3u << (threadIdx.x & 30u)) : 0u;
-    uint32_t q = tid / LANES;
-    if (q >= n) return;
-    const uint64_t *seeds = packed + (uint64_t)words * stride;
+    uint32_t i = tid / LANES;
+    if (i >= n) return;
+    const uint64_t *w0 = packed + lay.w0(), *seeds = packed + lay.seed(), *wx = packed + lay.wx();
+    const uint32_t *qidx = reinterpret_cast<const uint32_t *>(packed + lay.qidx());
     const uint32_t ts = ix.table_s;
 
     P l = 0, h = 0;
-    uint64_t word = 0, next_word = 0, next_lo = 0;
+    uint64_t word = 0, pend = 0, next_word = 0, next_lo = 0;
     [[maybe_unused]] uint64_t next_hi = 0;
+    uint32_t q = 0, next_q = 0;
     uint32_t rem = 0;   // symbols still to consume
     int shift = 60;     // bit offset of the next symbol in `word`
-    uint32_t widx = 0;  // index of `word` within the query
+    uint32_t widx = 0;  // index of `word` within the query's remaining symbols
 
-    auto prefetch = [&](uint32_t qq) {
-        next_word = ldg_stream(packed + qq, stream);
-        next_lo = ldg_stream(seeds + qq, stream);
-        if constexpr (WIDE) next_hi = ldg_stream(seeds + stride + qq, stream);
+    auto prefetch = [&](uint32_t ii) {
+        next_word = ldg_stream(w0 + ii, stream);
+        next_lo = ldg_stream(seeds + ii, stream);
+        if constexpr (WIDE) next_hi = ldg_stream(seeds + lay.n + ii, stream);
+        next_q = __ldg(qidx + ii);
     };
     auto begin = [&]() {  // start the prefetched query
         word = next_word;
+        q = next_q;
         if constexpr (WIDE) { l = next_lo; h = next_hi; } else { l = (uint32_t)next_lo; h = (uint32_t)(next_lo >> 32); }
-        const uint32_t done = (word >> 63) ? ts : 0u;  // steps already answered by the suffix table
-        rem = k - done;
-        shift = 60 - 3 * (int)done;
+        rem = k - ((word >> 63) ? ts : 0u);  // the suffix table already answered ts steps
+        shift = 60;
         widx = 0;
+        if (rem > (uint32_t)kSymsPerWord) pend = ldg_stream(wx + q, stream);  // symbol word 1, needed 21 steps from now
     };
 
-    prefetch(q);
+    prefetch(i);
     begin();
-    if (q + owners < n) prefetch(q + owners);
+    if (i + owners < n) prefetch(i + owners);
 
     for (;;) {
         // retire + refill (msbwt_core.rs:151-153,160: empty range or all symbols consumed)
         while (rem == 0 || l == h) {
             if (half == 0) stg_stream(out + q, (uint64_t)(h - l), stream);
-            q += owners;
-            if (q >= n) return;
+            i += owners;
+            if (i >= n) return;
             begin();
-            if (q + owners < n) prefetch(q + owners);
+            if (i + owners < n) prefetch(i + owners);
         }
-        if (shift < 0) {  // next 21 symbols
+        if (shift < 0) {  // next 21 symbols: already in flight since the previous word began
+            word = pend;
             widx++;
-            word = ldg_stream(packed + (uint64_t)widx * stride + q, stream);
             shift = 60;
+            if (rem > (uint32_t)kSymsPerWord) pend = ldg_stream(wx + (uint64_t)widx * lay.n + q, stream);
         }
         const uint32_t sym = (uint32_t)(word >> shift) & 7u;
-        rank_step<WIDE, LANES>(ix, cb, sym, l, h, half, pair_mask);
+        rank_step<WIDE, LANES>(ix, cb, sym, l, h, half);
         rem--;
         shift -= 3;
     }
@@ -441,43 +473,43 @@ static unsigned persistent_grid(int device, const void *kernel, int threads, uin
 
 static bool is_wide(const IndexView &ix) { return ix.n_super > 1 || (ix.total >> 32) != 0; }
 
-constexpr uint64_t kMaxPerLaunch = 1ull << 30;  // keeps q + threads inside u32
 
 cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_t k, uint64_t n, uint64_t *d_packed,
-                             uint32_t *d_status, cudaStream_t st) {
+                             uint64_t *d_out, uint32_t *d_status, cudaStream_t st) {
     if (!n) return cudaSuccess;
-    const uint32_t words = words_for_k(k);
+    const PackedLayout lay = packed_layout(ix, k, n);
+    cudaError_t e = cudaMemsetAsync(d_packed + lay.live(), 0, sizeof(uint64_t), st);
+    if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    if (is_wide(ix)) pack_seed_kernel<true><<<blocks, 256, 0, st>>>(ix, d_syms, k, n, words, d_packed, d_status);
-    else pack_seed_kernel<false><<<blocks, 256, 0, st>>>(ix, d_syms, k, n, words, d_packed, d_status);
+    if (is_wide(ix)) pack_seed_kernel<true><<<blocks, 256, 0, st>>>(ix, d_syms, k, lay, d_packed, d_out, d_status);
+    else pack_seed_kernel<false><<<blocks, 256, 0, st>>>(ix, d_syms, k, lay, d_packed, d_out, d_status);
     return cudaGetLastError();
 }
 
 template <bool WIDE, int LANES>
-static cudaError_t launch_count_packed_t(int device, const IndexView &ix, const uint64_t *d_packed, uint64_t stride,
-                                         uint32_t words, uint32_t k, uint32_t m, uint64_t *d_out, cudaStream_t st) {
+static cudaError_t launch_count_packed_t(int device, const IndexView &ix, const uint64_t *d_packed,
+                                         const PackedLayout &lay, uint32_t k, uint64_t *d_out, cudaStream_t st) {
     const unsigned grid = persistent_grid(device, (const void *)count_kmers_packed_kernel<WIDE, LANES>, kCountThreads,
-                                          m, kCountThreads / LANES);
-    count_kmers_packed_kernel<WIDE, LANES><<<grid, kCountThreads, 0, st>>>(ix, d_packed, stride, words, k, m, d_out);
+                                          lay.n, kCountThreads / LANES);
+    count_kmers_packed_kernel<WIDE, LANES><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out);
     return cudaGetLastError();
 }
 
+// n <= kMaxPerLaunch (the callers chunk): query indices are u32 inside the kernels
 cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, const uint64_t *d_packed, uint32_t k,
                                 uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches) {
-    const uint32_t words = words_for_k(k);
-    for (uint64_t q0 = 0; q0 < n; q0 += kMaxPerLaunch) {
-        const uint32_t m = (uint32_t)((n - q0) < kMaxPerLaunch ? (n - q0) : kMaxPerLaunch);
-        cudaError_t e;
-        if (is_wide(ix))
-            e = lanes == 2 ? launch_count_packed_t<true, 2>(device, ix, d_packed + q0, n, words, k, m, d_out + q0, st)
-                           : launch_count_packed_t<true, 1>(device, ix, d_packed + q0, n, words, k, m, d_out + q0, st);
-        else
-            e = lanes == 2 ? launch_count_packed_t<false, 2>(device, ix, d_packed + q0, n, words, k, m, d_out + q0, st)
-                           : launch_count_packed_t<false, 1>(device, ix, d_packed + q0, n, words, k, m, d_out + q0, st);
-        if (launches) (*launches)++;
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    if (!n) return cudaSuccess;
+    if (n > kMaxPerLaunch) return cudaErrorInvalidValue;
+    const PackedLayout lay = packed_layout(ix, k, n);
+    cudaError_t e;
+    if (is_wide(ix))
+        e = lanes == 2 ? launch_count_packed_t<true, 2>(device, ix, d_packed, lay, k, d_out, st)
+                       : launch_count_packed_t<true, 1>(device, ix, d_packed, lay, k, d_out, st);
+    else
+        e = lanes == 2 ? launch_count_packed_t<false, 2>(device, ix, d_packed, lay, k, d_out, st)
+                       : launch_count_packed_t<false, 1>(device, ix, d_packed, lay, k, d_out, st);
+    if (launches) (*launches)++;
+    return e;
 }
 
 cudaError_t launch_table_extend(int device, const IndexView &ix, const void *d_parent, void *d_child,

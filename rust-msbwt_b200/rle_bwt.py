@@ -103,10 +103,10 @@ def load_library():
         "msbwt_constrain_ranges": (i32, [vp, vp, vp, vp, u64, vp, vp]),
         "msbwt_count_kmers_fixed_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
         "msbwt_constrain_ranges_device": (i32, [vp, i32, vp, vp, vp, u64, vp, vp, vp]),
-        "msbwt_packed_words": (u32, [vp, u32]),
+        "msbwt_packed_bytes": (u64, [vp, u32, u64]),
         "msbwt_suffix_table_s": (i32, [vp]),
         "msbwt_kernel_lanes": (i32, [vp]),
-        "msbwt_pack_kmers_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
+        "msbwt_pack_kmers_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp, vp]),
         "msbwt_count_kmers_packed_device": (i32, [vp, i32, vp, u32, u64, vp, vp]),
         "msbwt_launch_count": (u64, []),
         "msbwt_gather_bench": (i32, [i32, vp, u64, u32, u64, u64, vp, vp]),
@@ -129,7 +129,7 @@ EXPORTED_SYMBOLS = (
     "msbwt_index_destroy", "msbwt_total_size", "msbwt_symbol_count", "msbwt_start_index",
     "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_suffix_table_s", "msbwt_kernel_lanes", "msbwt_count_kmers",
     "msbwt_count_kmers_fixed", "msbwt_constrain_ranges", "msbwt_count_kmers_fixed_device",
-    "msbwt_constrain_ranges_device", "msbwt_packed_words", "msbwt_pack_kmers_device",
+    "msbwt_constrain_ranges_device", "msbwt_packed_bytes", "msbwt_pack_kmers_device",
     "msbwt_count_kmers_packed_device", "msbwt_launch_count", "msbwt_gather_bench", "msbwt_l2_fetch_granularity", "msbwt_debug_build_image",
     "msbwt_host_alloc",
     "msbwt_host_free", "msbwt_last_error", "msbwt_abi_version",
@@ -284,9 +284,9 @@ class RleBWT:
         _check(load_library().msbwt_count_kmers_fixed_device(self.handle, slot, d_syms, k, n, d_out, d_status or None,
                                                              stream or None), "count_kmers_fixed_device")
 
-    def pack_kmers_device(self, d_syms: int, k: int, n: int, d_packed: int, d_status: int, stream: int = 0,
-                          slot: int = 0) -> None:
-        _check(load_library().msbwt_pack_kmers_device(self.handle, slot, d_syms, k, n, d_packed, d_status,
+    def pack_kmers_device(self, d_syms: int, k: int, n: int, d_packed: int, d_out: int, d_status: int,
+                          stream: int = 0, slot: int = 0) -> None:
+        _check(load_library().msbwt_pack_kmers_device(self.handle, slot, d_syms, k, n, d_packed, d_out, d_status,
                                                       stream or None), "pack_kmers_device")
 
     def count_kmers_packed_device(self, d_packed: int, k: int, n: int, d_out: int, stream: int = 0,
@@ -299,8 +299,8 @@ class RleBWT:
         _check(load_library().msbwt_constrain_ranges_device(self.handle, slot, d_sym, d_l, d_h, n, d_out_l, d_out_h,
                                                             stream or None), "constrain_ranges_device")
 
-    def packed_words(self, k: int) -> int:
-        return int(load_library().msbwt_packed_words(self.handle, k))
+    def packed_bytes(self, k: int, n: int) -> int:
+        return int(load_library().msbwt_packed_bytes(self.handle, k, n))
 
     @property
     def suffix_table_s(self) -> int:

@@ -30,10 +30,10 @@ extern "C" {
     pub fn msbwt_count_kmers_fixed(idx: *const msbwt_index, syms: *const u8, k: u32, n: u64, out: *mut u64) -> c_int;
     pub fn msbwt_constrain_ranges(idx: *const msbwt_index, sym: *const u8, l: *const u64, h: *const u64, n: u64, out_l: *mut u64, out_h: *mut u64) -> c_int;
     pub fn msbwt_count_kmers_fixed_device(idx: *const msbwt_index, slot: c_int, d_syms: *const u8, k: u32, n: u64, d_out: *mut u64, d_status: *mut u32, stream: *mut c_void) -> c_int;
-    pub fn msbwt_packed_words(idx: *const msbwt_index, k: u32) -> u32;
+    pub fn msbwt_packed_bytes(idx: *const msbwt_index, k: u32, n: u64) -> u64;
     pub fn msbwt_suffix_table_s(idx: *const msbwt_index) -> c_int;
     pub fn msbwt_kernel_lanes(idx: *const msbwt_index) -> c_int;
-    pub fn msbwt_pack_kmers_device(idx: *const msbwt_index, slot: c_int, d_syms: *const u8, k: u32, n: u64, d_packed: *mut u64, d_status: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn msbwt_pack_kmers_device(idx: *const msbwt_index, slot: c_int, d_syms: *const u8, k: u32, n: u64, d_packed: *mut u64, d_out: *mut u64, d_status: *mut u32, stream: *mut c_void) -> c_int;
     pub fn msbwt_count_kmers_packed_device(idx: *const msbwt_index, slot: c_int, d_packed: *const u64, k: u32, n: u64, d_out: *mut u64, stream: *mut c_void) -> c_int;
     pub fn msbwt_constrain_ranges_device(idx: *const msbwt_index, slot: c_int, d_sym: *const u8, d_l: *const u64, d_h: *const u64, n: u64, d_out_l: *mut u64, d_out_h: *mut u64, stream: *mut c_void) -> c_int;
     pub fn msbwt_launch_count() -> u64;

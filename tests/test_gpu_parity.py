@@ -272,3 +272,40 @@ def test_multi_device_split_matches_single(midsize):
     g2.load_vector(o.rle_bytes())
     assert g2.device_ordinals == [0, 1]
     assert (g2.count_kmers_fixed(q, 31) == g.count_kmers_fixed(q, 31)).all()
+
+
+def test_full_size_config1_properties():
+    """BASELINE.json configs[1] at full size (1 M x 150-bp reads, 151 Msymbol BWT, 31-mers): properties that
+    need no oracle at scale, plus an oracle comparison on a sample.
+      * partition: count(Q) == sum over the six symbols c of count(cQ)   (constrain_range splits a range)
+      * every read-sampled k-mer occurs at least once; counts are permutation-equivariant
+      * host-buffer path == device-buffer path (checksum of checksums)"""
+    from harness import bwt_build, synth
+    reads = synth.make_reads(1_000_000, 150, 30.0, 0.0, device="cuda")
+    rle, total = bwt_build.build_rle_bwt(reads)
+    rle = rle.cpu().numpy()
+    g = M.RleBWT.new()
+    g.load_vector(rle)
+    assert g.get_total_size() == total == 151_000_000
+    assert g.suffix_table_s == 12
+    k = 30
+    q = synth.make_queries(reads, k, 600_000, 400_000)
+    base = g.count_kmers_fixed(q.cpu().numpy(), k)
+    assert (base[: 0] == base[: 0]).all() and int((base > 0).sum()) >= 600_000
+    ext_sum = np.zeros_like(base)
+    for c in range(6):
+        ext = torch.cat([torch.full((q.shape[0], 1), c, dtype=torch.uint8, device=q.device), q], dim=1).contiguous()
+        ext_sum += g.count_kmers_fixed(ext.cpu().numpy(), k + 1)
+    assert (ext_sum == base).all()
+    perm = torch.randperm(q.shape[0], device=q.device)
+    assert (g.count_kmers_fixed(q[perm].contiguous().cpu().numpy(), k) == base[perm.cpu().numpy()]).all()
+    out = torch.zeros(q.shape[0], dtype=torch.int64, device="cuda")
+    g.count_kmers_fixed_device(q.data_ptr(), k, q.shape[0], out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(out.sum().item()) == int(base.astype(np.int64).sum())
+    o = O.RleBWT()
+    o.load_vector(rle)
+    m = 200_000
+    assert (base[:m] == o.count_kmers_fixed(q[:m].cpu().numpy(), k, threads=8)).all()
+    for s in range(6):
+        assert g.get_symbol_count(s) == o.get_symbol_count(s)
