@@ -30,13 +30,13 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # BASELINE.json configs[1]
-    "cfg2": dict(reads=1_000_000, read_len=150, coverage=30.0, error=0.0, n_read=5_000_000, n_random=5_000_000, k=31,
+    "cfg2": dict(key="cfg2", reads=1_000_000, read_len=150, coverage=30.0, error=0.0, n_read=5_000_000, n_random=5_000_000, k=31,
                  name="configs[1]: 1M synthetic 150bp reads (151 Msymbol BWT), 5M random + 5M read-sampled 31-mers"),
     # BASELINE.json configs[2]
-    "cfg3": dict(reads=10_000_000, read_len=150, coverage=30.0, error=0.01, n_read=100_000_000, n_random=0, k=31,
+    "cfg3": dict(key="cfg3", reads=10_000_000, read_len=150, coverage=30.0, error=0.01, n_read=100_000_000, n_random=0, k=31,
                  name="configs[2]: 10M synthetic 150bp reads with 1% errors (1.51 Gsymbol BWT), 100M read-sampled 31-mers"),
     # small shape for plumbing checks
-    "tiny": dict(reads=20_000, read_len=150, coverage=30.0, error=0.01, n_read=100_000, n_random=100_000, k=31,
+    "tiny": dict(key="tiny", reads=20_000, read_len=150, coverage=30.0, error=0.01, n_read=100_000, n_random=100_000, k=31,
                  name="tiny: 20k reads, 200k 31-mers (plumbing check, not a bench line)"),
 }
 METRIC = "count_kmer_31mer_queries_per_sec"
@@ -47,6 +47,19 @@ BLOCK_SHIFT = 7
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def ncu_traffic(workload_key: str, lanes: int, table_s: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel, per launch, from the committed
+    `ncu --set full` capture of this same workload/kernel configuration (profiles/ncu_traffic.json);
+    None when no capture matches."""
+    try:
+        for e in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["captures"]:
+            if e["workload"] == workload_key and e["lanes"] == lanes and e["suffix_table_s"] == table_s:
+                return e["dram_bytes_per_launch"], e["source"]
+    except Exception:
+        pass
+    return None, None
 
 
 def measured_peak_gbs():
@@ -338,9 +351,11 @@ def measure_ours(args, cfg, ctx, primary: bool):
         peak, peak_src = measured_peak_gbs()
         kern_s = statistics.mean(kern_ms) / 1e3
         achieved = bytes_per_query * n / kern_s / 1e9
+        traffic, traffic_src = ncu_traffic(cfg["key"], bwt.kernel_lanes, table_s)
         res["roofline"] = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "count_kmers_packed_kernel", "kernel_ms": 1e3 * kern_s,
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": "count_kmers_packed_kernel",
+            "kernel_ms": 1e3 * kern_s, "algorithmic_bytes_per_launch": bytes_per_query * n,
             "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": steps / ms,
             "two_block_step_share": two / max(1, steps), "suffix_table_s": table_s,
             "table_hits_per_query": hits / ms, "index_accesses_per_query": accesses_per_query,

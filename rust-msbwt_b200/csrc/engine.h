@@ -15,7 +15,7 @@ constexpr int kCountThreads = 256;
 constexpr uint64_t kMaxPerLaunch = 1ull << 30;  // queries per pack/count launch (u32 indices inside the kernels)
 // resident CTAs per SM the kernels are compiled for (register budget = 65536 / (256 * min_ctas)):
 // one thread per query keeps two 64-byte blocks (32 registers) in flight, a lane pair half of that
-constexpr int min_ctas(bool wide, int lanes) { return lanes == 2 ? (wide ? 4 : 6) : (wide ? 3 : 4); }
+constexpr int min_ctas(bool wide, int lanes) { return lanes == 2 ? (wide ? 4 : 5) : (wide ? 3 : 4); }
 
 inline uint32_t words_for_k(uint32_t k) { return k ? (k + kSymsPerWord - 1) / kSymsPerWord : 1; }
 

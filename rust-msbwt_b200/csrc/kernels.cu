@@ -199,10 +199,11 @@ __global__ void pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms,
     const uint32_t ts = ix.table_s;
     bool bad = false, acgt = valid && (ts != 0 && k >= ts);
     uint64_t tidx = 0;
-    if (acgt) {
+    if (acgt) {  // the last ts symbols: table index + validation in one pass
         for (uint32_t t = 0; t < ts; t++) {
             const uint32_t sy = src[k - 1 - t];
-            acgt &= ((0x2Eu >> (sy & 7u)) & 1u) != 0 && sy < 8u;  // {1,2,3,5}
+            bad |= sy >= (uint32_t)kAlphabet;
+            acgt &= sy < 8u && ((0x2Eu >> sy) & 1u) != 0;  // {1,2,3,5}
             tidx = (tidx << 2) | ((sy - 1u - (sy >> 2)) & 3u);
         }
     }
@@ -218,10 +219,9 @@ __global__ void pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms,
         }
         done = ts;
     }
-    // pack (and validate) every symbol; symbols the table consumed are validated but not stored
+    // pack (and validate) the symbols the table did not consume
     uint64_t word0 = 0;
     if (valid) {
-        for (uint32_t t = 0; t < done; t++) bad |= src[k - 1 - t] >= (uint32_t)kAlphabet;
         const uint32_t rest = k - done;
         for (uint32_t w = 0; w * kSymsPerWord < rest; w++) {
             const uint32_t t0 = w * kSymsPerWord;

@@ -291,7 +291,7 @@ def test_full_size_config1_properties():
     k = 30
     q = synth.make_queries(reads, k, 600_000, 400_000)
     base = g.count_kmers_fixed(q.cpu().numpy(), k)
-    assert (base[: 0] == base[: 0]).all() and int((base > 0).sum()) >= 600_000
+    assert int((base > 0).sum()) >= 600_000
     ext_sum = np.zeros_like(base)
     for c in range(6):
         ext = torch.cat([torch.full((q.shape[0], 1), c, dtype=torch.uint8, device=q.device), q], dim=1).contiguous()
