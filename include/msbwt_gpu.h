@@ -166,6 +166,11 @@ int msbwt_debug_build_image(const uint8_t *rle, uint64_t len, uint32_t superbloc
                             uint64_t *nblocks, uint32_t *n_super, uint32_t *blocks, uint32_t *aux,
                             uint64_t *cbase);
 
+/* Copies a replica's device-resident image out in the same form (NULL arrays: sizes only).  The image
+ * is built on the device (builder.cu); tests compare it with the host builder's word for word. */
+int msbwt_debug_copy_image(const msbwt_index *idx, int slot, uint64_t *nblocks, uint32_t *n_super,
+                           uint32_t *blocks, uint32_t *aux, uint64_t *cbase);
+
 /* ---- pinned host buffers for callers that want full copy/compute overlap ---- */
 void *msbwt_host_alloc(size_t bytes);
 void msbwt_host_free(void *p);

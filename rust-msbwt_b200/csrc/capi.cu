@@ -121,13 +121,12 @@ struct msbwt_index {
 
 namespace {
 
-int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev) {
+int resolve_devices(const int *devices, int ndev, std::vector<int> &devs) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         return fail(MSBWT_ENODEV, std::string("no usable CUDA device (there is no CPU fallback): ") +
                                       (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
-    std::vector<int> devs;
     if (ndev <= 0 || !devices) {
         int cur = 0;
         CU_TRY(cudaGetDevice(&cur));
@@ -137,14 +136,60 @@ int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev)
     }
     for (int d : devs)
         if (d < 0 || d >= count) return fail(MSBWT_ENODEV, "device ordinal " + std::to_string(d) + " out of range");
+    return MSBWT_OK;
+}
 
+int finish_replica(msbwt_index *idx, std::unique_ptr<Replica> rep, uint64_t total, uint64_t nblocks, uint32_t n_super,
+                   uint32_t sb_shift) {
+    CU_TRY(cudaMalloc((void **)&rep->d_status, 4 * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(rep->d_status, 0, 4 * sizeof(uint32_t)));
+    CU_TRY(cudaHostAlloc((void **)&rep->h_status, 4 * sizeof(uint32_t), cudaHostAllocDefault));
+    for (auto &ln : rep->lane) CU_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    rep->view.blocks = rep->d_blocks;
+    rep->view.cbase = rep->d_cbase;
+    rep->view.aux = rep->d_aux;
+    rep->view.total = total;
+    rep->view.nblocks = nblocks;
+    rep->view.n_super = n_super;
+    rep->view.sb_shift = sb_shift;
+    idx->bytes_per_replica = nblocks * kBlockBytes + nblocks * 2 * sizeof(uint32_t) + (uint64_t)n_super * 8 * sizeof(uint64_t);
+    idx->reps.push_back(std::move(rep));
+    return MSBWT_OK;
+}
+
+// Default load path: the block image is built on each device from the RLE bytes (builder.cu).
+int build_replicas_on_device(msbwt_index *idx, const uint8_t *rle, uint64_t len, uint32_t sb_shift, const int *devices,
+                             int ndev) {
+    std::vector<int> devs;
+    if (int rc = resolve_devices(devices, ndev, devs); rc != MSBWT_OK) return rc;
+    for (int d : devs) {
+        DeviceGuard guard(d);
+        DeviceImage img;
+        std::string why;
+        int rc = build_image_on_device(rle, len, sb_shift, img, why);
+        if (rc != MSBWT_OK) { free_device_image(img); return fail(rc, why); }
+        auto rep = std::make_unique<Replica>();
+        rep->device = d;
+        rep->d_blocks = img.blocks;
+        rep->d_aux = img.aux;
+        rep->d_cbase = img.cbase;
+        idx->total = img.total;
+        for (int s = 0; s < kAlphabet; s++) { idx->counts[s] = img.counts[s]; idx->start[s] = img.start[s]; }
+        rc = finish_replica(idx, std::move(rep), img.total, img.nblocks, img.n_super, img.sb_shift);
+        if (rc != MSBWT_OK) return rc;
+    }
+    return MSBWT_OK;
+}
+
+// MSBWT_HOST_BUILD=1: build the image with the serial host builder (loader.cu) and copy it up.
+int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev) {
+    std::vector<int> devs;
+    if (int rc = resolve_devices(devices, ndev, devs); rc != MSBWT_OK) return rc;
     idx->total = img.total;
     for (int s = 0; s < kAlphabet; s++) { idx->counts[s] = img.counts[s]; idx->start[s] = img.start[s]; }
     const size_t block_bytes = img.blocks.size() * sizeof(uint32_t);
     const size_t cbase_bytes = img.cbase.size() * sizeof(uint64_t);
     const size_t aux_bytes = img.aux.size() * sizeof(uint32_t);
-    idx->bytes_per_replica = block_bytes + cbase_bytes + aux_bytes;
-
     for (int d : devs) {
         DeviceGuard guard(d);
         auto rep = std::make_unique<Replica>();
@@ -155,18 +200,8 @@ int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev)
         CU_TRY(cudaMemcpy(rep->d_aux, img.aux.data(), aux_bytes, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(rep->d_blocks, img.blocks.data(), block_bytes, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(rep->d_cbase, img.cbase.data(), cbase_bytes, cudaMemcpyHostToDevice));
-        CU_TRY(cudaMalloc((void **)&rep->d_status, 4 * sizeof(uint32_t)));
-        CU_TRY(cudaMemset(rep->d_status, 0, 4 * sizeof(uint32_t)));
-        CU_TRY(cudaHostAlloc((void **)&rep->h_status, 4 * sizeof(uint32_t), cudaHostAllocDefault));
-        for (auto &ln : rep->lane) CU_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
-        rep->view.blocks = rep->d_blocks;
-        rep->view.cbase = rep->d_cbase;
-        rep->view.aux = rep->d_aux;
-        rep->view.total = img.total;
-        rep->view.nblocks = img.nblocks;
-        rep->view.n_super = img.n_super;
-        rep->view.sb_shift = img.sb_shift;
-        idx->reps.push_back(std::move(rep));
+        int rc = finish_replica(idx, std::move(rep), img.total, img.nblocks, img.n_super, img.sb_shift);
+        if (rc != MSBWT_OK) return rc;
     }
     return MSBWT_OK;
 }
@@ -236,11 +271,16 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
     int rc;
     std::string why;
     auto idx = std::make_unique<msbwt_index>();
-    {
+    const char *host_build = getenv("MSBWT_HOST_BUILD");
+    if ((rc = validate_rle(rle, len, why)) != MSBWT_OK) {
+        fail(rc, why);
+    } else if (host_build && atoi(host_build) == 1) {
         HostImage img;
         rc = build_image_from_rle(rle, len, sb_shift, img, why);
         if (rc == MSBWT_OK) rc = upload(idx.get(), img, devices, ndev);
         else fail(rc, why);
+    } else {
+        rc = build_replicas_on_device(idx.get(), rle, len, sb_shift, devices, ndev);
     }
     if (rc == MSBWT_OK) {
         const int s = pick_table_s(idx->total, table_s);
@@ -609,6 +649,20 @@ extern "C" int msbwt_debug_build_image(const uint8_t *rle, uint64_t len, uint32_
     if (blocks) memcpy(blocks, img.blocks.data(), img.blocks.size() * sizeof(uint32_t));
     if (aux) memcpy(aux, img.aux.data(), img.aux.size() * sizeof(uint32_t));
     if (cbase) memcpy(cbase, img.cbase.data(), img.cbase.size() * sizeof(uint64_t));
+    return MSBWT_OK;
+}
+
+extern "C" int msbwt_debug_copy_image(const msbwt_index *idx, int slot, uint64_t *nblocks, uint32_t *n_super,
+                                      uint32_t *blocks, uint32_t *aux, uint64_t *cbase) {
+    g_last_error.clear();
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size() || !nblocks || !n_super) return fail(MSBWT_EINVAL, "bad handle, slot or size outputs");
+    const Replica &rep = *idx->reps[slot];
+    DeviceGuard guard(rep.device);
+    *nblocks = rep.view.nblocks;
+    *n_super = rep.view.n_super;
+    if (blocks) CU_TRY(cudaMemcpy(blocks, rep.d_blocks, rep.view.nblocks * kBlockBytes, cudaMemcpyDeviceToHost));
+    if (aux) CU_TRY(cudaMemcpy(aux, rep.d_aux, rep.view.nblocks * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (cbase) CU_TRY(cudaMemcpy(cbase, rep.d_cbase, (size_t)rep.view.n_super * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return MSBWT_OK;
 }
 

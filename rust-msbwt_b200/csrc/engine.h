@@ -32,7 +32,23 @@ struct HostImage {
     uint32_t sb_shift = kDefaultSuperShift;
 };
 
+// ---- builder.cu: RLE byte stream -> block image built ON the current device ----
+struct DeviceImage {
+    uint4 *blocks = nullptr;
+    uint32_t *aux = nullptr;
+    uint64_t *cbase = nullptr;
+    uint64_t counts[kAlphabet] = {0, 0, 0, 0, 0, 0};
+    uint64_t start[kAlphabet] = {0, 0, 0, 0, 0, 0};
+    uint64_t total = 0;
+    uint64_t nblocks = 0;
+    uint32_t n_super = 0;
+    uint32_t sb_shift = kDefaultSuperShift;
+};
+int build_image_on_device(const uint8_t *h_rle, uint64_t len, uint32_t sb_shift, DeviceImage &img, std::string &why);
+void free_device_image(DeviceImage &img);
+
 // return an msbwt_status; on failure `why` explains
+int validate_rle(const uint8_t *rle, uint64_t len, std::string &why);
 int build_image_from_rle(const uint8_t *rle, uint64_t len, uint32_t sb_shift, HostImage &img, std::string &why);
 int read_npy_payload(const char *path, std::vector<uint8_t> &payload, std::string &why);
 

@@ -78,6 +78,26 @@ struct ImageWriter {
 
 }  // namespace
 
+// Format check shared by both builders, done on the host before any device is touched so that a
+// malformed stream is MSBWT_EFORMAT regardless of the machine: symbol >= 6 (the reference panics
+// indexing symbol_counts, src/rle_bwt.rs:371) or a single run of 13+ bytes (>= 2^60 symbols).
+int validate_rle(const uint8_t *rle, uint64_t len, std::string &why) {
+    if (len && !rle) { why = "rle is NULL"; return MSBWT_EINVAL; }
+    uint8_t prev = 255;
+    int digits = 0;
+    for (uint64_t i = 0; i < len; i++) {
+        const uint8_t c = rle[i] & 7u;
+        if (c >= kAlphabet) {
+            why = "RLE byte " + std::to_string(i) + " has symbol " + std::to_string(c) + " (>= 6)";
+            return MSBWT_EFORMAT;
+        }
+        digits = (c == prev) ? digits + 1 : 0;
+        prev = c;
+        if (digits >= 12) { why = "run longer than 2^60 symbols"; return MSBWT_EFORMAT; }
+    }
+    return MSBWT_OK;
+}
+
 int build_image_from_rle(const uint8_t *rle, uint64_t len, uint32_t sb_shift, HostImage &img, std::string &why) {
     if (len && !rle) { why = "rle is NULL"; return MSBWT_EINVAL; }
     if (sb_shift == 0) sb_shift = kDefaultSuperShift;

@@ -112,6 +112,7 @@ def load_library():
         "msbwt_gather_bench": (i32, [i32, vp, u64, u32, u64, u64, vp, vp]),
         "msbwt_l2_fetch_granularity": (i32, [i32, i32]),
         "msbwt_debug_build_image": (i32, [vp, u64, u32, C.POINTER(u64), C.POINTER(u32), vp, vp, vp]),
+        "msbwt_debug_copy_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp, vp]),
         "msbwt_host_alloc": (vp, [C.c_size_t]),
         "msbwt_host_free": (None, [vp]),
         "msbwt_last_error": (C.c_char_p, []),
@@ -130,7 +131,7 @@ EXPORTED_SYMBOLS = (
     "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_suffix_table_s", "msbwt_kernel_lanes", "msbwt_count_kmers",
     "msbwt_count_kmers_fixed", "msbwt_constrain_ranges", "msbwt_count_kmers_fixed_device",
     "msbwt_constrain_ranges_device", "msbwt_packed_bytes", "msbwt_pack_kmers_device",
-    "msbwt_count_kmers_packed_device", "msbwt_launch_count", "msbwt_gather_bench", "msbwt_l2_fetch_granularity", "msbwt_debug_build_image",
+    "msbwt_count_kmers_packed_device", "msbwt_launch_count", "msbwt_gather_bench", "msbwt_l2_fetch_granularity", "msbwt_debug_build_image", "msbwt_debug_copy_image",
     "msbwt_host_alloc",
     "msbwt_host_free", "msbwt_last_error", "msbwt_abi_version",
 )
@@ -305,6 +306,18 @@ class RleBWT:
     @property
     def suffix_table_s(self) -> int:
         return int(load_library().msbwt_suffix_table_s(self.handle))
+
+    def device_image(self, slot: int = 0) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(blocks[nblocks,16] u32, aux[nblocks,2] u32, cbase[n_super,8] u64) copied back from the device."""
+        L = load_library()
+        nb, ns = C.c_uint64(0), C.c_uint32(0)
+        _check(L.msbwt_debug_copy_image(self.handle, slot, C.byref(nb), C.byref(ns), None, None, None), "image")
+        blocks = np.zeros((nb.value, 16), dtype=np.uint32)
+        aux = np.zeros((nb.value, 2), dtype=np.uint32)
+        cbase = np.zeros((ns.value, 8), dtype=np.uint64)
+        _check(L.msbwt_debug_copy_image(self.handle, slot, C.byref(nb), C.byref(ns), _p(blocks), _p(aux), _p(cbase)),
+               "image")
+        return blocks, aux, cbase
 
     @property
     def kernel_lanes(self) -> int:

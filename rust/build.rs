@@ -8,7 +8,7 @@ fn main() {
     let csrc = root.join("rust-msbwt_b200").join("csrc");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let mut objs = vec![];
-    for f in ["capi.cu", "kernels.cu", "loader.cu"] {
+    for f in ["capi.cu", "kernels.cu", "loader.cu", "builder.cu"] {
         let obj = out.join(f).with_extension("o");
         let ok = Command::new(&nvcc)
             .args(["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

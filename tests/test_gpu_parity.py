@@ -309,3 +309,77 @@ def test_full_size_config1_properties():
     assert (base[:m] == o.count_kmers_fixed(q[:m].cpu().numpy(), k, threads=8)).all()
     for s in range(6):
         assert g.get_symbol_count(s) == o.get_symbol_count(s)
+
+
+def test_wide_index_beyond_2_pow_32_symbols():
+    """Maximum-size edge: N > 2^32 (u64 positions, two default-size superblocks).  Any RLE stream is a legal
+    index, so a 4.6 Gsymbol one is made from ~4.6 M long runs; ranges and k-mer counts must match the
+    oracle at positions on both sides of 2^32."""
+    rng = np.random.default_rng(2032)
+    nruns = 4_600_000
+    syms = rng.choice(np.array([0, 1, 2, 3, 4, 5], dtype=np.uint8), size=nruns, p=[0.02, 0.26, 0.24, 0.24, 0.02, 0.22])
+    keep = np.ones(nruns, dtype=bool)
+    keep[1:] = syms[1:] != syms[:-1]
+    syms = syms[keep]
+    counts = rng.integers(1, 2800, size=syms.size).astype(np.uint64)
+    rle = O.encode_runs(syms, counts)
+    g, o = both(rle)
+    n = o.get_total_size()
+    assert n > (1 << 32) and g.get_total_size() == n
+    m = 200_000
+    sym = rng.integers(0, 6, m).astype(np.uint8)
+    lo = rng.integers(0, n + 1, m).astype(np.uint64)
+    width = rng.choice(np.array([0, 1, 5, 100, 4000, 1 << 20, 1 << 33], dtype=np.uint64), m)
+    hi = np.minimum(lo + width, np.uint64(n))
+    lo[:4], hi[:4] = [0, (1 << 32) - 1, 1 << 32, n], [n, (1 << 32) + 1, (1 << 32) + 7, n]
+    gl, gh = g.constrain_ranges(sym, lo, hi)
+    for i in range(0, m, 37):
+        assert (int(gl[i]), int(gh[i])) == o.constrain_range(int(sym[i]), int(lo[i]), int(hi[i])), i
+    for i in range(4):
+        assert (int(gl[i]), int(gh[i])) == o.constrain_range(int(sym[i]), int(lo[i]), int(hi[i])), i
+    for k in (3, 9, 24):
+        q = rng.choice(np.array([1, 2, 3, 5], dtype=np.uint8), size=(100_000, k))
+        q[::97, 0] = 4
+        assert (g.count_kmers_fixed(q, k) == o.count_kmers_fixed(q, k, threads=8)).all(), k
+    ragged = [rng.integers(0, 6, int(rng.integers(0, 9))).astype(np.uint8) for _ in range(3000)]
+    assert (g.count_kmers(ragged) == o.count_kmers(ragged)).all()
+
+
+@pytest.mark.parametrize("sb_shift", [0, 2])
+def test_device_built_image_equals_host_built_image(sb_shift):
+    """The GPU builder (builder.cu: scan / select / fill / stamp) must produce exactly the block image the
+    serial host builder (loader.cu) produces: words, $/N side array and superblock bases."""
+    rng = np.random.default_rng(515 + sb_shift)
+    streams = [
+        _random_rle(rng, 40000, [1, 1, 1, 2, 3, 5, 9, 31, 32, 33, 255, 256, 257, 1025, 3104, 40000]),
+        O.encode_runs([1, 2, 1, 0, 4, 5], [128, 128, 1, 127, 3104, 5]),
+        np.array([1, 9, 25, 10, 2, 2, 10, 11, 0, 8], dtype=np.uint8),  # zero low digits and zero-length runs
+        O.convert_to_vec("A"),
+        np.zeros(0, np.uint8),
+    ]
+    from harness import bwt_build, synth
+    reads = synth.make_reads(3000, 80, 20.0, 0.02, device="cuda")
+    streams.append(bwt_build.build_rle_bwt(reads)[0].cpu().numpy())
+    for rle in streams:
+        hb, ha, hc = M.debug_build_image(rle, sb_shift)
+        g = M.RleBWT(superblock_shift=sb_shift)
+        g.load_vector(rle)
+        db, da, dc = g.device_image()
+        assert db.shape == hb.shape and (db == hb).all()
+        assert (da == ha).all()
+        assert dc.shape == hc.shape and (dc == hc).all()
+        o = O.RleBWT()
+        o.load_vector(rle)
+        assert g.get_total_size() == o.get_total_size()
+        assert [g.get_symbol_count(s) for s in range(6)] == [o.get_symbol_count(s) for s in range(6)]
+        assert [g.start_index(s) for s in range(6)] == [o.start_index(s) for s in range(6)]
+
+
+def test_host_build_path_still_answers_identically(monkeypatch, midsize):
+    from harness import synth
+    reads, g, o = midsize
+    monkeypatch.setenv("MSBWT_HOST_BUILD", "1")
+    h = M.RleBWT()
+    h.load_vector(o.rle_bytes())
+    q = synth.make_queries(reads, 25, 5000, 5000).cpu().numpy()
+    assert (h.count_kmers_fixed(q, 25) == g.count_kmers_fixed(q, 25)).all()
