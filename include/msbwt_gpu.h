@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MSBWT_ABI_VERSION 1
+#define MSBWT_ABI_VERSION 2
 
 /* Return codes.  The reference panics where we return EINVAL / EFORMAT; the
  * Rust shim turns those back into panics to keep trait behaviour
@@ -78,6 +78,22 @@ msbwt_index *msbwt_index_create_from_npy(const char *path, const int *devices, i
 msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
                                    uint32_t superblock_shift, int suffix_table_s, int *err);
 
+/* The same with every knob in one growable struct (set struct_size = sizeof(msbwt_options)).
+ * `pair_index`: the PAIR image -- one 128-byte line per 96 BWT positions that answers TWO
+ * constrain_range steps with one line fill (layout.h) -- is built next to the one-step blocks when
+ * the index lives in HBM (-1 = automatic: one-step blocks + suffix table > 2 x L2; the
+ * MSBWT_PAIR_INDEX=0|1 environment variable overrides), 0 = never, 1 = always.  Results are
+ * identical either way.  `kernel_lanes`: 0 = automatic, 1 or 2 (see msbwt_kernel_lanes). */
+typedef struct msbwt_options {
+    uint32_t struct_size;
+    uint32_t superblock_shift; /* 0 = default */
+    int32_t suffix_table_s;    /* -1 = automatic */
+    int32_t pair_index;        /* -1 = automatic */
+    int32_t kernel_lanes;      /* 0 = automatic */
+} msbwt_options;
+msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
+                                     const msbwt_options *opts, int *err);
+
 void msbwt_index_destroy(msbwt_index *idx);
 
 /* ---- accessors: get_total_size / get_symbol_count (src/rle_bwt.rs:172-193) ---- */
@@ -92,6 +108,7 @@ int msbwt_suffix_table_s(const msbwt_index *idx);     /* suffix table depth in u
 /* lanes per query of the search kernel chosen for this index: 1 = one thread per query (index
  * L2-resident), 2 = a lane pair per query (index in HBM); MSBWT_LANES=1|2 overrides at create */
 int msbwt_kernel_lanes(const msbwt_index *idx);
+int msbwt_pair_index(const msbwt_index *idx); /* 1 when the pair image is in use */
 
 /* ---- queries from HOST buffers (the drop-in calls) ---- */
 
@@ -170,6 +187,11 @@ int msbwt_debug_build_image(const uint8_t *rle, uint64_t len, uint32_t superbloc
  * is built on the device (builder.cu); tests compare it with the host builder's word for word. */
 int msbwt_debug_copy_image(const msbwt_index *idx, int slot, uint64_t *nblocks, uint32_t *n_super,
                            uint32_t *blocks, uint32_t *aux, uint64_t *cbase);
+
+/* The pair image of a replica: *npair lines of 32 u32 words; *n_super2 rows of 16 u64 in c2base
+ * (0 rows when positions are 32-bit: the checkpoints are then absolute).  NULL arrays: sizes only. */
+int msbwt_debug_copy_pair_image(const msbwt_index *idx, int slot, uint64_t *npair, uint32_t *n_super2,
+                                uint32_t *lines, uint64_t *c2base);
 
 /* ---- pinned host buffers for callers that want full copy/compute overlap ---- */
 void *msbwt_host_alloc(size_t bytes);

@@ -16,8 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmsbwt_b200.so")
-SOURCES = ["capi.cu", "kernels.cu", "loader.cu", "builder.cu"]
-HEADERS = ["engine.h", "layout.h", os.path.join(ROOT, "include", "msbwt_gpu.h")]
+SOURCES = ["capi.cu", "kernels.cu", "loader.cu", "builder.cu", "pair_builder.cu"]
+HEADERS = ["engine.h", "layout.h", "device_rank.cuh", os.path.join(ROOT, "include", "msbwt_gpu.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

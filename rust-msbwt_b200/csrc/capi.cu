@@ -69,6 +69,8 @@ struct Replica {
     uint4 *d_blocks = nullptr;
     uint32_t *d_aux = nullptr;
     void *d_table = nullptr;
+    void *d_table2 = nullptr;  // suffix table of depth table_s - 1 (kept for the pair path's parity choice)
+    PairImage pair;            // 128-byte pair lines (layout.h), when the index lives in HBM
     int lanes = 1;           // kernel mapping: 1 = thread per query, 2 = lane pair per query (kernels.cu)
     uint64_t *d_cbase = nullptr;
     IndexView view{};
@@ -94,6 +96,8 @@ struct Replica {
         if (d_blocks) cudaFree(d_blocks);
         if (d_aux) cudaFree(d_aux);
         if (d_table) cudaFree(d_table);
+        if (d_table2) cudaFree(d_table2);
+        free_pair_image(pair);
         if (d_cbase) cudaFree(d_cbase);
         cudaSetDevice(cur);
     }
@@ -211,6 +215,13 @@ int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev)
 // depth at which a read set's BWT ranges stop being shared between unrelated k-mers.
 constexpr int kAutoMaxTableS = 13;
 
+struct Options {
+    uint32_t sb_shift = 0;
+    int table_s = -1;   // -1 auto
+    int pair = -1;      // -1 auto, 0 off, 1 on
+    int lanes = 0;      // 0 auto, 1, 2
+};
+
 int pick_table_s(uint64_t total, int requested) {
     if (requested >= 0) return requested > kMaxTableS ? kMaxTableS : requested;
     if (const char *env = getenv("MSBWT_SUFFIX_TABLE_S")) {
@@ -224,11 +235,40 @@ int pick_table_s(uint64_t total, int requested) {
 
 // Kernel mapping (kernels.cu): one thread per query while blocks + table are (mostly) L2-resident,
 // a lane pair per query -- one coalesced 64-byte request per block -- once they live in HBM.
-int pick_lanes(int device, uint64_t index_bytes) {
-    if (const char *env = getenv("MSBWT_LANES")) return atoi(env) == 2 ? 2 : 1;
+bool lives_in_hbm(int device, uint64_t index_bytes) {
     int l2 = 0;
     if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device) != cudaSuccess || l2 <= 0) l2 = 96 << 20;
-    return index_bytes > 2ull * (uint64_t)l2 ? 2 : 1;
+    return index_bytes > 2ull * (uint64_t)l2;
+}
+
+int pick_lanes(int device, uint64_t index_bytes, int requested) {
+    if (requested == 1 || requested == 2) return requested;
+    if (const char *env = getenv("MSBWT_LANES")) return atoi(env) == 2 ? 2 : 1;
+    return lives_in_hbm(device, index_bytes) ? 2 : 1;
+}
+
+// The pair image (layout.h: one 128-byte line per two steps) pays off once the index lives in HBM;
+// an L2-resident index is served faster by the 64-byte one-step blocks (smaller footprint).
+bool pick_pair(int device, uint64_t index_bytes, int requested) {
+    if (requested == 0 || requested == 1) return requested == 1;
+    if (const char *env = getenv("MSBWT_PAIR_INDEX")) return atoi(env) != 0;
+    return lives_in_hbm(device, index_bytes);
+}
+
+int build_pair(msbwt_index *idx, Replica &rep) {
+    DeviceGuard guard(rep.device);
+    std::string why;
+    int n = 0;
+    int rc = build_pair_image_on_device(rep.device, rep.view, idx->start, rep.pair, why, &n);
+    g_launches += (uint64_t)n;
+    if (rc != MSBWT_OK) { free_pair_image(rep.pair); return fail(rc, why); }
+    rep.view.pair = rep.pair.lines;
+    rep.view.c2base = rep.pair.c2base;
+    rep.view.npair = rep.pair.npair;
+    rep.view.n_super2 = rep.pair.n_super2;
+    if (idx->reps[0].get() == &rep)
+        idx->bytes_per_replica += rep.pair.npair * kPairBytes + (rep.pair.c2base ? (uint64_t)rep.pair.n_super2 * 16 * sizeof(uint64_t) : 0);
+    return MSBWT_OK;
 }
 
 int build_suffix_table(msbwt_index *idx, Replica &rep, int s) {
@@ -252,21 +292,25 @@ int build_suffix_table(msbwt_index *idx, Replica &rep, int s) {
         g_launches++;
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    cudaFree(tmp);
+    const bool keep2 = rep.view.pair != nullptr && s >= 2;  // level s-1 ended up in `tmp`
+    if (!keep2 || e != cudaSuccess) cudaFree(tmp);
     if (e != cudaSuccess) {
         cudaFree(fin);
         return fail(MSBWT_ECUDA, std::string("suffix table build: ") + cudaGetErrorString(e));
     }
     rep.d_table = fin;
     rep.view.table = fin;
+    if (keep2) { rep.d_table2 = tmp; rep.view.table2 = tmp; }
     rep.view.table_s = (uint32_t)s;
     idx->table_s = (uint32_t)s;
-    idx->bytes_per_replica += (idx->reps[0].get() == &rep) ? entries * eb : 0;
+    idx->bytes_per_replica += (idx->reps[0].get() == &rep) ? entries * eb + (keep2 ? (entries / 4) * eb : 0) : 0;
     return MSBWT_OK;
 }
 
-msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices, int ndev, uint32_t sb_shift,
-                           int table_s, int *err) {
+msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices, int ndev, const Options &opt,
+                           int *err) {
+    const uint32_t sb_shift = opt.sb_shift;
+    const int table_s = opt.table_s;
     g_last_error.clear();
     int rc;
     std::string why;
@@ -284,10 +328,13 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
     }
     if (rc == MSBWT_OK) {
         const int s = pick_table_s(idx->total, table_s);
+        const bool wide = index_is_wide(idx->reps[0]->view);
+        const uint64_t one_step_bytes = idx->bytes_per_replica + (s > 0 ? (1ull << (2 * s)) * (wide ? 16 : 8) : 0);
         for (auto &rep : idx->reps) {
+            if (pick_pair(rep->device, one_step_bytes, opt.pair) && (rc = build_pair(idx.get(), *rep)) != MSBWT_OK) break;
             rc = build_suffix_table(idx.get(), *rep, s);
             if (rc != MSBWT_OK) break;
-            rep->lanes = pick_lanes(rep->device, idx->bytes_per_replica);
+            rep->lanes = pick_lanes(rep->device, one_step_bytes, opt.lanes);
         }
     }
     if (err) *err = rc;
@@ -313,12 +360,32 @@ int check_status_flags(msbwt_index const *idx, const char *what) {
 
 extern "C" msbwt_index *msbwt_index_create_from_rle(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
                                                    int *err) {
-    return create_common(rle, len, devices, ndev, 0, -1, err);
+    return create_common(rle, len, devices, ndev, Options{}, err);
 }
 
 extern "C" msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
                                              uint32_t superblock_shift, int suffix_table_s, int *err) {
-    return create_common(rle, len, devices, ndev, superblock_shift, suffix_table_s, err);
+    Options o;
+    o.sb_shift = superblock_shift;
+    o.table_s = suffix_table_s;
+    return create_common(rle, len, devices, ndev, o, err);
+}
+
+extern "C" msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
+                                               const msbwt_options *opts, int *err) {
+    Options o;
+    if (opts) {
+        if (opts->struct_size < sizeof(msbwt_options)) {
+            fail(MSBWT_EINVAL, "msbwt_options.struct_size is smaller than this library's msbwt_options");
+            if (err) *err = MSBWT_EINVAL;
+            return nullptr;
+        }
+        o.sb_shift = opts->superblock_shift;
+        o.table_s = opts->suffix_table_s;
+        o.pair = opts->pair_index;
+        o.lanes = opts->kernel_lanes;
+    }
+    return create_common(rle, len, devices, ndev, o, err);
 }
 
 extern "C" msbwt_index *msbwt_index_create_from_npy(const char *path, const int *devices, int ndev, int *err) {
@@ -331,7 +398,7 @@ extern "C" msbwt_index *msbwt_index_create_from_npy(const char *path, const int 
         if (err) *err = rc;
         return nullptr;
     }
-    return create_common(payload.data(), payload.size(), devices, ndev, 0, -1, err);
+    return create_common(payload.data(), payload.size(), devices, ndev, Options{}, err);
 }
 
 extern "C" void msbwt_index_destroy(msbwt_index *idx) { delete idx; }
@@ -353,6 +420,7 @@ extern "C" int msbwt_device_ordinal(const msbwt_index *idx, int slot) {
 extern "C" uint64_t msbwt_index_bytes(const msbwt_index *idx) { return idx ? idx->bytes_per_replica : 0; }
 extern "C" int msbwt_suffix_table_s(const msbwt_index *idx) { return idx ? (int)idx->table_s : 0; }
 extern "C" int msbwt_kernel_lanes(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->lanes : 0; }
+extern "C" int msbwt_pair_index(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.pair) ? 1 : 0; }
 extern "C" uint64_t msbwt_launch_count(void) { return g_launches.load(); }
 extern "C" const char *msbwt_last_error(void) { return g_last_error.c_str(); }
 extern "C" int msbwt_abi_version(void) { return MSBWT_ABI_VERSION; }
@@ -663,6 +731,20 @@ extern "C" int msbwt_debug_copy_image(const msbwt_index *idx, int slot, uint64_t
     if (blocks) CU_TRY(cudaMemcpy(blocks, rep.d_blocks, rep.view.nblocks * kBlockBytes, cudaMemcpyDeviceToHost));
     if (aux) CU_TRY(cudaMemcpy(aux, rep.d_aux, rep.view.nblocks * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (cbase) CU_TRY(cudaMemcpy(cbase, rep.d_cbase, (size_t)rep.view.n_super * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return MSBWT_OK;
+}
+
+extern "C" int msbwt_debug_copy_pair_image(const msbwt_index *idx, int slot, uint64_t *npair, uint32_t *n_super2,
+                                           uint32_t *lines, uint64_t *c2base) {
+    g_last_error.clear();
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size() || !npair || !n_super2) return fail(MSBWT_EINVAL, "bad handle, slot or size outputs");
+    const Replica &rep = *idx->reps[slot];
+    if (!rep.view.pair) return fail(MSBWT_EINVAL, "this index has no pair image");
+    DeviceGuard guard(rep.device);
+    *npair = rep.view.npair;
+    *n_super2 = rep.view.c2base ? rep.view.n_super2 : 0;
+    if (lines) CU_TRY(cudaMemcpy(lines, rep.view.pair, rep.view.npair * kPairBytes, cudaMemcpyDeviceToHost));
+    if (c2base && rep.view.c2base) CU_TRY(cudaMemcpy(c2base, rep.view.c2base, (size_t)rep.view.n_super2 * 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return MSBWT_OK;
 }
 

@@ -47,6 +47,17 @@ struct DeviceImage {
 int build_image_on_device(const uint8_t *h_rle, uint64_t len, uint32_t sb_shift, DeviceImage &img, std::string &why);
 void free_device_image(DeviceImage &img);
 
+// ---- pair_builder.cu: one-step image (resident on the current device) -> pair image ----
+struct PairImage {
+    uint4 *lines = nullptr;      // npair * 128 B
+    uint64_t *c2base = nullptr;  // n_super2 * 16, WIDE only
+    uint64_t npair = 0;
+    uint32_t n_super2 = 0;
+};
+int build_pair_image_on_device(int device, const IndexView &ix, const uint64_t start[kAlphabet], PairImage &img,
+                               std::string &why, int *launches);
+void free_pair_image(PairImage &img);
+
 // return an msbwt_status; on failure `why` explains
 int validate_rle(const uint8_t *rle, uint64_t len, std::string &why);
 int build_image_from_rle(const uint8_t *rle, uint64_t len, uint32_t sb_shift, HostImage &img, std::string &why);
@@ -58,15 +69,20 @@ cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_
 cudaError_t launch_table_extend(int device, const IndexView &ix, const void *d_parent, void *d_child,
                                 uint32_t n_child, cudaStream_t st);
 bool index_is_wide(const IndexView &ix);
-// Device scratch produced by pack_seed_kernel and consumed by count_kmers_packed_kernel
-// (all u64 units, n = queries in the batch, `words` = words_for_k(k)):
-//   [0, n)                      W0    first symbol word of the i-th LIVE query      (compacted)
-//   [n, n + seedw*n)            SEED  starting range: l | h<<32, or l then h (WIDE)   (compacted)
-//   [.., + (n+1)/2)             QIDX  u32 original query index of the i-th live query (compacted)
+// Device scratch produced by pack_seed_kernel and consumed by the search kernels (all u64 units,
+// n = queries in the batch, `words` = words_for_k(k)).  Two compacted live lists share the arrays:
+// list A (pair path: every remaining symbol is ACGT and their number is even) grows from index 0
+// upwards, list B (one-step path) from index n-1 downwards.
+//   [0, n)                      W0    first symbol word of a live query: A = 32 x 2-bit symbols,
+//                                     B = 21 x 3-bit symbols, first-consumed symbol in the top bits
+//   [n, n + seedw*n)            SEED  starting range: l | h<<32, or l then h (WIDE)
+//   [.., + (n+1)/2)             QIDX  u32: original query index | table depth used << 30
+//                                     (0 = none, 1 = table_s, 2 = table_s - 1)
 //   [.., + (words-1)*n)         WX    symbol words 1.. of query q, word-major, by ORIGINAL index
-//   [.., + 1)                   LIVE  number of live queries (u64 counter)
+//   [.., + 2)                   LIVE  number of live queries in list A, list B (u64 counters)
 // Queries that need no search step (empty seed range, or the suffix table answered every symbol)
-// are finished by the pack kernel itself and never reach the search kernel.
+// are finished by the pack kernel itself and never reach the search kernels.
+constexpr uint32_t kQidxMask = (1u << 30) - 1u;
 struct PackedLayout {
     uint64_t n;
     uint32_t words, seedw;
@@ -75,12 +91,13 @@ struct PackedLayout {
     __host__ __device__ uint64_t qidx() const { return n + (uint64_t)seedw * n; }
     __host__ __device__ uint64_t wx() const { return qidx() + (n + 1) / 2; }
     __host__ __device__ uint64_t live() const { return wx() + (uint64_t)(words - 1) * n; }
-    __host__ __device__ uint64_t total() const { return live() + 1; }
+    __host__ __device__ uint64_t total() const { return live() + 2; }
 };
 inline PackedLayout packed_layout(const IndexView &ix, uint32_t k, uint64_t n) {
     return PackedLayout{n, words_for_k(k), index_is_wide(ix) ? 2u : 1u};
 }
-// `launches` (optional) is incremented once per kernel launch issued
+// `launches` (optional) is incremented once per kernel launch issued.  Runs the pair kernel over
+// list A (when the index has a pair image) and the one-step kernel over list B.
 cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, const uint64_t *d_packed, uint32_t k,
                                 uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches);
 cudaError_t launch_count_bytes(int device, const IndexView &ix, const uint8_t *d_syms,

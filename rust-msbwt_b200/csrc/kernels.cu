@@ -14,257 +14,180 @@
 //              request per block -- HBM serves ~39 G random requests/s whatever their
 //              size, so one request per rank matters more than instruction count), counts
 //              its 64 symbols, and three shuffles combine the pair.
-// In both, a lane (pair) whose k-mer ends refills itself from its own query stream, so
+// A third kernel walks the PAIR image (layout.h): a quad of lanes per query, one coalesced
+// 128-byte line per TWO backward-search steps -- the mapping for an index that lives in HBM,
+// where every L2 miss costs a whole 128-byte line fill whatever the request size.
+// In all of them a lane (group) whose k-mer ends refills itself from its own query stream, so
 // every lane of a warp stays busy.  (v1-v3 used 8- then 4-lane groups per query; ncu
 // showed them issue-bound at ~12 warp instructions per query-step -- profiles/.)
 #include <type_traits>
 
+#include "device_rank.cuh"
 #include "engine.h"
 
 namespace msbwt {
 
-// ---------------------------------------------------------------- device helpers
-
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-
-struct Half { uint32_t w[8]; };  // 32 bytes = one sector of a block
-
-// half an index block: read-only path, no L1 allocation, evict-last in L2 (256-bit load)
-__device__ __forceinline__ Half ldg_index256(const void *p) {
-    Half r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
-                   "=r"(r.w[7])
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint4 ldg_plain(const uint4 *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-// streaming data (packed queries, results): do not let it displace the index in L2
-__device__ __forceinline__ uint64_t ldg_stream(const uint64_t *p, uint64_t pol) {
-    uint64_t r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ void stg_stream(uint64_t *p, uint64_t v, uint64_t pol) {
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
-}
-
-__device__ __forceinline__ uint32_t below_mask(int nbits) {
-    // mask of the low `nbits` bits, nbits clamped to [0,32]
-    uint32_t m;
-    int w = max(nbits, 0);
-    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0), "r"(w));
-    return m;
-}
-
-template <bool WIDE> struct Pos { using type = uint32_t; };
-template <> struct Pos<true> { using type = uint64_t; };
-
-// Per-CTA constants: C array (+ superblock bases).  NARROW (N < 2^32, one superblock):
-// 8 x u32 in shared memory.  WIDE: u64 rows per superblock, shared memory when they fit.
-template <bool WIDE> struct CBase;
-template <> struct CBase<false> {
-    const uint32_t *c;
-    __device__ __forceinline__ uint32_t at(uint32_t, uint32_t sym) const { return c[sym]; }
-};
-template <> struct CBase<true> {
-    const uint64_t *c;
-    uint32_t sb_shift;
-    __device__ __forceinline__ uint64_t at(uint64_t blk, uint32_t sym) const { return c[((blk >> sb_shift) << 3) + sym]; }
-};
-
-template <bool WIDE>
-__device__ __forceinline__ CBase<WIDE> stage_cbase(const IndexView &ix, uint64_t *smem) {
-    if constexpr (WIDE) {
-        if (ix.n_super > (uint32_t)kMaxSuperInSmem) return CBase<true>{ix.cbase, ix.sb_shift};
-        for (uint32_t i = threadIdx.x; i < ix.n_super * 8u; i += blockDim.x) smem[i] = ix.cbase[i];
-        __syncthreads();
-        return CBase<true>{smem, ix.sb_shift};
-    } else {
-        uint32_t *s32 = reinterpret_cast<uint32_t *>(smem);
-        if (threadIdx.x < 8) s32[threadIdx.x] = (uint32_t)ix.cbase[threadIdx.x];
-        __syncthreads();
-        return CBase<false>{s32};
-    }
-}
-
-// the 64 match bits of one half for the symbol selected by the plane-inversion masks
-__device__ __forceinline__ void match_half(const Half &v, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t &m0,
-                                           uint32_t &m1) {
-    m0 = (v.w[2] ^ x0) & (v.w[4] ^ x1) & (v.w[6] ^ x2);
-    m1 = (v.w[3] ^ x0) & (v.w[5] ^ x1) & (v.w[7] ^ x2);
-}
-
-// occurrences among 64 match bits at half offsets < p (p may be <= 0 or >= 64)
-__device__ __forceinline__ uint32_t count_below64(uint32_t m0, uint32_t m1, int p) {
-    return __popc(m0 & below_mask(p)) + __popc(m1 & below_mask(p - 32));
-}
-
-// One constrain_range: [l,h) -> [C[sym]+rank(sym,l), C[sym]+rank(sym,h)).
-// LANES == 1: the calling thread does all of it.  LANES == 2: the two lanes of a pair call
-// it together with identical (sym, l, h); `half` = lane & 1.  Every non-exited lane of the warp
-// reaches the shuffles in the same iteration of the caller's loop (lanes leave only by returning),
-// so they use the full mask -- a per-pair mask would make ptxas emit MATCH/REDUX guards.
-template <bool WIDE, int LANES>
-__device__ __forceinline__ void rank_step(const IndexView &ix, const CBase<WIDE> &cb, uint32_t sym,
-                                          typename Pos<WIDE>::type &l, typename Pos<WIDE>::type &h,
-                                          uint32_t half = 0) {
-    using P = typename Pos<WIDE>::type;
-    const P bl = l >> kBlockShift, bh = h >> kBlockShift;
-    const bool two = bh != bl;
-    const char *base = reinterpret_cast<const char *>(ix.blocks);
-    const uint32_t x0 = (sym & 1u) - 1u, x1 = ((sym >> 1) & 1u) - 1u, x2 = ((sym >> 2) & 1u) - 1u;  // 0 or ~0
-    const uint32_t slot = (sym - 1u - (sym >> 2)) & 3u;  // ckpt_slot(sym) for A,C,G,T
-    const int pl = (int)((uint32_t)l & (kBlockSyms - 1)), ph = (int)((uint32_t)h & (kBlockSyms - 1));
-    uint32_t ckl, ckh, cl, ch;
-    if constexpr (LANES == 1) {
-        // issue every load before the first use: up to four 32-byte sectors in flight per thread
-        const Half l0 = ldg_index256(base + (size_t)bl * kBlockBytes);
-        const Half l1 = ldg_index256(base + (size_t)bl * kBlockBytes + 32);
-        Half h0, h1;
-        if (two) {
-            h0 = ldg_index256(base + (size_t)bh * kBlockBytes);
-            h1 = ldg_index256(base + (size_t)bh * kBlockBytes + 32);
-        }
-        uint32_t ml[4], mh[4];
-        match_half(l0, x0, x1, x2, ml[0], ml[1]);
-        match_half(l1, x0, x1, x2, ml[2], ml[3]);
-        const uint32_t lo = (slot & 1u) ? l0.w[1] : l0.w[0], hi = (slot & 1u) ? l1.w[1] : l1.w[0];
-        ckl = (slot & 2u) ? hi : lo;
-        ckh = ckl;
-#pragma unroll
-        for (int j = 0; j < 4; j++) mh[j] = ml[j];
-        if (two) {
-            match_half(h0, x0, x1, x2, mh[0], mh[1]);
-            match_half(h1, x0, x1, x2, mh[2], mh[3]);
-            const uint32_t lo2 = (slot & 1u) ? h0.w[1] : h0.w[0], hi2 = (slot & 1u) ? h1.w[1] : h1.w[0];
-            ckh = (slot & 2u) ? hi2 : lo2;
-        }
-        cl = count_below64(ml[0], ml[1], pl) + count_below64(ml[2], ml[3], pl - 64);
-        ch = count_below64(mh[0], mh[1], ph) + count_below64(mh[2], mh[3], ph - 64);
-    } else {
-        const Half a = ldg_index256(base + (size_t)bl * kBlockBytes + half * 32);
-        Half b;
-        if (two) b = ldg_index256(base + (size_t)bh * kBlockBytes + half * 32);
-        uint32_t ml0, ml1, mh0, mh1;
-        match_half(a, x0, x1, x2, ml0, ml1);
-        uint32_t cand_l = (slot & 1u) ? a.w[1] : a.w[0], cand_h = cand_l;
-        mh0 = ml0; mh1 = ml1;
-        if (two) {
-            match_half(b, x0, x1, x2, mh0, mh1);
-            cand_h = (slot & 1u) ? b.w[1] : b.w[0];
-        }
-        const int off = (int)half * 64;
-        uint32_t cnt = count_below64(ml0, ml1, pl - off) | (count_below64(mh0, mh1, ph - off) << 16);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
-        ckl = __shfl_sync(0xffffffffu, cand_l, slot >> 1, 2);  // the half that owns this symbol's checkpoint
-        ckh = __shfl_sync(0xffffffffu, cand_h, slot >> 1, 2);
-        cl = cnt & 0xffffu;
-        ch = cnt >> 16;
-    }
-    if ((0x11u >> sym) & 1u) {  // $ or N: checkpoints live in the side array
-        ckl = __ldg(ix.aux + (size_t)bl * 2 + (sym >> 2));
-        ckh = __ldg(ix.aux + (size_t)bh * 2 + (sym >> 2));
-    }
-    l = cb.at(bl, sym) + ckl + cl;
-    h = cb.at(bh, sym) + ckh + ch;
-}
-
 // ---------------------------------------------------------------- K0: pack + validate + seed
 
-// One thread per query: validate (symbol >= 6 sets *status), look the last table_s symbols up in
-// the suffix table when they are all ACGT (that many steps are then already done), pack the
-// REMAINING symbols 21 per u64 word (step t of the remaining search in bits 62-3(t%21) .. of word
-// t/21; step order = from the k-mer's last symbol to its first), and
-//   * finish the query right here when nothing is left to search (empty range -> count 0,
-//     msbwt_core.rs:151-153; or no symbols left -> h-l), or
-//   * append it to the compacted live list (PackedLayout) for the search kernel.
+// One thread per query.  The CTA first stages its 256 * k query bytes in shared memory with
+// coalesced 16-byte loads (the per-thread layout is k-byte rows: read straight from global memory
+// it costs one sector per byte load), then every thread
+//   1. validates its k symbols (symbol >= 6 sets *status) and takes the base-4 value of its last
+//      min(k, table_s) symbols,
+//   2. picks the path: PAIR (list A) when the index has a pair image and the whole k-mer is ACGT --
+//      the suffix-table depth is then chosen from {table_s, table_s - 1} so that an EVEN number of
+//      symbols is left -- otherwise ONE-STEP (list B) with depth table_s when the last table_s
+//      symbols are ACGT,
+//   3. looks the starting range up, packs the REMAINING symbols (step t of the remaining search in
+//      the top bits of word t/32 (A, 2 bits each) or t/21 (B, 3 bits each); step order = from the
+//      k-mer's last symbol to its first), and
+//   4. finishes the query right here when nothing is left to search (empty range -> count 0,
+//      msbwt_core.rs:151-153; or no symbols left -> h-l), or appends it to its live list.
+constexpr uint32_t kPackSmemMaxK = 160;  // 256 * k + 16 bytes of shared memory; longer k-mers read global memory
+
 template <bool WIDE>
-__global__ void pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, PackedLayout lay,
-                                 uint64_t *__restrict__ packed, uint64_t *__restrict__ out,
-                                 uint32_t *__restrict__ status) {
-    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, PackedLayout lay,
+                 uint64_t *__restrict__ packed, uint64_t *__restrict__ out, uint32_t *__restrict__ status) {
+    extern __shared__ uint4 pack_smem_v[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(pack_smem_v);
+    const uint64_t q0 = (uint64_t)blockIdx.x * blockDim.x;
+    const uint64_t q = q0 + threadIdx.x;
     const bool valid = q < lay.n;
     const uint8_t *src = syms + (valid ? q : 0) * k;
+    if (k <= kPackSmemMaxK) {
+        const uint8_t *g = syms + q0 * k;
+        const uint32_t rows = (uint32_t)min((uint64_t)blockDim.x, lay.n - q0);
+        const uint32_t bytes = rows * k;
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);  // smem mirrors the global alignment
+        const uint32_t head = min(bytes, (16u - mis) & 15u);
+        for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) smem[mis + i] = g[i];
+        const uint32_t vecs = (bytes - head) >> 4;
+        const uint4 *gv = reinterpret_cast<const uint4 *>(g + head);
+        uint4 *sv = reinterpret_cast<uint4 *>(smem + mis + head);
+        for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x) sv[i] = ldg_plain(gv + i);
+        for (uint32_t i = head + (vecs << 4) + threadIdx.x; i < bytes; i += blockDim.x) smem[mis + i] = g[i];
+        __syncthreads();
+        src = smem + mis + threadIdx.x * k;
+    }
     const uint32_t ts = ix.table_s;
-    bool bad = false, acgt = valid && (ts != 0 && k >= ts);
+    const bool have_pair = ix.pair != nullptr;
+
+    // 1. validate; is the whole k-mer ACGT; trailing ACGT run (at most ts symbols) as a base-4 number
+    bool bad = false, all_acgt = true;
+    uint32_t na = 0;
     uint64_t tidx = 0;
-    if (acgt) {  // the last ts symbols: table index + validation in one pass
-        for (uint32_t t = 0; t < ts; t++) {
-            const uint32_t sy = src[k - 1 - t];
-            bad |= sy >= (uint32_t)kAlphabet;
-            acgt &= sy < 8u && ((0x2Eu >> sy) & 1u) != 0;  // {1,2,3,5}
-            tidx = (tidx << 2) | ((sy - 1u - (sy >> 2)) & 3u);
-        }
-    }
-    uint64_t lo = 0, hi = ix.total;
-    uint32_t done = 0;
-    if (acgt) {
-        if constexpr (WIDE) {
-            const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(ix.table) + tidx);
-            lo = e.x; hi = e.y;
-        } else {
-            const uint2 e = __ldg(reinterpret_cast<const uint2 *>(ix.table) + tidx);
-            lo = e.x; hi = e.y;
-        }
-        done = ts;
-    }
-    // pack (and validate) the symbols the table did not consume
-    uint64_t word0 = 0;
     if (valid) {
-        const uint32_t rest = k - done;
-        for (uint32_t w = 0; w * kSymsPerWord < rest; w++) {
-            const uint32_t t0 = w * kSymsPerWord;
-            const uint32_t cnt = min((uint32_t)kSymsPerWord, rest - t0);
-            uint64_t word = 0;
-            for (uint32_t i = 0; i < cnt; i++) {
-                const uint32_t sy = src[k - 1 - (done + t0 + i)];
-                bad |= (sy >= (uint32_t)kAlphabet);
-                word |= (uint64_t)(sy & 7u) << (60 - 3 * i);
+        for (uint32_t t = 0; t < k; t++) {
+            const uint32_t sy = src[k - 1 - t];
+            const bool ok = sy < 8u && ((0x2Eu >> sy) & 1u) != 0;  // {1,2,3,5}
+            bad |= sy >= (uint32_t)kAlphabet;
+            all_acgt &= ok;
+            if (t < ts && na == t && ok) {
+                tidx = (tidx << 2) | ((sy - 1u - (sy >> 2)) & 3u);
+                na++;
             }
-            if (w == 0) word0 = word; else packed[lay.wx() + (uint64_t)(w - 1) * lay.n + q] = word;
+        }
+    }
+    // 2. path and table depth
+    uint32_t done = 0;
+    bool list_a = false;
+    if (valid) {
+        if (have_pair && all_acgt) {
+            if (ts && k >= ts) done = ((k - ts) & 1u) ? ts - 1u : ts;
+            else if (ts && k + 1u == ts) done = k;
+            list_a = ((k - done) & 1u) == 0;
+        } else if (ts && na >= ts) {
+            done = ts;
+        }
+    }
+    // 3. starting range
+    uint64_t lo = 0, hi = ix.total;
+    uint32_t flag = 0;
+    if (done) {
+        const bool full = done == ts;
+        flag = full ? 1u : 2u;
+        const uint64_t e = tidx >> (2u * (na - done));
+        const void *tab = full ? ix.table : ix.table2;
+        if constexpr (WIDE) {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(tab) + e);
+            lo = v.x; hi = v.y;
+        } else {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(tab) + e);
+            lo = v.x; hi = v.y;
         }
     }
     const bool finished = valid && (lo == hi || done == k);
     if (finished) out[q] = hi - lo;
     const bool live = valid && !finished;
-    // warp-aggregated append to the live list
-    const uint32_t mask = __ballot_sync(0xffffffffu, live);
-    if (mask) {
-        const uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(reinterpret_cast<unsigned long long *>(packed + lay.live()), (unsigned long long)__popc(mask));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (live) {
-            const uint64_t pos = base + __popc(mask & ((1u << lane) - 1u));
-            packed[lay.w0() + pos] = word0 | ((uint64_t)(done != 0) << 63);
-            if constexpr (WIDE) {
-                packed[lay.seed() + pos] = lo;
-                packed[lay.seed() + lay.n + pos] = hi;
-            } else {
-                packed[lay.seed() + pos] = lo | (hi << 32);
+    // pack the symbols the table did not consume
+    uint64_t word0 = 0;
+    if (live) {
+        const uint32_t rest = k - done;
+        if (list_a) {
+            for (uint32_t w = 0; w * kPairSymsPerWord < rest; w++) {
+                const uint32_t t0 = w * kPairSymsPerWord;
+                const uint32_t cnt = min((uint32_t)kPairSymsPerWord, rest - t0);
+                uint64_t word = 0;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const uint32_t sy = src[k - 1 - (done + t0 + i)];
+                    word |= (uint64_t)((sy - 1u - (sy >> 2)) & 3u) << (62 - 2 * i);
+                }
+                if (w == 0) word0 = word; else packed[lay.wx() + (uint64_t)(w - 1) * lay.n + q] = word;
             }
-            reinterpret_cast<uint32_t *>(packed + lay.qidx())[pos] = (uint32_t)q;
+        } else {
+            for (uint32_t w = 0; w * kSymsPerWord < rest; w++) {
+                const uint32_t t0 = w * kSymsPerWord;
+                const uint32_t cnt = min((uint32_t)kSymsPerWord, rest - t0);
+                uint64_t word = 0;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const uint32_t sy = src[k - 1 - (done + t0 + i)];
+                    word |= (uint64_t)(sy & 7u) << (60 - 3 * i);
+                }
+                if (w == 0) word0 = word; else packed[lay.wx() + (uint64_t)(w - 1) * lay.n + q] = word;
+            }
         }
+    }
+    // warp-aggregated append to the live lists (A from the front, B from the back)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t mask_a = __ballot_sync(0xffffffffu, live && list_a);
+    const uint32_t mask_b = __ballot_sync(0xffffffffu, live && !list_a);
+    unsigned long long *counters = reinterpret_cast<unsigned long long *>(packed + lay.live());
+    uint64_t pos = 0;
+    if (mask_a) {
+        const uint32_t leader = __ffs(mask_a) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(counters, (unsigned long long)__popc(mask_a));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (live && list_a) pos = base + __popc(mask_a & ((1u << lane) - 1u));
+    }
+    if (mask_b) {
+        const uint32_t leader = __ffs(mask_b) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(counters + 1, (unsigned long long)__popc(mask_b));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (live && !list_a) pos = lay.n - 1 - (base + __popc(mask_b & ((1u << lane) - 1u)));
+    }
+    if (live) {
+        packed[lay.w0() + pos] = word0;
+        if constexpr (WIDE) {
+            packed[lay.seed() + pos] = lo;
+            packed[lay.seed() + lay.n + pos] = hi;
+        } else {
+            packed[lay.seed() + pos] = lo | (hi << 32);
+        }
+        reinterpret_cast<uint32_t *>(packed + lay.qidx())[pos] = (uint32_t)q | (flag << 30);
     }
     if (bad) atomicOr(status, 1u);
 }
 
 // ---------------------------------------------------------------- K1: count_kmers
 
-// Persistent kernel: every owner -- a thread (LANES = 1) or a lane pair (LANES = 2) -- walks its
-// own stream of live queries (i, i+T, i+2T, ... of the compacted list) and refills itself as soon
-// as its current k-mer is finished.  The next query's first word, seed and index are loaded one
+__device__ __forceinline__ uint32_t table_depth(uint32_t flag, uint32_t ts) { return flag == 0 ? 0u : (flag == 1 ? ts : ts - 1u); }
+
+// Persistent kernel over live list B: every owner -- a thread (LANES = 1) or a lane pair (LANES = 2) --
+// walks its own stream of live queries (i, i+T, i+2T, ... of the compacted list) and refills itself as
+// soon as its current k-mer is finished.  The next query's first word, seed and index are loaded one
 // query ahead and the next symbol word 21 steps ahead, so neither exposes memory latency.
 template <bool WIDE, int LANES>
 __global__ void __launch_bounds__(kCountThreads, min_ctas(WIDE, LANES))
@@ -275,12 +198,13 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, Pac
     const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
     const uint64_t stream = policy_evict_first();
 
-    const uint32_t n = (uint32_t)packed[lay.live()];  // live queries (written by the pack kernel)
+    const uint32_t n = (uint32_t)packed[lay.live() + 1];  // live queries of list B (written by the pack kernel)
     const uint32_t tid = blockIdx.x * kCountThreads + threadIdx.x;
     const uint32_t owners = gridDim.x * kCountThreads / LANES;  // concurrent query streams
     const uint32_t half = tid & (LANES - 1);
     uint32_t i = tid / LANES;
     if (i >= n) return;
+    const uint32_t last = (uint32_t)lay.n - 1u;  // list B is stored back to front
     const uint64_t *w0 = packed + lay.w0(), *seeds = packed + lay.seed(), *wx = packed + lay.wx();
     const uint32_t *qidx = reinterpret_cast<const uint32_t *>(packed + lay.qidx());
     const uint32_t ts = ix.table_s;
@@ -294,16 +218,17 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, Pac
     uint32_t widx = 0;  // index of `word` within the query's remaining symbols
 
     auto prefetch = [&](uint32_t ii) {
-        next_word = ldg_stream(w0 + ii, stream);
-        next_lo = ldg_stream(seeds + ii, stream);
-        if constexpr (WIDE) next_hi = ldg_stream(seeds + lay.n + ii, stream);
-        next_q = __ldg(qidx + ii);
+        const uint32_t at = last - ii;
+        next_word = ldg_stream(w0 + at, stream);
+        next_lo = ldg_stream(seeds + at, stream);
+        if constexpr (WIDE) next_hi = ldg_stream(seeds + lay.n + at, stream);
+        next_q = __ldg(qidx + at);
     };
     auto begin = [&]() {  // start the prefetched query
         word = next_word;
-        q = next_q;
+        q = next_q & kQidxMask;
         if constexpr (WIDE) { l = next_lo; h = next_hi; } else { l = (uint32_t)next_lo; h = (uint32_t)(next_lo >> 32); }
-        rem = k - ((word >> 63) ? ts : 0u);  // the suffix table already answered ts steps
+        rem = k - table_depth(next_q >> 30, ts);  // the suffix table already answered that many steps
         shift = 60;
         widx = 0;
         if (rem > (uint32_t)kSymsPerWord) pend = ldg_stream(wx + q, stream);  // symbol word 1, needed 21 steps from now
@@ -332,6 +257,78 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, Pac
         rank_step<WIDE, LANES>(ix, cb, sym, l, h, half);
         rem--;
         shift -= 3;
+    }
+}
+
+// Persistent kernel over live list A: a quad of lanes per query walks the PAIR image, two symbols per
+// step (one 128-byte line per boundary); same refill / prefetch structure as above.
+constexpr int pair_min_ctas(bool wide) { return wide ? 4 : 6; }
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kCountThreads, pair_min_ctas(WIDE))
+count_kmers_pair_kernel(IndexView ix, const uint64_t *__restrict__ packed, PackedLayout lay, uint32_t k,
+                        uint64_t *__restrict__ out) {
+    using P = typename Pos<WIDE>::type;
+    __shared__ uint64_t c2_smem[WIDE ? kMaxSuperInSmem * 16 : 1];
+    const C2Base<WIDE> c2 = stage_c2base<WIDE>(ix, c2_smem);
+    const uint64_t stream = policy_evict_first();
+
+    const uint32_t n = (uint32_t)packed[lay.live()];  // live queries of list A
+    const uint32_t tid = blockIdx.x * kCountThreads + threadIdx.x;
+    const uint32_t owners = gridDim.x * kCountThreads / 4;
+    const uint32_t quarter = tid & 3u;
+    uint32_t i = tid >> 2;
+    if (i >= n) return;
+    const uint64_t *w0 = packed + lay.w0(), *seeds = packed + lay.seed(), *wx = packed + lay.wx();
+    const uint32_t *qidx = reinterpret_cast<const uint32_t *>(packed + lay.qidx());
+    const uint32_t ts = ix.table_s;
+
+    P l = 0, h = 0;
+    uint64_t word = 0, pend = 0, next_word = 0, next_lo = 0;
+    [[maybe_unused]] uint64_t next_hi = 0;
+    uint32_t q = 0, next_q = 0;
+    uint32_t rem = 0;   // symbols still to consume (even)
+    int shift = 60;     // bit offset of the next pair (4 bits) in `word`
+    uint32_t widx = 0;
+
+    auto prefetch = [&](uint32_t ii) {
+        next_word = ldg_stream(w0 + ii, stream);
+        next_lo = ldg_stream(seeds + ii, stream);
+        if constexpr (WIDE) next_hi = ldg_stream(seeds + lay.n + ii, stream);
+        next_q = __ldg(qidx + ii);
+    };
+    auto begin = [&]() {
+        word = next_word;
+        q = next_q & kQidxMask;
+        if constexpr (WIDE) { l = next_lo; h = next_hi; } else { l = (uint32_t)next_lo; h = (uint32_t)(next_lo >> 32); }
+        rem = k - table_depth(next_q >> 30, ts);
+        shift = 60;
+        widx = 0;
+        if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + q, stream);  // needed 16 pair steps from now
+    };
+
+    prefetch(i);
+    begin();
+    if (i + owners < n) prefetch(i + owners);
+
+    for (;;) {
+        while (rem == 0 || l == h) {
+            if (quarter == 0) stg_stream(out + q, (uint64_t)(h - l), stream);
+            i += owners;
+            if (i >= n) return;
+            begin();
+            if (i + owners < n) prefetch(i + owners);
+        }
+        if (shift < 0) {
+            word = pend;
+            widx++;
+            shift = 60;
+            if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + (uint64_t)widx * lay.n + q, stream);
+        }
+        const uint32_t code = (uint32_t)(word >> shift) & 15u;
+        pair_step<WIDE>(ix, c2, code, l, h, quarter);
+        rem -= 2;
+        shift -= 4;
     }
 }
 
@@ -478,11 +475,12 @@ cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_
                              uint64_t *d_out, uint32_t *d_status, cudaStream_t st) {
     if (!n) return cudaSuccess;
     const PackedLayout lay = packed_layout(ix, k, n);
-    cudaError_t e = cudaMemsetAsync(d_packed + lay.live(), 0, sizeof(uint64_t), st);
+    cudaError_t e = cudaMemsetAsync(d_packed + lay.live(), 0, 2 * sizeof(uint64_t), st);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    if (is_wide(ix)) pack_seed_kernel<true><<<blocks, 256, 0, st>>>(ix, d_syms, k, lay, d_packed, d_out, d_status);
-    else pack_seed_kernel<false><<<blocks, 256, 0, st>>>(ix, d_syms, k, lay, d_packed, d_out, d_status);
+    const size_t smem = k <= kPackSmemMaxK ? 256u * (size_t)k + 16u : 0u;
+    if (is_wide(ix)) pack_seed_kernel<true><<<blocks, 256, smem, st>>>(ix, d_syms, k, lay, d_packed, d_out, d_status);
+    else pack_seed_kernel<false><<<blocks, 256, smem, st>>>(ix, d_syms, k, lay, d_packed, d_out, d_status);
     return cudaGetLastError();
 }
 
@@ -495,6 +493,15 @@ static cudaError_t launch_count_packed_t(int device, const IndexView &ix, const 
     return cudaGetLastError();
 }
 
+template <bool WIDE>
+static cudaError_t launch_count_pair_t(int device, const IndexView &ix, const uint64_t *d_packed,
+                                       const PackedLayout &lay, uint32_t k, uint64_t *d_out, cudaStream_t st) {
+    const unsigned grid = persistent_grid(device, (const void *)count_kmers_pair_kernel<WIDE>, kCountThreads, lay.n,
+                                          kCountThreads / 4);
+    count_kmers_pair_kernel<WIDE><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out);
+    return cudaGetLastError();
+}
+
 // n <= kMaxPerLaunch (the callers chunk): query indices are u32 inside the kernels
 cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, const uint64_t *d_packed, uint32_t k,
                                 uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches) {
@@ -502,6 +509,12 @@ cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, cons
     if (n > kMaxPerLaunch) return cudaErrorInvalidValue;
     const PackedLayout lay = packed_layout(ix, k, n);
     cudaError_t e;
+    if (ix.pair) {  // list A: the pair image
+        e = is_wide(ix) ? launch_count_pair_t<true>(device, ix, d_packed, lay, k, d_out, st)
+                        : launch_count_pair_t<false>(device, ix, d_packed, lay, k, d_out, st);
+        if (launches) (*launches)++;
+        if (e != cudaSuccess) return e;
+    }
     if (is_wide(ix))
         e = lanes == 2 ? launch_count_packed_t<true, 2>(device, ix, d_packed, lay, k, d_out, st)
                        : launch_count_packed_t<true, 1>(device, ix, d_packed, lay, k, d_out, st);

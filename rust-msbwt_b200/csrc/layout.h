@@ -59,15 +59,54 @@ __host__ __device__ constexpr int ckpt_slot(int s) { return s == 5 ? 3 : s - 1; 
 // Entries are {u32 l, u32 h} when N < 2^32 (one superblock), {u64 l, u64 h} otherwise.
 constexpr int kMaxTableS = 15;
 
+// ---- pair ("two-step") blocks -------------------------------------------------------------
+//
+// Measured on B200 (profiles/r1_gather_dram_bytes.csv): an L2 miss fills a whole 128-byte line
+// whatever the size of the request, and HBM serves ~39 G random line fills/s.  A 64-byte block
+// therefore wastes half of every line it pulls in.  The pair image spends the whole line on the
+// query instead: one line answers TWO backward-search steps at once.
+//
+// For every BWT position j with B[j] = b in ACGT let LF(j) = C[b] + rank(b, j) and a = B[LF(j)].
+// If a is in ACGT too, position j carries the pair code 4*idx(b) + idx(a) (idx: A,C,G,T = 0..3)
+// and is "valid"; otherwise it is invalid.  Then for every 0 <= i <= N (pure counting, no BWT
+// property needed):
+//
+//     C[a] + rank(a, C[b] + rank(b, i))  ==  C2[b,a] + #{ j < i : code(j) == (b,a) }
+//     with  C2[b,a] = C[a] + rank(a, C[b]),
+//
+// i.e. two successive constrain_range calls (first b, then a; src/rle_bwt.rs:202-287) equal one
+// rank over the pair codes.  Bit-exact by construction; k-mers containing $ or N, and an odd
+// leftover step, use the one-step blocks above.
+//
+//   one 128-byte line per 96 BWT positions = four 32-byte quarters; quarter t (= idx(b)):
+//       word 0..3   u32 ckpt[4t + a], a = 0..3: occurrences of pair (t,a) before the block.
+//                   N < 2^32: ABSOLUTE, C2[t,a] included (no base lookup at all);
+//                   otherwise relative to the pair superblock, base in c2base[sb][16] (u64).
+//       word 4..7   positions 24t .. 24t+23 as five bit-planes of 24 bits: word 4+p holds plane p
+//                   (p = 0..3 = the four code bits) in bits 0..23; plane 4 (valid) is spread over
+//                   the top bytes of words 4,5,6 (bits 0-7, 8-15, 16-23).  Top byte of word 7: 0.
+//   A quad of lanes reads the line with one 256-bit load each (one coalesced 128-byte request).
+//   Positions >= N are invalid.  There is always a line for position N (N / 96).
+constexpr int kPairSyms = 96;
+constexpr int kPairBytes = 128;
+constexpr int kPairQuarterSyms = 24;
+constexpr int kPairWords = 32;        // u32 words per line
+constexpr int kPairSymsPerWord = 32;  // packed query word of the pair path: 32 x 2-bit ACGT symbols
+
 struct IndexView {
     const uint4 *blocks;     // nblocks * 4 uint4 (64 B per block)
     const uint32_t *aux;     // nblocks * 2  ($, N checkpoints)
     const uint64_t *cbase;   // n_super * 8
     const void *table;       // 4^table_s entries, or nullptr
+    const void *table2;      // 4^(table_s-1) entries (kept when the pair image exists), or nullptr
+    const uint4 *pair;       // npair * 8 uint4 (128 B per 96 positions), or nullptr
+    const uint64_t *c2base;  // n_super2 * 16 (u64), only when positions are 64-bit
     uint64_t total;          // N
     uint64_t nblocks;        // (N >> 7) + 1
+    uint64_t npair;          // N / 96 + 1
     uint32_t n_super;
     uint32_t sb_shift;
+    uint32_t n_super2;       // pair superblocks (2^sb_shift lines each)
     uint32_t table_s;        // 0 = no table
 };
 

@@ -69,6 +69,12 @@ class BWTRange:
     h: int = 0
 
 
+class Options(C.Structure):
+    """`msbwt_options` (include/msbwt_gpu.h)."""
+    _fields_ = [("struct_size", C.c_uint32), ("superblock_shift", C.c_uint32), ("suffix_table_s", C.c_int32),
+                ("pair_index", C.c_int32), ("kernel_lanes", C.c_int32)]
+
+
 _lib = None
 
 
@@ -91,6 +97,7 @@ def load_library():
         "msbwt_index_create_from_rle": (vp, [vp, u64, ip, i32, ip]),
         "msbwt_index_create_from_npy": (vp, [C.c_char_p, ip, i32, ip]),
         "msbwt_index_create_ex": (vp, [vp, u64, ip, i32, u32, i32, ip]),
+        "msbwt_index_create_opts": (vp, [vp, u64, ip, i32, C.POINTER(Options), ip]),
         "msbwt_index_destroy": (None, [vp]),
         "msbwt_total_size": (u64, [vp]),
         "msbwt_symbol_count": (u64, [vp, C.c_uint8]),
@@ -106,6 +113,8 @@ def load_library():
         "msbwt_packed_bytes": (u64, [vp, u32, u64]),
         "msbwt_suffix_table_s": (i32, [vp]),
         "msbwt_kernel_lanes": (i32, [vp]),
+        "msbwt_pair_index": (i32, [vp]),
+        "msbwt_debug_copy_pair_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp]),
         "msbwt_pack_kmers_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp, vp]),
         "msbwt_count_kmers_packed_device": (i32, [vp, i32, vp, u32, u64, vp, vp]),
         "msbwt_launch_count": (u64, []),
@@ -126,7 +135,8 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = (
-    "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex",
+    "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
+    "msbwt_pair_index", "msbwt_debug_copy_pair_image",
     "msbwt_index_destroy", "msbwt_total_size", "msbwt_symbol_count", "msbwt_start_index",
     "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_suffix_table_s", "msbwt_kernel_lanes", "msbwt_count_kmers",
     "msbwt_count_kmers_fixed", "msbwt_constrain_ranges", "msbwt_count_kmers_fixed_device",
@@ -163,13 +173,15 @@ class RleBWT:
     (None = the current device); batches are split across them (no collective)."""
 
     def __init__(self, bin_power: int = 8, devices: list[int] | None = None, superblock_shift: int = 0,
-                 suffix_table_s: int = -1):
+                 suffix_table_s: int = -1, pair_index: int = -1, kernel_lanes: int = 0):
         # bin_power is accepted for signature parity (src/rle_bwt.rs:309-322); it never
         # changed results in the reference and has no counterpart in the device layout.
         self.bin_power = bin_power
         self._devices = list(devices) if devices else []
         self._sb_shift = superblock_shift
         self._table_s = suffix_table_s  # -1 auto, 0 none, 1..15 explicit (include/msbwt_gpu.h)
+        self._pair = pair_index         # -1 auto, 0 never, 1 always: the 128-byte pair image (two steps per line)
+        self._lanes = kernel_lanes      # 0 auto, 1, 2
         self._h = None
 
     @classmethod
@@ -211,7 +223,8 @@ class RleBWT:
         a = _u8(bwt)
         err = C.c_int(0)
         devs, nd = self._dev_args()
-        h = L.msbwt_index_create_ex(_p(a), a.size, devs, nd, self._sb_shift, self._table_s, C.byref(err))
+        opts = Options(C.sizeof(Options), self._sb_shift, self._table_s, self._pair, self._lanes)
+        h = L.msbwt_index_create_opts(_p(a), a.size, devs, nd, C.byref(opts), C.byref(err))
         if not h:
             _check(err.value or ECUDA, "load_vector")
         self._h = h
@@ -318,6 +331,21 @@ class RleBWT:
         _check(L.msbwt_debug_copy_image(self.handle, slot, C.byref(nb), C.byref(ns), _p(blocks), _p(aux), _p(cbase)),
                "image")
         return blocks, aux, cbase
+
+    def pair_image(self, slot: int = 0) -> tuple[np.ndarray, np.ndarray]:
+        """(lines[npair,32] u32, c2base[n_super2,16] u64) of the pair image, copied back from the device."""
+        L = load_library()
+        nb, ns = C.c_uint64(0), C.c_uint32(0)
+        _check(L.msbwt_debug_copy_pair_image(self.handle, slot, C.byref(nb), C.byref(ns), None, None), "pair image")
+        lines = np.zeros((nb.value, 32), dtype=np.uint32)
+        c2base = np.zeros((ns.value, 16), dtype=np.uint64)
+        _check(L.msbwt_debug_copy_pair_image(self.handle, slot, C.byref(nb), C.byref(ns), _p(lines), _p(c2base)),
+               "pair image")
+        return lines, c2base
+
+    @property
+    def pair_index(self) -> bool:
+        return bool(load_library().msbwt_pair_index(self.handle))
 
     @property
     def kernel_lanes(self) -> int:
