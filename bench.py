@@ -41,21 +41,24 @@ WORKLOADS = {
 }
 METRIC = "count_kmer_31mer_queries_per_sec"
 UNIT = "queries/s"
-BLOCK_BYTES = 64      # layout.h: one 64-byte block per 128 symbols
+BLOCK_BYTES = 64      # layout.h: one 64-byte block per 128 symbols (one-step path)
 BLOCK_SHIFT = 7
+PAIR_BYTES = 128      # layout.h: one 128-byte line per 96 positions, two steps per line (pair path)
+PAIR_SYMS = 96
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def ncu_traffic(workload_key: str, lanes: int, table_s: int):
+def ncu_traffic(workload_key: str, lanes: int, table_s: int, pair: bool = False):
     """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel, per launch, from the committed
     `ncu --set full` capture of this same workload/kernel configuration (profiles/ncu_traffic.json);
     None when no capture matches."""
     try:
         for e in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["captures"]:
-            if e["workload"] == workload_key and e["lanes"] == lanes and e["suffix_table_s"] == table_s:
+            if (e["workload"] == workload_key and e["suffix_table_s"] == table_s and bool(e.get("pair", False)) == pair
+                    and (pair or e["lanes"] == lanes)):
                 return e["dram_bytes_per_launch"], e["source"]
     except Exception:
         pass
@@ -303,17 +306,22 @@ def measure_ours(args, cfg, ctx, primary: bool):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * n * args.steps / e2e_s
+    h2d_bytes, d2h_bytes = M.last_transfer_bytes()   # counted by the library from the copies it issued
     assert int(out_np.astype(np.int64).sum()) == checksum, "host-path and device-path results differ"
 
     res = {
         "value": value, "ms_per_step": total_ms / args.steps,
         "config": {"workload": cfg["name"], "bwt_symbols": total, "index_bytes": bwt.index_bytes, "k": k,
-                   "suffix_table_s": table_s, "kernel_lanes_per_query": bwt.kernel_lanes, "queries_per_gpu_per_step": n,
+                   "suffix_table_s": table_s, "pair_index": bwt.pair_index,
+                   "kernel_lanes_per_query": 4 if bwt.pair_index else bwt.kernel_lanes, "queries_per_gpu_per_step": n,
                    "parallelism": f"replica x{world}, query batch sharded",
                    "l2": "L2 flushed (512 MB fill) between timed iterations; query batch (n*k bytes) exceeds L2",
                    "seeds": "torch Philox 0x5EED0001.. (harness/synth.py)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * k, "d2h_bytes_per_step": n * 8,
-                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "host_input_bytes_per_step": n * k,
+                "route": "host threads pack 2 bit/symbol into pinned staging -> H2D -> seed + search kernels -> D2H"
+                         if h2d_bytes < n * k else "symbol bytes H2D -> pack + search kernels -> D2H",
+                "host_pack_threads": M.host_pack_threads()},
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "checksum": checksum,
     }
 
@@ -338,26 +346,41 @@ def measure_ours(args, cfg, ctx, primary: bool):
             m = min(n, 200_000)
             assert (got[:m] == orc.count_kmers_fixed(q_host[:m], k, threads=cores)).all()
             res["cpu_baseline"] = None
-        # algorithmic bytes: steps the reference executes x distinct 64-B index blocks per step;
-        # with the suffix table the first table_s steps of an ACGT-suffixed k-mer are one 32-B table
-        # sector instead of table_s block steps; the no-table figure is reported beside it
+        # algorithmic bytes: the index lines the implemented algorithm must touch -- per executed
+        # step the distinct 64-B blocks (one-step path) or 128-B lines (pair path: two of the reference's
+        # constrain_range calls per line) holding l and h, one 32-B sector per suffix-table lookup, the packed
+        # query and the result.  The no-table / one-step figure (what the reference's 31 steps would cost on
+        # 64-B blocks) is reported beside it.  All counted by replaying the batch through the oracle.
         ms = min(n, 1_000_000)
         steps0, two0 = orc.count_kmers_stats(q_host[:ms], k, BLOCK_SHIFT)
-        steps, two, hits = orc.count_kmers_stats_skip(q_host[:ms], k, BLOCK_SHIFT, table_s)
         packed_q = 8 * (-(-k // 21) + 1) + 4   # symbol words + seed + index of the compacted live list
-        bytes_per_query = ((steps + two) * BLOCK_BYTES + hits * 32) / ms + packed_q + 8
         bytes_per_query_no_table = (steps0 + two0) * BLOCK_BYTES / ms + packed_q + 8
-        accesses_per_query = (steps + two + hits) / ms
+        pair = bwt.pair_index
+        if pair:
+            st = orc.count_kmers_stats_pair(q_host[:ms], k, table_s, PAIR_SYMS, BLOCK_SHIFT)
+            hits = st["table_hits"]
+            pair_lines = st["pair_steps"] + st["two_line_pair_steps"]
+            one_blocks = st["one_steps"] + st["two_block_one_steps"]
+            ref_steps = 2 * st["pair_steps"] + st["one_steps"]
+            two_share = st["two_line_pair_steps"] / max(1, st["pair_steps"])
+        else:
+            steps, two, hits = orc.count_kmers_stats_skip(q_host[:ms], k, BLOCK_SHIFT, table_s)
+            pair_lines, one_blocks, ref_steps = 0, steps + two, steps
+            two_share = two / max(1, steps)
+        bytes_per_query = (pair_lines * PAIR_BYTES + one_blocks * BLOCK_BYTES + hits * 32) / ms + packed_q + 8
+        accesses_per_query = (pair_lines + one_blocks + hits) / ms
         peak, peak_src = measured_peak_gbs()
         kern_s = statistics.mean(kern_ms) / 1e3
         achieved = bytes_per_query * n / kern_s / 1e9
-        traffic, traffic_src = ncu_traffic(cfg["key"], bwt.kernel_lanes, table_s)
+        traffic, traffic_src = ncu_traffic(cfg["key"], bwt.kernel_lanes, table_s, pair)
         res["roofline"] = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "traffic_source": traffic_src, "kernel": "count_kmers_packed_kernel",
+            "traffic": traffic, "traffic_source": traffic_src,
+            "kernel": "count_kmers_pair_kernel" if pair else "count_kmers_packed_kernel",
             "kernel_ms": 1e3 * kern_s, "algorithmic_bytes_per_launch": bytes_per_query * n,
-            "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": steps / ms,
-            "two_block_step_share": two / max(1, steps), "suffix_table_s": table_s,
+            "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": ref_steps / ms,
+            "pair_lines_per_query": pair_lines / ms, "one_step_blocks_per_query": one_blocks / ms,
+            "two_block_step_share": two_share, "suffix_table_s": table_s,
             "table_hits_per_query": hits / ms, "index_accesses_per_query": accesses_per_query,
             "index_accesses_per_s": accesses_per_query * n / kern_s,
             "no_table": {"algorithmic_bytes_per_query": bytes_per_query_no_table,

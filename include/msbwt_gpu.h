@@ -73,8 +73,10 @@ msbwt_index *msbwt_index_create_from_npy(const char *path, const int *devices, i
  * `suffix_table_s`: depth of the suffix table -- the range after the first s backward-search
  * steps, precomputed for all 4^s ACGT suffixes (the `kmer_cache` the reference author planned
  * but never implemented, src/msbwt_core.rs:133-146); k-mers whose last s symbols are ACGT
- * start from it, bit-exactly.  -1 = automatic (ceil(log4(N/32)), at most 13; the
- * MSBWT_SUFFIX_TABLE_S environment variable overrides), 0 = none, 1..15 explicit. */
+ * start from it, bit-exactly.  -1 = automatic (ceil(log4(N/32)), at most 13 -- deepened up to 15 for
+ * an index that lives in HBM, while the tables stay below 4x the block images and a quarter of the
+ * free device memory; the MSBWT_SUFFIX_TABLE_S environment variable overrides), 0 = none, 1..15
+ * explicit. */
 msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
                                    uint32_t superblock_shift, int suffix_table_s, int *err);
 
@@ -121,9 +123,18 @@ int msbwt_pair_index(const msbwt_index *idx); /* 1 when the pair image is in use
 int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, const uint64_t *offsets,
                       uint64_t n, uint64_t *out);
 
-/* Fixed-length form: query i is syms[i*k .. (i+1)*k).  This is the fast path. */
+/* Fixed-length form: query i is syms[i*k .. (i+1)*k).  This is the fast path.
+ * How the batch reaches the device: with enough host threads (>= 8 usable by this process;
+ * MSBWT_HOST_PACK=0|1 overrides, MSBWT_HOST_THREADS=n sets the pool size) a worker pool packs all-ACGT
+ * k-mers 2 bits per symbol into pinned staging while earlier chunks are copied and searched, so the
+ * link carries 8*ceil(k/32) bytes per query instead of k; k-mers holding any other symbol, and every
+ * batch when the pool is off, are copied as bytes and packed / validated on the device.  Counts
+ * are identical either way.  `syms` and `out` may be pageable or pinned (msbwt_host_alloc). */
 int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n,
                             uint64_t *out);
+/* host->device and device->host bytes moved by the calling thread's last msbwt_count_kmers_fixed */
+void msbwt_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
+int msbwt_host_pack_threads(void); /* size the packing pool would have in this process */
 
 /* Batched BWT::constrain_range (src/rle_bwt.rs:202-287): for each i,
  * [out_l, out_h) = [C[sym]+rank(sym,l), C[sym]+rank(sym,h)).  The reference's
@@ -192,6 +203,13 @@ int msbwt_debug_copy_image(const msbwt_index *idx, int slot, uint64_t *nblocks, 
  * (0 rows when positions are 32-bit: the checkpoints are then absolute).  NULL arrays: sizes only. */
 int msbwt_debug_copy_pair_image(const msbwt_index *idx, int slot, uint64_t *npair, uint32_t *n_super2,
                                 uint32_t *lines, uint64_t *c2base);
+
+/* The host-side 2-bit packer of the end-to-end path, on its own (no device needed): packs n k-mers of k
+ * symbol bytes with `threads` workers into words[w * n + q], w < ceil(k/32) (the k-mer's last symbol in
+ * the top bits of word 0, A,C,G,T = 0..3) and lists the queries holding any symbol outside ACGT
+ * (*n_exceptions of them, the first max_exceptions written to `exceptions`, in no particular order). */
+int msbwt_debug_host_pack(const uint8_t *syms, uint32_t k, uint64_t n, int threads, uint64_t *words,
+                          uint64_t *exceptions, uint64_t max_exceptions, uint64_t *n_exceptions);
 
 /* ---- pinned host buffers for callers that want full copy/compute overlap ---- */
 void *msbwt_host_alloc(size_t bytes);

@@ -463,6 +463,62 @@ int orc_count_kmers_stats(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k,
     return orc_count_kmers_stats_skip(b, syms, k, n, block_shift, 0, steps, two_block_steps, NULL);
 }
 
+/* Accounting replay of the engine's PAIR path (rust-msbwt_b200/csrc/layout.h): which index lines a batch
+ * must touch.  An all-ACGT k-mer starts from the suffix table at depth table_s or table_s-1 (whichever
+ * leaves an even number of symbols) and then takes one pair step per two symbols -- one line of
+ * `line_syms` positions per boundary; any other k-mer takes the one-step path (blocks of
+ * 2^block_shift positions, depth table_s when its last table_s symbols are ACGT).  Ranges evolve
+ * exactly as in count_kmer (msbwt_core.rs:125-161); a step is counted when the engine executes it
+ * (range non-empty at its start).  out[0..5] = pair steps, pair steps whose l and h fall in
+ * different lines, one-step steps, one-step steps over two blocks, table lookups, queries. */
+int orc_count_kmers_stats_pair(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                               uint32_t table_s, uint32_t line_syms, unsigned block_shift, uint64_t *out) {
+    uint64_t ps = 0, p2 = 0, os = 0, o2 = 0, hits = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *q = syms + i * (uint64_t)k;
+        int all_acgt = 1;
+        uint32_t na = 0;
+        for (uint32_t t = 0; t < k; t++) {
+            const uint8_t sy = q[k - 1 - t];
+            if (sy >= ORC_VC_LEN) return ORC_PANIC_BAD_SYMBOL;
+            const int ok = sy == 1 || sy == 2 || sy == 3 || sy == 5;
+            all_acgt &= ok;
+            if (t < table_s && na == t && ok) na++;
+        }
+        uint32_t done = 0;
+        int pair = 0;
+        if (all_acgt) {
+            if (table_s && k >= table_s) done = ((k - table_s) & 1u) ? table_s - 1 : table_s;
+            else if (table_s && k + 1 == table_s) done = k;
+            pair = ((k - done) & 1u) == 0;
+        } else if (table_s && na >= table_s) {
+            done = table_s;
+        }
+        hits += done != 0;
+        orc_range r = { 0, b->total_size };
+        uint32_t t = k;
+        for (uint32_t c = 0; c < done; c++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
+        if (pair) {
+            while (t >= 2 && r.h != r.l) {
+                ps++;
+                if (r.l / line_syms != r.h / line_syms) p2++;
+                r = orc_constrain_range(b, q[t - 1], r);
+                if (r.h != r.l) r = orc_constrain_range(b, q[t - 2], r);
+                t -= 2;
+            }
+        } else {
+            while (t >= 1 && r.h != r.l) {
+                os++;
+                if ((r.l >> block_shift) != (r.h >> block_shift)) o2++;
+                r = orc_constrain_range(b, q[t - 1], r);
+                t--;
+            }
+        }
+    }
+    out[0] = ps; out[1] = p2; out[2] = os; out[3] = o2; out[4] = hits; out[5] = n;
+    return ORC_OK;
+}
+
 /* ---- bwt_converter.rs ---- */
 static inline uint64_t emit_run(uint8_t sym, uint64_t count, uint8_t *out, uint64_t cap, uint64_t at) {
     /* little-endian base-32 digits, one per byte, zero digits kept (:52-56, :166-171) */

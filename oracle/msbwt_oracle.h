@@ -93,6 +93,8 @@ int orc_count_kmers(const orc_rle_bwt *b, const uint8_t *syms, const uint64_t *o
  * `1<<block_shift`-symbol blocks (two_block_steps).  SURVEY.md section 8(d). */
 int orc_count_kmers_stats(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
                           unsigned block_shift, uint64_t *steps, uint64_t *two_block_steps);
+int orc_count_kmers_stats_pair(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                               uint32_t table_s, uint32_t line_syms, unsigned block_shift, uint64_t *out);
 /* Same replay, but for an engine that answers the first `skip` steps of every k-mer whose
  * last `skip` symbols are all ACGT from a precomputed suffix table: those steps are not
  * counted, *table_hits counts the k-mers that took the shortcut. */

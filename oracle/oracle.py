@@ -95,6 +95,7 @@ def lib():
         "orc_count_kmers": (C.c_int, [vp, vp, vp, C.c_uint64, vp, C.c_int]),
         "orc_count_kmers_stats": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, C.c_uint, u64p, u64p]),
         "orc_count_kmers_stats_skip": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, C.c_uint, C.c_uint32, u64p, u64p, u64p]),
+        "orc_count_kmers_stats_pair": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint, u64p]),
         "orc_convert_to_vec": (C.c_uint64, [vp, C.c_uint64, vp, C.c_uint64]),
         "orc_encode_runs": (C.c_uint64, [vp, vp, C.c_uint64, vp, C.c_uint64]),
         "orc_save_bwt_numpy": (C.c_int, [vp, C.c_uint64, C.c_char_p]),
@@ -262,6 +263,16 @@ class RleBWT:
         _raise(lib().orc_count_kmers_stats_skip(self._h, _ptr(a), k, n, block_shift, skip, C.byref(st), C.byref(tb),
                                                 C.byref(th)), "count_kmers_stats_skip")
         return int(st.value), int(tb.value), int(th.value)
+
+    def count_kmers_stats_pair(self, syms, k: int, table_s: int, line_syms: int = 96, block_shift: int = 7) -> dict:
+        """Accounting replay of the engine's pair path: index lines a batch must touch."""
+        a = _u8(syms).reshape(-1)
+        n = a.size // k
+        out = (C.c_uint64 * 6)()
+        _raise(lib().orc_count_kmers_stats_pair(self._h, _ptr(a), k, n, table_s, line_syms, block_shift, out),
+               "count_kmers_stats_pair")
+        keys = ("pair_steps", "two_line_pair_steps", "one_steps", "two_block_one_steps", "table_hits", "queries")
+        return dict(zip(keys, (int(v) for v in out)))
 
     def count_kmers_stats(self, syms, k: int, block_shift: int = 8) -> tuple[int, int]:
         a = _u8(syms).reshape(-1)

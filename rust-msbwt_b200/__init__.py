@@ -15,7 +15,11 @@ from .rle_bwt import (  # noqa: F401
     convert_itos,
     convert_stoi,
     debug_build_image,
+    debug_host_pack,
     gather_bench,
+    host_pack_threads,
+    last_transfer_bytes,
+    Options,
     launch_count,
     l2_fetch_granularity,
     EXPORTED_SYMBOLS,

@@ -17,7 +17,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmsbwt_b200.so")
 SOURCES = ["capi.cu", "kernels.cu", "loader.cu", "builder.cu", "pair_builder.cu"]
-HEADERS = ["engine.h", "layout.h", "device_rank.cuh", os.path.join(ROOT, "include", "msbwt_gpu.h")]
+HOST_SOURCES = ["hostpack.cpp"]  # plain g++ (AVX2 intrinsics behind a runtime check)
+HEADERS = ["engine.h", "layout.h", "device_rank.cuh", "hostpack.h", os.path.join(ROOT, "include", "msbwt_gpu.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -39,7 +40,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HOST_SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     deps.append(os.path.abspath(__file__))
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -50,10 +51,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     if not have_sources:
         raise RuntimeError("engine sources missing")
+    objs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        res = subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-pthread", "-c",
+                              os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("g++ failed")
+        objs.append(obj)
     cmd = [nvcc_path(), *NVCC_FLAGS]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -14,6 +14,7 @@
 
 #include "../../include/msbwt_gpu.h"
 #include "engine.h"
+#include "hostpack.h"
 
 using namespace msbwt;
 
@@ -57,11 +58,28 @@ struct DevBuf {
     template <class T> T *as() const { return (T *)p; }
 };
 
-// per-device staging for the host-buffer entry points: two lanes so that the copy-in of
-// chunk c+1 overlaps the kernels of chunk c
+// grow-only pinned host buffer
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// per-device staging for the host-buffer entry points: several lanes so that the host-side packing
+// and copy-in of the next chunks overlap the kernels of the current one
+constexpr int kLanes = 3;
 struct Lane {
     cudaStream_t stream = nullptr;
+    cudaEvent_t h2d_done = nullptr;  // the lane's pinned staging buffer may be rewritten after this
     DevBuf in_a, in_b, in_c, packed, out_a, out_b;
+    PinnedBuf h_stage;
 };
 
 struct Replica {
@@ -75,9 +93,9 @@ struct Replica {
     uint64_t *d_cbase = nullptr;
     IndexView view{};
     std::mutex mu;
-    Lane lane[2];
+    Lane lane[kLanes];
     DevBuf dev_packed;       // scratch for the *_device entry points
-    uint32_t *d_status = nullptr;  // [0,1]: per-lane flags; [2]: device entry points
+    uint32_t *d_status = nullptr;  // [0,kLanes): per-lane flags; [kStatusDev]: device entry points
     uint32_t *h_status = nullptr;  // pinned mirror
 
     ~Replica() {
@@ -87,6 +105,8 @@ struct Replica {
         cudaSetDevice(device);
         for (auto &ln : lane) {
             if (ln.stream) cudaStreamDestroy(ln.stream);
+            if (ln.h2d_done) cudaEventDestroy(ln.h2d_done);
+            ln.h_stage.release();
             ln.in_a.release(); ln.in_b.release(); ln.in_c.release();
             ln.packed.release(); ln.out_a.release(); ln.out_b.release();
         }
@@ -109,7 +129,9 @@ struct DeviceGuard {
     ~DeviceGuard() { cudaSetDevice(prev); }
 };
 
-constexpr uint64_t kChunkQueries = 1ull << 20;  // host-path pipeline granularity
+constexpr int kStatusWords = 8, kStatusDev = 7;
+constexpr uint64_t kChunkQueries = 1ull << 20;  // host-path pipeline granularity (byte route)
+constexpr uint64_t kPackedChunkQueries = 1ull << 19;  // packed route: smaller chunks fill / drain the pipeline sooner
 constexpr uint64_t kChunkBytes = 1ull << 27;
 
 }  // namespace
@@ -145,10 +167,14 @@ int resolve_devices(const int *devices, int ndev, std::vector<int> &devs) {
 
 int finish_replica(msbwt_index *idx, std::unique_ptr<Replica> rep, uint64_t total, uint64_t nblocks, uint32_t n_super,
                    uint32_t sb_shift) {
-    CU_TRY(cudaMalloc((void **)&rep->d_status, 4 * sizeof(uint32_t)));
-    CU_TRY(cudaMemset(rep->d_status, 0, 4 * sizeof(uint32_t)));
-    CU_TRY(cudaHostAlloc((void **)&rep->h_status, 4 * sizeof(uint32_t), cudaHostAllocDefault));
-    for (auto &ln : rep->lane) CU_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    CU_TRY(cudaMalloc((void **)&rep->d_status, kStatusWords * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(rep->d_status, 0, kStatusWords * sizeof(uint32_t)));
+    CU_TRY(cudaHostAlloc((void **)&rep->h_status, kStatusWords * sizeof(uint32_t), cudaHostAllocDefault));
+    memset(rep->h_status, 0, kStatusWords * sizeof(uint32_t));
+    for (auto &ln : rep->lane) {
+        CU_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&ln.h2d_done, cudaEventDisableTiming));
+    }
     rep->view.blocks = rep->d_blocks;
     rep->view.cbase = rep->d_cbase;
     rep->view.aux = rep->d_aux;
@@ -222,14 +248,33 @@ struct Options {
     int lanes = 0;      // 0 auto, 1, 2
 };
 
-int pick_table_s(uint64_t total, int requested) {
+// `explicit_choice` is set when the caller or the environment fixed the depth
+int pick_table_s(uint64_t total, int requested, bool *explicit_choice) {
+    *explicit_choice = true;
     if (requested >= 0) return requested > kMaxTableS ? kMaxTableS : requested;
     if (const char *env = getenv("MSBWT_SUFFIX_TABLE_S")) {
         int v = atoi(env);
         return v < 0 ? 0 : (v > kMaxTableS ? kMaxTableS : v);
     }
+    *explicit_choice = false;
     int s = 0;
     while (s < kAutoMaxTableS && (1ull << (2 * s)) < total / 32) s++;
+    return s;
+}
+
+// An index that lives in HBM pays one 128-byte line fill per pair step whatever it does, and HBM is
+// large: every two further table levels remove one of those steps from every query.  Deepen the
+// automatic choice while the tables (depth s and s-1) stay below 4x the block images and a quarter
+// of the free device memory.
+int deepen_table_for_hbm(int s, uint64_t image_bytes, size_t entry_bytes) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return s;
+    const uint64_t budget = std::min<uint64_t>(4 * image_bytes, free_b / 4);
+    while (s < kMaxTableS) {
+        const uint64_t next = ((1ull << (2 * (s + 1))) + (1ull << (2 * s))) * entry_bytes;
+        if (next > budget) break;
+        s++;
+    }
     return s;
 }
 
@@ -327,11 +372,20 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
         rc = build_replicas_on_device(idx.get(), rle, len, sb_shift, devices, ndev);
     }
     if (rc == MSBWT_OK) {
-        const int s = pick_table_s(idx->total, table_s);
+        bool explicit_s = false;
+        const int s0 = pick_table_s(idx->total, table_s, &explicit_s);
         const bool wide = index_is_wide(idx->reps[0]->view);
-        const uint64_t one_step_bytes = idx->bytes_per_replica + (s > 0 ? (1ull << (2 * s)) * (wide ? 16 : 8) : 0);
+        const uint64_t one_step_bytes = idx->bytes_per_replica + (s0 > 0 ? (1ull << (2 * s0)) * (wide ? 16 : 8) : 0);
         for (auto &rep : idx->reps) {
-            if (pick_pair(rep->device, one_step_bytes, opt.pair) && (rc = build_pair(idx.get(), *rep)) != MSBWT_OK) break;
+            int s = s0;
+            if (pick_pair(rep->device, one_step_bytes, opt.pair)) {
+                if ((rc = build_pair(idx.get(), *rep)) != MSBWT_OK) break;
+                if (!explicit_s && lives_in_hbm(rep->device, one_step_bytes)) {
+                    DeviceGuard guard(rep->device);
+                    s = deepen_table_for_hbm(s0, idx->reps[0]->view.nblocks * kBlockBytes + idx->reps[0]->view.npair * kPairBytes,
+                                             wide ? 16 : 8);
+                }
+            }
             rc = build_suffix_table(idx.get(), *rep, s);
             if (rc != MSBWT_OK) break;
             rep->lanes = pick_lanes(rep->device, one_step_bytes, opt.lanes);
@@ -349,7 +403,7 @@ Slice slice_for(uint64_t n, size_t d, size_t ndev) { return {n * d / ndev, n * (
 
 int check_status_flags(msbwt_index const *idx, const char *what) {
     for (auto &rep : idx->reps)
-        if (rep->h_status[0] | rep->h_status[1])
+        if (rep->h_status[0] | rep->h_status[1] | rep->h_status[2])
             return fail(MSBWT_EINVAL, std::string(what) + ": symbol >= 6 or range out of bounds in the batch");
     return MSBWT_OK;
 }
@@ -448,7 +502,7 @@ extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, 
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t per = std::min<uint64_t>(n, kMaxPerLaunch);
     CU_TRY(rep.dev_packed.reserve(packed_layout(rep.view, k, per).total() * sizeof(uint64_t)));
-    uint32_t *flag = d_status ? d_status : rep.d_status + 2;
+    uint32_t *flag = d_status ? d_status : rep.d_status + kStatusDev;
     CU_TRY(cudaMemsetAsync(flag, 0, sizeof(uint32_t), st));
     for (uint64_t q0 = 0; q0 < n; q0 += per) {  // sub-batches reuse the scratch in stream order
         const uint64_t m = std::min(per, n - q0);
@@ -506,18 +560,16 @@ extern "C" int msbwt_constrain_ranges_device(const msbwt_index *idx, int slot, c
 
 // ================================================================ host-buffer entry points
 
-extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n,
-                                       uint64_t *out) {
-    g_last_error.clear();
-    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
-    if (n && (!out || (k && !syms))) return fail(MSBWT_EINVAL, "NULL host buffer");
-    if (!n) return MSBWT_OK;
+namespace {
+
+thread_local uint64_t g_last_h2d = 0, g_last_d2h = 0;
+
+// The byte path: the caller's symbol bytes are copied to the device as they are and packed there
+// (pack_seed_kernel).  PCIe carries k bytes per query.  Caller holds the replica locks.
+int fixed_bytes_path(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n, uint64_t *out) {
     const size_t ndev = idx->reps.size();
     uint64_t chunk = kChunkQueries;
     if (k && chunk * k > kChunkBytes) chunk = std::max<uint64_t>(1, kChunkBytes / k);
-
-    std::vector<std::unique_lock<std::mutex>> locks;
-    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
 
     uint64_t max_chunks = 0;
     for (size_t d = 0; d < ndev; d++) {
@@ -528,11 +580,12 @@ extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *sy
         const uint64_t c = std::min(chunk, len);
         max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
         for (auto &ln : rep.lane) {
+            CU_TRY(cudaStreamSynchronize(ln.stream));
             CU_TRY(ln.in_a.reserve(std::max<uint64_t>(1, c * k)));
             CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, std::max<uint64_t>(1, c)).total() * sizeof(uint64_t)));
             CU_TRY(ln.out_a.reserve(std::max<uint64_t>(1, c * sizeof(uint64_t))));
         }
-        CU_TRY(cudaMemsetAsync(rep.d_status, 0, 2 * sizeof(uint32_t), rep.lane[0].stream));
+        CU_TRY(cudaMemsetAsync(rep.d_status, 0, kLanes * sizeof(uint32_t), rep.lane[0].stream));
         CU_TRY(cudaStreamSynchronize(rep.lane[0].stream));
     }
     // chunks are issued round-robin over devices so every GPU always has work queued
@@ -544,25 +597,138 @@ extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *sy
             if (b >= sl.end) continue;
             const uint64_t m = std::min(chunk, sl.end - b);
             DeviceGuard guard(rep.device);
-            Lane &ln = rep.lane[c & 1];
+            const int li = (int)(c % kLanes);
+            Lane &ln = rep.lane[li];
             if (k) CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + b * k, m * k, cudaMemcpyHostToDevice, ln.stream));
             CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
-                                    rep.d_status + (c & 1), ln.stream));
+                                    rep.d_status + li, ln.stream));
             g_launches++;
             CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
                                        ln.stream, &g_call_launches));
             flush_launches();
             CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+            g_last_h2d += m * k;
+            g_last_d2h += m * sizeof(uint64_t);
         }
     }
     for (auto &rep : idx->reps) {
         DeviceGuard guard(rep->device);
-        CU_TRY(cudaStreamSynchronize(rep->lane[0].stream));
-        CU_TRY(cudaStreamSynchronize(rep->lane[1].stream));
-        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
+        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, kLanes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
     return check_status_flags(idx, "count_kmers_fixed");
 }
+
+HostPool &host_pool() {
+    static HostPool pool(host_threads_available());
+    return pool;
+}
+
+// Host-side 2-bit packing pays off when enough host threads can feed it: the byte path moves k bytes
+// per query over PCIe (~55 GB/s), the packed path 8 * ceil(k/32) but needs the CPU to read the k bytes.
+bool use_host_pack(uint32_t k, uint64_t n) {
+    if (!k || k > max_host_packed_k() || n < 4096) return false;
+    if (const char *env = getenv("MSBWT_HOST_PACK")) return atoi(env) != 0;
+    return host_threads_available() >= 8;
+}
+
+// The packed path (hostpack.cpp): worker threads pack all-ACGT k-mers 2 bits per symbol into the lane's
+// pinned staging buffer while the previous chunks are copied and searched; the device receives
+// 8 * ceil(k/32) bytes per query (seed_packed_kernel).  K-mers with any other symbol are exceptions:
+// they are collected and sent through the byte path afterwards, which validates and counts them.
+int fixed_packed_path(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n, uint64_t *out) {
+    const size_t ndev = idx->reps.size();
+    const uint32_t nw = (k + kPairSymsPerWord - 1) / kPairSymsPerWord;
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(kPackedChunkQueries, kChunkBytes / (8ull * nw)));
+    HostPool &pool = host_pool();
+    struct Session {  // the workers spin for the duration of this call only
+        HostPool &p;
+        explicit Session(HostPool &pool_) : p(pool_) { p.begin_session(); }
+        ~Session() { p.end_session(); }
+    } session(pool);
+    const int nt = pool.size();
+    std::vector<std::vector<uint64_t>> exc_by_thread((size_t)nt);
+
+    uint64_t max_chunks = 0;
+    for (size_t d = 0; d < ndev; d++) {
+        Replica &rep = *idx->reps[d];
+        DeviceGuard guard(rep.device);
+        const Slice sl = slice_for(n, d, ndev);
+        const uint64_t len = sl.end - sl.begin;
+        const uint64_t c = std::max<uint64_t>(1, std::min(chunk, len));
+        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
+        for (auto &ln : rep.lane) {
+            CU_TRY(cudaStreamSynchronize(ln.stream));
+            CU_TRY(ln.h_stage.reserve(c * nw * sizeof(uint64_t)));
+            CU_TRY(ln.in_b.reserve(c * nw * sizeof(uint64_t)));
+            CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, c).total() * sizeof(uint64_t)));
+            CU_TRY(ln.out_a.reserve(c * sizeof(uint64_t)));
+        }
+    }
+    for (uint64_t c = 0; c < max_chunks; c++) {
+        for (size_t d = 0; d < ndev; d++) {
+            Replica &rep = *idx->reps[d];
+            const Slice sl = slice_for(n, d, ndev);
+            const uint64_t b = sl.begin + c * chunk;
+            if (b >= sl.end) continue;
+            const uint64_t m = std::min(chunk, sl.end - b);
+            DeviceGuard guard(rep.device);
+            Lane &ln = rep.lane[c % kLanes];
+            CU_TRY(cudaEventSynchronize(ln.h2d_done));  // the lane's staging buffer is free again
+            uint64_t *stage = (uint64_t *)ln.h_stage.p;
+            pool.run([&](int tid, int nthreads) {
+                const uint64_t q0 = b + m * (uint64_t)tid / (uint64_t)nthreads, q1 = b + m * (uint64_t)(tid + 1) / (uint64_t)nthreads;
+                host_pack_range(syms, k, n, q0, q1, b, m, stage, exc_by_thread[(size_t)tid]);
+            });
+            CU_TRY(cudaMemcpyAsync(ln.in_b.p, stage, m * nw * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(cudaEventRecord(ln.h2d_done, ln.stream));
+            CU_TRY(launch_seed_packed(rep.view, ln.in_b.as<uint64_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
+                                      ln.stream));
+            g_launches++;
+            CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
+                                       ln.stream, &g_call_launches, packed_batch_needs_list_b(rep.view, k)));
+            flush_launches();
+            CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+            g_last_h2d += m * nw * sizeof(uint64_t);
+            g_last_d2h += m * sizeof(uint64_t);
+        }
+    }
+    for (auto &rep : idx->reps) {
+        DeviceGuard guard(rep->device);
+        for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
+    }
+    // exceptions: k-mers with a symbol outside ACGT go through the byte path (device-side validation)
+    std::vector<uint64_t> exc;
+    for (auto &v : exc_by_thread) exc.insert(exc.end(), v.begin(), v.end());
+    if (exc.empty()) return MSBWT_OK;
+    std::vector<uint8_t> esyms(exc.size() * (size_t)k);
+    std::vector<uint64_t> eout(exc.size());
+    for (size_t i = 0; i < exc.size(); i++) memcpy(esyms.data() + i * k, syms + exc[i] * k, k);
+    if (int rc = fixed_bytes_path(idx, esyms.data(), k, exc.size(), eout.data()); rc != MSBWT_OK) return rc;
+    for (size_t i = 0; i < exc.size(); i++) out[exc[i]] = eout[i];
+    return MSBWT_OK;
+}
+
+}  // namespace
+
+extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n,
+                                       uint64_t *out) {
+    g_last_error.clear();
+    g_last_h2d = g_last_d2h = 0;
+    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
+    if (n && (!out || (k && !syms))) return fail(MSBWT_EINVAL, "NULL host buffer");
+    if (!n) return MSBWT_OK;
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
+    return use_host_pack(k, n) ? fixed_packed_path(idx, syms, k, n, out) : fixed_bytes_path(idx, syms, k, n, out);
+}
+
+extern "C" void msbwt_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h) {
+    if (h2d) *h2d = g_last_h2d;
+    if (d2h) *d2h = g_last_d2h;
+}
+
+extern "C" int msbwt_host_pack_threads(void) { return host_threads_available(); }
 
 extern "C" int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, const uint64_t *offsets, uint64_t n,
                                  uint64_t *out) {
@@ -579,7 +745,7 @@ extern "C" int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, co
     for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
     for (auto &rep : idx->reps) {
         DeviceGuard guard(rep->device);
-        CU_TRY(cudaMemsetAsync(rep->d_status, 0, 2 * sizeof(uint32_t), rep->lane[0].stream));
+        CU_TRY(cudaMemsetAsync(rep->d_status, 0, kLanes * sizeof(uint32_t), rep->lane[0].stream));
         CU_TRY(cudaStreamSynchronize(rep->lane[0].stream));
     }
     // per device: walk its slice in chunks bounded in both queries and symbol bytes
@@ -621,9 +787,8 @@ extern "C" int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, co
     }
     for (auto &rep : idx->reps) {
         DeviceGuard guard(rep->device);
-        CU_TRY(cudaStreamSynchronize(rep->lane[0].stream));
-        CU_TRY(cudaStreamSynchronize(rep->lane[1].stream));
-        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
+        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, kLanes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
     return check_status_flags(idx, "count_kmers");
 }
@@ -684,8 +849,7 @@ extern "C" int msbwt_constrain_ranges(const msbwt_index *idx, const uint8_t *sym
     }
     for (auto &rep : idx->reps) {
         DeviceGuard guard(rep->device);
-        CU_TRY(cudaStreamSynchronize(rep->lane[0].stream));
-        CU_TRY(cudaStreamSynchronize(rep->lane[1].stream));
+        for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
     }
     return MSBWT_OK;
 }
@@ -731,6 +895,29 @@ extern "C" int msbwt_debug_copy_image(const msbwt_index *idx, int slot, uint64_t
     if (blocks) CU_TRY(cudaMemcpy(blocks, rep.d_blocks, rep.view.nblocks * kBlockBytes, cudaMemcpyDeviceToHost));
     if (aux) CU_TRY(cudaMemcpy(aux, rep.d_aux, rep.view.nblocks * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (cbase) CU_TRY(cudaMemcpy(cbase, rep.d_cbase, (size_t)rep.view.n_super * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return MSBWT_OK;
+}
+
+extern "C" int msbwt_debug_host_pack(const uint8_t *syms, uint32_t k, uint64_t n, int threads, uint64_t *words,
+                                     uint64_t *exceptions, uint64_t max_exceptions, uint64_t *n_exceptions) {
+    g_last_error.clear();
+    if (!k || (n && (!syms || !words)) || !n_exceptions) return fail(MSBWT_EINVAL, "host_pack: k == 0 or NULL buffer");
+    if (threads < 1) threads = 1;
+    HostPool pool(threads);
+    std::vector<std::vector<uint64_t>> exc((size_t)threads);
+    pool.begin_session();
+    pool.run([&](int tid, int nthreads) {
+        host_pack_range(syms, k, n, n * (uint64_t)tid / (uint64_t)nthreads, n * (uint64_t)(tid + 1) / (uint64_t)nthreads, 0, n,
+                        words, exc[(size_t)tid]);
+    });
+    pool.end_session();
+    uint64_t total = 0;
+    for (auto &v : exc)
+        for (uint64_t q : v) {
+            if (exceptions && total < max_exceptions) exceptions[total] = q;
+            total++;
+        }
+    *n_exceptions = total;
     return MSBWT_OK;
 }
 

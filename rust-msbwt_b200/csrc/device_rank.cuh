@@ -201,7 +201,10 @@ __device__ __forceinline__ uint32_t match_quarter(const Half &v, uint32_t x0, ui
 
 // Two constrain_range steps at once: code = 4*idx(b) + idx(a), b consumed first.
 // [l,h) -> [C2[b,a] + rank2(code,l), C2[b,a] + rank2(code,h)).  Called by the four lanes of a quad
-// together with identical (code, l, h); `quarter` = lane & 3.  Full-mask shuffles: see rank_step.
+// together with identical (code, l, h); `quarter` = lane & 3: one 256-bit load per lane = ONE coalesced
+// 128-byte request per line.  (Measured: splitting it into a 128-bit plane load plus a 32-bit load of
+// the one checkpoint needed saves registers but doubles the kernel time -- profiles/README.md.)
+// Full-mask shuffles: see rank_step.
 template <bool WIDE>
 __device__ __forceinline__ void pair_step(const IndexView &ix, const C2Base<WIDE> &c2, uint32_t code,
                                           typename Pos<WIDE>::type &l, typename Pos<WIDE>::type &h, uint32_t quarter) {

@@ -99,7 +99,13 @@ inline PackedLayout packed_layout(const IndexView &ix, uint32_t k, uint64_t n) {
 // `launches` (optional) is incremented once per kernel launch issued.  Runs the pair kernel over
 // list A (when the index has a pair image) and the one-step kernel over list B.
 cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, const uint64_t *d_packed, uint32_t k,
-                                uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches);
+                                uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches, bool with_b = true);
+// host-packed batches (hostpack.cpp): words[w * n + q], 2-bit ACGT symbols, the k-mer's last symbol in the
+// top bits of word 0 -> live list A (same scratch layout as launch_pack_seed produces)
+cudaError_t launch_seed_packed(const IndexView &ix, const uint64_t *d_words, uint32_t k, uint64_t n,
+                               uint64_t *d_packed, uint64_t *d_out, cudaStream_t st);
+bool packed_batch_needs_list_b(const IndexView &ix, uint32_t k);
+uint32_t max_host_packed_k();  // seed_packed_kernel handles k-mers of at most this many symbols
 cudaError_t launch_count_bytes(int device, const IndexView &ix, const uint8_t *d_syms,
                                const uint64_t *d_offsets, uint64_t n, uint64_t *d_out, uint32_t *d_status,
                                cudaStream_t st, int *launches);

@@ -29,22 +29,171 @@ namespace msbwt {
 
 // ---------------------------------------------------------------- K0: pack + validate + seed
 
-// One thread per query.  The CTA first stages its 256 * k query bytes in shared memory with
-// coalesced 16-byte loads (the per-thread layout is k-byte rows: read straight from global memory
-// it costs one sector per byte load), then every thread
-//   1. validates its k symbols (symbol >= 6 sets *status) and takes the base-4 value of its last
-//      min(k, table_s) symbols,
-//   2. picks the path: PAIR (list A) when the index has a pair image and the whole k-mer is ACGT --
-//      the suffix-table depth is then chosen from {table_s, table_s - 1} so that an EVEN number of
-//      symbols is left -- otherwise ONE-STEP (list B) with depth table_s when the last table_s
-//      symbols are ACGT,
-//   3. looks the starting range up, packs the REMAINING symbols (step t of the remaining search in
-//      the top bits of word t/32 (A, 2 bits each) or t/21 (B, 3 bits each); step order = from the
-//      k-mer's last symbol to its first), and
-//   4. finishes the query right here when nothing is left to search (empty range -> count 0,
-//      msbwt_core.rs:151-153; or no symbols left -> h-l), or appends it to its live list.
-constexpr uint32_t kPackSmemMaxK = 160;  // 256 * k + 16 bytes of shared memory; longer k-mers read global memory
+// Suffix-table depth for an all-ACGT k-mer.  With a pair image the depth is picked from
+// {ts, ts - 1} so that an even number of symbols is left (k < ts - 1: no table).
+__host__ __device__ __forceinline__ uint32_t acgt_table_depth(uint32_t k, uint32_t ts, bool have_pair) {
+    if (!ts) return 0;
+    if (!have_pair) return k >= ts ? ts : 0;
+    if (k >= ts) return ((k - ts) & 1u) ? ts - 1u : ts;
+    return k + 1u == ts ? k : 0;
+}
 
+// CTA-wide append to the two live lists (A grows from slot 0 upwards, B from slot n-1 downwards): one
+// atomicAdd per list per CTA -- a per-warp atomic on the same two counters serialises in L2.  Every
+// thread of the (256-thread) CTA must call it; returns the caller's slot (meaningless unless live).
+__device__ __forceinline__ uint64_t append_live(bool live, bool list_a, unsigned long long *counters, uint64_t n) {
+    __shared__ uint32_t warp_cnt[2][8];
+    __shared__ unsigned long long warp_base[2][8];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t mask_a = __ballot_sync(0xffffffffu, live && list_a);
+    const uint32_t mask_b = __ballot_sync(0xffffffffu, live && !list_a);
+    if (lane == 0) { warp_cnt[0][warp] = __popc(mask_a); warp_cnt[1][warp] = __popc(mask_b); }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const uint32_t which = threadIdx.x;
+        uint32_t total = 0;
+        for (uint32_t w = 0; w < 8; w++) total += warp_cnt[which][w];
+        unsigned long long base = total ? atomicAdd(counters + which, (unsigned long long)total) : 0ull;
+        for (uint32_t w = 0; w < 8; w++) { warp_base[which][w] = base; base += warp_cnt[which][w]; }
+    }
+    __syncthreads();
+    const uint32_t below = (1u << lane) - 1u;
+    return list_a ? warp_base[0][warp] + __popc(mask_a & below) : n - 1 - (warp_base[1][warp] + __popc(mask_b & below));
+}
+
+constexpr uint32_t kPackSmemMaxK = 160;  // 256 * k + 64 bytes of shared memory; longer k-mers read global memory
+constexpr uint32_t kPackMaxWords = (kPackSmemMaxK + kPairSymsPerWord - 1) / kPairSymsPerWord;  // 5
+
+// ---- four symbols per 32-bit word (SWAR)
+__device__ __forceinline__ uint32_t swar_haszero(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
+// nonzero iff some byte is not one of A,C,G,T = 1,2,3,5
+__device__ __forceinline__ uint32_t swar_non_acgt(uint32_t x) {
+    const uint32_t ge6 = (((x & 0x7F7F7F7Fu) + 0x7A7A7A7Au) | x) & 0x80808080u;
+    return ge6 | swar_haszero(x) | swar_haszero(x ^ 0x04040404u);
+}
+// four ACGT symbol bytes -> 8 bits, byte i at bits 2i (A,C,G,T = 0..3)
+__device__ __forceinline__ uint32_t swar_pack4(uint32_t x) {
+    uint32_t c = (x - 0x01010101u - ((x >> 2) & 0x01010101u)) & 0x03030303u;
+    c = (c | (c >> 6)) & 0x000F000Fu;
+    return (c | (c >> 12)) & 0xFFu;
+}
+
+// Seeds one all-ACGT k-mer given as 2-bit words (`get(w)`, w < nw: the k-mer's last symbol in the top
+// bits of word 0): suffix-table lookup at the depth acgt_table_depth picks, then either the final count
+// (written by the caller) or the remaining symbols re-aligned to the top of word 0 and stored for the
+// search kernel.  Returns through the reference arguments; stores words 1.. itself.
+template <bool WIDE, class GetWord>
+__device__ __forceinline__ void seed_acgt(const IndexView &ix, uint32_t k, uint32_t nw, GetWord get, const PackedLayout &lay,
+                                          uint64_t q, uint64_t *__restrict__ packed, uint64_t &lo, uint64_t &hi,
+                                          uint32_t &flag, bool &list_a, bool &finished, uint64_t &word0) {
+    const uint32_t ts = ix.table_s;
+    const bool have_pair = ix.pair != nullptr;
+    const uint32_t done = acgt_table_depth(k, ts, have_pair);
+    list_a = !have_pair || ((k - done) & 1u) == 0;
+    lo = 0; hi = ix.total; flag = 0;
+    if (done) {
+        const bool full = done == ts;
+        flag = full ? 1u : 2u;
+        const uint64_t e = get(0) >> (64u - 2u * done);
+        const void *tab = full ? ix.table : ix.table2;
+        if constexpr (WIDE) {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(tab) + e);
+            lo = v.x; hi = v.y;
+        } else {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(tab) + e);
+            lo = v.x; hi = v.y;
+        }
+    }
+    finished = lo == hi || done == k;
+    if (finished) return;
+    const uint32_t rest = k - done;
+    if (list_a) {
+        const uint32_t nout = (rest + kPairSymsPerWord - 1) / kPairSymsPerWord;
+        uint64_t cur = get(0);
+#pragma unroll
+        for (uint32_t w = 0; w < kPackMaxWords; w++) {
+            if (w < nout) {
+                const uint64_t nxt = (w + 1 < nw) ? get(w + 1) : 0;
+                const uint64_t word = done ? (cur << (2u * done)) | (nxt >> (64u - 2u * done)) : cur;
+                if (w == 0) word0 = word; else packed[lay.wx() + (uint64_t)(w - 1) * lay.n + q] = word;
+                cur = nxt;
+            }
+        }
+    } else {  // odd remainder without a usable table depth: re-expand to 3-bit symbols for the one-step kernel
+        const uint32_t nout = (rest + kSymsPerWord - 1) / kSymsPerWord;
+        for (uint32_t w = 0; w < nout; w++) {
+            uint64_t word = 0;
+            const uint32_t cnt = min((uint32_t)kSymsPerWord, rest - w * kSymsPerWord);
+            for (uint32_t i = 0; i < cnt; i++) {
+                const uint32_t t = done + w * kSymsPerWord + i;  // consumption index within the k-mer
+                uint64_t src = 0;
+#pragma unroll
+                for (uint32_t j = 0; j < kPackMaxWords; j++) if (j == (t >> 5)) src = get(j);
+                const uint32_t c = (uint32_t)(src >> (62u - 2u * (t & 31u))) & 3u;
+                word |= (uint64_t)((0x5321u >> (4u * c)) & 7u) << (60 - 3 * i);
+            }
+            if (w == 0) word0 = word; else packed[lay.wx() + (uint64_t)(w - 1) * lay.n + q] = word;
+        }
+    }
+}
+
+// General path of the pack kernel, one symbol at a time from `src` (k bytes): k-mers holding a symbol
+// outside ACGT (list B, 3 bits per symbol, table depth table_s when the last table_s symbols are ACGT)
+// and k-mers longer than kPackSmemMaxK.
+template <bool WIDE>
+__device__ __forceinline__ void seed_general(const IndexView &ix, const uint8_t *src, uint32_t k, const PackedLayout &lay,
+                                          uint64_t q, uint64_t *__restrict__ packed, uint64_t &lo, uint64_t &hi,
+                                          uint32_t &flag, bool &finished, uint64_t &word0, bool &bad) {
+    const uint32_t ts = ix.table_s;
+    uint32_t na = 0;
+    uint64_t tidx = 0;
+    for (uint32_t t = 0; t < k; t++) {
+        const uint32_t sy = src[k - 1 - t];
+        const bool ok = sy < 8u && ((0x2Eu >> sy) & 1u) != 0;  // {1,2,3,5}
+        bad |= sy >= (uint32_t)kAlphabet;
+        if (t < ts && na == t && ok) {
+            tidx = (tidx << 2) | ((sy - 1u - (sy >> 2)) & 3u);
+            na++;
+        }
+    }
+    const uint32_t done = (ts && na >= ts) ? ts : 0u;
+    lo = 0; hi = ix.total; flag = done ? 1u : 0u;
+    if (done) {
+        if constexpr (WIDE) {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(ix.table) + tidx);
+            lo = v.x; hi = v.y;
+        } else {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ix.table) + tidx);
+            lo = v.x; hi = v.y;
+        }
+    }
+    finished = lo == hi || done == k;
+    if (finished) return;
+    const uint32_t rest = k - done;
+    for (uint32_t w = 0; w * kSymsPerWord < rest; w++) {
+        const uint32_t t0 = w * kSymsPerWord;
+        const uint32_t cnt = min((uint32_t)kSymsPerWord, rest - t0);
+        uint64_t word = 0;
+        for (uint32_t i = 0; i < cnt; i++) {
+            const uint32_t sy = src[k - 1 - (done + t0 + i)];
+            word |= (uint64_t)(sy & 7u) << (60 - 3 * i);
+        }
+        if (w == 0) word0 = word; else packed[lay.wx() + (uint64_t)(w - 1) * lay.n + q] = word;
+    }
+}
+
+// One thread per query.  The CTA first stages its 256 * k query bytes in shared memory with
+// coalesced 16-byte loads (the caller's layout is k-byte rows: read straight from global memory a
+// thread would touch one sector per byte load), then every thread
+//   1. packs its k-mer four symbols at a time (SWAR on 32-bit shared-memory words) into 2-bit words,
+//      the last symbol in the top bits, noting whether every symbol is ACGT;
+//   2. all-ACGT k-mers (list A): suffix-table lookup -- if the index has a pair image the depth is
+//      chosen from {table_s, table_s - 1} so that an EVEN number of symbols is left for the pair
+//      kernel -- and the remaining symbols shifted to the top (seed_acgt);
+//      any other k-mer (list B, rare): validated symbol by symbol (symbol >= 6 sets *status), table
+//      depth table_s when its last table_s symbols are ACGT, 3 bits per symbol (seed_general);
+//   3. finishes the query right here when nothing is left to search (empty range -> count 0,
+//      msbwt_core.rs:151-153; or no symbols left -> h-l), or appends it to its live list.
 template <bool WIDE>
 __global__ void __launch_bounds__(256)
 pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, PackedLayout lay,
@@ -54,8 +203,10 @@ pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, Pac
     const uint64_t q0 = (uint64_t)blockIdx.x * blockDim.x;
     const uint64_t q = q0 + threadIdx.x;
     const bool valid = q < lay.n;
+    const bool staged = k <= kPackSmemMaxK;
     const uint8_t *src = syms + (valid ? q : 0) * k;
-    if (k <= kPackSmemMaxK) {
+    uint32_t row = 0;  // byte offset of this thread's k-mer in shared memory
+    if (staged) {
         const uint8_t *g = syms + q0 * k;
         const uint32_t rows = (uint32_t)min((uint64_t)blockDim.x, lay.n - q0);
         const uint32_t bytes = rows * k;
@@ -68,106 +219,62 @@ pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, Pac
         for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x) sv[i] = ldg_plain(gv + i);
         for (uint32_t i = head + (vecs << 4) + threadIdx.x; i < bytes; i += blockDim.x) smem[mis + i] = g[i];
         __syncthreads();
-        src = smem + mis + threadIdx.x * k;
+        row = mis + threadIdx.x * k;
+        src = smem + row;
     }
-    const uint32_t ts = ix.table_s;
-    const bool have_pair = ix.pair != nullptr;
 
-    // 1. validate; is the whole k-mer ACGT; trailing ACGT run (at most ts symbols) as a base-4 number
-    bool bad = false, all_acgt = true;
-    uint32_t na = 0;
-    uint64_t tidx = 0;
-    if (valid) {
-        for (uint32_t t = 0; t < k; t++) {
-            const uint32_t sy = src[k - 1 - t];
-            const bool ok = sy < 8u && ((0x2Eu >> sy) & 1u) != 0;  // {1,2,3,5}
-            bad |= sy >= (uint32_t)kAlphabet;
-            all_acgt &= ok;
-            if (t < ts && na == t && ok) {
-                tidx = (tidx << 2) | ((sy - 1u - (sy >> 2)) & 3u);
-                na++;
-            }
-        }
-    }
-    // 2. path and table depth
-    uint32_t done = 0;
-    bool list_a = false;
-    if (valid) {
-        if (have_pair && all_acgt) {
-            if (ts && k >= ts) done = ((k - ts) & 1u) ? ts - 1u : ts;
-            else if (ts && k + 1u == ts) done = k;
-            list_a = ((k - done) & 1u) == 0;
-        } else if (ts && na >= ts) {
-            done = ts;
-        }
-    }
-    // 3. starting range
-    uint64_t lo = 0, hi = ix.total;
+    uint64_t lo = 0, hi = 0, word0 = 0;
     uint32_t flag = 0;
-    if (done) {
-        const bool full = done == ts;
-        flag = full ? 1u : 2u;
-        const uint64_t e = tidx >> (2u * (na - done));
-        const void *tab = full ? ix.table : ix.table2;
-        if constexpr (WIDE) {
-            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(tab) + e);
-            lo = v.x; hi = v.y;
+    bool list_a = false, finished = false, bad = false;
+    bool general = valid && !staged;
+    if (valid && staged) {
+        // 1. 2-bit words: chunk w = the 32 symbols consumed at steps 32w .. 32w+31 (the last chunk is short)
+        const uint32_t nw = (k + kPairSymsPerWord - 1) / kPairSymsPerWord, tail = k - kPairSymsPerWord * (nw - 1);
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(smem);
+        uint64_t w2[kPackMaxWords];
+        uint32_t other = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < kPackMaxWords; w++) {
+            w2[w] = 0;
+            if (w < nw) {
+                const bool last = w + 1 == nw;
+                const uint32_t c = last ? tail : kPairSymsPerWord;
+                const uint32_t o = row + (last ? 0u : k - kPairSymsPerWord * (w + 1));
+                const uint32_t *p = sw + (o >> 2);
+                const uint32_t sh = (o & 3u) * 8u;
+                uint32_t prev = p[0];
+                uint64_t le = 0;
+#pragma unroll
+                for (uint32_t i = 0; i < 8; i++) {
+                    const uint32_t nxt = p[i + 1];
+                    uint32_t x = __funnelshift_r(prev, nxt, sh);
+                    prev = nxt;
+                    if (c < 4u * (i + 1)) {  // bytes past the chunk count as 'A' (code 0, never an exception)
+                        const uint32_t keep = c > 4u * i ? (1u << (8u * (c - 4u * i))) - 1u : 0u;
+                        x = (x & keep) | (0x01010101u & ~keep);
+                    }
+                    other |= swar_non_acgt(x);
+                    le |= (uint64_t)swar_pack4(x) << (8u * i);
+                }
+                w2[w] = le << (64u - 2u * c);
+            }
+        }
+        if (other) {
+            general = true;
         } else {
-            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(tab) + e);
-            lo = v.x; hi = v.y;
+            auto get = [&](uint32_t w) {
+                uint64_t v = w2[0];
+#pragma unroll
+                for (uint32_t j = 1; j < kPackMaxWords; j++) if (j == w) v = w2[j];
+                return v;
+            };
+            seed_acgt<WIDE>(ix, k, nw, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
         }
     }
-    const bool finished = valid && (lo == hi || done == k);
-    if (finished) out[q] = hi - lo;
+    if (general) seed_general<WIDE>(ix, src, k, lay, q, packed, lo, hi, flag, finished, word0, bad);
+    if (valid && finished) out[q] = hi - lo;
     const bool live = valid && !finished;
-    // pack the symbols the table did not consume
-    uint64_t word0 = 0;
-    if (live) {
-        const uint32_t rest = k - done;
-        if (list_a) {
-            for (uint32_t w = 0; w * kPairSymsPerWord < rest; w++) {
-                const uint32_t t0 = w * kPairSymsPerWord;
-                const uint32_t cnt = min((uint32_t)kPairSymsPerWord, rest - t0);
-                uint64_t word = 0;
-                for (uint32_t i = 0; i < cnt; i++) {
-                    const uint32_t sy = src[k - 1 - (done + t0 + i)];
-                    word |= (uint64_t)((sy - 1u - (sy >> 2)) & 3u) << (62 - 2 * i);
-                }
-                if (w == 0) word0 = word; else packed[lay.wx() + (uint64_t)(w - 1) * lay.n + q] = word;
-            }
-        } else {
-            for (uint32_t w = 0; w * kSymsPerWord < rest; w++) {
-                const uint32_t t0 = w * kSymsPerWord;
-                const uint32_t cnt = min((uint32_t)kSymsPerWord, rest - t0);
-                uint64_t word = 0;
-                for (uint32_t i = 0; i < cnt; i++) {
-                    const uint32_t sy = src[k - 1 - (done + t0 + i)];
-                    word |= (uint64_t)(sy & 7u) << (60 - 3 * i);
-                }
-                if (w == 0) word0 = word; else packed[lay.wx() + (uint64_t)(w - 1) * lay.n + q] = word;
-            }
-        }
-    }
-    // warp-aggregated append to the live lists (A from the front, B from the back)
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t mask_a = __ballot_sync(0xffffffffu, live && list_a);
-    const uint32_t mask_b = __ballot_sync(0xffffffffu, live && !list_a);
-    unsigned long long *counters = reinterpret_cast<unsigned long long *>(packed + lay.live());
-    uint64_t pos = 0;
-    if (mask_a) {
-        const uint32_t leader = __ffs(mask_a) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(counters, (unsigned long long)__popc(mask_a));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (live && list_a) pos = base + __popc(mask_a & ((1u << lane) - 1u));
-    }
-    if (mask_b) {
-        const uint32_t leader = __ffs(mask_b) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(counters + 1, (unsigned long long)__popc(mask_b));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (live && !list_a) pos = lay.n - 1 - (base + __popc(mask_b & ((1u << lane) - 1u)));
-    }
+    const uint64_t pos = append_live(live, list_a, reinterpret_cast<unsigned long long *>(packed + lay.live()), lay.n);
     if (live) {
         packed[lay.w0() + pos] = word0;
         if constexpr (WIDE) {
@@ -181,15 +288,50 @@ pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, Pac
     if (bad) atomicOr(status, 1u);
 }
 
+// K0b: the same job for a batch the HOST has already packed (capi.cu, hostpack.cpp): all-ACGT
+// k-mers as ceil(k/32) words of 2-bit symbols, word-major (`words[w * n + q]`), the k-mer's last
+// symbol in the top bits of word 0.  Takes the table index off the top, shifts the rest up and
+// appends to list A (or finishes the query).  No symbol bytes ever reach the device on this path.
+template <bool WIDE>
+__global__ void __launch_bounds__(256)
+seed_packed_kernel(IndexView ix, const uint64_t *__restrict__ words, uint32_t k, PackedLayout lay,
+                   uint64_t *__restrict__ packed, uint64_t *__restrict__ out) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = q < lay.n;
+    const uint32_t nw = (k + kPairSymsPerWord - 1) / kPairSymsPerWord;  // <= kPackMaxWords (the host checks)
+    uint64_t lo = 0, hi = 0, word0 = 0;
+    uint32_t flag = 0;
+    bool list_a = false, finished = false;
+    if (valid) {
+        auto get = [&](uint32_t w) { return __ldg(words + (uint64_t)w * lay.n + q); };
+        seed_acgt<WIDE>(ix, k, nw, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
+        if (finished) out[q] = hi - lo;
+    }
+    const bool live = valid && !finished;
+    const uint64_t pos = append_live(live, list_a, reinterpret_cast<unsigned long long *>(packed + lay.live()), lay.n);
+    if (live) {
+        packed[lay.w0() + pos] = word0;
+        if constexpr (WIDE) {
+            packed[lay.seed() + pos] = lo;
+            packed[lay.seed() + lay.n + pos] = hi;
+        } else {
+            packed[lay.seed() + pos] = lo | (hi << 32);
+        }
+        reinterpret_cast<uint32_t *>(packed + lay.qidx())[pos] = (uint32_t)q | (flag << 30);
+    }
+}
+
 // ---------------------------------------------------------------- K1: count_kmers
 
 __device__ __forceinline__ uint32_t table_depth(uint32_t flag, uint32_t ts) { return flag == 0 ? 0u : (flag == 1 ? ts : ts - 1u); }
 
-// Persistent kernel over live list B: every owner -- a thread (LANES = 1) or a lane pair (LANES = 2) --
-// walks its own stream of live queries (i, i+T, i+2T, ... of the compacted list) and refills itself as
-// soon as its current k-mer is finished.  The next query's first word, seed and index are loaded one
-// query ahead and the next symbol word 21 steps ahead, so neither exposes memory latency.
-template <bool WIDE, int LANES>
+// Persistent one-step kernel over a live list -- BITS = 2: list A (all-ACGT k-mers, 32 symbols per word,
+// stored front to back; used when the index has no pair image), BITS = 3: list B (21 symbols per word,
+// stored back to front).  Every owner -- a thread (LANES = 1) or a lane pair (LANES = 2) -- walks its own
+// stream of live queries (i, i+T, i+2T, ... of the compacted list) and refills itself as soon as its
+// current k-mer is finished.  The next query's first word, seed and index are loaded one query ahead
+// and the next symbol word a whole word of steps ahead, so neither exposes memory latency.
+template <bool WIDE, int LANES, int BITS>
 __global__ void __launch_bounds__(kCountThreads, min_ctas(WIDE, LANES))
 count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, PackedLayout lay, uint32_t k,
                           uint64_t *__restrict__ out) {
@@ -198,13 +340,16 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, Pac
     const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
     const uint64_t stream = policy_evict_first();
 
-    const uint32_t n = (uint32_t)packed[lay.live() + 1];  // live queries of list B (written by the pack kernel)
+    constexpr uint32_t kPerWord = BITS == 3 ? kSymsPerWord : kPairSymsPerWord;
+    constexpr int kTop = 64 - BITS - (BITS == 3 ? 1 : 0);  // bit offset of a word's first symbol: 60 / 62
+    const uint32_t n = (uint32_t)packed[lay.live() + (BITS == 3 ? 1 : 0)];  // live queries of this list
     const uint32_t tid = blockIdx.x * kCountThreads + threadIdx.x;
     const uint32_t owners = gridDim.x * kCountThreads / LANES;  // concurrent query streams
     const uint32_t half = tid & (LANES - 1);
     uint32_t i = tid / LANES;
     if (i >= n) return;
     const uint32_t last = (uint32_t)lay.n - 1u;  // list B is stored back to front
+    auto slot = [&](uint32_t ii) { return BITS == 3 ? last - ii : ii; };
     const uint64_t *w0 = packed + lay.w0(), *seeds = packed + lay.seed(), *wx = packed + lay.wx();
     const uint32_t *qidx = reinterpret_cast<const uint32_t *>(packed + lay.qidx());
     const uint32_t ts = ix.table_s;
@@ -214,11 +359,11 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, Pac
     [[maybe_unused]] uint64_t next_hi = 0;
     uint32_t q = 0, next_q = 0;
     uint32_t rem = 0;   // symbols still to consume
-    int shift = 60;     // bit offset of the next symbol in `word`
+    int shift = kTop;   // bit offset of the next symbol in `word`
     uint32_t widx = 0;  // index of `word` within the query's remaining symbols
 
     auto prefetch = [&](uint32_t ii) {
-        const uint32_t at = last - ii;
+        const uint32_t at = slot(ii);
         next_word = ldg_stream(w0 + at, stream);
         next_lo = ldg_stream(seeds + at, stream);
         if constexpr (WIDE) next_hi = ldg_stream(seeds + lay.n + at, stream);
@@ -229,9 +374,9 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, Pac
         q = next_q & kQidxMask;
         if constexpr (WIDE) { l = next_lo; h = next_hi; } else { l = (uint32_t)next_lo; h = (uint32_t)(next_lo >> 32); }
         rem = k - table_depth(next_q >> 30, ts);  // the suffix table already answered that many steps
-        shift = 60;
+        shift = kTop;
         widx = 0;
-        if (rem > (uint32_t)kSymsPerWord) pend = ldg_stream(wx + q, stream);  // symbol word 1, needed 21 steps from now
+        if (rem > kPerWord) pend = ldg_stream(wx + q, stream);  // symbol word 1, needed a word of steps from now
     };
 
     prefetch(i);
@@ -247,22 +392,27 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, Pac
             begin();
             if (i + owners < n) prefetch(i + owners);
         }
-        if (shift < 0) {  // next 21 symbols: already in flight since the previous word began
+        if (shift < 0) {  // next word of symbols: already in flight since the previous word began
             word = pend;
             widx++;
-            shift = 60;
-            if (rem > (uint32_t)kSymsPerWord) pend = ldg_stream(wx + (uint64_t)widx * lay.n + q, stream);
+            shift = kTop;
+            if (rem > kPerWord) pend = ldg_stream(wx + (uint64_t)widx * lay.n + q, stream);
         }
-        const uint32_t sym = (uint32_t)(word >> shift) & 7u;
+        uint32_t sym;
+        if constexpr (BITS == 3) sym = (uint32_t)(word >> shift) & 7u;
+        else sym = (0x5321u >> (4u * ((uint32_t)(word >> shift) & 3u))) & 7u;  // A,C,G,T = 1,2,3,5
         rank_step<WIDE, LANES>(ix, cb, sym, l, h, half);
         rem--;
-        shift -= 3;
+        shift -= BITS;
     }
 }
 
 // Persistent kernel over live list A: a quad of lanes per query walks the PAIR image, two symbols per
 // step (one 128-byte line per boundary); same refill / prefetch structure as above.
-constexpr int pair_min_ctas(bool wide) { return wide ? 4 : 6; }
+#ifndef MSBWT_PAIR_CTAS
+#define MSBWT_PAIR_CTAS 6
+#endif
+constexpr int pair_min_ctas(bool wide) { return wide ? 4 : MSBWT_PAIR_CTAS; }
 
 template <bool WIDE>
 __global__ void __launch_bounds__(kCountThreads, pair_min_ctas(WIDE))
@@ -478,19 +628,29 @@ cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_
     cudaError_t e = cudaMemsetAsync(d_packed + lay.live(), 0, 2 * sizeof(uint64_t), st);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    const size_t smem = k <= kPackSmemMaxK ? 256u * (size_t)k + 16u : 0u;
+    const size_t smem = k <= kPackSmemMaxK ? 256u * (size_t)k + 64u : 0u;
     if (is_wide(ix)) pack_seed_kernel<true><<<blocks, 256, smem, st>>>(ix, d_syms, k, lay, d_packed, d_out, d_status);
     else pack_seed_kernel<false><<<blocks, 256, smem, st>>>(ix, d_syms, k, lay, d_packed, d_out, d_status);
     return cudaGetLastError();
 }
 
-template <bool WIDE, int LANES>
+template <bool WIDE, int LANES, int BITS>
 static cudaError_t launch_count_packed_t(int device, const IndexView &ix, const uint64_t *d_packed,
                                          const PackedLayout &lay, uint32_t k, uint64_t *d_out, cudaStream_t st) {
-    const unsigned grid = persistent_grid(device, (const void *)count_kmers_packed_kernel<WIDE, LANES>, kCountThreads,
+    const unsigned grid = persistent_grid(device, (const void *)count_kmers_packed_kernel<WIDE, LANES, BITS>, kCountThreads,
                                           lay.n, kCountThreads / LANES);
-    count_kmers_packed_kernel<WIDE, LANES><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out);
+    count_kmers_packed_kernel<WIDE, LANES, BITS><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out);
     return cudaGetLastError();
+}
+
+template <int BITS>
+static cudaError_t launch_one_step(int device, const IndexView &ix, int lanes, const uint64_t *d_packed,
+                                   const PackedLayout &lay, uint32_t k, uint64_t *d_out, cudaStream_t st) {
+    if (is_wide(ix))
+        return lanes == 2 ? launch_count_packed_t<true, 2, BITS>(device, ix, d_packed, lay, k, d_out, st)
+                          : launch_count_packed_t<true, 1, BITS>(device, ix, d_packed, lay, k, d_out, st);
+    return lanes == 2 ? launch_count_packed_t<false, 2, BITS>(device, ix, d_packed, lay, k, d_out, st)
+                      : launch_count_packed_t<false, 1, BITS>(device, ix, d_packed, lay, k, d_out, st);
 }
 
 template <bool WIDE>
@@ -502,27 +662,45 @@ static cudaError_t launch_count_pair_t(int device, const IndexView &ix, const ui
     return cudaGetLastError();
 }
 
-// n <= kMaxPerLaunch (the callers chunk): query indices are u32 inside the kernels
+// n <= kMaxPerLaunch (the callers chunk): query indices are u32 inside the kernels.
+// list A: pair kernel when the index has a pair image, else the one-step kernel on 2-bit words;
+// list B: the one-step kernel on 3-bit words (`with_b` false: the caller knows list B is empty).
 cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, const uint64_t *d_packed, uint32_t k,
-                                uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches) {
+                                uint64_t n, uint64_t *d_out, cudaStream_t st, int *launches, bool with_b) {
     if (!n) return cudaSuccess;
     if (n > kMaxPerLaunch) return cudaErrorInvalidValue;
     const PackedLayout lay = packed_layout(ix, k, n);
     cudaError_t e;
-    if (ix.pair) {  // list A: the pair image
+    if (ix.pair)
         e = is_wide(ix) ? launch_count_pair_t<true>(device, ix, d_packed, lay, k, d_out, st)
                         : launch_count_pair_t<false>(device, ix, d_packed, lay, k, d_out, st);
-        if (launches) (*launches)++;
-        if (e != cudaSuccess) return e;
-    }
-    if (is_wide(ix))
-        e = lanes == 2 ? launch_count_packed_t<true, 2>(device, ix, d_packed, lay, k, d_out, st)
-                       : launch_count_packed_t<true, 1>(device, ix, d_packed, lay, k, d_out, st);
     else
-        e = lanes == 2 ? launch_count_packed_t<false, 2>(device, ix, d_packed, lay, k, d_out, st)
-                       : launch_count_packed_t<false, 1>(device, ix, d_packed, lay, k, d_out, st);
+        e = launch_one_step<2>(device, ix, lanes, d_packed, lay, k, d_out, st);
+    if (launches) (*launches)++;
+    if (e != cudaSuccess || !with_b) return e;
+    e = launch_one_step<3>(device, ix, lanes, d_packed, lay, k, d_out, st);
     if (launches) (*launches)++;
     return e;
+}
+
+cudaError_t launch_seed_packed(const IndexView &ix, const uint64_t *d_words, uint32_t k, uint64_t n,
+                               uint64_t *d_packed, uint64_t *d_out, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const PackedLayout lay = packed_layout(ix, k, n);
+    cudaError_t e = cudaMemsetAsync(d_packed + lay.live(), 0, 2 * sizeof(uint64_t), st);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (is_wide(ix)) seed_packed_kernel<true><<<blocks, 256, 0, st>>>(ix, d_words, k, lay, d_packed, d_out);
+    else seed_packed_kernel<false><<<blocks, 256, 0, st>>>(ix, d_words, k, lay, d_packed, d_out);
+    return cudaGetLastError();
+}
+
+// does a host-packed all-ACGT batch of this k ever reach list B? (odd remainder with no usable table depth)
+uint32_t max_host_packed_k() { return kPackSmemMaxK; }
+
+bool packed_batch_needs_list_b(const IndexView &ix, uint32_t k) {
+    const bool have_pair = ix.pair != nullptr;
+    return have_pair && ((k - acgt_table_depth(k, ix.table_s, true)) & 1u) != 0;
 }
 
 cudaError_t launch_table_extend(int device, const IndexView &ix, const void *d_parent, void *d_child,

@@ -25,7 +25,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libmsbwt_b200.so")
+# MSBWT_LIBRARY_PATH: load another build of the same library (kernel tuning variants, tools/)
+_LIB_PATH = os.environ.get("MSBWT_LIBRARY_PATH") or os.path.join(_HERE, "libmsbwt_b200.so")
 
 OK, EINVAL, EIO, EFORMAT, ECUDA, ENOMEM, ENODEV = range(7)
 _NAMES = {EINVAL: "EINVAL", EIO: "EIO", EFORMAT: "EFORMAT", ECUDA: "ECUDA", ENOMEM: "ENOMEM", ENODEV: "ENODEV"}
@@ -114,6 +115,9 @@ def load_library():
         "msbwt_suffix_table_s": (i32, [vp]),
         "msbwt_kernel_lanes": (i32, [vp]),
         "msbwt_pair_index": (i32, [vp]),
+        "msbwt_last_transfer_bytes": (None, [C.POINTER(u64), C.POINTER(u64)]),
+        "msbwt_host_pack_threads": (i32, []),
+        "msbwt_debug_host_pack": (i32, [vp, u32, u64, i32, vp, vp, u64, C.POINTER(u64)]),
         "msbwt_debug_copy_pair_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp]),
         "msbwt_pack_kmers_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp, vp]),
         "msbwt_count_kmers_packed_device": (i32, [vp, i32, vp, u32, u64, vp, vp]),
@@ -136,7 +140,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
-    "msbwt_pair_index", "msbwt_debug_copy_pair_image",
+    "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
+    "msbwt_debug_host_pack",
     "msbwt_index_destroy", "msbwt_total_size", "msbwt_symbol_count", "msbwt_start_index",
     "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_suffix_table_s", "msbwt_kernel_lanes", "msbwt_count_kmers",
     "msbwt_count_kmers_fixed", "msbwt_constrain_ranges", "msbwt_count_kmers_fixed_device",
@@ -379,6 +384,29 @@ def debug_build_image(rle, superblock_shift: int = 0) -> tuple[np.ndarray, np.nd
 
 def l2_fetch_granularity(device: int, nbytes: int = 0) -> int:
     return int(load_library().msbwt_l2_fetch_granularity(device, nbytes))
+
+
+def last_transfer_bytes() -> tuple[int, int]:
+    """(host->device, device->host) bytes of the calling thread's last count_kmers_fixed."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    load_library().msbwt_last_transfer_bytes(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def debug_host_pack(syms, k: int, threads: int = 1) -> tuple[np.ndarray, np.ndarray]:
+    """(words[ceil(k/32), n] u64, sorted exception indices) from the host-side 2-bit packer.  Needs no device."""
+    a = _u8(syms).reshape(-1)
+    n = a.size // k
+    words = np.zeros((-(-k // 32), n), dtype=np.uint64)
+    exc = np.zeros(max(n, 1), dtype=np.uint64)
+    ne = C.c_uint64(0)
+    _check(load_library().msbwt_debug_host_pack(_p(a), k, n, threads, _p(words), _p(exc), exc.size, C.byref(ne)),
+           "host_pack")
+    return words, np.sort(exc[:ne.value])
+
+
+def host_pack_threads() -> int:
+    return int(load_library().msbwt_host_pack_threads())
 
 
 def launch_count() -> int:
