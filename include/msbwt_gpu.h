@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MSBWT_ABI_VERSION 2
+#define MSBWT_ABI_VERSION 3
 
 /* Return codes.  The reference panics where we return EINVAL / EFORMAT; the
  * Rust shim turns those back into panics to keep trait behaviour
@@ -85,13 +85,18 @@ msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *
  * constrain_range steps with one line fill (layout.h) -- is built next to the one-step blocks when
  * the index lives in HBM (-1 = automatic: one-step blocks + suffix table > 2 x L2; the
  * MSBWT_PAIR_INDEX=0|1 environment variable overrides), 0 = never, 1 = always.  Results are
- * identical either way.  `kernel_lanes`: 0 = automatic, 1 or 2 (see msbwt_kernel_lanes). */
+ * identical either way.  `kernel_lanes`: 0 = automatic, 1 or 2 (see msbwt_kernel_lanes).
+ * `quad_index`: the QUAD image -- one occurrence bit-vector per 4-symbol code in self-contained
+ * 32-byte sectors (layout.h), FOUR constrain_range steps per line fill, 256*N/7 bytes -- replaces the
+ * pair image (-1 = automatic: the index lives in HBM and the image is <= 64 GB and <= half the free
+ * device memory; MSBWT_QUAD_INDEX=0|1 overrides), 0 = never, 1 = always.  Results are identical. */
 typedef struct msbwt_options {
     uint32_t struct_size;
     uint32_t superblock_shift; /* 0 = default */
     int32_t suffix_table_s;    /* -1 = automatic */
     int32_t pair_index;        /* -1 = automatic */
     int32_t kernel_lanes;      /* 0 = automatic */
+    int32_t quad_index;        /* -1 = automatic (ABI 3; a caller's shorter ABI-2 struct means -1) */
 } msbwt_options;
 msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
                                      const msbwt_options *opts, int *err);
@@ -111,6 +116,7 @@ int msbwt_suffix_table_s(const msbwt_index *idx);     /* suffix table depth in u
  * L2-resident), 2 = a lane pair per query (index in HBM); MSBWT_LANES=1|2 overrides at create */
 int msbwt_kernel_lanes(const msbwt_index *idx);
 int msbwt_pair_index(const msbwt_index *idx); /* 1 when the pair image is in use */
+int msbwt_quad_index(const msbwt_index *idx); /* 1 when the quad image is in use (it replaces the pair image) */
 
 /* ---- queries from HOST buffers (the drop-in calls) ---- */
 
@@ -203,6 +209,11 @@ int msbwt_debug_copy_image(const msbwt_index *idx, int slot, uint64_t *nblocks, 
  * (0 rows when positions are 32-bit: the checkpoints are then absolute).  NULL arrays: sizes only. */
 int msbwt_debug_copy_pair_image(const msbwt_index *idx, int slot, uint64_t *npair, uint32_t *n_super2,
                                 uint32_t *lines, uint64_t *c2base);
+
+/* The quad image of a replica: 256 * *nsec4 sectors of 8 u32 words, code-major; *n_super4 rows of 256 u64
+ * in c4base (0 rows when positions are 32-bit).  NULL arrays: sizes only. */
+int msbwt_debug_copy_quad_image(const msbwt_index *idx, int slot, uint64_t *nsec4, uint32_t *n_super4,
+                                uint32_t *sectors, uint64_t *c4base);
 
 /* The host-side 2-bit packer of the end-to-end path, on its own (no device needed): packs n k-mers of k
  * symbol bytes with `threads` workers into words[w * n + q], w < ceil(k/32) (the k-mer's last symbol in

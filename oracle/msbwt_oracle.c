@@ -519,6 +519,62 @@ int orc_count_kmers_stats_pair(const orc_rle_bwt *b, const uint8_t *syms, uint32
     return ORC_OK;
 }
 
+/* Accounting replay of the engine's QUAD path (layout.h): an all-ACGT k-mer starts from the suffix table
+ * at the deepest of the four levels table_s .. table_s-3 that leaves a multiple of four symbols, then
+ * takes one quad step per four symbols -- one `sector_syms`-position sector per boundary, `line_sectors`
+ * sectors per 128-byte line -- and finishes a remainder with one-step ranks; any other k-mer takes the
+ * one-step path.  out[0..7] = quad steps, quad steps whose l and h fall in different sectors, ... in
+ * different lines, one-step steps, one-step steps over two blocks, table lookups, queries, 0. */
+int orc_count_kmers_stats_quad(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                               uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
+                               unsigned block_shift, uint64_t *out) {
+    uint64_t qs = 0, q2s = 0, q2l = 0, os = 0, o2 = 0, hits = 0;
+    const uint64_t line_syms = (uint64_t)sector_syms * line_sectors;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *q = syms + i * (uint64_t)k;
+        int all_acgt = 1;
+        uint32_t na = 0;
+        for (uint32_t t = 0; t < k; t++) {
+            const uint8_t sy = q[k - 1 - t];
+            if (sy >= ORC_VC_LEN) return ORC_PANIC_BAD_SYMBOL;
+            const int ok = sy == 1 || sy == 2 || sy == 3 || sy == 5;
+            all_acgt &= ok;
+            if (t < table_s && na == t && ok) na++;
+        }
+        uint32_t done = 0;
+        if (all_acgt) {
+            if (table_s && k >= table_s) {
+                const uint32_t back = (4u - (k - table_s) % 4u) % 4u;
+                done = back < table_s ? table_s - back : 0;
+            } else if (table_s && k + 4 > table_s) {
+                done = k;
+            }
+        } else if (table_s && na >= table_s) {
+            done = table_s;
+        }
+        hits += done != 0;
+        orc_range r = { 0, b->total_size };
+        uint32_t t = k;
+        for (uint32_t c = 0; c < done; c++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
+        if (all_acgt) {
+            while (t >= 4 && r.h != r.l) {
+                qs++;
+                if (r.l / sector_syms != r.h / sector_syms) q2s++;
+                if (r.l / line_syms != r.h / line_syms) q2l++;
+                for (int u = 0; u < 4; u++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
+            }
+        }
+        while (t >= 1 && r.h != r.l) {
+            os++;
+            if ((r.l >> block_shift) != (r.h >> block_shift)) o2++;
+            r = orc_constrain_range(b, q[t - 1], r);
+            t--;
+        }
+    }
+    out[0] = qs; out[1] = q2s; out[2] = q2l; out[3] = os; out[4] = o2; out[5] = hits; out[6] = n; out[7] = 0;
+    return ORC_OK;
+}
+
 /* ---- bwt_converter.rs ---- */
 static inline uint64_t emit_run(uint8_t sym, uint64_t count, uint8_t *out, uint64_t cap, uint64_t at) {
     /* little-endian base-32 digits, one per byte, zero digits kept (:52-56, :166-171) */

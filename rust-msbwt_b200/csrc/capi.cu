@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -87,8 +88,11 @@ struct Replica {
     uint4 *d_blocks = nullptr;
     uint32_t *d_aux = nullptr;
     void *d_table = nullptr;
-    void *d_table2 = nullptr;  // suffix table of depth table_s - 1 (kept for the pair path's parity choice)
+    void *d_table_lower[3] = {nullptr, nullptr, nullptr};  // depths table_s - 1 .. table_s - 3, kept so that a
+                                                           // multi-step image always finds a depth that leaves a multiple
+                                                           // of its stride (pair: one level, quad: three)
     PairImage pair;            // 128-byte pair lines (layout.h), when the index lives in HBM
+    QuadImage quad;            // 32-byte quad sectors (layout.h), when the index lives in HBM and the image fits
     int lanes = 1;           // kernel mapping: 1 = thread per query, 2 = lane pair per query (kernels.cu)
     uint64_t *d_cbase = nullptr;
     IndexView view{};
@@ -116,8 +120,9 @@ struct Replica {
         if (d_blocks) cudaFree(d_blocks);
         if (d_aux) cudaFree(d_aux);
         if (d_table) cudaFree(d_table);
-        if (d_table2) cudaFree(d_table2);
+        for (void *t : d_table_lower) if (t) cudaFree(t);
         free_pair_image(pair);
+        free_quad_image(quad);
         if (d_cbase) cudaFree(d_cbase);
         cudaSetDevice(cur);
     }
@@ -245,6 +250,7 @@ struct Options {
     uint32_t sb_shift = 0;
     int table_s = -1;   // -1 auto
     int pair = -1;      // -1 auto, 0 off, 1 on
+    int quad = -1;      // -1 auto, 0 off, 1 on (builds the pair image on the way and drops it)
     int lanes = 0;      // 0 auto, 1, 2
 };
 
@@ -300,19 +306,65 @@ bool pick_pair(int device, uint64_t index_bytes, int requested) {
     return lives_in_hbm(device, index_bytes);
 }
 
-int build_pair(msbwt_index *idx, Replica &rep) {
+uint64_t pair_image_bytes(const PairImage &p) {
+    return p.npair * kPairBytes + (p.c2base ? (uint64_t)p.n_super2 * 16 * sizeof(uint64_t) : 0);
+}
+
+int build_pair(msbwt_index *idx, Replica &rep, uint8_t **keep_codes = nullptr) {
     DeviceGuard guard(rep.device);
     std::string why;
     int n = 0;
-    int rc = build_pair_image_on_device(rep.device, rep.view, idx->start, rep.pair, why, &n);
+    int rc = build_pair_image_on_device(rep.device, rep.view, idx->start, rep.pair, why, &n, keep_codes);
     g_launches += (uint64_t)n;
     if (rc != MSBWT_OK) { free_pair_image(rep.pair); return fail(rc, why); }
     rep.view.pair = rep.pair.lines;
     rep.view.c2base = rep.pair.c2base;
     rep.view.npair = rep.pair.npair;
     rep.view.n_super2 = rep.pair.n_super2;
+    if (idx->reps[0].get() == &rep) idx->bytes_per_replica += pair_image_bytes(rep.pair);
+    return MSBWT_OK;
+}
+
+// The quad image (layout.h: one 32-byte sector per FOUR steps, 256 * N / 7 bytes) halves the line fills
+// of the pair image again.  Automatic choice: the index lives in HBM, the image stays below 64 GB
+// (measured, profiles/r1_gather_big.json: random reads keep 93 % of their rate over a 64 GB buffer and
+// lose three quarters of it over 128 GB) and below half of the free device memory.
+bool pick_quad(int device, uint64_t index_bytes, uint64_t total, int requested) {
+    if (requested == 0 || requested == 1) return requested == 1;
+    if (const char *env = getenv("MSBWT_QUAD_INDEX")) return atoi(env) != 0;
+    if (!lives_in_hbm(device, index_bytes)) return false;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+    const uint64_t need = quad_image_bytes(total);
+    return need <= (64ull << 30) && need <= free_b / 2;
+}
+
+// Builds pair image -> quad image, then drops the pair image (the quad kernel finishes a remainder with
+// one-step ranks, so nothing reads it afterwards).
+int build_quad(msbwt_index *idx, Replica &rep) {
+    uint8_t *codes2 = nullptr;
+    if (int rc = build_pair(idx, rep, &codes2); rc != MSBWT_OK) return rc;
+    DeviceGuard guard(rep.device);
+    std::string why;
+    int n = 0;
+    int rc = build_quad_image_on_device(rep.device, rep.view, codes2, rep.quad, why, &n);
+    g_launches += (uint64_t)n;
+    cudaFree(codes2);
+    if (idx->reps[0].get() == &rep) idx->bytes_per_replica -= pair_image_bytes(rep.pair);
+    free_pair_image(rep.pair);
+    rep.view.pair = nullptr;
+    rep.view.c2base = nullptr;
+    rep.view.npair = 0;
+    rep.view.n_super2 = 0;
+    if (rc != MSBWT_OK) { free_quad_image(rep.quad); return fail(rc, why); }
+    rep.view.quad = rep.quad.sectors;
+    rep.view.c4base = rep.quad.c4base;
+    rep.view.nsec4 = rep.quad.nsec4;
+    rep.view.n_super4 = rep.quad.n_super4;
+    rep.view.sb_shift4 = rep.quad.sb_shift4;
     if (idx->reps[0].get() == &rep)
-        idx->bytes_per_replica += rep.pair.npair * kPairBytes + (rep.pair.c2base ? (uint64_t)rep.pair.n_super2 * 16 * sizeof(uint64_t) : 0);
+        idx->bytes_per_replica += (uint64_t)kQuadCodes * rep.quad.nsec4 * kQuadSectorBytes +
+                                  (rep.quad.c4base ? (uint64_t)rep.quad.n_super4 * kQuadCodes * sizeof(uint64_t) : 0);
     return MSBWT_OK;
 }
 
@@ -321,34 +373,54 @@ int build_suffix_table(msbwt_index *idx, Replica &rep, int s) {
     DeviceGuard guard(rep.device);
     const bool wide = index_is_wide(rep.view);
     const size_t eb = wide ? 16 : 8;
-    const uint64_t entries = 1ull << (2 * s);
-    void *fin = nullptr, *tmp = nullptr;
-    CU_TRY(cudaMalloc(&fin, entries * eb));
-    if (cudaError_t e = cudaMalloc(&tmp, (entries / 4) * eb); e != cudaSuccess) {
-        cudaFree(fin);
-        return fail(MSBWT_ENOMEM, std::string("suffix table scratch: ") + cudaGetErrorString(e));
+    // levels kept: s, and the (stride - 1) below it that a multi-step image may start from
+    const int keep_lower = rep.view.quad ? 3 : (rep.view.pair ? 1 : 0);
+    const int lowest_kept = std::max(1, s - keep_lower);
+    std::vector<void *> level((size_t)s + 1, nullptr);
+    void *scratch[2] = {nullptr, nullptr};
+    auto cleanup = [&](bool all) {
+        for (void *p : scratch) if (p) cudaFree(p);
+        if (all) for (int j = lowest_kept; j <= s; j++) if (level[(size_t)j]) cudaFree(level[(size_t)j]);
+    };
+    cudaError_t e = cudaSuccess;
+    for (int j = lowest_kept; j <= s && e == cudaSuccess; j++) e = cudaMalloc(&level[(size_t)j], (1ull << (2 * j)) * eb);
+    if (lowest_kept > 0 && e == cudaSuccess) {  // levels below the kept ones ping-pong through two scratch buffers
+        const uint64_t big = 1ull << (2 * (lowest_kept - 1));
+        e = cudaMalloc(&scratch[0], big * eb);
+        if (e == cudaSuccess) e = cudaMalloc(&scratch[1], std::max<uint64_t>(1, big / 4) * eb);
+        for (int j = lowest_kept - 1, t = 0; j >= 0; j--, t ^= 1) level[(size_t)j] = scratch[t];
     }
-    auto level_buf = [&](int j) { return ((s - j) % 2 == 0) ? fin : tmp; };
+    if (e != cudaSuccess) {
+        cleanup(true);
+        return fail(MSBWT_ENOMEM, std::string("suffix table: ") + cudaGetErrorString(e));
+    }
     uint64_t root[2] = {0, rep.view.total};
     uint32_t root32[2] = {0, (uint32_t)rep.view.total};
-    cudaError_t e = cudaMemcpy(level_buf(0), wide ? (const void *)root : (const void *)root32, eb, cudaMemcpyHostToDevice);
+    e = cudaMemcpy(level[0], wide ? (const void *)root : (const void *)root32, eb, cudaMemcpyHostToDevice);
     for (int j = 0; j < s && e == cudaSuccess; j++) {
-        e = launch_table_extend(rep.device, rep.view, level_buf(j), level_buf(j + 1), (uint32_t)(1ull << (2 * (j + 1))), nullptr);
+        e = launch_table_extend(rep.device, rep.view, level[(size_t)j], level[(size_t)j + 1], (uint32_t)(1ull << (2 * (j + 1))), nullptr);
         g_launches++;
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    const bool keep2 = rep.view.pair != nullptr && s >= 2;  // level s-1 ended up in `tmp`
-    if (!keep2 || e != cudaSuccess) cudaFree(tmp);
     if (e != cudaSuccess) {
-        cudaFree(fin);
+        cleanup(true);
         return fail(MSBWT_ECUDA, std::string("suffix table build: ") + cudaGetErrorString(e));
     }
-    rep.d_table = fin;
-    rep.view.table = fin;
-    if (keep2) { rep.d_table2 = tmp; rep.view.table2 = tmp; }
+    cleanup(false);
+    rep.d_table = level[(size_t)s];
+    rep.view.table = rep.d_table;
+    const void **lower[3] = {&rep.view.table2, &rep.view.table3, &rep.view.table4};
+    uint64_t bytes = (1ull << (2 * s)) * eb;
+    for (int b = 1; b <= 3; b++) {
+        const int j = s - b;
+        if (j < lowest_kept) break;
+        rep.d_table_lower[b - 1] = level[(size_t)j];
+        *lower[b - 1] = level[(size_t)j];
+        bytes += (1ull << (2 * j)) * eb;
+    }
     rep.view.table_s = (uint32_t)s;
     idx->table_s = (uint32_t)s;
-    idx->bytes_per_replica += (idx->reps[0].get() == &rep) ? entries * eb + (keep2 ? (entries / 4) * eb : 0) : 0;
+    if (idx->reps[0].get() == &rep) idx->bytes_per_replica += bytes;
     return MSBWT_OK;
 }
 
@@ -378,12 +450,18 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
         const uint64_t one_step_bytes = idx->bytes_per_replica + (s0 > 0 ? (1ull << (2 * s0)) * (wide ? 16 : 8) : 0);
         for (auto &rep : idx->reps) {
             int s = s0;
-            if (pick_pair(rep->device, one_step_bytes, opt.pair)) {
-                if ((rc = build_pair(idx.get(), *rep)) != MSBWT_OK) break;
+            bool quad;
+            {
+                DeviceGuard guard(rep->device);
+                quad = pick_quad(rep->device, one_step_bytes, idx->total, opt.quad);
+            }
+            if (quad || pick_pair(rep->device, one_step_bytes, opt.pair)) {
+                if ((rc = quad ? build_quad(idx.get(), *rep) : build_pair(idx.get(), *rep)) != MSBWT_OK) break;
                 if (!explicit_s && lives_in_hbm(rep->device, one_step_bytes)) {
                     DeviceGuard guard(rep->device);
-                    s = deepen_table_for_hbm(s0, idx->reps[0]->view.nblocks * kBlockBytes + idx->reps[0]->view.npair * kPairBytes,
-                                             wide ? 16 : 8);
+                    const uint64_t multi = quad ? (uint64_t)kQuadCodes * rep->quad.nsec4 * kQuadSectorBytes
+                                                : rep->view.npair * kPairBytes;
+                    s = deepen_table_for_hbm(s0, idx->reps[0]->view.nblocks * kBlockBytes + multi, wide ? 16 : 8);
                 }
             }
             rc = build_suffix_table(idx.get(), *rep, s);
@@ -429,8 +507,8 @@ extern "C" msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len
                                                const msbwt_options *opts, int *err) {
     Options o;
     if (opts) {
-        if (opts->struct_size < sizeof(msbwt_options)) {
-            fail(MSBWT_EINVAL, "msbwt_options.struct_size is smaller than this library's msbwt_options");
+        if (opts->struct_size < offsetof(msbwt_options, quad_index)) {  // the ABI-2 struct ended before quad_index
+            fail(MSBWT_EINVAL, "msbwt_options.struct_size is smaller than the oldest msbwt_options this library accepts");
             if (err) *err = MSBWT_EINVAL;
             return nullptr;
         }
@@ -438,6 +516,7 @@ extern "C" msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len
         o.table_s = opts->suffix_table_s;
         o.pair = opts->pair_index;
         o.lanes = opts->kernel_lanes;
+        if (opts->struct_size >= offsetof(msbwt_options, quad_index) + sizeof(int32_t)) o.quad = opts->quad_index;
     }
     return create_common(rle, len, devices, ndev, o, err);
 }
@@ -475,6 +554,7 @@ extern "C" uint64_t msbwt_index_bytes(const msbwt_index *idx) { return idx ? idx
 extern "C" int msbwt_suffix_table_s(const msbwt_index *idx) { return idx ? (int)idx->table_s : 0; }
 extern "C" int msbwt_kernel_lanes(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->lanes : 0; }
 extern "C" int msbwt_pair_index(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.pair) ? 1 : 0; }
+extern "C" int msbwt_quad_index(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.quad) ? 1 : 0; }
 extern "C" uint64_t msbwt_launch_count(void) { return g_launches.load(); }
 extern "C" const char *msbwt_last_error(void) { return g_last_error.c_str(); }
 extern "C" int msbwt_abi_version(void) { return MSBWT_ABI_VERSION; }
@@ -932,6 +1012,20 @@ extern "C" int msbwt_debug_copy_pair_image(const msbwt_index *idx, int slot, uin
     *n_super2 = rep.view.c2base ? rep.view.n_super2 : 0;
     if (lines) CU_TRY(cudaMemcpy(lines, rep.view.pair, rep.view.npair * kPairBytes, cudaMemcpyDeviceToHost));
     if (c2base && rep.view.c2base) CU_TRY(cudaMemcpy(c2base, rep.view.c2base, (size_t)rep.view.n_super2 * 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return MSBWT_OK;
+}
+
+extern "C" int msbwt_debug_copy_quad_image(const msbwt_index *idx, int slot, uint64_t *nsec4, uint32_t *n_super4,
+                                           uint32_t *sectors, uint64_t *c4base) {
+    g_last_error.clear();
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size() || !nsec4 || !n_super4) return fail(MSBWT_EINVAL, "bad handle, slot or size outputs");
+    const Replica &rep = *idx->reps[slot];
+    if (!rep.view.quad) return fail(MSBWT_EINVAL, "this index has no quad image");
+    DeviceGuard guard(rep.device);
+    *nsec4 = rep.view.nsec4;
+    *n_super4 = rep.view.c4base ? rep.view.n_super4 : 0;
+    if (sectors) CU_TRY(cudaMemcpy(sectors, rep.view.quad, (size_t)kQuadCodes * rep.view.nsec4 * kQuadSectorBytes, cudaMemcpyDeviceToHost));
+    if (c4base && rep.view.c4base) CU_TRY(cudaMemcpy(c4base, rep.view.c4base, (size_t)rep.view.n_super4 * kQuadCodes * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return MSBWT_OK;
 }
 

@@ -237,4 +237,55 @@ __device__ __forceinline__ void pair_step(const IndexView &ix, const C2Base<WIDE
     h = c2.at(bh, code) + ckh + (cnt >> 16);
 }
 
+// ---- quad image (layout.h): four constrain_range steps per 32-byte sector
+
+template <bool WIDE> struct C4Base;
+template <> struct C4Base<false> {  // N < 2^32: the sector's checkpoint is absolute
+    __device__ __forceinline__ uint32_t at(uint32_t, uint32_t) const { return 0u; }
+};
+template <> struct C4Base<true> {
+    const uint64_t *c;
+    uint32_t sb_shift;
+    __device__ __forceinline__ uint64_t at(uint64_t sector, uint32_t code) const {
+        return c[((sector >> sb_shift) << 8) + code];
+    }
+};
+
+template <bool WIDE>
+__device__ __forceinline__ C4Base<WIDE> stage_c4base(const IndexView &ix, uint64_t *smem) {
+    if constexpr (WIDE) {
+        if (ix.n_super4 > (uint32_t)kQuadMaxSuperInSmem) return C4Base<true>{ix.c4base, ix.sb_shift4};
+        for (uint32_t i = threadIdx.x; i < ix.n_super4 * (uint32_t)kQuadCodes; i += blockDim.x) smem[i] = ix.c4base[i];
+        __syncthreads();
+        return C4Base<true>{smem, ix.sb_shift4};
+    } else {
+        return C4Base<false>{};
+    }
+}
+
+// set bits of a sector's 224 occurrence bits at offsets < p (0 <= p < 224)
+__device__ __forceinline__ uint32_t sector_count_below(const Half &v, int p) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < 7; w++) c += __popc(v.w[1 + w] & below_mask(p - 32 * w));
+    return c;
+}
+
+// Four constrain_range steps at once: code = 64*idx(b0) + 16*idx(b1) + 4*idx(b2) + idx(b3), b0 consumed
+// first.  [l,h) -> [C4[code] + rank4(code,l), C4[code] + rank4(code,h)).  One thread, one 256-bit load
+// per boundary (the second one only when h falls in another sector), both issued before either is used.
+template <bool WIDE>
+__device__ __forceinline__ void quad_step(const IndexView &ix, const C4Base<WIDE> &c4, uint32_t code,
+                                          typename Pos<WIDE>::type &l, typename Pos<WIDE>::type &h) {
+    using P = typename Pos<WIDE>::type;
+    const P sl = l / (P)kQuadSyms, sh = h / (P)kQuadSyms;
+    const int pl = (int)(uint32_t)(l - sl * (P)kQuadSyms), ph = (int)(uint32_t)(h - sh * (P)kQuadSyms);
+    const char *base = reinterpret_cast<const char *>(ix.quad) + (size_t)code * ix.nsec4 * kQuadSectorBytes;
+    const Half a = ldg_index256(base + (size_t)sl * kQuadSectorBytes);
+    Half b = a;
+    if (sh != sl) b = ldg_index256(base + (size_t)sh * kQuadSectorBytes);
+    l = c4.at(sl, code) + a.w[0] + sector_count_below(a, pl);
+    h = c4.at(sh, code) + b.w[0] + sector_count_below(b, ph);
+}
+
 }  // namespace msbwt

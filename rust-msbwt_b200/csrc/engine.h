@@ -54,9 +54,25 @@ struct PairImage {
     uint64_t npair = 0;
     uint32_t n_super2 = 0;
 };
+// `keep_codes` (optional): receives the per-position pair-code bytes (16 | code, or 0 when invalid;
+// npair * 96 of them, device memory the caller must cudaFree) -- the quad builder's input.
 int build_pair_image_on_device(int device, const IndexView &ix, const uint64_t start[kAlphabet], PairImage &img,
-                               std::string &why, int *launches);
+                               std::string &why, int *launches, uint8_t **keep_codes = nullptr);
 void free_pair_image(PairImage &img);
+
+// ---- quad_builder.cu: pair image + pair codes (resident on the current device) -> quad image ----
+struct QuadImage {
+    uint4 *sectors = nullptr;    // 256 * nsec4 * 32 B
+    uint64_t *c4base = nullptr;  // n_super4 * 256, WIDE only
+    uint64_t nsec4 = 0;
+    uint32_t n_super4 = 0;
+    uint32_t sb_shift4 = 0;
+};
+uint64_t quad_image_bytes(uint64_t total);
+// `ix` must carry the one-step blocks and the pair image; `d_codes2` = build_pair_image_on_device's keep_codes
+int build_quad_image_on_device(int device, const IndexView &ix, const uint8_t *d_codes2, QuadImage &img,
+                               std::string &why, int *launches);
+void free_quad_image(QuadImage &img);
 
 // return an msbwt_status; on failure `why` explains
 int validate_rle(const uint8_t *rle, uint64_t len, std::string &why);

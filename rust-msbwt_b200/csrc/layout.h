@@ -93,20 +93,61 @@ constexpr int kPairQuarterSyms = 24;
 constexpr int kPairWords = 32;        // u32 words per line
 constexpr int kPairSymsPerWord = 32;  // packed query word of the pair path: 32 x 2-bit ACGT symbols
 
+// ---- quad ("four-step") sectors -----------------------------------------------------------
+//
+// The same identity composed once more (induction over the pair identity above): for the quad code
+// c = (b0,b1,b2,b3) of position j -- b0 = B[j], b1 = B[LF(j)], b2 = B[LF^2(j)], b3 = B[LF^3(j)], all
+// four in ACGT, else j is invalid -- and every 0 <= i <= N,
+//
+//     four successive constrain_range calls (b0 first) applied to i  ==  C4[c] + #{ j < i : code4(j) == c }
+//     with  C4[c] = those four calls applied to 0,
+//
+// because LF^2 restricted to one pair code is the order-preserving bijection onto
+// [C2[code], C2[code] + count(code)).  HBM is large (180 GB) and an L2 miss costs one 128-byte line
+// fill whatever it asks for, so this image spends memory to save line fills: ONE occurrence bit-vector
+// per quad code (256 of them), cut into self-contained 32-byte sectors:
+//
+//     sector (c, s), s = position / 224:   word 0      u32 checkpoint: #{ j < 224 s : code4(j) == c };
+//                                                      N < 2^32: ABSOLUTE, C4[c] included; otherwise
+//                                                      relative to the quad superblock (2^sb_shift4
+//                                                      sectors), base in c4base[sb][256] (u64)
+//                                          word 1..7   bit t of word 1+w: code4(224 s + 32 w + t) == c
+//     address = ((c * nsec4) + s) * 32 bytes, nsec4 = N / 224 + 2 (the sector of position N, plus one
+//     trailing all-zero sector per code whose checkpoint is the code's total -- the builder reads it).
+//
+// Code-major, so the sectors of l and h (a read-set range is a few dozen positions wide) share a
+// 128-byte line 97 % of the time.  One thread per query, one 256-bit load per boundary, <= 7 POPC; a
+// 31-mer seeded by a depth-15 suffix table needs 4 line fills instead of the pair image's 8.8.
+// 256 * N / 7 bytes: 55 GB at N = 1.51 G, 110 GB at N = 3.02 G.  Chosen automatically only when the
+// index lives in HBM and the image fits the device comfortably (capi.cu).
+constexpr int kQuadSyms = 224;        // positions per sector
+constexpr int kQuadWords = 8;         // u32 words per sector
+constexpr int kQuadSectorBytes = 32;
+constexpr int kQuadCodes = 256;
+constexpr int kQuadMaxSuperShift = 24;  // 2^24 sectors * 224 positions < 2^32
+constexpr int kQuadMaxSuperInSmem = 8;  // rows of 256 u64 staged in shared memory (16 KB)
+
 struct IndexView {
     const uint4 *blocks;     // nblocks * 4 uint4 (64 B per block)
     const uint32_t *aux;     // nblocks * 2  ($, N checkpoints)
     const uint64_t *cbase;   // n_super * 8
     const void *table;       // 4^table_s entries, or nullptr
-    const void *table2;      // 4^(table_s-1) entries (kept when the pair image exists), or nullptr
+    const void *table2;      // 4^(table_s-1) entries (kept when a pair or quad image exists), or nullptr
+    const void *table3;      // 4^(table_s-2), 4^(table_s-3) entries (kept when the quad image exists)
+    const void *table4;
     const uint4 *pair;       // npair * 8 uint4 (128 B per 96 positions), or nullptr
     const uint64_t *c2base;  // n_super2 * 16 (u64), only when positions are 64-bit
+    const uint4 *quad;       // 256 * nsec4 sectors of 32 B (2 uint4 each), or nullptr
+    const uint64_t *c4base;  // n_super4 * 256 (u64), only when positions are 64-bit
+    uint64_t nsec4;          // sectors per quad code: N / 224 + 2
     uint64_t total;          // N
     uint64_t nblocks;        // (N >> 7) + 1
     uint64_t npair;          // N / 96 + 1
     uint32_t n_super;
     uint32_t sb_shift;
     uint32_t n_super2;       // pair superblocks (2^sb_shift lines each)
+    uint32_t n_super4;       // quad superblocks (2^sb_shift4 sectors each)
+    uint32_t sb_shift4;
     uint32_t table_s;        // 0 = no table
 };
 

@@ -14,6 +14,8 @@
 //   4. stamp : checkpoints -- absolute (C2 included) when N < 2^32, otherwise relative to the pair
 //              superblock with the base in c2base.
 //   C2[b,a] = C[a] + rank(a, C[b]) comes from 16 constrain_range calls of our own kernel.
+#include <algorithm>
+
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
@@ -139,7 +141,7 @@ struct Scratch {
 }  // namespace
 
 int build_pair_image_on_device(int device, const IndexView &ix, const uint64_t start[kAlphabet], PairImage &img,
-                               std::string &why, int *launches) {
+                               std::string &why, int *launches, uint8_t **keep_codes) {
     const bool wide = index_is_wide(ix);
     const uint64_t npair = ix.total / kPairSyms + 1;
     const uint32_t sb_shift = ix.sb_shift;
@@ -206,6 +208,10 @@ int build_pair_image_on_device(int device, const IndexView &ix, const uint64_t s
         }
     }
     P_TRY(cudaDeviceSynchronize());
+    if (keep_codes) {  // hand the code bytes to the caller instead of freeing them with the scratch
+        *keep_codes = d_codes;
+        tmp.ptrs.erase(std::find(tmp.ptrs.begin(), tmp.ptrs.end(), (void *)d_codes));
+    }
     return MSBWT_OK;
 }
 

@@ -73,7 +73,7 @@ class BWTRange:
 class Options(C.Structure):
     """`msbwt_options` (include/msbwt_gpu.h)."""
     _fields_ = [("struct_size", C.c_uint32), ("superblock_shift", C.c_uint32), ("suffix_table_s", C.c_int32),
-                ("pair_index", C.c_int32), ("kernel_lanes", C.c_int32)]
+                ("pair_index", C.c_int32), ("kernel_lanes", C.c_int32), ("quad_index", C.c_int32)]
 
 
 _lib = None
@@ -115,6 +115,8 @@ def load_library():
         "msbwt_suffix_table_s": (i32, [vp]),
         "msbwt_kernel_lanes": (i32, [vp]),
         "msbwt_pair_index": (i32, [vp]),
+        "msbwt_quad_index": (i32, [vp]),
+        "msbwt_debug_copy_quad_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp]),
         "msbwt_last_transfer_bytes": (None, [C.POINTER(u64), C.POINTER(u64)]),
         "msbwt_host_pack_threads": (i32, []),
         "msbwt_debug_host_pack": (i32, [vp, u32, u64, i32, vp, vp, u64, C.POINTER(u64)]),
@@ -140,7 +142,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
-    "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
+    "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
     "msbwt_debug_host_pack",
     "msbwt_index_destroy", "msbwt_total_size", "msbwt_symbol_count", "msbwt_start_index",
     "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_suffix_table_s", "msbwt_kernel_lanes", "msbwt_count_kmers",
@@ -178,7 +180,7 @@ class RleBWT:
     (None = the current device); batches are split across them (no collective)."""
 
     def __init__(self, bin_power: int = 8, devices: list[int] | None = None, superblock_shift: int = 0,
-                 suffix_table_s: int = -1, pair_index: int = -1, kernel_lanes: int = 0):
+                 suffix_table_s: int = -1, pair_index: int = -1, kernel_lanes: int = 0, quad_index: int = -1):
         # bin_power is accepted for signature parity (src/rle_bwt.rs:309-322); it never
         # changed results in the reference and has no counterpart in the device layout.
         self.bin_power = bin_power
@@ -187,6 +189,7 @@ class RleBWT:
         self._table_s = suffix_table_s  # -1 auto, 0 none, 1..15 explicit (include/msbwt_gpu.h)
         self._pair = pair_index         # -1 auto, 0 never, 1 always: the 128-byte pair image (two steps per line)
         self._lanes = kernel_lanes      # 0 auto, 1, 2
+        self._quad = quad_index         # -1 auto, 0 never, 1 always: the 32-byte quad sectors (four steps per sector)
         self._h = None
 
     @classmethod
@@ -228,7 +231,7 @@ class RleBWT:
         a = _u8(bwt)
         err = C.c_int(0)
         devs, nd = self._dev_args()
-        opts = Options(C.sizeof(Options), self._sb_shift, self._table_s, self._pair, self._lanes)
+        opts = Options(C.sizeof(Options), self._sb_shift, self._table_s, self._pair, self._lanes, self._quad)
         h = L.msbwt_index_create_opts(_p(a), a.size, devs, nd, C.byref(opts), C.byref(err))
         if not h:
             _check(err.value or ECUDA, "load_vector")
@@ -347,6 +350,21 @@ class RleBWT:
         _check(L.msbwt_debug_copy_pair_image(self.handle, slot, C.byref(nb), C.byref(ns), _p(lines), _p(c2base)),
                "pair image")
         return lines, c2base
+
+    def quad_image(self, slot: int = 0) -> tuple[np.ndarray, np.ndarray]:
+        """(sectors[256, nsec4, 8] u32, c4base[n_super4, 256] u64) of the quad image, copied back from the device."""
+        L = load_library()
+        nb, ns = C.c_uint64(0), C.c_uint32(0)
+        _check(L.msbwt_debug_copy_quad_image(self.handle, slot, C.byref(nb), C.byref(ns), None, None), "quad image")
+        sectors = np.zeros((256, nb.value, 8), dtype=np.uint32)
+        c4base = np.zeros((ns.value, 256), dtype=np.uint64)
+        _check(L.msbwt_debug_copy_quad_image(self.handle, slot, C.byref(nb), C.byref(ns), _p(sectors), _p(c4base)),
+               "quad image")
+        return sectors, c4base
+
+    @property
+    def quad_index(self) -> bool:
+        return bool(load_library().msbwt_quad_index(self.handle))
 
     @property
     def pair_index(self) -> bool:
