@@ -323,8 +323,11 @@ def measure_ours(args, cfg, ctx, primary: bool):
                    "seeds": "torch Philox 0x5EED0001.. (harness/synth.py)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "host_input_bytes_per_step": n * k,
-                "route": "host threads pack 2 bit/symbol into pinned staging -> H2D -> seed + search kernels -> D2H"
-                         if h2d_bytes < n * k else "symbol bytes H2D -> pack + search kernels -> D2H",
+                "route": ("symbol bytes H2D -> pack + search kernels -> D2H" if h2d_bytes >= n * k else
+                          "host threads pack 2 bit/symbol into pinned staging -> H2D -> seed + search kernels -> D2H"
+                          if h2d_bytes <= 8 * -(-k // 32) * n + 4096 else
+                          "hybrid: chunks packed 2 bit/symbol by the host pool, and raw symbol-byte chunks whenever the "
+                          "copy engine is idle -> seed / pack + search kernels -> D2H"),
                 "host_pack_threads": M.host_pack_threads()},
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "checksum": checksum,
     }

@@ -75,7 +75,9 @@ struct PinnedBuf {
 
 // per-device staging for the host-buffer entry points: several lanes so that the host-side packing
 // and copy-in of the next chunks overlap the kernels of the current one
-constexpr int kLanes = 3;
+constexpr int kPackLanes = 3;  // lanes whose input is packed by the host pool (or every lane of the byte path)
+constexpr int kRawLanes = 2;   // hybrid route only: lanes that take their chunk as raw symbol bytes over PCIe
+constexpr int kLanes = kPackLanes + kRawLanes;
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t h2d_done = nullptr;  // the lane's pinned staging buffer may be rewritten after this
@@ -326,13 +328,18 @@ int build_pair(msbwt_index *idx, Replica &rep, uint8_t **keep_codes = nullptr) {
 }
 
 // The quad image (layout.h: one 32-byte sector per FOUR steps, 256 * N / 7 bytes) halves the line fills
-// of the pair image again.  Automatic choice: the index lives in HBM, the image stays below 64 GB
-// (measured, profiles/r1_gather_big.json: random reads keep 93 % of their rate over a 64 GB buffer and
-// lose three quarters of it over 128 GB) and below half of the free device memory.
-bool pick_quad(int device, uint64_t index_bytes, uint64_t total, int requested) {
+// of the pair image again.  Automatic choice: the one-step index does not fit L2 (measured on the
+// 151 Msymbol BWT, 1.7 x L2: 10.2 G queries/s through quad sectors + a depth-15 table in HBM against 7.3 G
+// through the mostly L2-resident one-step blocks), the image stays below 64 GB (measured,
+// profiles/r1_gather_big.json: random reads keep 93 % of their rate over a 64 GB buffer and lose three
+// quarters of it over 128 GB) and below half of the free device memory.
+bool pick_quad(int device, uint64_t index_bytes, uint64_t total, int requested, int pair_requested) {
     if (requested == 0 || requested == 1) return requested == 1;
+    if (pair_requested == 0 || pair_requested == 1) return false;  // the caller pinned the layout
     if (const char *env = getenv("MSBWT_QUAD_INDEX")) return atoi(env) != 0;
-    if (!lives_in_hbm(device, index_bytes)) return false;
+    int l2 = 0;
+    if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device) != cudaSuccess || l2 <= 0) l2 = 96 << 20;
+    if (index_bytes <= (uint64_t)l2) return false;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
     const uint64_t need = quad_image_bytes(total);
@@ -453,11 +460,11 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
             bool quad;
             {
                 DeviceGuard guard(rep->device);
-                quad = pick_quad(rep->device, one_step_bytes, idx->total, opt.quad);
+                quad = pick_quad(rep->device, one_step_bytes, idx->total, opt.quad, opt.pair);
             }
             if (quad || pick_pair(rep->device, one_step_bytes, opt.pair)) {
                 if ((rc = quad ? build_quad(idx.get(), *rep) : build_pair(idx.get(), *rep)) != MSBWT_OK) break;
-                if (!explicit_s && lives_in_hbm(rep->device, one_step_bytes)) {
+                if (!explicit_s && (quad || lives_in_hbm(rep->device, one_step_bytes))) {
                     DeviceGuard guard(rep->device);
                     const uint64_t multi = quad ? (uint64_t)kQuadCodes * rep->quad.nsec4 * kQuadSectorBytes
                                                 : rep->view.npair * kPairBytes;
@@ -481,7 +488,7 @@ Slice slice_for(uint64_t n, size_t d, size_t ndev) { return {n * d / ndev, n * (
 
 int check_status_flags(msbwt_index const *idx, const char *what) {
     for (auto &rep : idx->reps)
-        if (rep->h_status[0] | rep->h_status[1] | rep->h_status[2])
+        if (std::any_of(rep->h_status, rep->h_status + kLanes, [](uint32_t v) { return v != 0; }))
             return fail(MSBWT_EINVAL, std::string(what) + ": symbol >= 6 or range out of bounds in the batch");
     return MSBWT_OK;
 }
@@ -712,14 +719,32 @@ bool use_host_pack(uint32_t k, uint64_t n) {
     return host_threads_available() >= 8;
 }
 
-// The packed path (hostpack.cpp): worker threads pack all-ACGT k-mers 2 bits per symbol into the lane's
-// pinned staging buffer while the previous chunks are copied and searched; the device receives
+// true when `p` is page-locked host memory the copy engine can read while the host does something else
+// (cudaMemcpyAsync from pageable memory stages through the driver and holds the calling thread)
+bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// The packed / hybrid path (hostpack.cpp): worker threads pack all-ACGT k-mers 2 bits per symbol into a
+// lane's pinned staging buffer while earlier chunks are copied and searched; the device receives
 // 8 * ceil(k/32) bytes per query (seed_packed_kernel).  K-mers with any other symbol are exceptions:
 // they are collected and sent through the byte path afterwards, which validates and counts them.
+// HYBRID (the caller's buffer is pinned): the host pool is bound by host memory bandwidth (it has to read
+// k bytes per query) while the PCIe link idles at 8 bytes per query, so whenever the copy engine has
+// drained the previous raw chunk the next chunk goes over the link as it is -- k symbol bytes, packed and
+// validated on the device (pack_seed_kernel) -- instead of through the pool.  The split balances itself:
+// a raw lane is taken exactly when its last copy-in has completed.
 int fixed_packed_path(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n, uint64_t *out) {
     const size_t ndev = idx->reps.size();
     const uint32_t nw = (k + kPairSymsPerWord - 1) / kPairSymsPerWord;
     const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(kPackedChunkQueries, kChunkBytes / (8ull * nw)));
+    bool hybrid = is_pinned_host(syms);
+    if (const char *env = getenv("MSBWT_HYBRID")) hybrid = hybrid && atoi(env) != 0;
     HostPool &pool = host_pool();
     struct Session {  // the workers spin for the duration of this call only
         HostPool &p;
@@ -737,14 +762,24 @@ int fixed_packed_path(const msbwt_index *idx, const uint8_t *syms, uint32_t k, u
         const uint64_t len = sl.end - sl.begin;
         const uint64_t c = std::max<uint64_t>(1, std::min(chunk, len));
         max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
-        for (auto &ln : rep.lane) {
+        for (int li = 0; li < kLanes; li++) {
+            Lane &ln = rep.lane[li];
             CU_TRY(cudaStreamSynchronize(ln.stream));
-            CU_TRY(ln.h_stage.reserve(c * nw * sizeof(uint64_t)));
-            CU_TRY(ln.in_b.reserve(c * nw * sizeof(uint64_t)));
+            if (li < kPackLanes) {
+                CU_TRY(ln.h_stage.reserve(c * nw * sizeof(uint64_t)));
+                CU_TRY(ln.in_b.reserve(c * nw * sizeof(uint64_t)));
+            } else if (hybrid) {
+                CU_TRY(ln.in_a.reserve(c * k));
+            } else {
+                continue;
+            }
             CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, c).total() * sizeof(uint64_t)));
             CU_TRY(ln.out_a.reserve(c * sizeof(uint64_t)));
         }
+        CU_TRY(cudaMemsetAsync(rep.d_status, 0, kLanes * sizeof(uint32_t), rep.lane[0].stream));
+        CU_TRY(cudaStreamSynchronize(rep.lane[0].stream));
     }
+    std::vector<uint64_t> packed_turn(ndev, 0);
     for (uint64_t c = 0; c < max_chunks; c++) {
         for (size_t d = 0; d < ndev; d++) {
             Replica &rep = *idx->reps[d];
@@ -753,7 +788,26 @@ int fixed_packed_path(const msbwt_index *idx, const uint8_t *syms, uint32_t k, u
             if (b >= sl.end) continue;
             const uint64_t m = std::min(chunk, sl.end - b);
             DeviceGuard guard(rep.device);
-            Lane &ln = rep.lane[c % kLanes];
+            int raw_lane = -1;
+            if (hybrid)
+                for (int r = 0; r < kRawLanes && raw_lane < 0; r++)
+                    if (cudaEventQuery(rep.lane[kPackLanes + r].h2d_done) == cudaSuccess) raw_lane = kPackLanes + r;
+            if (raw_lane >= 0) {  // the link is idle: this chunk travels as symbol bytes
+                Lane &ln = rep.lane[raw_lane];
+                CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + b * k, m * k, cudaMemcpyHostToDevice, ln.stream));
+                CU_TRY(cudaEventRecord(ln.h2d_done, ln.stream));
+                CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
+                                        rep.d_status + raw_lane, ln.stream));
+                g_launches++;
+                CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
+                                           ln.stream, &g_call_launches));
+                flush_launches();
+                CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+                g_last_h2d += m * k;
+                g_last_d2h += m * sizeof(uint64_t);
+                continue;
+            }
+            Lane &ln = rep.lane[packed_turn[d]++ % kPackLanes];
             CU_TRY(cudaEventSynchronize(ln.h2d_done));  // the lane's staging buffer is free again
             uint64_t *stage = (uint64_t *)ln.h_stage.p;
             pool.run([&](int tid, int nthreads) {
@@ -776,7 +830,9 @@ int fixed_packed_path(const msbwt_index *idx, const uint8_t *syms, uint32_t k, u
     for (auto &rep : idx->reps) {
         DeviceGuard guard(rep->device);
         for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
+        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, kLanes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
+    if (int rc = check_status_flags(idx, "count_kmers_fixed"); rc != MSBWT_OK) return rc;  // raw chunks validate on the device
     // exceptions: k-mers with a symbol outside ACGT go through the byte path (device-side validation)
     std::vector<uint64_t> exc;
     for (auto &v : exc_by_thread) exc.insert(exc.end(), v.begin(), v.end());

@@ -76,3 +76,45 @@ def test_packed_route_many_chunks_and_all_exceptions(midsize, monkeypatch):
     q2 = q[:50_000].copy()
     q2[:, 30] = 4
     assert (g.count_kmers_fixed(q2, k) == o.count_kmers_fixed(q2, k, threads=8)).all()
+
+
+def test_hybrid_route_with_pinned_input(midsize, monkeypatch):
+    """A pinned caller buffer enables the hybrid route: chunks go either through the host pool (2 bits per
+    symbol) or, whenever the copy engine is idle, over the link as raw symbol bytes packed and validated on the
+    device.  Whatever the split, the counts equal the byte route's and the oracle's."""
+    from harness import synth
+    reads, o = midsize
+    monkeypatch.setenv("MSBWT_HOST_PACK", "1")
+    monkeypatch.setenv("MSBWT_HOST_THREADS", "2")  # a slow pool: the link takes a visible share
+    k = 31
+    q_dev = synth.make_queries(reads, k, 2_500_000, 1_000_001)
+    n = q_dev.shape[0]
+    pinned = torch.empty((n, k), dtype=torch.uint8, pin_memory=True)
+    pinned.copy_(q_dev)
+    q = pinned.numpy()
+    q[5, 0] = 4                      # exceptions in the first (raw) chunk and far into the batch
+    q[7, k - 1] = 0
+    q[3_000_000:3_000_100, k // 2] = 4
+    for quad, pair in ((0, 0), (0, 1), (1, 0)):
+        g = M.RleBWT(pair_index=pair, quad_index=quad)
+        g.load_vector(o.rle_bytes())
+        got = g.count_kmers_fixed(q, k)
+        h2d, d2h = M.last_transfer_bytes()
+        assert d2h >= n * 8
+        assert n * 8 < h2d < n * k + 4096, "both routes should have carried chunks"
+        m = 300_000
+        assert (got[:m] == o.count_kmers_fixed(q[:m], k, threads=8)).all()
+        assert (got[-m:] == o.count_kmers_fixed(q[-m:], k, threads=8)).all()
+        monkeypatch.setenv("MSBWT_HYBRID", "0")
+        assert (g.count_kmers_fixed(q, k) == got).all()
+        assert M.last_transfer_bytes()[0] < n * 8 + 200 * k + 4096
+        monkeypatch.delenv("MSBWT_HYBRID")
+    # a symbol >= 6 is refused whichever route its chunk takes
+    q[11, 3] = 9
+    with pytest.raises(M.MsbwtError) as e:
+        g.count_kmers_fixed(q, k)
+    assert e.value.code == 1
+    q[11, 3] = 1
+    q[n - 3, 3] = 7
+    with pytest.raises(M.MsbwtError):
+        g.count_kmers_fixed(q, k)

@@ -20,16 +20,16 @@ for w in $what; do
       timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
       echo "ref rc=$?"; head -c 600 gpurun_out/${tag}_bench_ref.json; echo ;;
     launches)
-      timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -c 400 --csv \
+      timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -c 250 --csv \
         --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/${tag}_launches.log 2>&1
       echo "launches rc=$?" ;;
     full_cfg3)
-      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:count_kmers_pair -s 3 -c 1 \
-        -f -o gpurun_out/${tag}_pair_cfg3 python bench.py --workload cfg3 --steps 1 --warmup 3 > gpurun_out/${tag}_full_cfg3.log 2>&1
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:count_kmers_quad -s 3 -c 1 \
+        -f -o gpurun_out/${tag}_quad_cfg3 python bench.py --workload cfg3 --steps 1 --warmup 3 > gpurun_out/${tag}_full_cfg3.log 2>&1
       echo "full_cfg3 rc=$?" ;;
     full_cfg2)
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:count_kmers_packed -s 6 -c 1 \
-        -f -o gpurun_out/${tag}_packed_cfg2 python bench.py --workload cfg2 --steps 1 --warmup 3 > gpurun_out/${tag}_full_cfg2.log 2>&1
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:count_kmers_quad -s 3 -c 1 \
+        -f -o gpurun_out/${tag}_quad_cfg2 python bench.py --workload cfg2 --steps 1 --warmup 3 > gpurun_out/${tag}_full_cfg2.log 2>&1
       echo "full_cfg2 rc=$?" ;;
   esac
 done
