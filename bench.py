@@ -35,6 +35,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]
     "cfg3": dict(key="cfg3", reads=10_000_000, read_len=150, coverage=30.0, error=0.01, n_read=100_000_000, n_random=0, k=31,
                  name="configs[2]: 10M synthetic 150bp reads with 1% errors (1.51 Gsymbol BWT), 100M read-sampled 31-mers"),
+    # BASELINE.json configs[4], one GPU's share: the 3.02 Gsymbol index is replicated, the 1 B queries are split 8 ways
+    "cfg5": dict(key="cfg5", reads=20_000_000, read_len=150, coverage=30.0, error=0.01, n_read=125_000_000, n_random=0, k=31,
+                 name="configs[4]: 20M synthetic 150bp reads with 1% errors (3.02 Gsymbol BWT), 125M read-sampled 31-mers per GPU (1 B over 8)"),
     # small shape for plumbing checks
     "tiny": dict(key="tiny", reads=20_000, read_len=150, coverage=30.0, error=0.01, n_read=100_000, n_random=100_000, k=31,
                  name="tiny: 20k reads, 200k 31-mers (plumbing check, not a bench line)"),

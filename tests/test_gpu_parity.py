@@ -287,7 +287,8 @@ def test_full_size_config1_properties():
     g = M.RleBWT.new()
     g.load_vector(rle)
     assert g.get_total_size() == total == 151_000_000
-    assert g.suffix_table_s == 12
+    # 219 MB of one-step blocks + depth-12 table exceed L2: the loader builds the quad image and deepens the table
+    assert g.quad_index and g.suffix_table_s == 15
     k = 30
     q = synth.make_queries(reads, k, 600_000, 400_000)
     base = g.count_kmers_fixed(q.cpu().numpy(), k)
