@@ -140,9 +140,16 @@ def build_workload(cfg: dict, device, rank: int):
     from harness import bwt_build, synth
     t0 = time.time()
     reads = synth.make_reads(cfg["reads"], cfg["read_len"], cfg["coverage"], cfg["error"], device=device)
-    rle, total = bwt_build.build_rle_bwt(reads)
-    rle_host = rle.cpu().numpy()
-    del rle
+    if device.type == "cuda":
+        # the library's own device-side builder (bwt_build.cu; equals the harness builder and naive_bwt, tests/)
+        import rust_msbwt_b200 as M
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        rle_host, total = M.build_rle_bwt(reads.data_ptr(), device.index or 0, reads.shape[0], reads.shape[1])
+    else:
+        rle, total = bwt_build.build_rle_bwt(reads)
+        rle_host = rle.cpu().numpy()
+        del rle
     queries = synth.make_queries(reads, cfg["k"], cfg["n_read"], cfg["n_random"], seed_offset=1000 * rank)
     del reads
     if device.type == "cuda":

@@ -222,6 +222,18 @@ int msbwt_debug_copy_quad_image(const msbwt_index *idx, int slot, uint64_t *nsec
 int msbwt_debug_host_pack(const uint8_t *syms, uint32_t k, uint64_t n, int threads, uint64_t *words,
                           uint64_t *exceptions, uint64_t max_exceptions, uint64_t *n_exceptions);
 
+/* ---- building the BWT itself (the step before the query path) ----
+ * Multi-string BWT of `n_reads` reads of `read_len` symbols each (one symbol per byte, 1..5 = A,C,G,N,T;
+ * 0 or >= 6 -> MSBWT_EINVAL), built on `device` and returned in the msbwt RLE byte format
+ * (src/bwt_converter.rs:52-56) -- what `msbwt2-build` produces for the same reads with its default sorted
+ * insertion (src/bin/msbwt2-build.rs:19-114, src/dynamic_bwt.rs:305-381), i.e. naive_bwt's order
+ * (src/bwt_util.rs:154-171).  `reads` is host memory, or device memory on `device` when reads_on_device != 0.
+ * *rle is a buffer of *rle_len bytes owned by the caller: release it with msbwt_buffer_free.
+ * *total = n_reads * (read_len + 1).  Equal-length reads only. */
+int msbwt_build_rle_bwt(const uint8_t *reads, uint64_t n_reads, uint32_t read_len, int reads_on_device,
+                        int device, uint8_t **rle, uint64_t *rle_len, uint64_t *total);
+void msbwt_buffer_free(uint8_t *p);
+
 /* ---- pinned host buffers for callers that want full copy/compute overlap ---- */
 void *msbwt_host_alloc(size_t bytes);
 void msbwt_host_free(void *p);

@@ -10,6 +10,7 @@ of that name at the repo root loads this package).
 """
 from .rle_bwt import (  # noqa: F401
     BWTRange,
+    build_rle_bwt,
     MsbwtError,
     RleBWT,
     convert_itos,

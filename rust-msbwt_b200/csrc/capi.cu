@@ -1085,6 +1085,53 @@ extern "C" int msbwt_debug_copy_quad_image(const msbwt_index *idx, int slot, uin
     return MSBWT_OK;
 }
 
+// ================================================================ construction of the BWT itself
+
+extern "C" int msbwt_build_rle_bwt(const uint8_t *reads, uint64_t n_reads, uint32_t read_len, int reads_on_device,
+                                   int device, uint8_t **rle, uint64_t *rle_len, uint64_t *total) {
+    g_last_error.clear();
+    if (!rle || !rle_len || !total) return fail(MSBWT_EINVAL, "NULL output pointer");
+    *rle = nullptr;
+    *rle_len = 0;
+    *total = 0;
+    if (n_reads && (!reads || !read_len)) return fail(MSBWT_EINVAL, "NULL reads or read_len == 0");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(MSBWT_ENODEV, "no usable CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= count) return fail(MSBWT_ENODEV, "device ordinal out of range");
+    DeviceGuard guard(device);
+    const uint8_t *d_reads = reads;
+    uint8_t *d_copy = nullptr;
+    if (!reads_on_device && n_reads) {
+        CU_TRY(cudaMalloc((void **)&d_copy, n_reads * read_len));
+        if (cudaError_t e = cudaMemcpy(d_copy, reads, n_reads * read_len, cudaMemcpyHostToDevice); e != cudaSuccess) {
+            cudaFree(d_copy);
+            return fail(MSBWT_ECUDA, std::string("copying the reads: ") + cudaGetErrorString(e));
+        }
+        d_reads = d_copy;
+    }
+    uint8_t *d_rle = nullptr;
+    std::string why;
+    int n = 0;
+    int rc = build_rle_bwt_on_device(d_reads, n_reads, read_len, &d_rle, rle_len, total, why, &n);
+    g_launches += (uint64_t)n;
+    if (d_copy) cudaFree(d_copy);
+    if (rc != MSBWT_OK) return fail(rc, why);
+    uint8_t *host = (uint8_t *)malloc(*rle_len ? *rle_len : 1);
+    if (!host) { cudaFree(d_rle); return fail(MSBWT_ENOMEM, "host buffer for the RLE bytes"); }
+    if (*rle_len) {
+        if (cudaError_t e = cudaMemcpy(host, d_rle, *rle_len, cudaMemcpyDeviceToHost); e != cudaSuccess) {
+            cudaFree(d_rle);
+            free(host);
+            return fail(MSBWT_ECUDA, std::string("copying the RLE bytes: ") + cudaGetErrorString(e));
+        }
+    }
+    if (d_rle) cudaFree(d_rle);
+    *rle = host;
+    return MSBWT_OK;
+}
+
+extern "C" void msbwt_buffer_free(uint8_t *p) { free(p); }
+
 // ================================================================ measurement aid
 
 extern "C" int msbwt_gather_bench(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,

@@ -74,6 +74,10 @@ int build_quad_image_on_device(int device, const IndexView &ix, const uint8_t *d
                                std::string &why, int *launches);
 void free_quad_image(QuadImage &img);
 
+// ---- bwt_build.cu: equal-length reads (device) -> RLE bytes of their multi-string BWT (device) ----
+int build_rle_bwt_on_device(const uint8_t *d_reads, uint64_t n_reads, uint32_t read_len, uint8_t **d_rle_out,
+                            uint64_t *rle_len, uint64_t *total, std::string &why, int *launches);
+
 // return an msbwt_status; on failure `why` explains
 int validate_rle(const uint8_t *rle, uint64_t len, std::string &why);
 int build_image_from_rle(const uint8_t *rle, uint64_t len, uint32_t sb_shift, HostImage &img, std::string &why);

@@ -128,6 +128,8 @@ def load_library():
         "msbwt_l2_fetch_granularity": (i32, [i32, i32]),
         "msbwt_debug_build_image": (i32, [vp, u64, u32, C.POINTER(u64), C.POINTER(u32), vp, vp, vp]),
         "msbwt_debug_copy_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp, vp]),
+        "msbwt_build_rle_bwt": (i32, [vp, u64, u32, i32, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]),
+        "msbwt_buffer_free": (None, [vp]),
         "msbwt_host_alloc": (vp, [C.c_size_t]),
         "msbwt_host_free": (None, [vp]),
         "msbwt_last_error": (C.c_char_p, []),
@@ -149,7 +151,7 @@ EXPORTED_SYMBOLS = (
     "msbwt_count_kmers_fixed", "msbwt_constrain_ranges", "msbwt_count_kmers_fixed_device",
     "msbwt_constrain_ranges_device", "msbwt_packed_bytes", "msbwt_pack_kmers_device",
     "msbwt_count_kmers_packed_device", "msbwt_launch_count", "msbwt_gather_bench", "msbwt_l2_fetch_granularity", "msbwt_debug_build_image", "msbwt_debug_copy_image",
-    "msbwt_host_alloc",
+    "msbwt_host_alloc", "msbwt_build_rle_bwt", "msbwt_buffer_free",
     "msbwt_host_free", "msbwt_last_error", "msbwt_abi_version",
 )
 
@@ -398,6 +400,30 @@ def debug_build_image(rle, superblock_shift: int = 0) -> tuple[np.ndarray, np.nd
     _check(L.msbwt_debug_build_image(_p(a), a.size, superblock_shift, C.byref(nb), C.byref(ns), _p(blocks), _p(aux),
                                      _p(cbase)), "image")
     return blocks, aux, cbase
+
+
+def build_rle_bwt(reads, device: int = 0, n_reads: int | None = None, read_len: int | None = None) -> tuple[np.ndarray, int]:
+    """Multi-string BWT of equal-length reads, built on the GPU, as msbwt RLE bytes: what `msbwt2-build`
+    writes for the same reads (sorted insertion; src/bin/msbwt2-build.rs, src/bwt_util.rs:154-171).
+    `reads`: an [n, L] uint8 array of symbols 1..5, or a raw device pointer (int) with n_reads / read_len.
+    Returns (rle bytes, total symbols)."""
+    L = load_library()
+    if isinstance(reads, int):
+        ptr, on_dev, n, ln = C.c_void_p(reads), 1, int(n_reads), int(read_len)
+        keep = None
+    else:
+        keep = _u8(reads)
+        if keep.ndim != 2:
+            raise MsbwtError(EINVAL, "reads must be an [n, L] array")
+        n, ln = keep.shape
+        ptr, on_dev = _p(keep), 0
+    out, nbytes, total = C.c_void_p(0), C.c_uint64(0), C.c_uint64(0)
+    _check(L.msbwt_build_rle_bwt(ptr, n, ln, on_dev, device, C.byref(out), C.byref(nbytes), C.byref(total)), "build_rle_bwt")
+    try:
+        rle = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(nbytes.value,)).copy() if nbytes.value else np.zeros(0, np.uint8)
+    finally:
+        L.msbwt_buffer_free(out)
+    return rle, int(total.value)
 
 
 def l2_fetch_granularity(device: int, nbytes: int = 0) -> int:
