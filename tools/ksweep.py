@@ -45,8 +45,7 @@ def main():
     torch.cuda.set_device(0)
     t0 = time.time()
     reads = synth.make_reads(args.reads, 150, 30.0, args.error, device=dev)
-    rle, total = bwt_build.build_rle_bwt(reads)
-    rle = rle.cpu().numpy()
+    rle, total = M.build_rle_bwt(reads.data_ptr(), 0, reads.shape[0], reads.shape[1])  # the library's own builder
     bwt = M.RleBWT.new(devices=[0])
     bwt.load_vector(rle)
     orc = O.RleBWT()
@@ -55,6 +54,7 @@ def main():
           f"lanes={bwt.kernel_lanes}, built in {time.time() - t0:.1f}s", file=sys.stderr)
     stream = torch.cuda.current_stream().cuda_stream
     out = {"bwt_symbols": total, "suffix_table_s": bwt.suffix_table_s, "kernel_lanes": bwt.kernel_lanes,
+           "quad_index": bwt.quad_index, "pair_index": bwt.pair_index,
            "queries_per_k": args.queries, "results": []}
     for k in (15, 31, 63, 101):
         q = synth.make_queries(reads, k, args.queries, 0, seed_offset=k)
