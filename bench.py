@@ -50,6 +50,7 @@ PAIR_BYTES = 128      # layout.h: one 128-byte line per 96 positions, two steps 
 PAIR_SYMS = 96
 QUAD_SECTOR_BYTES = 32  # layout.h: one 32-byte sector per 224 positions and 4-symbol code, four steps per sector (quad path)
 QUAD_SYMS = 224
+OCT_BUCKET_SHIFT = 20  # layout.h: one 128-byte line per (8-symbol code, 2^20-position bucket), eight steps per line (oct path)
 LINE_BYTES = 128      # what one L2 miss costs HBM whatever the request size (profiles/r1_gather_dram_bytes.csv)
 
 
@@ -57,14 +58,15 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def ncu_traffic(workload_key: str, lanes: int, table_s: int, pair: bool = False, quad: bool = False):
+def ncu_traffic(workload_key: str, lanes: int, table_s: int, pair: bool = False, quad: bool = False, oct_: bool = False):
     """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel, per launch, from the committed
     `ncu --set full` capture of this same workload/kernel configuration (profiles/ncu_traffic.json);
     None when no capture matches."""
     try:
         for e in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["captures"]:
             if (e["workload"] == workload_key and e["suffix_table_s"] == table_s and bool(e.get("pair", False)) == pair
-                    and bool(e.get("quad", False)) == quad and (pair or quad or e["lanes"] == lanes)):
+                    and bool(e.get("quad", False)) == quad and bool(e.get("oct", False)) == oct_
+                    and (pair or quad or e["lanes"] == lanes)):
                 return e["dram_bytes_per_launch"], e["source"]
     except Exception:
         pass
@@ -325,7 +327,7 @@ def measure_ours(args, cfg, ctx, primary: bool):
     res = {
         "value": value, "ms_per_step": total_ms / args.steps,
         "config": {"workload": cfg["name"], "bwt_symbols": total, "index_bytes": bwt.index_bytes, "k": k,
-                   "suffix_table_s": table_s, "pair_index": bwt.pair_index, "quad_index": bwt.quad_index,
+                   "suffix_table_s": table_s, "pair_index": bwt.pair_index, "quad_index": bwt.quad_index, "oct_index": bwt.oct_index,
                    "kernel_lanes_per_query": 1 if bwt.quad_index else (4 if bwt.pair_index else bwt.kernel_lanes),
                    "queries_per_gpu_per_step": n,
                    "parallelism": f"replica x{world}, query batch sharded",
@@ -373,19 +375,22 @@ def measure_ours(args, cfg, ctx, primary: bool):
         packed_q = 8 * (-(-k // 21) + 1) + 4   # symbol words + seed + index of the compacted live list
         bytes_per_query_no_table = (steps0 + two0) * BLOCK_BYTES / ms + packed_q + 8
         pair, quad = bwt.pair_index, bwt.quad_index
-        quad_lines = quad_sectors = 0
+        quad_lines = quad_sectors = oct_lines = 0
         if quad:
             # quad path: four of the reference's constrain_range calls per 32-B sector.  An L2 miss fills the
             # whole 128-B line, so the bytes HBM must move are counted per distinct LINE (l and h share one
             # 97 % of the time); the sector-granular figure is reported beside it.
-            st = orc.count_kmers_stats_quad(q_host[:ms], k, table_s, QUAD_SYMS, LINE_BYTES // QUAD_SECTOR_BYTES, BLOCK_SHIFT)
+            # with the oct image on top: eight calls per 128-B line while >= 8 symbols are left
+            st = orc.count_kmers_stats_quad(q_host[:ms], k, table_s, QUAD_SYMS, LINE_BYTES // QUAD_SECTOR_BYTES, BLOCK_SHIFT,
+                                            OCT_BUCKET_SHIFT if bwt.oct_index else 0)
             hits = st["table_hits"]
+            oct_lines = st["oct_steps"] + st["two_bucket_oct_steps"]
             quad_lines = st["quad_steps"] + st["two_line_quad_steps"]
             quad_sectors = st["quad_steps"] + st["two_sector_quad_steps"]
             pair_lines = 0
             one_blocks = st["one_steps"] + st["two_block_one_steps"]
-            ref_steps = 4 * st["quad_steps"] + st["one_steps"]
-            two_share = st["two_line_quad_steps"] / max(1, st["quad_steps"])
+            ref_steps = 8 * st["oct_steps"] + 4 * st["quad_steps"] + st["one_steps"]
+            two_share = (st["two_line_quad_steps"] + st["two_bucket_oct_steps"]) / max(1, st["quad_steps"] + st["oct_steps"])
         elif pair:
             st = orc.count_kmers_stats_pair(q_host[:ms], k, table_s, PAIR_SYMS, BLOCK_SHIFT)
             hits = st["table_hits"]
@@ -397,19 +402,20 @@ def measure_ours(args, cfg, ctx, primary: bool):
             steps, two, hits = orc.count_kmers_stats_skip(q_host[:ms], k, BLOCK_SHIFT, table_s)
             pair_lines, one_blocks, ref_steps = 0, steps + two, steps
             two_share = two / max(1, steps)
-        bytes_per_query = (quad_lines * LINE_BYTES + pair_lines * PAIR_BYTES + one_blocks * BLOCK_BYTES + hits * 32) / ms + packed_q + 8
-        sector_bytes_per_query = (quad_sectors * QUAD_SECTOR_BYTES + pair_lines * PAIR_BYTES + one_blocks * BLOCK_BYTES + hits * 32) / ms + packed_q + 8
-        accesses_per_query = (quad_lines + pair_lines + one_blocks + hits) / ms
+        bytes_per_query = (oct_lines * LINE_BYTES + quad_lines * LINE_BYTES + pair_lines * PAIR_BYTES + one_blocks * BLOCK_BYTES + hits * 32) / ms + packed_q + 8
+        sector_bytes_per_query = (oct_lines * LINE_BYTES + quad_sectors * QUAD_SECTOR_BYTES + pair_lines * PAIR_BYTES + one_blocks * BLOCK_BYTES + hits * 32) / ms + packed_q + 8
+        accesses_per_query = (oct_lines + quad_lines + pair_lines + one_blocks + hits) / ms
         peak, peak_src = measured_peak_gbs()
         kern_s = statistics.mean(kern_ms) / 1e3
         achieved = bytes_per_query * n / kern_s / 1e9
-        traffic, traffic_src = ncu_traffic(cfg["key"], bwt.kernel_lanes, table_s, pair, quad)
+        traffic, traffic_src = ncu_traffic(cfg["key"], bwt.kernel_lanes, table_s, pair, quad, bwt.oct_index)
         res["roofline"] = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src,
             "kernel": "count_kmers_quad_kernel" if quad else ("count_kmers_pair_kernel" if pair else "count_kmers_packed_kernel"),
             "kernel_ms": 1e3 * kern_s, "algorithmic_bytes_per_launch": bytes_per_query * n,
             "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": ref_steps / ms,
+            "oct_lines_per_query": oct_lines / ms, "oct_overflow_lines": bwt.oct_overflow_lines,
             "quad_lines_per_query": quad_lines / ms, "quad_sectors_per_query": quad_sectors / ms,
             "achieved_sector_granular": sector_bytes_per_query * n / kern_s / 1e9,
             "pair_lines_per_query": pair_lines / ms, "one_step_blocks_per_query": one_blocks / ms,

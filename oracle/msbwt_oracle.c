@@ -528,7 +528,18 @@ int orc_count_kmers_stats_pair(const orc_rle_bwt *b, const uint8_t *syms, uint32
 int orc_count_kmers_stats_quad(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
                                uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
                                unsigned block_shift, uint64_t *out) {
-    uint64_t qs = 0, q2s = 0, q2l = 0, os = 0, o2 = 0, hits = 0;
+    return orc_count_kmers_stats_oct(b, syms, k, n, table_s, sector_syms, line_sectors, block_shift, 0, out);
+}
+
+/* The same with an OCT image on top (oct_bucket_shift != 0): while eight or more symbols are left a step
+ * reads one line of the (code, 2^oct_bucket_shift-position bucket) it needs -- two when l and h fall in
+ * different buckets.  out[7] = oct steps, out[8] = oct steps over two buckets.  (Lines the engine answers
+ * through the quad image because they overflowed are not modelled: msbwt_oct_overflow_lines reports how
+ * many exist.) */
+int orc_count_kmers_stats_oct(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                              uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
+                              unsigned block_shift, unsigned oct_bucket_shift, uint64_t *out) {
+    uint64_t qs = 0, q2s = 0, q2l = 0, os = 0, o2 = 0, hits = 0, es = 0, e2 = 0;
     const uint64_t line_syms = (uint64_t)sector_syms * line_sectors;
     for (uint64_t i = 0; i < n; i++) {
         const uint8_t *q = syms + i * (uint64_t)k;
@@ -556,6 +567,13 @@ int orc_count_kmers_stats_quad(const orc_rle_bwt *b, const uint8_t *syms, uint32
         orc_range r = { 0, b->total_size };
         uint32_t t = k;
         for (uint32_t c = 0; c < done; c++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
+        if (all_acgt && oct_bucket_shift) {
+            while (t >= 8 && r.h != r.l) {
+                es++;
+                if ((r.l >> oct_bucket_shift) != (r.h >> oct_bucket_shift)) e2++;
+                for (int u = 0; u < 8; u++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
+            }
+        }
         if (all_acgt) {
             while (t >= 4 && r.h != r.l) {
                 qs++;
@@ -571,7 +589,8 @@ int orc_count_kmers_stats_quad(const orc_rle_bwt *b, const uint8_t *syms, uint32
             t--;
         }
     }
-    out[0] = qs; out[1] = q2s; out[2] = q2l; out[3] = os; out[4] = o2; out[5] = hits; out[6] = n; out[7] = 0;
+    out[0] = qs; out[1] = q2s; out[2] = q2l; out[3] = os; out[4] = o2; out[5] = hits; out[6] = n;
+    if (oct_bucket_shift) { out[7] = es; out[8] = e2; } else { out[7] = 0; }
     return ORC_OK;
 }
 

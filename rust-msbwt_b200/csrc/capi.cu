@@ -95,6 +95,7 @@ struct Replica {
                                                            // of its stride (pair: one level, quad: three)
     PairImage pair;            // 128-byte pair lines (layout.h), when the index lives in HBM
     QuadImage quad;            // 32-byte quad sectors (layout.h), when the index lives in HBM and the image fits
+    OctImage oct;              // 128-byte oct lines (layout.h), next to the quad image when positions are 32-bit
     int lanes = 1;           // kernel mapping: 1 = thread per query, 2 = lane pair per query (kernels.cu)
     uint64_t *d_cbase = nullptr;
     IndexView view{};
@@ -125,6 +126,7 @@ struct Replica {
         for (void *t : d_table_lower) if (t) cudaFree(t);
         free_pair_image(pair);
         free_quad_image(quad);
+        free_oct_image(oct);
         if (d_cbase) cudaFree(d_cbase);
         cudaSetDevice(cur);
     }
@@ -253,6 +255,7 @@ struct Options {
     int table_s = -1;   // -1 auto
     int pair = -1;      // -1 auto, 0 off, 1 on
     int quad = -1;      // -1 auto, 0 off, 1 on (builds the pair image on the way and drops it)
+    int oct = -1;       // -1 auto (with an automatic or requested quad image), 0 off, 1 on (implies quad)
     int lanes = 0;      // 0 auto, 1, 2
 };
 
@@ -346,15 +349,26 @@ bool pick_quad(int device, uint64_t index_bytes, uint64_t total, int requested, 
     return need <= (64ull << 30) && need <= free_b / 2;
 }
 
-// Builds pair image -> quad image, then drops the pair image (the quad kernel finishes a remainder with
-// one-step ranks, so nothing reads it afterwards).
-int build_quad(msbwt_index *idx, Replica &rep) {
+// The oct image (layout.h: one 128-byte line per EIGHT steps, 8 B/symbol) rides on the quad image: same
+// automatic condition, 32-bit positions only, and it must fit a quarter of the free device memory.
+bool pick_oct(const IndexView &view, int requested) {
+    if (index_is_wide(view)) return false;
+    if (requested == 0 || requested == 1) return requested == 1;
+    if (const char *env = getenv("MSBWT_OCT_INDEX")) return atoi(env) != 0;
+    return false;  // measured slower than the quad image alone on 30x read sets (gpurun_out/o1_*): opt-in
+}
+
+// Builds pair image -> quad image (-> oct image), then drops the pair image (the quad kernel finishes a
+// remainder with one-step ranks, so nothing reads it afterwards).
+int build_quad(msbwt_index *idx, Replica &rep, int oct_requested) {
     uint8_t *codes2 = nullptr;
     if (int rc = build_pair(idx, rep, &codes2); rc != MSBWT_OK) return rc;
     DeviceGuard guard(rep.device);
+    const bool want_oct = pick_oct(rep.view, oct_requested);
+    uint16_t *codes4 = nullptr;
     std::string why;
     int n = 0;
-    int rc = build_quad_image_on_device(rep.device, rep.view, codes2, rep.quad, why, &n);
+    int rc = build_quad_image_on_device(rep.device, rep.view, codes2, rep.quad, why, &n, want_oct ? &codes4 : nullptr);
     g_launches += (uint64_t)n;
     cudaFree(codes2);
     if (idx->reps[0].get() == &rep) idx->bytes_per_replica -= pair_image_bytes(rep.pair);
@@ -363,7 +377,7 @@ int build_quad(msbwt_index *idx, Replica &rep) {
     rep.view.c2base = nullptr;
     rep.view.npair = 0;
     rep.view.n_super2 = 0;
-    if (rc != MSBWT_OK) { free_quad_image(rep.quad); return fail(rc, why); }
+    if (rc != MSBWT_OK) { free_quad_image(rep.quad); if (codes4) cudaFree(codes4); return fail(rc, why); }
     rep.view.quad = rep.quad.sectors;
     rep.view.c4base = rep.quad.c4base;
     rep.view.nsec4 = rep.quad.nsec4;
@@ -372,6 +386,16 @@ int build_quad(msbwt_index *idx, Replica &rep) {
     if (idx->reps[0].get() == &rep)
         idx->bytes_per_replica += (uint64_t)kQuadCodes * rep.quad.nsec4 * kQuadSectorBytes +
                                   (rep.quad.c4base ? (uint64_t)rep.quad.n_super4 * kQuadCodes * sizeof(uint64_t) : 0);
+    if (want_oct) {
+        n = 0;
+        rc = build_oct_image_on_device(rep.device, rep.view, codes4, rep.oct, why, &n);
+        g_launches += (uint64_t)n;
+        cudaFree(codes4);
+        if (rc != MSBWT_OK) { free_oct_image(rep.oct); return fail(rc, why); }
+        rep.view.oct = rep.oct.lines;
+        rep.view.nbuck8 = rep.oct.nbuck8;
+        if (idx->reps[0].get() == &rep) idx->bytes_per_replica += (uint64_t)kOctCodes * rep.oct.nbuck8 * kOctLineBytes;
+    }
     return MSBWT_OK;
 }
 
@@ -460,10 +484,10 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
             bool quad;
             {
                 DeviceGuard guard(rep->device);
-                quad = pick_quad(rep->device, one_step_bytes, idx->total, opt.quad, opt.pair);
+                quad = opt.oct == 1 || pick_quad(rep->device, one_step_bytes, idx->total, opt.quad, opt.pair);
             }
             if (quad || pick_pair(rep->device, one_step_bytes, opt.pair)) {
-                if ((rc = quad ? build_quad(idx.get(), *rep) : build_pair(idx.get(), *rep)) != MSBWT_OK) break;
+                if ((rc = quad ? build_quad(idx.get(), *rep, opt.oct) : build_pair(idx.get(), *rep)) != MSBWT_OK) break;
                 if (!explicit_s && (quad || lives_in_hbm(rep->device, one_step_bytes))) {
                     DeviceGuard guard(rep->device);
                     const uint64_t multi = quad ? (uint64_t)kQuadCodes * rep->quad.nsec4 * kQuadSectorBytes
@@ -524,6 +548,7 @@ extern "C" msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len
         o.pair = opts->pair_index;
         o.lanes = opts->kernel_lanes;
         if (opts->struct_size >= offsetof(msbwt_options, quad_index) + sizeof(int32_t)) o.quad = opts->quad_index;
+        if (opts->struct_size >= offsetof(msbwt_options, oct_index) + sizeof(int32_t)) o.oct = opts->oct_index;
     }
     return create_common(rle, len, devices, ndev, o, err);
 }
@@ -562,6 +587,8 @@ extern "C" int msbwt_suffix_table_s(const msbwt_index *idx) { return idx ? (int)
 extern "C" int msbwt_kernel_lanes(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->lanes : 0; }
 extern "C" int msbwt_pair_index(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.pair) ? 1 : 0; }
 extern "C" int msbwt_quad_index(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.quad) ? 1 : 0; }
+extern "C" int msbwt_oct_index(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.oct) ? 1 : 0; }
+extern "C" uint64_t msbwt_oct_overflow_lines(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.overflow_lines : 0; }
 extern "C" uint64_t msbwt_launch_count(void) { return g_launches.load(); }
 extern "C" const char *msbwt_last_error(void) { return g_last_error.c_str(); }
 extern "C" int msbwt_abi_version(void) { return MSBWT_ABI_VERSION; }
@@ -1082,6 +1109,17 @@ extern "C" int msbwt_debug_copy_quad_image(const msbwt_index *idx, int slot, uin
     *n_super4 = rep.view.c4base ? rep.view.n_super4 : 0;
     if (sectors) CU_TRY(cudaMemcpy(sectors, rep.view.quad, (size_t)kQuadCodes * rep.view.nsec4 * kQuadSectorBytes, cudaMemcpyDeviceToHost));
     if (c4base && rep.view.c4base) CU_TRY(cudaMemcpy(c4base, rep.view.c4base, (size_t)rep.view.n_super4 * kQuadCodes * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return MSBWT_OK;
+}
+
+extern "C" int msbwt_debug_copy_oct_image(const msbwt_index *idx, int slot, uint64_t *nbuck8, uint32_t *lines) {
+    g_last_error.clear();
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size() || !nbuck8) return fail(MSBWT_EINVAL, "bad handle, slot or size output");
+    const Replica &rep = *idx->reps[slot];
+    if (!rep.view.oct) return fail(MSBWT_EINVAL, "this index has no oct image");
+    DeviceGuard guard(rep.device);
+    *nbuck8 = rep.view.nbuck8;
+    if (lines) CU_TRY(cudaMemcpy(lines, rep.view.oct, (size_t)kOctCodes * rep.view.nbuck8 * kOctLineBytes, cudaMemcpyDeviceToHost));
     return MSBWT_OK;
 }
 

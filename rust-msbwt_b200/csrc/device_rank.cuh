@@ -288,4 +288,55 @@ __device__ __forceinline__ void quad_step(const IndexView &ix, const C4Base<WIDE
     h = c4.at(sh, code) + b.w[0] + sector_count_below(b, ph);
 }
 
+// ---- oct image (layout.h): eight constrain_range steps per 128-byte line (32-bit positions only)
+
+struct OctLine { Half s[4]; };
+
+__device__ __forceinline__ OctLine ldg_oct_line(const IndexView &ix, uint32_t code, uint32_t bucket) {
+    const char *p = reinterpret_cast<const char *>(ix.oct) + ((size_t)code * ix.nbuck8 + bucket) * kOctLineBytes;
+    OctLine v;
+#pragma unroll
+    for (int i = 0; i < 4; i++) v.s[i] = ldg_index256(p + 32 * i);
+    return v;
+}
+
+// stored 24-bit offsets below pl / below ph (both < 2^20; empty slots hold 0xFFFFFF)
+__device__ __forceinline__ void oct_count_below(const OctLine &v, uint32_t pl, uint32_t ph, uint32_t &cl, uint32_t &ch) {
+    cl = 0; ch = 0;
+#pragma unroll
+    for (int g = 0; g < 10; g++) {  // 4 entries in every 3 words, words 2..31
+        const int w = 2 + 3 * g;
+        const uint32_t a = v.s[w >> 3].w[w & 7], b = v.s[(w + 1) >> 3].w[(w + 1) & 7], c = v.s[(w + 2) >> 3].w[(w + 2) & 7];
+        const uint32_t e0 = a & 0xFFFFFFu, e1 = __funnelshift_r(a, b, 24) & 0xFFFFFFu,
+                       e2 = __funnelshift_r(b, c, 16) & 0xFFFFFFu, e3 = c >> 8;
+        cl += (e0 < pl) + (e1 < pl) + (e2 < pl) + (e3 < pl);
+        ch += (e0 < ph) + (e1 < ph) + (e2 < ph) + (e3 < ph);
+    }
+}
+
+// Eight constrain_range steps at once: code = the eight symbols as base-4 digits, the first consumed one
+// most significant.  Returns false -- l, h untouched -- when a line involved holds more occurrences than it
+// can store; the caller then takes two quad steps instead.
+__device__ __forceinline__ bool oct_step(const IndexView &ix, uint32_t code, uint32_t &l, uint32_t &h) {
+    constexpr uint32_t kMask = (1u << kOctBucketShift) - 1u;
+    const uint32_t bl = l >> kOctBucketShift, bh = h >> kOctBucketShift;
+    const OctLine a = ldg_oct_line(ix, code, bl);
+    uint32_t cl, ch;
+    if (bh == bl) {
+        if (a.s[0].w[1] > (uint32_t)kOctCapacity) return false;
+        oct_count_below(a, l & kMask, h & kMask, cl, ch);
+        l = a.s[0].w[0] + cl;
+        h = a.s[0].w[0] + ch;
+        return true;
+    }
+    const OctLine b = ldg_oct_line(ix, code, bh);  // a range across a bucket boundary: one in 2^15 steps
+    if (a.s[0].w[1] > (uint32_t)kOctCapacity || b.s[0].w[1] > (uint32_t)kOctCapacity) return false;
+    uint32_t unused;
+    oct_count_below(a, l & kMask, 0u, cl, unused);
+    oct_count_below(b, h & kMask, 0u, ch, unused);
+    l = a.s[0].w[0] + cl;
+    h = b.s[0].w[0] + ch;
+    return true;
+}
+
 }  // namespace msbwt

@@ -70,9 +70,24 @@ struct QuadImage {
 };
 uint64_t quad_image_bytes(uint64_t total);
 // `ix` must carry the one-step blocks and the pair image; `d_codes2` = build_pair_image_on_device's keep_codes
+// `keep_codes` (optional): receives the per-position quad codes (0x100 | code, or 0 when invalid; device
+// memory the caller must cudaFree) -- the oct builder's input.
 int build_quad_image_on_device(int device, const IndexView &ix, const uint8_t *d_codes2, QuadImage &img,
-                               std::string &why, int *launches);
+                               std::string &why, int *launches, uint16_t **keep_codes = nullptr);
 void free_quad_image(QuadImage &img);
+
+// ---- oct_builder.cu: quad image + quad codes (resident on the current device) -> oct image ----
+struct OctImage {
+    uint4 *lines = nullptr;  // 65536 * nbuck8 * 128 B
+    uint64_t nbuck8 = 0;
+    uint64_t overflow_lines = 0;  // (code, bucket) lines with more than kOctCapacity occurrences
+};
+uint64_t oct_image_bytes(uint64_t total);
+// `ix` must carry the one-step blocks and the quad image, N < 2^32 with one superblock; `d_codes4` = the
+// quad builder's keep_codes
+int build_oct_image_on_device(int device, const IndexView &ix, const uint16_t *d_codes4, OctImage &img,
+                              std::string &why, int *launches);
+void free_oct_image(OctImage &img);
 
 // ---- bwt_build.cu: equal-length reads (device) -> RLE bytes of their multi-string BWT (device) ----
 int build_rle_bwt_on_device(const uint8_t *d_reads, uint64_t n_reads, uint32_t read_len, uint8_t **d_rle_out,
@@ -124,6 +139,9 @@ cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, cons
 // top bits of word 0 -> live list A (same scratch layout as launch_pack_seed produces)
 cudaError_t launch_seed_packed(const IndexView &ix, const uint64_t *d_words, uint32_t k, uint64_t n,
                                uint64_t *d_packed, uint64_t *d_out, cudaStream_t st);
+// quad_kernels.cu: live list A over the quad (and oct) image
+cudaError_t launch_count_quad(int device, const IndexView &ix, const uint64_t *d_packed, const PackedLayout &lay,
+                              uint32_t k, uint64_t *d_out, cudaStream_t st);
 bool packed_batch_needs_list_b(const IndexView &ix, uint32_t k);
 uint32_t max_host_packed_k();  // seed_packed_kernel handles k-mers of at most this many symbols
 cudaError_t launch_count_bytes(int device, const IndexView &ix, const uint8_t *d_syms,

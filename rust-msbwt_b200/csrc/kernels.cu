@@ -24,27 +24,11 @@
 
 #include "device_rank.cuh"
 #include "engine.h"
+#include "kernel_common.cuh"
 
 namespace msbwt {
 
 // ---------------------------------------------------------------- K0: pack + validate + seed
-
-// Symbols per step of the kernel that walks live list A: 4 with a quad image, 2 with a pair image, else 1.
-__host__ __device__ __forceinline__ uint32_t list_a_stride(const IndexView &ix) {
-    return ix.quad ? 4u : (ix.pair ? 2u : 1u);
-}
-
-// Suffix-table depth for an all-ACGT k-mer.  With a multi-step image (stride 2 or 4) the depth is
-// picked from the `stride` deepest levels {ts, ts-1, ..} so that the number of symbols left is a
-// multiple of the stride (k below those levels: no table).
-__host__ __device__ __forceinline__ uint32_t acgt_table_depth(uint32_t k, uint32_t ts, uint32_t stride) {
-    if (!ts) return 0;
-    if (k >= ts) {
-        const uint32_t back = (stride - (k - ts) % stride) % stride;
-        return back < ts ? ts - back : 0;
-    }
-    return k + stride > ts ? k : 0;  // level k itself is one of the kept ones: the table answers everything
-}
 
 // CTA-wide append to the two live lists (A grows from slot 0 upwards, B from slot n-1 downwards): one
 // atomicAdd per list per CTA -- a per-warp atomic on the same two counters serialises in L2.  Every
@@ -491,95 +475,6 @@ count_kmers_pair_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packe
     }
 }
 
-// Persistent kernel over live list A with a QUAD image: one thread per query, four symbols per step
-// (one 32-byte sector per boundary).  The depth the suffix table answered is a function of k alone for
-// an all-ACGT k-mer (acgt_table_depth), so the remaining count is uniform across the list; a remainder
-// that is not a multiple of four (k below the kept table levels) ends with one-step ranks.
-constexpr int quad_min_ctas(bool wide) { return wide ? 4 : 6; }
-
-// the rare remainder step of the quad kernel, kept out of line so that its 32 load registers do not
-// set the register budget of the quad loop
-template <bool WIDE>
-__device__ __noinline__ void remainder_step(const IndexView &ix, const CBase<WIDE> &cb, uint32_t sym,
-                                            typename Pos<WIDE>::type &l, typename Pos<WIDE>::type &h) {
-    rank_step<WIDE, 1>(ix, cb, sym, l, h);
-}
-
-template <bool WIDE>
-__global__ void __launch_bounds__(kCountThreads, quad_min_ctas(WIDE))
-count_kmers_quad_kernel(IndexView ix, const uint64_t *__restrict__ packed, PackedLayout lay, uint32_t k,
-                        uint64_t *__restrict__ out) {
-    using P = typename Pos<WIDE>::type;
-    __shared__ uint64_t c4_smem[WIDE ? kQuadMaxSuperInSmem * kQuadCodes : 1];
-    __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
-    const C4Base<WIDE> c4 = stage_c4base<WIDE>(ix, c4_smem);
-    const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
-    const uint64_t stream = policy_evict_first();
-
-    const uint32_t n = (uint32_t)packed[lay.live()];  // live queries of list A
-    const uint32_t owners = gridDim.x * kCountThreads;
-    uint32_t i = blockIdx.x * kCountThreads + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t *w0 = packed + lay.w0(), *seeds = packed + lay.seed(), *wx = packed + lay.wx();
-    const uint32_t *qidx = reinterpret_cast<const uint32_t *>(packed + lay.qidx());
-    const uint32_t rem0 = k - acgt_table_depth(k, ix.table_s, 4u);
-
-    P l = 0, h = 0;
-    uint64_t word = 0, pend = 0, next_word = 0, next_lo = 0;
-    [[maybe_unused]] uint64_t next_hi = 0;
-    uint32_t q = 0, next_q = 0;
-    uint32_t rem = 0;   // symbols still to consume
-    int shift = 62;     // bit offset of the next symbol (2 bits) in `word`
-    uint32_t widx = 0;
-
-    auto prefetch = [&](uint32_t ii) {
-        next_word = ldg_stream(w0 + ii, stream);
-        next_lo = ldg_stream(seeds + ii, stream);
-        if constexpr (WIDE) next_hi = ldg_stream(seeds + lay.n + ii, stream);
-        next_q = __ldg(qidx + ii);
-    };
-    auto begin = [&]() {
-        word = next_word;
-        q = next_q & kQidxMask;
-        if constexpr (WIDE) { l = next_lo; h = next_hi; } else { l = (uint32_t)next_lo; h = (uint32_t)(next_lo >> 32); }
-        rem = rem0;
-        shift = 62;
-        widx = 0;
-        if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + q, stream);  // needed 8 quad steps from now
-    };
-
-    prefetch(i);
-    begin();
-    if (i + owners < n) prefetch(i + owners);
-
-    for (;;) {
-        while (rem == 0 || l == h) {
-            stg_stream(out + q, (uint64_t)(h - l), stream);
-            i += owners;
-            if (i >= n) return;
-            begin();
-            if (i + owners < n) prefetch(i + owners);
-        }
-        if (shift < 0) {  // 32 symbols per word: a quad never straddles two words
-            word = pend;
-            widx++;
-            shift = 62;
-            if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + (uint64_t)widx * lay.n + q, stream);
-        }
-        if (rem >= 4u) {
-            const uint32_t code = (uint32_t)(word >> (shift - 6)) & 255u;
-            quad_step<WIDE>(ix, c4, code, l, h);
-            rem -= 4;
-            shift -= 8;
-        } else {
-            const uint32_t sym = (0x5321u >> (4u * ((uint32_t)(word >> shift) & 3u))) & 7u;  // A,C,G,T = 1,2,3,5
-            remainder_step<WIDE>(ix, cb, sym, l, h);
-            rem--;
-            shift -= 2;
-        }
-    }
-}
-
 // Variable-length form, symbols read straight from the caller's byte layout.
 template <bool WIDE>
 __global__ void __launch_bounds__(kCountThreads, min_ctas(WIDE, 1))
@@ -692,30 +587,6 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint4 *__restrict__ b
 
 // ---------------------------------------------------------------- launch wrappers
 
-static int g_sm_count[64];
-
-static int sm_count(int device) {
-    if (device < 0 || device >= 64) return 148;
-    if (!g_sm_count[device]) {
-        int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
-        g_sm_count[device] = v;
-    }
-    return g_sm_count[device];
-}
-
-// one full wave of CTAs (a multiple of the SM count), fewer if there is less work
-static unsigned persistent_grid(int device, const void *kernel, int threads, uint64_t work_groups,
-                                int groups_per_cta) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    uint64_t full = (uint64_t)sm_count(device) * (uint64_t)per_sm;
-    uint64_t need = (work_groups + groups_per_cta - 1) / groups_per_cta;
-    if (need < 1) need = 1;
-    return (unsigned)(need < full ? need : full);
-}
-
 static bool is_wide(const IndexView &ix) { return ix.n_super > 1 || (ix.total >> 32) != 0; }
 
 
@@ -760,15 +631,6 @@ static cudaError_t launch_count_pair_t(int device, const IndexView &ix, const ui
     return cudaGetLastError();
 }
 
-template <bool WIDE>
-static cudaError_t launch_count_quad_t(int device, const IndexView &ix, const uint64_t *d_packed,
-                                       const PackedLayout &lay, uint32_t k, uint64_t *d_out, cudaStream_t st) {
-    const unsigned grid = persistent_grid(device, (const void *)count_kmers_quad_kernel<WIDE>, kCountThreads, lay.n,
-                                          kCountThreads);
-    count_kmers_quad_kernel<WIDE><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out);
-    return cudaGetLastError();
-}
-
 // n <= kMaxPerLaunch (the callers chunk): query indices are u32 inside the kernels.
 // list A: quad kernel when the index has a quad image, pair kernel when it has a pair image, else the
 // one-step kernel on 2-bit words;
@@ -780,8 +642,7 @@ cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, cons
     const PackedLayout lay = packed_layout(ix, k, n);
     cudaError_t e;
     if (ix.quad)
-        e = is_wide(ix) ? launch_count_quad_t<true>(device, ix, d_packed, lay, k, d_out, st)
-                        : launch_count_quad_t<false>(device, ix, d_packed, lay, k, d_out, st);
+        e = launch_count_quad(device, ix, d_packed, lay, k, d_out, st);
     else if (ix.pair)
         e = is_wide(ix) ? launch_count_pair_t<true>(device, ix, d_packed, lay, k, d_out, st)
                         : launch_count_pair_t<false>(device, ix, d_packed, lay, k, d_out, st);

@@ -127,6 +127,32 @@ constexpr int kQuadCodes = 256;
 constexpr int kQuadMaxSuperShift = 24;  // 2^24 sectors * 224 positions < 2^32
 constexpr int kQuadMaxSuperInSmem = 8;  // rows of 256 u64 staged in shared memory (16 KB)
 
+// ---- oct ("eight-step") lines ---------------------------------------------------------------
+//
+// One more composition: code8(j) = code4(j) * 256 + code4(LF^4(j)) (valid when both halves are), and
+//
+//     eight successive constrain_range calls applied to i  ==  C8[c] + #{ j < i : code8(j) == c }.
+//
+// 65536 codes: a bit-vector per code is out of reach, but each code is rare (one position in 65536 on a
+// random text), so the occurrences are stored explicitly.  BWT positions are cut into buckets of 2^20;
+// one 128-byte line per (code, bucket), code-major (`address = (c * nbuck8 + (pos >> 20)) * 128`):
+//
+//     word 0      u32 checkpoint: C8[c] + #{ j < bucket start : code8(j) == c }   (N < 2^32 only)
+//     word 1      u32 number of occurrences of c in the bucket
+//     byte 8..127 up to 40 occurrences as 24-bit offsets within the bucket (little-endian, any order);
+//                 unused slots hold 0xFFFFFF, which no offset reaches
+//
+// rank8(c, p) = word0 + #{ stored offsets < (p & (2^20-1)) }: one line fill, no order needed.  A line
+// expects 16 occurrences; when a bucket holds more than 40 of one code (word 1 > 40: low-complexity
+// text) the kernel falls back to two quad steps for that query-step, so the result is exact on any
+// input.  128 * 65536 * (N / 2^20 + 1) bytes = 8 B/symbol: 12 GB at N = 1.51 G.  Built only next to a
+// quad image (which also serves remainders of 4..7 symbols) and only when N < 2^32.
+constexpr int kOctBucketShift = 20;
+constexpr int kOctCodes = 65536;
+constexpr int kOctLineBytes = 128;
+constexpr int kOctLineWords = 32;
+constexpr int kOctCapacity = 40;
+
 struct IndexView {
     const uint4 *blocks;     // nblocks * 4 uint4 (64 B per block)
     const uint32_t *aux;     // nblocks * 2  ($, N checkpoints)
@@ -140,6 +166,8 @@ struct IndexView {
     const uint4 *quad;       // 256 * nsec4 sectors of 32 B (2 uint4 each), or nullptr
     const uint64_t *c4base;  // n_super4 * 256 (u64), only when positions are 64-bit
     uint64_t nsec4;          // sectors per quad code: N / 224 + 2
+    const uint4 *oct;        // 65536 * nbuck8 lines of 128 B (8 uint4 each), or nullptr
+    uint64_t nbuck8;         // buckets per oct code: (N >> 20) + 1
     uint64_t total;          // N
     uint64_t nblocks;        // (N >> 7) + 1
     uint64_t npair;          // N / 96 + 1

@@ -152,7 +152,7 @@ uint64_t quad_image_bytes(uint64_t total) {
 }
 
 int build_quad_image_on_device(int device, const IndexView &ix, const uint8_t *d_codes2, QuadImage &img,
-                               std::string &why, int *launches) {
+                               std::string &why, int *launches, uint16_t **keep_codes) {
     if (!ix.pair || !d_codes2) { why = "quad image: needs the pair image and its code bytes"; return MSBWT_EINVAL; }
     const bool wide = index_is_wide(ix);
     const uint64_t nsec_real = ix.total / kQuadSyms + 1;  // the last one holds position N
@@ -229,6 +229,10 @@ int build_quad_image_on_device(int device, const IndexView &ix, const uint8_t *d
         }
     }
     Q_TRY(cudaDeviceSynchronize());
+    if (keep_codes) {  // hand the quad codes to the caller instead of freeing them with the scratch
+        *keep_codes = d_codes4;
+        tmp.ptrs.erase(std::find(tmp.ptrs.begin(), tmp.ptrs.end(), (void *)d_codes4));
+    }
     return MSBWT_OK;
 }
 

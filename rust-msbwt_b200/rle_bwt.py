@@ -73,7 +73,7 @@ class BWTRange:
 class Options(C.Structure):
     """`msbwt_options` (include/msbwt_gpu.h)."""
     _fields_ = [("struct_size", C.c_uint32), ("superblock_shift", C.c_uint32), ("suffix_table_s", C.c_int32),
-                ("pair_index", C.c_int32), ("kernel_lanes", C.c_int32), ("quad_index", C.c_int32)]
+                ("pair_index", C.c_int32), ("kernel_lanes", C.c_int32), ("quad_index", C.c_int32), ("oct_index", C.c_int32)]
 
 
 _lib = None
@@ -116,6 +116,9 @@ def load_library():
         "msbwt_kernel_lanes": (i32, [vp]),
         "msbwt_pair_index": (i32, [vp]),
         "msbwt_quad_index": (i32, [vp]),
+        "msbwt_oct_index": (i32, [vp]),
+        "msbwt_oct_overflow_lines": (u64, [vp]),
+        "msbwt_debug_copy_oct_image": (i32, [vp, i32, C.POINTER(u64), vp]),
         "msbwt_debug_copy_quad_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp]),
         "msbwt_last_transfer_bytes": (None, [C.POINTER(u64), C.POINTER(u64)]),
         "msbwt_host_pack_threads": (i32, []),
@@ -144,7 +147,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
-    "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
+    "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_oct_index", "msbwt_oct_overflow_lines",
+    "msbwt_debug_copy_oct_image", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
     "msbwt_debug_host_pack",
     "msbwt_index_destroy", "msbwt_total_size", "msbwt_symbol_count", "msbwt_start_index",
     "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_suffix_table_s", "msbwt_kernel_lanes", "msbwt_count_kmers",
@@ -182,7 +186,8 @@ class RleBWT:
     (None = the current device); batches are split across them (no collective)."""
 
     def __init__(self, bin_power: int = 8, devices: list[int] | None = None, superblock_shift: int = 0,
-                 suffix_table_s: int = -1, pair_index: int = -1, kernel_lanes: int = 0, quad_index: int = -1):
+                 suffix_table_s: int = -1, pair_index: int = -1, kernel_lanes: int = 0, quad_index: int = -1,
+                 oct_index: int = -1):
         # bin_power is accepted for signature parity (src/rle_bwt.rs:309-322); it never
         # changed results in the reference and has no counterpart in the device layout.
         self.bin_power = bin_power
@@ -192,6 +197,7 @@ class RleBWT:
         self._pair = pair_index         # -1 auto, 0 never, 1 always: the 128-byte pair image (two steps per line)
         self._lanes = kernel_lanes      # 0 auto, 1, 2
         self._quad = quad_index         # -1 auto, 0 never, 1 always: the 32-byte quad sectors (four steps per sector)
+        self._oct = oct_index           # -1 auto, 0 never, 1 always: the 128-byte oct lines (eight steps per line)
         self._h = None
 
     @classmethod
@@ -233,7 +239,7 @@ class RleBWT:
         a = _u8(bwt)
         err = C.c_int(0)
         devs, nd = self._dev_args()
-        opts = Options(C.sizeof(Options), self._sb_shift, self._table_s, self._pair, self._lanes, self._quad)
+        opts = Options(C.sizeof(Options), self._sb_shift, self._table_s, self._pair, self._lanes, self._quad, self._oct)
         h = L.msbwt_index_create_opts(_p(a), a.size, devs, nd, C.byref(opts), C.byref(err))
         if not h:
             _check(err.value or ECUDA, "load_vector")
@@ -363,6 +369,23 @@ class RleBWT:
         _check(L.msbwt_debug_copy_quad_image(self.handle, slot, C.byref(nb), C.byref(ns), _p(sectors), _p(c4base)),
                "quad image")
         return sectors, c4base
+
+    def oct_image(self, slot: int = 0) -> np.ndarray:
+        """lines[65536, nbuck8, 32] u32 of the oct image, copied back from the device."""
+        L = load_library()
+        nb = C.c_uint64(0)
+        _check(L.msbwt_debug_copy_oct_image(self.handle, slot, C.byref(nb), None), "oct image")
+        lines = np.zeros((65536, nb.value, 32), dtype=np.uint32)
+        _check(L.msbwt_debug_copy_oct_image(self.handle, slot, C.byref(nb), _p(lines)), "oct image")
+        return lines
+
+    @property
+    def oct_index(self) -> bool:
+        return bool(load_library().msbwt_oct_index(self.handle))
+
+    @property
+    def oct_overflow_lines(self) -> int:
+        return int(load_library().msbwt_oct_overflow_lines(self.handle))
 
     @property
     def quad_index(self) -> bool:

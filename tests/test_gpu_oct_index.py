@@ -1,0 +1,183 @@
+"""The OCT image (layout.h: one 128-byte line of explicit occurrence offsets per (8-symbol code, 2^20-position
+bucket); one line answers EIGHT constrain_range steps, src/rle_bwt.rs:202-287 composed eight times) and the
+kernel that walks it, falling back to two quad steps where a line overflowed.
+
+  * the image built on the device is compared with a numpy brute-force construction from the decoded BWT
+    (LF by counting, eight-symbol codes, per-bucket occurrence sets, checkpoints);
+  * every count through the oct path must equal the CPU oracle's (the reference's algorithm), for every
+    suffix-table depth / k remainder combination, with $ / N inside the k-mers, on typical read sets and on
+    low-complexity ones where most lines overflow."""
+import numpy as np
+import pytest
+
+import rust_msbwt_b200 as M
+from oracle import naive
+from oracle import oracle as O
+from tests.test_gpu_pair_index import _random_rle, decode
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+ACGT = np.array([1, 2, 3, 5])
+CAP, SHIFT = 40, 20
+
+
+def brute_oct(bwt: np.ndarray):
+    """(code8 per position or -1, C8[65536])"""
+    n = bwt.size
+    cnt = np.bincount(bwt, minlength=6)
+    cstart = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    lf = np.zeros(n, dtype=np.int64)
+    occ = np.zeros((6, n + 1), dtype=np.int64)
+    for s in range(6):
+        is_s = bwt == s
+        occ[s, 1:] = np.cumsum(is_s)
+        at = np.flatnonzero(is_s)
+        lf[at] = cstart[s] + np.arange(at.size)
+    idx = np.full(8, -1)
+    idx[ACGT] = np.arange(4)
+    j = np.arange(n)
+    code = np.zeros(n, dtype=np.int64)
+    valid = np.ones(n, dtype=bool)
+    for _ in range(8):
+        b = idx[bwt[j]] if n else np.zeros(0, dtype=np.int64)
+        valid &= b >= 0
+        code = code * 4 + np.maximum(b, 0)
+        j = lf[j] if n else j
+    codes = np.arange(65536)
+    pos = np.zeros(65536, dtype=np.int64)
+    for r in range(8):
+        sym = ACGT[(codes >> (2 * (7 - r))) & 3]
+        pos = cstart[sym] + occ[sym, pos]
+    return np.where(valid, code, -1), pos
+
+
+def check_oct_image(g, bwt):
+    lines = g.oct_image()
+    n = bwt.size
+    nb = (n >> SHIFT) + 1
+    assert lines.shape == (65536, nb, 32)
+    code, c8 = brute_oct(bwt)
+    pos = np.flatnonzero(code >= 0)
+    per = np.zeros((65536, nb), dtype=np.int64)
+    np.add.at(per, (code[pos], pos >> SHIFT), 1)
+    before = np.cumsum(per, axis=1) - per
+    assert (lines[:, :, 1] == per).all()
+    assert (lines[:, :, 0] == (before + c8[:, None]).astype(np.uint32)).all()
+    assert g.oct_overflow_lines == int((per > CAP).sum())
+    # stored offsets: 24-bit little-endian from byte 8; every non-overflowed line holds exactly its occurrences
+    raw = lines.view(np.uint8).reshape(65536, nb, 128)[:, :, 8:].reshape(65536, nb, CAP, 3).astype(np.uint32)
+    ent = raw[..., 0] | (raw[..., 1] << 8) | (raw[..., 2] << 16)
+    ent.sort(axis=2)
+    want = np.full((65536, nb, CAP), 0xFFFFFF, dtype=np.uint32)
+    order = np.lexsort((pos, pos >> SHIFT, code[pos]))
+    p_sorted = pos[order]
+    c_sorted, b_sorted = code[p_sorted], p_sorted >> SHIFT
+    first = np.flatnonzero(np.r_[True, (c_sorted[1:] != c_sorted[:-1]) | (b_sorted[1:] != b_sorted[:-1])]) if pos.size else np.zeros(0, int)
+    rank_in_line = np.arange(pos.size) - np.repeat(first, np.diff(np.r_[first, pos.size])) if pos.size else np.zeros(0, int)
+    keep = rank_in_line < CAP
+    want[c_sorted[keep], b_sorted[keep], rank_in_line[keep]] = (p_sorted[keep] & ((1 << SHIFT) - 1)).astype(np.uint32)
+    ok = per <= CAP
+    assert (ent[ok] == want[ok]).all()
+    # overflowed lines hold some 40 of their occurrences (which ones depends on the scatter's timing)
+    for c, b in np.argwhere(~ok)[:50]:
+        mine = set((pos[(code[pos] == c) & ((pos >> SHIFT) == b)] & ((1 << SHIFT) - 1)).tolist())
+        assert set(ent[c, b].tolist()) <= mine and len(set(ent[c, b].tolist())) == CAP
+
+
+def test_oct_image_equals_brute_force():
+    rng = np.random.default_rng(2020)
+    from harness import bwt_build, synth
+    reads = synth.make_reads(400, 60, 15.0, 0.02, device="cuda")
+    reads[3, 10:12] = 4
+    low = synth.make_reads(3000, 50, 600.0, 0.0, device="cuda")    # 250-base genome: every line that is used overflows
+    streams = [
+        O.convert_to_vec(naive.naive_bwt(["CCGTACGTA", "GGTACAGTA", "ACGACGACG", "ANNT"])),
+        _random_rle(rng, 3000, [1, 1, 1, 2, 3, 5, 9, 31, 32, 33, 95, 96, 97, 223, 224, 225, 255]),
+        O.convert_to_vec("ACGT" * 56 + "T"),
+        bwt_build.build_rle_bwt(reads)[0].cpu().numpy(),
+        bwt_build.build_rle_bwt(low)[0].cpu().numpy(),
+        np.zeros(0, np.uint8),
+    ]
+    for rle in streams:
+        g = M.RleBWT(oct_index=1)
+        g.load_vector(rle)
+        assert g.oct_index and g.quad_index and not g.pair_index
+        bwt = decode(np.asarray(rle, dtype=np.uint8))
+        assert bwt.size == g.get_total_size()
+        check_oct_image(g, bwt)
+
+
+@pytest.fixture(scope="module")
+def midsize():
+    from harness import bwt_build, synth
+    reads = synth.make_reads(20000, read_len=100, coverage=25.0, error_rate=0.01, device="cuda")
+    reads[17, 40:43] = 4  # a few N
+    rle, n = bwt_build.build_rle_bwt(reads)
+    o = O.RleBWT()
+    o.load_vector(rle.cpu().numpy())
+    return reads, o
+
+
+def test_oct_image_over_several_buckets(midsize):
+    reads, o = midsize
+    g = M.RleBWT(oct_index=1)
+    g.load_vector(o.rle_bytes())
+    assert g.oct_index and (g.get_total_size() >> SHIFT) >= 1
+    check_oct_image(g, decode(o.rle_bytes()))
+
+
+@pytest.mark.parametrize("table_s", [-1, 0, 1, 2, 3, 4, 5, 7])
+def test_oct_path_is_bit_exact(midsize, table_s):
+    from harness import synth
+    reads, o = midsize
+    g = M.RleBWT(suffix_table_s=table_s, oct_index=1)
+    g.load_vector(o.rle_bytes())
+    assert g.oct_index
+    rng = np.random.default_rng(11 + 10 * (table_s + 1))
+    for k in (1, 2, 3, 4, 5, 7, 8, 9, 11, 12, 13, 15, 16, 17, 23, 24, 25, 31, 32, 33, 39, 40, 41, 47, 48, 63, 64, 65, 66, 67, 71, 72, 100):
+        q = synth.make_queries(reads, k, 12001, 8000).cpu().numpy()
+        q[5, 0] = 4
+        q[7, k - 1] = 0
+        q[11, k // 2] = 4
+        got = g.count_kmers_fixed(q, k)
+        want = o.count_kmers_fixed(q, k, threads=8)
+        assert (got == want).all(), (table_s, k, np.flatnonzero(got != want)[:5])
+        if k >= 29:
+            assert int((got > 0).sum()) >= 11990
+    ragged = [rng.integers(0, 6, int(rng.integers(0, 40))).astype(np.uint8) for _ in range(3000)]
+    assert (g.count_kmers(ragged) == o.count_kmers(ragged)).all()
+
+
+def test_oct_path_on_low_complexity_reads_where_lines_overflow(monkeypatch):
+    """A 2 kb genome at 1500x: a handful of codes own every position of a bucket, most lines in use hold far
+    more than 40 occurrences and are answered through the quad image -- the counts must not notice."""
+    from harness import bwt_build, synth
+    reads = synth.make_reads(30000, read_len=100, coverage=1500.0, error_rate=0.002, device="cuda")
+    rle = bwt_build.build_rle_bwt(reads)[0].cpu().numpy()
+    o = O.RleBWT()
+    o.load_vector(rle)
+    g = M.RleBWT(oct_index=1)
+    g.load_vector(rle)
+    assert g.oct_index and g.oct_overflow_lines > 1000
+    for k in (8, 16, 31, 32, 41, 64):
+        q = synth.make_queries(reads, k, 20000, 5000).cpu().numpy()
+        assert (g.count_kmers_fixed(q, k) == o.count_kmers_fixed(q, k, threads=8)).all(), k
+    monkeypatch.setenv("MSBWT_HOST_PACK", "1")
+    q = synth.make_queries(reads, 31, 50000, 5000).cpu().numpy()
+    assert (g.count_kmers_fixed(q, 31) == o.count_kmers_fixed(q, 31, threads=8)).all()
+
+
+def test_oct_on_golden_fixture_and_wide_indexes_refuse_it(golden_dir):
+    z = np.load(f"{golden_dir}/reads30x_k31.npz")
+    g = M.RleBWT(oct_index=1)
+    g.load_vector(z["rle"])
+    assert g.oct_index
+    assert (g.count_kmers_fixed(z["queries"], int(z["k"])) == z["counts"]).all()
+    assert (g.count_kmers_fixed(z["queries_k12"], 12) == z["counts_k12"]).all()
+    # 64-bit positions (several superblocks): the oct image is not built, the quad image serves alone
+    w = M.RleBWT(oct_index=1, superblock_shift=3)
+    w.load_vector(z["rle"])
+    assert w.quad_index and not w.oct_index
+    assert (w.count_kmers_fixed(z["queries"], int(z["k"])) == z["counts"]).all()
