@@ -50,7 +50,6 @@ PAIR_BYTES = 128      # layout.h: one 128-byte line per 96 positions, two steps 
 PAIR_SYMS = 96
 QUAD_SECTOR_BYTES = 32  # layout.h: one 32-byte sector per 224 positions and 4-symbol code, four steps per sector (quad path)
 QUAD_SYMS = 224
-OCT_BUCKET_SHIFT = 20  # layout.h: one 128-byte line per (8-symbol code, 2^20-position bucket), eight steps per line (oct path)
 LINE_BYTES = 128      # what one L2 miss costs HBM whatever the request size (profiles/r1_gather_dram_bytes.csv)
 
 
@@ -382,7 +381,7 @@ def measure_ours(args, cfg, ctx, primary: bool):
             # 97 % of the time); the sector-granular figure is reported beside it.
             # with the oct image on top: eight calls per 128-B line while >= 8 symbols are left
             st = orc.count_kmers_stats_quad(q_host[:ms], k, table_s, QUAD_SYMS, LINE_BYTES // QUAD_SECTOR_BYTES, BLOCK_SHIFT,
-                                            OCT_BUCKET_SHIFT if bwt.oct_index else 0)
+                                            bwt.oct_bucket_shift if bwt.oct_index else 0)
             hits = st["table_hits"]
             oct_lines = st["oct_steps"] + st["two_bucket_oct_steps"]
             quad_lines = st["quad_steps"] + st["two_line_quad_steps"]
@@ -416,6 +415,7 @@ def measure_ours(args, cfg, ctx, primary: bool):
             "kernel_ms": 1e3 * kern_s, "algorithmic_bytes_per_launch": bytes_per_query * n,
             "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": ref_steps / ms,
             "oct_lines_per_query": oct_lines / ms, "oct_overflow_lines": bwt.oct_overflow_lines,
+            "oct_overflow_position_share": bwt.oct_overflow_occurrences / max(1, total), "oct_bucket_shift": bwt.oct_bucket_shift,
             "quad_lines_per_query": quad_lines / ms, "quad_sectors_per_query": quad_sectors / ms,
             "achieved_sector_granular": sector_bytes_per_query * n / kern_s / 1e9,
             "pair_lines_per_query": pair_lines / ms, "one_step_blocks_per_query": one_blocks / ms,

@@ -90,12 +90,13 @@ msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *
  * 32-byte sectors (layout.h), FOUR constrain_range steps per line fill, 256*N/7 bytes -- replaces the
  * pair image (-1 = automatic: the index lives in HBM and the image is <= 64 GB and <= half the free
  * device memory; MSBWT_QUAD_INDEX=0|1 overrides), 0 = never, 1 = always.  Results are identical.
- * `oct_index`: the OCT image -- one 128-byte line of explicit occurrence offsets per (8-symbol code,
- * 2^20-position bucket), EIGHT constrain_range steps per line fill, 8 bytes per symbol -- is built next
- * to the quad image when positions are 32-bit (-1 = automatic: whenever the quad image is built and both
- * fit half the free device memory; MSBWT_OCT_INDEX=0|1 overrides), 0 = never, 1 = always (implies
- * quad_index).  Lines that cannot hold their bucket's occurrences are answered through the quad image,
- * so results are identical on any input. */
+ * `oct_index`: the OCT image -- one 128-byte line of explicit occurrence RUNS per (8-symbol code, 2^b-position
+ * bucket), EIGHT constrain_range steps per line fill, 2^(23-b) bytes per symbol -- is built next to the quad
+ * image when positions are 32-bit (-1 = automatic: whenever the quad image is built and the oct image fits a
+ * quarter of the device memory left; MSBWT_OCT_INDEX=0|1 overrides), 0 = never, 1 = always (implies
+ * quad_index).  Lines that cannot hold their bucket's runs are answered through the quad image, so results
+ * are identical on any input.  `oct_bucket_shift`: b, 8..23 (0 = automatic: the largest b that keeps the mean
+ * number of runs per line <= 12). */
 typedef struct msbwt_options {
     uint32_t struct_size;
     uint32_t superblock_shift; /* 0 = default */
@@ -104,6 +105,7 @@ typedef struct msbwt_options {
     int32_t kernel_lanes;      /* 0 = automatic */
     int32_t quad_index;        /* -1 = automatic (ABI 3; a caller's shorter ABI-2 struct means -1) */
     int32_t oct_index;         /* -1 = automatic (ABI 3) */
+    int32_t oct_bucket_shift;  /* 0 = automatic (ABI 3) */
 } msbwt_options;
 msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
                                      const msbwt_options *opts, int *err);
@@ -126,6 +128,9 @@ int msbwt_pair_index(const msbwt_index *idx); /* 1 when the pair image is in use
 int msbwt_quad_index(const msbwt_index *idx); /* 1 when the quad image is in use (it replaces the pair image) */
 int msbwt_oct_index(const msbwt_index *idx);  /* 1 when the oct image is in use (next to the quad image) */
 uint64_t msbwt_oct_overflow_lines(const msbwt_index *idx); /* oct lines answered through the quad image */
+uint64_t msbwt_oct_overflow_occurrences(const msbwt_index *idx); /* BWT positions those lines cover */
+uint64_t msbwt_oct_runs(const msbwt_index *idx);           /* runs of equal 8-symbol codes in the BWT (chose b) */
+int msbwt_oct_bucket_shift(const msbwt_index *idx);        /* b of the oct image in use, 0 without one */
 
 /* ---- queries from HOST buffers (the drop-in calls) ---- */
 
@@ -224,7 +229,8 @@ int msbwt_debug_copy_pair_image(const msbwt_index *idx, int slot, uint64_t *npai
 int msbwt_debug_copy_quad_image(const msbwt_index *idx, int slot, uint64_t *nsec4, uint32_t *n_super4,
                                 uint32_t *sectors, uint64_t *c4base);
 
-/* The oct image of a replica: 65536 * *nbuck8 lines of 32 u32 words, code-major.  NULL array: size only. */
+/* The oct image of a replica: 65536 * *nbuck8 lines of 32 u32 words, code-major (nbuck8 = (N >> b) + 1).
+ * NULL array: size only. */
 int msbwt_debug_copy_oct_image(const msbwt_index *idx, int slot, uint64_t *nbuck8, uint32_t *lines);
 
 /* The host-side 2-bit packer of the end-to-end path, on its own (no device needed): packs n k-mers of k

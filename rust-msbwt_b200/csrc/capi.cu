@@ -256,6 +256,7 @@ struct Options {
     int pair = -1;      // -1 auto, 0 off, 1 on
     int quad = -1;      // -1 auto, 0 off, 1 on (builds the pair image on the way and drops it)
     int oct = -1;       // -1 auto (with an automatic or requested quad image), 0 off, 1 on (implies quad)
+    int oct_shift = 0;  // 0 auto, else the oct image's bucket shift
     int lanes = 0;      // 0 auto, 1, 2
 };
 
@@ -349,18 +350,19 @@ bool pick_quad(int device, uint64_t index_bytes, uint64_t total, int requested, 
     return need <= (64ull << 30) && need <= free_b / 2;
 }
 
-// The oct image (layout.h: one 128-byte line per EIGHT steps, 8 B/symbol) rides on the quad image: same
-// automatic condition, 32-bit positions only, and it must fit a quarter of the free device memory.
+// The oct image (layout.h: one 128-byte line per EIGHT steps, 1..8 B/symbol) rides on the quad image: same
+// automatic condition, 32-bit positions only; it may take a quarter of the device memory left after the quad
+// image (the builder picks coarser buckets, or builds nothing, beyond that).
 bool pick_oct(const IndexView &view, int requested) {
     if (index_is_wide(view)) return false;
     if (requested == 0 || requested == 1) return requested == 1;
     if (const char *env = getenv("MSBWT_OCT_INDEX")) return atoi(env) != 0;
-    return false;  // measured slower than the quad image alone on 30x read sets (gpurun_out/o1_*): opt-in
+    return true;
 }
 
 // Builds pair image -> quad image (-> oct image), then drops the pair image (the quad kernel finishes a
 // remainder with one-step ranks, so nothing reads it afterwards).
-int build_quad(msbwt_index *idx, Replica &rep, int oct_requested) {
+int build_quad(msbwt_index *idx, Replica &rep, int oct_requested, int oct_shift) {
     uint8_t *codes2 = nullptr;
     if (int rc = build_pair(idx, rep, &codes2); rc != MSBWT_OK) return rc;
     DeviceGuard guard(rep.device);
@@ -388,13 +390,23 @@ int build_quad(msbwt_index *idx, Replica &rep, int oct_requested) {
                                   (rep.quad.c4base ? (uint64_t)rep.quad.n_super4 * kQuadCodes * sizeof(uint64_t) : 0);
     if (want_oct) {
         n = 0;
-        rc = build_oct_image_on_device(rep.device, rep.view, codes4, rep.oct, why, &n);
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+        // the 8-symbol codes (4 B per position) are scratch of the build and must fit next to the image
+        const uint64_t scratch = 4 * rep.view.total;
+        const uint64_t budget = oct_requested == 1 ? (free_b > scratch ? free_b - scratch : 0)
+                                                   : (free_b / 2 > scratch ? std::min<uint64_t>(free_b / 4, free_b / 2 - scratch) : 0);
+        if (!oct_shift)
+            if (const char *env = getenv("MSBWT_OCT_BUCKET_SHIFT")) oct_shift = atoi(env);
+        rc = build_oct_image_on_device(rep.device, rep.view, codes4, oct_shift, budget, rep.oct, why, &n);  // frees codes4
         g_launches += (uint64_t)n;
-        cudaFree(codes4);
         if (rc != MSBWT_OK) { free_oct_image(rep.oct); return fail(rc, why); }
-        rep.view.oct = rep.oct.lines;
-        rep.view.nbuck8 = rep.oct.nbuck8;
-        if (idx->reps[0].get() == &rep) idx->bytes_per_replica += (uint64_t)kOctCodes * rep.oct.nbuck8 * kOctLineBytes;
+        if (rep.oct.lines) {
+            rep.view.oct = rep.oct.lines;
+            rep.view.nbuck8 = rep.oct.nbuck8;
+            rep.view.oct_shift = (uint32_t)rep.oct.shift;
+            if (idx->reps[0].get() == &rep) idx->bytes_per_replica += (uint64_t)kOctCodes * rep.oct.nbuck8 * kOctLineBytes;
+        }
     }
     return MSBWT_OK;
 }
@@ -487,7 +499,7 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
                 quad = opt.oct == 1 || pick_quad(rep->device, one_step_bytes, idx->total, opt.quad, opt.pair);
             }
             if (quad || pick_pair(rep->device, one_step_bytes, opt.pair)) {
-                if ((rc = quad ? build_quad(idx.get(), *rep, opt.oct) : build_pair(idx.get(), *rep)) != MSBWT_OK) break;
+                if ((rc = quad ? build_quad(idx.get(), *rep, opt.oct, opt.oct_shift) : build_pair(idx.get(), *rep)) != MSBWT_OK) break;
                 if (!explicit_s && (quad || lives_in_hbm(rep->device, one_step_bytes))) {
                     DeviceGuard guard(rep->device);
                     const uint64_t multi = quad ? (uint64_t)kQuadCodes * rep->quad.nsec4 * kQuadSectorBytes
@@ -549,6 +561,7 @@ extern "C" msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len
         o.lanes = opts->kernel_lanes;
         if (opts->struct_size >= offsetof(msbwt_options, quad_index) + sizeof(int32_t)) o.quad = opts->quad_index;
         if (opts->struct_size >= offsetof(msbwt_options, oct_index) + sizeof(int32_t)) o.oct = opts->oct_index;
+        if (opts->struct_size >= offsetof(msbwt_options, oct_bucket_shift) + sizeof(int32_t)) o.oct_shift = opts->oct_bucket_shift;
     }
     return create_common(rle, len, devices, ndev, o, err);
 }
@@ -589,6 +602,9 @@ extern "C" int msbwt_pair_index(const msbwt_index *idx) { return (idx && !idx->r
 extern "C" int msbwt_quad_index(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.quad) ? 1 : 0; }
 extern "C" int msbwt_oct_index(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.oct) ? 1 : 0; }
 extern "C" uint64_t msbwt_oct_overflow_lines(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.overflow_lines : 0; }
+extern "C" uint64_t msbwt_oct_overflow_occurrences(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.overflow_occurrences : 0; }
+extern "C" uint64_t msbwt_oct_runs(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.runs : 0; }
+extern "C" int msbwt_oct_bucket_shift(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.oct) ? (int)idx->reps[0]->view.oct_shift : 0; }
 extern "C" uint64_t msbwt_launch_count(void) { return g_launches.load(); }
 extern "C" const char *msbwt_last_error(void) { return g_last_error.c_str(); }
 extern "C" int msbwt_abi_version(void) { return MSBWT_ABI_VERSION; }

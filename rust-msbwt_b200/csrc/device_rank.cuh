@@ -300,42 +300,58 @@ __device__ __forceinline__ OctLine ldg_oct_line(const IndexView &ix, uint32_t co
     return v;
 }
 
-// stored 24-bit offsets below pl / below ph (both < 2^20; empty slots hold 0xFFFFFF)
-__device__ __forceinline__ void oct_count_below(const OctLine &v, uint32_t pl, uint32_t ph, uint32_t &cl, uint32_t &ch) {
-    cl = 0; ch = 0;
+// occurrences of the line's code below bucket offsets pl / ph: sum over the stored runs `(len << b) | off`
+// of clamp(p - off, 0, len); empty slots are 0 and add nothing.  `nruns` (word 1) tells which sectors of
+// the line hold runs at all (slots fill in order).
+__device__ __forceinline__ void oct_count_below(const OctLine &v, uint32_t b, int pl, int ph, uint32_t &cl, uint32_t &ch) {
+    const uint32_t mask = (1u << b) - 1u;
+    const uint32_t nruns = v.s[0].w[1];
+    int sl = 0, sh = 0;
+    auto add = [&](uint32_t e) {
+        const int off = (int)(e & mask), len = (int)(e >> b);
+        sl += min(max(pl - off, 0), len);
+        sh += min(max(ph - off, 0), len);
+    };
 #pragma unroll
-    for (int g = 0; g < 10; g++) {  // 4 entries in every 3 words, words 2..31
-        const int w = 2 + 3 * g;
-        const uint32_t a = v.s[w >> 3].w[w & 7], b = v.s[(w + 1) >> 3].w[(w + 1) & 7], c = v.s[(w + 2) >> 3].w[(w + 2) & 7];
-        const uint32_t e0 = a & 0xFFFFFFu, e1 = __funnelshift_r(a, b, 24) & 0xFFFFFFu,
-                       e2 = __funnelshift_r(b, c, 16) & 0xFFFFFFu, e3 = c >> 8;
-        cl += (e0 < pl) + (e1 < pl) + (e2 < pl) + (e3 < pl);
-        ch += (e0 < ph) + (e1 < ph) + (e2 < ph) + (e3 < ph);
+    for (int w = 2; w < 8; w++) add(v.s[0].w[w]);
+    if (nruns > 6u) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) add(v.s[1].w[w]);
+        if (nruns > 14u) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) add(v.s[2].w[w]);
+            if (nruns > 22u) {
+#pragma unroll
+                for (int w = 0; w < 8; w++) add(v.s[3].w[w]);
+            }
+        }
     }
+    cl = (uint32_t)sl;
+    ch = (uint32_t)sh;
 }
 
 // Eight constrain_range steps at once: code = the eight symbols as base-4 digits, the first consumed one
-// most significant.  Returns false -- l, h untouched -- when a line involved holds more occurrences than it
+// most significant.  Returns false -- l, h untouched -- when a line involved holds more runs than it
 // can store; the caller then takes two quad steps instead.
 __device__ __forceinline__ bool oct_step(const IndexView &ix, uint32_t code, uint32_t &l, uint32_t &h) {
-    constexpr uint32_t kMask = (1u << kOctBucketShift) - 1u;
-    const uint32_t bl = l >> kOctBucketShift, bh = h >> kOctBucketShift;
+    const uint32_t b = ix.oct_shift, mask = (1u << b) - 1u;
+    const uint32_t bl = l >> b, bh = h >> b;
     const OctLine a = ldg_oct_line(ix, code, bl);
     uint32_t cl, ch;
     if (bh == bl) {
         if (a.s[0].w[1] > (uint32_t)kOctCapacity) return false;
-        oct_count_below(a, l & kMask, h & kMask, cl, ch);
+        oct_count_below(a, b, (int)(l & mask), (int)(h & mask), cl, ch);
         l = a.s[0].w[0] + cl;
         h = a.s[0].w[0] + ch;
         return true;
     }
-    const OctLine b = ldg_oct_line(ix, code, bh);  // a range across a bucket boundary: one in 2^15 steps
-    if (a.s[0].w[1] > (uint32_t)kOctCapacity || b.s[0].w[1] > (uint32_t)kOctCapacity) return false;
+    const OctLine c = ldg_oct_line(ix, code, bh);  // a range across a bucket boundary: rare
+    if (a.s[0].w[1] > (uint32_t)kOctCapacity || c.s[0].w[1] > (uint32_t)kOctCapacity) return false;
     uint32_t unused;
-    oct_count_below(a, l & kMask, 0u, cl, unused);
-    oct_count_below(b, h & kMask, 0u, ch, unused);
+    oct_count_below(a, b, (int)(l & mask), 0, cl, unused);
+    oct_count_below(c, b, (int)(h & mask), 0, ch, unused);
     l = a.s[0].w[0] + cl;
-    h = b.s[0].w[0] + ch;
+    h = c.s[0].w[0] + ch;
     return true;
 }
 

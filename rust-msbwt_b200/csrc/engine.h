@@ -80,13 +80,18 @@ void free_quad_image(QuadImage &img);
 struct OctImage {
     uint4 *lines = nullptr;  // 65536 * nbuck8 * 128 B
     uint64_t nbuck8 = 0;
-    uint64_t overflow_lines = 0;  // (code, bucket) lines with more than kOctCapacity occurrences
+    int shift = 0;                      // b: log2 of the bucket size
+    uint64_t runs = 0;                  // code8 runs of the BWT (what chose b)
+    uint64_t overflow_lines = 0;        // (code, bucket) lines with more than kOctCapacity runs
+    uint64_t overflow_occurrences = 0;  // positions whose line overflowed (answered through the quad image)
 };
-uint64_t oct_image_bytes(uint64_t total);
+uint64_t oct_image_bytes(uint64_t total, int shift);
 // `ix` must carry the one-step blocks and the quad image, N < 2^32 with one superblock; `d_codes4` = the
-// quad builder's keep_codes
-int build_oct_image_on_device(int device, const IndexView &ix, const uint16_t *d_codes4, OctImage &img,
-                              std::string &why, int *launches);
+// quad builder's keep_codes, OWNED by this call (freed as soon as the 8-symbol codes exist).
+// `requested_shift` 0 = automatic (layout.h).  When even the coarsest buckets exceed `max_bytes` nothing is
+// built (img.lines stays null) and MSBWT_OK is returned.
+int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes4, int requested_shift,
+                              uint64_t max_bytes, OctImage &img, std::string &why, int *launches);
 void free_oct_image(OctImage &img);
 
 // ---- bwt_build.cu: equal-length reads (device) -> RLE bytes of their multi-string BWT (device) ----

@@ -134,24 +134,38 @@ constexpr int kQuadMaxSuperInSmem = 8;  // rows of 256 u64 staged in shared memo
 //     eight successive constrain_range calls applied to i  ==  C8[c] + #{ j < i : code8(j) == c }.
 //
 // 65536 codes: a bit-vector per code is out of reach, but each code is rare (one position in 65536 on a
-// random text), so the occurrences are stored explicitly.  BWT positions are cut into buckets of 2^20;
-// one 128-byte line per (code, bucket), code-major (`address = (c * nbuck8 + (pos >> 20)) * 128`):
+// random text) and on a read set its occurrences come in RUNS of consecutive BWT positions: the suffixes
+// that share a long prefix -- the reads covering one genome position -- sit next to each other and are
+// preceded by the same eight symbols (mean run 11 on error-free 30x reads, 3 with 1 % errors).  So the
+// occurrences are stored explicitly as runs.  BWT positions are cut into buckets of 2^b (b = the
+// image's bucket shift, chosen when it is built); one 128-byte line per (code, bucket), code-major
+// (`address = (c * nbuck8 + (pos >> b)) * 128`):
 //
 //     word 0      u32 checkpoint: C8[c] + #{ j < bucket start : code8(j) == c }   (N < 2^32 only)
-//     word 1      u32 number of occurrences of c in the bucket
-//     byte 8..127 up to 40 occurrences as 24-bit offsets within the bucket (little-endian, any order);
-//                 unused slots hold 0xFFFFFF, which no offset reaches
+//     word 1      u32 number of runs of c in the bucket
+//     word 2..31  up to 30 runs `(len << b) | offset within the bucket`, any order; unused words are 0
 //
-// rank8(c, p) = word0 + #{ stored offsets < (p & (2^20-1)) }: one line fill, no order needed.  A line
-// expects 16 occurrences; when a bucket holds more than 40 of one code (word 1 > 40: low-complexity
-// text) the kernel falls back to two quad steps for that query-step, so the result is exact on any
-// input.  128 * 65536 * (N / 2^20 + 1) bytes = 8 B/symbol: 12 GB at N = 1.51 G.  Built only next to a
-// quad image (which also serves remainders of 4..7 symbols) and only when N < 2^32.
-constexpr int kOctBucketShift = 20;
+// rank8(c, p) = word0 + sum over runs of clamp((p & (2^b-1)) - offset, 0, len): one line fill, no order
+// needed.  A run never crosses a multiple of 2^cs, cs = oct_chunk_shift(b) <= b, so len <= 2^cs fits its
+// 32-b bits and no run crosses a bucket.  When a bucket holds more than 30 runs of one code (word 1 > 30:
+// low-complexity text) the kernel falls back to two quad steps for that query-step, so the result is
+// exact on any input.  128 * 65536 * (N / 2^b + 1) bytes = 2^(23-b) B/symbol; b is the largest shift that
+// keeps the mean number of runs per line <= kOctTargetRuns (b = 21, 4 B/symbol, on 30x reads with 1 %
+// errors).  Built only next to a quad image (which also serves remainders of 4..7 symbols) and only when
+// N < 2^32.
 constexpr int kOctCodes = 65536;
 constexpr int kOctLineBytes = 128;
 constexpr int kOctLineWords = 32;
-constexpr int kOctCapacity = 40;
+constexpr int kOctCapacity = 30;      // runs per line
+constexpr int kOctMinShift = 8, kOctMaxShift = 23;
+constexpr int kOctAutoMinShift = 16;  // automatic choice: 16..23 (128 B/symbol .. 1 B/symbol)
+constexpr int kOctTargetRuns = 12;
+__host__ __device__ constexpr int oct_chunk_shift(int b) {  // cs = min(31 - b, 10, b)
+    int c = 31 - b;
+    if (c > 10) c = 10;
+    if (c > b) c = b;
+    return c;
+}
 
 struct IndexView {
     const uint4 *blocks;     // nblocks * 4 uint4 (64 B per block)
@@ -167,7 +181,8 @@ struct IndexView {
     const uint64_t *c4base;  // n_super4 * 256 (u64), only when positions are 64-bit
     uint64_t nsec4;          // sectors per quad code: N / 224 + 2
     const uint4 *oct;        // 65536 * nbuck8 lines of 128 B (8 uint4 each), or nullptr
-    uint64_t nbuck8;         // buckets per oct code: (N >> 20) + 1
+    uint64_t nbuck8;         // buckets per oct code: (N >> oct_shift) + 1
+    uint32_t oct_shift;      // b: log2 of the oct bucket size
     uint64_t total;          // N
     uint64_t nblocks;        // (N >> 7) + 1
     uint64_t npair;          // N / 96 + 1

@@ -5,13 +5,18 @@
 // src/rle_bwt.rs:387-467); what the oct image must reproduce is the composition of eight
 // RleBWT::constrain_range calls (src/rle_bwt.rs:202-287); layout.h states the identity.
 //
-//   1. scatter: one thread per BWT position j with a valid quad code a: LF^4(j) = rank4(a, j) through the
-//               quad image (one sector), b = code4(LF^4(j)) (one random read); when b is valid too the
-//               position's 20-bit offset is appended to line (a*256+b, j >> 20): the slot comes from an
-//               atomicAdd on the line's occurrence counter, which keeps counting past the line's capacity.
-//   2. stamp  : one warp per code: exclusive prefix sum of the occurrence counters over the code's
-//               buckets, plus C8[code]; lines holding more than kOctCapacity occurrences are counted
-//               (the kernel answers those through the quad image).
+//   1. code8  : one thread per BWT position j with a valid quad code a: LF^4(j) = rank4(a, j) through the
+//               quad image (one sector), b = code4(LF^4(j)) (one random read); code8(j) = a*256+b when b is
+//               valid too.
+//   2. count  : run heads (code8 changes) are counted; the bucket shift b is the largest one that keeps the
+//               mean number of runs per line <= kOctTargetRuns (and the image within the caller's budget).
+//   3. emit   : every run head (also forced at multiples of 2^cs, layout.h) walks to the end of its run and
+//               appends `(len << b) | offset` to line (code8, j >> b): the slot comes from an atomicAdd on
+//               the line's run counter, which keeps counting past the line's capacity; word 0 gathers the
+//               line's occurrences.
+//   4. stamp  : one warp per code: exclusive prefix sum of the occurrence counts over the code's buckets,
+//               plus C8[code]; lines holding more than kOctCapacity runs are counted (the kernel answers
+//               those through the quad image).
 //   C8[c] = eight constrain_range calls of our own kernel applied to position 0.
 #include <algorithm>
 
@@ -23,31 +28,57 @@ namespace msbwt {
 
 namespace {
 
-__global__ void __launch_bounds__(256) oct_scatter_kernel(IndexView ix, const uint16_t *__restrict__ codes4,
-                                                          uint64_t nbuck8, uint32_t *__restrict__ lines) {
+constexpr uint32_t kValid8 = 0x10000u;
+
+__global__ void __launch_bounds__(256) oct_code8_kernel(IndexView ix, const uint16_t *__restrict__ codes4,
+                                                        uint32_t *__restrict__ codes8) {
     const C4Base<false> c4{};
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < ix.total; j += step) {
         const uint32_t a = codes4[j];
-        if (!(a & 0x100u)) continue;
-        uint32_t l = (uint32_t)j, h = (uint32_t)j;
-        quad_step<false>(ix, c4, a & 255u, l, h);  // l = LF^4(j)
-        const uint32_t b = codes4[l];
-        if (!(b & 0x100u)) continue;
-        const uint32_t code = ((a & 255u) << 8) | (b & 255u);
-        uint32_t *line = lines + ((uint64_t)code * nbuck8 + (j >> kOctBucketShift)) * kOctLineWords;
-        const uint32_t slot = atomicAdd(line + 1, 1u);
-        if (slot < (uint32_t)kOctCapacity) {
-            const uint32_t off = (uint32_t)j & ((1u << kOctBucketShift) - 1u);
-            uint8_t *e = reinterpret_cast<uint8_t *>(line) + 8 + 3 * slot;
-            e[0] = (uint8_t)off;
-            e[1] = (uint8_t)(off >> 8);
-            e[2] = (uint8_t)(off >> 16);
+        uint32_t v = 0;
+        if (a & 0x100u) {
+            uint32_t l = (uint32_t)j, h = (uint32_t)j;
+            quad_step<false>(ix, c4, a & 255u, l, h);  // l = LF^4(j)
+            const uint32_t b = codes4[l];
+            if (b & 0x100u) v = kValid8 | ((a & 255u) << 8) | (b & 255u);
         }
+        codes8[j] = v;
     }
 }
 
-// one warp per code: checkpoints of its buckets
+__global__ void __launch_bounds__(256) oct_count_runs_kernel(const uint32_t *__restrict__ codes8, uint64_t total,
+                                                             unsigned long long *__restrict__ runs) {
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t mine = 0;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += step) {
+        const uint32_t v = codes8[j];
+        mine += (v & kValid8) && (j == 0 || codes8[j - 1] != v);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(runs, (unsigned long long)mine);
+}
+
+__global__ void __launch_bounds__(256) oct_emit_kernel(const uint32_t *__restrict__ codes8, uint64_t total,
+                                                       uint32_t shift, uint64_t nbuck8, uint32_t *__restrict__ lines) {
+    const uint64_t chunk_mask = (1ull << oct_chunk_shift((int)shift)) - 1ull;
+    const uint32_t off_mask = (1u << shift) - 1u;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += step) {
+        const uint32_t v = codes8[j];
+        if (!(v & kValid8)) continue;
+        if (!((j & chunk_mask) == 0 || codes8[j - 1] != v)) continue;
+        uint32_t len = 1;
+        while (j + len < total && ((j + len) & chunk_mask) != 0 && codes8[j + len] == v) len++;
+        uint32_t *line = lines + ((uint64_t)(v & 0xFFFFu) * nbuck8 + (j >> shift)) * kOctLineWords;
+        atomicAdd(line, len);
+        const uint32_t slot = atomicAdd(line + 1, 1u);
+        if (slot < (uint32_t)kOctCapacity) line[2 + slot] = (len << shift) | ((uint32_t)j & off_mask);
+    }
+}
+
+// one warp per code: occurrence counts of its buckets (word 0) -> checkpoints
 __global__ void __launch_bounds__(256) oct_stamp_kernel(const uint64_t *__restrict__ c8, uint64_t nbuck8,
                                                         uint32_t *__restrict__ lines, unsigned long long *__restrict__ overflow) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -55,11 +86,11 @@ __global__ void __launch_bounds__(256) oct_stamp_kernel(const uint64_t *__restri
     if (code >= (uint32_t)kOctCodes) return;
     uint32_t *base = lines + (uint64_t)code * nbuck8 * kOctLineWords;
     uint32_t run = (uint32_t)c8[code];
-    uint32_t over = 0;
+    uint32_t over = 0, over_occ = 0;
     for (uint64_t b0 = 0; b0 < nbuck8; b0 += 32) {
         const uint64_t b = b0 + lane;
-        const uint32_t cnt = b < nbuck8 ? base[b * kOctLineWords + 1] : 0u;
-        over += cnt > (uint32_t)kOctCapacity;
+        const uint32_t cnt = b < nbuck8 ? base[b * kOctLineWords] : 0u;
+        if (b < nbuck8 && base[b * kOctLineWords + 1] > (uint32_t)kOctCapacity) { over++; over_occ += cnt; }
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -70,8 +101,14 @@ __global__ void __launch_bounds__(256) oct_stamp_kernel(const uint64_t *__restri
         run += __shfl_sync(0xffffffffu, incl, 31);
     }
 #pragma unroll
-    for (int d = 16; d; d >>= 1) over += __shfl_xor_sync(0xffffffffu, over, d);
-    if (lane == 0 && over) atomicAdd(overflow, (unsigned long long)over);
+    for (int d = 16; d; d >>= 1) {
+        over += __shfl_xor_sync(0xffffffffu, over, d);
+        over_occ += __shfl_xor_sync(0xffffffffu, over_occ, d);
+    }
+    if (lane == 0 && over) {
+        atomicAdd(overflow, (unsigned long long)over);
+        atomicAdd(overflow + 1, (unsigned long long)over_occ);
+    }
 }
 
 struct Scratch {
@@ -95,31 +132,62 @@ struct Scratch {
 
 }  // namespace
 
-uint64_t oct_image_bytes(uint64_t total) {
-    return (uint64_t)kOctCodes * ((total >> kOctBucketShift) + 1) * kOctLineBytes;
+uint64_t oct_image_bytes(uint64_t total, int shift) {
+    return (uint64_t)kOctCodes * ((total >> shift) + 1) * kOctLineBytes;
 }
 
-int build_oct_image_on_device(int device, const IndexView &ix, const uint16_t *d_codes4, OctImage &img,
-                              std::string &why, int *launches) {
+int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes4, int requested_shift,
+                              uint64_t max_bytes, OctImage &img, std::string &why, int *launches) {
+    struct Owned { uint16_t *p; ~Owned() { if (p) cudaFree(p); } } codes4{d_codes4};
     if (!ix.quad || !d_codes4) { why = "oct image: needs the quad image and its codes"; return MSBWT_EINVAL; }
     if (index_is_wide(ix)) { why = "oct image: only for indexes with 32-bit positions (N < 2^32, one superblock)"; return MSBWT_EINVAL; }
-    const uint64_t nbuck8 = (ix.total >> kOctBucketShift) + 1;
-    const uint64_t nlines = (uint64_t)kOctCodes * nbuck8;
-    img.nbuck8 = nbuck8;
+    if (requested_shift && (requested_shift < kOctMinShift || requested_shift > kOctMaxShift)) {
+        why = "oct image: bucket shift out of range"; return MSBWT_EINVAL;
+    }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((ix.total + 255) / 256, (uint64_t)sms * 32));
 
     Scratch tmp;
+    uint32_t *d_codes8 = nullptr;
     uint8_t *d_sym = nullptr;
     uint64_t *d_pos = nullptr;
-    unsigned long long *d_over = nullptr;
+    unsigned long long *d_stat = nullptr;  // [0] runs, [1] overflowed lines, [2] their occurrences
+    O_TRY(tmp.alloc(&d_codes8, ix.total));
+    O_TRY(tmp.alloc(&d_stat, 3));
+    O_TRY(cudaMemsetAsync(d_stat, 0, 3 * sizeof(unsigned long long)));
+
+    // 1. code8 per position, 2. run heads
+    oct_code8_kernel<<<grid, 256>>>(ix, d_codes4, d_codes8);
+    O_TRY(cudaGetLastError());
+    oct_count_runs_kernel<<<grid, 256>>>(d_codes8, ix.total, d_stat);
+    O_TRY(cudaGetLastError());
+    if (launches) (*launches) += 2;
+    unsigned long long runs = 0;
+    O_TRY(cudaMemcpy(&runs, d_stat, sizeof(runs), cudaMemcpyDeviceToHost));
+    cudaFree(codes4.p);
+    codes4.p = nullptr;
+    img.runs = runs;
+
+    int shift = requested_shift;
+    if (!shift) {  // mean runs per line = runs * 2^shift / (65536 * N)
+        shift = kOctMaxShift;
+        while (shift > kOctAutoMinShift &&
+               (long double)runs * (long double)(1ull << shift) >
+                   (long double)kOctTargetRuns * (long double)kOctCodes * (long double)std::max<uint64_t>(ix.total, 1))
+            shift--;
+        while (shift < kOctMaxShift && oct_image_bytes(ix.total, shift) > max_bytes) shift++;
+    }
+    if (oct_image_bytes(ix.total, shift) > max_bytes) return MSBWT_OK;  // no room: img.lines stays null, the quad image serves alone
+    const uint64_t nbuck8 = (ix.total >> shift) + 1;
+    const uint64_t nlines = (uint64_t)kOctCodes * nbuck8;
+    img.nbuck8 = nbuck8;
+    img.shift = shift;
+
     O_TRY(cudaMalloc((void **)&img.lines, nlines * kOctLineBytes));
-    O_TRY(cudaMemsetAsync(img.lines, 0xFF, nlines * kOctLineBytes));           // empty slots: 0xFFFFFF
-    O_TRY(cudaMemset2DAsync(img.lines, kOctLineBytes, 0, 8, nlines));          // checkpoint + counter
+    O_TRY(cudaMemsetAsync(img.lines, 0, nlines * kOctLineBytes));
     O_TRY(tmp.alloc(&d_sym, kOctCodes));
     O_TRY(tmp.alloc(&d_pos, 3 * (size_t)kOctCodes));
-    O_TRY(tmp.alloc(&d_over, 1));
-    O_TRY(cudaMemsetAsync(d_over, 0, sizeof(unsigned long long)));
 
     // C8[c]: the eight steps applied to position 0
     static const uint8_t acgt[4] = {1, 2, 3, 5};
@@ -133,20 +201,20 @@ int build_oct_image_on_device(int device, const IndexView &ix, const uint16_t *d
         std::swap(cur, nxt);
     }
 
-    // 1. scatter
+    // 3. emit
     if (ix.total) {
-        const unsigned grid = (unsigned)std::min<uint64_t>((ix.total + 255) / 256, (uint64_t)sms * 32);
-        oct_scatter_kernel<<<grid, 256>>>(ix, d_codes4, nbuck8, reinterpret_cast<uint32_t *>(img.lines));
+        oct_emit_kernel<<<grid, 256>>>(d_codes8, ix.total, (uint32_t)shift, nbuck8, reinterpret_cast<uint32_t *>(img.lines));
         O_TRY(cudaGetLastError());
         if (launches) (*launches)++;
     }
-    // 2. stamp
-    oct_stamp_kernel<<<kOctCodes / 8, 256>>>(cur, nbuck8, reinterpret_cast<uint32_t *>(img.lines), d_over);
+    // 4. stamp
+    oct_stamp_kernel<<<kOctCodes / 8, 256>>>(cur, nbuck8, reinterpret_cast<uint32_t *>(img.lines), d_stat + 1);
     O_TRY(cudaGetLastError());
     if (launches) (*launches)++;
-    unsigned long long over = 0;
-    O_TRY(cudaMemcpy(&over, d_over, sizeof(over), cudaMemcpyDeviceToHost));
-    img.overflow_lines = over;
+    unsigned long long over[2] = {0, 0};
+    O_TRY(cudaMemcpy(over, d_stat + 1, sizeof(over), cudaMemcpyDeviceToHost));
+    img.overflow_lines = over[0];
+    img.overflow_occurrences = over[1];
     O_TRY(cudaDeviceSynchronize());
     return MSBWT_OK;
 }

@@ -73,7 +73,8 @@ class BWTRange:
 class Options(C.Structure):
     """`msbwt_options` (include/msbwt_gpu.h)."""
     _fields_ = [("struct_size", C.c_uint32), ("superblock_shift", C.c_uint32), ("suffix_table_s", C.c_int32),
-                ("pair_index", C.c_int32), ("kernel_lanes", C.c_int32), ("quad_index", C.c_int32), ("oct_index", C.c_int32)]
+                ("pair_index", C.c_int32), ("kernel_lanes", C.c_int32), ("quad_index", C.c_int32), ("oct_index", C.c_int32),
+                ("oct_bucket_shift", C.c_int32)]
 
 
 _lib = None
@@ -118,6 +119,9 @@ def load_library():
         "msbwt_quad_index": (i32, [vp]),
         "msbwt_oct_index": (i32, [vp]),
         "msbwt_oct_overflow_lines": (u64, [vp]),
+        "msbwt_oct_overflow_occurrences": (u64, [vp]),
+        "msbwt_oct_runs": (u64, [vp]),
+        "msbwt_oct_bucket_shift": (i32, [vp]),
         "msbwt_debug_copy_oct_image": (i32, [vp, i32, C.POINTER(u64), vp]),
         "msbwt_debug_copy_quad_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp]),
         "msbwt_last_transfer_bytes": (None, [C.POINTER(u64), C.POINTER(u64)]),
@@ -148,6 +152,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
     "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_oct_index", "msbwt_oct_overflow_lines",
+    "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift",
     "msbwt_debug_copy_oct_image", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
     "msbwt_debug_host_pack",
     "msbwt_index_destroy", "msbwt_total_size", "msbwt_symbol_count", "msbwt_start_index",
@@ -187,7 +192,7 @@ class RleBWT:
 
     def __init__(self, bin_power: int = 8, devices: list[int] | None = None, superblock_shift: int = 0,
                  suffix_table_s: int = -1, pair_index: int = -1, kernel_lanes: int = 0, quad_index: int = -1,
-                 oct_index: int = -1):
+                 oct_index: int = -1, oct_bucket_shift: int = 0):
         # bin_power is accepted for signature parity (src/rle_bwt.rs:309-322); it never
         # changed results in the reference and has no counterpart in the device layout.
         self.bin_power = bin_power
@@ -198,6 +203,7 @@ class RleBWT:
         self._lanes = kernel_lanes      # 0 auto, 1, 2
         self._quad = quad_index         # -1 auto, 0 never, 1 always: the 32-byte quad sectors (four steps per sector)
         self._oct = oct_index           # -1 auto, 0 never, 1 always: the 128-byte oct lines (eight steps per line)
+        self._oct_shift = oct_bucket_shift  # 0 auto, else log2 of the oct bucket size (8..23)
         self._h = None
 
     @classmethod
@@ -239,7 +245,8 @@ class RleBWT:
         a = _u8(bwt)
         err = C.c_int(0)
         devs, nd = self._dev_args()
-        opts = Options(C.sizeof(Options), self._sb_shift, self._table_s, self._pair, self._lanes, self._quad, self._oct)
+        opts = Options(C.sizeof(Options), self._sb_shift, self._table_s, self._pair, self._lanes, self._quad, self._oct,
+                       self._oct_shift)
         h = L.msbwt_index_create_opts(_p(a), a.size, devs, nd, C.byref(opts), C.byref(err))
         if not h:
             _check(err.value or ECUDA, "load_vector")
@@ -386,6 +393,18 @@ class RleBWT:
     @property
     def oct_overflow_lines(self) -> int:
         return int(load_library().msbwt_oct_overflow_lines(self.handle))
+
+    @property
+    def oct_overflow_occurrences(self) -> int:
+        return int(load_library().msbwt_oct_overflow_occurrences(self.handle))
+
+    @property
+    def oct_runs(self) -> int:
+        return int(load_library().msbwt_oct_runs(self.handle))
+
+    @property
+    def oct_bucket_shift(self) -> int:
+        return int(load_library().msbwt_oct_bucket_shift(self.handle))
 
     @property
     def quad_index(self) -> bool:
