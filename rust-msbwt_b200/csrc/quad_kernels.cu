@@ -109,28 +109,28 @@ count_kmers_quad_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packe
 // image (layout.h) instead of two quad sectors; the quad image serves remainders of 4..7 symbols, ranges
 // that straddle two oct buckets and the lines that overflowed (two quad steps instead of one oct step).
 //
-// Mapping: a QUAD OF LANES per query, each lane loading one 32-byte sector of the line, so that the line
-// is ONE 128-byte request to L2.  What HBM random access is bound by is the number of requests that miss
-// (about 40 G/s whatever their size, profiles/r1_gather_*.json): a thread that reads its line with four
-// 256-bit loads pays four of them per line and ran at a quarter of the line rate
-// (profiles/r1_o2_oct_cfg3_ncu_summary.txt).
+// What HBM random access is bound by is the number of L2 requests that miss -- about 40 G/s whatever their
+// size (profiles/r1_gather_*.json) -- and what reaches that bound is the number of them in flight.  So:
 //
-// Every iteration of the persistent loop is split into ISSUE and CONSUME.  ISSUE is branch-free: whatever
-// the query's next step is (oct line, quad sectors, nothing) it is the same predicated 256-bit load, so a
-// warp whose eight queries need different kinds of step still has all its index requests in flight at once
-// and pays one memory round trip per iteration; CONSUME diverges by kind, without memory accesses.
+//  * one thread per query (1024 queries in flight per SM), but the index lines are fetched by the WARP:
+//    every lane publishes the address of the line (or the two quad sectors) its query needs next, and in
+//    eight rounds the warp copies the 32 lines into shared memory with cp.async, eight lanes x 16 bytes per
+//    line, i.e. ONE 128-byte request per line and no load registers.  (A thread that read its own line with
+//    four 256-bit loads paid four requests per line and ran at a quarter of the line rate; a quad of lanes
+//    per query kept only 384 queries per SM in flight: profiles/r1_o2_*, r1_o6_* summaries.)
+//  * every iteration is ISSUE (branch-free, whatever kind of step each lane needs), one wait, CONSUME (each
+//    lane ranks in its own staged line; divergent, but without memory accesses): one memory round trip per
+//    iteration even when the lanes of a warp need different kinds of step -- one lane in fourteen lands on
+//    an overflowed line on 30x reads with 1 % errors.
+//  * every warp owns one contiguous slice of the live list and stages it through shared memory 32 queries
+//    at a time, double-buffered (coalesced cp.async one pool ahead); lanes that finished take the next
+//    queries of the pool in lane order, so the warp stays full whatever the mix of early exits.
 #ifndef MSBWT_OCT_CTAS
-#define MSBWT_OCT_CTAS 6
+#define MSBWT_OCT_CTAS 4
 #endif
-
-// Query staging: every quad of lanes keeps the next kOctGroup queries of its slice (symbol word, seed
-// range, original index) in its own 336 bytes of shared memory, filled with cp.async one group ahead: three
-// full-line requests per 16 queries.  (A quad that read its next query with three 8-byte loads paid three
-// L2 misses per query once the quads of a warp had drifted apart -- more than the two index lines the
-// query itself needs: 42.6 GB of DRAM reads per 100 M queries against 25.6 GB of index lines,
-// profiles/r1_o5_oct_cfg3_ncu_summary.txt.)
-constexpr int kOctGroup = 16;
-constexpr int kOctStageWords = 84;  // 16 u64 + 16 u64 + 16 u32 = 80 words, padded: 16-byte multiple, bank-conflict-free
+constexpr int kOctRowBytes = 144;    // a 128-byte line + 16: rows of consecutive lanes start 4 banks apart (conflict-free LDS.128)
+constexpr int kOctPoolBytes = 640;   // 32 x (u64 symbol word, u64 seed range, u32 original index)
+constexpr int kOctWarpSmem = 32 * kOctRowBytes + 2 * kOctPoolBytes;  // 5888 bytes per warp, 47104 per CTA
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool on) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
@@ -140,14 +140,9 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool on)
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gmem), "r"(on ? 8u : 0u) : "memory");
 }
-
-// 32 bytes at p into v when `on` (v is left undefined otherwise); same cache policy as ldg_index256
-__device__ __forceinline__ void ldg_index256_if(Half &v, const void *p, uint32_t on) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
-        "@p ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
-        : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
-        : "l"(p), "r"(on));
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem, bool on) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(gmem), "r"(on ? 4u : 0u) : "memory");
 }
 
 // the rare one-symbol remainder step, out of line and by value so that neither its 32 load registers nor a
@@ -158,37 +153,75 @@ __device__ __noinline__ uint2 oct_remainder_step(const IndexView &ix, const uint
     return make_uint2(l, h);
 }
 
+// occurrences below bucket offsets pl / ph contributed by one stored run `(len << b) | off` (0 = empty slot)
+__device__ __forceinline__ void oct_add_run(uint32_t e, uint32_t b, uint32_t mask, int pl, int ph, int &sl, int &sh) {
+    const int off = (int)(e & mask), len = (int)(e >> b);
+    sl += min(max(pl - off, 0), len);
+    sh += min(max(ph - off, 0), len);
+}
+__device__ __forceinline__ void oct_add_runs(const uint4 &v, uint32_t b, uint32_t mask, int pl, int ph, int &sl, int &sh) {
+    oct_add_run(v.x, b, mask, pl, ph, sl, sh);
+    oct_add_run(v.y, b, mask, pl, ph, sl, sh);
+    oct_add_run(v.z, b, mask, pl, ph, sl, sh);
+    oct_add_run(v.w, b, mask, pl, ph, sl, sh);
+}
+// a staged quad sector {checkpoint, 224 occurrence bits}: checkpoint + set bits at offsets < p
+__device__ __forceinline__ uint32_t staged_sector_rank(const uint4 &a, const uint4 &b, int p) {
+    return a.x + __popc(a.y & below_mask(p)) + __popc(a.z & below_mask(p - 32)) + __popc(a.w & below_mask(p - 64)) +
+           __popc(b.x & below_mask(p - 96)) + __popc(b.y & below_mask(p - 128)) + __popc(b.z & below_mask(p - 160)) +
+           __popc(b.w & below_mask(p - 192));
+}
+
 // TAIL: the batch ends with 1..3 one-symbol steps (k below the kept table levels); the out-of-line call is
-// compiled only into that instantiation, so the common one keeps all its state in registers.
+// compiled only into that instantiation.
 template <bool TAIL>
 __global__ void __launch_bounds__(kCountThreads, MSBWT_OCT_CTAS)
 count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, PackedLayout lay, uint32_t k,
                        uint64_t *__restrict__ out) {
+    __shared__ __align__(16) uint8_t smem[(kCountThreads / 32) * kOctWarpSmem];
     __shared__ uint64_t cb_smem[4];
-    __shared__ __align__(16) uint32_t stage[(kCountThreads / 4) * kOctStageWords];
     [[maybe_unused]] CBase<false> cb{nullptr};
     if constexpr (TAIL) cb = stage_cbase<false>(ix, cb_smem);
     const uint64_t stream = policy_evict_first();
+    constexpr uint32_t kFull = 0xffffffffu;
 
     const uint32_t n = (uint32_t)packed[lay.live()];  // live queries of list A
-    const uint32_t tid = blockIdx.x * kCountThreads + threadIdx.x;
-    const uint32_t t = tid & 3u;                         // this lane's sector of the line
-    const uint32_t qmask = 0xFu << (threadIdx.x & 28u);  // the lanes of this query
-    // every quad of lanes owns one CONTIGUOUS slice of the live list (a multiple of kOctGroup queries)
-    const uint32_t nquads = gridDim.x * (kCountThreads / 4);
-    const uint32_t per = ((n + nquads - 1) / nquads + (uint32_t)kOctGroup - 1u) & ~((uint32_t)kOctGroup - 1u);
-    const uint64_t start64 = (uint64_t)(tid >> 2) * per;
+    const uint32_t lane = threadIdx.x & 31u;
+    // every warp owns one CONTIGUOUS slice of the live list (a multiple of 32 queries)
+    const uint32_t nwarps = gridDim.x * (kCountThreads / 32);
+    const uint32_t per = ((n + nwarps - 1) / nwarps + 31u) & ~31u;
+    const uint64_t start64 = (uint64_t)(blockIdx.x * (kCountThreads / 32) + (threadIdx.x >> 5)) * per;
     if (start64 >= n) return;
-    uint32_t i = (uint32_t)start64;
+    const uint32_t start = (uint32_t)start64;
     const uint32_t end = (uint32_t)(start64 + per < n ? start64 + per : n);
     const uint64_t *w0 = packed + lay.w0(), *seeds = packed + lay.seed(), *wx = packed + lay.wx();
     const uint32_t *qidx = reinterpret_cast<const uint32_t *>(packed + lay.qidx());
     const uint32_t rem0 = k - acgt_table_depth(k, ix.table_s, 4u);
     const uint32_t bshift = ix.oct_shift, bmask = (1u << bshift) - 1u;
-    const char *const oct_base = reinterpret_cast<const char *>(ix.oct) + 32u * t;
+    const char *const oct_base = reinterpret_cast<const char *>(ix.oct);
     const char *const quad_base = reinterpret_cast<const char *>(ix.quad);
-    uint32_t *const my = stage + (threadIdx.x >> 2) * kOctStageWords;  // w0[16] | seed[16] | qidx[16]
+    uint8_t *const rows = smem + (threadIdx.x >> 5) * kOctWarpSmem;  // 32 rows of kOctRowBytes
+    uint8_t *const pools = rows + 32 * kOctRowBytes;                  // 2 pools: w0[32] | seed[32] | qidx[32]
+    const uint4 *const my_row = reinterpret_cast<const uint4 *>(rows + lane * kOctRowBytes);
 
+    // pool b holds the queries [base, base + 32) with ((base - start) >> 5) & 1 == b
+    auto load_pool = [&](uint32_t base) {
+        uint8_t *p = pools + (((base - start) >> 5) & 1u) * kOctPoolBytes;
+        const uint32_t idx = base + lane;
+        const bool on = idx < end;
+        cp_async8(p + 8u * lane, w0 + idx, on);
+        cp_async8(p + 256u + 8u * lane, seeds + idx, on);
+        cp_async4(p + 512u + 4u * lane, qidx + idx, on);
+    };
+    load_pool(start);
+    load_pool(start + 32u);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+
+    uint32_t next_i = start;     // first query of the slice nobody has taken (warp-uniform)
+    uint32_t pool_base = start;  // the two pools hold [pool_base, pool_base + 64)
+    bool active = false;
     uint32_t l = 0, h = 0;
     uint64_t word = 0, pend = 0;
     uint32_t q = 0;
@@ -197,115 +230,132 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     uint32_t widx = 0;
     uint32_t forced = 0;  // quad steps to take before the next oct step (after an overflowed line)
 
-    // the next kOctGroup queries of the slice, global -> this quad's staging area (i0: a multiple of kOctGroup)
-    auto fetch_group = [&](uint32_t i0) {
-#pragma unroll
-        for (uint32_t c = t; c < 8u; c += 4u) cp_async16(my + 4u * c, w0 + i0 + 2u * c, i0 + 2u * c < end);
-#pragma unroll
-        for (uint32_t c = t; c < 16u; c += 4u) cp_async8(my + 32u + 2u * c, seeds + i0 + c, i0 + c < end);
-        cp_async16(my + 64u + 4u * t, qidx + i0 + 4u * t, i0 + 4u * t < end);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto begin = [&]() {
-        const uint32_t j = i & ((uint32_t)kOctGroup - 1u);
-        if (j == 0) {
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncwarp(qmask);
-        }
-        word = *reinterpret_cast<const volatile uint64_t *>(my + 2u * j);
-        const uint64_t lo = *reinterpret_cast<const volatile uint64_t *>(my + 32u + 2u * j);
-        q = *reinterpret_cast<const volatile uint32_t *>(my + 64u + j) & kQidxMask;
-        l = (uint32_t)lo;
-        h = (uint32_t)(lo >> 32);
-        rem = rem0;
-        shift = 62;
-        widx = 0;
-        forced = 0;
-        if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + q, stream);
-        if (j == (uint32_t)kOctGroup - 1u && i + 1u < end) {  // the group is used up: stage the next one under this query's steps
-            __syncwarp(qmask);
-            fetch_group(i + 1u);
-        }
-    };
-
-    fetch_group(i);
-    begin();
-
     for (;;) {
-        while (rem == 0 || l == h) {
-            if (t == 0) stg_stream(out + q, (uint64_t)(h - l), stream);
-            if (++i >= end) return;
-            begin();
+        // ---- RETIRE + REFILL (warp-uniform control)
+        if (active && (rem == 0 || l == h)) {
+            stg_stream(out + q, (uint64_t)(h - l), stream);
+            active = false;
         }
-        if (shift < 0) {  // 32 symbols per word; steps of 8 and 4 symbols never straddle two words
+        const uint32_t want = __ballot_sync(kFull, !active);
+        if (want) {
+            if (next_i < end) {
+                const uint32_t gi = next_i + __popc(want & ((1u << lane) - 1u));
+                if (!active && gi < end) {
+                    const uint8_t *p = pools + (((gi - start) >> 5) & 1u) * kOctPoolBytes;
+                    const uint32_t slot = (gi - start) & 31u;
+                    word = *reinterpret_cast<const volatile uint64_t *>(p + 8u * slot);
+                    const uint64_t lo = *reinterpret_cast<const volatile uint64_t *>(p + 256u + 8u * slot);
+                    q = *reinterpret_cast<const volatile uint32_t *>(p + 512u + 4u * slot) & kQidxMask;
+                    l = (uint32_t)lo;
+                    h = (uint32_t)(lo >> 32);
+                    rem = rem0;
+                    shift = 62;
+                    widx = 0;
+                    forced = 0;
+                    active = true;
+                    if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + q, stream);
+                }
+                const uint32_t taken = min((uint32_t)__popc(want), end - next_i);
+                next_i += taken;
+                if (next_i >= pool_base + 32u) {  // the older pool is used up: stage the one after the newer into its place
+                    __syncwarp();
+                    pool_base += 32u;
+                    load_pool(pool_base + 32u);  // (committed with this iteration's lines)
+                }
+            } else if (want == kFull) {
+                return;  // slice finished
+            }
+        }
+        if (active && shift < 0) {  // 32 symbols per word; steps of 8 and 4 symbols never straddle two words
             word = pend;
             widx++;
             shift = 62;
             if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + (uint64_t)widx * lay.n + q, stream);
         }
 
-        // ---- ISSUE (branch-free): lane t reads sector t of the oct line; lanes 0 / 1 the quad sectors of l / h
+        // ---- ISSUE (branch-free): every lane publishes what its query needs, the warp fetches it
         // (a range over two buckets takes the eight symbols as two quad steps as well: oct steps stay aligned
         // to multiples of eight symbols and never straddle two words)
+        const bool live = active && rem != 0 && l != h;
         const uint32_t bl = l >> bshift, bh = h >> bshift;
-        const bool want_oct = rem >= 8u && forced == 0u;
+        const bool want_oct = live && rem >= 8u && forced == 0u;
         const bool is_oct = want_oct && bl == bh;
-        const bool is_quad = !is_oct && rem >= 4u;
+        const bool is_quad = live && !is_oct && rem >= 4u;
         if (want_oct && !is_oct) forced = 2;
         const uint32_t code16 = (uint32_t)(word >> (shift >= 14 ? shift - 14 : 0)) & 0xFFFFu;
-        const uint32_t code8 = (uint32_t)(word >> (shift - 6)) & 255u;
-        const uint32_t mine = t == 0 ? l : h;  // the boundary this lane ranks in a quad step
-        const uint32_t sec = mine / (uint32_t)kQuadSyms;
-        const char *p = is_oct ? oct_base + ((size_t)code16 * ix.nbuck8 + bl) * kOctLineBytes
-                               : quad_base + ((size_t)code8 * ix.nsec4 + sec) * kQuadSectorBytes;
-        Half v;
-        ldg_index256_if(v, p, is_oct || (is_quad && t < 2u));
-
-        // ---- CONSUME
-        uint32_t x = 0;  // oct: this sector's occurrences below l (low half) and below h (high half); quad: the new boundary
-        if (is_oct) {
-            const int pl = (int)(l & bmask), ph = (int)(h & bmask);
-            int sl = 0, sh = 0;
+        const uint32_t code8 = (uint32_t)(word >> (shift >= 6 ? shift - 6 : 0)) & 255u;
+        const uint32_t sl = l / (uint32_t)kQuadSyms, sh = h / (uint32_t)kQuadSyms;
+        const char *p0 = is_oct ? oct_base + ((size_t)code16 * ix.nbuck8 + bl) * kOctLineBytes
+                                : quad_base + ((size_t)code8 * ix.nsec4 + sl) * kQuadSectorBytes;
+        // low two bits: kind (1 oct, 2 quad, 0 nothing); the rest: byte distance from the sector of l to the sector of h
+        const uint32_t meta = is_oct ? 1u : (is_quad ? (2u | ((sh - sl) * (uint32_t)kQuadSectorBytes)) : 0u);
+        const uint32_t p0_lo = (uint32_t)(uintptr_t)p0, p0_hi = (uint32_t)((uintptr_t)p0 >> 32);
+        {
+            const uint32_t j = lane & 7u;  // this lane's 16 bytes of a line
 #pragma unroll
-            for (int w = 0; w < 8; w++) {
-                const uint32_t e = (w < 2 && t == 0) ? 0u : v.w[w];  // words 0, 1 of the line are not runs
-                const int off = (int)(e & bmask), len = (int)(e >> bshift);
-                sl += min(max(pl - off, 0), len);
-                sh += min(max(ph - off, 0), len);
+            for (uint32_t c = 0; c < 8u; c++) {
+                const uint32_t o = 4u * c + (lane >> 3);  // the lane whose line this is
+                const uint32_t m = __shfl_sync(kFull, meta, o);
+                const uint64_t a = ((uint64_t)__shfl_sync(kFull, p0_hi, o) << 32) | __shfl_sync(kFull, p0_lo, o);
+                // oct: bytes 16j.. of the line; quad: the sector of l into bytes 0..31, the sector of h into 32..63
+                const uint64_t src = a + 16u * j + (((m & 3u) == 2u && j >= 2u) ? (uint64_t)(m & ~31u) - 32u : 0u);
+                cp_async16(rows + o * kOctRowBytes + 16u * j, reinterpret_cast<const void *>(src),
+                           (m & 3u) == 1u || ((m & 3u) == 2u && j < 4u));
             }
-            x = (uint32_t)sl | ((uint32_t)sh << 16);  // a line holds <= 30 runs of <= 1024 positions
-        } else if (is_quad) {
-            x = v.w[0] + sector_count_below(v, (int)(mine - sec * (uint32_t)kQuadSyms));
         }
-        const uint32_t x0 = __shfl_sync(qmask, x, 0, 4), x1 = __shfl_sync(qmask, x, 1, 4);
-        const uint32_t ckpt = __shfl_sync(qmask, v.w[0], 0, 4), nruns = __shfl_sync(qmask, v.w[1], 0, 4);
-        uint32_t sum = x + __shfl_xor_sync(qmask, x, 1, 4);
-        sum += __shfl_xor_sync(qmask, sum, 2, 4);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+
+        // ---- CONSUME (each lane ranks in its own staged line)
         if (is_oct) {
-            if (nruns > (uint32_t)kOctCapacity) {
+            const uint4 a = my_row[0], b = my_row[1];
+            if (a.y > (uint32_t)kOctCapacity) {
                 forced = 2;  // this line cannot hold its runs: the same eight symbols as two quad steps
             } else {
-                l = ckpt + (sum & 0xFFFFu);
-                h = ckpt + (sum >> 16);
+                const int pl = (int)(l & bmask), ph = (int)(h & bmask);
+                int cl = 0, ch = 0;
+                oct_add_run(a.z, bshift, bmask, pl, ph, cl, ch);
+                oct_add_run(a.w, bshift, bmask, pl, ph, cl, ch);
+                oct_add_runs(b, bshift, bmask, pl, ph, cl, ch);
+                if (a.y > 6u) {
+                    oct_add_runs(my_row[2], bshift, bmask, pl, ph, cl, ch);
+                    oct_add_runs(my_row[3], bshift, bmask, pl, ph, cl, ch);
+                    if (a.y > 14u) {
+                        oct_add_runs(my_row[4], bshift, bmask, pl, ph, cl, ch);
+                        oct_add_runs(my_row[5], bshift, bmask, pl, ph, cl, ch);
+                        if (a.y > 22u) {
+                            oct_add_runs(my_row[6], bshift, bmask, pl, ph, cl, ch);
+                            oct_add_runs(my_row[7], bshift, bmask, pl, ph, cl, ch);
+                        }
+                    }
+                }
+                l = a.x + (uint32_t)cl;
+                h = a.x + (uint32_t)ch;
                 rem -= 8;
                 shift -= 16;
             }
         } else if (is_quad) {
-            l = x0;
-            h = x1;
+            const uint32_t nl = staged_sector_rank(my_row[0], my_row[1], (int)(l - sl * (uint32_t)kQuadSyms));
+            const uint32_t nh = staged_sector_rank(my_row[2], my_row[3], (int)(h - sh * (uint32_t)kQuadSyms));
+            l = nl;
+            h = nh;
             rem -= 4;
             shift -= 8;
             forced = forced ? forced - 1u : 0u;
-        } else if constexpr (TAIL) {
-            const uint32_t sym = (0x5321u >> (4u * ((uint32_t)(word >> shift) & 3u))) & 7u;  // A,C,G,T = 1,2,3,5
-            const uint2 r = oct_remainder_step(ix, cb.c, sym, l, h);
-            l = r.x;
-            h = r.y;
-            rem--;
-            shift -= 2;
-        } else {
-            rem = 0;  // unreachable: the launcher picks TAIL whenever the remainder is not a multiple of four
+        } else if (live) {
+            if constexpr (TAIL) {
+                const uint32_t sym = (0x5321u >> (4u * ((uint32_t)(word >> shift) & 3u))) & 7u;  // A,C,G,T = 1,2,3,5
+                const uint2 r = oct_remainder_step(ix, cb.c, sym, l, h);
+                l = r.x;
+                h = r.y;
+                rem--;
+                shift -= 2;
+            } else {
+                rem = 0;  // unreachable: the launcher picks TAIL whenever the remainder is not a multiple of four
+            }
         }
+        __syncwarp();  // the rows are rewritten by the next ISSUE
     }
 }
 
@@ -322,11 +372,17 @@ cudaError_t launch_count_quad(int device, const IndexView &ix, const uint64_t *d
                               uint32_t k, uint64_t *d_out, cudaStream_t st) {
     if (index_is_wide(ix)) return launch_count_quad_t<true>(device, ix, d_packed, lay, k, d_out, st);
     if (ix.oct) {
+        static bool carveout_set = false;  // 4 CTAs x 47 KB of staging per SM need the large shared-memory configuration
+        if (!carveout_set) {
+            cudaFuncSetAttribute((const void *)count_kmers_oct_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute((const void *)count_kmers_oct_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carveout_set = true;
+        }
         if ((k - acgt_table_depth(k, ix.table_s, 4u)) % 4u) {
-            const unsigned grid = persistent_grid(device, (const void *)count_kmers_oct_kernel<true>, kCountThreads, lay.n, kCountThreads / 4);
+            const unsigned grid = persistent_grid(device, (const void *)count_kmers_oct_kernel<true>, kCountThreads, lay.n, kCountThreads);
             count_kmers_oct_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out);
         } else {
-            const unsigned grid = persistent_grid(device, (const void *)count_kmers_oct_kernel<false>, kCountThreads, lay.n, kCountThreads / 4);
+            const unsigned grid = persistent_grid(device, (const void *)count_kmers_oct_kernel<false>, kCountThreads, lay.n, kCountThreads);
             count_kmers_oct_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out);
         }
         return cudaGetLastError();

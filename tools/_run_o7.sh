@@ -1,11 +1,11 @@
-timeout 1200 python -m pytest tests/test_gpu_oct_index.py -x -q > gpurun_out/o6_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/o6_pytest.log
+timeout 1200 python -m pytest tests/test_gpu_oct_index.py -x -q > gpurun_out/o7_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/o7_pytest.log
 run() { tag=$1; shift; env "$@" timeout 600 python bench.py --workload ${WL:-cfg3} --steps ${ST:-5} > gpurun_out/$tag.json 2> gpurun_out/$tag.err; echo "$tag rc=$?"; }
-run o6_cfg3 A=1
-run o6_cfg3_b20 MSBWT_OCT_BUCKET_SHIFT=20
-WL=cfg2 ST=10 run o6_cfg2 A=1
+run o7_cfg3 A=1
+run o7_cfg3_b20 MSBWT_OCT_BUCKET_SHIFT=20
+WL=cfg2 ST=10 run o7_cfg2 A=1
 python - <<'PY'
 import json,glob
-for f in sorted(glob.glob("gpurun_out/o6_*.json")):
+for f in sorted(glob.glob("gpurun_out/o7_*.json")):
     try:
         d=json.load(open(f)); r=d["roofline"]
         print(f, "value %.4g ms %.3f kernel_ms %.3f e2e %.4g acc/q %.2f acc/s %.3g frac %.3f idx %.1f GB oct %s shift %s ovf %s share %.4f" % (d["value"], d["ms_per_step"], r["kernel_ms"], d["e2e"]["value"], r["index_accesses_per_query"], r["index_accesses_per_s"], r["frac"], d["config"]["index_bytes"]/1e9, d["config"].get("oct_index"), r.get("oct_bucket_shift"), r.get("oct_overflow_lines"), r.get("oct_overflow_position_share")))
