@@ -96,7 +96,7 @@ msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *
  * quarter of the device memory left; MSBWT_OCT_INDEX=0|1 overrides), 0 = never, 1 = always (implies
  * quad_index).  Lines that cannot hold their bucket's runs are answered through the quad image, so results
  * are identical on any input.  `oct_bucket_shift`: b, 8..23 (0 = automatic: the largest b that keeps the mean
- * number of runs per line <= 12). */
+ * number of runs per line <= 6). */
 typedef struct msbwt_options {
     uint32_t struct_size;
     uint32_t superblock_shift; /* 0 = default */

@@ -150,8 +150,8 @@ constexpr int kQuadMaxSuperInSmem = 8;  // rows of 256 u64 staged in shared memo
 // 32-b bits and no run crosses a bucket.  When a bucket holds more than 30 runs of one code (word 1 > 30:
 // low-complexity text) the kernel falls back to two quad steps for that query-step, so the result is
 // exact on any input.  128 * 65536 * (N / 2^b + 1) bytes = 2^(23-b) B/symbol; b is the largest shift that
-// keeps the mean number of runs per line <= kOctTargetRuns (b = 21, 4 B/symbol, on 30x reads with 1 %
-// errors).  Built only next to a quad image (which also serves remainders of 4..7 symbols) and only when
+// keeps the mean number of runs per line <= kOctTargetRuns (b = 20, 8 B/symbol, on 30x reads with 1 %
+// errors: 0.7 % of the positions sit on overflowed lines; 7 % at b = 21).  Built only next to a quad image (which also serves remainders of 4..7 symbols) and only when
 // N < 2^32.
 constexpr int kOctCodes = 65536;
 constexpr int kOctLineBytes = 128;
@@ -159,7 +159,7 @@ constexpr int kOctLineWords = 32;
 constexpr int kOctCapacity = 30;      // runs per line
 constexpr int kOctMinShift = 8, kOctMaxShift = 23;
 constexpr int kOctAutoMinShift = 16;  // automatic choice: 16..23 (128 B/symbol .. 1 B/symbol)
-constexpr int kOctTargetRuns = 12;
+constexpr int kOctTargetRuns = 6;
 __host__ __device__ constexpr int oct_chunk_shift(int b) {  // cs = min(31 - b, 10, b)
     int c = 31 - b;
     if (c > 10) c = 10;

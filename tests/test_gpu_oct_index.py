@@ -54,9 +54,9 @@ def brute_oct(bwt: np.ndarray):
 
 
 def auto_shift(runs: int, n: int) -> int:
-    """layout.h: the largest bucket shift in 16..23 that keeps the mean number of runs per line <= 12"""
+    """layout.h: the largest bucket shift in 16..23 that keeps the mean number of runs per line <= 6"""
     s = 23
-    while s > 16 and runs * (1 << s) > 12 * 65536 * max(n, 1):
+    while s > 16 and runs * (1 << s) > 6 * 65536 * max(n, 1):
         s -= 1
     return s
 

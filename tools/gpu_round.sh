@@ -24,11 +24,11 @@ for w in $what; do
         --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/${tag}_launches.log 2>&1
       echo "launches rc=$?" ;;
     full_cfg3)
-      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:count_kmers_quad -s 3 -c 1 \
+      timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:count_kmers_(quad|oct)" -s 3 -c 1 \
         -f -o gpurun_out/${tag}_quad_cfg3 python bench.py --workload cfg3 --steps 1 --warmup 3 > gpurun_out/${tag}_full_cfg3.log 2>&1
       echo "full_cfg3 rc=$?" ;;
     full_cfg2)
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:count_kmers_quad -s 3 -c 1 \
+      timeout 900 ncu --set full --clock-control none --import-source on -k "regex:count_kmers_(quad|oct)" -s 3 -c 1 \
         -f -o gpurun_out/${tag}_quad_cfg2 python bench.py --workload cfg2 --steps 1 --warmup 3 > gpurun_out/${tag}_full_cfg2.log 2>&1
       echo "full_cfg2 rc=$?" ;;
   esac
