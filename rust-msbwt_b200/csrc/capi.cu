@@ -336,8 +336,11 @@ int build_pair(msbwt_index *idx, Replica &rep, uint8_t **keep_codes = nullptr) {
 // 151 Msymbol BWT, 1.7 x L2: 10.2 G queries/s through quad sectors + a depth-15 table in HBM against 7.3 G
 // through the mostly L2-resident one-step blocks), the image stays below 64 GB (measured,
 // profiles/r1_gather_big.json: random reads keep 93 % of their rate over a 64 GB buffer and lose three
-// quarters of it over 128 GB) and below half of the free device memory.
-bool pick_quad(int device, uint64_t index_bytes, uint64_t total, int requested, int pair_requested) {
+// quarters of it over 128 GB) and below half of the free device memory.  When the oct image will sit on top
+// (`with_oct`: 32-bit positions, not switched off) the quad image only serves fallbacks and remainders, the
+// randomly read footprint is the oct image + the suffix table, and the quad image may take up to 65 % of the
+// free memory (110 GB for configs[4]'s 3.02 Gsymbol BWT).
+bool pick_quad(int device, uint64_t index_bytes, uint64_t total, int requested, int pair_requested, bool with_oct) {
     if (requested == 0 || requested == 1) return requested == 1;
     if (pair_requested == 0 || pair_requested == 1) return false;  // the caller pinned the layout
     if (const char *env = getenv("MSBWT_QUAD_INDEX")) return atoi(env) != 0;
@@ -347,6 +350,7 @@ bool pick_quad(int device, uint64_t index_bytes, uint64_t total, int requested, 
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
     const uint64_t need = quad_image_bytes(total);
+    if (with_oct) return need <= free_b / 100 * 65;
     return need <= (64ull << 30) && need <= free_b / 2;
 }
 
@@ -496,7 +500,10 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
             bool quad;
             {
                 DeviceGuard guard(rep->device);
-                quad = opt.oct == 1 || pick_quad(rep->device, one_step_bytes, idx->total, opt.quad, opt.pair);
+                const char *oct_env = getenv("MSBWT_OCT_INDEX");
+                const bool with_oct = idx->total < (1ull << 32) && !index_is_wide(rep->view) && opt.oct != 0 &&
+                                      (opt.oct == 1 || !oct_env || atoi(oct_env) != 0);
+                quad = opt.oct == 1 || pick_quad(rep->device, one_step_bytes, idx->total, opt.quad, opt.pair, with_oct);
             }
             if (quad || pick_pair(rep->device, one_step_bytes, opt.pair)) {
                 if ((rc = quad ? build_quad(idx.get(), *rep, opt.oct, opt.oct_shift) : build_pair(idx.get(), *rep)) != MSBWT_OK) break;

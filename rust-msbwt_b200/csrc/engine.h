@@ -120,6 +120,7 @@ bool index_is_wide(const IndexView &ix);
 //                                     (0 = none, 1 = table_s, 2 = table_s - 1)
 //   [.., + (words-1)*n)         WX    symbol words 1.. of query q, word-major, by ORIGINAL index
 //   [.., + 2)                   LIVE  number of live queries in list A, list B (u64 counters)
+//   [.., + 2)                   WORK  the oct kernel's chunk dispenser over list A (u32 counter; + padding)
 // Queries that need no search step (empty seed range, or the suffix table answered every symbol)
 // are finished by the pack kernel itself and never reach the search kernels.
 constexpr uint32_t kQidxMask = (1u << 30) - 1u;
@@ -131,7 +132,8 @@ struct PackedLayout {
     __host__ __device__ uint64_t qidx() const { return n + (uint64_t)seedw * n; }
     __host__ __device__ uint64_t wx() const { return qidx() + (n + 1) / 2; }
     __host__ __device__ uint64_t live() const { return wx() + (uint64_t)(words - 1) * n; }
-    __host__ __device__ uint64_t total() const { return live() + 2; }
+    __host__ __device__ uint64_t work() const { return live() + 2; }
+    __host__ __device__ uint64_t total() const { return live() + 4; }
 };
 inline PackedLayout packed_layout(const IndexView &ix, uint32_t k, uint64_t n) {
     return PackedLayout{n, words_for_k(k), index_is_wide(ix) ? 2u : 1u};

@@ -122,15 +122,17 @@ count_kmers_quad_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packe
 //    lane ranks in its own staged line; divergent, but without memory accesses): one memory round trip per
 //    iteration even when the lanes of a warp need different kinds of step -- one lane in fourteen lands on
 //    an overflowed line on 30x reads with 1 % errors.
-//  * every warp owns one contiguous slice of the live list and stages it through shared memory 32 queries
-//    at a time, double-buffered (coalesced cp.async one pool ahead); lanes that finished take the next
-//    queries of the pool in lane order, so the warp stays full whatever the mix of early exits.
+//  * every warp takes chunks of 512 consecutive queries of the live list from an atomic counter and stages
+//    them through shared memory 32 queries at a time, double-buffered (coalesced cp.async one pool ahead);
+//    lanes that finished take the next queries of the pool in lane order, so the warp stays full whatever the
+//    mix of early exits and no warp is left with a slow slice of a skewed batch.
 #ifndef MSBWT_OCT_CTAS
 #define MSBWT_OCT_CTAS 4
 #endif
 constexpr int kOctRowBytes = 144;    // a 128-byte line + 16: rows of consecutive lanes start 4 banks apart (conflict-free LDS.128)
 constexpr int kOctPoolBytes = 640;   // 32 x (u64 symbol word, u64 seed range, u32 original index)
 constexpr int kOctWarpSmem = 32 * kOctRowBytes + 2 * kOctPoolBytes;  // 5888 bytes per warp, 47104 per CTA
+constexpr int kOctChunk = 512;       // queries a warp takes from the live list at a time
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool on) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
@@ -177,7 +179,7 @@ __device__ __forceinline__ uint32_t staged_sector_rank(const uint4 &a, const uin
 template <bool TAIL>
 __global__ void __launch_bounds__(kCountThreads, MSBWT_OCT_CTAS)
 count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, PackedLayout lay, uint32_t k,
-                       uint64_t *__restrict__ out) {
+                       uint64_t *__restrict__ out, uint32_t *__restrict__ work) {
     __shared__ __align__(16) uint8_t smem[(kCountThreads / 32) * kOctWarpSmem];
     __shared__ uint64_t cb_smem[4];
     [[maybe_unused]] CBase<false> cb{nullptr};
@@ -187,13 +189,7 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
 
     const uint32_t n = (uint32_t)packed[lay.live()];  // live queries of list A
     const uint32_t lane = threadIdx.x & 31u;
-    // every warp owns one CONTIGUOUS slice of the live list (a multiple of 32 queries)
-    const uint32_t nwarps = gridDim.x * (kCountThreads / 32);
-    const uint32_t per = ((n + nwarps - 1) / nwarps + 31u) & ~31u;
-    const uint64_t start64 = (uint64_t)(blockIdx.x * (kCountThreads / 32) + (threadIdx.x >> 5)) * per;
-    if (start64 >= n) return;
-    const uint32_t start = (uint32_t)start64;
-    const uint32_t end = (uint32_t)(start64 + per < n ? start64 + per : n);
+    if ((blockIdx.x * (kCountThreads / 32) + (threadIdx.x >> 5)) * 32u >= n) return;  // more warps than pools of work
     const uint64_t *w0 = packed + lay.w0(), *seeds = packed + lay.seed(), *wx = packed + lay.wx();
     const uint32_t *qidx = reinterpret_cast<const uint32_t *>(packed + lay.qidx());
     const uint32_t rem0 = k - acgt_table_depth(k, ix.table_s, 4u);
@@ -204,23 +200,40 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     uint8_t *const pools = rows + 32 * kOctRowBytes;                  // 2 pools: w0[32] | seed[32] | qidx[32]
     const uint4 *const my_row = reinterpret_cast<const uint4 *>(rows + lane * kOctRowBytes);
 
-    // pool b holds the queries [base, base + 32) with ((base - start) >> 5) & 1 == b
-    auto load_pool = [&](uint32_t base) {
-        uint8_t *p = pools + (((base - start) >> 5) & 1u) * kOctPoolBytes;
+    // The live list is handed out in chunks of kOctChunk queries (an atomic counter: a warp whose queries die
+    // early simply comes back sooner, whatever the order of the batch) and staged pool by pool: pool A
+    // (sequence number `seq`, buffer seq & 1) is being handed to the lanes, pool B (the other buffer) is
+    // already staged or on its way.
+    uint32_t chunk_next = 0, chunk_end = 0;  // the rest of this warp's current chunk (warp-uniform)
+    auto next_pool = [&](uint32_t &base, uint32_t &cnt) {
+        if (chunk_next >= chunk_end) {
+            uint32_t c = 0;
+            if (lane == 0) c = atomicAdd(work, (uint32_t)kOctChunk);
+            c = __shfl_sync(kFull, c, 0);
+            chunk_next = min(c, n);
+            chunk_end = min(c + (uint32_t)kOctChunk, n);
+        }
+        base = chunk_next;
+        cnt = min(32u, chunk_end - chunk_next);
+        chunk_next += cnt;
+    };
+    auto load_pool = [&](uint32_t buf, uint32_t base, uint32_t cnt) {
+        uint8_t *p = pools + buf * kOctPoolBytes;
         const uint32_t idx = base + lane;
-        const bool on = idx < end;
+        const bool on = lane < cnt;
         cp_async8(p + 8u * lane, w0 + idx, on);
         cp_async8(p + 256u + 8u * lane, seeds + idx, on);
         cp_async4(p + 512u + 4u * lane, qidx + idx, on);
     };
-    load_pool(start);
-    load_pool(start + 32u);
+    uint32_t seq = 0, a_pos = 0, a_cnt, b_cnt, base;
+    next_pool(base, a_cnt);
+    load_pool(0u, base, a_cnt);
+    next_pool(base, b_cnt);
+    load_pool(1u, base, b_cnt);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
 
-    uint32_t next_i = start;     // first query of the slice nobody has taken (warp-uniform)
-    uint32_t pool_base = start;  // the two pools hold [pool_base, pool_base + 64)
     bool active = false;
     uint32_t l = 0, h = 0;
     uint64_t word = 0, pend = 0;
@@ -238,11 +251,13 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         }
         const uint32_t want = __ballot_sync(kFull, !active);
         if (want) {
-            if (next_i < end) {
-                const uint32_t gi = next_i + __popc(want & ((1u << lane) - 1u));
-                if (!active && gi < end) {
-                    const uint8_t *p = pools + (((gi - start) >> 5) & 1u) * kOctPoolBytes;
-                    const uint32_t slot = (gi - start) & 31u;
+            const uint32_t avail_a = a_cnt - a_pos, avail = avail_a + b_cnt;
+            if (avail) {
+                const uint32_t r = __popc(want & ((1u << lane) - 1u));  // idle lanes take queries in lane order
+                if (!active && r < avail) {
+                    const bool from_a = r < avail_a;
+                    const uint8_t *p = pools + ((from_a ? seq : seq + 1u) & 1u) * kOctPoolBytes;
+                    const uint32_t slot = from_a ? a_pos + r : r - avail_a;
                     word = *reinterpret_cast<const volatile uint64_t *>(p + 8u * slot);
                     const uint64_t lo = *reinterpret_cast<const volatile uint64_t *>(p + 256u + 8u * slot);
                     q = *reinterpret_cast<const volatile uint32_t *>(p + 512u + 4u * slot) & kQidxMask;
@@ -255,15 +270,19 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                     active = true;
                     if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + q, stream);
                 }
-                const uint32_t taken = min((uint32_t)__popc(want), end - next_i);
-                next_i += taken;
-                if (next_i >= pool_base + 32u) {  // the older pool is used up: stage the one after the newer into its place
+                const uint32_t taken = min((uint32_t)__popc(want), avail);
+                if (taken >= avail_a) {  // pool A is used up: B becomes A, the next pool is staged into A's buffer
+                    a_cnt = b_cnt;
+                    a_pos = taken - avail_a;
+                    seq++;
+                    next_pool(base, b_cnt);
                     __syncwarp();
-                    pool_base += 32u;
-                    load_pool(pool_base + 32u);  // (committed with this iteration's lines)
+                    load_pool((seq + 1u) & 1u, base, b_cnt);  // (committed with this iteration's lines)
+                } else {
+                    a_pos += taken;
                 }
             } else if (want == kFull) {
-                return;  // slice finished
+                return;  // nothing left to hand out and every lane is done
             }
         }
         if (active && shift < 0) {  // 32 symbols per word; steps of 8 and 4 symbols never straddle two words
@@ -378,12 +397,16 @@ cudaError_t launch_count_quad(int device, const IndexView &ix, const uint64_t *d
             cudaFuncSetAttribute((const void *)count_kmers_oct_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             carveout_set = true;
         }
+        // the chunk dispenser lives in the scratch buffer next to the live counters (engine bookkeeping: the
+        // buffer is the engine's own scratch, `const` only towards the caller's data in it)
+        uint32_t *work = reinterpret_cast<uint32_t *>(const_cast<uint64_t *>(d_packed) + lay.work());
+        if (cudaError_t e = cudaMemsetAsync(work, 0, sizeof(uint32_t), st); e != cudaSuccess) return e;
         if ((k - acgt_table_depth(k, ix.table_s, 4u)) % 4u) {
             const unsigned grid = persistent_grid(device, (const void *)count_kmers_oct_kernel<true>, kCountThreads, lay.n, kCountThreads);
-            count_kmers_oct_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out);
+            count_kmers_oct_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out, work);
         } else {
             const unsigned grid = persistent_grid(device, (const void *)count_kmers_oct_kernel<false>, kCountThreads, lay.n, kCountThreads);
-            count_kmers_oct_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out);
+            count_kmers_oct_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out, work);
         }
         return cudaGetLastError();
     }

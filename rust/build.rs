@@ -8,7 +8,8 @@ fn main() {
     let csrc = root.join("rust-msbwt_b200").join("csrc");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let mut objs = vec![];
-    for f in ["capi.cu", "kernels.cu", "loader.cu", "builder.cu"] {
+    for f in ["capi.cu", "kernels.cu", "quad_kernels.cu", "loader.cu", "builder.cu", "pair_builder.cu", "quad_builder.cu",
+              "oct_builder.cu", "bwt_build.cu"] {
         let obj = out.join(f).with_extension("o");
         let ok = Command::new(&nvcc)
             .args(["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -22,6 +23,11 @@ fn main() {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
         objs.push(obj);
     }
+    // the host-side 2-bit packer of the end-to-end path (plain C++, AVX2 behind a runtime check)
+    let hp = out.join("hostpack.o");
+    assert!(Command::new("g++").args(["-O3", "-std=c++17", "-fPIC", "-pthread", "-c", "-o"]).arg(&hp)
+        .arg(csrc.join("hostpack.cpp")).status().expect("g++ not found").success());
+    objs.push(hp);
     let lib = out.join("libmsbwt_b200.a");
     assert!(Command::new("ar").arg("crs").arg(&lib).args(&objs).status().unwrap().success());
     let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());

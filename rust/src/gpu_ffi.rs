@@ -7,6 +7,19 @@ pub struct msbwt_index {
     _private: [u8; 0],
 }
 
+/// `msbwt_options` (include/msbwt_gpu.h): which device images serve the path.  Results never depend on it.
+#[repr(C)]
+pub struct msbwt_options {
+    pub struct_size: u32,
+    pub superblock_shift: u32,
+    pub suffix_table_s: i32,
+    pub pair_index: i32,
+    pub kernel_lanes: i32,
+    pub quad_index: i32,
+    pub oct_index: i32,
+    pub oct_bucket_shift: i32,
+}
+
 pub const MSBWT_OK: c_int = 0;
 pub const MSBWT_EINVAL: c_int = 1;
 pub const MSBWT_EIO: c_int = 2;
@@ -19,6 +32,7 @@ extern "C" {
     pub fn msbwt_index_create_from_rle(rle: *const u8, len: u64, devices: *const c_int, ndev: c_int, err: *mut c_int) -> *mut msbwt_index;
     pub fn msbwt_index_create_from_npy(path: *const c_char, devices: *const c_int, ndev: c_int, err: *mut c_int) -> *mut msbwt_index;
     pub fn msbwt_index_create_ex(rle: *const u8, len: u64, devices: *const c_int, ndev: c_int, superblock_shift: u32, suffix_table_s: c_int, err: *mut c_int) -> *mut msbwt_index;
+    pub fn msbwt_index_create_opts(rle: *const u8, len: u64, devices: *const c_int, ndev: c_int, opts: *const msbwt_options, err: *mut c_int) -> *mut msbwt_index;
     pub fn msbwt_index_destroy(idx: *mut msbwt_index);
     pub fn msbwt_total_size(idx: *const msbwt_index) -> u64;
     pub fn msbwt_symbol_count(idx: *const msbwt_index, sym: u8) -> u64;
@@ -33,6 +47,13 @@ extern "C" {
     pub fn msbwt_packed_bytes(idx: *const msbwt_index, k: u32, n: u64) -> u64;
     pub fn msbwt_suffix_table_s(idx: *const msbwt_index) -> c_int;
     pub fn msbwt_kernel_lanes(idx: *const msbwt_index) -> c_int;
+    pub fn msbwt_pair_index(idx: *const msbwt_index) -> c_int;
+    pub fn msbwt_quad_index(idx: *const msbwt_index) -> c_int;
+    pub fn msbwt_oct_index(idx: *const msbwt_index) -> c_int;
+    pub fn msbwt_oct_bucket_shift(idx: *const msbwt_index) -> c_int;
+    pub fn msbwt_oct_runs(idx: *const msbwt_index) -> u64;
+    pub fn msbwt_oct_overflow_lines(idx: *const msbwt_index) -> u64;
+    pub fn msbwt_oct_overflow_occurrences(idx: *const msbwt_index) -> u64;
     pub fn msbwt_pack_kmers_device(idx: *const msbwt_index, slot: c_int, d_syms: *const u8, k: u32, n: u64, d_packed: *mut u64, d_out: *mut u64, d_status: *mut u32, stream: *mut c_void) -> c_int;
     pub fn msbwt_count_kmers_packed_device(idx: *const msbwt_index, slot: c_int, d_packed: *const u64, k: u32, n: u64, d_out: *mut u64, stream: *mut c_void) -> c_int;
     pub fn msbwt_constrain_ranges_device(idx: *const msbwt_index, slot: c_int, d_sym: *const u8, d_l: *const u64, d_h: *const u64, n: u64, d_out_l: *mut u64, d_out_h: *mut u64, stream: *mut c_void) -> c_int;
