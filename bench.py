@@ -152,13 +152,14 @@ def build_workload(cfg: dict, device, rank: int):
         rle_host = rle.cpu().numpy()
         del rle
     queries = synth.make_queries(reads, cfg["k"], cfg["n_read"], cfg["n_random"], seed_offset=1000 * rank)
+    reads_sample = reads[:100_000].cpu().numpy()   # for the pileup leg (count_read_kmers)
     del reads
     if device.type == "cuda":
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
     log(f"[rank {rank}] workload built in {time.time() - t0:.1f}s: {total} symbols, {rle_host.size} RLE bytes, "
         f"{queries.shape[0]} queries")
-    return rle_host, total, queries
+    return rle_host, total, queries, reads_sample
 
 
 def cpu_reference_leg(orc, q_host, k, threads, target_s, label):
@@ -182,7 +183,7 @@ def reference_measure(args, cfg):
     import torch
     from oracle import oracle as O
     dev = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")  # GPU only manufactures the inputs
-    rle_host, total, queries = build_workload(cfg, dev, 0)
+    rle_host, total, queries, _ = build_workload(cfg, dev, 0)
     q_host = queries.cpu().numpy()
     del queries
     orc = O.RleBWT()
@@ -247,7 +248,7 @@ def measure_ours(args, cfg, ctx, primary: bool):
     rank, world, local, dev = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"]
     barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
     k = cfg["k"]
-    rle_host, total, queries = build_workload(cfg, dev, rank)
+    rle_host, total, queries, reads_sample = build_workload(cfg, dev, rank)
     n = queries.shape[0]
     t0 = time.time()
     bwt = M.RleBWT.new(devices=[local])
@@ -323,6 +324,31 @@ def measure_ours(args, cfg, ctx, primary: bool):
     h2d_bytes, d2h_bytes = M.last_transfer_bytes()   # counted by the library from the copies it issued
     assert int(out_np.astype(np.int64).sum()) == checksum, "host-path and device-path results differ"
 
+    # ---- pileup: count_kmer of every window of whole reads (msbwt_count_read_kmers): only the reads cross PCIe ----
+    nr, rl = reads_sample.shape
+    r_pinned = torch.empty((nr, rl), dtype=torch.uint8, pin_memory=True)
+    r_pinned.copy_(torch.from_numpy(reads_sample))
+    p_out = torch.empty((nr, rl - k + 1), dtype=torch.int64, pin_memory=True)
+    r_np, p_np = r_pinned.numpy(), p_out.numpy().view(np.uint64)
+
+    def pile_step():
+        rc = lib.msbwt_count_read_kmers(bwt.handle, ctypes.c_void_p(r_np.ctypes.data), rl, nr, k, 1,
+                                        ctypes.c_void_p(p_np.ctypes.data))
+        assert rc == 0, lib.msbwt_last_error()
+
+    pile_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pile_step()
+    torch.cuda.synchronize()
+    pile_s = max_over_ranks(time.perf_counter() - t0)
+    pileup = {"value": world * nr * (rl - k + 1) * args.steps / pile_s, "unit": UNIT, "reads_per_step": nr,
+              "windows_per_read": rl - k + 1, "h2d_bytes_per_step": nr * rl, "d2h_bytes_per_step": nr * (rl - k + 1) * 8,
+              "ms_per_step": 1e3 * pile_s / args.steps,
+              "what": "msbwt_count_read_kmers on pinned host reads: every 31-mer window of every read, forward strand"}
+    pile_counts = p_np[:64].copy()
+
     res = {
         "value": value, "ms_per_step": total_ms / args.steps,
         "config": {"workload": cfg["name"], "bwt_symbols": total, "index_bytes": bwt.index_bytes, "k": k,
@@ -340,6 +366,7 @@ def measure_ours(args, cfg, ctx, primary: bool):
                           "hybrid: chunks packed 2 bit/symbol by the host pool, and raw symbol-byte chunks whenever the "
                           "copy engine is idle -> seed / pack + search kernels -> D2H"),
                 "host_pack_threads": M.host_pack_threads()},
+        "e2e_pileup": pileup,
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "checksum": checksum,
     }
 
@@ -350,6 +377,8 @@ def measure_ours(args, cfg, ctx, primary: bool):
         orc.load_vector(rle_host)
         cores = os.cpu_count() or 1
         got = d_out.cpu().numpy().view(np.uint64)
+        pw = np.ascontiguousarray(np.lib.stride_tricks.sliding_window_view(reads_sample[:64], k, axis=1)).reshape(-1, k)
+        assert (pile_counts.reshape(-1) == orc.count_kmers_fixed(pw, k, threads=cores)).all(), "pileup counts differ from the CPU oracle"
         if world == 1:
             tgt = 8.0 if primary else 4.0
             v1, m1, c1 = cpu_reference_leg(orc, q_host, k, 1, tgt, "single thread")
@@ -527,12 +556,12 @@ def run_ours(args, cfgs):
             "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         }
-        for key in ("config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "wall_s_timed_region",
+        for key in ("config", "e2e", "e2e_pileup", "gpu_launches", "clocks", "roofline", "cpu_baseline", "wall_s_timed_region",
                     "checksum", "kernel_share_of_step"):
             line[key] = main_res.get(key)
         if others:
             line["other_workloads"] = [
-                {key: r.get(key) for key in ("value", "ms_per_step", "config", "e2e", "gpu_launches", "roofline",
+                {key: r.get(key) for key in ("value", "ms_per_step", "config", "e2e", "e2e_pileup", "gpu_launches", "roofline",
                                              "cpu_baseline", "checksum")} for r in others]
         print(json.dumps(line), flush=True)
     if dist is not None:

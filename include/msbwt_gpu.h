@@ -229,6 +229,26 @@ int msbwt_debug_copy_pair_image(const msbwt_index *idx, int slot, uint64_t *npai
 int msbwt_debug_copy_quad_image(const msbwt_index *idx, int slot, uint64_t *nsec4, uint32_t *n_super4,
                                 uint32_t *sectors, uint64_t *c4base);
 
+/* ---- batched callers of the path (what a correction / assembly loop around msbwt2 does with it) ---- */
+
+/* Fan-out: the four constrain_range calls of a backward-search extension at once.  For every input range i
+ * and j = 0..3: (out_l[4*i+j], out_h[4*i+j]) = RleBWT::constrain_range(ACGT[j], [l[i], h[i]))
+ * (src/rle_bwt.rs:202-287 called with sym = 1, 2, 3, 5); the index blocks holding l and h are fetched once
+ * for the four symbols.  EINVAL (nothing written) when some l > h or h > total_size. */
+int msbwt_constrain_ranges_fanout(const msbwt_index *idx, const uint64_t *l, const uint64_t *h, uint64_t n,
+                                  uint64_t *out_l /* 4n */, uint64_t *out_h /* 4n */);
+int msbwt_constrain_ranges_fanout_device(const msbwt_index *idx, int slot, const uint64_t *d_l, const uint64_t *d_h,
+                                         uint64_t n, uint64_t *d_out_l, uint64_t *d_out_h, void *stream);
+
+/* Pileup: BWT::count_kmer (src/msbwt_core.rs:125-161) of every k-mer window of every read.  `reads` =
+ * n_reads * read_len symbol bytes (0..5); out[r * (read_len-k+1) + w] = count_kmer(reads[r][w .. w+k)) when
+ * strands == 1, and count_kmer(window) + count_kmer(reverse_complement_i(window)) (src/string_util.rs:45-50)
+ * when strands == 2.  Only the reads cross PCIe (read_len bytes per read instead of k per window); the
+ * windows are laid out on the device and go through the same pack / search kernels as msbwt_count_kmers_fixed.
+ * EINVAL (nothing written) when k == 0, k > read_len, strands not in {1,2} or a symbol is >= 6. */
+int msbwt_count_read_kmers(const msbwt_index *idx, const uint8_t *reads, uint32_t read_len, uint64_t n_reads,
+                           uint32_t k, uint32_t strands, uint64_t *out /* n_reads * (read_len-k+1) */);
+
 /* The oct image of a replica: 65536 * *nbuck8 lines of 32 u32 words, code-major (nbuck8 = (N >> b) + 1).
  * NULL array: size only. */
 int msbwt_debug_copy_oct_image(const msbwt_index *idx, int slot, uint64_t *nbuck8, uint32_t *lines);

@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <stdexcept>
+#include <array>
 #include <string>
 #include <vector>
 
@@ -90,6 +91,24 @@ class RleBWT {
         if (!k || syms.size() % k) throw Panic(MSBWT_EINVAL, "len(syms) must be a positive multiple of k");
         std::vector<uint64_t> out(syms.size() / k);
         check(msbwt_count_kmers_fixed(h_, syms.data(), k, out.size(), out.data()));
+        return out;
+    }
+    // the four constrain_range calls (A, C, G, T) of one extension step, from one fetch of the index blocks
+    std::array<BWTRange, 4> constrain_range_fanout(const BWTRange &in) const {
+        uint64_t l[4], h[4];
+        check(msbwt_constrain_ranges_fanout(h_, &in.l, &in.h, 1, l, h));
+        std::array<BWTRange, 4> out;
+        for (int j = 0; j < 4; j++) { out[j].l = l[j]; out[j].h = h[j]; }
+        return out;
+    }
+    // count_kmer of every k-mer window of every read (reads: n * read_len symbol bytes); both_strands adds the
+    // count of each window's reverse complement (string_util::reverse_complement_i)
+    std::vector<uint64_t> count_read_kmers(const std::vector<uint8_t> &reads, uint32_t read_len, uint32_t k,
+                                           bool both_strands = false) const {
+        if (!read_len || reads.size() % read_len || !k || k > read_len) throw Panic(MSBWT_EINVAL, "bad read_len / k");
+        const uint64_t n = reads.size() / read_len;
+        std::vector<uint64_t> out(n * (read_len - k + 1));
+        check(msbwt_count_read_kmers(h_, reads.data(), read_len, n, k, both_strands ? 2 : 1, out.data()));
         return out;
     }
     const msbwt_index *handle() const { return h_; }

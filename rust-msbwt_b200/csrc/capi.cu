@@ -1146,6 +1146,152 @@ extern "C" int msbwt_debug_copy_oct_image(const msbwt_index *idx, int slot, uint
     return MSBWT_OK;
 }
 
+// ================================================================ batched callers of the path
+
+extern "C" int msbwt_constrain_ranges_fanout_device(const msbwt_index *idx, int slot, const uint64_t *d_l,
+                                                    const uint64_t *d_h, uint64_t n, uint64_t *d_out_l,
+                                                    uint64_t *d_out_h, void *stream) {
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
+    if (n && (!d_l || !d_h || !d_out_l || !d_out_h)) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (!n) return MSBWT_OK;
+    Replica &rep = *idx->reps[slot];
+    DeviceGuard guard(rep.device);
+    CU_TRY(launch_constrain_fanout(rep.device, rep.view, d_l, d_h, n, d_out_l, d_out_h, (cudaStream_t)stream, &g_call_launches));
+    flush_launches();
+    return MSBWT_OK;
+}
+
+extern "C" int msbwt_constrain_ranges_fanout(const msbwt_index *idx, const uint64_t *l, const uint64_t *h, uint64_t n,
+                                             uint64_t *out_l, uint64_t *out_h) {
+    g_last_error.clear();
+    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
+    if (!n) return MSBWT_OK;
+    if (!l || !h || !out_l || !out_h) return fail(MSBWT_EINVAL, "NULL host buffer");
+    const size_t ndev = idx->reps.size();
+    const uint64_t chunk = kChunkQueries;
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
+    for (uint64_t i = 0; i < n; i++)
+        if (l[i] > h[i] || h[i] > idx->total)
+            return fail(MSBWT_EINVAL, "constrain_ranges_fanout: item " + std::to_string(i) + " has l > h or h > total_size");
+    uint64_t max_chunks = 0;
+    for (size_t d = 0; d < ndev; d++) {
+        Replica &rep = *idx->reps[d];
+        DeviceGuard guard(rep.device);
+        const Slice sl = slice_for(n, d, ndev);
+        const uint64_t len = sl.end - sl.begin, c = std::max<uint64_t>(1, std::min(chunk, len));
+        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
+        for (int li = 0; li < 2; li++) {
+            Lane &ln = rep.lane[li];
+            CU_TRY(cudaStreamSynchronize(ln.stream));
+            CU_TRY(ln.in_b.reserve(c * sizeof(uint64_t)));
+            CU_TRY(ln.in_c.reserve(c * sizeof(uint64_t)));
+            CU_TRY(ln.out_a.reserve(4 * c * sizeof(uint64_t)));
+            CU_TRY(ln.out_b.reserve(4 * c * sizeof(uint64_t)));
+        }
+    }
+    for (uint64_t c = 0; c < max_chunks; c++) {
+        for (size_t d = 0; d < ndev; d++) {
+            Replica &rep = *idx->reps[d];
+            const Slice sl = slice_for(n, d, ndev);
+            const uint64_t b = sl.begin + c * chunk;
+            if (b >= sl.end) continue;
+            const uint64_t m = std::min(chunk, sl.end - b);
+            DeviceGuard guard(rep.device);
+            Lane &ln = rep.lane[c & 1];
+            CU_TRY(cudaMemcpyAsync(ln.in_b.p, l + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(cudaMemcpyAsync(ln.in_c.p, h + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(launch_constrain_fanout(rep.device, rep.view, ln.in_b.as<uint64_t>(), ln.in_c.as<uint64_t>(), m,
+                                           ln.out_a.as<uint64_t>(), ln.out_b.as<uint64_t>(), ln.stream, &g_call_launches));
+            flush_launches();
+            CU_TRY(cudaMemcpyAsync(out_l + 4 * b, ln.out_a.p, 4 * m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+            CU_TRY(cudaMemcpyAsync(out_h + 4 * b, ln.out_b.p, 4 * m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+        }
+    }
+    for (auto &rep : idx->reps) {
+        DeviceGuard guard(rep->device);
+        for (int li = 0; li < 2; li++) CU_TRY(cudaStreamSynchronize(rep->lane[li].stream));
+    }
+    return MSBWT_OK;
+}
+
+extern "C" int msbwt_count_read_kmers(const msbwt_index *idx, const uint8_t *reads, uint32_t read_len, uint64_t n_reads,
+                                      uint32_t k, uint32_t strands, uint64_t *out) {
+    g_last_error.clear();
+    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
+    if (!k || k > read_len) return fail(MSBWT_EINVAL, "count_read_kmers: k must be in 1..read_len");
+    if (strands != 1 && strands != 2) return fail(MSBWT_EINVAL, "count_read_kmers: strands must be 1 or 2");
+    if (!n_reads) return MSBWT_OK;
+    if (!reads || !out) return fail(MSBWT_EINVAL, "NULL host buffer");
+    const uint64_t windows = (uint64_t)read_len - k + 1, per_read_q = windows * strands;
+    const size_t ndev = idx->reps.size();
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
+    // validation first, as count_kmer does (src/msbwt_core.rs:127): no output is written for a bad batch
+    {
+        const uint64_t bytes = n_reads * read_len;
+        for (uint64_t i = 0; i < bytes; i++)
+            if (reads[i] >= kAlphabet)
+                return fail(MSBWT_EINVAL, "count_read_kmers: read " + std::to_string(i / read_len) + " holds a symbol >= 6");
+    }
+    const uint64_t chunk = std::max<uint64_t>(1, kChunkQueries / per_read_q);  // reads per chunk
+    uint64_t max_chunks = 0;
+    for (size_t d = 0; d < ndev; d++) {
+        Replica &rep = *idx->reps[d];
+        DeviceGuard guard(rep.device);
+        const Slice sl = slice_for(n_reads, d, ndev);
+        const uint64_t len = sl.end - sl.begin, c = std::max<uint64_t>(1, std::min(chunk, len));
+        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
+        for (int li = 0; li < 2; li++) {
+            Lane &ln = rep.lane[li];
+            CU_TRY(cudaStreamSynchronize(ln.stream));
+            CU_TRY(ln.in_a.reserve(c * read_len));
+            CU_TRY(ln.in_b.reserve(c * per_read_q * k + 16));
+            CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, c * per_read_q).total() * sizeof(uint64_t)));
+            CU_TRY(ln.out_a.reserve(c * per_read_q * sizeof(uint64_t)));
+            CU_TRY(ln.out_b.reserve(c * windows * sizeof(uint64_t)));
+        }
+    }
+    uint64_t h2d = 0, d2h = 0;
+    for (uint64_t c = 0; c < max_chunks; c++) {
+        for (size_t d = 0; d < ndev; d++) {
+            Replica &rep = *idx->reps[d];
+            const Slice sl = slice_for(n_reads, d, ndev);
+            const uint64_t b = sl.begin + c * chunk;
+            if (b >= sl.end) continue;
+            const uint64_t m = std::min(chunk, sl.end - b), nq = m * per_read_q;
+            DeviceGuard guard(rep.device);
+            Lane &ln = rep.lane[c & 1];
+            uint32_t *flag = rep.d_status + (c & 1);
+            CU_TRY(cudaMemcpyAsync(ln.in_a.p, reads + b * read_len, m * read_len, cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(launch_expand_read_kmers(rep.device, ln.in_a.as<uint8_t>(), read_len, m, k, strands, ln.in_b.as<uint8_t>(), ln.stream));
+            g_launches++;
+            CU_TRY(cudaMemsetAsync(flag, 0, sizeof(uint32_t), ln.stream));
+            CU_TRY(launch_pack_seed(rep.view, ln.in_b.as<uint8_t>(), k, nq, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(), flag, ln.stream));
+            g_launches++;
+            CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, nq, ln.out_a.as<uint64_t>(),
+                                       ln.stream, &g_call_launches));
+            flush_launches();
+            const uint64_t *res = ln.out_a.as<uint64_t>();
+            if (strands == 2) {
+                CU_TRY(launch_sum_strands(rep.device, ln.out_a.as<uint64_t>(), m * windows, ln.out_b.as<uint64_t>(), ln.stream));
+                g_launches++;
+                res = ln.out_b.as<uint64_t>();
+            }
+            CU_TRY(cudaMemcpyAsync(out + b * windows, res, m * windows * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+            h2d += m * read_len;
+            d2h += m * windows * sizeof(uint64_t);
+        }
+    }
+    for (auto &rep : idx->reps) {
+        DeviceGuard guard(rep->device);
+        for (int li = 0; li < 2; li++) CU_TRY(cudaStreamSynchronize(rep->lane[li].stream));
+    }
+    g_last_h2d = h2d;
+    g_last_d2h = d2h;
+    return MSBWT_OK;
+}
+
 // ================================================================ construction of the BWT itself
 
 extern "C" int msbwt_build_rle_bwt(const uint8_t *reads, uint64_t n_reads, uint32_t read_len, int reads_on_device,

@@ -167,6 +167,39 @@ __device__ __forceinline__ void rank_step(const IndexView &ix, const CBase<WIDE>
     h = cb.at(bh, sym) + ckh + ch;
 }
 
+// The four constrain_range calls of a backward-search extension at once: the block(s) holding
+// l and h are fetched ONCE and ranked for A, C, G and T.  out_l[j], out_h[j] = constrain_range(ACGT[j], [l,h)).
+template <bool WIDE>
+__device__ __forceinline__ void rank_fanout4(const IndexView &ix, const CBase<WIDE> &cb, typename Pos<WIDE>::type l,
+                                             typename Pos<WIDE>::type h, typename Pos<WIDE>::type (&out_l)[4],
+                                             typename Pos<WIDE>::type (&out_h)[4]) {
+    using P = typename Pos<WIDE>::type;
+    const P bl = l >> kBlockShift, bh = h >> kBlockShift;
+    const bool two = bh != bl;
+    const char *base = reinterpret_cast<const char *>(ix.blocks);
+    const int pl = (int)((uint32_t)l & (kBlockSyms - 1)), ph = (int)((uint32_t)h & (kBlockSyms - 1));
+    const Half l0 = ldg_index256(base + (size_t)bl * kBlockBytes);
+    const Half l1 = ldg_index256(base + (size_t)bl * kBlockBytes + 32);
+    Half h0 = l0, h1 = l1;
+    if (two) {
+        h0 = ldg_index256(base + (size_t)bh * kBlockBytes);
+        h1 = ldg_index256(base + (size_t)bh * kBlockBytes + 32);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t sym = (0x5321u >> (4 * j)) & 7u;  // A,C,G,T = 1,2,3,5; their checkpoint slot is j
+        const uint32_t x0 = (sym & 1u) - 1u, x1 = ((sym >> 1) & 1u) - 1u, x2 = ((sym >> 2) & 1u) - 1u;
+        uint32_t ml[4], mh[4];
+        match_half(l0, x0, x1, x2, ml[0], ml[1]);
+        match_half(l1, x0, x1, x2, ml[2], ml[3]);
+        match_half(h0, x0, x1, x2, mh[0], mh[1]);
+        match_half(h1, x0, x1, x2, mh[2], mh[3]);
+        const uint32_t ckl = (j & 2) ? l1.w[j & 1] : l0.w[j & 1], ckh = (j & 2) ? h1.w[j & 1] : h0.w[j & 1];
+        out_l[j] = cb.at(bl, sym) + ckl + count_below64(ml[0], ml[1], pl) + count_below64(ml[2], ml[3], pl - 64);
+        out_h[j] = cb.at(bh, sym) + ckh + count_below64(mh[0], mh[1], ph) + count_below64(mh[2], mh[3], ph - 64);
+    }
+}
+
 // ---- pair image (layout.h): two constrain_range steps per 128-byte line
 
 template <bool WIDE> struct C2Base;

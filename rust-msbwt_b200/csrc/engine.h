@@ -157,6 +157,14 @@ cudaError_t launch_count_bytes(int device, const IndexView &ix, const uint8_t *d
 cudaError_t launch_constrain_ranges(int device, const IndexView &ix, const uint8_t *d_sym, const uint64_t *d_l,
                                     const uint64_t *d_h, uint64_t n, uint64_t *d_out_l, uint64_t *d_out_h,
                                     cudaStream_t st, int *launches);
+// ext_kernels.cu: the four constrain_range calls (A,C,G,T) of every range from one fetch of its blocks
+// (out[4 * i + j]); the k-mers of every window of every read (and their reverse complements) as symbol bytes;
+// per-window sums of the two strands' counts
+cudaError_t launch_constrain_fanout(int device, const IndexView &ix, const uint64_t *d_l, const uint64_t *d_h,
+                                    uint64_t n, uint64_t *d_out_l, uint64_t *d_out_h, cudaStream_t st, int *launches);
+cudaError_t launch_expand_read_kmers(int device, const uint8_t *d_reads, uint32_t read_len, uint64_t n_reads, uint32_t k,
+                                     uint32_t strands, uint8_t *d_syms, cudaStream_t st);
+cudaError_t launch_sum_strands(int device, const uint64_t *d_per_query, uint64_t n_windows, uint64_t *d_out, cudaStream_t st);
 cudaError_t launch_gather(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,
                           uint64_t n_gathers, uint64_t seed, uint64_t *d_sink, cudaStream_t st);
 

@@ -123,6 +123,9 @@ def load_library():
         "msbwt_oct_runs": (u64, [vp]),
         "msbwt_oct_bucket_shift": (i32, [vp]),
         "msbwt_debug_copy_oct_image": (i32, [vp, i32, C.POINTER(u64), vp]),
+        "msbwt_constrain_ranges_fanout": (i32, [vp, vp, vp, u64, vp, vp]),
+        "msbwt_constrain_ranges_fanout_device": (i32, [vp, i32, vp, vp, u64, vp, vp, vp]),
+        "msbwt_count_read_kmers": (i32, [vp, vp, u32, u64, u32, u32, vp]),
         "msbwt_debug_copy_quad_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp]),
         "msbwt_last_transfer_bytes": (None, [C.POINTER(u64), C.POINTER(u64)]),
         "msbwt_host_pack_threads": (i32, []),
@@ -153,7 +156,8 @@ EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
     "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_oct_index", "msbwt_oct_overflow_lines",
     "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift",
-    "msbwt_debug_copy_oct_image", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
+    "msbwt_debug_copy_oct_image", "msbwt_constrain_ranges_fanout", "msbwt_constrain_ranges_fanout_device",
+    "msbwt_count_read_kmers", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
     "msbwt_debug_host_pack",
     "msbwt_index_destroy", "msbwt_total_size", "msbwt_symbol_count", "msbwt_start_index",
     "msbwt_device_count", "msbwt_device_ordinal", "msbwt_index_bytes", "msbwt_suffix_table_s", "msbwt_kernel_lanes", "msbwt_count_kmers",
@@ -314,6 +318,31 @@ class RleBWT:
         _check(load_library().msbwt_constrain_ranges(self.handle, _p(s), _p(lo), _p(hi), s.size, _p(out_l), _p(out_h)),
                "constrain_range")
         return out_l, out_h
+
+    def constrain_ranges_fanout(self, l, h) -> tuple[np.ndarray, np.ndarray]:
+        """The four `constrain_range` calls (A, C, G, T) of every range at once: (out_l[n,4], out_h[n,4])."""
+        lo, hi = _u64(l).reshape(-1), _u64(h).reshape(-1)
+        if lo.size != hi.size:
+            raise MsbwtError(EINVAL, "l/h length mismatch")
+        out_l = np.zeros((lo.size, 4), dtype=np.uint64)
+        out_h = np.zeros((lo.size, 4), dtype=np.uint64)
+        _check(load_library().msbwt_constrain_ranges_fanout(self.handle, _p(lo), _p(hi), lo.size, _p(out_l), _p(out_h)),
+               "constrain_ranges_fanout")
+        return out_l, out_h
+
+    def count_read_kmers(self, reads, k: int, both_strands: bool = False) -> np.ndarray:
+        """`count_kmer` of every k-mer window of every read (reads[n, read_len] symbol bytes): out[n, read_len-k+1];
+        with `both_strands` each entry is count(window) + count(reverse_complement_i(window))."""
+        a = _u8(reads)
+        if a.ndim != 2:
+            raise MsbwtError(EINVAL, "reads must be a 2-D array [n_reads, read_len]")
+        n, L = a.shape
+        if k < 1 or k > L:
+            raise MsbwtError(EINVAL, "k must be in 1..read_len")
+        out = np.zeros((n, L - k + 1), dtype=np.uint64)
+        _check(load_library().msbwt_count_read_kmers(self.handle, _p(a), L, n, k, 2 if both_strands else 1, _p(out)),
+               "count_read_kmers")
+        return out
 
     # -- device-buffer entry points (raw pointers: torch `.data_ptr()` / stream handles)
     def count_kmers_fixed_device(self, d_syms: int, k: int, n: int, d_out: int, d_status: int = 0,

@@ -57,6 +57,9 @@ extern "C" {
     pub fn msbwt_pack_kmers_device(idx: *const msbwt_index, slot: c_int, d_syms: *const u8, k: u32, n: u64, d_packed: *mut u64, d_out: *mut u64, d_status: *mut u32, stream: *mut c_void) -> c_int;
     pub fn msbwt_count_kmers_packed_device(idx: *const msbwt_index, slot: c_int, d_packed: *const u64, k: u32, n: u64, d_out: *mut u64, stream: *mut c_void) -> c_int;
     pub fn msbwt_constrain_ranges_device(idx: *const msbwt_index, slot: c_int, d_sym: *const u8, d_l: *const u64, d_h: *const u64, n: u64, d_out_l: *mut u64, d_out_h: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn msbwt_constrain_ranges_fanout(idx: *const msbwt_index, l: *const u64, h: *const u64, n: u64, out_l: *mut u64, out_h: *mut u64) -> c_int;
+    pub fn msbwt_constrain_ranges_fanout_device(idx: *const msbwt_index, slot: c_int, d_l: *const u64, d_h: *const u64, n: u64, d_out_l: *mut u64, d_out_h: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn msbwt_count_read_kmers(idx: *const msbwt_index, reads: *const u8, read_len: u32, n_reads: u64, k: u32, strands: u32, out: *mut u64) -> c_int;
     pub fn msbwt_launch_count() -> u64;
     pub fn msbwt_l2_fetch_granularity(device: c_int, bytes: c_int) -> c_int;
     pub fn msbwt_host_alloc(bytes: usize) -> *mut c_void;
