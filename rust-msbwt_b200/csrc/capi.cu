@@ -1227,14 +1227,9 @@ extern "C" int msbwt_count_read_kmers(const msbwt_index *idx, const uint8_t *rea
     const size_t ndev = idx->reps.size();
     std::vector<std::unique_lock<std::mutex>> locks;
     for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
-    // validation first, as count_kmer does (src/msbwt_core.rs:127): no output is written for a bad batch
-    {
-        const uint64_t bytes = n_reads * read_len;
-        for (uint64_t i = 0; i < bytes; i++)
-            if (reads[i] >= kAlphabet)
-                return fail(MSBWT_EINVAL, "count_read_kmers: read " + std::to_string(i / read_len) + " holds a symbol >= 6");
-    }
-    const uint64_t chunk = std::max<uint64_t>(1, kChunkQueries / per_read_q);  // reads per chunk
+    // symbols are validated where they are packed (count_kmer's own check, src/msbwt_core.rs:127): the pack
+    // kernel flags any symbol >= 6 and the call then returns EINVAL
+    const uint64_t chunk = std::max<uint64_t>(1, 4 * kChunkQueries / per_read_q);  // reads per chunk
     uint64_t max_chunks = 0;
     for (size_t d = 0; d < ndev; d++) {
         Replica &rep = *idx->reps[d];
@@ -1242,6 +1237,7 @@ extern "C" int msbwt_count_read_kmers(const msbwt_index *idx, const uint8_t *rea
         const Slice sl = slice_for(n_reads, d, ndev);
         const uint64_t len = sl.end - sl.begin, c = std::max<uint64_t>(1, std::min(chunk, len));
         max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
+        CU_TRY(cudaMemset(rep.d_status, 0, kLanes * sizeof(uint32_t)));
         for (int li = 0; li < 2; li++) {
             Lane &ln = rep.lane[li];
             CU_TRY(cudaStreamSynchronize(ln.stream));
@@ -1266,7 +1262,6 @@ extern "C" int msbwt_count_read_kmers(const msbwt_index *idx, const uint8_t *rea
             CU_TRY(cudaMemcpyAsync(ln.in_a.p, reads + b * read_len, m * read_len, cudaMemcpyHostToDevice, ln.stream));
             CU_TRY(launch_expand_read_kmers(rep.device, ln.in_a.as<uint8_t>(), read_len, m, k, strands, ln.in_b.as<uint8_t>(), ln.stream));
             g_launches++;
-            CU_TRY(cudaMemsetAsync(flag, 0, sizeof(uint32_t), ln.stream));
             CU_TRY(launch_pack_seed(rep.view, ln.in_b.as<uint8_t>(), k, nq, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(), flag, ln.stream));
             g_launches++;
             CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, nq, ln.out_a.as<uint64_t>(),
@@ -1286,10 +1281,11 @@ extern "C" int msbwt_count_read_kmers(const msbwt_index *idx, const uint8_t *rea
     for (auto &rep : idx->reps) {
         DeviceGuard guard(rep->device);
         for (int li = 0; li < 2; li++) CU_TRY(cudaStreamSynchronize(rep->lane[li].stream));
+        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, kLanes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
     g_last_h2d = h2d;
     g_last_d2h = d2h;
-    return MSBWT_OK;
+    return check_status_flags(idx, "count_read_kmers");
 }
 
 // ================================================================ construction of the BWT itself
