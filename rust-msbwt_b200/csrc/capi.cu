@@ -929,6 +929,19 @@ extern "C" int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, co
 
     std::vector<std::unique_lock<std::mutex>> locks;
     for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
+    // A batch whose k-mers all have the same length -- what `count_kmers(&[Vec<u8>])` is called with in a k-mer
+    // counting loop -- is the fixed-k batch laid out contiguously: it takes the packed / table-seeded route.
+    {
+        const uint64_t k0 = offsets[1] - offsets[0];
+        bool uniform = k0 > 0 && k0 <= 0xFFFFFFFFull;
+        for (uint64_t i = 1; uniform && i < n; i++) uniform = offsets[i + 1] - offsets[i] == k0;
+        if (uniform) {
+            g_last_h2d = g_last_d2h = 0;
+            const uint8_t *base = syms + offsets[0];
+            return use_host_pack((uint32_t)k0, n) ? fixed_packed_path(idx, base, (uint32_t)k0, n, out)
+                                                  : fixed_bytes_path(idx, base, (uint32_t)k0, n, out);
+        }
+    }
     for (auto &rep : idx->reps) {
         DeviceGuard guard(rep->device);
         CU_TRY(cudaMemsetAsync(rep->d_status, 0, kLanes * sizeof(uint32_t), rep->lane[0].stream));

@@ -136,3 +136,20 @@ def test_count_read_kmers_refuses_bad_input(readset):
     with pytest.raises(M.MsbwtError):
         g.count_read_kmers(bad, 31)
     assert g.count_read_kmers(reads[:0], 31).shape == (0, 70)
+
+
+def test_ragged_batches_of_one_length_equal_the_fixed_call(readset):
+    """`count_kmers(&[Vec<u8>])` with k-mers of one length (the usual k-mer counting loop) is routed to the
+    fixed-k path (suffix table, packed queries); a batch of mixed lengths keeps the byte-wise path."""
+    reads, o, g = readset
+    q = windows_of(reads[:300], 31).copy()
+    q[5, 0] = 4
+    q[7, 30] = 0
+    kmers = [row for row in q]
+    want = o.count_kmers_fixed(q, 31, threads=8)
+    assert (g.count_kmers(kmers) == want).all()
+    assert (g.count_kmers_fixed(q, 31) == want).all()
+    mixed = kmers[:5000] + [q[0][:17], q[1][:1], q[2][:0]] + kmers[5000:6000]
+    assert (g.count_kmers(mixed) == o.count_kmers(mixed, threads=8)).all()
+    one = [q[3]]
+    assert g.count_kmers(one)[0] == want[3]
