@@ -410,15 +410,15 @@ def measure_ours(args, cfg, ctx, primary: bool):
             # 97 % of the time); the sector-granular figure is reported beside it.
             # with the oct image on top: eight calls per 128-B line while >= 8 symbols are left
             st = orc.count_kmers_stats_quad(q_host[:ms], k, table_s, QUAD_SYMS, LINE_BYTES // QUAD_SECTOR_BYTES, BLOCK_SHIFT,
-                                            bwt.oct_bucket_shift if bwt.oct_index else 0)
+                                            bwt.oct_bucket_shift if bwt.oct_index else 0, M.oct_symbols())
             hits = st["table_hits"]
-            oct_lines = st["oct_steps"] + st["two_bucket_oct_steps"]
+            oct_lines = st["oct_steps"]   # (a range over two buckets takes its symbols as quad / one-symbol steps: counted there)
             quad_lines = st["quad_steps"] + st["two_line_quad_steps"]
             quad_sectors = st["quad_steps"] + st["two_sector_quad_steps"]
             pair_lines = 0
             one_blocks = st["one_steps"] + st["two_block_one_steps"]
-            ref_steps = 8 * st["oct_steps"] + 4 * st["quad_steps"] + st["one_steps"]
-            two_share = (st["two_line_quad_steps"] + st["two_bucket_oct_steps"]) / max(1, st["quad_steps"] + st["oct_steps"])
+            ref_steps = M.oct_symbols() * st["oct_steps"] + 4 * st["quad_steps"] + st["one_steps"]
+            two_share = st["two_line_quad_steps"] / max(1, st["quad_steps"] + st["oct_steps"])
         elif pair:
             st = orc.count_kmers_stats_pair(q_host[:ms], k, table_s, PAIR_SYMS, BLOCK_SHIFT)
             hits = st["table_hits"]
@@ -448,7 +448,7 @@ def measure_ours(args, cfg, ctx, primary: bool):
             "kernel_ms": 1e3 * kern_s, "algorithmic_bytes_per_launch": bytes_per_query * n,
             "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": ref_steps / ms,
             "oct_lines_per_query": oct_lines / ms, "oct_overflow_lines": bwt.oct_overflow_lines,
-            "oct_overflow_position_share": bwt.oct_overflow_occurrences / max(1, total), "oct_bucket_shift": bwt.oct_bucket_shift,
+            "oct_overflow_position_share": bwt.oct_overflow_occurrences / max(1, total), "oct_bucket_shift": bwt.oct_bucket_shift, "oct_symbols_per_line": M.oct_symbols(),
             "quad_lines_per_query": quad_lines / ms, "quad_sectors_per_query": quad_sectors / ms,
             "achieved_sector_granular": sector_bytes_per_query * n / kern_s / 1e9,
             "pair_lines_per_query": pair_lines / ms, "one_step_blocks_per_query": one_blocks / ms,

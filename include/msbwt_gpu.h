@@ -90,13 +90,14 @@ msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *
  * 32-byte sectors (layout.h), FOUR constrain_range steps per line fill, 256*N/7 bytes -- replaces the
  * pair image (-1 = automatic: the index lives in HBM and the image is <= 64 GB and <= half the free
  * device memory; MSBWT_QUAD_INDEX=0|1 overrides), 0 = never, 1 = always.  Results are identical.
- * `oct_index`: the OCT image -- one 128-byte line of explicit occurrence RUNS per (8-symbol code, 2^b-position
- * bucket), EIGHT constrain_range steps per line fill, 2^(23-b) bytes per symbol -- is built next to the quad
- * image when positions are 32-bit (-1 = automatic: whenever the quad image is built and the oct image fits a
- * quarter of the device memory left; MSBWT_OCT_INDEX=0|1 overrides), 0 = never, 1 = always (implies
- * quad_index).  Lines that cannot hold their bucket's runs are answered through the quad image, so results
- * are identical on any input.  `oct_bucket_shift`: b, 8..23 (0 = automatic: the largest b that keeps the mean
- * number of runs per line <= 6). */
+ * `oct_index`: the OCT image -- one 128-byte line of explicit occurrence RUNS per (m-symbol code, 2^b-position
+ * bucket), m = msbwt_oct_symbols() = 10 constrain_range steps per line fill, 128 * 4^m * (N / 2^b + 1) bytes --
+ * is built next to the quad image when positions are 32-bit (-1 = automatic: whenever the quad image is built
+ * and the oct image fits a quarter of the device memory left; MSBWT_OCT_INDEX=0|1 overrides), 0 = never,
+ * 1 = always (implies quad_index).  Lines that cannot hold their bucket's runs are answered through the quad
+ * image, so results are identical on any input.  `oct_bucket_shift`: b, 8..24 (0 = automatic: the largest b
+ * that keeps the mean number of runs per line <= 6).  Under an oct image the automatic suffix-table depth is
+ * 14 with levels 11..13 kept: a 31-mer is one L2-resident table entry (depth 11) + two oct lines. */
 typedef struct msbwt_options {
     uint32_t struct_size;
     uint32_t superblock_shift; /* 0 = default */
@@ -129,8 +130,9 @@ int msbwt_quad_index(const msbwt_index *idx); /* 1 when the quad image is in use
 int msbwt_oct_index(const msbwt_index *idx);  /* 1 when the oct image is in use (next to the quad image) */
 uint64_t msbwt_oct_overflow_lines(const msbwt_index *idx); /* oct lines answered through the quad image */
 uint64_t msbwt_oct_overflow_occurrences(const msbwt_index *idx); /* BWT positions those lines cover */
-uint64_t msbwt_oct_runs(const msbwt_index *idx);           /* runs of equal 8-symbol codes in the BWT (chose b) */
+uint64_t msbwt_oct_runs(const msbwt_index *idx);           /* runs of equal m-symbol codes in the BWT (chose b) */
 int msbwt_oct_bucket_shift(const msbwt_index *idx);        /* b of the oct image in use, 0 without one */
+int msbwt_oct_symbols(void);                               /* m: symbols (constrain_range steps) per oct line */
 
 /* ---- queries from HOST buffers (the drop-in calls) ---- */
 
@@ -250,7 +252,7 @@ int msbwt_constrain_ranges_fanout_device(const msbwt_index *idx, int slot, const
 int msbwt_count_read_kmers(const msbwt_index *idx, const uint8_t *reads, uint32_t read_len, uint64_t n_reads,
                            uint32_t k, uint32_t strands, uint64_t *out /* n_reads * (read_len-k+1) */);
 
-/* The oct image of a replica: 65536 * *nbuck8 lines of 32 u32 words, code-major (nbuck8 = (N >> b) + 1).
+/* The oct image of a replica: 4^m * *nbuck8 lines of 32 u32 words, code-major (nbuck8 = (N >> b) + 1).
  * NULL array: size only. */
 int msbwt_debug_copy_oct_image(const msbwt_index *idx, int slot, uint64_t *nbuck8, uint32_t *lines);
 

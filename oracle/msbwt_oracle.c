@@ -528,19 +528,24 @@ int orc_count_kmers_stats_pair(const orc_rle_bwt *b, const uint8_t *syms, uint32
 int orc_count_kmers_stats_quad(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
                                uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
                                unsigned block_shift, uint64_t *out) {
-    return orc_count_kmers_stats_oct(b, syms, k, n, table_s, sector_syms, line_sectors, block_shift, 0, out);
+    return orc_count_kmers_stats_oct(b, syms, k, n, table_s, sector_syms, line_sectors, block_shift, 0, 0, out);
 }
 
-/* The same with an OCT image on top (oct_bucket_shift != 0): while eight or more symbols are left a step
- * reads one line of the (code, 2^oct_bucket_shift-position bucket) it needs -- two when l and h fall in
- * different buckets.  out[7] = oct steps, out[8] = oct steps over two buckets.  (Lines the engine answers
- * through the quad image because they overflowed are not modelled: msbwt_oct_overflow_lines reports how
- * many exist.) */
+/* The same with an OCT image on top (oct_bucket_shift != 0; oct_syms symbols per line, 8 or 10): the table depth
+ * is the one of the four kept levels that leaves the cheapest walk (kernel_common.cuh: one access per oct or
+ * quad step, two per one-symbol step); while oct_syms or more symbols are left a step reads one line of the
+ * (code, 2^oct_bucket_shift-position bucket) it needs -- when l and h fall in different buckets the same
+ * symbols are taken as quad steps (and one-symbol steps for what four does not divide).  out[7] = oct steps,
+ * out[8] = two-bucket events.  (Lines the engine answers without the oct image because they overflowed are not
+ * modelled: msbwt_oct_overflow_lines reports how many exist.) */
+static uint32_t oct_walk_cost(uint32_t rest, uint32_t m) { const uint32_t r = rest % m; return rest / m + r / 4u + 2u * (r % 4u); }
+
 int orc_count_kmers_stats_oct(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
                               uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
-                              unsigned block_shift, unsigned oct_bucket_shift, uint64_t *out) {
+                              unsigned block_shift, unsigned oct_bucket_shift, unsigned oct_syms, uint64_t *out) {
     uint64_t qs = 0, q2s = 0, q2l = 0, os = 0, o2 = 0, hits = 0, es = 0, e2 = 0;
     const uint64_t line_syms = (uint64_t)sector_syms * line_sectors;
+    const uint32_t m = oct_bucket_shift ? (oct_syms ? oct_syms : 8u) : 0u;
     for (uint64_t i = 0; i < n; i++) {
         const uint8_t *q = syms + i * (uint64_t)k;
         int all_acgt = 1;
@@ -555,8 +560,16 @@ int orc_count_kmers_stats_oct(const orc_rle_bwt *b, const uint8_t *syms, uint32_
         uint32_t done = 0;
         if (all_acgt) {
             if (table_s && k >= table_s) {
-                const uint32_t back = (4u - (k - table_s) % 4u) % 4u;
-                done = back < table_s ? table_s - back : 0;
+                if (m) {
+                    uint32_t best_cost = oct_walk_cost(k, m);
+                    for (uint32_t back = 0; back < 4u && back < table_s; back++) {
+                        const uint32_t c = oct_walk_cost(k - (table_s - back), m);
+                        if (c < best_cost) { best_cost = c; done = table_s - back; }
+                    }
+                } else {
+                    const uint32_t back = (4u - (k - table_s) % 4u) % 4u;
+                    done = back < table_s ? table_s - back : 0;
+                }
             } else if (table_s && k + 4 > table_s) {
                 done = k;
             }
@@ -565,28 +578,31 @@ int orc_count_kmers_stats_oct(const orc_rle_bwt *b, const uint8_t *syms, uint32_
         }
         hits += done != 0;
         orc_range r = { 0, b->total_size };
-        uint32_t t = k;
+        uint32_t t = k, forced = 0;
         for (uint32_t c = 0; c < done; c++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
-        if (all_acgt && oct_bucket_shift) {
-            while (t >= 8 && r.h != r.l) {
-                es++;
-                if ((r.l >> oct_bucket_shift) != (r.h >> oct_bucket_shift)) e2++;
-                for (int u = 0; u < 8; u++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
+        while (t >= 1 && r.h != r.l) {
+            if (all_acgt && m && t >= m && forced == 0) {
+                if ((r.l >> oct_bucket_shift) == (r.h >> oct_bucket_shift)) {
+                    es++;
+                    for (uint32_t u = 0; u < m; u++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
+                    continue;
+                }
+                e2++;
+                forced = m;
             }
-        }
-        if (all_acgt) {
-            while (t >= 4 && r.h != r.l) {
+            if (all_acgt && t >= 4 && (forced == 0 || forced >= 4)) {
                 qs++;
                 if (r.l / sector_syms != r.h / sector_syms) q2s++;
                 if (r.l / line_syms != r.h / line_syms) q2l++;
                 for (int u = 0; u < 4; u++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
+                forced = forced >= 4 ? forced - 4 : 0;
+                continue;
             }
-        }
-        while (t >= 1 && r.h != r.l) {
             os++;
             if ((r.l >> block_shift) != (r.h >> block_shift)) o2++;
             r = orc_constrain_range(b, q[t - 1], r);
             t--;
+            if (forced) forced--;
         }
     }
     out[0] = qs; out[1] = q2s; out[2] = q2l; out[3] = os; out[4] = o2; out[5] = hits; out[6] = n;

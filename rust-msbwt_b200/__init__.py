@@ -26,6 +26,7 @@ from .rle_bwt import (  # noqa: F401
     EXPORTED_SYMBOLS,
     library_path,
     load_library,
+    oct_symbols,
     reverse_complement_i,
 )
 from . import build as _build  # noqa: F401

@@ -139,6 +139,7 @@ struct DeviceGuard {
 };
 
 constexpr int kStatusWords = 8, kStatusDev = 7;
+constexpr int kOctAutoTableS = 14;  // automatic suffix-table depth under an oct image (levels 11..14 are kept)
 constexpr uint64_t kChunkQueries = 1ull << 20;  // host-path pipeline granularity (byte route)
 constexpr uint64_t kPackedChunkQueries = 1ull << 19;  // packed route: smaller chunks fill / drain the pipeline sooner
 constexpr uint64_t kChunkBytes = 1ull << 27;
@@ -376,7 +377,7 @@ int build_quad(msbwt_index *idx, Replica &rep, int oct_requested, int oct_shift)
     int n = 0;
     int rc = build_quad_image_on_device(rep.device, rep.view, codes2, rep.quad, why, &n, want_oct ? &codes4 : nullptr);
     g_launches += (uint64_t)n;
-    cudaFree(codes2);
+    struct Codes2 { uint8_t *p; ~Codes2() { if (p) cudaFree(p); } } codes2_owner{codes2};  // the oct builder reads them too
     if (idx->reps[0].get() == &rep) idx->bytes_per_replica -= pair_image_bytes(rep.pair);
     free_pair_image(rep.pair);
     rep.view.pair = nullptr;
@@ -396,13 +397,13 @@ int build_quad(msbwt_index *idx, Replica &rep, int oct_requested, int oct_shift)
         n = 0;
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
-        // the 8-symbol codes (4 B per position) are scratch of the build and must fit next to the image
+        // the kOctSyms-symbol codes (4 B per position) are scratch of the build and must fit next to the image
         const uint64_t scratch = 4 * rep.view.total;
         const uint64_t budget = oct_requested == 1 ? (free_b > scratch ? free_b - scratch : 0)
                                                    : (free_b / 2 > scratch ? std::min<uint64_t>(free_b / 4, free_b / 2 - scratch) : 0);
         if (!oct_shift)
             if (const char *env = getenv("MSBWT_OCT_BUCKET_SHIFT")) oct_shift = atoi(env);
-        rc = build_oct_image_on_device(rep.device, rep.view, codes4, oct_shift, budget, rep.oct, why, &n);  // frees codes4
+        rc = build_oct_image_on_device(rep.device, rep.view, codes4, codes2, oct_shift, budget, rep.oct, why, &n);  // frees codes4
         g_launches += (uint64_t)n;
         if (rc != MSBWT_OK) { free_oct_image(rep.oct); return fail(rc, why); }
         if (rep.oct.lines) {
@@ -512,6 +513,9 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
                     const uint64_t multi = quad ? (uint64_t)kQuadCodes * rep->quad.nsec4 * kQuadSectorBytes
                                                 : rep->view.npair * kPairBytes;
                     s = deepen_table_for_hbm(s0, idx->reps[0]->view.nblocks * kBlockBytes + multi, wide ? 16 : 8);
+                    // with ten symbols per oct line a 31-mer wants the depth-11 level (33 MB, L2-resident): the
+                    // deepest of the four kept levels need not go beyond 14 (2.1 GB instead of 8.6 GB at 15)
+                    if (rep->view.oct) s = std::min(s, kOctAutoTableS);
                 }
             }
             rc = build_suffix_table(idx.get(), *rep, s);
@@ -611,6 +615,7 @@ extern "C" int msbwt_oct_index(const msbwt_index *idx) { return (idx && !idx->re
 extern "C" uint64_t msbwt_oct_overflow_lines(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.overflow_lines : 0; }
 extern "C" uint64_t msbwt_oct_overflow_occurrences(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.overflow_occurrences : 0; }
 extern "C" uint64_t msbwt_oct_runs(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.runs : 0; }
+extern "C" int msbwt_oct_symbols(void) { return kOctSyms; }
 extern "C" int msbwt_oct_bucket_shift(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.oct) ? (int)idx->reps[0]->view.oct_shift : 0; }
 extern "C" uint64_t msbwt_launch_count(void) { return g_launches.load(); }
 extern "C" const char *msbwt_last_error(void) { return g_last_error.c_str(); }

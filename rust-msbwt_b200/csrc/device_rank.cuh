@@ -321,71 +321,4 @@ __device__ __forceinline__ void quad_step(const IndexView &ix, const C4Base<WIDE
     h = c4.at(sh, code) + b.w[0] + sector_count_below(b, ph);
 }
 
-// ---- oct image (layout.h): eight constrain_range steps per 128-byte line (32-bit positions only)
-
-struct OctLine { Half s[4]; };
-
-__device__ __forceinline__ OctLine ldg_oct_line(const IndexView &ix, uint32_t code, uint32_t bucket) {
-    const char *p = reinterpret_cast<const char *>(ix.oct) + ((size_t)code * ix.nbuck8 + bucket) * kOctLineBytes;
-    OctLine v;
-#pragma unroll
-    for (int i = 0; i < 4; i++) v.s[i] = ldg_index256(p + 32 * i);
-    return v;
-}
-
-// occurrences of the line's code below bucket offsets pl / ph: sum over the stored runs `(len << b) | off`
-// of clamp(p - off, 0, len); empty slots are 0 and add nothing.  `nruns` (word 1) tells which sectors of
-// the line hold runs at all (slots fill in order).
-__device__ __forceinline__ void oct_count_below(const OctLine &v, uint32_t b, int pl, int ph, uint32_t &cl, uint32_t &ch) {
-    const uint32_t mask = (1u << b) - 1u;
-    const uint32_t nruns = v.s[0].w[1];
-    int sl = 0, sh = 0;
-    auto add = [&](uint32_t e) {
-        const int off = (int)(e & mask), len = (int)(e >> b);
-        sl += min(max(pl - off, 0), len);
-        sh += min(max(ph - off, 0), len);
-    };
-#pragma unroll
-    for (int w = 2; w < 8; w++) add(v.s[0].w[w]);
-    if (nruns > 6u) {
-#pragma unroll
-        for (int w = 0; w < 8; w++) add(v.s[1].w[w]);
-        if (nruns > 14u) {
-#pragma unroll
-            for (int w = 0; w < 8; w++) add(v.s[2].w[w]);
-            if (nruns > 22u) {
-#pragma unroll
-                for (int w = 0; w < 8; w++) add(v.s[3].w[w]);
-            }
-        }
-    }
-    cl = (uint32_t)sl;
-    ch = (uint32_t)sh;
-}
-
-// Eight constrain_range steps at once: code = the eight symbols as base-4 digits, the first consumed one
-// most significant.  Returns false -- l, h untouched -- when a line involved holds more runs than it
-// can store; the caller then takes two quad steps instead.
-__device__ __forceinline__ bool oct_step(const IndexView &ix, uint32_t code, uint32_t &l, uint32_t &h) {
-    const uint32_t b = ix.oct_shift, mask = (1u << b) - 1u;
-    const uint32_t bl = l >> b, bh = h >> b;
-    const OctLine a = ldg_oct_line(ix, code, bl);
-    uint32_t cl, ch;
-    if (bh == bl) {
-        if (a.s[0].w[1] > (uint32_t)kOctCapacity) return false;
-        oct_count_below(a, b, (int)(l & mask), (int)(h & mask), cl, ch);
-        l = a.s[0].w[0] + cl;
-        h = a.s[0].w[0] + ch;
-        return true;
-    }
-    const OctLine c = ldg_oct_line(ix, code, bh);  // a range across a bucket boundary: rare
-    if (a.s[0].w[1] > (uint32_t)kOctCapacity || c.s[0].w[1] > (uint32_t)kOctCapacity) return false;
-    uint32_t unused;
-    oct_count_below(a, b, (int)(l & mask), 0, cl, unused);
-    oct_count_below(c, b, (int)(h & mask), 0, ch, unused);
-    l = a.s[0].w[0] + cl;
-    h = c.s[0].w[0] + ch;
-    return true;
-}
-
 }  // namespace msbwt

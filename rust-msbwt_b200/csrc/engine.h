@@ -87,11 +87,12 @@ struct OctImage {
 };
 uint64_t oct_image_bytes(uint64_t total, int shift);
 // `ix` must carry the one-step blocks and the quad image, N < 2^32 with one superblock; `d_codes4` = the
-// quad builder's keep_codes, OWNED by this call (freed as soon as the 8-symbol codes exist).
+// quad builder's keep_codes, OWNED by this call (freed as soon as the kOctSyms-symbol codes exist); `d_codes2`
+// = the pair builder's keep_codes (borrowed).
 // `requested_shift` 0 = automatic (layout.h).  When even the coarsest buckets exceed `max_bytes` nothing is
 // built (img.lines stays null) and MSBWT_OK is returned.
-int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes4, int requested_shift,
-                              uint64_t max_bytes, OctImage &img, std::string &why, int *launches);
+int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes4, const uint8_t *d_codes2,
+                              int requested_shift, uint64_t max_bytes, OctImage &img, std::string &why, int *launches);
 void free_oct_image(OctImage &img);
 
 // ---- bwt_build.cu: equal-length reads (device) -> RLE bytes of their multi-string BWT (device) ----

@@ -24,6 +24,30 @@ __host__ __device__ __forceinline__ uint32_t acgt_table_depth(uint32_t k, uint32
     return k + stride > ts ? k : 0;  // level k itself is one of the kept ones: the table answers everything
 }
 
+// With an oct image (kOctSyms symbols per line, quad steps of four for what is left, one-symbol steps for the
+// rest) the depth is the one of the four kept levels {ts, .., ts-3} that leaves the cheapest walk: one index
+// access per oct and per quad step, two per one-symbol step (a one-step block per boundary); ties go to the
+// deeper level.
+__host__ __device__ __forceinline__ uint32_t oct_walk_cost(uint32_t rest) {
+    const uint32_t r = rest % (uint32_t)kOctSyms;
+    return rest / (uint32_t)kOctSyms + r / 4u + 2u * (r % 4u);
+}
+__host__ __device__ __forceinline__ uint32_t oct_table_depth(uint32_t k, uint32_t ts) {
+    if (!ts) return 0;
+    if (k < ts) return k + 4u > ts ? k : 0;  // level k itself is one of the kept ones: the table answers everything
+    uint32_t best = 0, best_cost = oct_walk_cost(k);
+    for (uint32_t back = 0; back < 4u && back < ts; back++) {
+        const uint32_t c = oct_walk_cost(k - (ts - back));
+        if (c < best_cost) { best_cost = c; best = ts - back; }
+    }
+    return best;
+}
+
+// The depth the pack / seed kernels look an all-ACGT k-mer up at, and the search kernels resume from.
+__host__ __device__ __forceinline__ uint32_t list_a_table_depth(const IndexView &ix, uint32_t k) {
+    return ix.oct ? oct_table_depth(k, ix.table_s) : acgt_table_depth(k, ix.table_s, list_a_stride(ix));
+}
+
 inline int sm_count(int device) {
     static int cached[64];
     if (device < 0 || device >= 64) return 148;

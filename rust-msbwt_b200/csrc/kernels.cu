@@ -80,7 +80,7 @@ __device__ __forceinline__ void seed_acgt(const IndexView &ix, uint32_t k, uint3
                                           uint32_t &flag, bool &list_a, bool &finished, uint64_t &word0) {
     const uint32_t ts = ix.table_s;
     const uint32_t stride = list_a_stride(ix);
-    const uint32_t done = acgt_table_depth(k, ts, stride);
+    const uint32_t done = list_a_table_depth(ix, k);
     // the quad kernel finishes a remainder with one-step ranks; the pair kernel cannot
     list_a = stride != 2u || ((k - done) & 1u) == 0;
     lo = 0; hi = ix.total; flag = 0;

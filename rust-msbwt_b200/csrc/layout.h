@@ -127,38 +127,45 @@ constexpr int kQuadCodes = 256;
 constexpr int kQuadMaxSuperShift = 24;  // 2^24 sectors * 224 positions < 2^32
 constexpr int kQuadMaxSuperInSmem = 8;  // rows of 256 u64 staged in shared memory (16 KB)
 
-// ---- oct ("eight-step") lines ---------------------------------------------------------------
+// ---- oct lines: kOctSyms steps per line --------------------------------------------------------
 //
-// One more composition: code8(j) = code4(j) * 256 + code4(LF^4(j)) (valid when both halves are), and
+// One more composition (m = kOctSyms = 10 symbols; the image began with eight, hence the name):
+// code_m(j) = the m symbols B[j], B[LF j], .., B[LF^(m-1) j] as base-4 digits, the first most significant
+// (valid when all are ACGT), and
 //
-//     eight successive constrain_range calls applied to i  ==  C8[c] + #{ j < i : code8(j) == c }.
+//     m successive constrain_range calls applied to i  ==  Cm[c] + #{ j < i : code_m(j) == c }.
 //
-// 65536 codes: a bit-vector per code is out of reach, but each code is rare (one position in 65536 on a
-// random text) and on a read set its occurrences come in RUNS of consecutive BWT positions: the suffixes
-// that share a long prefix -- the reads covering one genome position -- sit next to each other and are
-// preceded by the same eight symbols (mean run 11 on error-free 30x reads, 3 with 1 % errors).  So the
-// occurrences are stored explicitly as runs.  BWT positions are cut into buckets of 2^b (b = the
-// image's bucket shift, chosen when it is built); one 128-byte line per (code, bucket), code-major
-// (`address = (c * nbuck8 + (pos >> b)) * 128`):
+// 4^m codes: a bit-vector per code is out of reach, but each code is rare and on a read set its occurrences
+// come in RUNS of consecutive BWT positions: the suffixes that share a long prefix -- the reads covering
+// one genome position -- sit next to each other and are preceded by the same m symbols (mean run 11 on
+// error-free 30x reads, 3 with 1 % errors).  So the occurrences are stored explicitly as runs.  BWT
+// positions are cut into buckets of 2^b (b = the image's bucket shift, chosen when it is built); one
+// 128-byte line per (code, bucket), code-major (`address = (c * nbuck8 + (pos >> b)) * 128`):
 //
-//     word 0      u32 checkpoint: C8[c] + #{ j < bucket start : code8(j) == c }   (N < 2^32 only)
+//     word 0      u32 checkpoint: Cm[c] + #{ j < bucket start : code_m(j) == c }   (N < 2^32 only)
 //     word 1      u32 number of runs of c in the bucket
 //     word 2..31  up to 30 runs `(len << b) | offset within the bucket`, any order; unused words are 0
 //
-// rank8(c, p) = word0 + sum over runs of clamp((p & (2^b-1)) - offset, 0, len): one line fill, no order
+// rank_m(c, p) = word0 + sum over runs of clamp((p & (2^b-1)) - offset, 0, len): one line fill, no order
 // needed.  A run never crosses a multiple of 2^cs, cs = oct_chunk_shift(b) <= b, so len <= 2^cs fits its
 // 32-b bits and no run crosses a bucket.  When a bucket holds more than 30 runs of one code (word 1 > 30:
-// low-complexity text) the kernel falls back to two quad steps for that query-step, so the result is
-// exact on any input.  128 * 65536 * (N / 2^b + 1) bytes = 2^(23-b) B/symbol; b is the largest shift that
-// keeps the mean number of runs per line <= kOctTargetRuns (b = 20, 8 B/symbol, on 30x reads with 1 %
-// errors: 0.7 % of the positions sit on overflowed lines; 7 % at b = 21).  Built only next to a quad image (which also serves remainders of 4..7 symbols) and only when
+// low-complexity text) the kernel falls back to quad / one-step ranks for that query-step, so the result is
+// exact on any input.  128 * 4^m * (N / 2^b + 1) bytes; b is the largest shift that keeps the mean number of
+// runs per line <= kOctTargetRuns (b = 24, 8 B/symbol, on 30x reads with 1 % errors), never below one bucket
+// (128 MB).  Built only next to a quad image (which also serves remainders of 4..m-1 symbols) and only when
 // N < 2^32.
-constexpr int kOctCodes = 65536;
+//
+// Why ten: a 31-mer then is a suffix-table entry at depth 11 -- 4^11 entries of 8 bytes = 33 MB, resident in
+// L2 -- plus TWO lines: two HBM requests per query instead of three with eight symbols per line and a
+// depth-15 table (8.6 GB, one HBM request per lookup).
+constexpr int kOctSyms = 10;
+constexpr int kOctCodeBits = 2 * kOctSyms;
+constexpr int kOctCodes = 1 << kOctCodeBits;
 constexpr int kOctLineBytes = 128;
 constexpr int kOctLineWords = 32;
 constexpr int kOctCapacity = 30;      // runs per line
-constexpr int kOctMinShift = 8, kOctMaxShift = 23;
-constexpr int kOctAutoMinShift = 16;  // automatic choice: 16..23 (128 B/symbol .. 1 B/symbol)
+constexpr int kOctMinShift = 8, kOctMaxShift = 24;
+constexpr int kOctAutoMinShift = 16;  // automatic choice: 16..24
 constexpr int kOctTargetRuns = 6;
 __host__ __device__ constexpr int oct_chunk_shift(int b) {  // cs = min(31 - b, 10, b)
     int c = 31 - b;

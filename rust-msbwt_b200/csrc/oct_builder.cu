@@ -3,11 +3,12 @@
 //
 // The reference has no counterpart (its index is the sampled table of construct_fmindex,
 // src/rle_bwt.rs:387-467); what the oct image must reproduce is the composition of eight
-// RleBWT::constrain_range calls (src/rle_bwt.rs:202-287); layout.h states the identity.
+// RleBWT::constrain_range calls (src/rle_bwt.rs:202-287) -- kOctSyms of them since the image holds ten
+// symbols per line; layout.h states the identity.
 //
-//   1. code8  : one thread per BWT position j with a valid quad code a: LF^4(j) = rank4(a, j) through the
-//               quad image (one sector), b = code4(LF^4(j)) (one random read); code8(j) = a*256+b when b is
-//               valid too.
+//   1. codes  : one thread per BWT position j with a valid quad code a: j4 = LF^4(j) = rank4(a, j) through the
+//               quad image (one sector), b = code4(j4) (one random read), j8 = rank4(b, j4), c = the pair code
+//               (two symbols) at j8; code(j) = a * 4^6 + b * 4^2 + c when all three are valid.
 //   2. count  : run heads (code8 changes) are counted; the bucket shift b is the largest one that keeps the
 //               mean number of runs per line <= kOctTargetRuns (and the image within the caller's budget).
 //   3. emit   : every run head (also forced at multiples of 2^cs, layout.h) walks to the end of its run and
@@ -17,7 +18,7 @@
 //   4. stamp  : one warp per code: exclusive prefix sum of the occurrence counts over the code's buckets,
 //               plus C8[code]; lines holding more than kOctCapacity runs are counted (the kernel answers
 //               those through the quad image).
-//   C8[c] = eight constrain_range calls of our own kernel applied to position 0.
+//   Cm[c] = kOctSyms constrain_range calls of our own kernel applied to position 0.
 #include <algorithm>
 
 #include "../../include/msbwt_gpu.h"
@@ -28,9 +29,12 @@ namespace msbwt {
 
 namespace {
 
-constexpr uint32_t kValid8 = 0x10000u;
+static_assert(kOctSyms == 8 || kOctSyms == 10, "the code kernel composes quad codes (+ one pair code)");
+constexpr uint32_t kValid8 = 1u << kOctCodeBits;
+constexpr uint32_t kCodeMask = kValid8 - 1u;
 
 __global__ void __launch_bounds__(256) oct_code8_kernel(IndexView ix, const uint16_t *__restrict__ codes4,
+                                                        const uint8_t *__restrict__ codes2,
                                                         uint32_t *__restrict__ codes8) {
     const C4Base<false> c4{};
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
@@ -41,7 +45,16 @@ __global__ void __launch_bounds__(256) oct_code8_kernel(IndexView ix, const uint
             uint32_t l = (uint32_t)j, h = (uint32_t)j;
             quad_step<false>(ix, c4, a & 255u, l, h);  // l = LF^4(j)
             const uint32_t b = codes4[l];
-            if (b & 0x100u) v = kValid8 | ((a & 255u) << 8) | (b & 255u);
+            if (b & 0x100u) {
+                if constexpr (kOctSyms == 8) {
+                    v = kValid8 | ((a & 255u) << 8) | (b & 255u);
+                } else {
+                    h = l;
+                    quad_step<false>(ix, c4, b & 255u, l, h);  // l = LF^8(j)
+                    const uint32_t c = codes2[l];                // 16 | pair code (B[l], B[LF l]) when both are ACGT
+                    if (c & 16u) v = kValid8 | ((a & 255u) << 12) | ((b & 255u) << 4) | (c & 15u);
+                }
+            }
         }
         codes8[j] = v;
     }
@@ -71,7 +84,7 @@ __global__ void __launch_bounds__(256) oct_emit_kernel(const uint32_t *__restric
         if (!((j & chunk_mask) == 0 || codes8[j - 1] != v)) continue;
         uint32_t len = 1;
         while (j + len < total && ((j + len) & chunk_mask) != 0 && codes8[j + len] == v) len++;
-        uint32_t *line = lines + ((uint64_t)(v & 0xFFFFu) * nbuck8 + (j >> shift)) * kOctLineWords;
+        uint32_t *line = lines + ((uint64_t)(v & kCodeMask) * nbuck8 + (j >> shift)) * kOctLineWords;
         atomicAdd(line, len);
         const uint32_t slot = atomicAdd(line + 1, 1u);
         if (slot < (uint32_t)kOctCapacity) line[2 + slot] = (len << shift) | ((uint32_t)j & off_mask);
@@ -136,10 +149,10 @@ uint64_t oct_image_bytes(uint64_t total, int shift) {
     return (uint64_t)kOctCodes * ((total >> shift) + 1) * kOctLineBytes;
 }
 
-int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes4, int requested_shift,
-                              uint64_t max_bytes, OctImage &img, std::string &why, int *launches) {
+int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes4, const uint8_t *d_codes2,
+                              int requested_shift, uint64_t max_bytes, OctImage &img, std::string &why, int *launches) {
     struct Owned { uint16_t *p; ~Owned() { if (p) cudaFree(p); } } codes4{d_codes4};
-    if (!ix.quad || !d_codes4) { why = "oct image: needs the quad image and its codes"; return MSBWT_EINVAL; }
+    if (!ix.quad || !d_codes4 || !d_codes2) { why = "oct image: needs the quad image, its codes and the pair codes"; return MSBWT_EINVAL; }
     if (index_is_wide(ix)) { why = "oct image: only for indexes with 32-bit positions (N < 2^32, one superblock)"; return MSBWT_EINVAL; }
     if (requested_shift && (requested_shift < kOctMinShift || requested_shift > kOctMaxShift)) {
         why = "oct image: bucket shift out of range"; return MSBWT_EINVAL;
@@ -158,7 +171,7 @@ int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes
     O_TRY(cudaMemsetAsync(d_stat, 0, 3 * sizeof(unsigned long long)));
 
     // 1. code8 per position, 2. run heads
-    oct_code8_kernel<<<grid, 256>>>(ix, d_codes4, d_codes8);
+    oct_code8_kernel<<<grid, 256>>>(ix, d_codes4, d_codes2, d_codes8);
     O_TRY(cudaGetLastError());
     oct_count_runs_kernel<<<grid, 256>>>(d_codes8, ix.total, d_stat);
     O_TRY(cudaGetLastError());
@@ -189,13 +202,13 @@ int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes
     O_TRY(tmp.alloc(&d_sym, kOctCodes));
     O_TRY(tmp.alloc(&d_pos, 3 * (size_t)kOctCodes));
 
-    // C8[c]: the eight steps applied to position 0
+    // Cm[c]: the kOctSyms steps applied to position 0
     static const uint8_t acgt[4] = {1, 2, 3, 5};
     O_TRY(cudaMemsetAsync(d_pos, 0, 3 * (size_t)kOctCodes * sizeof(uint64_t)));
     uint64_t *cur = d_pos, *nxt = d_pos + kOctCodes, *spare = d_pos + 2 * (size_t)kOctCodes;
     std::vector<uint8_t> h_sym(kOctCodes);
-    for (int r = 0; r < 8; r++) {
-        for (int c = 0; c < kOctCodes; c++) h_sym[(size_t)c] = acgt[(c >> (2 * (7 - r))) & 3];
+    for (int r = 0; r < kOctSyms; r++) {
+        for (int c = 0; c < kOctCodes; c++) h_sym[(size_t)c] = acgt[(c >> (2 * (kOctSyms - 1 - r))) & 3];
         O_TRY(cudaMemcpy(d_sym, h_sym.data(), h_sym.size(), cudaMemcpyHostToDevice));
         O_TRY(launch_constrain_ranges(device, ix, d_sym, cur, cur, kOctCodes, nxt, spare, nullptr, launches));
         std::swap(cur, nxt);

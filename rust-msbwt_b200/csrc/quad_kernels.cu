@@ -5,7 +5,7 @@
 //
 // Replaces the reference's hot loop: BWT::count_kmer (src/msbwt_core.rs:125-161) calling
 // RleBWT::constrain_range (src/rle_bwt.rs:202-287) once per symbol -- here four or eight symbols per
-// index access (layout.h states the identities).
+// index access, ten with the oct image (layout.h states the identities).
 #include "device_rank.cuh"
 #include "engine.h"
 #include "kernel_common.cuh"
@@ -105,9 +105,9 @@ count_kmers_quad_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packe
 
 // ---------------------------------------------------------------- oct image on top of the quad image
 //
-// 32-bit positions only.  While eight or more symbols are left a step reads one 128-byte line of the oct
-// image (layout.h) instead of two quad sectors; the quad image serves remainders of 4..7 symbols, ranges
-// that straddle two oct buckets and the lines that overflowed (two quad steps instead of one oct step).
+// 32-bit positions only.  While kOctSyms (ten) or more symbols are left a step reads one 128-byte line of the
+// oct image (layout.h); the quad image (and one-symbol ranks) serve remainders, ranges that straddle two oct
+// buckets and the lines that overflowed (two quad steps + two one-symbol steps instead of one oct step).
 //
 // What HBM random access is bound by is the number of L2 requests that miss -- about 40 G/s whatever their
 // size (profiles/r1_gather_*.json) -- and what reaches that bound is the number of them in flight.  So:
@@ -174,16 +174,12 @@ __device__ __forceinline__ uint32_t staged_sector_rank(const uint4 &a, const uin
            __popc(b.w & below_mask(p - 192));
 }
 
-// TAIL: the batch ends with 1..3 one-symbol steps (k below the kept table levels); the out-of-line call is
-// compiled only into that instantiation.
-template <bool TAIL>
 __global__ void __launch_bounds__(kCountThreads, MSBWT_OCT_CTAS)
 count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, PackedLayout lay, uint32_t k,
                        uint64_t *__restrict__ out, uint32_t *__restrict__ work) {
     __shared__ __align__(16) uint8_t smem[(kCountThreads / 32) * kOctWarpSmem];
     __shared__ uint64_t cb_smem[4];
-    [[maybe_unused]] CBase<false> cb{nullptr};
-    if constexpr (TAIL) cb = stage_cbase<false>(ix, cb_smem);
+    const CBase<false> cb = stage_cbase<false>(ix, cb_smem);
     const uint64_t stream = policy_evict_first();
     constexpr uint32_t kFull = 0xffffffffu;
 
@@ -192,7 +188,7 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     if ((blockIdx.x * (kCountThreads / 32) + (threadIdx.x >> 5)) * 32u >= n) return;  // more warps than pools of work
     const uint64_t *w0 = packed + lay.w0(), *seeds = packed + lay.seed(), *wx = packed + lay.wx();
     const uint32_t *qidx = reinterpret_cast<const uint32_t *>(packed + lay.qidx());
-    const uint32_t rem0 = k - acgt_table_depth(k, ix.table_s, 4u);
+    const uint32_t rem0 = k - list_a_table_depth(ix, k);
     const uint32_t bshift = ix.oct_shift, bmask = (1u << bshift) - 1u;
     const char *const oct_base = reinterpret_cast<const char *>(ix.oct);
     const char *const quad_base = reinterpret_cast<const char *>(ix.quad);
@@ -239,9 +235,17 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     uint64_t word = 0, pend = 0;
     uint32_t q = 0;
     uint32_t rem = 0;     // symbols still to consume
-    int shift = 62;       // bit offset of the next symbol (2 bits) in `word`
+    int shift = 62;       // bit offset of the next symbol (2 bits) in `word`; negative: already inside `pend`
     uint32_t widx = 0;
-    uint32_t forced = 0;  // quad steps to take before the next oct step (after an overflowed line)
+    uint32_t forced = 0;  // quad steps to take instead of the next oct step (overflowed line / two buckets)
+
+    // the next `nsym` symbols as one code (first consumed most significant); a step may straddle two words
+    auto peek = [&](uint32_t nsym) -> uint32_t {
+        const int bits = 2 * (int)nsym, avail = shift + 2;  // avail >= 2 here
+        if (avail >= bits) return (uint32_t)(word >> (avail - bits)) & ((1u << bits) - 1u);
+        const int need = bits - avail;
+        return (uint32_t)(((word & ((1ull << avail) - 1ull)) << need) | (pend >> (64 - need)));
+    };
 
     for (;;) {
         // ---- RETIRE + REFILL (warp-uniform control)
@@ -285,26 +289,26 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                 return;  // nothing left to hand out and every lane is done
             }
         }
-        if (active && shift < 0) {  // 32 symbols per word; steps of 8 and 4 symbols never straddle two words
+        if (active && shift < 0) {  // 32 symbols per word: on to the next one (a step may have ended inside it)
             word = pend;
             widx++;
-            shift = 62;
-            if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + (uint64_t)widx * lay.n + q, stream);
+            shift += 64;
+            if (2u * rem > (uint32_t)(shift + 2)) pend = ldg_stream(wx + (uint64_t)widx * lay.n + q, stream);
         }
 
         // ---- ISSUE (branch-free): every lane publishes what its query needs, the warp fetches it
-        // (a range over two buckets takes the eight symbols as two quad steps as well: oct steps stay aligned
-        // to multiples of eight symbols and never straddle two words)
+        // (a range over two buckets, like an overflowed line, takes its kOctSyms symbols as quad steps and, for
+        // the last two of ten, one-symbol steps)
         const bool live = active && rem != 0 && l != h;
         const uint32_t bl = l >> bshift, bh = h >> bshift;
-        const bool want_oct = live && rem >= 8u && forced == 0u;
+        const bool want_oct = live && rem >= (uint32_t)kOctSyms && forced == 0u;
         const bool is_oct = want_oct && bl == bh;
-        const bool is_quad = live && !is_oct && rem >= 4u;
-        if (want_oct && !is_oct) forced = 2;
-        const uint32_t code16 = (uint32_t)(word >> (shift >= 14 ? shift - 14 : 0)) & 0xFFFFu;
-        const uint32_t code8 = (uint32_t)(word >> (shift >= 6 ? shift - 6 : 0)) & 255u;
+        if (want_oct && !is_oct) forced = (uint32_t)kOctSyms;  // symbols to take without the oct image
+        const bool is_quad = live && !is_oct && rem >= 4u && (forced == 0u || forced >= 4u);
+        const uint32_t codem = peek((uint32_t)kOctSyms);
+        const uint32_t code8 = peek(4u);
         const uint32_t sl = l / (uint32_t)kQuadSyms, sh = h / (uint32_t)kQuadSyms;
-        const char *p0 = is_oct ? oct_base + ((size_t)code16 * ix.nbuck8 + bl) * kOctLineBytes
+        const char *p0 = is_oct ? oct_base + ((size_t)codem * ix.nbuck8 + bl) * kOctLineBytes
                                 : quad_base + ((size_t)code8 * ix.nsec4 + sl) * kQuadSectorBytes;
         // low two bits: kind (1 oct, 2 quad, 0 nothing); the rest: byte distance from the sector of l to the sector of h
         const uint32_t meta = is_oct ? 1u : (is_quad ? (2u | ((sh - sl) * (uint32_t)kQuadSectorBytes)) : 0u);
@@ -330,7 +334,7 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         if (is_oct) {
             const uint4 a = my_row[0], b = my_row[1];
             if (a.y > (uint32_t)kOctCapacity) {
-                forced = 2;  // this line cannot hold its runs: the same eight symbols as two quad steps
+                forced = (uint32_t)kOctSyms;  // this line cannot hold its runs: the same symbols without the oct image
             } else {
                 const int pl = (int)(l & bmask), ph = (int)(h & bmask);
                 int cl = 0, ch = 0;
@@ -351,8 +355,8 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                 }
                 l = a.x + (uint32_t)cl;
                 h = a.x + (uint32_t)ch;
-                rem -= 8;
-                shift -= 16;
+                rem -= (uint32_t)kOctSyms;
+                shift -= 2 * kOctSyms;
             }
         } else if (is_quad) {
             const uint32_t nl = staged_sector_rank(my_row[0], my_row[1], (int)(l - sl * (uint32_t)kQuadSyms));
@@ -361,18 +365,15 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             h = nh;
             rem -= 4;
             shift -= 8;
+            forced = forced >= 4u ? forced - 4u : 0u;
+        } else if (live) {  // one symbol: the tail of a k-mer, or the last two of ten symbols taken without the oct image
+            const uint32_t sym = (0x5321u >> (4u * peek(1u))) & 7u;  // A,C,G,T = 1,2,3,5
+            const uint2 r = oct_remainder_step(ix, cb.c, sym, l, h);
+            l = r.x;
+            h = r.y;
+            rem--;
+            shift -= 2;
             forced = forced ? forced - 1u : 0u;
-        } else if (live) {
-            if constexpr (TAIL) {
-                const uint32_t sym = (0x5321u >> (4u * ((uint32_t)(word >> shift) & 3u))) & 7u;  // A,C,G,T = 1,2,3,5
-                const uint2 r = oct_remainder_step(ix, cb.c, sym, l, h);
-                l = r.x;
-                h = r.y;
-                rem--;
-                shift -= 2;
-            } else {
-                rem = 0;  // unreachable: the launcher picks TAIL whenever the remainder is not a multiple of four
-            }
         }
         __syncwarp();  // the rows are rewritten by the next ISSUE
     }
@@ -391,23 +392,19 @@ cudaError_t launch_count_quad(int device, const IndexView &ix, const uint64_t *d
                               uint32_t k, uint64_t *d_out, cudaStream_t st) {
     if (index_is_wide(ix)) return launch_count_quad_t<true>(device, ix, d_packed, lay, k, d_out, st);
     if (ix.oct) {
-        static bool carveout_set = false;  // 4 CTAs x 47 KB of staging per SM need the large shared-memory configuration
+        static bool carveout_done[64] = {};  // per device: 4 CTAs x 47 KB of staging per SM need the large shared-memory configuration
+        bool dummy = false;
+        bool &carveout_set = (device >= 0 && device < 64) ? carveout_done[device] : dummy;
         if (!carveout_set) {
-            cudaFuncSetAttribute((const void *)count_kmers_oct_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute((const void *)count_kmers_oct_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute((const void *)count_kmers_oct_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             carveout_set = true;
         }
         // the chunk dispenser lives in the scratch buffer next to the live counters (engine bookkeeping: the
         // buffer is the engine's own scratch, `const` only towards the caller's data in it)
         uint32_t *work = reinterpret_cast<uint32_t *>(const_cast<uint64_t *>(d_packed) + lay.work());
         if (cudaError_t e = cudaMemsetAsync(work, 0, sizeof(uint32_t), st); e != cudaSuccess) return e;
-        if ((k - acgt_table_depth(k, ix.table_s, 4u)) % 4u) {
-            const unsigned grid = persistent_grid(device, (const void *)count_kmers_oct_kernel<true>, kCountThreads, lay.n, kCountThreads);
-            count_kmers_oct_kernel<true><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out, work);
-        } else {
-            const unsigned grid = persistent_grid(device, (const void *)count_kmers_oct_kernel<false>, kCountThreads, lay.n, kCountThreads);
-            count_kmers_oct_kernel<false><<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out, work);
-        }
+        const unsigned grid = persistent_grid(device, (const void *)count_kmers_oct_kernel, kCountThreads, lay.n, kCountThreads);
+        count_kmers_oct_kernel<<<grid, kCountThreads, 0, st>>>(ix, d_packed, lay, k, d_out, work);
         return cudaGetLastError();
     }
     return launch_count_quad_t<false>(device, ix, d_packed, lay, k, d_out, st);

@@ -122,6 +122,7 @@ def load_library():
         "msbwt_oct_overflow_occurrences": (u64, [vp]),
         "msbwt_oct_runs": (u64, [vp]),
         "msbwt_oct_bucket_shift": (i32, [vp]),
+        "msbwt_oct_symbols": (i32, []),
         "msbwt_debug_copy_oct_image": (i32, [vp, i32, C.POINTER(u64), vp]),
         "msbwt_constrain_ranges_fanout": (i32, [vp, vp, vp, u64, vp, vp]),
         "msbwt_constrain_ranges_fanout_device": (i32, [vp, i32, vp, vp, u64, vp, vp, vp]),
@@ -155,7 +156,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
     "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_oct_index", "msbwt_oct_overflow_lines",
-    "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift",
+    "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift", "msbwt_oct_symbols",
     "msbwt_debug_copy_oct_image", "msbwt_constrain_ranges_fanout", "msbwt_constrain_ranges_fanout_device",
     "msbwt_count_read_kmers", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
     "msbwt_debug_host_pack",
@@ -188,6 +189,11 @@ def _u64(a) -> np.ndarray:
 
 def _p(a: np.ndarray):
     return C.c_void_p(a.ctypes.data)
+
+
+def oct_symbols() -> int:
+    """m: symbols (constrain_range steps) one oct line answers."""
+    return int(load_library().msbwt_oct_symbols())
 
 
 class RleBWT:
@@ -407,11 +413,11 @@ class RleBWT:
         return sectors, c4base
 
     def oct_image(self, slot: int = 0) -> np.ndarray:
-        """lines[65536, nbuck8, 32] u32 of the oct image, copied back from the device."""
+        """lines[4^m, nbuck8, 32] u32 of the oct image (m = oct_symbols()), copied back from the device."""
         L = load_library()
         nb = C.c_uint64(0)
         _check(L.msbwt_debug_copy_oct_image(self.handle, slot, C.byref(nb), None), "oct image")
-        lines = np.zeros((65536, nb.value, 32), dtype=np.uint32)
+        lines = np.zeros((4 ** oct_symbols(), nb.value, 32), dtype=np.uint32)
         _check(L.msbwt_debug_copy_oct_image(self.handle, slot, C.byref(nb), _p(lines)), "oct image")
         return lines
 

@@ -1,9 +1,9 @@
-"""The OCT image (layout.h: one 128-byte line of explicit occurrence runs per (8-symbol code, 2^b-position
-bucket); one line answers EIGHT constrain_range steps, src/rle_bwt.rs:202-287 composed eight times) and the
-kernel that walks it, falling back to two quad steps where a line overflowed.
+"""The OCT image (layout.h: one 128-byte line of explicit occurrence runs per (m-symbol code, 2^b-position
+bucket), m = oct_symbols() = 10; one line answers m constrain_range steps, src/rle_bwt.rs:202-287 composed m
+times) and the kernel that walks it, falling back to quad and one-symbol steps where a line overflowed.
 
   * the image built on the device is compared with a numpy brute-force construction from the decoded BWT
-    (LF by counting, eight-symbol codes, runs cut at chunk boundaries, per-bucket run sets, checkpoints);
+    (LF by counting, m-symbol codes, runs cut at chunk boundaries, per-bucket run sets, checkpoints);
   * every count through the oct path must equal the CPU oracle's (the reference's algorithm), for every
     suffix-table depth / k remainder combination, with $ / N inside the k-mers, on typical read sets and on
     low-complexity ones where most lines overflow."""
@@ -21,10 +21,19 @@ torch = pytest.importorskip("torch")
 
 ACGT = np.array([1, 2, 3, 5])
 CAP = 30
+M_SYMS = None  # oct_symbols(), read from the library on first use
+
+
+def m_syms() -> int:
+    global M_SYMS
+    if M_SYMS is None:
+        M_SYMS = M.oct_symbols()
+    return M_SYMS
 
 
 def brute_oct(bwt: np.ndarray):
-    """(code8 per position or -1, C8[65536])"""
+    """(m-symbol code per position or -1, Cm[4^m])"""
+    m = m_syms()
     n = bwt.size
     cnt = np.bincount(bwt, minlength=6)
     cstart = np.concatenate([[0], np.cumsum(cnt)[:-1]])
@@ -40,23 +49,23 @@ def brute_oct(bwt: np.ndarray):
     j = np.arange(n)
     code = np.zeros(n, dtype=np.int64)
     valid = np.ones(n, dtype=bool)
-    for _ in range(8):
+    for _ in range(m):
         b = idx[bwt[j]] if n else np.zeros(0, dtype=np.int64)
         valid &= b >= 0
         code = code * 4 + np.maximum(b, 0)
         j = lf[j] if n else j
-    codes = np.arange(65536)
-    pos = np.zeros(65536, dtype=np.int64)
-    for r in range(8):
-        sym = ACGT[(codes >> (2 * (7 - r))) & 3]
+    codes = np.arange(4 ** m)
+    pos = np.zeros(4 ** m, dtype=np.int64)
+    for r in range(m):
+        sym = ACGT[(codes >> (2 * (m - 1 - r))) & 3]
         pos = cstart[sym] + occ[sym, pos]
     return np.where(valid, code, -1), pos
 
 
 def auto_shift(runs: int, n: int) -> int:
-    """layout.h: the largest bucket shift in 16..23 that keeps the mean number of runs per line <= 6"""
-    s = 23
-    while s > 16 and runs * (1 << s) > 6 * 65536 * max(n, 1):
+    """layout.h: the largest bucket shift in 16..24 that keeps the mean number of runs per line <= 6"""
+    s = 24
+    while s > 16 and runs * (1 << s) > 6 * (4 ** m_syms()) * max(n, 1):
         s -= 1
     return s
 
@@ -67,7 +76,8 @@ def check_oct_image(g, bwt):
     shift = g.oct_bucket_shift
     cs = min(31 - shift, 10, shift)
     nb = (n >> shift) + 1
-    assert lines.shape == (65536, nb, 32)
+    ncodes = 4 ** m_syms()
+    assert lines.shape == (ncodes, nb, 32)
     code, c8 = brute_oct(bwt)
     # runs of equal codes, cut at every multiple of 2^cs (so no run crosses a bucket, len <= 2^cs)
     bound = np.ones(n, dtype=bool)
@@ -80,8 +90,8 @@ def check_oct_image(g, bwt):
     rc, rb = code[starts], starts >> shift
     plain_heads = int((bound & (code >= 0) & np.r_[True, code[1:] != code[:-1]]).sum()) if n else 0
     assert g.oct_runs == plain_heads
-    per = np.zeros((65536, nb), dtype=np.int64)
-    nruns = np.zeros((65536, nb), dtype=np.int64)
+    per = np.zeros((ncodes, nb), dtype=np.int64)
+    nruns = np.zeros((ncodes, nb), dtype=np.int64)
     np.add.at(per, (rc, rb), lens)
     np.add.at(nruns, (rc, rb), 1)
     before = np.cumsum(per, axis=1) - per
@@ -93,7 +103,7 @@ def check_oct_image(g, bwt):
     # stored runs `(len << shift) | offset`: every non-overflowed line holds exactly its runs, the rest is 0
     ent = np.sort(lines[:, :, 2:], axis=2)
     entry = ((lens << shift) | (starts & ((1 << shift) - 1))).astype(np.uint32)
-    want = np.zeros((65536, nb, CAP), dtype=np.uint32)
+    want = np.zeros((ncodes, nb, CAP), dtype=np.uint32)
     order = np.lexsort((entry, rb, rc))
     c_s, b_s, e_s = rc[order], rb[order], entry[order]
     first = np.flatnonzero(np.r_[True, (c_s[1:] != c_s[:-1]) | (b_s[1:] != b_s[:-1])]) if e_s.size else np.zeros(0, int)
@@ -108,7 +118,7 @@ def check_oct_image(g, bwt):
         assert set(ent[c, b].tolist()) <= mine and len(set(ent[c, b].tolist())) == CAP
 
 
-@pytest.mark.parametrize("shift", [0, 8, 11])
+@pytest.mark.parametrize("shift", [0, 16, 17])
 def test_oct_image_equals_brute_force(shift):
     rng = np.random.default_rng(2020)
     from harness import bwt_build, synth
@@ -146,13 +156,13 @@ def midsize():
 
 def test_oct_image_over_several_buckets(midsize):
     reads, o = midsize
-    g = M.RleBWT(oct_index=1, oct_bucket_shift=14)
+    g = M.RleBWT(oct_index=1, oct_bucket_shift=20)
     g.load_vector(o.rle_bytes())
-    assert g.oct_index and g.oct_bucket_shift == 14 and (g.get_total_size() >> 14) >= 100
+    assert g.oct_index and g.oct_bucket_shift == 20 and (g.get_total_size() >> 20) >= 1
     check_oct_image(g, decode(o.rle_bytes()))
 
 
-@pytest.mark.parametrize("table_s,shift", [(-1, 0), (0, 14), (1, 16), (2, 0), (3, 12), (4, 23), (5, 13), (7, 15)])
+@pytest.mark.parametrize("table_s,shift", [(-1, 0), (0, 18), (1, 17), (2, 0), (3, 19), (4, 24), (5, 20), (7, 18), (11, 19), (12, 20)])
 def test_oct_path_is_bit_exact(midsize, table_s, shift):
     from harness import synth
     reads, o = midsize

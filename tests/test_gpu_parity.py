@@ -287,8 +287,9 @@ def test_full_size_config1_properties():
     g = M.RleBWT.new()
     g.load_vector(rle)
     assert g.get_total_size() == total == 151_000_000
-    # 219 MB of one-step blocks + depth-12 table exceed L2: the loader builds the quad image and deepens the table
-    assert g.quad_index and g.suffix_table_s == 15
+    # 219 MB of one-step blocks + depth-12 table exceed L2: the loader builds the quad and oct images and deepens
+    # the table (to 14 under the oct image: levels 11..14 are kept, a 31-mer starts from the L2-resident depth 11)
+    assert g.quad_index and g.oct_index and g.suffix_table_s == 14
     k = 30
     q = synth.make_queries(reads, k, 600_000, 400_000)
     base = g.count_kmers_fixed(q.cpu().numpy(), k)
