@@ -263,12 +263,19 @@ def measure_ours(args, cfg, ctx, primary: bool):
     d_status = torch.zeros(1, dtype=torch.int32, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > L2: evicts index + queries between steps
 
+    fused = bwt.oct_index and k <= 32 and os.environ.get("MSBWT_FUSED", "0") not in ("", "0")   # opt-in, slower
+
     def step(ev=None):
         d_status.zero_()
-        bwt.pack_kmers_device(queries.data_ptr(), k, n, d_packed.data_ptr(), d_out.data_ptr(), d_status.data_ptr(), stream)
-        if ev:
-            ev[0].record()
-        bwt.count_kmers_packed_device(d_packed.data_ptr(), k, n, d_out.data_ptr(), stream)
+        if fused:   # one kernel from symbol bytes to counts (msbwt_count_kmers_fixed_device, fused_kernels.cu)
+            if ev:
+                ev[0].record()
+            bwt.count_kmers_fixed_device(queries.data_ptr(), k, n, d_out.data_ptr(), d_status.data_ptr(), stream)
+        else:
+            bwt.pack_kmers_device(queries.data_ptr(), k, n, d_packed.data_ptr(), d_out.data_ptr(), d_status.data_ptr(), stream)
+            if ev:
+                ev[0].record()
+            bwt.count_kmers_packed_device(d_packed.data_ptr(), k, n, d_out.data_ptr(), stream)
         if ev:
             ev[1].record()
 
@@ -435,6 +442,8 @@ def measure_ours(args, cfg, ctx, primary: bool):
         # pack/seed kernel and is accounted in `step` below, next to the whole step's time
         index_bytes_q = (oct_lines * LINE_BYTES + quad_lines * LINE_BYTES + pair_lines * PAIR_BYTES + one_blocks * BLOCK_BYTES) / ms
         bytes_per_query = index_bytes_q + packed_q + 8
+        if fused:   # the fused kernel reads the k symbol bytes itself and one 16-byte piece of the (L2-resident) table level
+            bytes_per_query = index_bytes_q + hits / ms * 16 + k + 8
         sector_bytes_per_query = (oct_lines * LINE_BYTES + quad_sectors * QUAD_SECTOR_BYTES + pair_lines * PAIR_BYTES + one_blocks * BLOCK_BYTES) / ms + packed_q + 8
         accesses_per_query = (oct_lines + quad_lines + pair_lines + one_blocks) / ms
         peak, peak_src = measured_peak_gbs()
@@ -444,8 +453,8 @@ def measure_ours(args, cfg, ctx, primary: bool):
         res["roofline"] = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src,
-            "kernel": "count_kmers_oct_kernel" if bwt.oct_index else "count_kmers_quad_kernel" if quad else ("count_kmers_pair_kernel" if pair else "count_kmers_packed_kernel"),
-            "kernel_ms": 1e3 * kern_s, "algorithmic_bytes_per_launch": bytes_per_query * n,
+            "kernel": "count_kmers_oct_kernel<RAW> (fused: pack + table + search)" if fused else "count_kmers_oct_kernel" if bwt.oct_index else "count_kmers_quad_kernel" if quad else ("count_kmers_pair_kernel" if pair else "count_kmers_packed_kernel"),
+            "fused": bool(fused), "kernel_ms": 1e3 * kern_s, "algorithmic_bytes_per_launch": bytes_per_query * n,
             "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": ref_steps / ms,
             "oct_lines_per_query": oct_lines / ms, "oct_overflow_lines": bwt.oct_overflow_lines,
             "oct_overflow_position_share": bwt.oct_overflow_occurrences / max(1, total), "oct_bucket_shift": bwt.oct_bucket_shift, "oct_symbols_per_line": M.oct_symbols(),

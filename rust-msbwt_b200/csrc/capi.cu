@@ -633,6 +633,17 @@ extern "C" void msbwt_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 // ================================================================ device-buffer entry points
 
+namespace {
+// MSBWT_FUSED=1 routes the fixed-k device entry point through the fused kernel (fused_kernels.cu).  Off by
+// default: measured on B200 it is slower than pack / seed + search (9.5 ms against 7.4 ms per 100 M 31-mers on
+// the 1.51 Gsymbol BWT) -- the search loop is already 62 % issue-bound and the fused one adds the packing and a
+// third iteration (the table entry) per query to it.
+bool fused_enabled() {
+    const char *e = getenv("MSBWT_FUSED");
+    return e && atoi(e) != 0;
+}
+}  // namespace
+
 extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, const uint8_t *d_syms, uint32_t k,
                                               uint64_t n, uint64_t *d_out, uint32_t *d_status, void *stream) {
     if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
@@ -643,9 +654,20 @@ extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, 
     DeviceGuard guard(rep.device);
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t per = std::min<uint64_t>(n, kMaxPerLaunch);
-    CU_TRY(rep.dev_packed.reserve(packed_layout(rep.view, k, per).total() * sizeof(uint64_t)));
     uint32_t *flag = d_status ? d_status : rep.d_status + kStatusDev;
     CU_TRY(cudaMemsetAsync(flag, 0, sizeof(uint32_t), st));
+    if (fused_enabled() && fused_path_applies(rep.view, d_syms, k)) {
+        // one kernel from symbol bytes to counts (fused_kernels.cu); sub-batches of 2^30 keep the 16-byte alignment
+        CU_TRY(rep.dev_packed.reserve(fused_scratch_bytes(per)));
+        for (uint64_t q0 = 0; q0 < n; q0 += per) {
+            const uint64_t m = std::min(per, n - q0);
+            CU_TRY(launch_count_fused(rep.device, rep.view, d_syms + q0 * k, k, m, d_out + q0, flag,
+                                      rep.dev_packed.as<uint32_t>(), st, &g_call_launches));
+            flush_launches();
+        }
+        return MSBWT_OK;
+    }
+    CU_TRY(rep.dev_packed.reserve(packed_layout(rep.view, k, per).total() * sizeof(uint64_t)));
     for (uint64_t q0 = 0; q0 < n; q0 += per) {  // sub-batches reuse the scratch in stream order
         const uint64_t m = std::min(per, n - q0);
         CU_TRY(launch_pack_seed(rep.view, d_syms + q0 * k, k, m, rep.dev_packed.as<uint64_t>(), d_out + q0, flag, st));

@@ -48,6 +48,20 @@ __host__ __device__ __forceinline__ uint32_t list_a_table_depth(const IndexView 
     return ix.oct ? oct_table_depth(k, ix.table_s) : acgt_table_depth(k, ix.table_s, list_a_stride(ix));
 }
 
+// ---- four symbols per 32-bit word (SWAR)
+__device__ __forceinline__ uint32_t swar_haszero(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
+// nonzero iff some byte is not one of A,C,G,T = 1,2,3,5
+__device__ __forceinline__ uint32_t swar_non_acgt(uint32_t x) {
+    const uint32_t ge6 = (((x & 0x7F7F7F7Fu) + 0x7A7A7A7Au) | x) & 0x80808080u;
+    return ge6 | swar_haszero(x) | swar_haszero(x ^ 0x04040404u);
+}
+// four ACGT symbol bytes -> 8 bits, byte i at bits 2i (A,C,G,T = 0..3)
+__device__ __forceinline__ uint32_t swar_pack4(uint32_t x) {
+    uint32_t c = (x - 0x01010101u - ((x >> 2) & 0x01010101u)) & 0x03030303u;
+    c = (c | (c >> 6)) & 0x000F000Fu;
+    return (c | (c >> 12)) & 0xFFu;
+}
+
 inline int sm_count(int device) {
     static int cached[64];
     if (device < 0 || device >= 64) return 148;

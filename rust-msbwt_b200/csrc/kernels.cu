@@ -56,20 +56,6 @@ __device__ __forceinline__ uint64_t append_live(bool live, bool list_a, unsigned
 constexpr uint32_t kPackSmemMaxK = 160;  // 256 * k + 64 bytes of shared memory; longer k-mers read global memory
 constexpr uint32_t kPackMaxWords = (kPackSmemMaxK + kPairSymsPerWord - 1) / kPairSymsPerWord;  // 5
 
-// ---- four symbols per 32-bit word (SWAR)
-__device__ __forceinline__ uint32_t swar_haszero(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
-// nonzero iff some byte is not one of A,C,G,T = 1,2,3,5
-__device__ __forceinline__ uint32_t swar_non_acgt(uint32_t x) {
-    const uint32_t ge6 = (((x & 0x7F7F7F7Fu) + 0x7A7A7A7Au) | x) & 0x80808080u;
-    return ge6 | swar_haszero(x) | swar_haszero(x ^ 0x04040404u);
-}
-// four ACGT symbol bytes -> 8 bits, byte i at bits 2i (A,C,G,T = 0..3)
-__device__ __forceinline__ uint32_t swar_pack4(uint32_t x) {
-    uint32_t c = (x - 0x01010101u - ((x >> 2) & 0x01010101u)) & 0x03030303u;
-    c = (c | (c >> 6)) & 0x000F000Fu;
-    return (c | (c >> 12)) & 0xFFu;
-}
-
 // Seeds one all-ACGT k-mer given as 2-bit words (`get(w)`, w < nw: the k-mer's last symbol in the top
 // bits of word 0): suffix-table lookup at the depth acgt_table_depth picks, then either the final count
 // (written by the caller) or the remaining symbols re-aligned to the top of word 0 and stored for the

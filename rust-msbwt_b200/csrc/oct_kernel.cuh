@@ -1,0 +1,374 @@
+// oct_kernel.cuh -- the search kernel over the oct image (layout.h), shared by the two translation units that
+// instantiate it: quad_kernels.cu (packed live list) and fused_kernels.cu (symbol bytes in, counts out).  Two
+// modules because ptxas 12.9 crashes on one that holds both instantiations.
+#pragma once
+#include "device_rank.cuh"
+#include "engine.h"
+#include "kernel_common.cuh"
+
+namespace msbwt {
+
+// ---------------------------------------------------------------- oct image on top of the quad image
+//
+// 32-bit positions only.  While kOctSyms (ten) or more symbols are left a step reads one 128-byte line of the
+// oct image (layout.h); the quad image (and one-symbol ranks) serve remainders, ranges that straddle two oct
+// buckets and the lines that overflowed (two quad steps + two one-symbol steps instead of one oct step).
+//
+// What HBM random access is bound by is the number of L2 requests that miss -- about 40 G/s whatever their
+// size (profiles/r1_gather_*.json) -- and what reaches that bound is the number of them in flight.  So:
+//
+//  * one thread per query (1024 queries in flight per SM), but the index lines are fetched by the WARP:
+//    every lane publishes the address of the line (or the two quad sectors) its query needs next, and in
+//    eight rounds the warp copies the 32 lines into shared memory with cp.async, eight lanes x 16 bytes per
+//    line, i.e. ONE 128-byte request per line and no load registers.  (A thread that read its own line with
+//    four 256-bit loads paid four requests per line and ran at a quarter of the line rate; a quad of lanes
+//    per query kept only 384 queries per SM in flight: profiles/r1_o2_*, r1_o6_* summaries.)
+//  * every iteration is ISSUE (branch-free, whatever kind of step each lane needs), one wait, CONSUME (each
+//    lane ranks in its own staged line; divergent, but without memory accesses): one memory round trip per
+//    iteration even when the lanes of a warp need different kinds of step -- one lane in fourteen lands on
+//    an overflowed line on 30x reads with 1 % errors.
+//  * every warp takes chunks of 512 consecutive queries of the live list from an atomic counter and stages
+//    them through shared memory 32 queries at a time, double-buffered (coalesced cp.async one pool ahead);
+//    lanes that finished take the next queries of the pool in lane order, so the warp stays full whatever the
+//    mix of early exits and no warp is left with a slow slice of a skewed batch.
+#ifndef MSBWT_OCT_CTAS
+#define MSBWT_OCT_CTAS 4
+#endif
+constexpr int kOctRowBytes = 144;    // a 128-byte line + 16: rows of consecutive lanes start 4 banks apart (conflict-free LDS.128)
+constexpr int kOctPoolBytes = 640;   // 32 x (u64 symbol word, u64 seed range, u32 original index)
+constexpr int kOctChunk = 512;       // queries a warp takes from the live list at a time
+constexpr int kOctRawPoolBytes = 1072;  // fused path: 32 queries x k <= 32 symbol bytes, + the slack an unaligned 36-byte read needs
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool on) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(on ? 16u : 0u) : "memory");
+}
+// `bytes` (0..16) from gmem, the rest of the 16 zero-filled
+__device__ __forceinline__ void cp_async16_partial(void *smem, const void *gmem, uint32_t bytes) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool on) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gmem), "r"(on ? 8u : 0u) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem, bool on) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(gmem), "r"(on ? 4u : 0u) : "memory");
+}
+
+// the rare one-symbol remainder step, out of line and by value so that neither its 32 load registers nor a
+// stack slot for l / h burden the main loop
+static __device__ __noinline__ uint2 oct_remainder_step(const IndexView &ix, const uint32_t *cbase, uint32_t sym, uint32_t l, uint32_t h) {
+    const CBase<false> cb{cbase};
+    rank_step<false, 1>(ix, cb, sym, l, h);
+    return make_uint2(l, h);
+}
+
+// occurrences below bucket offsets pl / ph contributed by one stored run `(len << b) | off` (0 = empty slot)
+__device__ __forceinline__ void oct_add_run(uint32_t e, uint32_t b, uint32_t mask, int pl, int ph, int &sl, int &sh) {
+    const int off = (int)(e & mask), len = (int)(e >> b);
+    sl += min(max(pl - off, 0), len);
+    sh += min(max(ph - off, 0), len);
+}
+__device__ __forceinline__ void oct_add_runs(const uint4 &v, uint32_t b, uint32_t mask, int pl, int ph, int &sl, int &sh) {
+    oct_add_run(v.x, b, mask, pl, ph, sl, sh);
+    oct_add_run(v.y, b, mask, pl, ph, sl, sh);
+    oct_add_run(v.z, b, mask, pl, ph, sl, sh);
+    oct_add_run(v.w, b, mask, pl, ph, sl, sh);
+}
+// a staged quad sector {checkpoint, 224 occurrence bits}: checkpoint + set bits at offsets < p
+__device__ __forceinline__ uint32_t staged_sector_rank(const uint4 &a, const uint4 &b, int p) {
+    return a.x + __popc(a.y & below_mask(p)) + __popc(a.z & below_mask(p - 32)) + __popc(a.w & below_mask(p - 64)) +
+           __popc(b.x & below_mask(p - 96)) + __popc(b.y & below_mask(p - 128)) + __popc(b.z & below_mask(p - 160)) +
+           __popc(b.w & below_mask(p - 192));
+}
+
+// RAW = false: the queries come packed and seeded from the pack / seed kernels (live list A of `packed`).
+// RAW = true (fused path, k <= 32): the queries come as the caller's symbol bytes (`syms`, n * k); every warp
+// stages 32 of them at a time, each lane packs its own k-mer (SWAR, the same arithmetic as pack_seed_kernel),
+// fetches its suffix-table entry as one more kind of step of the same loop and writes its count to out[query]
+// -- no pack kernel, no live list written and read back.  A k-mer holding a symbol outside ACGT is appended to
+// `exc` (count, then query indices) and counted afterwards by count_exceptions_kernel.
+template <bool RAW>
+__global__ void __launch_bounds__(kCountThreads, MSBWT_OCT_CTAS)
+count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, PackedLayout lay, uint32_t k,
+                       uint64_t *__restrict__ out, uint32_t *__restrict__ work, const uint8_t *__restrict__ syms,
+                       uint32_t n_raw, uint32_t *__restrict__ exc) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint64_t cb_smem[4];
+    const CBase<false> cb = stage_cbase<false>(ix, cb_smem);
+    const uint64_t stream = policy_evict_first();
+    constexpr uint32_t kFull = 0xffffffffu;
+    constexpr uint32_t kPool = RAW ? kOctRawPoolBytes : kOctPoolBytes;
+    constexpr uint32_t kWarpSmem = 32 * kOctRowBytes + 2 * kPool;
+
+    const uint32_t n = RAW ? n_raw : (uint32_t)packed[lay.live()];  // queries to walk (live list A)
+    const uint32_t lane = threadIdx.x & 31u;
+    if ((blockIdx.x * (kCountThreads / 32) + (threadIdx.x >> 5)) * 32u >= n) return;  // more warps than pools of work
+    const uint64_t *w0 = packed + lay.w0(), *seeds = packed + lay.seed(), *wx = packed + lay.wx();
+    const uint32_t *qidx = reinterpret_cast<const uint32_t *>(packed + lay.qidx());
+    const uint32_t depth0 = list_a_table_depth(ix, k);
+    const uint32_t rem0 = k - depth0;
+    const uint32_t bshift = ix.oct_shift, bmask = (1u << bshift) - 1u;
+    const char *const oct_base = reinterpret_cast<const char *>(ix.oct);
+    const char *const quad_base = reinterpret_cast<const char *>(ix.quad);
+    const uint32_t back0 = ix.table_s - depth0;  // which of the kept table levels (RAW)
+    const char *const table_base = reinterpret_cast<const char *>(
+        back0 == 0 ? ix.table : (back0 == 1 ? ix.table2 : (back0 == 2 ? ix.table3 : ix.table4)));
+    uint8_t *const rows = smem + (threadIdx.x >> 5) * kWarpSmem;  // 32 rows of kOctRowBytes
+    uint8_t *const pools = rows + 32 * kOctRowBytes;               // 2 pools of 32 queries
+    const uint4 *const my_row = reinterpret_cast<const uint4 *>(rows + lane * kOctRowBytes);
+
+    // The queries are handed out in chunks of kOctChunk (an atomic counter: a warp whose queries die early
+    // simply comes back sooner, whatever the order of the batch) and staged pool by pool: pool A (sequence
+    // number `seq`, buffer seq & 1) is being handed to the lanes, pool B (the other buffer) is already staged
+    // or on its way.
+    uint32_t chunk_next = 0, chunk_end = 0;  // the rest of this warp's current chunk (warp-uniform)
+    auto next_pool = [&](uint32_t &base, uint32_t &cnt) {
+        if (chunk_next >= chunk_end) {
+            uint32_t c = 0;
+            if (lane == 0) c = atomicAdd(work, (uint32_t)kOctChunk);
+            c = __shfl_sync(kFull, c, 0);
+            chunk_next = min(c, n);
+            chunk_end = min(c + (uint32_t)kOctChunk, n);
+        }
+        base = chunk_next;
+        cnt = min(32u, chunk_end - chunk_next);
+        chunk_next += cnt;
+    };
+    auto load_pool = [&](uint32_t buf, uint32_t base, uint32_t cnt) {
+        uint8_t *p = pools + buf * kPool;
+        if constexpr (RAW) {  // cnt * k symbol bytes, 16 at a time (base is a multiple of 32: 16-byte aligned)
+            const uint8_t *src = syms + (uint64_t)base * k;
+            const uint32_t bytes = cnt * k;
+#pragma unroll
+            for (uint32_t c = lane; c < 64u; c += 32u) {
+                const uint32_t at = 16u * c;
+                cp_async16_partial(p + at, src + at, at < bytes ? min(16u, bytes - at) : 0u);
+            }
+        } else {
+            const uint32_t idx = base + lane;
+            const bool on = lane < cnt;
+            cp_async8(p + 8u * lane, w0 + idx, on);
+            cp_async8(p + 256u + 8u * lane, seeds + idx, on);
+            cp_async4(p + 512u + 4u * lane, qidx + idx, on);
+        }
+    };
+    uint32_t seq = 0, a_pos = 0, a_cnt, b_cnt, a_base, b_base;
+    next_pool(a_base, a_cnt);
+    load_pool(0u, a_base, a_cnt);
+    next_pool(b_base, b_cnt);
+    load_pool(1u, b_base, b_cnt);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+
+    bool active = false;
+    bool need_table = false;  // RAW: the next step is the suffix-table lookup
+    uint32_t l = 0, h = 0;
+    uint64_t word = 0, pend = 0;
+    uint32_t q = 0;
+    uint32_t rem = 0;     // symbols still to consume
+    int shift = 62;       // bit offset of the next symbol (2 bits) in `word`; negative: already inside `pend`
+    uint32_t widx = 0;
+    uint32_t forced = 0;  // symbols to take without the oct image (overflowed line / two buckets)
+
+    // the next `nsym` symbols as one code (first consumed most significant); a step may straddle two words
+    auto peek = [&](uint32_t nsym) -> uint32_t {
+        const int bits = 2 * (int)nsym, avail = shift + 2;  // avail >= 2 here
+        if (avail >= bits) return (uint32_t)(word >> (avail - bits)) & ((1u << bits) - 1u);
+        const int need = bits - avail;
+        return (uint32_t)(((word & ((1ull << avail) - 1ull)) << need) | (pend >> (64 - need)));
+    };
+
+    for (;;) {
+        // ---- RETIRE + REFILL (warp-uniform control)
+        if (active && !need_table && (rem == 0 || l == h)) {
+            stg_stream(out + q, (uint64_t)(h - l), stream);
+            active = false;
+        }
+        const uint32_t want = __ballot_sync(kFull, !active);
+        if (want) {
+            const uint32_t avail_a = a_cnt - a_pos, avail = avail_a + b_cnt;
+            if (avail) {
+                const uint32_t r = __popc(want & ((1u << lane) - 1u));  // idle lanes take queries in lane order
+                if (!active && r < avail) {
+                    const bool from_a = r < avail_a;
+                    const uint8_t *p = pools + ((from_a ? seq : seq + 1u) & 1u) * kPool;
+                    const uint32_t slot = from_a ? a_pos + r : r - avail_a;
+                    shift = 62;
+                    widx = 0;
+                    forced = 0;
+                    active = true;
+                    if constexpr (RAW) {
+                        q = (from_a ? a_base : b_base) + slot;
+                        // k symbol bytes at p + slot * k -> 2 bits each, the k-mer's last symbol in the top bits
+                        const uint32_t off = slot * k, sh8 = 8u * (off & 3u);
+                        const volatile uint32_t *wsrc = reinterpret_cast<const volatile uint32_t *>(p + (off & ~3u));
+                        uint32_t prev = wsrc[0], bad = 0;
+                        uint64_t le = 0;
+#pragma unroll
+                        for (uint32_t i = 0; i < 8u; i++) {
+                            const uint32_t nxt = wsrc[i + 1];
+                            uint32_t x = __funnelshift_r(prev, nxt, sh8);  // symbols 4i .. 4i+3
+                            prev = nxt;
+                            const uint32_t nvalid = k > 4u * i ? min(4u, k - 4u * i) : 0u;
+                            const uint32_t keep = nvalid >= 4u ? 0xFFFFFFFFu : ((1u << (8u * nvalid)) - 1u);
+                            x = (x & keep) | (0x01010101u & ~keep);  // bytes past the k-mer count as 'A'
+                            bad |= swar_non_acgt(x);
+                            le |= (uint64_t)swar_pack4(x) << (8u * i);
+                        }
+                        word = le << (64u - 2u * k);
+                        if (bad) {  // $, N or an invalid byte: counted by count_exceptions_kernel
+                            exc[1u + atomicAdd(exc, 1u)] = q;
+                            active = false;
+                        } else if (depth0) {
+                            need_table = true;
+                            rem = k;
+                        } else {
+                            l = 0;
+                            h = (uint32_t)ix.total;
+                            rem = k;
+                        }
+                    } else {
+                        word = *reinterpret_cast<const volatile uint64_t *>(p + 8u * slot);
+                        const uint64_t lo = *reinterpret_cast<const volatile uint64_t *>(p + 256u + 8u * slot);
+                        q = *reinterpret_cast<const volatile uint32_t *>(p + 512u + 4u * slot) & kQidxMask;
+                        l = (uint32_t)lo;
+                        h = (uint32_t)(lo >> 32);
+                        rem = rem0;
+                        if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + q, stream);
+                    }
+                }
+                const uint32_t taken = min((uint32_t)__popc(want), avail);
+                if (taken >= avail_a) {  // pool A is used up: B becomes A, the next pool is staged into A's buffer
+                    a_cnt = b_cnt;
+                    a_base = b_base;
+                    a_pos = taken - avail_a;
+                    seq++;
+                    next_pool(b_base, b_cnt);
+                    __syncwarp();
+                    load_pool((seq + 1u) & 1u, b_base, b_cnt);  // (committed with this iteration's lines)
+                } else {
+                    a_pos += taken;
+                }
+            } else if (want == kFull) {
+                return;  // nothing left to hand out and every lane is done
+            }
+        }
+        if (active && shift < 0) {  // 32 symbols per word: on to the next one (a step may have ended inside it)
+            word = pend;
+            widx++;
+            shift += 64;
+            if (2u * rem > (uint32_t)(shift + 2)) pend = ldg_stream(wx + (uint64_t)widx * lay.n + q, stream);
+        }
+
+        // ---- ISSUE (branch-free): every lane publishes what its query needs, the warp fetches it
+        // (a range over two buckets, like an overflowed line, takes its kOctSyms symbols as quad steps and, for
+        // the last two of ten, one-symbol steps)
+        const bool is_table = RAW && active && need_table;
+        const bool live = active && !is_table && rem != 0 && l != h;
+        const uint32_t bl = l >> bshift, bh = h >> bshift;
+        const bool want_oct = live && rem >= (uint32_t)kOctSyms && forced == 0u;
+        const bool is_oct = want_oct && bl == bh;
+        if (want_oct && !is_oct) forced = (uint32_t)kOctSyms;  // symbols to take without the oct image
+        const bool is_quad = live && !is_oct && rem >= 4u && (forced == 0u || forced >= 4u);
+        const uint32_t codem = peek((uint32_t)kOctSyms);
+        const uint32_t code8 = peek(4u);
+        const uint32_t sl = l / (uint32_t)kQuadSyms, sh = h / (uint32_t)kQuadSyms;
+        const uint64_t entry = RAW ? (word >> (64u - 2u * (depth0 ? depth0 : 1u))) : 0ull;  // suffix-table index
+        const char *p0 = is_oct ? oct_base + ((size_t)codem * ix.nbuck8 + bl) * kOctLineBytes
+                                : quad_base + ((size_t)code8 * ix.nsec4 + sl) * kQuadSectorBytes;
+        if (is_table) p0 = table_base + ((entry * 8u) & ~15ull);
+        // low two bits: kind (1 oct, 2 quad, 3 table entry, 0 nothing); the rest (quad): byte distance from the
+        // sector of l to the sector of h
+        const uint32_t meta = is_table ? 3u : (is_oct ? 1u : (is_quad ? (2u | ((sh - sl) * (uint32_t)kQuadSectorBytes)) : 0u));
+        const uint32_t p0_lo = (uint32_t)(uintptr_t)p0, p0_hi = (uint32_t)((uintptr_t)p0 >> 32);
+        {
+            const uint32_t j = lane & 7u;  // this lane's 16 bytes of a line
+#pragma unroll
+            for (uint32_t c = 0; c < 8u; c++) {
+                const uint32_t o = 4u * c + (lane >> 3);  // the lane whose line this is
+                const uint32_t m = __shfl_sync(kFull, meta, o);
+                const uint64_t a = ((uint64_t)__shfl_sync(kFull, p0_hi, o) << 32) | __shfl_sync(kFull, p0_lo, o);
+                // oct: bytes 16j.. of the line; quad: the sector of l into bytes 0..31, the sector of h into 32..63;
+                // table: the 16 bytes that hold the entry into bytes 0..15
+                const uint64_t src = a + 16u * j + (((m & 3u) == 2u && j >= 2u) ? (uint64_t)(m & ~31u) - 32u : 0u);
+                cp_async16(rows + o * kOctRowBytes + 16u * j, reinterpret_cast<const void *>(src),
+                           (m & 3u) == 1u || ((m & 3u) == 2u && j < 4u) || ((m & 3u) == 3u && j == 0u));
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+
+        // ---- CONSUME (each lane ranks in its own staged line)
+        if (is_table) {
+            const uint4 e = my_row[0];
+            l = (entry & 1ull) ? e.z : e.x;
+            h = (entry & 1ull) ? e.w : e.y;
+            word <<= 2u * depth0;
+            rem = rem0;
+            need_table = false;
+        } else if (is_oct) {
+            const uint4 a = my_row[0], b = my_row[1];
+            if (a.y > (uint32_t)kOctCapacity) {
+                forced = (uint32_t)kOctSyms;  // this line cannot hold its runs: the same symbols without the oct image
+            } else {
+                const int pl = (int)(l & bmask), ph = (int)(h & bmask);
+                int cl = 0, ch = 0;
+                oct_add_run(a.z, bshift, bmask, pl, ph, cl, ch);
+                oct_add_run(a.w, bshift, bmask, pl, ph, cl, ch);
+                oct_add_runs(b, bshift, bmask, pl, ph, cl, ch);
+                if (a.y > 6u) {
+                    oct_add_runs(my_row[2], bshift, bmask, pl, ph, cl, ch);
+                    oct_add_runs(my_row[3], bshift, bmask, pl, ph, cl, ch);
+                    if (a.y > 14u) {
+                        oct_add_runs(my_row[4], bshift, bmask, pl, ph, cl, ch);
+                        oct_add_runs(my_row[5], bshift, bmask, pl, ph, cl, ch);
+                        if (a.y > 22u) {
+                            oct_add_runs(my_row[6], bshift, bmask, pl, ph, cl, ch);
+                            oct_add_runs(my_row[7], bshift, bmask, pl, ph, cl, ch);
+                        }
+                    }
+                }
+                l = a.x + (uint32_t)cl;
+                h = a.x + (uint32_t)ch;
+                rem -= (uint32_t)kOctSyms;
+                shift -= 2 * kOctSyms;
+            }
+        } else if (is_quad) {
+            const uint32_t nl = staged_sector_rank(my_row[0], my_row[1], (int)(l - sl * (uint32_t)kQuadSyms));
+            const uint32_t nh = staged_sector_rank(my_row[2], my_row[3], (int)(h - sh * (uint32_t)kQuadSyms));
+            l = nl;
+            h = nh;
+            rem -= 4;
+            shift -= 8;
+            forced = forced >= 4u ? forced - 4u : 0u;
+        } else if (live) {  // one symbol: the tail of a k-mer, or the last two of ten symbols taken without the oct image
+            const uint32_t sym = (0x5321u >> (4u * peek(1u))) & 7u;  // A,C,G,T = 1,2,3,5
+            const uint2 r = oct_remainder_step(ix, cb.c, sym, l, h);
+            l = r.x;
+            h = r.y;
+            rem--;
+            shift -= 2;
+            forced = forced ? forced - 1u : 0u;
+        }
+        __syncwarp();  // the rows are rewritten by the next ISSUE
+    }
+}
+
+// dynamic shared memory per CTA
+constexpr int kOctSmemPacked = (kCountThreads / 32) * (32 * kOctRowBytes + 2 * kOctPoolBytes);
+constexpr int kOctSmemRaw = (kCountThreads / 32) * (32 * kOctRowBytes + 2 * kOctRawPoolBytes);
+
+// one full wave of CTAs for a kernel with `smem` bytes of dynamic shared memory, fewer if there is less work
+inline unsigned oct_grid(int device, const void *kernel, int smem, uint64_t n) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kCountThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const uint64_t full = (uint64_t)sm_count(device) * (uint64_t)per_sm, need = (n + kCountThreads - 1) / kCountThreads;
+    return (unsigned)(need < 1 ? 1 : (need < full ? need : full));
+}
+
+}  // namespace msbwt

@@ -8,7 +8,7 @@ fn main() {
     let csrc = root.join("rust-msbwt_b200").join("csrc");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let mut objs = vec![];
-    for f in ["capi.cu", "kernels.cu", "quad_kernels.cu", "ext_kernels.cu", "loader.cu", "builder.cu", "pair_builder.cu", "quad_builder.cu",
+    for f in ["capi.cu", "kernels.cu", "quad_kernels.cu", "fused_kernels.cu", "ext_kernels.cu", "loader.cu", "builder.cu", "pair_builder.cu", "quad_builder.cu",
               "oct_builder.cu", "bwt_build.cu"] {
         let obj = out.join(f).with_extension("o");
         let ok = Command::new(&nvcc)
