@@ -446,6 +446,11 @@ def measure_ours(args, cfg, ctx, primary: bool):
             bytes_per_query = index_bytes_q + hits / ms * 16 + k + 8
         sector_bytes_per_query = (oct_lines * LINE_BYTES + quad_sectors * QUAD_SECTOR_BYTES + pair_lines * PAIR_BYTES + one_blocks * BLOCK_BYTES) / ms + packed_q + 8
         accesses_per_query = (oct_lines + quad_lines + pair_lines + one_blocks) / ms
+        # a suffix-table lookup fills a 128-B line from HBM unless the level it reads is L2-resident (depth 11 under
+        # the oct image: 4^11 entries of 8 B = 33 MB), where it costs its 8 bytes
+        depth = bwt.table_depth_for_k(k)
+        table_level_bytes = (4 ** depth) * 8
+        table_hit_bytes = 8 if table_level_bytes <= 64 << 20 else LINE_BYTES
         peak, peak_src = measured_peak_gbs()
         kern_s = statistics.mean(kern_ms) / 1e3
         achieved = bytes_per_query * n / kern_s / 1e9
@@ -471,7 +476,9 @@ def measure_ours(args, cfg, ctx, primary: bool):
                              "lookup + query bytes in + packed query out and in + result",
                      "index_accesses_per_query": accesses_per_query + hits / ms,
                      "index_accesses_per_s": (accesses_per_query + hits / ms) * n / (statistics.mean(step_ms) / 1e3),
-                     "achieved": (index_bytes_q + hits / ms * LINE_BYTES + k + 2 * packed_q + 8) * n / (statistics.mean(step_ms) / 1e3) / 1e9},
+                     "achieved": (index_bytes_q + hits / ms * table_hit_bytes + k + 2 * packed_q + 8) * n / (statistics.mean(step_ms) / 1e3) / 1e9,
+                     "suffix_table_depth_used": depth, "suffix_table_level_bytes": table_level_bytes,
+                     "hbm_requests_per_query": accesses_per_query + (hits / ms if table_hit_bytes == LINE_BYTES else 0.0)},
             "note": ("achieved counts every index line as a 128-B HBM line fill; where part of the image stays in L2 "
                      "(oct image of the 151 Msym index: 300 MB against 126 MB of L2) the kernel runs above the HBM "
                      "random-request rate and frac can exceed what DRAM alone would allow -- `traffic` is the DRAM side"),

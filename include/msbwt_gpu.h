@@ -133,6 +133,7 @@ uint64_t msbwt_oct_overflow_occurrences(const msbwt_index *idx); /* BWT position
 uint64_t msbwt_oct_runs(const msbwt_index *idx);           /* runs of equal m-symbol codes in the BWT (chose b) */
 int msbwt_oct_bucket_shift(const msbwt_index *idx);        /* b of the oct image in use, 0 without one */
 int msbwt_oct_symbols(void);                               /* m: symbols (constrain_range steps) per oct line */
+int msbwt_table_depth_for_k(const msbwt_index *idx, uint32_t k); /* suffix-table level an all-ACGT k-mer starts from */
 
 /* ---- queries from HOST buffers (the drop-in calls) ---- */
 

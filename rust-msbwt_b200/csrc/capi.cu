@@ -15,6 +15,7 @@
 
 #include "../../include/msbwt_gpu.h"
 #include "engine.h"
+#include "kernel_common.cuh"
 #include "hostpack.h"
 
 using namespace msbwt;
@@ -616,6 +617,9 @@ extern "C" uint64_t msbwt_oct_overflow_lines(const msbwt_index *idx) { return (i
 extern "C" uint64_t msbwt_oct_overflow_occurrences(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.overflow_occurrences : 0; }
 extern "C" uint64_t msbwt_oct_runs(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.runs : 0; }
 extern "C" int msbwt_oct_symbols(void) { return kOctSyms; }
+extern "C" int msbwt_table_depth_for_k(const msbwt_index *idx, uint32_t k) {
+    return (idx && !idx->reps.empty()) ? (int)list_a_table_depth(idx->reps[0]->view, k) : 0;
+}
 extern "C" int msbwt_oct_bucket_shift(const msbwt_index *idx) { return (idx && !idx->reps.empty() && idx->reps[0]->view.oct) ? (int)idx->reps[0]->view.oct_shift : 0; }
 extern "C" uint64_t msbwt_launch_count(void) { return g_launches.load(); }
 extern "C" const char *msbwt_last_error(void) { return g_last_error.c_str(); }
