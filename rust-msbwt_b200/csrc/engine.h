@@ -78,7 +78,7 @@ void free_quad_image(QuadImage &img);
 
 // ---- oct_builder.cu: quad image + quad codes (resident on the current device) -> oct image ----
 struct OctImage {
-    uint4 *lines = nullptr;  // 65536 * nbuck8 * 128 B
+    uint4 *lines = nullptr;  // 4^m * nbuck8 * 128 B
     uint64_t nbuck8 = 0;
     int shift = 0;                      // b: log2 of the bucket size
     uint64_t runs = 0;                  // code8 runs of the BWT (what chose b)

@@ -187,7 +187,7 @@ struct IndexView {
     const uint4 *quad;       // 256 * nsec4 sectors of 32 B (2 uint4 each), or nullptr
     const uint64_t *c4base;  // n_super4 * 256 (u64), only when positions are 64-bit
     uint64_t nsec4;          // sectors per quad code: N / 224 + 2
-    const uint4 *oct;        // 65536 * nbuck8 lines of 128 B (8 uint4 each), or nullptr
+    const uint4 *oct;        // 4^m * nbuck8 lines of 128 B (8 uint4 each), or nullptr
     uint64_t nbuck8;         // buckets per oct code: (N >> oct_shift) + 1
     uint32_t oct_shift;      // b: log2 of the oct bucket size
     uint64_t total;          // N

@@ -2,7 +2,7 @@
 // per-position quad codes that are already resident on the device.
 //
 // The reference has no counterpart (its index is the sampled table of construct_fmindex,
-// src/rle_bwt.rs:387-467); what the oct image must reproduce is the composition of eight
+// src/rle_bwt.rs:387-467); what the oct image must reproduce is the composition of several
 // RleBWT::constrain_range calls (src/rle_bwt.rs:202-287) -- kOctSyms of them since the image holds ten
 // symbols per line; layout.h states the identity.
 //
@@ -183,7 +183,7 @@ int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes
     img.runs = runs;
 
     int shift = requested_shift;
-    if (!shift) {  // mean runs per line = runs * 2^shift / (65536 * N)
+    if (!shift) {  // mean runs per line = runs * 2^shift / (4^m * N)
         shift = kOctMaxShift;
         while (shift > kOctAutoMinShift &&
                (long double)runs * (long double)(1ull << shift) >

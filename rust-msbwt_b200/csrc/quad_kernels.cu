@@ -4,8 +4,8 @@
 // the module that holds every search kernel together.
 //
 // Replaces the reference's hot loop: BWT::count_kmer (src/msbwt_core.rs:125-161) calling
-// RleBWT::constrain_range (src/rle_bwt.rs:202-287) once per symbol -- here four or eight symbols per
-// index access, ten with the oct image (layout.h states the identities).
+// RleBWT::constrain_range (src/rle_bwt.rs:202-287) once per symbol -- here four symbols per index access,
+// ten with the oct image (oct_kernel.cuh; layout.h states the identities).
 #include "device_rank.cuh"
 #include "engine.h"
 #include "kernel_common.cuh"

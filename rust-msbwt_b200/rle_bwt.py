@@ -213,7 +213,7 @@ class RleBWT:
         self._pair = pair_index         # -1 auto, 0 never, 1 always: the 128-byte pair image (two steps per line)
         self._lanes = kernel_lanes      # 0 auto, 1, 2
         self._quad = quad_index         # -1 auto, 0 never, 1 always: the 32-byte quad sectors (four steps per sector)
-        self._oct = oct_index           # -1 auto, 0 never, 1 always: the 128-byte oct lines (eight steps per line)
+        self._oct = oct_index           # -1 auto, 0 never, 1 always: the 128-byte oct lines (ten steps per line)
         self._oct_shift = oct_bucket_shift  # 0 auto, else log2 of the oct bucket size (8..23)
         self._h = None
 

@@ -51,6 +51,8 @@ extern "C" {
     pub fn msbwt_quad_index(idx: *const msbwt_index) -> c_int;
     pub fn msbwt_oct_index(idx: *const msbwt_index) -> c_int;
     pub fn msbwt_oct_bucket_shift(idx: *const msbwt_index) -> c_int;
+    pub fn msbwt_oct_symbols() -> c_int;
+    pub fn msbwt_table_depth_for_k(idx: *const msbwt_index, k: u32) -> c_int;
     pub fn msbwt_oct_runs(idx: *const msbwt_index) -> u64;
     pub fn msbwt_oct_overflow_lines(idx: *const msbwt_index) -> u64;
     pub fn msbwt_oct_overflow_occurrences(idx: *const msbwt_index) -> u64;
