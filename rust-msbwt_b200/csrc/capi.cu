@@ -357,8 +357,8 @@ bool pick_quad(int device, uint64_t index_bytes, uint64_t total, int requested, 
 }
 
 // The oct image (layout.h: one 128-byte line per EIGHT steps, 1..8 B/symbol) rides on the quad image: same
-// automatic condition, 32-bit positions only; it may take a quarter of the device memory left after the quad
-// image (the builder picks coarser buckets, or builds nothing, beyond that).
+// automatic condition, 32-bit positions only; it may take the device memory left after the quad image minus its
+// own build scratch and 8 GB (the builder picks coarser buckets, or builds nothing, beyond that).
 bool pick_oct(const IndexView &view, int requested) {
     if (index_is_wide(view)) return false;
     if (requested == 0 || requested == 1) return requested == 1;
@@ -400,8 +400,10 @@ int build_quad(msbwt_index *idx, Replica &rep, int oct_requested, int oct_shift)
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
         // the kOctSyms-symbol codes (4 B per position) are scratch of the build and must fit next to the image
         const uint64_t scratch = 4 * rep.view.total;
-        const uint64_t budget = oct_requested == 1 ? (free_b > scratch ? free_b - scratch : 0)
-                                                   : (free_b / 2 > scratch ? std::min<uint64_t>(free_b / 4, free_b / 2 - scratch) : 0);
+        // what is left after that scratch and 8 GB kept for the suffix table and the query pipeline; the builder
+        // picks coarser buckets, or builds nothing, beyond it
+        const uint64_t keep = scratch + (8ull << 30);
+        const uint64_t budget = oct_requested == 1 ? (free_b > scratch ? free_b - scratch : 0) : (free_b > keep ? free_b - keep : 0);
         if (!oct_shift)
             if (const char *env = getenv("MSBWT_OCT_BUCKET_SHIFT")) oct_shift = atoi(env);
         rc = build_oct_image_on_device(rep.device, rep.view, codes4, codes2, oct_shift, budget, rep.oct, why, &n);  // frees codes4
