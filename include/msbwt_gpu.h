@@ -134,6 +134,8 @@ uint64_t msbwt_oct_runs(const msbwt_index *idx);           /* runs of equal m-sy
 int msbwt_oct_bucket_shift(const msbwt_index *idx);        /* b of the oct image in use, 0 without one */
 int msbwt_oct_symbols(void);                               /* m: symbols (constrain_range steps) per oct line */
 int msbwt_table_depth_for_k(const msbwt_index *idx, uint32_t k); /* suffix-table level an all-ACGT k-mer starts from */
+/* the same policy without an index: `steps` = symbols per step of the image (1, 2, 4 or msbwt_oct_symbols()); -1 otherwise */
+int msbwt_debug_table_depth(uint32_t k, uint32_t table_s, uint32_t steps);
 
 /* ---- queries from HOST buffers (the drop-in calls) ---- */
 

@@ -619,6 +619,13 @@ extern "C" uint64_t msbwt_oct_overflow_lines(const msbwt_index *idx) { return (i
 extern "C" uint64_t msbwt_oct_overflow_occurrences(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.overflow_occurrences : 0; }
 extern "C" uint64_t msbwt_oct_runs(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.runs : 0; }
 extern "C" int msbwt_oct_symbols(void) { return kOctSyms; }
+// the depth policy on its own (no device needed): `steps` = symbols per step of the image that serves list A
+// (1 one-step blocks, 2 pair lines, 4 quad sectors, kOctSyms oct lines)
+extern "C" int msbwt_debug_table_depth(uint32_t k, uint32_t table_s, uint32_t steps) {
+    if (steps == (uint32_t)kOctSyms) return (int)oct_table_depth(k, table_s);
+    if (steps == 1 || steps == 2 || steps == 4) return (int)acgt_table_depth(k, table_s, steps);
+    return -1;
+}
 extern "C" int msbwt_table_depth_for_k(const msbwt_index *idx, uint32_t k) {
     return (idx && !idx->reps.empty()) ? (int)list_a_table_depth(idx->reps[0]->view, k) : 0;
 }

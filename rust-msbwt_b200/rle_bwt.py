@@ -124,6 +124,7 @@ def load_library():
         "msbwt_oct_bucket_shift": (i32, [vp]),
         "msbwt_oct_symbols": (i32, []),
         "msbwt_table_depth_for_k": (i32, [vp, u32]),
+        "msbwt_debug_table_depth": (i32, [u32, u32, u32]),
         "msbwt_debug_copy_oct_image": (i32, [vp, i32, C.POINTER(u64), vp]),
         "msbwt_constrain_ranges_fanout": (i32, [vp, vp, vp, u64, vp, vp]),
         "msbwt_constrain_ranges_fanout_device": (i32, [vp, i32, vp, vp, u64, vp, vp, vp]),
@@ -157,7 +158,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
     "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_oct_index", "msbwt_oct_overflow_lines",
-    "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift", "msbwt_oct_symbols", "msbwt_table_depth_for_k",
+    "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift", "msbwt_oct_symbols", "msbwt_table_depth_for_k", "msbwt_debug_table_depth",
     "msbwt_debug_copy_oct_image", "msbwt_constrain_ranges_fanout", "msbwt_constrain_ranges_fanout_device",
     "msbwt_count_read_kmers", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
     "msbwt_debug_host_pack",

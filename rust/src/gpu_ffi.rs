@@ -53,6 +53,7 @@ extern "C" {
     pub fn msbwt_oct_bucket_shift(idx: *const msbwt_index) -> c_int;
     pub fn msbwt_oct_symbols() -> c_int;
     pub fn msbwt_table_depth_for_k(idx: *const msbwt_index, k: u32) -> c_int;
+    pub fn msbwt_debug_table_depth(k: u32, table_s: u32, steps: u32) -> c_int;
     pub fn msbwt_oct_runs(idx: *const msbwt_index) -> u64;
     pub fn msbwt_oct_overflow_lines(idx: *const msbwt_index) -> u64;
     pub fn msbwt_oct_overflow_occurrences(idx: *const msbwt_index) -> u64;

@@ -55,3 +55,41 @@ def test_tiny_batches_and_zero_queries():
         want |= c << (62 - 2 * t)
     assert int(w[0, 0]) == want
     assert M.host_pack_threads() >= 1
+
+
+def test_suffix_table_depth_policy():
+    """Which kept suffix-table level an all-ACGT k-mer starts from (kernel_common.cuh; no device needed): with a
+    pair / quad image the level that leaves a multiple of 2 / 4 symbols; with the oct image the level of the
+    four kept ones that leaves the cheapest walk (oct steps of m symbols, quad steps of four, one-symbol steps
+    at two accesses each) -- e.g. depth 11 for k = 31 under a depth-14 table: two oct steps."""
+    import rust_msbwt_b200 as M
+    L = M.load_library()
+    m = L.msbwt_oct_symbols()
+    assert m == 10
+
+    def cost(rest):
+        r = rest % m
+        return rest // m + r // 4 + 2 * (r % 4)
+
+    for ts in range(0, 17):
+        for k in range(1, 140):
+            got = L.msbwt_debug_table_depth(k, ts, m)
+            if ts == 0:
+                want = 0
+            elif k < ts:
+                want = k if k + 4 > ts else 0
+            else:
+                want, best = 0, cost(k)
+                for back in range(min(4, ts)):
+                    c = cost(k - (ts - back))
+                    if c < best:
+                        best, want = c, ts - back
+            assert got == want, (k, ts, got, want)
+            for stride in (1, 2, 4):
+                d = L.msbwt_debug_table_depth(k, ts, stride)
+                assert 0 <= d <= min(k, ts)
+                if d and k >= ts:
+                    assert (k - d) % stride == 0 and ts - d < stride
+    assert L.msbwt_debug_table_depth(31, 14, m) == 11
+    assert L.msbwt_debug_table_depth(31, 15, 4) == 15
+    assert L.msbwt_debug_table_depth(31, 14, 3) == -1
