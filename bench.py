@@ -415,7 +415,7 @@ def measure_ours(args, cfg, ctx, primary: bool):
             # quad path: four of the reference's constrain_range calls per 32-B sector.  An L2 miss fills the
             # whole 128-B line, so the bytes HBM must move are counted per distinct LINE (l and h share one
             # 97 % of the time); the sector-granular figure is reported beside it.
-            # with the oct image on top: eight calls per 128-B line while >= 8 symbols are left
+            # with the oct image on top: M.oct_symbols() (ten) calls per 128-B line while that many symbols are left
             st = orc.count_kmers_stats_quad(q_host[:ms], k, table_s, QUAD_SYMS, LINE_BYTES // QUAD_SECTOR_BYTES, BLOCK_SHIFT,
                                             bwt.oct_bucket_shift if bwt.oct_index else 0, M.oct_symbols())
             hits = st["table_hits"]

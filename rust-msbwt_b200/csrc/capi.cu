@@ -356,7 +356,7 @@ bool pick_quad(int device, uint64_t index_bytes, uint64_t total, int requested, 
     return need <= (64ull << 30) && need <= free_b / 2;
 }
 
-// The oct image (layout.h: one 128-byte line per EIGHT steps, 1..8 B/symbol) rides on the quad image: same
+// The oct image (layout.h: one 128-byte line per kOctSyms = 10 steps) rides on the quad image: same
 // automatic condition, 32-bit positions only; it may take the device memory left after the quad image minus its
 // own build scratch and 8 GB (the builder picks coarser buckets, or builds nothing, beyond that).
 bool pick_oct(const IndexView &view, int requested) {

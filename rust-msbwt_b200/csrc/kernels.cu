@@ -53,20 +53,24 @@ __device__ __forceinline__ uint64_t append_live(bool live, bool list_a, unsigned
     return list_a ? warp_base[0][warp] + __popc(mask_a & below) : n - 1 - (warp_base[1][warp] + __popc(mask_b & below));
 }
 
+// resident CTAs per SM the fixed-k instantiation of the pack kernel is compiled for (engine.h: register budget)
+#ifndef MSBWT_PACK_CTAS_FIXED_K
+#define MSBWT_PACK_CTAS_FIXED_K 8
+#endif
 constexpr uint32_t kPackSmemMaxK = 160;  // 256 * k + 64 bytes of shared memory; longer k-mers read global memory
 constexpr uint32_t kPackMaxWords = (kPackSmemMaxK + kPairSymsPerWord - 1) / kPairSymsPerWord;  // 5
 
 // Seeds one all-ACGT k-mer given as 2-bit words (`get(w)`, w < nw: the k-mer's last symbol in the top
 // bits of word 0): suffix-table lookup at the depth acgt_table_depth picks, then either the final count
 // (written by the caller) or the remaining symbols re-aligned to the top of word 0 and stored for the
-// search kernel.  Returns through the reference arguments; stores words 1.. itself.
+// search kernel.  Returns through the reference arguments; stores words 1.. itself.  `done` =
+// list_a_table_depth(ix, k), uniform over the batch: the launch wrappers compute it once on the host.
 template <bool WIDE, class GetWord>
-__device__ __forceinline__ void seed_acgt(const IndexView &ix, uint32_t k, uint32_t nw, GetWord get, const PackedLayout &lay,
+__device__ __forceinline__ void seed_acgt(const IndexView &ix, uint32_t k, uint32_t done, uint32_t nw, GetWord get, const PackedLayout &lay,
                                           uint64_t q, uint64_t *__restrict__ packed, uint64_t &lo, uint64_t &hi,
                                           uint32_t &flag, bool &list_a, bool &finished, uint64_t &word0) {
     const uint32_t ts = ix.table_s;
     const uint32_t stride = list_a_stride(ix);
-    const uint32_t done = list_a_table_depth(ix, k);
     // the quad kernel finishes a remainder with one-step ranks; the pair kernel cannot
     list_a = stride != 2u || ((k - done) & 1u) == 0;
     lo = 0; hi = ix.total; flag = 0;
@@ -173,10 +177,13 @@ __device__ __forceinline__ void seed_general(const IndexView &ix, const uint8_t 
 //      depth table_s when its last table_s symbols are ACGT, 3 bits per symbol (seed_general);
 //   3. finishes the query right here when nothing is left to search (empty range -> count 0,
 //      msbwt_core.rs:151-153; or no symbols left -> h-l), or appends it to its live list.
-template <bool WIDE>
-__global__ void __launch_bounds__(256)
-pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, PackedLayout lay,
+// K = the k-mer length when it is one the library is compiled for (31: the headline query; every shift, mask
+// and word count of steps 1-2 is then a constant), 0 = any length (`k_rt`).  `depth` = list_a_table_depth(ix, k).
+template <bool WIDE, uint32_t K>
+__global__ void __launch_bounds__(256, K ? MSBWT_PACK_CTAS_FIXED_K : 6)
+pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k_rt, uint32_t depth, PackedLayout lay,
                  uint64_t *__restrict__ packed, uint64_t *__restrict__ out, uint32_t *__restrict__ status) {
+    const uint32_t k = K ? K : k_rt;
     extern __shared__ uint4 pack_smem_v[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(pack_smem_v);
     const uint64_t q0 = (uint64_t)blockIdx.x * blockDim.x;
@@ -247,7 +254,7 @@ pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, Pac
                 for (uint32_t j = 1; j < kPackMaxWords; j++) if (j == w) v = w2[j];
                 return v;
             };
-            seed_acgt<WIDE>(ix, k, nw, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
+            seed_acgt<WIDE>(ix, k, depth, nw, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
         }
     }
     if (general) seed_general<WIDE>(ix, src, k, lay, q, packed, lo, hi, flag, finished, word0, bad);
@@ -273,7 +280,7 @@ pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k, Pac
 // appends to list A (or finishes the query).  No symbol bytes ever reach the device on this path.
 template <bool WIDE>
 __global__ void __launch_bounds__(256)
-seed_packed_kernel(IndexView ix, const uint64_t *__restrict__ words, uint32_t k, PackedLayout lay,
+seed_packed_kernel(IndexView ix, const uint64_t *__restrict__ words, uint32_t k, uint32_t depth, PackedLayout lay,
                    uint64_t *__restrict__ packed, uint64_t *__restrict__ out) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = q < lay.n;
@@ -283,7 +290,7 @@ seed_packed_kernel(IndexView ix, const uint64_t *__restrict__ words, uint32_t k,
     bool list_a = false, finished = false;
     if (valid) {
         auto get = [&](uint32_t w) { return __ldg(words + (uint64_t)w * lay.n + q); };
-        seed_acgt<WIDE>(ix, k, nw, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
+        seed_acgt<WIDE>(ix, k, depth, nw, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
         if (finished) out[q] = hi - lo;
     }
     const bool live = valid && !finished;
@@ -584,8 +591,10 @@ cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     const size_t smem = k <= kPackSmemMaxK ? 256u * (size_t)k + 64u : 0u;
-    if (is_wide(ix)) pack_seed_kernel<true><<<blocks, 256, smem, st>>>(ix, d_syms, k, lay, d_packed, d_out, d_status);
-    else pack_seed_kernel<false><<<blocks, 256, smem, st>>>(ix, d_syms, k, lay, d_packed, d_out, d_status);
+    const uint32_t depth = list_a_table_depth(ix, k);
+    if (is_wide(ix)) pack_seed_kernel<true, 0><<<blocks, 256, smem, st>>>(ix, d_syms, k, depth, lay, d_packed, d_out, d_status);
+    else if (k == 31) pack_seed_kernel<false, 31><<<blocks, 256, smem, st>>>(ix, d_syms, k, depth, lay, d_packed, d_out, d_status);
+    else pack_seed_kernel<false, 0><<<blocks, 256, smem, st>>>(ix, d_syms, k, depth, lay, d_packed, d_out, d_status);
     return cudaGetLastError();
 }
 
@@ -648,8 +657,9 @@ cudaError_t launch_seed_packed(const IndexView &ix, const uint64_t *d_words, uin
     cudaError_t e = cudaMemsetAsync(d_packed + lay.live(), 0, 2 * sizeof(uint64_t), st);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    if (is_wide(ix)) seed_packed_kernel<true><<<blocks, 256, 0, st>>>(ix, d_words, k, lay, d_packed, d_out);
-    else seed_packed_kernel<false><<<blocks, 256, 0, st>>>(ix, d_words, k, lay, d_packed, d_out);
+    const uint32_t depth = list_a_table_depth(ix, k);
+    if (is_wide(ix)) seed_packed_kernel<true><<<blocks, 256, 0, st>>>(ix, d_words, k, depth, lay, d_packed, d_out);
+    else seed_packed_kernel<false><<<blocks, 256, 0, st>>>(ix, d_words, k, depth, lay, d_packed, d_out);
     return cudaGetLastError();
 }
 
