@@ -62,6 +62,31 @@ __device__ __forceinline__ uint32_t swar_pack4(uint32_t x) {
     return (c | (c >> 12)) & 0xFFu;
 }
 
+// The same two jobs in one pass through an 8-entry byte table (PRMT): the four symbol bytes become four selector
+// nibbles, the table answers A,C,G,T = 1,2,3,5 with their 2-bit codes and every other symbol < 8 with 0x80.
+// `acc` collects x | table bytes: the k-mer holds a symbol outside ACGT iff (acc & kSwarBadMask) != 0 at the end
+// (a byte >= 8 shows in x itself, whatever the table then answers).  Returns the four codes packed into the TOP
+// byte (byte i of x at bits 24 + 2i; one multiply: the partial products do not overlap), meaningful only when
+// the word is clean; swar_gather4 collects the top bytes of four such words.  7 instructions per word against
+// 17 for swar_non_acgt + swar_pack4 + the shift into place.
+constexpr uint32_t kSwarBadMask = 0xF8F8F8F8u;
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {  // no & 0x7777 as in __byte_perm
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t swar_lut_pack4_top(uint32_t x, uint32_t &acc) {
+    const uint32_t t = x + (x >> 4);                                // byte 0 = b0 | b1 << 4, byte 2 = b2 | b3 << 4
+    const uint32_t sel = prmt_b32(t, 0u, 0x4420u);                  // selector nibbles b0, b1, b2, b3 (all < 8 if clean)
+    const uint32_t y = prmt_b32(0x02010080u, 0x80800380u, sel);     // table[0..7] = 80 00 01 02 80 03 80 80
+    acc |= x | y;
+    return y * 0x01041040u;
+}
+// top bytes of four words -> one word, word i at byte i
+__device__ __forceinline__ uint32_t swar_gather4(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    return prmt_b32(prmt_b32(m0, m1, 0x0073u), prmt_b32(m2, m3, 0x0073u), 0x5410u);
+}
+
 inline int sm_count(int device) {
     static int cached[64];
     if (device < 0 || device >= 64) return 148;

@@ -57,33 +57,55 @@ __device__ __forceinline__ uint64_t append_live(bool live, bool list_a, unsigned
 #ifndef MSBWT_PACK_CTAS_FIXED_K
 #define MSBWT_PACK_CTAS_FIXED_K 8
 #endif
+// 16 bytes from global to shared memory without passing through registers (L2 only: the bytes are read once)
+__device__ __forceinline__ void stage_cp_async16(void *smem, const void *gmem) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem) : "memory");
+}
+
+constexpr uint32_t kPackThreads = 256;   // CTA size of the pack / seed kernels (append_live counts eight warps)
 constexpr uint32_t kPackSmemMaxK = 160;  // 256 * k + 64 bytes of shared memory; longer k-mers read global memory
 constexpr uint32_t kPackMaxWords = (kPackSmemMaxK + kPairSymsPerWord - 1) / kPairSymsPerWord;  // 5
 
 // Seeds one all-ACGT k-mer given as 2-bit words (`get(w)`, w < nw: the k-mer's last symbol in the top
 // bits of word 0): suffix-table lookup at the depth acgt_table_depth picks, then either the final count
 // (written by the caller) or the remaining symbols re-aligned to the top of word 0 and stored for the
-// search kernel.  Returns through the reference arguments; stores words 1.. itself.  `done` =
-// list_a_table_depth(ix, k), uniform over the batch: the launch wrappers compute it once on the host.
+// search kernel.  Returns through the reference arguments; stores words 1.. itself.
+// What seed_acgt needs to know about the batch, uniform over its queries and computed once on the host by the
+// launch wrappers: the suffix-table level an all-ACGT k-mer of this length starts from (list_a_table_depth), that
+// level's array, the flag the pair / one-step kernels read their resume depth from, and whether list A takes it.
+struct SeedPlan {
+    const void *tab;
+    uint32_t depth;
+    uint32_t flag;
+    uint32_t list_a;
+};
+static SeedPlan make_seed_plan(const IndexView &ix, uint32_t k) {
+    SeedPlan p{nullptr, list_a_table_depth(ix, k), 0u, 0u};
+    // the quad kernel finishes a remainder with one-step ranks; the pair kernel cannot
+    p.list_a = (list_a_stride(ix) != 2u || ((k - p.depth) & 1u) == 0) ? 1u : 0u;
+    if (p.depth) {
+        const uint32_t back = ix.table_s - p.depth;  // 0..3
+        p.flag = back < 2u ? back + 1u : 0u;         // read by the pair / one-step kernels only (back <= 1 there)
+        p.tab = back == 0 ? ix.table : (back == 1 ? ix.table2 : (back == 2 ? ix.table3 : ix.table4));
+    }
+    return p;
+}
+
 template <bool WIDE, class GetWord>
-__device__ __forceinline__ void seed_acgt(const IndexView &ix, uint32_t k, uint32_t done, uint32_t nw, GetWord get, const PackedLayout &lay,
+__device__ __forceinline__ void seed_acgt(const IndexView &ix, uint32_t k, const SeedPlan &plan, uint32_t nw, GetWord get, const PackedLayout &lay,
                                           uint64_t q, uint64_t *__restrict__ packed, uint64_t &lo, uint64_t &hi,
                                           uint32_t &flag, bool &list_a, bool &finished, uint64_t &word0) {
-    const uint32_t ts = ix.table_s;
-    const uint32_t stride = list_a_stride(ix);
-    // the quad kernel finishes a remainder with one-step ranks; the pair kernel cannot
-    list_a = stride != 2u || ((k - done) & 1u) == 0;
-    lo = 0; hi = ix.total; flag = 0;
+    const uint32_t done = plan.depth;
+    list_a = plan.list_a != 0;
+    lo = 0; hi = ix.total; flag = plan.flag;
     if (done) {
-        const uint32_t back = ts - done;  // 0..3
-        flag = back < 2u ? back + 1u : 0u;  // read by the pair / one-step kernels only (back <= 1 there)
         const uint64_t e = get(0) >> (64u - 2u * done);
-        const void *tab = back == 0 ? ix.table : (back == 1 ? ix.table2 : (back == 2 ? ix.table3 : ix.table4));
         if constexpr (WIDE) {
-            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(tab) + e);
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(plan.tab) + e);
             lo = v.x; hi = v.y;
         } else {
-            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(tab) + e);
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(plan.tab) + e);
             lo = v.x; hi = v.y;
         }
     }
@@ -95,7 +117,7 @@ __device__ __forceinline__ void seed_acgt(const IndexView &ix, uint32_t k, uint3
         uint64_t cur = get(0);
 #pragma unroll
         for (uint32_t w = 0; w < kPackMaxWords; w++) {
-            if (w < nout) {
+            if (w < nout && w < nw) {  // nout <= nw; nw is a constant in the fixed-k instantiations
                 const uint64_t nxt = (w + 1 < nw) ? get(w + 1) : 0;
                 const uint64_t word = done ? (cur << (2u * done)) | (nxt >> (64u - 2u * done)) : cur;
                 if (w == 0) word0 = word; else packed[lay.wx() + (uint64_t)(w - 1) * lay.n + q] = word;
@@ -178,15 +200,15 @@ __device__ __forceinline__ void seed_general(const IndexView &ix, const uint8_t 
 //   3. finishes the query right here when nothing is left to search (empty range -> count 0,
 //      msbwt_core.rs:151-153; or no symbols left -> h-l), or appends it to its live list.
 // K = the k-mer length when it is one the library is compiled for (31: the headline query; every shift, mask
-// and word count of steps 1-2 is then a constant), 0 = any length (`k_rt`).  `depth` = list_a_table_depth(ix, k).
+// and word count of steps 1-2 is then a constant), 0 = any length (`k_rt`).
 template <bool WIDE, uint32_t K>
 __global__ void __launch_bounds__(256, K ? MSBWT_PACK_CTAS_FIXED_K : 6)
-pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k_rt, uint32_t depth, PackedLayout lay,
+pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k_rt, SeedPlan plan, PackedLayout lay,
                  uint64_t *__restrict__ packed, uint64_t *__restrict__ out, uint32_t *__restrict__ status) {
     const uint32_t k = K ? K : k_rt;
     extern __shared__ uint4 pack_smem_v[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(pack_smem_v);
-    const uint64_t q0 = (uint64_t)blockIdx.x * blockDim.x;
+    const uint64_t q0 = (uint64_t)blockIdx.x * kPackThreads;
     const uint64_t q = q0 + threadIdx.x;
     const bool valid = q < lay.n;
     const bool staged = k <= kPackSmemMaxK;
@@ -194,16 +216,29 @@ pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k_rt, 
     uint32_t row = 0;  // byte offset of this thread's k-mer in shared memory
     if (staged) {
         const uint8_t *g = syms + q0 * k;
-        const uint32_t rows = (uint32_t)min((uint64_t)blockDim.x, lay.n - q0);
+        const uint32_t rows = (uint32_t)min((uint64_t)kPackThreads, lay.n - q0);
         const uint32_t bytes = rows * k;
         const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);  // smem mirrors the global alignment
-        const uint32_t head = min(bytes, (16u - mis) & 15u);
-        for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) smem[mis + i] = g[i];
+        const uint32_t head = min(bytes, (16u - mis) & 15u);                    // < 16 <= kPackThreads: one pass
+        if (threadIdx.x < head) smem[mis + threadIdx.x] = g[threadIdx.x];
         const uint32_t vecs = (bytes - head) >> 4;
         const uint4 *gv = reinterpret_cast<const uint4 *>(g + head);
         uint4 *sv = reinterpret_cast<uint4 *>(smem + mis + head);
-        for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x) sv[i] = ldg_plain(gv + i);
-        for (uint32_t i = head + (vecs << 4) + threadIdx.x; i < bytes; i += blockDim.x) smem[mis + i] = g[i];
+        // no registers held: every round in flight
+        if constexpr (K != 0) {
+            constexpr uint32_t kRounds = (K + 15u) / 16u;  // vecs <= 256 * K / 16: two rounds for K = 31
+#pragma unroll
+            for (uint32_t r = 0; r < kRounds; r++) {
+                const uint32_t i = threadIdx.x + r * kPackThreads;
+                if (i < vecs) stage_cp_async16(sv + i, gv + i);
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < vecs; i += kPackThreads) stage_cp_async16(sv + i, gv + i);
+        }
+        const uint32_t at = head + (vecs << 4) + threadIdx.x;                    // < 16 bytes are left
+        if (at < bytes) smem[mis + at] = g[at];
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
         row = mis + threadIdx.x * k;
         src = smem + row;
@@ -229,7 +264,7 @@ pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k_rt, 
                 const uint32_t *p = sw + (o >> 2);
                 const uint32_t sh = (o & 3u) * 8u;
                 uint32_t prev = p[0];
-                uint64_t le = 0;
+                uint32_t m[8];
 #pragma unroll
                 for (uint32_t i = 0; i < 8; i++) {
                     const uint32_t nxt = p[i + 1];
@@ -239,13 +274,14 @@ pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k_rt, 
                         const uint32_t keep = c > 4u * i ? (1u << (8u * (c - 4u * i))) - 1u : 0u;
                         x = (x & keep) | (0x01010101u & ~keep);
                     }
-                    other |= swar_non_acgt(x);
-                    le |= (uint64_t)swar_pack4(x) << (8u * i);
+                    m[i] = swar_lut_pack4_top(x, other);
                 }
+                const uint64_t le = (uint64_t)swar_gather4(m[0], m[1], m[2], m[3]) |
+                                    ((uint64_t)swar_gather4(m[4], m[5], m[6], m[7]) << 32);
                 w2[w] = le << (64u - 2u * c);
             }
         }
-        if (other) {
+        if (other & kSwarBadMask) {
             general = true;
         } else {
             auto get = [&](uint32_t w) {
@@ -254,7 +290,7 @@ pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k_rt, 
                 for (uint32_t j = 1; j < kPackMaxWords; j++) if (j == w) v = w2[j];
                 return v;
             };
-            seed_acgt<WIDE>(ix, k, depth, nw, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
+            seed_acgt<WIDE>(ix, k, plan, nw, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
         }
     }
     if (general) seed_general<WIDE>(ix, src, k, lay, q, packed, lo, hi, flag, finished, word0, bad);
@@ -280,7 +316,7 @@ pack_seed_kernel(IndexView ix, const uint8_t *__restrict__ syms, uint32_t k_rt, 
 // appends to list A (or finishes the query).  No symbol bytes ever reach the device on this path.
 template <bool WIDE>
 __global__ void __launch_bounds__(256)
-seed_packed_kernel(IndexView ix, const uint64_t *__restrict__ words, uint32_t k, uint32_t depth, PackedLayout lay,
+seed_packed_kernel(IndexView ix, const uint64_t *__restrict__ words, uint32_t k, SeedPlan plan, PackedLayout lay,
                    uint64_t *__restrict__ packed, uint64_t *__restrict__ out) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = q < lay.n;
@@ -290,7 +326,7 @@ seed_packed_kernel(IndexView ix, const uint64_t *__restrict__ words, uint32_t k,
     bool list_a = false, finished = false;
     if (valid) {
         auto get = [&](uint32_t w) { return __ldg(words + (uint64_t)w * lay.n + q); };
-        seed_acgt<WIDE>(ix, k, depth, nw, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
+        seed_acgt<WIDE>(ix, k, plan, nw, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
         if (finished) out[q] = hi - lo;
     }
     const bool live = valid && !finished;
@@ -591,10 +627,10 @@ cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     const size_t smem = k <= kPackSmemMaxK ? 256u * (size_t)k + 64u : 0u;
-    const uint32_t depth = list_a_table_depth(ix, k);
-    if (is_wide(ix)) pack_seed_kernel<true, 0><<<blocks, 256, smem, st>>>(ix, d_syms, k, depth, lay, d_packed, d_out, d_status);
-    else if (k == 31) pack_seed_kernel<false, 31><<<blocks, 256, smem, st>>>(ix, d_syms, k, depth, lay, d_packed, d_out, d_status);
-    else pack_seed_kernel<false, 0><<<blocks, 256, smem, st>>>(ix, d_syms, k, depth, lay, d_packed, d_out, d_status);
+    const SeedPlan plan = make_seed_plan(ix, k);
+    if (is_wide(ix)) pack_seed_kernel<true, 0><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
+    else if (k == 31) pack_seed_kernel<false, 31><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
+    else pack_seed_kernel<false, 0><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
     return cudaGetLastError();
 }
 
@@ -657,9 +693,9 @@ cudaError_t launch_seed_packed(const IndexView &ix, const uint64_t *d_words, uin
     cudaError_t e = cudaMemsetAsync(d_packed + lay.live(), 0, 2 * sizeof(uint64_t), st);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    const uint32_t depth = list_a_table_depth(ix, k);
-    if (is_wide(ix)) seed_packed_kernel<true><<<blocks, 256, 0, st>>>(ix, d_words, k, depth, lay, d_packed, d_out);
-    else seed_packed_kernel<false><<<blocks, 256, 0, st>>>(ix, d_words, k, depth, lay, d_packed, d_out);
+    const SeedPlan plan = make_seed_plan(ix, k);
+    if (is_wide(ix)) seed_packed_kernel<true><<<blocks, 256, 0, st>>>(ix, d_words, k, plan, lay, d_packed, d_out);
+    else seed_packed_kernel<false><<<blocks, 256, 0, st>>>(ix, d_words, k, plan, lay, d_packed, d_out);
     return cudaGetLastError();
 }
 
