@@ -93,3 +93,54 @@ def test_suffix_table_depth_policy():
     assert L.msbwt_debug_table_depth(31, 14, m) == 11
     assert L.msbwt_debug_table_depth(31, 15, 4) == 15
     assert L.msbwt_debug_table_depth(31, 14, 3) == -1
+
+
+def test_pack_kernel_table_arithmetic_is_exact_for_every_symbol_word():
+    """The pack / seed kernels validate and 2-bit-pack four symbol bytes at a time through an 8-entry PRMT byte
+    table and one multiply (swar_lut_pack4_top / swar_gather4, kernel_common.cuh).  The constants are read from
+    the source and the arithmetic is replayed with PTX `prmt.b32` semantics (generic mode: the 3 low bits of a
+    selector nibble pick one of the 8 source bytes, the top bit replicates that byte's sign) over every word of
+    four bytes drawn from a set that holds all symbols 0..9 and bytes with every high bit: a word is flagged
+    iff some byte is outside ACGT = {1,2,3,5} (the reference's count_kmer takes any symbol < 6,
+    msbwt_core.rs:127; the others go to the byte-wise path), and a clean word packs to byte i at bits 2i."""
+    import itertools
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                            "rust-msbwt_b200", "csrc", "kernel_common.cuh")).read()
+    body = src[src.index("swar_lut_pack4_top(uint32_t x"):src.index("inline int sm_count")]
+    bad_mask = int(re.search(r"kSwarBadMask = (0x[0-9A-Fa-f]+)u", src).group(1), 16)
+    sel_nibbles = int(re.search(r"prmt_b32\(t, 0u, (0x[0-9A-Fa-f]+)u\)", body).group(1), 16)
+    lut_lo, lut_hi = (int(v, 16) for v in re.search(r"prmt_b32\((0x[0-9A-Fa-f]+)u, (0x[0-9A-Fa-f]+)u, sel\)", body).groups())
+    mul = int(re.search(r"return y \* (0x[0-9A-Fa-f]+)u", body).group(1), 16)
+    pair_sel = int(re.search(r"prmt_b32\(m0, m1, (0x[0-9A-Fa-f]+)u\)", body).group(1), 16)
+    join_sel = int(re.search(r"\), (0x[0-9A-Fa-f]+)u\);\n\}", body).group(1), 16)
+
+    def prmt(a, b, sel):
+        srcb = [(a >> (8 * i)) & 0xFF for i in range(4)] + [(b >> (8 * i)) & 0xFF for i in range(4)]
+        out = 0
+        for i in range(4):
+            nib = (sel >> (4 * i)) & 0xF
+            byte = srcb[nib & 7]
+            if nib & 8:
+                byte = 0xFF if byte & 0x80 else 0
+            out |= byte << (8 * i)
+        return out
+
+    def top(x):
+        t = (x + (x >> 4)) & 0xFFFFFFFF
+        y = prmt(lut_lo, lut_hi, prmt(t, 0, sel_nibbles))
+        return (y * mul) & 0xFFFFFFFF, x | y
+
+    code = {1: 0, 2: 1, 3: 2, 5: 3}
+    vals = list(range(10)) + [0x0F, 0x10, 0x11, 0x15, 0x21, 0x51, 0x80, 0xF0, 0xFF]
+    for bs in itertools.product(vals, repeat=4):
+        x = bs[0] | bs[1] << 8 | bs[2] << 16 | bs[3] << 24
+        m, acc = top(x)
+        clean = all(b in code for b in bs)
+        assert ((acc & bad_mask) != 0) == (not clean), bs
+        if clean:
+            assert m >> 24 == sum(code[b] << (2 * i) for i, b in enumerate(bs)), bs
+    ms = [0x12345678, 0x9ABCDEF0, 0x0F1E2D3C, 0xC0FFEE11]
+    g = prmt(prmt(ms[0], ms[1], pair_sel), prmt(ms[2], ms[3], pair_sel), join_sel)
+    assert g == sum((ms[i] >> 24) << (8 * i) for i in range(4))
