@@ -1,0 +1,53 @@
+"""The `bench.py --impl reference` arm (the reference's own CPU algorithm -- the oracle port, since the Rust crate
+cannot be built here -- timed on the host cores) runs without a GPU: its JSON line must carry the keys the driver
+reads, and under torchrun only rank 0 may work and print.  The `ours` arm needs a B200 and must refuse to run
+without one (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_bench(*argv, env=None):
+    e = dict(os.environ)
+    e.pop("RANK", None)
+    e.pop("WORLD_SIZE", None)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *argv], capture_output=True, text=True,
+                          env=e, timeout=600)
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    res = run_bench("--impl", "reference", "--workload", "tiny", "--steps", "2", "--warmup", "1")
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "stdout carries exactly one JSON line"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference"
+    assert d["metric"] == "count_kmer_31mer_queries_per_sec" and d["unit"] == "queries/s"
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["dtype"] == "u64" and d["data"] == "synthetic" and d["gpu_launches"] == 0
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"].startswith("tiny") and d["config"]["k"] == 31 and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "queries per step" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    res = run_bench("--impl", "reference", "--workload", "tiny", "--gpus", "2", env={"RANK": "1", "WORLD_SIZE": "2"})
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip() == ""
+
+
+def test_our_arm_refuses_to_run_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    res = run_bench("--workload", "tiny", "--steps", "1", "--warmup", "1")
+    assert res.returncode != 0
+    assert "no CPU fallback" in (res.stderr + res.stdout)
