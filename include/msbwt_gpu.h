@@ -157,6 +157,14 @@ int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, const uint64_
  * are identical either way.  `syms` and `out` may be pageable or pinned (msbwt_host_alloc). */
 int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n,
                             uint64_t *out);
+/* The same counts for k-mers the caller already holds as integers, 2 bits per symbol -- what k-mer counting
+ * pipelines keep: k <= 32, kmers[i] = sum over j of code(s_j) << 2*(k-1-j) with A,C,G,T = 0,1,2,3 and s_0 the FIRST
+ * symbol (bits above 2k are ignored); out[i] = BWT::count_kmer of that k-mer (src/msbwt_core.rs:125-161).  Nothing is
+ * packed or validated anywhere (such a k-mer cannot hold `$` or `N`): the link carries 8 bytes per query each way
+ * instead of k bytes in.  EINVAL when k == 0 or k > 32.
+ * EXPERIMENTAL in this round: built and exported, parity tests written (tests/test_gpu_u64_kmers.py) but not yet run
+ * on a GPU -- they are skipped unless MSBWT_EXPERIMENTAL=1. */
+int msbwt_count_kmers_u64(const msbwt_index *idx, const uint64_t *kmers, uint32_t k, uint64_t n, uint64_t *out);
 /* host->device and device->host bytes moved by the calling thread's last msbwt_count_kmers_fixed */
 void msbwt_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
 int msbwt_host_pack_threads(void); /* size the packing pool would have in this process */

@@ -949,6 +949,71 @@ extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *sy
     return use_host_pack(k, n) ? fixed_packed_path(idx, syms, k, n, out) : fixed_bytes_path(idx, syms, k, n, out);
 }
 
+namespace {
+
+// K-mers the caller already holds as integers (k <= 32): nothing to do on the host, 8 bytes per query over the
+// link each way.  Chunks go round-robin over devices and lanes; a lane's stream orders copy-in, seed, search and
+// copy-out, so its buffers are reused safely by its next chunk.  Caller holds the replica locks.
+int u64_path(const msbwt_index *idx, const uint64_t *kmers, uint32_t k, uint64_t n, uint64_t *out) {
+    const size_t ndev = idx->reps.size();
+    const uint64_t chunk = kPackedChunkQueries;
+    uint64_t max_chunks = 0;
+    for (size_t d = 0; d < ndev; d++) {
+        Replica &rep = *idx->reps[d];
+        DeviceGuard guard(rep.device);
+        const Slice sl = slice_for(n, d, ndev);
+        const uint64_t len = sl.end - sl.begin;
+        const uint64_t c = std::max<uint64_t>(1, std::min(chunk, len));
+        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
+        for (auto &ln : rep.lane) {
+            CU_TRY(cudaStreamSynchronize(ln.stream));
+            CU_TRY(ln.in_b.reserve(c * sizeof(uint64_t)));
+            CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, c).total() * sizeof(uint64_t)));
+            CU_TRY(ln.out_a.reserve(c * sizeof(uint64_t)));
+        }
+    }
+    for (uint64_t c = 0; c < max_chunks; c++) {
+        for (size_t d = 0; d < ndev; d++) {
+            Replica &rep = *idx->reps[d];
+            const Slice sl = slice_for(n, d, ndev);
+            const uint64_t b = sl.begin + c * chunk;
+            if (b >= sl.end) continue;
+            const uint64_t m = std::min(chunk, sl.end - b);
+            DeviceGuard guard(rep.device);
+            Lane &ln = rep.lane[c % kLanes];
+            CU_TRY(cudaMemcpyAsync(ln.in_b.p, kmers + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(launch_seed_u64(rep.view, ln.in_b.as<uint64_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
+                                   ln.stream));
+            g_launches++;
+            CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
+                                       ln.stream, &g_call_launches, packed_batch_needs_list_b(rep.view, k)));
+            flush_launches();
+            CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+            g_last_h2d += m * sizeof(uint64_t);
+            g_last_d2h += m * sizeof(uint64_t);
+        }
+    }
+    for (auto &rep : idx->reps) {
+        DeviceGuard guard(rep->device);
+        for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
+    }
+    return MSBWT_OK;
+}
+
+}  // namespace
+
+extern "C" int msbwt_count_kmers_u64(const msbwt_index *idx, const uint64_t *kmers, uint32_t k, uint64_t n, uint64_t *out) {
+    g_last_error.clear();
+    g_last_h2d = g_last_d2h = 0;
+    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
+    if (k == 0 || k > 32) return fail(MSBWT_EINVAL, "count_kmers_u64: k must be 1..32 (one 2-bit-per-symbol word per k-mer)");
+    if (n && (!out || !kmers)) return fail(MSBWT_EINVAL, "NULL host buffer");
+    if (!n) return MSBWT_OK;
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
+    return u64_path(idx, kmers, k, n, out);
+}
+
 extern "C" void msbwt_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h) {
     if (h2d) *h2d = g_last_h2d;
     if (d2h) *d2h = g_last_d2h;

@@ -147,6 +147,9 @@ cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, cons
 // top bits of word 0 -> live list A (same scratch layout as launch_pack_seed produces)
 cudaError_t launch_seed_packed(const IndexView &ix, const uint64_t *d_words, uint32_t k, uint64_t n,
                                uint64_t *d_packed, uint64_t *d_out, cudaStream_t st);
+// caller-packed batches, k <= 32: kmers[q] = the k-mer as a 2k-bit integer, first symbol most significant -> live list A
+cudaError_t launch_seed_u64(const IndexView &ix, const uint64_t *d_kmers, uint32_t k, uint64_t n,
+                            uint64_t *d_packed, uint64_t *d_out, cudaStream_t st);
 // quad_kernels.cu: live list A over the quad (and oct) image
 cudaError_t launch_count_quad(int device, const IndexView &ix, const uint64_t *d_packed, const PackedLayout &lay,
                               uint32_t k, uint64_t *d_out, cudaStream_t st);

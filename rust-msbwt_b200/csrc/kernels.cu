@@ -343,6 +343,44 @@ seed_packed_kernel(IndexView ix, const uint64_t *__restrict__ words, uint32_t k,
     }
 }
 
+// K0c: the same job for k-mers the CALLER holds as integers -- k <= 32, kmers[q] = sum code(s_i) << 2 (k-1-i), A,C,G,T =
+// 0..3, the first symbol in the most significant of the 2k bits: what k-mer counters keep.  Reversing the 2-bit groups of
+// the word puts the k-mer's LAST symbol in the top bits, which is the word format of live list A; bits above 2k are ignored.
+// Every such k-mer is all-ACGT by construction: nothing to validate, no list B unless the pair image leaves an odd remainder.
+__device__ __forceinline__ uint64_t reverse_symbol_pairs(uint64_t x) {
+    const uint64_t r = __brevll(x);
+    return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+}
+template <bool WIDE>
+__global__ void __launch_bounds__(256)
+seed_u64_kernel(IndexView ix, const uint64_t *__restrict__ kmers, uint32_t k, SeedPlan plan, PackedLayout lay,
+                uint64_t *__restrict__ packed, uint64_t *__restrict__ out) {
+    const uint64_t q = (uint64_t)blockIdx.x * kPackThreads + threadIdx.x;
+    const bool valid = q < lay.n;
+    uint64_t lo = 0, hi = 0, word0 = 0;
+    uint32_t flag = 0;
+    bool list_a = false, finished = false;
+    if (valid) {
+        const uint64_t x = __ldg(kmers + q) & (k >= 32u ? ~0ull : ((1ull << (2u * k)) - 1ull));
+        const uint64_t w = reverse_symbol_pairs(x);
+        auto get = [&](uint32_t) { return w; };
+        seed_acgt<WIDE>(ix, k, plan, 1u, get, lay, q, packed, lo, hi, flag, list_a, finished, word0);
+        if (finished) out[q] = hi - lo;
+    }
+    const bool live = valid && !finished;
+    const uint64_t pos = append_live(live, list_a, reinterpret_cast<unsigned long long *>(packed + lay.live()), lay.n);
+    if (live) {
+        packed[lay.w0() + pos] = word0;
+        if constexpr (WIDE) {
+            packed[lay.seed() + pos] = lo;
+            packed[lay.seed() + lay.n + pos] = hi;
+        } else {
+            packed[lay.seed() + pos] = lo | (hi << 32);
+        }
+        reinterpret_cast<uint32_t *>(packed + lay.qidx())[pos] = (uint32_t)q | (flag << 30);
+    }
+}
+
 // ---------------------------------------------------------------- K1: count_kmers
 
 __device__ __forceinline__ uint32_t table_depth(uint32_t flag, uint32_t ts) { return flag == 0 ? 0u : (flag == 1 ? ts : ts - 1u); }
@@ -696,6 +734,20 @@ cudaError_t launch_seed_packed(const IndexView &ix, const uint64_t *d_words, uin
     const SeedPlan plan = make_seed_plan(ix, k);
     if (is_wide(ix)) seed_packed_kernel<true><<<blocks, 256, 0, st>>>(ix, d_words, k, plan, lay, d_packed, d_out);
     else seed_packed_kernel<false><<<blocks, 256, 0, st>>>(ix, d_words, k, plan, lay, d_packed, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_seed_u64(const IndexView &ix, const uint64_t *d_kmers, uint32_t k, uint64_t n,
+                            uint64_t *d_packed, uint64_t *d_out, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    if (!k || k > 32u) return cudaErrorInvalidValue;
+    const PackedLayout lay = packed_layout(ix, k, n);
+    cudaError_t e = cudaMemsetAsync(d_packed + lay.live(), 0, 2 * sizeof(uint64_t), st);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)((n + kPackThreads - 1) / kPackThreads);
+    const SeedPlan plan = make_seed_plan(ix, k);
+    if (is_wide(ix)) seed_u64_kernel<true><<<blocks, kPackThreads, 0, st>>>(ix, d_kmers, k, plan, lay, d_packed, d_out);
+    else seed_u64_kernel<false><<<blocks, kPackThreads, 0, st>>>(ix, d_kmers, k, plan, lay, d_packed, d_out);
     return cudaGetLastError();
 }
 

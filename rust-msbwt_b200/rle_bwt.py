@@ -125,6 +125,7 @@ def load_library():
         "msbwt_oct_symbols": (i32, []),
         "msbwt_table_depth_for_k": (i32, [vp, u32]),
         "msbwt_debug_table_depth": (i32, [u32, u32, u32]),
+        "msbwt_count_kmers_u64": (i32, [vp, vp, u32, u64, vp]),
         "msbwt_debug_copy_oct_image": (i32, [vp, i32, C.POINTER(u64), vp]),
         "msbwt_constrain_ranges_fanout": (i32, [vp, vp, vp, u64, vp, vp]),
         "msbwt_constrain_ranges_fanout_device": (i32, [vp, i32, vp, vp, u64, vp, vp, vp]),
@@ -158,7 +159,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
     "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_oct_index", "msbwt_oct_overflow_lines",
-    "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift", "msbwt_oct_symbols", "msbwt_table_depth_for_k", "msbwt_debug_table_depth",
+    "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift", "msbwt_oct_symbols", "msbwt_table_depth_for_k", "msbwt_debug_table_depth", "msbwt_count_kmers_u64",
     "msbwt_debug_copy_oct_image", "msbwt_constrain_ranges_fanout", "msbwt_constrain_ranges_fanout_device",
     "msbwt_count_read_kmers", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
     "msbwt_debug_host_pack",
@@ -315,6 +316,14 @@ class RleBWT:
         n = a.size // k
         out = np.zeros(n, dtype=np.uint64)
         _check(load_library().msbwt_count_kmers_fixed(self.handle, _p(a), k, n, _p(out)), "count_kmers_fixed")
+        return out
+
+    def count_kmers_u64(self, kmers, k: int) -> np.ndarray:
+        """k-mers held as integers (k <= 32, first symbol in the most significant of the 2k bits, A,C,G,T = 0..3):
+        8 bytes per query over the link instead of k.  EXPERIMENTAL (msbwt_gpu.h)."""
+        a = _u64(kmers).reshape(-1)
+        out = np.zeros(a.size, dtype=np.uint64)
+        _check(load_library().msbwt_count_kmers_u64(self.handle, _p(a), k, a.size, _p(out)), "count_kmers_u64")
         return out
 
     def constrain_ranges(self, sym, l, h) -> tuple[np.ndarray, np.ndarray]:
