@@ -93,6 +93,12 @@ class RleBWT {
         check(msbwt_count_kmers_fixed(h_, syms.data(), k, out.size(), out.data()));
         return out;
     }
+    // k-mers held as integers (k <= 32, first symbol in the most significant of the 2k bits; A,C,G,T = 0..3) -- experimental
+    std::vector<uint64_t> count_kmers_u64(const std::vector<uint64_t> &kmers, uint32_t k) const {
+        std::vector<uint64_t> out(kmers.size());
+        check(msbwt_count_kmers_u64(h_, kmers.data(), k, kmers.size(), out.data()));
+        return out;
+    }
     // the four constrain_range calls (A, C, G, T) of one extension step, from one fetch of the index blocks
     std::array<BWTRange, 4> constrain_range_fanout(const BWTRange &in) const {
         uint64_t l[4], h[4];
