@@ -20,6 +20,8 @@
 // In all of them a lane (group) whose k-mer ends refills itself from its own query stream, so
 // every lane of a warp stays busy.  (v1-v3 used 8- then 4-lane groups per query; ncu
 // showed them issue-bound at ~12 warp instructions per query-step -- profiles/.)
+#include <cstdlib>
+#include <string>
 #include <type_traits>
 
 #include "device_rank.cuh"
@@ -666,8 +668,14 @@ cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_
     const unsigned blocks = (unsigned)((n + 255) / 256);
     const size_t smem = k <= kPackSmemMaxK ? 256u * (size_t)k + 64u : 0u;
     const SeedPlan plan = make_seed_plan(ix, k);
+    // fixed-k instantiations: 31 always (the headline query, validated on the GPU); the other lengths of the k-sweep
+    // (BASELINE.json configs[3]) only with MSBWT_PACK_FIXED_K=all until they have been measured and parity-tested there
+    static const bool more_k = [] { const char *e = getenv("MSBWT_PACK_FIXED_K"); return e && std::string(e) == "all"; }();
     if (is_wide(ix)) pack_seed_kernel<true, 0><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
     else if (k == 31) pack_seed_kernel<false, 31><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
+    else if (more_k && k == 15) pack_seed_kernel<false, 15><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
+    else if (more_k && k == 63) pack_seed_kernel<false, 63><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
+    else if (more_k && k == 101) pack_seed_kernel<false, 101><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
     else pack_seed_kernel<false, 0><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
     return cudaGetLastError();
 }
