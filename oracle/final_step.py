@@ -52,7 +52,9 @@ def lf_mapping(bwt: np.ndarray) -> np.ndarray:
 
 
 def position_codes(bwt: np.ndarray, m: int = M_SYMS) -> np.ndarray:
-    """code_m(j) per position, -1 where one of the m symbols is not A, C, G or T; symbol t of the walk at bits 2t"""
+    """code_m(j) per position, -1 where one of the m symbols is not A, C, G or T; symbol t of the walk (t = 0: B[j],
+    the first one the search consumes) at bits 2 (m-1-t) -- first consumed most significant, the order in which the
+    search kernels read a step's symbols off the query word, so that code_20(j) = code_10(j) << 20 | code_10(LF^10 j)"""
     lf = lf_mapping(bwt)
     code = np.zeros(bwt.size, dtype=np.int64)
     ok = np.ones(bwt.size, dtype=bool)
@@ -60,17 +62,17 @@ def position_codes(bwt: np.ndarray, m: int = M_SYMS) -> np.ndarray:
     for t in range(m):
         c2 = _CODE[bwt[cur]]
         ok &= c2 >= 0
-        code |= np.where(c2 >= 0, c2, 0) << (2 * t)
+        code |= np.where(c2 >= 0, c2, 0) << (2 * (m - 1 - t))
         cur = lf[cur]
     return np.where(ok, code, -1)
 
 
 def query_code(kmer_prefix: np.ndarray) -> int:
-    """code of the FIRST m symbols of a k-mer as the search consumes them: the last of them first (bits 0..1)"""
+    """code of the FIRST m symbols of a k-mer as the search consumes them: the last of them first, most significant"""
     c = 0
     m = len(kmer_prefix)
     for t in range(m):
-        c |= int(_CODE[kmer_prefix[m - 1 - t]]) << (2 * t)
+        c |= int(_CODE[kmer_prefix[m - 1 - t]]) << (2 * (m - 1 - t))
     return c
 
 
