@@ -134,6 +134,12 @@ uint64_t msbwt_oct_runs(const msbwt_index *idx);           /* runs of equal m-sy
 int msbwt_oct_bucket_shift(const msbwt_index *idx);        /* b of the oct image in use, 0 without one */
 int msbwt_oct_symbols(void);                               /* m: symbols (constrain_range steps) per oct line */
 int msbwt_table_depth_for_k(const msbwt_index *idx, uint32_t k); /* suffix-table level an all-ACGT k-mer starts from */
+/* EXPERIMENTAL (not yet run on a GPU): final-step image -- the last 20 symbols of a k-mer answered from ONE hashed
+ * 128-byte line (a count needs no rank; DESIGN.md section 7, oracle/final_step.py).  Only in libraries compiled with
+ * -DMSBWT_FINAL_STEP and for indexes created with MSBWT_FINAL_INDEX=1; otherwise 0 / EINVAL. */
+int msbwt_final_index(const msbwt_index *idx);
+int msbwt_debug_copy_final_image(const msbwt_index *idx, int slot, uint64_t *nlines, uint32_t *bucket_shift,
+                                 uint32_t *lines_log2, uint64_t *overflow_lines, uint32_t *lines /* nlines * 32, or NULL */);
 /* the same policy without an index: `steps` = symbols per step of the image (1, 2, 4 or msbwt_oct_symbols()); -1 otherwise */
 int msbwt_debug_table_depth(uint32_t k, uint32_t table_s, uint32_t steps);
 

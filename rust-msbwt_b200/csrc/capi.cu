@@ -97,6 +97,9 @@ struct Replica {
     PairImage pair;            // 128-byte pair lines (layout.h), when the index lives in HBM
     QuadImage quad;            // 32-byte quad sectors (layout.h), when the index lives in HBM and the image fits
     OctImage oct;              // 128-byte oct lines (layout.h), next to the quad image when positions are 32-bit
+#ifdef MSBWT_FINAL_STEP
+    FinImage fin;              // EXPERIMENTAL final-step lines (layout.h), only with MSBWT_FINAL_INDEX=1
+#endif
     int lanes = 1;           // kernel mapping: 1 = thread per query, 2 = lane pair per query (kernels.cu)
     uint64_t *d_cbase = nullptr;
     IndexView view{};
@@ -128,6 +131,9 @@ struct Replica {
         free_pair_image(pair);
         free_quad_image(quad);
         free_oct_image(oct);
+#ifdef MSBWT_FINAL_STEP
+        free_fin_image(fin);
+#endif
         if (d_cbase) cudaFree(d_cbase);
         cudaSetDevice(cur);
     }
@@ -406,7 +412,15 @@ int build_quad(msbwt_index *idx, Replica &rep, int oct_requested, int oct_shift)
         const uint64_t budget = oct_requested == 1 ? (free_b > scratch ? free_b - scratch : 0) : (free_b > keep ? free_b - keep : 0);
         if (!oct_shift)
             if (const char *env = getenv("MSBWT_OCT_BUCKET_SHIFT")) oct_shift = atoi(env);
+#ifdef MSBWT_FINAL_STEP
+        const char *fin_env = getenv("MSBWT_FINAL_INDEX");
+        const bool want_fin = fin_env && atoi(fin_env) != 0;
+        uint32_t *codes10 = nullptr;
+        rc = build_oct_image_on_device(rep.device, rep.view, codes4, codes2, oct_shift, budget, rep.oct, why, &n,
+                                       want_fin ? &codes10 : nullptr);  // frees codes4
+#else
         rc = build_oct_image_on_device(rep.device, rep.view, codes4, codes2, oct_shift, budget, rep.oct, why, &n);  // frees codes4
+#endif
         g_launches += (uint64_t)n;
         if (rc != MSBWT_OK) { free_oct_image(rep.oct); return fail(rc, why); }
         if (rep.oct.lines) {
@@ -415,6 +429,22 @@ int build_quad(msbwt_index *idx, Replica &rep, int oct_requested, int oct_shift)
             rep.view.oct_shift = (uint32_t)rep.oct.shift;
             if (idx->reps[0].get() == &rep) idx->bytes_per_replica += (uint64_t)kOctCodes * rep.oct.nbuck8 * kOctLineBytes;
         }
+#ifdef MSBWT_FINAL_STEP
+        if (codes10 && !rep.oct.lines) { cudaFree(codes10); codes10 = nullptr; }
+        if (codes10) {  // EXPERIMENTAL: the final-step lines on top of the oct image
+            int fshift = 16, flb = 12;
+            if (const char *env = getenv("MSBWT_FINAL_BUCKET_SHIFT")) fshift = atoi(env);
+            if (const char *env = getenv("MSBWT_FINAL_LINES_LOG2")) flb = atoi(env);
+            n = 0;
+            rc = build_fin_image_on_device(rep.device, rep.view, codes10, fshift, flb, rep.fin, why, &n);  // frees codes10
+            g_launches += (uint64_t)n;
+            if (rc != MSBWT_OK) { free_fin_image(rep.fin); return fail(rc, why); }
+            rep.view.fin = rep.fin.lines;
+            rep.view.fin_shift = (uint32_t)rep.fin.shift;
+            rep.view.fin_lb = (uint32_t)rep.fin.lb;
+            if (idx->reps[0].get() == &rep) idx->bytes_per_replica += rep.fin.nlines * (uint64_t)kFinLineBytes;
+        }
+#endif
     }
     return MSBWT_OK;
 }
@@ -619,6 +649,37 @@ extern "C" uint64_t msbwt_oct_overflow_lines(const msbwt_index *idx) { return (i
 extern "C" uint64_t msbwt_oct_overflow_occurrences(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.overflow_occurrences : 0; }
 extern "C" uint64_t msbwt_oct_runs(const msbwt_index *idx) { return (idx && !idx->reps.empty()) ? idx->reps[0]->oct.runs : 0; }
 extern "C" int msbwt_oct_symbols(void) { return kOctSyms; }
+// EXPERIMENTAL final-step image (layout.h): 0 / EINVAL unless the library was compiled with -DMSBWT_FINAL_STEP and
+// the index was created with MSBWT_FINAL_INDEX=1
+extern "C" int msbwt_final_index(const msbwt_index *idx) {
+#ifdef MSBWT_FINAL_STEP
+    return (idx && !idx->reps.empty() && idx->reps[0]->view.fin) ? 1 : 0;
+#else
+    (void)idx;
+    return 0;
+#endif
+}
+extern "C" int msbwt_debug_copy_final_image(const msbwt_index *idx, int slot, uint64_t *nlines, uint32_t *bucket_shift,
+                                            uint32_t *lines_log2, uint64_t *overflow_lines, uint32_t *lines) {
+    g_last_error.clear();
+#ifdef MSBWT_FINAL_STEP
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
+    Replica &rep = *idx->reps[(size_t)slot];
+    if (!rep.fin.lines) return fail(MSBWT_EINVAL, "this index has no final-step image");
+    if (nlines) *nlines = rep.fin.nlines;
+    if (bucket_shift) *bucket_shift = (uint32_t)rep.fin.shift;
+    if (lines_log2) *lines_log2 = (uint32_t)rep.fin.lb;
+    if (overflow_lines) *overflow_lines = rep.fin.overflow_lines;
+    if (lines) {
+        DeviceGuard guard(rep.device);
+        CU_TRY(cudaMemcpy(lines, rep.fin.lines, rep.fin.nlines * (size_t)kFinLineBytes, cudaMemcpyDeviceToHost));
+    }
+    return MSBWT_OK;
+#else
+    (void)idx; (void)slot; (void)nlines; (void)bucket_shift; (void)lines_log2; (void)overflow_lines; (void)lines;
+    return fail(MSBWT_EINVAL, "the library was built without -DMSBWT_FINAL_STEP");
+#endif
+}
 // the depth policy on its own (no device needed): `steps` = symbols per step of the image that serves list A
 // (1 one-step blocks, 2 pair lines, 4 quad sectors, kOctSyms oct lines)
 extern "C" int msbwt_debug_table_depth(uint32_t k, uint32_t table_s, uint32_t steps) {

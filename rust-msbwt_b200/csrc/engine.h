@@ -92,8 +92,28 @@ uint64_t oct_image_bytes(uint64_t total, int shift);
 // `requested_shift` 0 = automatic (layout.h).  When even the coarsest buckets exceed `max_bytes` nothing is
 // built (img.lines stays null) and MSBWT_OK is returned.
 int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes4, const uint8_t *d_codes2,
-                              int requested_shift, uint64_t max_bytes, OctImage &img, std::string &why, int *launches);
+                              int requested_shift, uint64_t max_bytes, OctImage &img, std::string &why, int *launches
+#ifdef MSBWT_FINAL_STEP
+                              , uint32_t **keep_codes10 = nullptr  // receives the per-position codes (caller frees) instead of freeing them
+#endif
+                              );
 void free_oct_image(OctImage &img);
+
+#ifdef MSBWT_FINAL_STEP
+// ---- fin_builder.cu (EXPERIMENTAL): quad image + the oct builder's 10-symbol codes -> final-step lines (layout.h) ----
+struct FinImage {
+    uint4 *lines = nullptr;  // nlines * 128 B
+    uint64_t nlines = 0;     // ((N >> shift) + 1) << lb
+    int shift = 0, lb = 0;
+    uint64_t runs = 0;            // run records stored
+    uint64_t overflow_lines = 0;  // lines whose groups did not fit
+};
+uint64_t fin_image_bytes(uint64_t total, int shift, int lb);
+// `d_codes10` = the oct builder's per-position codes (valid bit 1 << 20), OWNED by this call
+int build_fin_image_on_device(int device, const IndexView &ix, uint32_t *d_codes10, int shift, int lb, FinImage &img,
+                              std::string &why, int *launches);
+void free_fin_image(FinImage &img);
+#endif
 
 // ---- bwt_build.cu: equal-length reads (device) -> RLE bytes of their multi-string BWT (device) ----
 int build_rle_bwt_on_device(const uint8_t *d_reads, uint64_t n_reads, uint32_t read_len, uint8_t **d_rle_out,

@@ -174,6 +174,32 @@ __host__ __device__ constexpr int oct_chunk_shift(int b) {  // cs = min(31 - b, 
     return c;
 }
 
+// ---- final-step lines (EXPERIMENTAL, only with -DMSBWT_FINAL_STEP; specification: oracle/final_step.py) ----
+//
+// The LAST kFinSyms symbols a count_kmer consumes need no rank, only #{ j in [l, h) : code_20(j) == c }: no
+// checkpoints, nothing stored for codes that do not occur.  `1 << lb` lines of 128 bytes per bucket of `1 << b`
+// positions (b <= 16); code c lives in line `(bucket << lb) | (fin_mix40(c) & (2^lb - 1))` under the tag
+// `fin_mix40(c) >> lb` (fin_mix40 is a bijection of the 40-bit codes, lb >= 12 so that a tag fits kFinTagBits):
+//     word 0      words in use after it (0..31), or kFinOverflow: the query takes the oct steps instead
+//     then groups `(tag << 4) | nruns` (1..15) followed by nruns words `(len << 16) | offset in the bucket`
+// A range over two buckets also takes the oct steps.  A 31-mer = an L2-resident depth-11 table entry + ONE line.
+constexpr int kFinSyms = 20;
+constexpr int kFinCodeBits = 2 * kFinSyms;
+constexpr int kFinTagBits = 28;
+constexpr int kFinLineBytes = 128;
+constexpr int kFinLineWords = 32;
+constexpr uint32_t kFinOverflow = 0xFFFFFFFFu;
+__host__ __device__ inline uint64_t fin_mix40(uint64_t c) {  // the same constants as oracle/final_step.py
+    constexpr uint64_t m = (1ull << kFinCodeBits) - 1ull;
+    c &= m;
+    c ^= c >> 20;
+    c = (c * 0x9E3779B97Full) & m;
+    c ^= c >> 20;
+    c = (c * 0xC2B2AE3D27ull) & m;
+    c ^= c >> 20;
+    return c;
+}
+
 struct IndexView {
     const uint4 *blocks;     // nblocks * 4 uint4 (64 B per block)
     const uint32_t *aux;     // nblocks * 2  ($, N checkpoints)
@@ -199,6 +225,11 @@ struct IndexView {
     uint32_t n_super4;       // quad superblocks (2^sb_shift4 sectors each)
     uint32_t sb_shift4;
     uint32_t table_s;        // 0 = no table
+#ifdef MSBWT_FINAL_STEP
+    const uint4 *fin;        // final-step lines (8 uint4 each), or nullptr
+    uint32_t fin_shift;      // b: log2 of the bucket size
+    uint32_t fin_lb;         // log2 of the lines per bucket
+#endif
 };
 
 }  // namespace msbwt

@@ -150,7 +150,11 @@ uint64_t oct_image_bytes(uint64_t total, int shift) {
 }
 
 int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes4, const uint8_t *d_codes2,
-                              int requested_shift, uint64_t max_bytes, OctImage &img, std::string &why, int *launches) {
+                              int requested_shift, uint64_t max_bytes, OctImage &img, std::string &why, int *launches
+#ifdef MSBWT_FINAL_STEP
+                              , uint32_t **keep_codes10
+#endif
+                              ) {
     struct Owned { uint16_t *p; ~Owned() { if (p) cudaFree(p); } } codes4{d_codes4};
     if (!ix.quad || !d_codes4 || !d_codes2) { why = "oct image: needs the quad image, its codes and the pair codes"; return MSBWT_EINVAL; }
     if (index_is_wide(ix)) { why = "oct image: only for indexes with 32-bit positions (N < 2^32, one superblock)"; return MSBWT_EINVAL; }
@@ -229,6 +233,12 @@ int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes
     img.overflow_lines = over[0];
     img.overflow_occurrences = over[1];
     O_TRY(cudaDeviceSynchronize());
+#ifdef MSBWT_FINAL_STEP
+    if (keep_codes10) {  // hand the codes to the final-step builder instead of freeing them with the scratch
+        tmp.ptrs.erase(std::find(tmp.ptrs.begin(), tmp.ptrs.end(), (void *)d_codes8));
+        *keep_codes10 = d_codes8;
+    }
+#endif
     return MSBWT_OK;
 }
 

@@ -173,6 +173,11 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     int shift = 62;       // bit offset of the next symbol (2 bits) in `word`; negative: already inside `pend`
     uint32_t widx = 0;
     uint32_t forced = 0;  // symbols to take without the oct image (overflowed line / two buckets)
+#ifdef MSBWT_FINAL_STEP
+    bool no_fin = false;  // this query's final-step line overflowed: its last kFinSyms symbols go through the oct steps
+    const char *const fin_base = reinterpret_cast<const char *>(ix.fin);
+    const uint32_t fshift = ix.fin_shift, fmask = (1u << fshift) - 1u, flb = ix.fin_lb;
+#endif
 
     // the next `nsym` symbols as one code (first consumed most significant); a step may straddle two words
     auto peek = [&](uint32_t nsym) -> uint32_t {
@@ -181,6 +186,16 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         const int need = bits - avail;
         return (uint32_t)(((word & ((1ull << avail) - 1ull)) << need) | (pend >> (64 - need)));
     };
+
+#ifdef MSBWT_FINAL_STEP
+    // the next kFinSyms symbols as one 40-bit code (first consumed most significant)
+    auto peek_fin = [&]() -> uint64_t {
+        const int bits = kFinCodeBits, avail = shift + 2;
+        if (avail >= bits) return (word >> (avail - bits)) & ((1ull << bits) - 1ull);
+        const int need = bits - avail;
+        return ((word & ((1ull << avail) - 1ull)) << need) | (pend >> (64 - need));
+    };
+#endif
 
     for (;;) {
         // ---- RETIRE + REFILL (warp-uniform control)
@@ -200,6 +215,9 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                     shift = 62;
                     widx = 0;
                     forced = 0;
+#ifdef MSBWT_FINAL_STEP
+                    no_fin = false;
+#endif
                     active = true;
                     if constexpr (RAW) {
                         q = (from_a ? a_base : b_base) + slot;
@@ -270,10 +288,22 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         const bool is_table = RAW && active && need_table;
         const bool live = active && !is_table && rem != 0 && l != h;
         const uint32_t bl = l >> bshift, bh = h >> bshift;
+#ifdef MSBWT_FINAL_STEP
+        // exactly kFinSyms symbols left: ONE final-step line answers the count (no rank needed for the last step)
+        const bool is_fin = live && fin_base != nullptr && rem == (uint32_t)kFinSyms && forced == 0u && !no_fin &&
+                            (l >> fshift) == (h >> fshift);
+        const uint64_t fin_mixed = fin_mix40(peek_fin());
+        const bool want_oct = live && !is_fin && rem >= (uint32_t)kOctSyms && forced == 0u;
+#else
         const bool want_oct = live && rem >= (uint32_t)kOctSyms && forced == 0u;
+#endif
         const bool is_oct = want_oct && bl == bh;
         if (want_oct && !is_oct) forced = (uint32_t)kOctSyms;  // symbols to take without the oct image
+#ifdef MSBWT_FINAL_STEP
+        const bool is_quad = live && !is_oct && !is_fin && rem >= 4u && (forced == 0u || forced >= 4u);
+#else
         const bool is_quad = live && !is_oct && rem >= 4u && (forced == 0u || forced >= 4u);
+#endif
         const uint32_t codem = peek((uint32_t)kOctSyms);
         const uint32_t code8 = peek(4u);
         const uint32_t sl = l / (uint32_t)kQuadSyms, sh = h / (uint32_t)kQuadSyms;
@@ -281,9 +311,17 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         const char *p0 = is_oct ? oct_base + ((size_t)codem * ix.nbuck8 + bl) * kOctLineBytes
                                 : quad_base + ((size_t)code8 * ix.nsec4 + sl) * kQuadSectorBytes;
         if (is_table) p0 = table_base + ((entry * 8u) & ~15ull);
+#ifdef MSBWT_FINAL_STEP
+        if (is_fin) p0 = fin_base + ((((size_t)(l >> fshift)) << flb) | (size_t)(fin_mixed & ((1ull << flb) - 1ull))) * kFinLineBytes;
+#endif
         // low two bits: kind (1 oct, 2 quad, 3 table entry, 0 nothing); the rest (quad): byte distance from the
         // sector of l to the sector of h
+#ifdef MSBWT_FINAL_STEP
+        // a final-step line is fetched like an oct line (kind 1: all eight 16-byte pieces)
+        const uint32_t meta = is_table ? 3u : ((is_oct || is_fin) ? 1u : (is_quad ? (2u | ((sh - sl) * (uint32_t)kQuadSectorBytes)) : 0u));
+#else
         const uint32_t meta = is_table ? 3u : (is_oct ? 1u : (is_quad ? (2u | ((sh - sl) * (uint32_t)kQuadSectorBytes)) : 0u));
+#endif
         const uint32_t p0_lo = (uint32_t)(uintptr_t)p0, p0_hi = (uint32_t)((uintptr_t)p0 >> 32);
         {
             const uint32_t j = lane & 7u;  // this lane's 16 bytes of a line
@@ -311,6 +349,44 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             word <<= 2u * depth0;
             rem = rem0;
             need_table = false;
+#ifdef MSBWT_FINAL_STEP
+        } else if (is_fin) {
+            const uint4 first = my_row[0];
+            const uint32_t used = first.x;
+            if (used == kFinOverflow) {
+                no_fin = true;  // the same symbols through two oct steps
+            } else {
+                const uint32_t tag = (uint32_t)(fin_mixed >> flb);
+                const int pl = (int)(l & fmask), ph = (int)(h & fmask);
+                int cnt = 0;
+                uint32_t left = 0;
+                bool match = false;
+                auto eat = [&](uint32_t w, uint32_t idx) {  // word `idx` of the line: a group header or one of its runs
+                    if (idx > used) return;
+                    if (left == 0u) {
+                        match = (w >> 4) == tag;
+                        left = w & 15u;
+                    } else {
+                        const int off = (int)(w & 0xFFFFu), len = (int)(w >> 16);
+                        if (match) cnt += min(max(ph - off, 0), len) - min(max(pl - off, 0), len);
+                        left--;
+                    }
+                };
+                eat(first.y, 1u);
+                eat(first.z, 2u);
+                eat(first.w, 3u);
+                for (uint32_t v = 1; v < 8u && 4u * v <= used; v++) {
+                    const uint4 r = my_row[v];
+                    eat(r.x, 4u * v);
+                    eat(r.y, 4u * v + 1u);
+                    eat(r.z, 4u * v + 2u);
+                    eat(r.w, 4u * v + 3u);
+                }
+                l = 0;
+                h = (uint32_t)cnt;  // only h - l is read from here on
+                rem = 0;
+            }
+#endif
         } else if (is_oct) {
             const uint4 a = my_row[0], b = my_row[1];
             if (a.y > (uint32_t)kOctCapacity) {

@@ -126,6 +126,8 @@ def load_library():
         "msbwt_table_depth_for_k": (i32, [vp, u32]),
         "msbwt_debug_table_depth": (i32, [u32, u32, u32]),
         "msbwt_count_kmers_u64": (i32, [vp, vp, u32, u64, vp]),
+        "msbwt_final_index": (i32, [vp]),
+        "msbwt_debug_copy_final_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64), vp]),
         "msbwt_debug_copy_oct_image": (i32, [vp, i32, C.POINTER(u64), vp]),
         "msbwt_constrain_ranges_fanout": (i32, [vp, vp, vp, u64, vp, vp]),
         "msbwt_constrain_ranges_fanout_device": (i32, [vp, i32, vp, vp, u64, vp, vp, vp]),
@@ -159,7 +161,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
     "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_oct_index", "msbwt_oct_overflow_lines",
-    "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift", "msbwt_oct_symbols", "msbwt_table_depth_for_k", "msbwt_debug_table_depth", "msbwt_count_kmers_u64",
+    "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift", "msbwt_oct_symbols", "msbwt_table_depth_for_k", "msbwt_debug_table_depth", "msbwt_count_kmers_u64", "msbwt_final_index", "msbwt_debug_copy_final_image",
     "msbwt_debug_copy_oct_image", "msbwt_constrain_ranges_fanout", "msbwt_constrain_ranges_fanout_device",
     "msbwt_count_read_kmers", "msbwt_last_transfer_bytes", "msbwt_host_pack_threads",
     "msbwt_debug_host_pack",
@@ -317,6 +319,21 @@ class RleBWT:
         out = np.zeros(n, dtype=np.uint64)
         _check(load_library().msbwt_count_kmers_fixed(self.handle, _p(a), k, n, _p(out)), "count_kmers_fixed")
         return out
+
+    @property
+    def final_index(self) -> bool:
+        """EXPERIMENTAL final-step image present (library built with -DMSBWT_FINAL_STEP, MSBWT_FINAL_INDEX=1)"""
+        return bool(load_library().msbwt_final_index(self.handle))
+
+    def final_image(self, slot: int = 0) -> tuple[np.ndarray, int, int, int]:
+        """(lines [nlines, 32] u32, bucket shift, log2 lines per bucket, overflowed lines) of the final-step image"""
+        L = load_library()
+        n, b, lb, over = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        _check(L.msbwt_debug_copy_final_image(self.handle, slot, C.byref(n), C.byref(b), C.byref(lb), C.byref(over), None),
+               "debug_copy_final_image")
+        lines = np.zeros((n.value, 32), dtype=np.uint32)
+        _check(L.msbwt_debug_copy_final_image(self.handle, slot, None, None, None, None, _p(lines)), "debug_copy_final_image")
+        return lines, int(b.value), int(lb.value), int(over.value)
 
     def count_kmers_u64(self, kmers, k: int) -> np.ndarray:
         """k-mers held as integers (k <= 32, first symbol in the most significant of the 2k bits, A,C,G,T = 0..3):

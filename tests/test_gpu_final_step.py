@@ -1,0 +1,87 @@
+"""EXPERIMENTAL final-step image (layout.h, fin_builder.cu, the `is_fin` step of count_kmers_oct_kernel): the last 20
+symbols of a k-mer answered from ONE hashed line.  Checked against its numpy specification (oracle/final_step.py)
+line by line, and against the oracle's count_kmer (src/msbwt_core.rs:125-161) for the lengths that reach the step
+(k = table depth + 10 a + 20) and for some that do not.
+
+Written after the round's GPU budget was spent: NOT yet run on a GPU.  Needs a library compiled with
+-DMSBWT_FINAL_STEP (`tools/build_variant.sh finalstep -DMSBWT_FINAL_STEP`, then
+`MSBWT_LIBRARY_PATH=build/variants/lib_finalstep.so MSBWT_EXPERIMENTAL=1 pytest -m gpu tests/test_gpu_final_step.py`);
+skipped otherwise."""
+import os
+
+import numpy as np
+import pytest
+
+import rust_msbwt_b200 as M
+from oracle import final_step as F
+from oracle import oracle as O
+from tests.test_oracle_final_step import decode
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MSBWT_EXPERIMENTAL", "0") in ("", "0"),
+                                 reason="the final-step image is unverified on a GPU: set MSBWT_EXPERIMENTAL=1")]
+
+torch = pytest.importorskip("torch")
+
+
+def make_index(rle, monkeypatch, shift=16, lb=12, **kw):
+    monkeypatch.setenv("MSBWT_FINAL_INDEX", "1")
+    monkeypatch.setenv("MSBWT_FINAL_BUCKET_SHIFT", str(shift))
+    monkeypatch.setenv("MSBWT_FINAL_LINES_LOG2", str(lb))
+    g = M.RleBWT(oct_index=1, **kw)
+    g.load_vector(rle)
+    if not g.final_index:
+        pytest.skip("library built without -DMSBWT_FINAL_STEP")
+    return g
+
+
+@pytest.fixture(scope="module")
+def midsize():
+    from harness import bwt_build, synth
+    reads = synth.make_reads(20000, read_len=100, coverage=25.0, error_rate=0.01, device="cuda")
+    reads[17, 40:43] = 4
+    rle, _ = bwt_build.build_rle_bwt(reads)
+    o = O.RleBWT()
+    o.load_vector(rle.cpu().numpy())
+    return reads, o
+
+
+@pytest.mark.parametrize("shift,lb", [(16, 12), (12, 12), (10, 13)])
+def test_device_image_equals_the_specification(midsize, monkeypatch, shift, lb):
+    reads, o = midsize
+    g = make_index(o.rle_bytes(), monkeypatch, shift, lb)
+    lines, b, l2, over = g.final_image()
+    assert (b, l2) == (shift, lb)
+    want, stats = F.build_final_image(decode(o.rle_bytes()), b=shift, lb=lb)
+    assert lines.shape == want.shape and over == stats["overflowed_lines"]
+    assert ((lines[:, 0] == F.OVERFLOW) == (want[:, 0] == F.OVERFLOW)).all()
+    for i in np.flatnonzero((want[:, 0] != 0) | (lines[:, 0] != 0)):
+        assert F.line_groups(lines[i]) == F.line_groups(want[i]), i
+
+
+@pytest.mark.parametrize("shift,lb,table_s", [(16, 12, -1), (12, 12, -1), (10, 13, 7), (16, 12, 0), (14, 12, 12)])
+def test_counts_are_bit_exact_with_the_final_step(midsize, monkeypatch, shift, lb, table_s):
+    from harness import synth
+    reads, o = midsize
+    g = make_index(o.rle_bytes(), monkeypatch, shift, lb, suffix_table_s=table_s)
+    for k in (20, 21, 24, 30, 31, 32, 33, 40, 41, 42, 51, 61, 64, 71, 100):
+        q = synth.make_queries(reads, k, 12001, 6000).cpu().numpy()
+        q[5, 0] = 4
+        q[11, k // 2] = 4
+        got = g.count_kmers_fixed(q, k)
+        want = o.count_kmers_fixed(q, k, threads=8)
+        assert (got == want).all(), (shift, lb, table_s, k, np.flatnonzero(got != want)[:5])
+
+
+def test_overflowed_lines_fall_back(monkeypatch):
+    """a 2 kb genome at 1500x: few codes own every position, their lines cannot hold the runs"""
+    from harness import bwt_build, synth
+    reads = synth.make_reads(30000, read_len=100, coverage=1500.0, error_rate=0.01, device="cuda")
+    rle = bwt_build.build_rle_bwt(reads)[0].cpu().numpy()
+    o = O.RleBWT()
+    o.load_vector(rle)
+    g = make_index(rle, monkeypatch)
+    assert g.final_image()[3] > 0
+    for k in (31, 41, 64):
+        q = synth.make_queries(reads, k, 20000, 5000).cpu().numpy()
+        assert (g.count_kmers_fixed(q, k) == o.count_kmers_fixed(q, k, threads=8)).all(), k

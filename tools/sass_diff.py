@@ -37,9 +37,14 @@ def functions(cubin: str) -> dict[str, list[str]]:
 
 
 def demangle(name: str) -> str:
+    """full demangled signature: the key functions are matched by (anonymous-namespace symbols carry a hash of the
+    source path in their mangled names, which differs between the checkout of the revision and the working tree)"""
     r = subprocess.run(["cu++filt", name], capture_output=True, text=True)
-    full = r.stdout.strip() or name
-    return full[:full.index(">(") + 1] if ">(" in full else full.split("(")[0]
+    return r.stdout.strip() or name
+
+
+def short(sig: str) -> str:
+    return sig[:sig.index(">(") + 1] if ">(" in sig else sig.split("(")[0]
 
 
 def main():
@@ -66,13 +71,13 @@ def main():
                     cub[side] = None
                     continue
                 subprocess.run([B.nvcc_path(), *NVCC, *flags, "-o", cub[side], unit], cwd=os.path.dirname(src), check=True)
-            a = functions(cub["rev"]) if cub["rev"] else {}
-            b = functions(cub["tree"]) if cub["tree"] else {}
+            a = {demangle(k): v for k, v in (functions(cub["rev"]) if cub["rev"] else {}).items()}
+            b = {demangle(k): v for k, v in (functions(cub["tree"]) if cub["tree"] else {}).items()}
             for k in sorted(set(a) | set(b)):
                 tag = "new " if k not in a else ("gone" if k not in b else ("same" if a[k] == b[k] else "DIFF"))
                 if tag != "same":
                     changed = True
-                    print(f"{tag} {unit:18s} {demangle(k)[:110]}  ({len(a.get(k, []))} -> {len(b.get(k, []))} instructions)")
+                    print(f"{tag} {unit:18s} {short(k)[:110]}  ({len(a.get(k, []))} -> {len(b.get(k, []))} instructions)")
             print(f"{unit}: {len(b)} functions, {sum(1 for k in b if k in a and a[k] == b[k])} identical to {args.rev}")
         return 1 if changed else 0
 
