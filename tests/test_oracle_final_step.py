@@ -87,3 +87,127 @@ def test_lines_compare_as_sets_of_groups_and_overflow_is_explicit(reads_index):
     assert stats2["overflowed_lines"] == int((lines2[:, 0] == F.OVERFLOW).sum())
     for ln in lines2[lines2[:, 0] != F.OVERFLOW]:
         assert int(ln[0]) <= F.LINE_WORDS - 1
+
+
+def _device_lines_from_records(keys, vals, nlines):
+    """fin_lines_kernel (fin_builder.cu) statement by statement: records sorted by key, the first record of a line
+    writes the whole line"""
+    TAG_BITS, WORDS = 28, F.LINE_WORDS
+    lines = np.zeros((nlines, WORDS), dtype=np.uint32)
+    n = len(keys)
+    for i in range(n):
+        line = int(keys[i]) >> TAG_BITS
+        if i and (int(keys[i - 1]) >> TAG_BITS) == line:
+            continue
+        w = lines[line]
+        used = header = in_group = 0
+        cur_key, over = None, False
+        r = i
+        while r < n and (int(keys[r]) >> TAG_BITS) == line:
+            if int(keys[r]) != cur_key or in_group == 15:
+                if used + 2 > WORDS - 1:
+                    over = True
+                    break
+                cur_key = int(keys[r])
+                used += 1
+                header = used
+                in_group = 0
+                w[header] = (cur_key & ((1 << TAG_BITS) - 1)) << 4
+            elif used + 1 > WORDS - 1:
+                over = True
+                break
+            used += 1
+            w[used] = vals[r]
+            in_group += 1
+            w[header] = (int(w[header]) & ~15) | in_group
+            r += 1
+        w[0] = F.OVERFLOW if over else used
+    return lines
+
+
+def _device_count(line, tag, pl, ph):
+    """the is_fin CONSUME step of count_kmers_oct_kernel (oct_kernel.cuh) statement by statement: eight uint4 of the
+    staged line, word 0 = words in use"""
+    used = int(line[0])
+    if used == F.OVERFLOW:
+        return None
+    state = {"cnt": 0, "left": 0, "match": False}
+
+    def eat(w, idx):
+        if idx > used:
+            return
+        if state["left"] == 0:
+            state["match"] = (int(w) >> 4) == tag
+            state["left"] = int(w) & 15
+        else:
+            off, ln = int(w) & 0xFFFF, int(w) >> 16
+            if state["match"]:
+                state["cnt"] += min(max(ph - off, 0), ln) - min(max(pl - off, 0), ln)
+            state["left"] -= 1
+
+    eat(line[1], 1)
+    eat(line[2], 2)
+    eat(line[3], 3)
+    v = 1
+    while v < 8 and 4 * v <= used:
+        for t in range(4):
+            eat(line[4 * v + t], 4 * v + t)
+        v += 1
+    return state["cnt"]
+
+
+@pytest.mark.parametrize("b,lb", [(16, 12), (11, 12)])
+def test_device_algorithms_replayed_on_the_cpu_agree_with_the_specification(reads_index, b, lb):
+    """The builder's record -> line loop and the kernel's line parse, transcribed from the CUDA sources, give the
+    specification's lines and counts (what can be checked of the experimental kernels without a GPU)."""
+    reads, o, bwt = reads_index
+    want, stats = F.build_final_image(bwt, b=b, lb=lb)
+    key = F.position_codes(bwt)
+    n = bwt.size
+    bmask = (1 << b) - 1
+    keys, vals = [], []
+    j = 0
+    while j < n:                                               # fin_emit_kernel: heads, runs cut at 65535 and at buckets
+        if key[j] < 0:
+            j += 1
+            continue
+        ln = 1
+        while j + ln < n and ((j + ln) & bmask) != 0 and key[j + ln] == key[j]:
+            ln += 1
+        mixed = int(F.mix40(np.uint64(key[j])))
+        line = ((j >> b) << lb) | (mixed & ((1 << lb) - 1))
+        at, left = j, ln
+        while left:
+            piece = min(left, 65535)
+            keys.append((line << 28) | (mixed >> lb))
+            vals.append((piece << 16) | (at & bmask))
+            at += piece
+            left -= piece
+        j += ln
+    order = np.argsort(np.array(keys, dtype=np.uint64), kind="stable")   # the device sorts with a CUB radix sort
+    keys = np.array(keys, dtype=np.uint64)[order]
+    vals = np.array(vals, dtype=np.uint32)[order]
+    got = _device_lines_from_records(keys, vals, want.shape[0])
+    assert ((got[:, 0] == F.OVERFLOW) == (want[:, 0] == F.OVERFLOW)).all()
+    for i in np.flatnonzero(want[:, 0] != 0):
+        assert F.line_groups(got[i]) == F.line_groups(want[i]), i
+    # the kernel's parse of those lines against final_count
+    from harness import synth
+    q = synth.make_queries(reads, 31, 400, 50).numpy()
+    q = q[np.isin(q, (1, 2, 3, 5)).all(axis=1)]
+    checked = 0
+    for kmer in q:
+        l, h = 0, int(n)
+        for t in range(11):
+            l, h = o.constrain_range(int(kmer[30 - t]), l, h)
+        if l == h or (l >> b) != (h >> b):
+            continue
+        code = F.query_code(kmer[:20])
+        mixed = int(F.mix40(np.uint64(code)))
+        line = got[((l >> b) << lb) | (mixed & ((1 << lb) - 1))]
+        dev = _device_count(line, mixed >> lb, l & bmask, h & bmask)
+        assert dev == F.final_count(want, code, l, h, b=b, lb=lb)
+        if dev is not None:
+            assert dev == o.count_kmer(kmer)
+            checked += 1
+    assert checked > 100
