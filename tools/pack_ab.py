@@ -61,7 +61,8 @@ def main():
     assert int(d_status.item()) == 0
     print(json.dumps({
         "library": os.environ.get("MSBWT_LIBRARY_PATH", "in-tree"), "workload": args.workload, "k": k, "queries": n,
-        "bwt_symbols": int(total), "oct_index": bool(bwt.oct_index), "suffix_table_s": bwt.suffix_table_s,
+        "bwt_symbols": int(total), "oct_index": bool(bwt.oct_index), "final_index": bool(bwt.final_index), "suffix_table_s": bwt.suffix_table_s,
+        "fixed_k_pack": os.environ.get("MSBWT_PACK_FIXED_K", ""),
         "pack_ms_median": statistics.median(pack_ms), "pack_ms_min": min(pack_ms),
         "search_ms_median": statistics.median(search_ms), "search_ms_min": min(search_ms),
         "checksum": int(d_out.sum().item()), "present": int((d_out > 0).sum().item()),
