@@ -292,7 +292,7 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         // exactly kFinSyms symbols left: ONE final-step line answers the count (no rank needed for the last step)
         const bool is_fin = live && fin_base != nullptr && rem == (uint32_t)kFinSyms && forced == 0u && !no_fin &&
                             (l >> fshift) == (h >> fshift);
-        const uint64_t fin_mixed = fin_mix40(peek_fin());
+        const uint64_t fin_mixed = is_fin ? fin_mix40(peek_fin()) : 0ull;  // (a dozen instructions: only where they are used)
         const bool want_oct = live && !is_fin && rem >= (uint32_t)kOctSyms && forced == 0u;
 #else
         const bool want_oct = live && rem >= (uint32_t)kOctSyms && forced == 0u;
