@@ -54,8 +54,8 @@ def main():
     ap.add_argument("units", nargs="*", default=[s for s in B.SOURCES])
     args = ap.parse_args()
     with tempfile.TemporaryDirectory() as tmp:
-        files = subprocess.run(["git", "ls-files", "rust-msbwt_b200/csrc", "include"], cwd=ROOT, capture_output=True,
-                               text=True, check=True).stdout.split()
+        files = subprocess.run(["git", "ls-tree", "-r", "--name-only", args.rev, "--", "rust-msbwt_b200/csrc", "include"],
+                               cwd=ROOT, capture_output=True, text=True, check=True).stdout.split()
         for f in files:
             dst = os.path.join(tmp, "rev", f)
             os.makedirs(os.path.dirname(dst), exist_ok=True)
