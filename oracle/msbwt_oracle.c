@@ -540,10 +540,15 @@ int orc_count_kmers_stats_quad(const orc_rle_bwt *b, const uint8_t *syms, uint32
  * modelled: msbwt_oct_overflow_lines reports how many exist.) */
 static uint32_t oct_walk_cost(uint32_t rest, uint32_t m) { const uint32_t r = rest % m; return rest / m + r / 4u + 2u * (r % 4u); }
 
-int orc_count_kmers_stats_oct(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
-                              uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
-                              unsigned block_shift, unsigned oct_bucket_shift, unsigned oct_syms, uint64_t *out) {
-    uint64_t qs = 0, q2s = 0, q2l = 0, os = 0, o2 = 0, hits = 0, es = 0, e2 = 0;
+/* fin_bucket_shift != 0: with the (experimental) final-step image on top of the oct image -- exactly fin_syms
+ * symbols left and l, h in one bucket of 2^fin_bucket_shift positions: ONE line answers the count and the query
+ * ends (a range over two buckets takes the oct steps; overflowed lines are not modelled, as for the oct image).
+ * fin[0] = final steps, fin[1] = two-bucket events. */
+static int stats_oct_fin(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                         uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
+                         unsigned block_shift, unsigned oct_bucket_shift, unsigned oct_syms,
+                         unsigned fin_bucket_shift, unsigned fin_syms, uint64_t *out, uint64_t *fin) {
+    uint64_t qs = 0, q2s = 0, q2l = 0, os = 0, o2 = 0, hits = 0, es = 0, e2 = 0, fs = 0, f2 = 0;
     const uint64_t line_syms = (uint64_t)sector_syms * line_sectors;
     const uint32_t m = oct_bucket_shift ? (oct_syms ? oct_syms : 8u) : 0u;
     for (uint64_t i = 0; i < n; i++) {
@@ -580,7 +585,17 @@ int orc_count_kmers_stats_oct(const orc_rle_bwt *b, const uint8_t *syms, uint32_
         orc_range r = { 0, b->total_size };
         uint32_t t = k, forced = 0;
         for (uint32_t c = 0; c < done; c++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
+        int fin_tried = 0;
         while (t >= 1 && r.h != r.l) {
+            if (all_acgt && m && fin_bucket_shift && t == fin_syms && forced == 0 && !fin_tried) {
+                if ((r.l >> fin_bucket_shift) == (r.h >> fin_bucket_shift)) {
+                    fs++;
+                    for (uint32_t u = 0; u < fin_syms; u++) { t--; if (r.h != r.l) r = orc_constrain_range(b, q[t], r); }
+                    continue;
+                }
+                f2++;
+                fin_tried = 1;
+            }
             if (all_acgt && m && t >= m && forced == 0) {
                 if ((r.l >> oct_bucket_shift) == (r.h >> oct_bucket_shift)) {
                     es++;
@@ -607,7 +622,22 @@ int orc_count_kmers_stats_oct(const orc_rle_bwt *b, const uint8_t *syms, uint32_
     }
     out[0] = qs; out[1] = q2s; out[2] = q2l; out[3] = os; out[4] = o2; out[5] = hits; out[6] = n;
     if (oct_bucket_shift) { out[7] = es; out[8] = e2; } else { out[7] = 0; }
+    if (fin) { fin[0] = fs; fin[1] = f2; }
     return ORC_OK;
+}
+
+int orc_count_kmers_stats_oct(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                              uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
+                              unsigned block_shift, unsigned oct_bucket_shift, unsigned oct_syms, uint64_t *out) {
+    return stats_oct_fin(b, syms, k, n, table_s, sector_syms, line_sectors, block_shift, oct_bucket_shift, oct_syms, 0, 0, out, NULL);
+}
+
+int orc_count_kmers_stats_fin(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                              uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
+                              unsigned block_shift, unsigned oct_bucket_shift, unsigned oct_syms,
+                              unsigned fin_bucket_shift, unsigned fin_syms, uint64_t *out /* 9 */, uint64_t *fin /* 2 */) {
+    return stats_oct_fin(b, syms, k, n, table_s, sector_syms, line_sectors, block_shift, oct_bucket_shift, oct_syms,
+                         fin_bucket_shift, fin_syms, out, fin);
 }
 
 /* ---- bwt_converter.rs ---- */

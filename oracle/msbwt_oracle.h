@@ -98,6 +98,10 @@ int orc_count_kmers_stats_pair(const orc_rle_bwt *b, const uint8_t *syms, uint32
 int orc_count_kmers_stats_oct(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
                               uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
                               unsigned block_shift, unsigned oct_bucket_shift, unsigned oct_syms, uint64_t *out);
+int orc_count_kmers_stats_fin(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
+                              uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
+                              unsigned block_shift, unsigned oct_bucket_shift, unsigned oct_syms,
+                              unsigned fin_bucket_shift, unsigned fin_syms, uint64_t *out, uint64_t *fin);
 int orc_count_kmers_stats_quad(const orc_rle_bwt *b, const uint8_t *syms, uint32_t k, uint64_t n,
                                uint32_t table_s, uint32_t sector_syms, uint32_t line_sectors,
                                unsigned block_shift, uint64_t *out);

@@ -98,6 +98,7 @@ def lib():
         "orc_count_kmers_stats_pair": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint, u64p]),
         "orc_count_kmers_stats_quad": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint, u64p]),
         "orc_count_kmers_stats_oct": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint, C.c_uint, C.c_uint, u64p]),
+        "orc_count_kmers_stats_fin": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, u64p, u64p]),
         "orc_convert_to_vec": (C.c_uint64, [vp, C.c_uint64, vp, C.c_uint64]),
         "orc_encode_runs": (C.c_uint64, [vp, vp, C.c_uint64, vp, C.c_uint64]),
         "orc_save_bwt_numpy": (C.c_int, [vp, C.c_uint64, C.c_char_p]),
@@ -277,17 +278,22 @@ class RleBWT:
         return dict(zip(keys, (int(v) for v in out)))
 
     def count_kmers_stats_quad(self, syms, k: int, table_s: int, sector_syms: int = 224, line_sectors: int = 4,
-                               block_shift: int = 7, oct_bucket_shift: int = 0, oct_syms: int = 8) -> dict:
-        """Accounting replay of the engine's quad path (oct_bucket_shift != 0: with the oct image on top):
-        index sectors / lines a batch must touch."""
+                               block_shift: int = 7, oct_bucket_shift: int = 0, oct_syms: int = 8,
+                               fin_bucket_shift: int = 0, fin_syms: int = 20) -> dict:
+        """Accounting replay of the engine's quad path (oct_bucket_shift != 0: with the oct image on top;
+        fin_bucket_shift != 0: and the experimental final-step image): index sectors / lines a batch must touch."""
         a = _u8(syms).reshape(-1)
         n = a.size // k
         out = (C.c_uint64 * 9)()
-        _raise(lib().orc_count_kmers_stats_oct(self._h, _ptr(a), k, n, table_s, sector_syms, line_sectors,
-                                               block_shift, oct_bucket_shift, oct_syms, out), "count_kmers_stats_quad")
+        fin = (C.c_uint64 * 2)()
+        _raise(lib().orc_count_kmers_stats_fin(self._h, _ptr(a), k, n, table_s, sector_syms, line_sectors,
+                                               block_shift, oct_bucket_shift, oct_syms, fin_bucket_shift, fin_syms, out, fin),
+               "count_kmers_stats_quad")
         keys = ("quad_steps", "two_sector_quad_steps", "two_line_quad_steps", "one_steps", "two_block_one_steps",
                 "table_hits", "queries", "oct_steps", "two_bucket_oct_steps")
-        return dict(zip(keys, (int(v) for v in out)))
+        d = dict(zip(keys, (int(v) for v in out)))
+        d["final_steps"], d["two_bucket_final_steps"] = int(fin[0]), int(fin[1])
+        return d
 
     def count_kmers_stats(self, syms, k: int, block_shift: int = 8) -> tuple[int, int]:
         a = _u8(syms).reshape(-1)

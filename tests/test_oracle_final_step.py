@@ -211,3 +211,32 @@ def test_device_algorithms_replayed_on_the_cpu_agree_with_the_specification(read
             assert dev == o.count_kmer(kmer)
             checked += 1
     assert checked > 100
+
+
+def test_accounting_replay_with_the_final_step(reads_index):
+    """bench.py's algorithmic-bytes replay (orc_count_kmers_stats_*): with the final-step image a 31-mer that
+    survives the depth-11 table entry costs ONE final line instead of two oct lines; without it nothing changes."""
+    from harness import synth
+    reads, o, bwt = reads_index
+    q = synth.make_queries(reads, 31, 3000, 500).numpy()
+    base = o.count_kmers_stats_quad(q, 31, 14, oct_bucket_shift=16, oct_syms=10)
+    assert base["final_steps"] == 0 and base["two_bucket_final_steps"] == 0
+    fin = o.count_kmers_stats_quad(q, 31, 14, oct_bucket_shift=16, oct_syms=10, fin_bucket_shift=16)
+    for key in ("queries", "table_hits"):
+        assert fin[key] == base[key], key
+    for key in ("quad_steps", "one_steps"):   # fallbacks of a SECOND oct step no longer happen: the query has ended
+        assert fin[key] <= base[key], key
+    assert fin["final_steps"] > 0
+    # every query that took a final step would have taken one oct step, and a second one unless it died on the first
+    assert base["oct_steps"] - fin["oct_steps"] >= fin["final_steps"]
+    assert base["oct_steps"] - fin["oct_steps"] <= 2 * fin["final_steps"]
+    # a bucket so small that ranges straddle it: the replay falls back to the oct steps and says so
+    tiny = o.count_kmers_stats_quad(q, 31, 14, oct_bucket_shift=16, oct_syms=10, fin_bucket_shift=3)
+    assert tiny["two_bucket_final_steps"] > 0
+    assert tiny["final_steps"] + tiny["two_bucket_final_steps"] == fin["final_steps"] + fin["two_bucket_final_steps"]
+    # other lengths: k = 41 (table 11 + one oct step) and k = 30 (no table: three oct steps cost no more) reach the
+    # final step with exactly 20 symbols left, k = 29 (table 11, 18 left) never does
+    for k, reaches in ((41, True), (30, True), (29, False)):
+        qk = synth.make_queries(reads, k, 2000, 0).numpy()
+        st = o.count_kmers_stats_quad(qk, k, 14, oct_bucket_shift=16, oct_syms=10, fin_bucket_shift=16)
+        assert (st["final_steps"] > 0) == reaches, (k, st)
