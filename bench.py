@@ -410,21 +410,23 @@ def measure_ours(args, cfg, ctx, primary: bool):
         packed_q = 8 * (-(-k // 21) + 1) + 4   # symbol words + seed + index of the compacted live list
         bytes_per_query_no_table = (steps0 + two0) * BLOCK_BYTES / ms + packed_q + 8
         pair, quad = bwt.pair_index, bwt.quad_index
-        quad_lines = quad_sectors = oct_lines = 0
+        quad_lines = quad_sectors = oct_lines = final_lines = 0
         if quad:
             # quad path: four of the reference's constrain_range calls per 32-B sector.  An L2 miss fills the
             # whole 128-B line, so the bytes HBM must move are counted per distinct LINE (l and h share one
             # 97 % of the time); the sector-granular figure is reported beside it.
             # with the oct image on top: M.oct_symbols() (ten) calls per 128-B line while that many symbols are left
             st = orc.count_kmers_stats_quad(q_host[:ms], k, table_s, QUAD_SYMS, LINE_BYTES // QUAD_SECTOR_BYTES, BLOCK_SHIFT,
-                                            bwt.oct_bucket_shift if bwt.oct_index else 0, M.oct_symbols())
+                                            bwt.oct_bucket_shift if bwt.oct_index else 0, M.oct_symbols(),
+                                            bwt.final_bucket_shift)   # experimental final-step image: 0 without one
             hits = st["table_hits"]
-            oct_lines = st["oct_steps"]   # (a range over two buckets takes its symbols as quad / one-symbol steps: counted there)
+            final_lines = st["final_steps"]   # one 128-B line for the last 20 symbols (0 unless that image exists)
+            oct_lines = st["oct_steps"] + final_lines   # (a range over two buckets takes its symbols as quad / one-symbol steps: counted there)
             quad_lines = st["quad_steps"] + st["two_line_quad_steps"]
             quad_sectors = st["quad_steps"] + st["two_sector_quad_steps"]
             pair_lines = 0
             one_blocks = st["one_steps"] + st["two_block_one_steps"]
-            ref_steps = M.oct_symbols() * st["oct_steps"] + 4 * st["quad_steps"] + st["one_steps"]
+            ref_steps = M.oct_symbols() * st["oct_steps"] + 20 * final_lines + 4 * st["quad_steps"] + st["one_steps"]
             two_share = st["two_line_quad_steps"] / max(1, st["quad_steps"] + st["oct_steps"])
         elif pair:
             st = orc.count_kmers_stats_pair(q_host[:ms], k, table_s, PAIR_SYMS, BLOCK_SHIFT)
@@ -461,7 +463,8 @@ def measure_ours(args, cfg, ctx, primary: bool):
             "kernel": "count_kmers_oct_kernel<RAW> (fused: pack + table + search)" if fused else "count_kmers_oct_kernel" if bwt.oct_index else "count_kmers_quad_kernel" if quad else ("count_kmers_pair_kernel" if pair else "count_kmers_packed_kernel"),
             "fused": bool(fused), "kernel_ms": 1e3 * kern_s, "algorithmic_bytes_per_launch": bytes_per_query * n,
             "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": ref_steps / ms,
-            "oct_lines_per_query": oct_lines / ms, "oct_overflow_lines": bwt.oct_overflow_lines,
+            "oct_lines_per_query": oct_lines / ms, "final_step_lines_per_query": final_lines / ms,
+            "oct_overflow_lines": bwt.oct_overflow_lines,
             "oct_overflow_position_share": bwt.oct_overflow_occurrences / max(1, total), "oct_bucket_shift": bwt.oct_bucket_shift, "oct_symbols_per_line": M.oct_symbols(),
             "quad_lines_per_query": quad_lines / ms, "quad_sectors_per_query": quad_sectors / ms,
             "achieved_sector_granular": sector_bytes_per_query * n / kern_s / 1e9,

@@ -325,6 +325,16 @@ class RleBWT:
         """EXPERIMENTAL final-step image present (library built with -DMSBWT_FINAL_STEP, MSBWT_FINAL_INDEX=1)"""
         return bool(load_library().msbwt_final_index(self.handle))
 
+    @property
+    def final_bucket_shift(self) -> int:
+        """log2 of the final-step image's bucket size, 0 without one"""
+        if not self.final_index:
+            return 0
+        b = C.c_uint32(0)
+        _check(load_library().msbwt_debug_copy_final_image(self.handle, 0, None, C.byref(b), None, None, None),
+               "debug_copy_final_image")
+        return int(b.value)
+
     def final_image(self, slot: int = 0) -> tuple[np.ndarray, int, int, int]:
         """(lines [nlines, 32] u32, bucket shift, log2 lines per bucket, overflowed lines) of the final-step image"""
         L = load_library()
