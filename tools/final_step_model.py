@@ -116,10 +116,10 @@ def main():
 
     # ---- hashed image: load and fallback shares.  Two line formats:
     #   flat    : `slots` entries {tag, offset, length} of 8 bytes, one per run
-    #   grouped : per code present in the line {tag 4 B, run count 1 B} + 3 bytes {offset 2 B, length 1 B} per run,
-    #             124 bytes of payload (runs of one code share the tag; a run longer than 255 counts as several)
+    #   grouped : per code present in the line a header word {tag, run count} + one word {length, offset} per run,
+    #             31 words of payload (oracle/final_step.py; runs of one code share the tag)
     hm = mix(run_code)
-    for b in (12, 14):
+    for b in (14, 16):
         bucket = run_start >> b
         nb = int(N >> b) + 1
         per_bucket = n_runs / nb
@@ -136,7 +136,8 @@ def main():
             load = np.bincount(line, minlength=nb * lines)
             over = load > args.slots
             gline = gbucket * lines + (gmix & np.uint64(lines - 1)).astype(np.int64)
-            gbytes = np.bincount(gline, weights=5 + 3 * gruns, minlength=nb * lines)
+            # the specified format (oracle/final_step.py): one header word per <= 15 runs of a code + one word per run
+            gbytes = np.bincount(gline, weights=4 * (-(-gruns // 15)) + 4 * gruns, minlength=nb * lines)
             gover = gbytes > 124
             qline = (lt >> b) * lines + (mix(qcode) & np.uint64(lines - 1)).astype(np.int64)
             two = (lt >> b) != ((np.maximum(ht, lt + 1) - 1) >> b)
