@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MSBWT_ABI_VERSION 3
+#define MSBWT_ABI_VERSION 4
 
 /* Return codes.  The reference panics where we return EINVAL / EFORMAT; the
  * Rust shim turns those back into panics to keep trait behaviour
@@ -97,7 +97,20 @@ msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *
  * 1 = always (implies quad_index).  Lines that cannot hold their bucket's runs are answered through the quad
  * image, so results are identical on any input.  `oct_bucket_shift`: b, 8..24 (0 = automatic: the largest b
  * that keeps the mean number of runs per line <= 6).  Under an oct image the automatic suffix-table depth is
- * 14 with levels 11..13 kept: a 31-mer is one L2-resident table entry (depth 11) + two oct lines. */
+ * 14 with levels 11..13 kept: a 31-mer is one L2-resident table entry (depth 11) + two oct lines.
+ * `keep_quad_index` (under an oct image): the quad image is what the builders walk LF^4 with; afterwards it only
+ * serves remainders of 4..9 symbols and the oct kernel's rare fallbacks, which one-symbol ranks answer as well.
+ * -1 = automatic (kept when quad + 40 bytes per symbol for the other images fit 70 % of the device: 55 GB at
+ * 1.51 Gsymbols; dropped at 3.02 Gsymbols, where it would be 110 GB), 0 = drop it once the images are built,
+ * 1 = keep (MSBWT_KEEP_QUAD=0|1 overrides the automatic choice).  Results are identical either way.
+ * `final_index`: the FINAL-STEP image on top of the oct image -- the LAST 20 symbols a count_kmer consumes need no
+ * rank, only the number of positions of [l, h) preceded by those 20 symbols, so one hashed 128-byte line of explicit
+ * runs per (20-symbol code, 2^16-position bucket) answers them: a 31-mer is one L2-resident depth-11 table entry +
+ * ONE line fill.  -1 = automatic (built whenever the oct image is; MSBWT_FINAL_INDEX=0|1 overrides), 0 = never,
+ * 1 = always (create fails if it cannot be built).  A line whose groups do not fit, or a range over two buckets,
+ * takes the two oct steps instead, so results are identical on any input.  `final_bucket_shift` (8..16, 0 = 16) and
+ * `final_lines_log2` (12..20 lines per bucket; 0 = automatic: 13 = 16 bytes per symbol when that fits a quarter of
+ * the device memory, else 12 = 8 bytes per symbol). */
 typedef struct msbwt_options {
     uint32_t struct_size;
     uint32_t superblock_shift; /* 0 = default */
@@ -107,9 +120,16 @@ typedef struct msbwt_options {
     int32_t quad_index;        /* -1 = automatic (ABI 3; a caller's shorter ABI-2 struct means -1) */
     int32_t oct_index;         /* -1 = automatic (ABI 3) */
     int32_t oct_bucket_shift;  /* 0 = automatic (ABI 3) */
+    int32_t keep_quad_index;   /* -1 = automatic (ABI 4; a caller's shorter struct means automatic for all four) */
+    int32_t final_index;       /* -1 = automatic (ABI 4) */
+    int32_t final_bucket_shift; /* 0 = default (ABI 4) */
+    int32_t final_lines_log2;  /* 0 = automatic (ABI 4) */
 } msbwt_options;
 msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
                                      const msbwt_options *opts, int *err);
+/* load_numpy_file (src/rle_bwt.rs:81-155) with the same knobs; opts == NULL is msbwt_index_create_from_npy */
+msbwt_index *msbwt_index_create_from_npy_opts(const char *path, const int *devices, int ndev,
+                                              const msbwt_options *opts, int *err);
 
 void msbwt_index_destroy(msbwt_index *idx);
 
@@ -127,16 +147,15 @@ int msbwt_suffix_table_s(const msbwt_index *idx);     /* suffix table depth in u
 int msbwt_kernel_lanes(const msbwt_index *idx);
 int msbwt_pair_index(const msbwt_index *idx); /* 1 when the pair image is in use */
 int msbwt_quad_index(const msbwt_index *idx); /* 1 when the quad image is in use (it replaces the pair image) */
-int msbwt_oct_index(const msbwt_index *idx);  /* 1 when the oct image is in use (next to the quad image) */
+int msbwt_oct_index(const msbwt_index *idx);  /* 1 when the oct image is in use (with or without the quad image beside it) */
 uint64_t msbwt_oct_overflow_lines(const msbwt_index *idx); /* oct lines answered through the quad image */
 uint64_t msbwt_oct_overflow_occurrences(const msbwt_index *idx); /* BWT positions those lines cover */
 uint64_t msbwt_oct_runs(const msbwt_index *idx);           /* runs of equal m-symbol codes in the BWT (chose b) */
 int msbwt_oct_bucket_shift(const msbwt_index *idx);        /* b of the oct image in use, 0 without one */
 int msbwt_oct_symbols(void);                               /* m: symbols (constrain_range steps) per oct line */
 int msbwt_table_depth_for_k(const msbwt_index *idx, uint32_t k); /* suffix-table level an all-ACGT k-mer starts from */
-/* EXPERIMENTAL (not yet run on a GPU): final-step image -- the last 20 symbols of a k-mer answered from ONE hashed
- * 128-byte line (a count needs no rank; DESIGN.md section 7, oracle/final_step.py).  Only in libraries compiled with
- * -DMSBWT_FINAL_STEP and for indexes created with MSBWT_FINAL_INDEX=1; otherwise 0 / EINVAL. */
+/* final-step image (msbwt_options.final_index; specification: oracle/final_step.py): 1 when in use; the debug copy
+ * returns its geometry and, when `lines` is not NULL, the lines themselves */
 int msbwt_final_index(const msbwt_index *idx);
 int msbwt_debug_copy_final_image(const msbwt_index *idx, int slot, uint64_t *nlines, uint32_t *bucket_shift,
                                  uint32_t *lines_log2, uint64_t *overflow_lines, uint32_t *lines /* nlines * 32, or NULL */);
@@ -167,10 +186,12 @@ int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *syms, uint32_
  * pipelines keep: k <= 32, kmers[i] = sum over j of code(s_j) << 2*(k-1-j) with A,C,G,T = 0,1,2,3 and s_0 the FIRST
  * symbol (bits above 2k are ignored); out[i] = BWT::count_kmer of that k-mer (src/msbwt_core.rs:125-161).  Nothing is
  * packed or validated anywhere (such a k-mer cannot hold `$` or `N`): the link carries 8 bytes per query each way
- * instead of k bytes in.  EINVAL when k == 0 or k > 32.
- * EXPERIMENTAL in this round: built and exported, parity tests written (tests/test_gpu_u64_kmers.py) but not yet run
- * on a GPU -- they are skipped unless MSBWT_EXPERIMENTAL=1. */
+ * instead of k bytes in.  EINVAL when k == 0 or k > 32. */
 int msbwt_count_kmers_u64(const msbwt_index *idx, const uint64_t *kmers, uint32_t k, uint64_t n, uint64_t *out);
+/* 32-bit counts: the same two calls for an index below 2^32 symbols (a count can reach total_size; EINVAL
+ * otherwise) -- the copy back to the host carries 4 bytes per query instead of 8. */
+int msbwt_count_kmers_fixed_u32(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n, uint32_t *out);
+int msbwt_count_kmers_u64_u32(const msbwt_index *idx, const uint64_t *kmers, uint32_t k, uint64_t n, uint32_t *out);
 /* host->device and device->host bytes moved by the calling thread's last msbwt_count_kmers_fixed */
 void msbwt_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
 int msbwt_host_pack_threads(void); /* size the packing pool would have in this process */
@@ -208,6 +229,12 @@ int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const uint8_t *d_s
                             void *stream);
 int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot, const uint64_t *d_packed,
                                     uint32_t k, uint64_t n, uint64_t *d_out, void *stream);
+/* Measurement aid (bench.py's roofline accounting): the search over the oct image with a counting build of the
+ * kernel.  d_stats = 8 u64 on the device: oct lines fetched, final-step lines fetched, of which had overflowed,
+ * quad steps, distinct 128-byte lines those read, one-symbol steps, distinct 64-byte blocks those read, queries
+ * walked.  Counts land in d_out as usual.  EINVAL when the index has no oct image. */
+int msbwt_count_kmers_packed_stats_device(const msbwt_index *idx, int slot, const uint64_t *d_packed, uint32_t k,
+                                          uint64_t n, uint64_t *d_out, uint64_t *d_stats, void *stream);
 
 /* Number of kernel launches the library has issued so far (all devices). */
 uint64_t msbwt_launch_count(void);

@@ -5,162 +5,22 @@
 // (src/msbwt_core.rs:28-162, src/rle_bwt.rs:44-322).  There is no CPU fallback
 // anywhere in this file: every query entry point ends in a kernel launch.
 #include <algorithm>
-#include <atomic>
 #include <cerrno>
 #include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <memory>
-#include <mutex>
 
-#include "../../include/msbwt_gpu.h"
-#include "engine.h"
+#include "handle.h"
 #include "kernel_common.cuh"
-#include "hostpack.h"
 
 using namespace msbwt;
 
-namespace {
-
+namespace msbwt {
 thread_local std::string g_last_error;
 thread_local int g_call_launches = 0;
 std::atomic<uint64_t> g_launches{0};
-
-void flush_launches() {
-    g_launches += (uint64_t)g_call_launches;
-    g_call_launches = 0;
-}
-
-int fail(int code, const std::string &msg) {
-    g_last_error = msg;
-    return code;
-}
-
-#define CU_TRY(expr)                                                                              \
-    do {                                                                                          \
-        cudaError_t e_ = (expr);                                                                  \
-        if (e_ != cudaSuccess)                                                                    \
-            return fail(e_ == cudaErrorMemoryAllocation ? MSBWT_ENOMEM : MSBWT_ECUDA,             \
-                        std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
-    } while (0)
-
-// grow-only device buffer
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
-        size_t want = bytes + bytes / 8;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <class T> T *as() const { return (T *)p; }
-};
-
-// grow-only pinned host buffer
-struct PinnedBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
-        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-// per-device staging for the host-buffer entry points: several lanes so that the host-side packing
-// and copy-in of the next chunks overlap the kernels of the current one
-constexpr int kPackLanes = 3;  // lanes whose input is packed by the host pool (or every lane of the byte path)
-constexpr int kRawLanes = 2;   // hybrid route only: lanes that take their chunk as raw symbol bytes over PCIe
-constexpr int kLanes = kPackLanes + kRawLanes;
-struct Lane {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t h2d_done = nullptr;  // the lane's pinned staging buffer may be rewritten after this
-    DevBuf in_a, in_b, in_c, packed, out_a, out_b;
-    PinnedBuf h_stage;
-};
-
-struct Replica {
-    int device = -1;
-    uint4 *d_blocks = nullptr;
-    uint32_t *d_aux = nullptr;
-    void *d_table = nullptr;
-    void *d_table_lower[3] = {nullptr, nullptr, nullptr};  // depths table_s - 1 .. table_s - 3, kept so that a
-                                                           // multi-step image always finds a depth that leaves a multiple
-                                                           // of its stride (pair: one level, quad: three)
-    PairImage pair;            // 128-byte pair lines (layout.h), when the index lives in HBM
-    QuadImage quad;            // 32-byte quad sectors (layout.h), when the index lives in HBM and the image fits
-    OctImage oct;              // 128-byte oct lines (layout.h), next to the quad image when positions are 32-bit
-#ifdef MSBWT_FINAL_STEP
-    FinImage fin;              // EXPERIMENTAL final-step lines (layout.h), only with MSBWT_FINAL_INDEX=1
-#endif
-    int lanes = 1;           // kernel mapping: 1 = thread per query, 2 = lane pair per query (kernels.cu)
-    uint64_t *d_cbase = nullptr;
-    IndexView view{};
-    std::mutex mu;
-    Lane lane[kLanes];
-    DevBuf dev_packed;       // scratch for the *_device entry points
-    uint32_t *d_status = nullptr;  // [0,kLanes): per-lane flags; [kStatusDev]: device entry points
-    uint32_t *h_status = nullptr;  // pinned mirror
-
-    ~Replica() {
-        if (device < 0) return;
-        int cur = 0;
-        cudaGetDevice(&cur);
-        cudaSetDevice(device);
-        for (auto &ln : lane) {
-            if (ln.stream) cudaStreamDestroy(ln.stream);
-            if (ln.h2d_done) cudaEventDestroy(ln.h2d_done);
-            ln.h_stage.release();
-            ln.in_a.release(); ln.in_b.release(); ln.in_c.release();
-            ln.packed.release(); ln.out_a.release(); ln.out_b.release();
-        }
-        dev_packed.release();
-        if (d_status) cudaFree(d_status);
-        if (h_status) cudaFreeHost(h_status);
-        if (d_blocks) cudaFree(d_blocks);
-        if (d_aux) cudaFree(d_aux);
-        if (d_table) cudaFree(d_table);
-        for (void *t : d_table_lower) if (t) cudaFree(t);
-        free_pair_image(pair);
-        free_quad_image(quad);
-        free_oct_image(oct);
-#ifdef MSBWT_FINAL_STEP
-        free_fin_image(fin);
-#endif
-        if (d_cbase) cudaFree(d_cbase);
-        cudaSetDevice(cur);
-    }
-};
-
-struct DeviceGuard {
-    int prev = 0;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
-    ~DeviceGuard() { cudaSetDevice(prev); }
-};
-
-constexpr int kStatusWords = 8, kStatusDev = 7;
-constexpr int kOctAutoTableS = 14;  // automatic suffix-table depth under an oct image (levels 11..14 are kept)
-constexpr uint64_t kChunkQueries = 1ull << 20;  // host-path pipeline granularity (byte route)
-constexpr uint64_t kPackedChunkQueries = 1ull << 19;  // packed route: smaller chunks fill / drain the pipeline sooner
-constexpr uint64_t kChunkBytes = 1ull << 27;
-
-}  // namespace
-
-struct msbwt_index {
-    uint64_t total = 0;
-    uint64_t counts[kAlphabet] = {0, 0, 0, 0, 0, 0};
-    uint64_t start[kAlphabet] = {0, 0, 0, 0, 0, 0};
-    uint64_t bytes_per_replica = 0;
-    uint32_t table_s = 0;
-    std::vector<std::unique_ptr<Replica>> reps;
-};
+}  // namespace msbwt
 
 namespace {
 
@@ -265,6 +125,10 @@ struct Options {
     int quad = -1;      // -1 auto, 0 off, 1 on (builds the pair image on the way and drops it)
     int oct = -1;       // -1 auto (with an automatic or requested quad image), 0 off, 1 on (implies quad)
     int oct_shift = 0;  // 0 auto, else the oct image's bucket shift
+    int keep_quad = -1; // under an oct image: -1 auto, 0 drop the quad image once the other images are built, 1 keep it
+    int fin = -1;       // final-step image on top of the oct image: -1 auto (on), 0 off, 1 on (fail if it cannot be built)
+    int fin_shift = 0;  // 0 = 16
+    int fin_lb = 0;     // 0 auto (13 = 16 B/symbol when that fits a quarter of the device, else 12 = 8 B/symbol)
     int lanes = 0;      // 0 auto, 1, 2
 };
 
@@ -372,19 +236,57 @@ bool pick_oct(const IndexView &view, int requested) {
     return true;
 }
 
-// Builds pair image -> quad image (-> oct image), then drops the pair image (the quad kernel finishes a
-// remainder with one-step ranks, so nothing reads it afterwards).
-int build_quad(msbwt_index *idx, Replica &rep, int oct_requested, int oct_shift) {
+void build_trace(const char *what) {
+    static const bool on = getenv("MSBWT_TRACE") != nullptr;
+    if (!on) return;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    fprintf(stderr, "[msbwt] index build: %s (%.1f GB of device memory free)\n", what, (double)free_b / 1e9);
+}
+
+int env_int(const char *name, int fallback) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : fallback;
+}
+
+void drop_quad(msbwt_index *idx, Replica &rep) {
+    if (!rep.quad.sectors) return;
+    if (idx->reps[0].get() == &rep)
+        idx->bytes_per_replica -= (uint64_t)kQuadCodes * rep.quad.nsec4 * kQuadSectorBytes +
+                                  (rep.quad.c4base ? (uint64_t)rep.quad.n_super4 * kQuadCodes * sizeof(uint64_t) : 0);
+    free_quad_image(rep.quad);
+    rep.view.quad = nullptr;
+    rep.view.c4base = nullptr;
+    rep.view.nsec4 = 0;
+    rep.view.n_super4 = 0;
+    rep.view.sb_shift4 = 0;
+}
+
+// The multi-step images of an index that lives in HBM, built on the replica's device in stages so that the peak
+// footprint stays below the device's memory even for a 3 Gsymbol BWT:
+//   pair image + pair codes -> quad image + quad codes (pair image dropped) -> 10-symbol codes (quad codes dropped)
+//   -> 20-symbol codes -> [quad image dropped unless it is kept] -> oct lines -> final-step lines.
+// The quad image is what the builders walk LF^4 with; afterwards it only serves remainders of 4..9 symbols and the
+// rare fallbacks (overflowed line, range over two buckets) of the oct kernel, which one-symbol ranks answer as
+// well.  It is kept when everything fits comfortably (`keep_quad` -1: quad + 40 B/symbol for the other two images
+// within 70 % of the device memory: 55 GB at 1.51 Gsymbols), dropped otherwise (110 GB at 3.02 Gsymbols) -- and
+// always kept when there is no oct image on top (N >= 2^32, or switched off): then it is the search image.
+int build_multi_step(msbwt_index *idx, Replica &rep, const Options &opt) {
     uint8_t *codes2 = nullptr;
     if (int rc = build_pair(idx, rep, &codes2); rc != MSBWT_OK) return rc;
     DeviceGuard guard(rep.device);
-    const bool want_oct = pick_oct(rep.view, oct_requested);
+    struct DevPtr { void *p = nullptr; ~DevPtr() { if (p) cudaFree(p); } void reset() { if (p) cudaFree(p); p = nullptr; } };
+    DevPtr codes2_owner, codes10_owner;
+    codes2_owner.p = codes2;
+    const bool want_oct = pick_oct(rep.view, opt.oct);
+    const int fin_req = opt.fin != -1 ? opt.fin : env_int("MSBWT_FINAL_INDEX", -1);
+    const bool want_fin = want_oct && fin_req != 0;
     uint16_t *codes4 = nullptr;
     std::string why;
     int n = 0;
+    build_trace("quad image");
     int rc = build_quad_image_on_device(rep.device, rep.view, codes2, rep.quad, why, &n, want_oct ? &codes4 : nullptr);
     g_launches += (uint64_t)n;
-    struct Codes2 { uint8_t *p; ~Codes2() { if (p) cudaFree(p); } } codes2_owner{codes2};  // the oct builder reads them too
     if (idx->reps[0].get() == &rep) idx->bytes_per_replica -= pair_image_bytes(rep.pair);
     free_pair_image(rep.pair);
     rep.view.pair = nullptr;
@@ -397,55 +299,88 @@ int build_quad(msbwt_index *idx, Replica &rep, int oct_requested, int oct_shift)
     rep.view.nsec4 = rep.quad.nsec4;
     rep.view.n_super4 = rep.quad.n_super4;
     rep.view.sb_shift4 = rep.quad.sb_shift4;
-    if (idx->reps[0].get() == &rep)
-        idx->bytes_per_replica += (uint64_t)kQuadCodes * rep.quad.nsec4 * kQuadSectorBytes +
-                                  (rep.quad.c4base ? (uint64_t)rep.quad.n_super4 * kQuadCodes * sizeof(uint64_t) : 0);
-    if (want_oct) {
+    const uint64_t quad_bytes = (uint64_t)kQuadCodes * rep.quad.nsec4 * kQuadSectorBytes +
+                                (rep.quad.c4base ? (uint64_t)rep.quad.n_super4 * kQuadCodes * sizeof(uint64_t) : 0);
+    if (idx->reps[0].get() == &rep) idx->bytes_per_replica += quad_bytes;
+    if (!want_oct) return MSBWT_OK;
+
+    const uint64_t N = rep.view.total;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { free_b = 0; total_b = 0; }
+    int keep_quad = opt.keep_quad != -1 ? opt.keep_quad : env_int("MSBWT_KEEP_QUAD", -1);
+    if (keep_quad == -1) keep_quad = quad_bytes + 40 * N <= (uint64_t)total_b / 10 * 7 ? 1 : 0;
+
+    // 10-symbol codes (4 B per position), then 20-symbol codes (8 B per position): both walk LF^4 through the quad image
+    uint32_t *codes10 = nullptr;
+    n = 0;
+    build_trace("10-symbol codes");
+    rc = build_oct_codes_on_device(rep.device, rep.view, codes4, codes2, &codes10, why, &n);  // frees codes4
+    g_launches += (uint64_t)n;
+    if (rc != MSBWT_OK) return fail(rc, why);
+    codes10_owner.p = codes10;
+    codes2_owner.reset();
+    uint64_t *codes20 = nullptr;
+    int fshift = opt.fin_shift ? opt.fin_shift : env_int("MSBWT_FINAL_BUCKET_SHIFT", 16);
+    int flb = opt.fin_lb ? opt.fin_lb : env_int("MSBWT_FINAL_LINES_LOG2", 0);
+    if (want_fin) {
+        if (!flb) flb = fin_image_bytes(N, fshift, 13) <= (uint64_t)total_b / 4 ? 13 : 12;  // 16 or 8 bytes per symbol
         n = 0;
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
-        // the kOctSyms-symbol codes (4 B per position) are scratch of the build and must fit next to the image
-        const uint64_t scratch = 4 * rep.view.total;
-        // what is left after that scratch and 8 GB kept for the suffix table and the query pipeline; the builder
-        // picks coarser buckets, or builds nothing, beyond it
-        const uint64_t keep = scratch + (8ull << 30);
-        const uint64_t budget = oct_requested == 1 ? (free_b > scratch ? free_b - scratch : 0) : (free_b > keep ? free_b - keep : 0);
-        if (!oct_shift)
-            if (const char *env = getenv("MSBWT_OCT_BUCKET_SHIFT")) oct_shift = atoi(env);
-#ifdef MSBWT_FINAL_STEP
-        const char *fin_env = getenv("MSBWT_FINAL_INDEX");
-        const bool want_fin = fin_env && atoi(fin_env) != 0;
-        uint32_t *codes10 = nullptr;
-        rc = build_oct_image_on_device(rep.device, rep.view, codes4, codes2, oct_shift, budget, rep.oct, why, &n,
-                                       want_fin ? &codes10 : nullptr);  // frees codes4
-#else
-        rc = build_oct_image_on_device(rep.device, rep.view, codes4, codes2, oct_shift, budget, rep.oct, why, &n);  // frees codes4
-#endif
+        rc = build_fin_codes_on_device(rep.device, rep.view, codes10, &codes20, why, &n);
         g_launches += (uint64_t)n;
-        if (rc != MSBWT_OK) { free_oct_image(rep.oct); return fail(rc, why); }
-        if (rep.oct.lines) {
-            rep.view.oct = rep.oct.lines;
-            rep.view.nbuck8 = rep.oct.nbuck8;
-            rep.view.oct_shift = (uint32_t)rep.oct.shift;
-            if (idx->reps[0].get() == &rep) idx->bytes_per_replica += (uint64_t)kOctCodes * rep.oct.nbuck8 * kOctLineBytes;
+        if (rc == MSBWT_ENOMEM && fin_req != 1) {  // no room for the codes: the index works without this image
+            cudaGetLastError();
+            codes20 = nullptr;
+        } else if (rc != MSBWT_OK) {
+            return fail(rc, why);
         }
-#ifdef MSBWT_FINAL_STEP
-        if (codes10 && !rep.oct.lines) { cudaFree(codes10); codes10 = nullptr; }
-        if (codes10) {  // EXPERIMENTAL: the final-step lines on top of the oct image
-            int fshift = 16, flb = 12;
-            if (const char *env = getenv("MSBWT_FINAL_BUCKET_SHIFT")) fshift = atoi(env);
-            if (const char *env = getenv("MSBWT_FINAL_LINES_LOG2")) flb = atoi(env);
-            n = 0;
-            rc = build_fin_image_on_device(rep.device, rep.view, codes10, fshift, flb, rep.fin, why, &n);  // frees codes10
-            g_launches += (uint64_t)n;
-            if (rc != MSBWT_OK) { free_fin_image(rep.fin); return fail(rc, why); }
-            rep.view.fin = rep.fin.lines;
-            rep.view.fin_shift = (uint32_t)rep.fin.shift;
-            rep.view.fin_lb = (uint32_t)rep.fin.lb;
-            if (idx->reps[0].get() == &rep) idx->bytes_per_replica += rep.fin.nlines * (uint64_t)kFinLineBytes;
-        }
-#endif
     }
+    struct Codes20 { uint64_t *p; ~Codes20() { if (p) cudaFree(p); } } codes20_owner{codes20};
+    if (!keep_quad) {
+        build_trace("dropping the quad image");
+        drop_quad(idx, rep);
+    }
+
+    // oct lines: what is left after the final-step lines, their sort scratch (about 16 B per position, of which the
+    // 12 B per position of the two code arrays are free again by then) and 8 GB for the suffix table and the query
+    // pipeline; the builder picks coarser buckets, or builds nothing, beyond that
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+    const uint64_t fin_need = codes20 ? fin_image_bytes(N, fshift, flb) + 4 * N : 0;
+    const uint64_t reserve = fin_need + (opt.oct == 1 ? 0 : (8ull << 30));
+    const uint64_t budget = free_b > reserve ? free_b - reserve : 0;
+    int oct_shift = opt.oct_shift ? opt.oct_shift : env_int("MSBWT_OCT_BUCKET_SHIFT", 0);
+    n = 0;
+    build_trace("oct lines");
+    rc = build_oct_lines_on_device(rep.device, rep.view, codes10, oct_shift, budget, rep.oct, why, &n);
+    g_launches += (uint64_t)n;
+    codes10_owner.reset();
+    if (rc != MSBWT_OK) { free_oct_image(rep.oct); return fail(rc, why); }
+    if (!rep.oct.lines) {  // no room at all: the quad image serves alone and must stay
+        if (!rep.view.quad) return fail(MSBWT_ENOMEM, "no room for the oct image after the quad image was dropped (MSBWT_KEEP_QUAD=1 keeps it)");
+        return MSBWT_OK;
+    }
+    rep.view.oct = rep.oct.lines;
+    rep.view.nbuck8 = rep.oct.nbuck8;
+    rep.view.oct_shift = (uint32_t)rep.oct.shift;
+    if (idx->reps[0].get() == &rep) idx->bytes_per_replica += (uint64_t)kOctCodes * rep.oct.nbuck8 * kOctLineBytes;
+
+    if (codes20) {  // final-step lines on top of the oct image
+        n = 0;
+        codes20_owner.p = nullptr;  // owned by the builder from here
+        rc = build_fin_lines_on_device(rep.device, N, codes20, fshift, flb, rep.fin, why, &n);
+        g_launches += (uint64_t)n;
+        if (rc == MSBWT_ENOMEM && fin_req != 1) {  // the index works without this image
+            cudaGetLastError();
+            free_fin_image(rep.fin);
+            rep.fin = FinImage{};
+            return MSBWT_OK;
+        }
+        if (rc != MSBWT_OK) { free_fin_image(rep.fin); return fail(rc, why); }
+        rep.view.fin = rep.fin.lines;
+        rep.view.fin_shift = (uint32_t)rep.fin.shift;
+        rep.view.fin_lb = (uint32_t)rep.fin.lb;
+        if (idx->reps[0].get() == &rep) idx->bytes_per_replica += rep.fin.nlines * (uint64_t)kFinLineBytes;
+    }
+    build_trace("multi-step images done");
     return MSBWT_OK;
 }
 
@@ -455,7 +390,7 @@ int build_suffix_table(msbwt_index *idx, Replica &rep, int s) {
     const bool wide = index_is_wide(rep.view);
     const size_t eb = wide ? 16 : 8;
     // levels kept: s, and the (stride - 1) below it that a multi-step image may start from
-    const int keep_lower = rep.view.quad ? 3 : (rep.view.pair ? 1 : 0);
+    const int keep_lower = (rep.view.quad || rep.view.oct) ? 3 : (rep.view.pair ? 1 : 0);
     const int lowest_kept = std::max(1, s - keep_lower);
     std::vector<void *> level((size_t)s + 1, nullptr);
     void *scratch[2] = {nullptr, nullptr};
@@ -540,11 +475,10 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
                 quad = opt.oct == 1 || pick_quad(rep->device, one_step_bytes, idx->total, opt.quad, opt.pair, with_oct);
             }
             if (quad || pick_pair(rep->device, one_step_bytes, opt.pair)) {
-                if ((rc = quad ? build_quad(idx.get(), *rep, opt.oct, opt.oct_shift) : build_pair(idx.get(), *rep)) != MSBWT_OK) break;
+                if ((rc = quad ? build_multi_step(idx.get(), *rep, opt) : build_pair(idx.get(), *rep)) != MSBWT_OK) break;
                 if (!explicit_s && (quad || lives_in_hbm(rep->device, one_step_bytes))) {
                     DeviceGuard guard(rep->device);
-                    const uint64_t multi = quad ? (uint64_t)kQuadCodes * rep->quad.nsec4 * kQuadSectorBytes
-                                                : rep->view.npair * kPairBytes;
+                    const uint64_t multi = quad ? quad_image_bytes(idx->total) : rep->view.npair * kPairBytes;
                     s = deepen_table_for_hbm(s0, idx->reps[0]->view.nblocks * kBlockBytes + multi, wide ? 16 : 8);
                     // with ten symbols per oct line a 31-mer wants the depth-11 level (33 MB, L2-resident): the
                     // deepest of the four kept levels need not go beyond 14 (2.1 GB instead of 8.6 GB at 15)
@@ -559,18 +493,6 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
     if (err) *err = rc;
     if (rc != MSBWT_OK) return nullptr;
     return idx.release();
-}
-
-// one device's share of a host batch
-struct Slice { uint64_t begin, end; };
-
-Slice slice_for(uint64_t n, size_t d, size_t ndev) { return {n * d / ndev, n * (d + 1) / ndev}; }
-
-int check_status_flags(msbwt_index const *idx, const char *what) {
-    for (auto &rep : idx->reps)
-        if (std::any_of(rep->h_status, rep->h_status + kLanes, [](uint32_t v) { return v != 0; }))
-            return fail(MSBWT_EINVAL, std::string(what) + ": symbol >= 6 or range out of bounds in the batch");
-    return MSBWT_OK;
 }
 
 }  // namespace
@@ -590,15 +512,11 @@ extern "C" msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, 
     return create_common(rle, len, devices, ndev, o, err);
 }
 
-extern "C" msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
-                                               const msbwt_options *opts, int *err) {
-    Options o;
+namespace {
+int parse_options(const msbwt_options *opts, Options &o) {
     if (opts) {
-        if (opts->struct_size < offsetof(msbwt_options, quad_index)) {  // the ABI-2 struct ended before quad_index
-            fail(MSBWT_EINVAL, "msbwt_options.struct_size is smaller than the oldest msbwt_options this library accepts");
-            if (err) *err = MSBWT_EINVAL;
-            return nullptr;
-        }
+        if (opts->struct_size < offsetof(msbwt_options, quad_index))  // the ABI-2 struct ended before quad_index
+            return fail(MSBWT_EINVAL, "msbwt_options.struct_size is smaller than the oldest msbwt_options this library accepts");
         o.sb_shift = opts->superblock_shift;
         o.table_s = opts->suffix_table_s;
         o.pair = opts->pair_index;
@@ -606,6 +524,24 @@ extern "C" msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len
         if (opts->struct_size >= offsetof(msbwt_options, quad_index) + sizeof(int32_t)) o.quad = opts->quad_index;
         if (opts->struct_size >= offsetof(msbwt_options, oct_index) + sizeof(int32_t)) o.oct = opts->oct_index;
         if (opts->struct_size >= offsetof(msbwt_options, oct_bucket_shift) + sizeof(int32_t)) o.oct_shift = opts->oct_bucket_shift;
+        if (opts->struct_size >= offsetof(msbwt_options, final_lines_log2) + sizeof(int32_t)) {  // the four ABI-4 fields
+            o.keep_quad = opts->keep_quad_index;
+            o.fin = opts->final_index;
+            o.fin_shift = opts->final_bucket_shift;
+            o.fin_lb = opts->final_lines_log2;
+        }
+    }
+    return MSBWT_OK;
+}
+
+}  // namespace
+
+extern "C" msbwt_index *msbwt_index_create_opts(const uint8_t *rle, uint64_t len, const int *devices, int ndev,
+                                               const msbwt_options *opts, int *err) {
+    Options o;
+    if (int rc = parse_options(opts, o); rc != MSBWT_OK) {
+        if (err) *err = rc;
+        return nullptr;
     }
     return create_common(rle, len, devices, ndev, o, err);
 }
@@ -621,6 +557,25 @@ extern "C" msbwt_index *msbwt_index_create_from_npy(const char *path, const int 
         return nullptr;
     }
     return create_common(payload.data(), payload.size(), devices, ndev, Options{}, err);
+}
+
+extern "C" msbwt_index *msbwt_index_create_from_npy_opts(const char *path, const int *devices, int ndev,
+                                                        const msbwt_options *opts, int *err) {
+    g_last_error.clear();
+    Options o;
+    if (int rc = parse_options(opts, o); rc != MSBWT_OK) {
+        if (err) *err = rc;
+        return nullptr;
+    }
+    std::vector<uint8_t> payload;
+    std::string why;
+    int rc = read_npy_payload(path, payload, why);
+    if (rc != MSBWT_OK) {
+        fail(rc, why);
+        if (err) *err = rc;
+        return nullptr;
+    }
+    return create_common(payload.data(), payload.size(), devices, ndev, o, err);
 }
 
 extern "C" void msbwt_index_destroy(msbwt_index *idx) { delete idx; }
@@ -652,17 +607,11 @@ extern "C" int msbwt_oct_symbols(void) { return kOctSyms; }
 // EXPERIMENTAL final-step image (layout.h): 0 / EINVAL unless the library was compiled with -DMSBWT_FINAL_STEP and
 // the index was created with MSBWT_FINAL_INDEX=1
 extern "C" int msbwt_final_index(const msbwt_index *idx) {
-#ifdef MSBWT_FINAL_STEP
     return (idx && !idx->reps.empty() && idx->reps[0]->view.fin) ? 1 : 0;
-#else
-    (void)idx;
-    return 0;
-#endif
 }
 extern "C" int msbwt_debug_copy_final_image(const msbwt_index *idx, int slot, uint64_t *nlines, uint32_t *bucket_shift,
                                             uint32_t *lines_log2, uint64_t *overflow_lines, uint32_t *lines) {
     g_last_error.clear();
-#ifdef MSBWT_FINAL_STEP
     if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
     Replica &rep = *idx->reps[(size_t)slot];
     if (!rep.fin.lines) return fail(MSBWT_EINVAL, "this index has no final-step image");
@@ -675,10 +624,6 @@ extern "C" int msbwt_debug_copy_final_image(const msbwt_index *idx, int slot, ui
         CU_TRY(cudaMemcpy(lines, rep.fin.lines, rep.fin.nlines * (size_t)kFinLineBytes, cudaMemcpyDeviceToHost));
     }
     return MSBWT_OK;
-#else
-    (void)idx; (void)slot; (void)nlines; (void)bucket_shift; (void)lines_log2; (void)overflow_lines; (void)lines;
-    return fail(MSBWT_EINVAL, "the library was built without -DMSBWT_FINAL_STEP");
-#endif
 }
 // the depth policy on its own (no device needed): `steps` = symbols per step of the image that serves list A
 // (1 one-step blocks, 2 pair lines, 4 quad sectors, kOctSyms oct lines)
@@ -729,6 +674,11 @@ extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, 
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t per = std::min<uint64_t>(n, kMaxPerLaunch);
     uint32_t *flag = d_status ? d_status : rep.d_status + kStatusDev;
+    // The call is asynchronous and its pack / seed scratch is the replica's: a later call on ANOTHER stream must not
+    // start rewriting the scratch while this one's kernels still read it.  Every call records an event after its last
+    // launch and makes its own stream wait for the previous call's event first (a no-op on the same stream).
+    if (!rep.dev_packed_free) CU_TRY(cudaEventCreateWithFlags(&rep.dev_packed_free, cudaEventDisableTiming));
+    else CU_TRY(cudaStreamWaitEvent(st, rep.dev_packed_free, 0));
     CU_TRY(cudaMemsetAsync(flag, 0, sizeof(uint32_t), st));
     if (fused_enabled() && fused_path_applies(rep.view, d_syms, k)) {
         // one kernel from symbol bytes to counts (fused_kernels.cu); sub-batches of 2^30 keep the 16-byte alignment
@@ -739,6 +689,7 @@ extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, 
                                       rep.dev_packed.as<uint32_t>(), st, &g_call_launches));
             flush_launches();
         }
+        CU_TRY(cudaEventRecord(rep.dev_packed_free, st));
         return MSBWT_OK;
     }
     CU_TRY(rep.dev_packed.reserve(packed_layout(rep.view, k, per).total() * sizeof(uint64_t)));
@@ -750,6 +701,7 @@ extern "C" int msbwt_count_kmers_fixed_device(const msbwt_index *idx, int slot, 
                                    &g_call_launches));
         flush_launches();
     }
+    CU_TRY(cudaEventRecord(rep.dev_packed_free, st));
     return MSBWT_OK;
 }
 
@@ -783,6 +735,23 @@ extern "C" int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot,
     return MSBWT_OK;
 }
 
+// Measurement aid: msbwt_count_kmers_packed_device over list A with the counting instantiation of the oct kernel
+// (stats_kernels.cu).  d_stats: 8 u64 on the device -- oct lines, final-step lines, of which overflowed, quad steps,
+// 128-byte lines those read, one-symbol steps, 64-byte blocks those read, queries walked.  EINVAL without an oct image.
+extern "C" int msbwt_count_kmers_packed_stats_device(const msbwt_index *idx, int slot, const uint64_t *d_packed, uint32_t k,
+                                                     uint64_t n, uint64_t *d_out, uint64_t *d_stats, void *stream) {
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
+    if (n && (!d_out || !d_packed || !d_stats)) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (n > kMaxPerLaunch) return fail(MSBWT_EINVAL, "more than 2^30 queries per pack/count pair: split the batch");
+    Replica &rep = *idx->reps[slot];
+    if (!rep.view.oct) return fail(MSBWT_EINVAL, "this index has no oct image");
+    if (!n) return MSBWT_OK;
+    DeviceGuard guard(rep.device);
+    CU_TRY(launch_count_oct_stats(rep.device, rep.view, d_packed, k, n, d_out, (unsigned long long *)d_stats, (cudaStream_t)stream));
+    g_launches++;
+    return MSBWT_OK;
+}
+
 extern "C" int msbwt_constrain_ranges_device(const msbwt_index *idx, int slot, const uint8_t *d_sym,
                                              const uint64_t *d_l, const uint64_t *d_h, uint64_t n,
                                              uint64_t *d_out_l, uint64_t *d_out_h, void *stream) {
@@ -793,429 +762,6 @@ extern "C" int msbwt_constrain_ranges_device(const msbwt_index *idx, int slot, c
     DeviceGuard guard(rep.device);
     CU_TRY(launch_constrain_ranges(rep.device, rep.view, d_sym, d_l, d_h, n, d_out_l, d_out_h, (cudaStream_t)stream, &g_call_launches));
     flush_launches();
-    return MSBWT_OK;
-}
-
-// ================================================================ host-buffer entry points
-
-namespace {
-
-thread_local uint64_t g_last_h2d = 0, g_last_d2h = 0;
-
-// The byte path: the caller's symbol bytes are copied to the device as they are and packed there
-// (pack_seed_kernel).  PCIe carries k bytes per query.  Caller holds the replica locks.
-int fixed_bytes_path(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n, uint64_t *out) {
-    const size_t ndev = idx->reps.size();
-    uint64_t chunk = kChunkQueries;
-    if (k && chunk * k > kChunkBytes) chunk = std::max<uint64_t>(1, kChunkBytes / k);
-
-    uint64_t max_chunks = 0;
-    for (size_t d = 0; d < ndev; d++) {
-        Replica &rep = *idx->reps[d];
-        DeviceGuard guard(rep.device);
-        const Slice sl = slice_for(n, d, ndev);
-        const uint64_t len = sl.end - sl.begin;
-        const uint64_t c = std::min(chunk, len);
-        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
-        for (auto &ln : rep.lane) {
-            CU_TRY(cudaStreamSynchronize(ln.stream));
-            CU_TRY(ln.in_a.reserve(std::max<uint64_t>(1, c * k)));
-            CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, std::max<uint64_t>(1, c)).total() * sizeof(uint64_t)));
-            CU_TRY(ln.out_a.reserve(std::max<uint64_t>(1, c * sizeof(uint64_t))));
-        }
-        CU_TRY(cudaMemsetAsync(rep.d_status, 0, kLanes * sizeof(uint32_t), rep.lane[0].stream));
-        CU_TRY(cudaStreamSynchronize(rep.lane[0].stream));
-    }
-    // chunks are issued round-robin over devices so every GPU always has work queued
-    for (uint64_t c = 0; c < max_chunks; c++) {
-        for (size_t d = 0; d < ndev; d++) {
-            Replica &rep = *idx->reps[d];
-            const Slice sl = slice_for(n, d, ndev);
-            const uint64_t b = sl.begin + c * chunk;
-            if (b >= sl.end) continue;
-            const uint64_t m = std::min(chunk, sl.end - b);
-            DeviceGuard guard(rep.device);
-            const int li = (int)(c % kLanes);
-            Lane &ln = rep.lane[li];
-            if (k) CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + b * k, m * k, cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
-                                    rep.d_status + li, ln.stream));
-            g_launches++;
-            CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
-                                       ln.stream, &g_call_launches));
-            flush_launches();
-            CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-            g_last_h2d += m * k;
-            g_last_d2h += m * sizeof(uint64_t);
-        }
-    }
-    for (auto &rep : idx->reps) {
-        DeviceGuard guard(rep->device);
-        for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
-        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, kLanes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    }
-    return check_status_flags(idx, "count_kmers_fixed");
-}
-
-HostPool &host_pool() {
-    static HostPool pool(host_threads_available());
-    return pool;
-}
-
-// Host-side 2-bit packing pays off when enough host threads can feed it: the byte path moves k bytes
-// per query over PCIe (~55 GB/s), the packed path 8 * ceil(k/32) but needs the CPU to read the k bytes.
-bool use_host_pack(uint32_t k, uint64_t n) {
-    if (!k || k > max_host_packed_k() || n < 4096) return false;
-    if (const char *env = getenv("MSBWT_HOST_PACK")) return atoi(env) != 0;
-    return host_threads_available() >= 8;
-}
-
-// true when `p` is page-locked host memory the copy engine can read while the host does something else
-// (cudaMemcpyAsync from pageable memory stages through the driver and holds the calling thread)
-bool is_pinned_host(const void *p) {
-    cudaPointerAttributes a{};
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost;
-}
-
-// The packed / hybrid path (hostpack.cpp): worker threads pack all-ACGT k-mers 2 bits per symbol into a
-// lane's pinned staging buffer while earlier chunks are copied and searched; the device receives
-// 8 * ceil(k/32) bytes per query (seed_packed_kernel).  K-mers with any other symbol are exceptions:
-// they are collected and sent through the byte path afterwards, which validates and counts them.
-// HYBRID (the caller's buffer is pinned): the host pool is bound by host memory bandwidth (it has to read
-// k bytes per query) while the PCIe link idles at 8 bytes per query, so whenever the copy engine has
-// drained the previous raw chunk the next chunk goes over the link as it is -- k symbol bytes, packed and
-// validated on the device (pack_seed_kernel) -- instead of through the pool.  The split balances itself:
-// a raw lane is taken exactly when its last copy-in has completed.
-int fixed_packed_path(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n, uint64_t *out) {
-    const size_t ndev = idx->reps.size();
-    const uint32_t nw = (k + kPairSymsPerWord - 1) / kPairSymsPerWord;
-    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(kPackedChunkQueries, kChunkBytes / (8ull * nw)));
-    bool hybrid = is_pinned_host(syms);
-    if (const char *env = getenv("MSBWT_HYBRID")) hybrid = hybrid && atoi(env) != 0;
-    HostPool &pool = host_pool();
-    struct Session {  // the workers spin for the duration of this call only
-        HostPool &p;
-        explicit Session(HostPool &pool_) : p(pool_) { p.begin_session(); }
-        ~Session() { p.end_session(); }
-    } session(pool);
-    const int nt = pool.size();
-    std::vector<std::vector<uint64_t>> exc_by_thread((size_t)nt);
-
-    uint64_t max_chunks = 0;
-    for (size_t d = 0; d < ndev; d++) {
-        Replica &rep = *idx->reps[d];
-        DeviceGuard guard(rep.device);
-        const Slice sl = slice_for(n, d, ndev);
-        const uint64_t len = sl.end - sl.begin;
-        const uint64_t c = std::max<uint64_t>(1, std::min(chunk, len));
-        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
-        for (int li = 0; li < kLanes; li++) {
-            Lane &ln = rep.lane[li];
-            CU_TRY(cudaStreamSynchronize(ln.stream));
-            if (li < kPackLanes) {
-                CU_TRY(ln.h_stage.reserve(c * nw * sizeof(uint64_t)));
-                CU_TRY(ln.in_b.reserve(c * nw * sizeof(uint64_t)));
-            } else if (hybrid) {
-                CU_TRY(ln.in_a.reserve(c * k));
-            } else {
-                continue;
-            }
-            CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, c).total() * sizeof(uint64_t)));
-            CU_TRY(ln.out_a.reserve(c * sizeof(uint64_t)));
-        }
-        CU_TRY(cudaMemsetAsync(rep.d_status, 0, kLanes * sizeof(uint32_t), rep.lane[0].stream));
-        CU_TRY(cudaStreamSynchronize(rep.lane[0].stream));
-    }
-    std::vector<uint64_t> packed_turn(ndev, 0);
-    for (uint64_t c = 0; c < max_chunks; c++) {
-        for (size_t d = 0; d < ndev; d++) {
-            Replica &rep = *idx->reps[d];
-            const Slice sl = slice_for(n, d, ndev);
-            const uint64_t b = sl.begin + c * chunk;
-            if (b >= sl.end) continue;
-            const uint64_t m = std::min(chunk, sl.end - b);
-            DeviceGuard guard(rep.device);
-            int raw_lane = -1;
-            if (hybrid)
-                for (int r = 0; r < kRawLanes && raw_lane < 0; r++)
-                    if (cudaEventQuery(rep.lane[kPackLanes + r].h2d_done) == cudaSuccess) raw_lane = kPackLanes + r;
-            if (raw_lane >= 0) {  // the link is idle: this chunk travels as symbol bytes
-                Lane &ln = rep.lane[raw_lane];
-                CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + b * k, m * k, cudaMemcpyHostToDevice, ln.stream));
-                CU_TRY(cudaEventRecord(ln.h2d_done, ln.stream));
-                CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
-                                        rep.d_status + raw_lane, ln.stream));
-                g_launches++;
-                CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
-                                           ln.stream, &g_call_launches));
-                flush_launches();
-                CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-                g_last_h2d += m * k;
-                g_last_d2h += m * sizeof(uint64_t);
-                continue;
-            }
-            Lane &ln = rep.lane[packed_turn[d]++ % kPackLanes];
-            CU_TRY(cudaEventSynchronize(ln.h2d_done));  // the lane's staging buffer is free again
-            uint64_t *stage = (uint64_t *)ln.h_stage.p;
-            pool.run([&](int tid, int nthreads) {
-                const uint64_t q0 = b + m * (uint64_t)tid / (uint64_t)nthreads, q1 = b + m * (uint64_t)(tid + 1) / (uint64_t)nthreads;
-                host_pack_range(syms, k, n, q0, q1, b, m, stage, exc_by_thread[(size_t)tid]);
-            });
-            CU_TRY(cudaMemcpyAsync(ln.in_b.p, stage, m * nw * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(cudaEventRecord(ln.h2d_done, ln.stream));
-            CU_TRY(launch_seed_packed(rep.view, ln.in_b.as<uint64_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
-                                      ln.stream));
-            g_launches++;
-            CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
-                                       ln.stream, &g_call_launches, packed_batch_needs_list_b(rep.view, k)));
-            flush_launches();
-            CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-            g_last_h2d += m * nw * sizeof(uint64_t);
-            g_last_d2h += m * sizeof(uint64_t);
-        }
-    }
-    for (auto &rep : idx->reps) {
-        DeviceGuard guard(rep->device);
-        for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
-        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, kLanes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    }
-    if (int rc = check_status_flags(idx, "count_kmers_fixed"); rc != MSBWT_OK) return rc;  // raw chunks validate on the device
-    // exceptions: k-mers with a symbol outside ACGT go through the byte path (device-side validation)
-    std::vector<uint64_t> exc;
-    for (auto &v : exc_by_thread) exc.insert(exc.end(), v.begin(), v.end());
-    if (exc.empty()) return MSBWT_OK;
-    std::vector<uint8_t> esyms(exc.size() * (size_t)k);
-    std::vector<uint64_t> eout(exc.size());
-    for (size_t i = 0; i < exc.size(); i++) memcpy(esyms.data() + i * k, syms + exc[i] * k, k);
-    if (int rc = fixed_bytes_path(idx, esyms.data(), k, exc.size(), eout.data()); rc != MSBWT_OK) return rc;
-    for (size_t i = 0; i < exc.size(); i++) out[exc[i]] = eout[i];
-    return MSBWT_OK;
-}
-
-}  // namespace
-
-extern "C" int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n,
-                                       uint64_t *out) {
-    g_last_error.clear();
-    g_last_h2d = g_last_d2h = 0;
-    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
-    if (n && (!out || (k && !syms))) return fail(MSBWT_EINVAL, "NULL host buffer");
-    if (!n) return MSBWT_OK;
-    std::vector<std::unique_lock<std::mutex>> locks;
-    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
-    return use_host_pack(k, n) ? fixed_packed_path(idx, syms, k, n, out) : fixed_bytes_path(idx, syms, k, n, out);
-}
-
-namespace {
-
-// K-mers the caller already holds as integers (k <= 32): nothing to do on the host, 8 bytes per query over the
-// link each way.  Chunks go round-robin over devices and lanes; a lane's stream orders copy-in, seed, search and
-// copy-out, so its buffers are reused safely by its next chunk.  Caller holds the replica locks.
-int u64_path(const msbwt_index *idx, const uint64_t *kmers, uint32_t k, uint64_t n, uint64_t *out) {
-    const size_t ndev = idx->reps.size();
-    const uint64_t chunk = kPackedChunkQueries;
-    uint64_t max_chunks = 0;
-    for (size_t d = 0; d < ndev; d++) {
-        Replica &rep = *idx->reps[d];
-        DeviceGuard guard(rep.device);
-        const Slice sl = slice_for(n, d, ndev);
-        const uint64_t len = sl.end - sl.begin;
-        const uint64_t c = std::max<uint64_t>(1, std::min(chunk, len));
-        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
-        for (auto &ln : rep.lane) {
-            CU_TRY(cudaStreamSynchronize(ln.stream));
-            CU_TRY(ln.in_b.reserve(c * sizeof(uint64_t)));
-            CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, c).total() * sizeof(uint64_t)));
-            CU_TRY(ln.out_a.reserve(c * sizeof(uint64_t)));
-        }
-    }
-    for (uint64_t c = 0; c < max_chunks; c++) {
-        for (size_t d = 0; d < ndev; d++) {
-            Replica &rep = *idx->reps[d];
-            const Slice sl = slice_for(n, d, ndev);
-            const uint64_t b = sl.begin + c * chunk;
-            if (b >= sl.end) continue;
-            const uint64_t m = std::min(chunk, sl.end - b);
-            DeviceGuard guard(rep.device);
-            Lane &ln = rep.lane[c % kLanes];
-            CU_TRY(cudaMemcpyAsync(ln.in_b.p, kmers + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(launch_seed_u64(rep.view, ln.in_b.as<uint64_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
-                                   ln.stream));
-            g_launches++;
-            CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
-                                       ln.stream, &g_call_launches, packed_batch_needs_list_b(rep.view, k)));
-            flush_launches();
-            CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-            g_last_h2d += m * sizeof(uint64_t);
-            g_last_d2h += m * sizeof(uint64_t);
-        }
-    }
-    for (auto &rep : idx->reps) {
-        DeviceGuard guard(rep->device);
-        for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
-    }
-    return MSBWT_OK;
-}
-
-}  // namespace
-
-extern "C" int msbwt_count_kmers_u64(const msbwt_index *idx, const uint64_t *kmers, uint32_t k, uint64_t n, uint64_t *out) {
-    g_last_error.clear();
-    g_last_h2d = g_last_d2h = 0;
-    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
-    if (k == 0 || k > 32) return fail(MSBWT_EINVAL, "count_kmers_u64: k must be 1..32 (one 2-bit-per-symbol word per k-mer)");
-    if (n && (!out || !kmers)) return fail(MSBWT_EINVAL, "NULL host buffer");
-    if (!n) return MSBWT_OK;
-    std::vector<std::unique_lock<std::mutex>> locks;
-    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
-    return u64_path(idx, kmers, k, n, out);
-}
-
-extern "C" void msbwt_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h) {
-    if (h2d) *h2d = g_last_h2d;
-    if (d2h) *d2h = g_last_d2h;
-}
-
-extern "C" int msbwt_host_pack_threads(void) { return host_threads_available(); }
-
-extern "C" int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, const uint64_t *offsets, uint64_t n,
-                                 uint64_t *out) {
-    g_last_error.clear();
-    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
-    if (!n) return MSBWT_OK;
-    if (!out || !offsets) return fail(MSBWT_EINVAL, "NULL host buffer");
-    for (uint64_t i = 0; i < n; i++)
-        if (offsets[i + 1] < offsets[i]) return fail(MSBWT_EINVAL, "offsets must be non-decreasing");
-    if (offsets[n] > offsets[0] && !syms) return fail(MSBWT_EINVAL, "NULL host buffer");
-    const size_t ndev = idx->reps.size();
-
-    std::vector<std::unique_lock<std::mutex>> locks;
-    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
-    // A batch whose k-mers all have the same length -- what `count_kmers(&[Vec<u8>])` is called with in a k-mer
-    // counting loop -- is the fixed-k batch laid out contiguously: it takes the packed / table-seeded route.
-    {
-        const uint64_t k0 = offsets[1] - offsets[0];
-        bool uniform = k0 > 0 && k0 <= 0xFFFFFFFFull;
-        for (uint64_t i = 1; uniform && i < n; i++) uniform = offsets[i + 1] - offsets[i] == k0;
-        if (uniform) {
-            g_last_h2d = g_last_d2h = 0;
-            const uint8_t *base = syms + offsets[0];
-            return use_host_pack((uint32_t)k0, n) ? fixed_packed_path(idx, base, (uint32_t)k0, n, out)
-                                                  : fixed_bytes_path(idx, base, (uint32_t)k0, n, out);
-        }
-    }
-    for (auto &rep : idx->reps) {
-        DeviceGuard guard(rep->device);
-        CU_TRY(cudaMemsetAsync(rep->d_status, 0, kLanes * sizeof(uint32_t), rep->lane[0].stream));
-        CU_TRY(cudaStreamSynchronize(rep->lane[0].stream));
-    }
-    // per device: walk its slice in chunks bounded in both queries and symbol bytes
-    std::vector<uint64_t> cursor(ndev);
-    std::vector<uint64_t> round(ndev, 0);
-    for (size_t d = 0; d < ndev; d++) cursor[d] = slice_for(n, d, ndev).begin;
-    for (bool any = true; any;) {
-        any = false;
-        for (size_t d = 0; d < ndev; d++) {
-            const Slice sl = slice_for(n, d, ndev);
-            uint64_t b = cursor[d];
-            if (b >= sl.end) continue;
-            any = true;
-            uint64_t e = std::min(sl.end, b + kChunkQueries);
-            if (offsets[e] - offsets[b] > kChunkBytes) {
-                // largest e with offsets[e]-offsets[b] <= kChunkBytes, at least one query
-                const uint64_t *hi = std::upper_bound(offsets + b, offsets + e + 1, offsets[b] + kChunkBytes);
-                e = std::max<uint64_t>(b + 1, (uint64_t)(hi - offsets) - 1);
-            }
-            const uint64_t m = e - b, nbytes = offsets[e] - offsets[b];
-            Replica &rep = *idx->reps[d];
-            DeviceGuard guard(rep.device);
-            Lane &ln = rep.lane[round[d] & 1];
-            CU_TRY(cudaStreamSynchronize(ln.stream));  // buffers may be regrown below
-            CU_TRY(ln.in_a.reserve(std::max<uint64_t>(1, nbytes)));
-            CU_TRY(ln.in_b.reserve((m + 1) * sizeof(uint64_t)));
-            CU_TRY(ln.out_a.reserve(m * sizeof(uint64_t)));
-            if (nbytes) CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + offsets[b], nbytes, cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(cudaMemcpyAsync(ln.in_b.p, offsets + b, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
-            // the kernel indexes syms with absolute offsets: bias the base pointer instead of rewriting them
-            const uint8_t *biased = ln.in_a.as<uint8_t>() - offsets[b];
-            CU_TRY(launch_count_bytes(rep.device, rep.view, biased, ln.in_b.as<uint64_t>(), m, ln.out_a.as<uint64_t>(),
-                                      rep.d_status + (round[d] & 1), ln.stream, &g_call_launches));
-            flush_launches();
-            CU_TRY(cudaMemcpyAsync(out + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-            cursor[d] = e;
-            round[d]++;
-        }
-    }
-    for (auto &rep : idx->reps) {
-        DeviceGuard guard(rep->device);
-        for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
-        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, kLanes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    }
-    return check_status_flags(idx, "count_kmers");
-}
-
-extern "C" int msbwt_constrain_ranges(const msbwt_index *idx, const uint8_t *sym, const uint64_t *l,
-                                      const uint64_t *h, uint64_t n, uint64_t *out_l, uint64_t *out_h) {
-    g_last_error.clear();
-    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
-    if (!n) return MSBWT_OK;
-    if (!sym || !l || !h || !out_l || !out_h) return fail(MSBWT_EINVAL, "NULL host buffer");
-    const size_t ndev = idx->reps.size();
-    const uint64_t chunk = kChunkQueries;
-
-    std::vector<std::unique_lock<std::mutex>> locks;
-    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
-
-    // validation first (the reference's constrain_range is unchecked; we refuse bad input
-    // before any output is written)
-    for (uint64_t i = 0; i < n; i++)
-        if (sym[i] >= kAlphabet || l[i] > h[i] || h[i] > idx->total)
-            return fail(MSBWT_EINVAL, "constrain_ranges: item " + std::to_string(i) + " has sym >= 6, l > h or h > total_size");
-
-    uint64_t max_chunks = 0;
-    for (size_t d = 0; d < ndev; d++) {
-        Replica &rep = *idx->reps[d];
-        DeviceGuard guard(rep.device);
-        const Slice sl = slice_for(n, d, ndev);
-        const uint64_t len = sl.end - sl.begin, c = std::max<uint64_t>(1, std::min(chunk, len));
-        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
-        for (auto &ln : rep.lane) {
-            CU_TRY(cudaStreamSynchronize(ln.stream));
-            CU_TRY(ln.in_a.reserve(c));
-            CU_TRY(ln.in_b.reserve(c * sizeof(uint64_t)));
-            CU_TRY(ln.in_c.reserve(c * sizeof(uint64_t)));
-            CU_TRY(ln.out_a.reserve(c * sizeof(uint64_t)));
-            CU_TRY(ln.out_b.reserve(c * sizeof(uint64_t)));
-        }
-    }
-    for (uint64_t c = 0; c < max_chunks; c++) {
-        for (size_t d = 0; d < ndev; d++) {
-            Replica &rep = *idx->reps[d];
-            const Slice sl = slice_for(n, d, ndev);
-            const uint64_t b = sl.begin + c * chunk;
-            if (b >= sl.end) continue;
-            const uint64_t m = std::min(chunk, sl.end - b);
-            DeviceGuard guard(rep.device);
-            Lane &ln = rep.lane[c & 1];
-            CU_TRY(cudaMemcpyAsync(ln.in_a.p, sym + b, m, cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(cudaMemcpyAsync(ln.in_b.p, l + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(cudaMemcpyAsync(ln.in_c.p, h + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(launch_constrain_ranges(rep.device, rep.view, ln.in_a.as<uint8_t>(), ln.in_b.as<uint64_t>(),
-                                           ln.in_c.as<uint64_t>(), m, ln.out_a.as<uint64_t>(), ln.out_b.as<uint64_t>(),
-                                           ln.stream, &g_call_launches));
-            flush_launches();
-            CU_TRY(cudaMemcpyAsync(out_l + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-            CU_TRY(cudaMemcpyAsync(out_h + b, ln.out_b.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-        }
-    }
-    for (auto &rep : idx->reps) {
-        DeviceGuard guard(rep->device);
-        for (auto &ln : rep->lane) CU_TRY(cudaStreamSynchronize(ln.stream));
-    }
     return MSBWT_OK;
 }
 
@@ -1338,133 +884,6 @@ extern "C" int msbwt_constrain_ranges_fanout_device(const msbwt_index *idx, int 
     CU_TRY(launch_constrain_fanout(rep.device, rep.view, d_l, d_h, n, d_out_l, d_out_h, (cudaStream_t)stream, &g_call_launches));
     flush_launches();
     return MSBWT_OK;
-}
-
-extern "C" int msbwt_constrain_ranges_fanout(const msbwt_index *idx, const uint64_t *l, const uint64_t *h, uint64_t n,
-                                             uint64_t *out_l, uint64_t *out_h) {
-    g_last_error.clear();
-    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
-    if (!n) return MSBWT_OK;
-    if (!l || !h || !out_l || !out_h) return fail(MSBWT_EINVAL, "NULL host buffer");
-    const size_t ndev = idx->reps.size();
-    const uint64_t chunk = kChunkQueries;
-    std::vector<std::unique_lock<std::mutex>> locks;
-    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
-    for (uint64_t i = 0; i < n; i++)
-        if (l[i] > h[i] || h[i] > idx->total)
-            return fail(MSBWT_EINVAL, "constrain_ranges_fanout: item " + std::to_string(i) + " has l > h or h > total_size");
-    uint64_t max_chunks = 0;
-    for (size_t d = 0; d < ndev; d++) {
-        Replica &rep = *idx->reps[d];
-        DeviceGuard guard(rep.device);
-        const Slice sl = slice_for(n, d, ndev);
-        const uint64_t len = sl.end - sl.begin, c = std::max<uint64_t>(1, std::min(chunk, len));
-        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
-        for (int li = 0; li < 2; li++) {
-            Lane &ln = rep.lane[li];
-            CU_TRY(cudaStreamSynchronize(ln.stream));
-            CU_TRY(ln.in_b.reserve(c * sizeof(uint64_t)));
-            CU_TRY(ln.in_c.reserve(c * sizeof(uint64_t)));
-            CU_TRY(ln.out_a.reserve(4 * c * sizeof(uint64_t)));
-            CU_TRY(ln.out_b.reserve(4 * c * sizeof(uint64_t)));
-        }
-    }
-    for (uint64_t c = 0; c < max_chunks; c++) {
-        for (size_t d = 0; d < ndev; d++) {
-            Replica &rep = *idx->reps[d];
-            const Slice sl = slice_for(n, d, ndev);
-            const uint64_t b = sl.begin + c * chunk;
-            if (b >= sl.end) continue;
-            const uint64_t m = std::min(chunk, sl.end - b);
-            DeviceGuard guard(rep.device);
-            Lane &ln = rep.lane[c & 1];
-            CU_TRY(cudaMemcpyAsync(ln.in_b.p, l + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(cudaMemcpyAsync(ln.in_c.p, h + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(launch_constrain_fanout(rep.device, rep.view, ln.in_b.as<uint64_t>(), ln.in_c.as<uint64_t>(), m,
-                                           ln.out_a.as<uint64_t>(), ln.out_b.as<uint64_t>(), ln.stream, &g_call_launches));
-            flush_launches();
-            CU_TRY(cudaMemcpyAsync(out_l + 4 * b, ln.out_a.p, 4 * m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-            CU_TRY(cudaMemcpyAsync(out_h + 4 * b, ln.out_b.p, 4 * m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-        }
-    }
-    for (auto &rep : idx->reps) {
-        DeviceGuard guard(rep->device);
-        for (int li = 0; li < 2; li++) CU_TRY(cudaStreamSynchronize(rep->lane[li].stream));
-    }
-    return MSBWT_OK;
-}
-
-extern "C" int msbwt_count_read_kmers(const msbwt_index *idx, const uint8_t *reads, uint32_t read_len, uint64_t n_reads,
-                                      uint32_t k, uint32_t strands, uint64_t *out) {
-    g_last_error.clear();
-    if (!idx || idx->reps.empty()) return fail(MSBWT_EINVAL, "bad handle");
-    if (!k || k > read_len) return fail(MSBWT_EINVAL, "count_read_kmers: k must be in 1..read_len");
-    if (strands != 1 && strands != 2) return fail(MSBWT_EINVAL, "count_read_kmers: strands must be 1 or 2");
-    if (!n_reads) return MSBWT_OK;
-    if (!reads || !out) return fail(MSBWT_EINVAL, "NULL host buffer");
-    const uint64_t windows = (uint64_t)read_len - k + 1, per_read_q = windows * strands;
-    const size_t ndev = idx->reps.size();
-    std::vector<std::unique_lock<std::mutex>> locks;
-    for (auto &rep : idx->reps) locks.emplace_back(rep->mu);
-    // symbols are validated where they are packed (count_kmer's own check, src/msbwt_core.rs:127): the pack
-    // kernel flags any symbol >= 6 and the call then returns EINVAL
-    const uint64_t chunk = std::max<uint64_t>(1, 4 * kChunkQueries / per_read_q);  // reads per chunk
-    uint64_t max_chunks = 0;
-    for (size_t d = 0; d < ndev; d++) {
-        Replica &rep = *idx->reps[d];
-        DeviceGuard guard(rep.device);
-        const Slice sl = slice_for(n_reads, d, ndev);
-        const uint64_t len = sl.end - sl.begin, c = std::max<uint64_t>(1, std::min(chunk, len));
-        max_chunks = std::max(max_chunks, (len + chunk - 1) / chunk);
-        CU_TRY(cudaMemset(rep.d_status, 0, kLanes * sizeof(uint32_t)));
-        for (int li = 0; li < 2; li++) {
-            Lane &ln = rep.lane[li];
-            CU_TRY(cudaStreamSynchronize(ln.stream));
-            CU_TRY(ln.in_a.reserve(c * read_len));
-            CU_TRY(ln.in_b.reserve(c * per_read_q * k + 16));
-            CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, c * per_read_q).total() * sizeof(uint64_t)));
-            CU_TRY(ln.out_a.reserve(c * per_read_q * sizeof(uint64_t)));
-            CU_TRY(ln.out_b.reserve(c * windows * sizeof(uint64_t)));
-        }
-    }
-    uint64_t h2d = 0, d2h = 0;
-    for (uint64_t c = 0; c < max_chunks; c++) {
-        for (size_t d = 0; d < ndev; d++) {
-            Replica &rep = *idx->reps[d];
-            const Slice sl = slice_for(n_reads, d, ndev);
-            const uint64_t b = sl.begin + c * chunk;
-            if (b >= sl.end) continue;
-            const uint64_t m = std::min(chunk, sl.end - b), nq = m * per_read_q;
-            DeviceGuard guard(rep.device);
-            Lane &ln = rep.lane[c & 1];
-            uint32_t *flag = rep.d_status + (c & 1);
-            CU_TRY(cudaMemcpyAsync(ln.in_a.p, reads + b * read_len, m * read_len, cudaMemcpyHostToDevice, ln.stream));
-            CU_TRY(launch_expand_read_kmers(rep.device, ln.in_a.as<uint8_t>(), read_len, m, k, strands, ln.in_b.as<uint8_t>(), ln.stream));
-            g_launches++;
-            CU_TRY(launch_pack_seed(rep.view, ln.in_b.as<uint8_t>(), k, nq, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(), flag, ln.stream));
-            g_launches++;
-            CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, nq, ln.out_a.as<uint64_t>(),
-                                       ln.stream, &g_call_launches));
-            flush_launches();
-            const uint64_t *res = ln.out_a.as<uint64_t>();
-            if (strands == 2) {
-                CU_TRY(launch_sum_strands(rep.device, ln.out_a.as<uint64_t>(), m * windows, ln.out_b.as<uint64_t>(), ln.stream));
-                g_launches++;
-                res = ln.out_b.as<uint64_t>();
-            }
-            CU_TRY(cudaMemcpyAsync(out + b * windows, res, m * windows * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-            h2d += m * read_len;
-            d2h += m * windows * sizeof(uint64_t);
-        }
-    }
-    for (auto &rep : idx->reps) {
-        DeviceGuard guard(rep->device);
-        for (int li = 0; li < 2; li++) CU_TRY(cudaStreamSynchronize(rep->lane[li].stream));
-        CU_TRY(cudaMemcpy(rep->h_status, rep->d_status, kLanes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    }
-    g_last_h2d = h2d;
-    g_last_d2h = d2h;
-    return check_status_flags(idx, "count_read_kmers");
 }
 
 // ================================================================ construction of the BWT itself

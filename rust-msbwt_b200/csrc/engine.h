@@ -86,21 +86,18 @@ struct OctImage {
     uint64_t overflow_occurrences = 0;  // positions whose line overflowed (answered through the quad image)
 };
 uint64_t oct_image_bytes(uint64_t total, int shift);
-// `ix` must carry the one-step blocks and the quad image, N < 2^32 with one superblock; `d_codes4` = the
-// quad builder's keep_codes, OWNED by this call (freed as soon as the kOctSyms-symbol codes exist); `d_codes2`
-// = the pair builder's keep_codes (borrowed).
-// `requested_shift` 0 = automatic (layout.h).  When even the coarsest buckets exceed `max_bytes` nothing is
-// built (img.lines stays null) and MSBWT_OK is returned.
-int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes4, const uint8_t *d_codes2,
-                              int requested_shift, uint64_t max_bytes, OctImage &img, std::string &why, int *launches
-#ifdef MSBWT_FINAL_STEP
-                              , uint32_t **keep_codes10 = nullptr  // receives the per-position codes (caller frees) instead of freeing them
-#endif
-                              );
+// stage 1 (needs the quad image): the kOctSyms-symbol code of every position, `1 << kOctCodeBits | code` or 0 when one of
+// the symbols is not ACGT (4 bytes per position, device memory the caller frees).  `d_codes4` = the quad builder's
+// keep_codes, OWNED by this call; `d_codes2` = the pair builder's keep_codes (borrowed).  N < 2^32 only.
+int build_oct_codes_on_device(int device, const IndexView &ix, uint16_t *d_codes4, const uint8_t *d_codes2,
+                              uint32_t **d_codes10, std::string &why, int *launches);
+// stage 2 (needs only the one-step blocks and the codes): the lines.  `requested_shift` 0 = automatic (layout.h).
+// When even the coarsest buckets exceed `max_bytes` nothing is built (img.lines stays null) and MSBWT_OK is returned.
+int build_oct_lines_on_device(int device, const IndexView &ix, const uint32_t *d_codes10, int requested_shift,
+                              uint64_t max_bytes, OctImage &img, std::string &why, int *launches);
 void free_oct_image(OctImage &img);
 
-#ifdef MSBWT_FINAL_STEP
-// ---- fin_builder.cu (EXPERIMENTAL): quad image + the oct builder's 10-symbol codes -> final-step lines (layout.h) ----
+// ---- fin_builder.cu: the oct builder's 10-symbol codes -> final-step lines (layout.h) ----
 struct FinImage {
     uint4 *lines = nullptr;  // nlines * 128 B
     uint64_t nlines = 0;     // ((N >> shift) + 1) << lb
@@ -109,11 +106,14 @@ struct FinImage {
     uint64_t overflow_lines = 0;  // lines whose groups did not fit
 };
 uint64_t fin_image_bytes(uint64_t total, int shift, int lb);
-// `d_codes10` = the oct builder's per-position codes (valid bit 1 << 20), OWNED by this call
-int build_fin_image_on_device(int device, const IndexView &ix, uint32_t *d_codes10, int shift, int lb, FinImage &img,
+// stage 1 (needs the quad image and the one-step blocks): the kFinSyms-symbol code of every position,
+// `1 << kFinCodeBits | code` or 0 (8 bytes per position, device memory OWNED by stage 2)
+int build_fin_codes_on_device(int device, const IndexView &ix, const uint32_t *d_codes10, uint64_t **d_codes20,
+                              std::string &why, int *launches);
+// stage 2 (needs only the codes, which it frees as soon as the run records exist): the lines
+int build_fin_lines_on_device(int device, uint64_t total, uint64_t *d_codes20, int shift, int lb, FinImage &img,
                               std::string &why, int *launches);
 void free_fin_image(FinImage &img);
-#endif
 
 // ---- bwt_build.cu: equal-length reads (device) -> RLE bytes of their multi-string BWT (device) ----
 int build_rle_bwt_on_device(const uint8_t *d_reads, uint64_t n_reads, uint32_t read_len, uint8_t **d_rle_out,
@@ -173,6 +173,9 @@ cudaError_t launch_seed_u64(const IndexView &ix, const uint64_t *d_kmers, uint32
 // quad_kernels.cu: live list A over the quad (and oct) image
 cudaError_t launch_count_quad(int device, const IndexView &ix, const uint64_t *d_packed, const PackedLayout &lay,
                               uint32_t k, uint64_t *d_out, cudaStream_t st);
+// stats_kernels.cu: live list A over the oct image with the counting instantiation -- d_stats[8] (oct_kernel.cuh)
+cudaError_t launch_count_oct_stats(int device, const IndexView &ix, const uint64_t *d_packed, uint32_t k, uint64_t n,
+                                   uint64_t *d_out, unsigned long long *d_stats, cudaStream_t st);
 // the fused path (oct image, k <= 32, 16-byte aligned symbol bytes): one kernel from symbol bytes to counts
 bool fused_path_applies(const IndexView &ix, const uint8_t *d_syms, uint32_t k);
 uint64_t fused_scratch_bytes(uint64_t n);
@@ -194,6 +197,7 @@ cudaError_t launch_constrain_fanout(int device, const IndexView &ix, const uint6
 cudaError_t launch_expand_read_kmers(int device, const uint8_t *d_reads, uint32_t read_len, uint64_t n_reads, uint32_t k,
                                      uint32_t strands, uint8_t *d_syms, cudaStream_t st);
 cudaError_t launch_sum_strands(int device, const uint64_t *d_per_query, uint64_t n_windows, uint64_t *d_out, cudaStream_t st);
+cudaError_t launch_narrow_counts(int device, const uint64_t *d_in, uint64_t n, uint32_t *d_out, cudaStream_t st);
 cudaError_t launch_gather(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,
                           uint64_t n_gathers, uint64_t seed, uint64_t *d_sink, cudaStream_t st);
 

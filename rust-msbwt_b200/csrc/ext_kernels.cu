@@ -87,6 +87,20 @@ sum_strands_kernel(const uint64_t *__restrict__ per_query, uint64_t n_windows, u
     }
 }
 
+// counts of an index below 2^32 symbols fit 32 bits: halves the bytes of the copy back to the host
+__global__ void __launch_bounds__(256)
+narrow_counts_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out) {
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) out[i] = (uint32_t)in[i];
+}
+
+cudaError_t launch_narrow_counts(int device, const uint64_t *d_in, uint64_t n, uint32_t *d_out, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count(device) * 16);
+    narrow_counts_kernel<<<grid, 256, 0, st>>>(d_in, n, d_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_constrain_fanout(int device, const IndexView &ix, const uint64_t *d_l, const uint64_t *d_h,
                                     uint64_t n, uint64_t *d_out_l, uint64_t *d_out_h, cudaStream_t st, int *launches) {
     for (uint64_t q0 = 0; q0 < n; q0 += kMaxPerLaunch) {

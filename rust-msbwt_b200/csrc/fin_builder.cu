@@ -13,8 +13,9 @@
 //   3. sort  : records by key (CUB radix sort, 56 bits): the runs of a line, and inside it of a code, are contiguous.
 //   4. lines : the first record of every line writes the line: groups `(tag << 4) | nruns` + run words, word 0 =
 //              words in use, or kFinOverflow when they do not fit (the kernel then takes the oct steps).
-#ifdef MSBWT_FINAL_STEP
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -157,47 +158,84 @@ struct Scratch {
 
 uint64_t fin_image_bytes(uint64_t total, int shift, int lb) { return (((total >> shift) + 1) << lb) * (uint64_t)kFinLineBytes; }
 
-int build_fin_image_on_device(int device, const IndexView &ix, uint32_t *d_codes10, int shift, int lb, FinImage &img,
+static void fin_trace(const char *what) {
+    static const bool on = getenv("MSBWT_TRACE") != nullptr;
+    if (on) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        fprintf(stderr, "[msbwt] final-step image: %s (%.1f GB of device memory free)\n", what, (double)free_b / 1e9);
+    }
+}
+
+// Stage 1 (needs the quad image and the one-step blocks): code20 of every position, 8 bytes each
+int build_fin_codes_on_device(int device, const IndexView &ix, const uint32_t *d_codes10, uint64_t **d_codes20_out,
                               std::string &why, int *launches) {
-    struct Owned { uint32_t *p; ~Owned() { if (p) cudaFree(p); } } codes10{d_codes10};
+    *d_codes20_out = nullptr;
     if (!ix.quad || !d_codes10 || index_is_wide(ix)) { why = "final-step image: needs the quad image, the 10-symbol codes and 32-bit positions"; return MSBWT_EINVAL; }
-    if (shift < 8 || shift > 16 || lb < kFinCodeBits - kFinTagBits || lb > 20) { why = "final-step image: bucket shift 8..16, lines per bucket 2^12..2^20"; return MSBWT_EINVAL; }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((ix.total + 255) / 256, (uint64_t)sms * 32));
+    uint64_t *d_codes20 = nullptr;
+    F_TRY(cudaMalloc((void **)&d_codes20, std::max<uint64_t>(1, ix.total) * sizeof(uint64_t)));
+    fin_trace("codes");
+    fin_code20_kernel<<<grid, 256>>>(ix, d_codes10, d_codes20);
+    if (launches) (*launches)++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(d_codes20);
+        why = std::string("final-step image: code kernel: ") + cudaGetErrorString(e);
+        return MSBWT_ECUDA;
+    }
+    *d_codes20_out = d_codes20;
+    return MSBWT_OK;
+}
+
+// Stage 2 (needs nothing but the codes, which it OWNS and frees as soon as the run records exist): the lines
+int build_fin_lines_on_device(int device, uint64_t total, uint64_t *d_codes20_in, int shift, int lb, FinImage &img,
+                              std::string &why, int *launches) {
+    struct Owned { uint64_t *p; ~Owned() { if (p) cudaFree(p); } } codes20{d_codes20_in};
+    if (!d_codes20_in) { why = "final-step image: no position codes"; return MSBWT_EINVAL; }
+    if (shift < 8 || shift > 16 || lb < kFinCodeBits - kFinTagBits || lb > 20) { why = "final-step image: bucket shift 8..16, lines per bucket 2^12..2^20"; return MSBWT_EINVAL; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * 32));
+    const uint64_t *d_codes20 = codes20.p;
 
     Scratch tmp;
-    uint64_t *d_codes20 = nullptr;
     unsigned long long *d_stat = nullptr;  // [0] records, [1] emit cursor, [2] overflowed lines
-    F_TRY(tmp.alloc(&d_codes20, ix.total));
     F_TRY(tmp.alloc(&d_stat, 3));
     F_TRY(cudaMemsetAsync(d_stat, 0, 3 * sizeof(unsigned long long)));
-    fin_code20_kernel<<<grid, 256>>>(ix, d_codes10, d_codes20);
+    fin_count_runs_kernel<<<grid, 256>>>(d_codes20, total, (uint32_t)shift, d_stat);
     F_TRY(cudaGetLastError());
-    fin_count_runs_kernel<<<grid, 256>>>(d_codes20, ix.total, (uint32_t)shift, d_stat);
-    F_TRY(cudaGetLastError());
-    if (launches) (*launches) += 2;
+    if (launches) (*launches)++;
     unsigned long long n_runs = 0;
     F_TRY(cudaMemcpy(&n_runs, d_stat, sizeof(n_runs), cudaMemcpyDeviceToHost));
-    cudaFree(codes10.p);
-    codes10.p = nullptr;
 
-    const uint64_t nlines = ((ix.total >> shift) + 1) << lb;
+    const uint64_t nlines = ((total >> shift) + 1) << lb;
     img.shift = shift;
     img.lb = lb;
     img.nlines = nlines;
     img.runs = n_runs;
+    uint64_t *k0 = nullptr, *k1 = nullptr;
+    uint32_t *v0 = nullptr, *v1 = nullptr;
+    if (n_runs) {
+        fin_trace("run records");
+        F_TRY(tmp.alloc(&k0, n_runs));
+        F_TRY(tmp.alloc(&v0, n_runs));
+        fin_emit_kernel<<<grid, 256>>>(d_codes20, total, (uint32_t)shift, (uint32_t)lb, k0, v0, d_stat + 1);
+        F_TRY(cudaGetLastError());
+        F_TRY(cudaDeviceSynchronize());
+        if (launches) (*launches)++;
+    }
+    cudaFree(codes20.p);  // the records carry everything from here on
+    codes20.p = nullptr;
     F_TRY(cudaMalloc((void **)&img.lines, nlines * kFinLineBytes));
     F_TRY(cudaMemsetAsync(img.lines, 0, nlines * kFinLineBytes));
     if (n_runs) {
-        uint64_t *k0 = nullptr, *k1 = nullptr;
-        uint32_t *v0 = nullptr, *v1 = nullptr;
-        F_TRY(tmp.alloc(&k0, n_runs));
+        fin_trace("sort");
         F_TRY(tmp.alloc(&k1, n_runs));
-        F_TRY(tmp.alloc(&v0, n_runs));
         F_TRY(tmp.alloc(&v1, n_runs));
-        fin_emit_kernel<<<grid, 256>>>(d_codes20, ix.total, (uint32_t)shift, (uint32_t)lb, k0, v0, d_stat + 1);
-        F_TRY(cudaGetLastError());
         cub::DoubleBuffer<uint64_t> keys(k0, k1);
         cub::DoubleBuffer<uint32_t> vals(v0, v1);
         size_t temp_bytes = 0;
@@ -206,14 +244,16 @@ int build_fin_image_on_device(int device, const IndexView &ix, uint32_t *d_codes
         void *d_temp = nullptr;
         F_TRY(tmp.alloc((uint8_t **)&d_temp, temp_bytes));
         F_TRY(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, keys, vals, (int64_t)n_runs, 0, end_bit));
+        fin_trace("lines");
         fin_lines_kernel<<<grid, 256>>>(keys.Current(), vals.Current(), n_runs, reinterpret_cast<uint32_t *>(img.lines), d_stat + 2);
         F_TRY(cudaGetLastError());
-        if (launches) (*launches) += 3;
+        if (launches) (*launches) += 2;
     }
     unsigned long long over = 0;
     F_TRY(cudaMemcpy(&over, d_stat + 2, sizeof(over), cudaMemcpyDeviceToHost));
     img.overflow_lines = over;
     F_TRY(cudaDeviceSynchronize());
+    fin_trace("done");
     return MSBWT_OK;
 }
 
@@ -223,4 +263,3 @@ void free_fin_image(FinImage &img) {
 }
 
 }  // namespace msbwt
-#endif  // MSBWT_FINAL_STEP

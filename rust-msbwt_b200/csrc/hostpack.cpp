@@ -15,6 +15,7 @@
 #include <immintrin.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -125,15 +126,20 @@ void host_pack_range(const uint8_t *syms, uint32_t k, uint64_t n_total, uint64_t
 
 // ---------------------------------------------------------------- worker pool
 
-// Workers sleep on a condition variable between sessions; inside a session (one batch call) they
-// spin on the job generation so that handing them a chunk costs about a microsecond, not a wake-up.
+// Workers sleep on a condition variable between sessions; inside a session (one batch call) they spin briefly
+// on the job generation -- handing them a chunk then costs about a microsecond, not a wake-up -- and fall back to
+// a timed sleep when no job shows up for a while (the issuing thread is waiting for the copy engine, or the host
+// has fewer free cores than the pool has threads: spinning workers would then starve the packers that have work).
 struct HostPool::Impl {
     std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cv_go;
+    std::mutex job_mu;
+    std::condition_variable cv_job;
     std::atomic<const std::function<void(int, int)> *> job{nullptr};
     std::atomic<uint64_t> generation{0};
     std::atomic<int> pending{0};
+    std::atomic<int> sleepers{0};
     std::atomic<bool> in_session{false};
     bool stop = false;
     int nthreads = 1;
@@ -146,12 +152,24 @@ struct HostPool::Impl {
                 cv_go.wait(lk, [&] { return stop || in_session.load(std::memory_order_acquire); });
                 if (stop) return;
             }
+            uint32_t idle = 0;
             while (in_session.load(std::memory_order_acquire)) {
                 const uint64_t g = generation.load(std::memory_order_acquire);
                 if (g == seen) {
-                    _mm_pause();
+                    if (++idle < 20000u) {
+                        _mm_pause();
+                        continue;
+                    }
+                    // nothing for ~0.1 ms: sleep until the next job (or at most 1 ms, to notice the session's end)
+                    std::unique_lock<std::mutex> lk(job_mu);
+                    sleepers.fetch_add(1, std::memory_order_acq_rel);
+                    cv_job.wait_for(lk, std::chrono::milliseconds(1), [&] {
+                        return generation.load(std::memory_order_acquire) != seen || !in_session.load(std::memory_order_acquire);
+                    });
+                    sleepers.fetch_sub(1, std::memory_order_acq_rel);
                     continue;
                 }
+                idle = 0;
                 seen = g;
                 (*job.load(std::memory_order_acquire))(tid, nthreads);
                 pending.fetch_sub(1, std::memory_order_acq_rel);
@@ -213,6 +231,10 @@ void HostPool::run(const std::function<void(int, int)> &fn) {
     impl_->job.store(&fn, std::memory_order_release);
     impl_->pending.store(impl_->nthreads - 1, std::memory_order_release);
     impl_->generation.fetch_add(1, std::memory_order_acq_rel);
+    if (impl_->sleepers.load(std::memory_order_acquire) > 0) {
+        std::lock_guard<std::mutex> lk(impl_->job_mu);
+        impl_->cv_job.notify_all();
+    }
     fn(0, impl_->nthreads);  // the caller is worker 0
     while (impl_->pending.load(std::memory_order_acquire) != 0) _mm_pause();
 }

@@ -668,14 +668,13 @@ cudaError_t launch_pack_seed(const IndexView &ix, const uint8_t *d_syms, uint32_
     const unsigned blocks = (unsigned)((n + 255) / 256);
     const size_t smem = k <= kPackSmemMaxK ? 256u * (size_t)k + 64u : 0u;
     const SeedPlan plan = make_seed_plan(ix, k);
-    // fixed-k instantiations: 31 always (the headline query, validated on the GPU); the other lengths of the k-sweep
-    // (BASELINE.json configs[3]) only with MSBWT_PACK_FIXED_K=all until they have been measured and parity-tested there
-    static const bool more_k = [] { const char *e = getenv("MSBWT_PACK_FIXED_K"); return e && std::string(e) == "all"; }();
+    // fixed-k instantiations (every shift, mask and word count a constant): measured on B200 against the runtime-k
+    // build on 10 M queries each (profiles/r2a_pack_fixed_k.json, equal checksums): k = 31 0.250 -> 0.150 ms,
+    // k = 15 0.188 -> 0.131 ms; k = 63 no difference and k = 101 slower (0.336 -> 0.406 ms: three fully unrolled
+    // words cost more registers than the loop), so those two stay on the runtime-k build
     if (is_wide(ix)) pack_seed_kernel<true, 0><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
     else if (k == 31) pack_seed_kernel<false, 31><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
-    else if (more_k && k == 15) pack_seed_kernel<false, 15><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
-    else if (more_k && k == 63) pack_seed_kernel<false, 63><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
-    else if (more_k && k == 101) pack_seed_kernel<false, 101><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
+    else if (k == 15) pack_seed_kernel<false, 15><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
     else pack_seed_kernel<false, 0><<<blocks, 256, smem, st>>>(ix, d_syms, k, plan, lay, d_packed, d_out, d_status);
     return cudaGetLastError();
 }
@@ -718,7 +717,7 @@ cudaError_t launch_count_packed(int device, const IndexView &ix, int lanes, cons
     if (n > kMaxPerLaunch) return cudaErrorInvalidValue;
     const PackedLayout lay = packed_layout(ix, k, n);
     cudaError_t e;
-    if (ix.quad)
+    if (ix.quad || ix.oct)  // (the oct kernel works with or without the quad image beside it)
         e = launch_count_quad(device, ix, d_packed, lay, k, d_out, st);
     else if (ix.pair)
         e = is_wide(ix) ? launch_count_pair_t<true>(device, ix, d_packed, lay, k, d_out, st)

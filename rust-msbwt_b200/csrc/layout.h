@@ -225,11 +225,9 @@ struct IndexView {
     uint32_t n_super4;       // quad superblocks (2^sb_shift4 sectors each)
     uint32_t sb_shift4;
     uint32_t table_s;        // 0 = no table
-#ifdef MSBWT_FINAL_STEP
     const uint4 *fin;        // final-step lines (8 uint4 each), or nullptr
     uint32_t fin_shift;      // b: log2 of the bucket size
     uint32_t fin_lb;         // log2 of the lines per bucket
-#endif
 };
 
 }  // namespace msbwt

@@ -6,6 +6,7 @@
 // RleBWT::constrain_range calls (src/rle_bwt.rs:202-287) -- kOctSyms of them since the image holds ten
 // symbols per line; layout.h states the identity.
 //
+// Two stages, so that the caller can drop the (large) quad image between them:
 //   1. codes  : one thread per BWT position j with a valid quad code a: j4 = LF^4(j) = rank4(a, j) through the
 //               quad image (one sector), b = code4(j4) (one random read), j8 = rank4(b, j4), c = the pair code
 //               (two symbols) at j8; code(j) = a * 4^6 + b * 4^2 + c when all three are valid.
@@ -149,15 +150,39 @@ uint64_t oct_image_bytes(uint64_t total, int shift) {
     return (uint64_t)kOctCodes * ((total >> shift) + 1) * kOctLineBytes;
 }
 
-int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes4, const uint8_t *d_codes2,
-                              int requested_shift, uint64_t max_bytes, OctImage &img, std::string &why, int *launches
-#ifdef MSBWT_FINAL_STEP
-                              , uint32_t **keep_codes10
-#endif
-                              ) {
+// Stage 1: the kOctSyms-symbol code of every position (4 bytes each; the caller frees them).  `ix` must carry the
+// one-step blocks and the quad image; `d_codes4` (the quad builder's keep_codes) is OWNED by this call and freed as
+// soon as the codes exist; `d_codes2` (the pair builder's keep_codes) is borrowed.
+int build_oct_codes_on_device(int device, const IndexView &ix, uint16_t *d_codes4, const uint8_t *d_codes2,
+                              uint32_t **d_codes10, std::string &why, int *launches) {
     struct Owned { uint16_t *p; ~Owned() { if (p) cudaFree(p); } } codes4{d_codes4};
+    *d_codes10 = nullptr;
     if (!ix.quad || !d_codes4 || !d_codes2) { why = "oct image: needs the quad image, its codes and the pair codes"; return MSBWT_EINVAL; }
     if (index_is_wide(ix)) { why = "oct image: only for indexes with 32-bit positions (N < 2^32, one superblock)"; return MSBWT_EINVAL; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((ix.total + 255) / 256, (uint64_t)sms * 32));
+    uint32_t *d_codes8 = nullptr;
+    O_TRY(cudaMalloc((void **)&d_codes8, std::max<uint64_t>(1, ix.total) * sizeof(uint32_t)));
+    oct_code8_kernel<<<grid, 256>>>(ix, d_codes4, d_codes2, d_codes8);
+    if (launches) (*launches)++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(d_codes8);
+        why = std::string("oct image: code kernel: ") + cudaGetErrorString(e);
+        return MSBWT_ECUDA;
+    }
+    *d_codes10 = d_codes8;
+    return MSBWT_OK;
+}
+
+// Stage 2: the lines, from the codes alone (plus the one-step blocks for Cm[c]): the quad image is not read, so
+// the caller may already have dropped it.  `requested_shift` 0 = automatic (layout.h).  When even the coarsest
+// buckets exceed `max_bytes` nothing is built (img.lines stays null) and MSBWT_OK is returned.
+int build_oct_lines_on_device(int device, const IndexView &ix, const uint32_t *d_codes8, int requested_shift,
+                              uint64_t max_bytes, OctImage &img, std::string &why, int *launches) {
+    if (!d_codes8 || index_is_wide(ix)) { why = "oct image: needs the position codes and 32-bit positions"; return MSBWT_EINVAL; }
     if (requested_shift && (requested_shift < kOctMinShift || requested_shift > kOctMaxShift)) {
         why = "oct image: bucket shift out of range"; return MSBWT_EINVAL;
     }
@@ -166,24 +191,16 @@ int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((ix.total + 255) / 256, (uint64_t)sms * 32));
 
     Scratch tmp;
-    uint32_t *d_codes8 = nullptr;
     uint8_t *d_sym = nullptr;
     uint64_t *d_pos = nullptr;
     unsigned long long *d_stat = nullptr;  // [0] runs, [1] overflowed lines, [2] their occurrences
-    O_TRY(tmp.alloc(&d_codes8, ix.total));
     O_TRY(tmp.alloc(&d_stat, 3));
     O_TRY(cudaMemsetAsync(d_stat, 0, 3 * sizeof(unsigned long long)));
-
-    // 1. code8 per position, 2. run heads
-    oct_code8_kernel<<<grid, 256>>>(ix, d_codes4, d_codes2, d_codes8);
-    O_TRY(cudaGetLastError());
     oct_count_runs_kernel<<<grid, 256>>>(d_codes8, ix.total, d_stat);
     O_TRY(cudaGetLastError());
-    if (launches) (*launches) += 2;
+    if (launches) (*launches)++;
     unsigned long long runs = 0;
     O_TRY(cudaMemcpy(&runs, d_stat, sizeof(runs), cudaMemcpyDeviceToHost));
-    cudaFree(codes4.p);
-    codes4.p = nullptr;
     img.runs = runs;
 
     int shift = requested_shift;
@@ -195,7 +212,7 @@ int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes
             shift--;
         while (shift < kOctMaxShift && oct_image_bytes(ix.total, shift) > max_bytes) shift++;
     }
-    if (oct_image_bytes(ix.total, shift) > max_bytes) return MSBWT_OK;  // no room: img.lines stays null, the quad image serves alone
+    if (oct_image_bytes(ix.total, shift) > max_bytes) return MSBWT_OK;  // no room: img.lines stays null
     const uint64_t nbuck8 = (ix.total >> shift) + 1;
     const uint64_t nlines = (uint64_t)kOctCodes * nbuck8;
     img.nbuck8 = nbuck8;
@@ -218,13 +235,13 @@ int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes
         std::swap(cur, nxt);
     }
 
-    // 3. emit
+    // emit
     if (ix.total) {
         oct_emit_kernel<<<grid, 256>>>(d_codes8, ix.total, (uint32_t)shift, nbuck8, reinterpret_cast<uint32_t *>(img.lines));
         O_TRY(cudaGetLastError());
         if (launches) (*launches)++;
     }
-    // 4. stamp
+    // stamp
     oct_stamp_kernel<<<kOctCodes / 8, 256>>>(cur, nbuck8, reinterpret_cast<uint32_t *>(img.lines), d_stat + 1);
     O_TRY(cudaGetLastError());
     if (launches) (*launches)++;
@@ -233,12 +250,6 @@ int build_oct_image_on_device(int device, const IndexView &ix, uint16_t *d_codes
     img.overflow_lines = over[0];
     img.overflow_occurrences = over[1];
     O_TRY(cudaDeviceSynchronize());
-#ifdef MSBWT_FINAL_STEP
-    if (keep_codes10) {  // hand the codes to the final-step builder instead of freeing them with the scratch
-        tmp.ptrs.erase(std::find(tmp.ptrs.begin(), tmp.ptrs.end(), (void *)d_codes8));
-        *keep_codes10 = d_codes8;
-    }
-#endif
     return MSBWT_OK;
 }
 

@@ -90,11 +90,17 @@ __device__ __forceinline__ uint32_t staged_sector_rank(const uint4 &a, const uin
 // fetches its suffix-table entry as one more kind of step of the same loop and writes its count to out[query]
 // -- no pack kernel, no live list written and read back.  A k-mer holding a symbol outside ACGT is appended to
 // `exc` (count, then query indices) and counted afterwards by count_exceptions_kernel.
-template <bool RAW>
+// STATS = true (stats_kernels.cu, never on a timed path): the same walk also counts what it fetches -- stats[0] oct
+// lines, [1] final-step lines, [2] final-step lines that had overflowed (their query then takes the oct steps),
+// [3] quad steps, [4] distinct 128-byte lines those read, [5] one-symbol steps, [6] distinct 64-byte blocks those
+// read, [7] queries walked: the exact index traffic of the implemented algorithm on a batch, for the roofline
+// accounting of bench.py.
+constexpr int kOctStatWords = 8;
+template <bool RAW, bool STATS = false>
 __global__ void __launch_bounds__(kCountThreads, MSBWT_OCT_CTAS)
 count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, PackedLayout lay, uint32_t k,
                        uint64_t *__restrict__ out, uint32_t *__restrict__ work, const uint8_t *__restrict__ syms,
-                       uint32_t n_raw, uint32_t *__restrict__ exc) {
+                       uint32_t n_raw, uint32_t *__restrict__ exc, unsigned long long *__restrict__ stats = nullptr) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint64_t cb_smem[4];
     const CBase<false> cb = stage_cbase<false>(ix, cb_smem);
@@ -164,6 +170,18 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
 
+    uint32_t st_cnt[kOctStatWords] = {0, 0, 0, 0, 0, 0, 0, 0};  // STATS only (dead code otherwise)
+    auto flush_stats = [&]() {
+        if constexpr (STATS) {
+#pragma unroll
+            for (int i = 0; i < kOctStatWords; i++) {
+                uint32_t v = st_cnt[i];
+#pragma unroll
+                for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+                if (lane == 0 && v) atomicAdd(stats + i, (unsigned long long)v);
+            }
+        }
+    };
     bool active = false;
     bool need_table = false;  // RAW: the next step is the suffix-table lookup
     uint32_t l = 0, h = 0;
@@ -173,11 +191,9 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     int shift = 62;       // bit offset of the next symbol (2 bits) in `word`; negative: already inside `pend`
     uint32_t widx = 0;
     uint32_t forced = 0;  // symbols to take without the oct image (overflowed line / two buckets)
-#ifdef MSBWT_FINAL_STEP
     bool no_fin = false;  // this query's final-step line overflowed: its last kFinSyms symbols go through the oct steps
     const char *const fin_base = reinterpret_cast<const char *>(ix.fin);
     const uint32_t fshift = ix.fin_shift, fmask = (1u << fshift) - 1u, flb = ix.fin_lb;
-#endif
 
     // the next `nsym` symbols as one code (first consumed most significant); a step may straddle two words
     auto peek = [&](uint32_t nsym) -> uint32_t {
@@ -187,7 +203,6 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         return (uint32_t)(((word & ((1ull << avail) - 1ull)) << need) | (pend >> (64 - need)));
     };
 
-#ifdef MSBWT_FINAL_STEP
     // the next kFinSyms symbols as one 40-bit code (first consumed most significant)
     auto peek_fin = [&]() -> uint64_t {
         const int bits = kFinCodeBits, avail = shift + 2;
@@ -195,7 +210,6 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         const int need = bits - avail;
         return ((word & ((1ull << avail) - 1ull)) << need) | (pend >> (64 - need));
     };
-#endif
 
     for (;;) {
         // ---- RETIRE + REFILL (warp-uniform control)
@@ -215,10 +229,9 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                     shift = 62;
                     widx = 0;
                     forced = 0;
-#ifdef MSBWT_FINAL_STEP
                     no_fin = false;
-#endif
                     active = true;
+                    if constexpr (STATS) st_cnt[7]++;
                     if constexpr (RAW) {
                         q = (from_a ? a_base : b_base) + slot;
                         // k symbol bytes at p + slot * k -> 2 bits each, the k-mer's last symbol in the top bits
@@ -272,6 +285,7 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                     a_pos += taken;
                 }
             } else if (want == kFull) {
+                flush_stats();
                 return;  // nothing left to hand out and every lane is done
             }
         }
@@ -288,22 +302,14 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         const bool is_table = RAW && active && need_table;
         const bool live = active && !is_table && rem != 0 && l != h;
         const uint32_t bl = l >> bshift, bh = h >> bshift;
-#ifdef MSBWT_FINAL_STEP
         // exactly kFinSyms symbols left: ONE final-step line answers the count (no rank needed for the last step)
         const bool is_fin = live && fin_base != nullptr && rem == (uint32_t)kFinSyms && forced == 0u && !no_fin &&
                             (l >> fshift) == (h >> fshift);
         const uint64_t fin_mixed = is_fin ? fin_mix40(peek_fin()) : 0ull;  // (a dozen instructions: only where they are used)
         const bool want_oct = live && !is_fin && rem >= (uint32_t)kOctSyms && forced == 0u;
-#else
-        const bool want_oct = live && rem >= (uint32_t)kOctSyms && forced == 0u;
-#endif
         const bool is_oct = want_oct && bl == bh;
         if (want_oct && !is_oct) forced = (uint32_t)kOctSyms;  // symbols to take without the oct image
-#ifdef MSBWT_FINAL_STEP
-        const bool is_quad = live && !is_oct && !is_fin && rem >= 4u && (forced == 0u || forced >= 4u);
-#else
-        const bool is_quad = live && !is_oct && rem >= 4u && (forced == 0u || forced >= 4u);
-#endif
+        const bool is_quad = live && quad_base != nullptr && !is_oct && !is_fin && rem >= 4u && (forced == 0u || forced >= 4u);
         const uint32_t codem = peek((uint32_t)kOctSyms);
         const uint32_t code8 = peek(4u);
         const uint32_t sl = l / (uint32_t)kQuadSyms, sh = h / (uint32_t)kQuadSyms;
@@ -311,17 +317,17 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         const char *p0 = is_oct ? oct_base + ((size_t)codem * ix.nbuck8 + bl) * kOctLineBytes
                                 : quad_base + ((size_t)code8 * ix.nsec4 + sl) * kQuadSectorBytes;
         if (is_table) p0 = table_base + ((entry * 8u) & ~15ull);
-#ifdef MSBWT_FINAL_STEP
         if (is_fin) p0 = fin_base + ((((size_t)(l >> fshift)) << flb) | (size_t)(fin_mixed & ((1ull << flb) - 1ull))) * kFinLineBytes;
-#endif
         // low two bits: kind (1 oct, 2 quad, 3 table entry, 0 nothing); the rest (quad): byte distance from the
         // sector of l to the sector of h
-#ifdef MSBWT_FINAL_STEP
         // a final-step line is fetched like an oct line (kind 1: all eight 16-byte pieces)
         const uint32_t meta = is_table ? 3u : ((is_oct || is_fin) ? 1u : (is_quad ? (2u | ((sh - sl) * (uint32_t)kQuadSectorBytes)) : 0u));
-#else
-        const uint32_t meta = is_table ? 3u : (is_oct ? 1u : (is_quad ? (2u | ((sh - sl) * (uint32_t)kQuadSectorBytes)) : 0u));
-#endif
+        if constexpr (STATS) {
+            st_cnt[0] += is_oct;
+            st_cnt[1] += is_fin;
+            st_cnt[3] += is_quad;
+            if (is_quad) st_cnt[4] += (((size_t)code8 * ix.nsec4 + sl) >> 2) == (((size_t)code8 * ix.nsec4 + sh) >> 2) ? 1u : 2u;
+        }
         const uint32_t p0_lo = (uint32_t)(uintptr_t)p0, p0_hi = (uint32_t)((uintptr_t)p0 >> 32);
         {
             const uint32_t j = lane & 7u;  // this lane's 16 bytes of a line
@@ -349,12 +355,12 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             word <<= 2u * depth0;
             rem = rem0;
             need_table = false;
-#ifdef MSBWT_FINAL_STEP
         } else if (is_fin) {
             const uint4 first = my_row[0];
             const uint32_t used = first.x;
             if (used == kFinOverflow) {
                 no_fin = true;  // the same symbols through two oct steps
+                if constexpr (STATS) st_cnt[2]++;
             } else {
                 const uint32_t tag = (uint32_t)(fin_mixed >> flb);
                 const int pl = (int)(l & fmask), ph = (int)(h & fmask);
@@ -386,7 +392,6 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                 h = (uint32_t)cnt;  // only h - l is read from here on
                 rem = 0;
             }
-#endif
         } else if (is_oct) {
             const uint4 a = my_row[0], b = my_row[1];
             if (a.y > (uint32_t)kOctCapacity) {
@@ -424,6 +429,10 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             forced = forced >= 4u ? forced - 4u : 0u;
         } else if (live) {  // one symbol: the tail of a k-mer, or the last two of ten symbols taken without the oct image
             const uint32_t sym = (0x5321u >> (4u * peek(1u))) & 7u;  // A,C,G,T = 1,2,3,5
+            if constexpr (STATS) {
+                st_cnt[5]++;
+                st_cnt[6] += (l >> kBlockShift) == (h >> kBlockShift) ? 1u : 2u;
+            }
             const uint2 r = oct_remainder_step(ix, cb.c, sym, l, h);
             l = r.x;
             h = r.y;

@@ -74,7 +74,8 @@ class Options(C.Structure):
     """`msbwt_options` (include/msbwt_gpu.h)."""
     _fields_ = [("struct_size", C.c_uint32), ("superblock_shift", C.c_uint32), ("suffix_table_s", C.c_int32),
                 ("pair_index", C.c_int32), ("kernel_lanes", C.c_int32), ("quad_index", C.c_int32), ("oct_index", C.c_int32),
-                ("oct_bucket_shift", C.c_int32)]
+                ("oct_bucket_shift", C.c_int32), ("keep_quad_index", C.c_int32), ("final_index", C.c_int32),
+                ("final_bucket_shift", C.c_int32), ("final_lines_log2", C.c_int32)]
 
 
 _lib = None
@@ -100,6 +101,7 @@ def load_library():
         "msbwt_index_create_from_npy": (vp, [C.c_char_p, ip, i32, ip]),
         "msbwt_index_create_ex": (vp, [vp, u64, ip, i32, u32, i32, ip]),
         "msbwt_index_create_opts": (vp, [vp, u64, ip, i32, C.POINTER(Options), ip]),
+        "msbwt_index_create_from_npy_opts": (vp, [C.c_char_p, ip, i32, C.POINTER(Options), ip]),
         "msbwt_index_destroy": (None, [vp]),
         "msbwt_total_size": (u64, [vp]),
         "msbwt_symbol_count": (u64, [vp, C.c_uint8]),
@@ -126,6 +128,8 @@ def load_library():
         "msbwt_table_depth_for_k": (i32, [vp, u32]),
         "msbwt_debug_table_depth": (i32, [u32, u32, u32]),
         "msbwt_count_kmers_u64": (i32, [vp, vp, u32, u64, vp]),
+        "msbwt_count_kmers_fixed_u32": (i32, [vp, vp, u32, u64, vp]),
+        "msbwt_count_kmers_u64_u32": (i32, [vp, vp, u32, u64, vp]),
         "msbwt_final_index": (i32, [vp]),
         "msbwt_debug_copy_final_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64), vp]),
         "msbwt_debug_copy_oct_image": (i32, [vp, i32, C.POINTER(u64), vp]),
@@ -139,6 +143,7 @@ def load_library():
         "msbwt_debug_copy_pair_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp]),
         "msbwt_pack_kmers_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp, vp]),
         "msbwt_count_kmers_packed_device": (i32, [vp, i32, vp, u32, u64, vp, vp]),
+        "msbwt_count_kmers_packed_stats_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
         "msbwt_launch_count": (u64, []),
         "msbwt_gather_bench": (i32, [i32, vp, u64, u32, u64, u64, vp, vp]),
         "msbwt_l2_fetch_granularity": (i32, [i32, i32]),
@@ -160,6 +165,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
+    "msbwt_index_create_from_npy_opts", "msbwt_count_kmers_packed_stats_device", "msbwt_count_kmers_fixed_u32", "msbwt_count_kmers_u64_u32",
     "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_oct_index", "msbwt_oct_overflow_lines",
     "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift", "msbwt_oct_symbols", "msbwt_table_depth_for_k", "msbwt_debug_table_depth", "msbwt_count_kmers_u64", "msbwt_final_index", "msbwt_debug_copy_final_image",
     "msbwt_debug_copy_oct_image", "msbwt_constrain_ranges_fanout", "msbwt_constrain_ranges_fanout_device",
@@ -207,7 +213,8 @@ class RleBWT:
 
     def __init__(self, bin_power: int = 8, devices: list[int] | None = None, superblock_shift: int = 0,
                  suffix_table_s: int = -1, pair_index: int = -1, kernel_lanes: int = 0, quad_index: int = -1,
-                 oct_index: int = -1, oct_bucket_shift: int = 0):
+                 oct_index: int = -1, oct_bucket_shift: int = 0, keep_quad_index: int = -1, final_index: int = -1,
+                 final_bucket_shift: int = 0, final_lines_log2: int = 0):
         # bin_power is accepted for signature parity (src/rle_bwt.rs:309-322); it never
         # changed results in the reference and has no counterpart in the device layout.
         self.bin_power = bin_power
@@ -219,6 +226,10 @@ class RleBWT:
         self._quad = quad_index         # -1 auto, 0 never, 1 always: the 32-byte quad sectors (four steps per sector)
         self._oct = oct_index           # -1 auto, 0 never, 1 always: the 128-byte oct lines (ten steps per line)
         self._oct_shift = oct_bucket_shift  # 0 auto, else log2 of the oct bucket size (8..23)
+        self._keep_quad = keep_quad_index   # under an oct image: -1 auto, 0 drop the quad image after the build, 1 keep
+        self._final = final_index           # -1 auto (with the oct image), 0 never, 1 always: the final-step lines
+        self._final_shift = final_bucket_shift  # 0 = 16
+        self._final_lb = final_lines_log2       # 0 auto, else log2 of the lines per bucket (12..20)
         self._h = None
 
     @classmethod
@@ -253,6 +264,10 @@ class RleBWT:
             raise MsbwtError(EINVAL, "no BWT loaded")
         return self._h
 
+    def _options(self) -> Options:
+        return Options(C.sizeof(Options), self._sb_shift, self._table_s, self._pair, self._lanes, self._quad, self._oct,
+                       self._oct_shift, self._keep_quad, self._final, self._final_shift, self._final_lb)
+
     # -- BWT trait
     def load_vector(self, bwt) -> None:
         L = load_library()
@@ -260,8 +275,7 @@ class RleBWT:
         a = _u8(bwt)
         err = C.c_int(0)
         devs, nd = self._dev_args()
-        opts = Options(C.sizeof(Options), self._sb_shift, self._table_s, self._pair, self._lanes, self._quad, self._oct,
-                       self._oct_shift)
+        opts = self._options()
         h = L.msbwt_index_create_opts(_p(a), a.size, devs, nd, C.byref(opts), C.byref(err))
         if not h:
             _check(err.value or ECUDA, "load_vector")
@@ -272,7 +286,8 @@ class RleBWT:
         self.close()
         err = C.c_int(0)
         devs, nd = self._dev_args()
-        h = L.msbwt_index_create_from_npy(os.fsencode(filename), devs, nd, C.byref(err))
+        opts = self._options()   # the same layout knobs as load_vector
+        h = L.msbwt_index_create_from_npy_opts(os.fsencode(filename), devs, nd, C.byref(opts), C.byref(err))
         if not h:
             _check(err.value or ECUDA, "load_numpy_file")
         self._h = h
@@ -308,21 +323,25 @@ class RleBWT:
         _check(load_library().msbwt_count_kmers(self.handle, _p(flat), _p(offs), n, _p(out)), "count_kmers")
         return out
 
-    def count_kmers_fixed(self, syms, k: int) -> np.ndarray:
-        """Fixed-k batch: `syms` is n*k symbols, row-major."""
+    def count_kmers_fixed(self, syms, k: int, counts32: bool = False) -> np.ndarray:
+        """Fixed-k batch: `syms` is n*k symbols, row-major.  `counts32`: u32 counts (index below 2^32 symbols)."""
         a = _u8(syms).reshape(-1)
         if k == 0:
             raise MsbwtError(EINVAL, "count_kmers_fixed needs k > 0 (use count_kmers for empty k-mers)")
         if a.size % k:
             raise MsbwtError(EINVAL, "len(syms) is not a multiple of k")
         n = a.size // k
+        if counts32:
+            out = np.zeros(n, dtype=np.uint32)
+            _check(load_library().msbwt_count_kmers_fixed_u32(self.handle, _p(a), k, n, _p(out)), "count_kmers_fixed_u32")
+            return out
         out = np.zeros(n, dtype=np.uint64)
         _check(load_library().msbwt_count_kmers_fixed(self.handle, _p(a), k, n, _p(out)), "count_kmers_fixed")
         return out
 
     @property
     def final_index(self) -> bool:
-        """EXPERIMENTAL final-step image present (library built with -DMSBWT_FINAL_STEP, MSBWT_FINAL_INDEX=1)"""
+        """final-step image in use (msbwt_options.final_index)"""
         return bool(load_library().msbwt_final_index(self.handle))
 
     @property
@@ -345,10 +364,14 @@ class RleBWT:
         _check(L.msbwt_debug_copy_final_image(self.handle, slot, None, None, None, None, _p(lines)), "debug_copy_final_image")
         return lines, int(b.value), int(lb.value), int(over.value)
 
-    def count_kmers_u64(self, kmers, k: int) -> np.ndarray:
+    def count_kmers_u64(self, kmers, k: int, counts32: bool = False) -> np.ndarray:
         """k-mers held as integers (k <= 32, first symbol in the most significant of the 2k bits, A,C,G,T = 0..3):
-        8 bytes per query over the link instead of k.  EXPERIMENTAL (msbwt_gpu.h)."""
+        8 bytes per query over the link instead of k.  `counts32`: u32 counts (index below 2^32 symbols)."""
         a = _u64(kmers).reshape(-1)
+        if counts32:
+            out = np.zeros(a.size, dtype=np.uint32)
+            _check(load_library().msbwt_count_kmers_u64_u32(self.handle, _p(a), k, a.size, _p(out)), "count_kmers_u64_u32")
+            return out
         out = np.zeros(a.size, dtype=np.uint64)
         _check(load_library().msbwt_count_kmers_u64(self.handle, _p(a), k, a.size, _p(out)), "count_kmers_u64")
         return out
@@ -403,6 +426,12 @@ class RleBWT:
                                   slot: int = 0) -> None:
         _check(load_library().msbwt_count_kmers_packed_device(self.handle, slot, d_packed, k, n, d_out,
                                                               stream or None), "count_kmers_packed_device")
+
+    def count_kmers_packed_stats_device(self, d_packed: int, k: int, n: int, d_out: int, d_stats: int, stream: int = 0,
+                                        slot: int = 0) -> None:
+        """the search with the counting build of the oct kernel: d_stats = 8 u64 on the device (msbwt_gpu.h)"""
+        _check(load_library().msbwt_count_kmers_packed_stats_device(self.handle, slot, d_packed, k, n, d_out, d_stats, stream),
+               "count_kmers_packed_stats_device")
 
     def constrain_ranges_device(self, d_sym: int, d_l: int, d_h: int, n: int, d_out_l: int, d_out_h: int,
                                 stream: int = 0, slot: int = 0) -> None:

@@ -1,14 +1,7 @@
-"""EXPERIMENTAL final-step image (layout.h, fin_builder.cu, the `is_fin` step of count_kmers_oct_kernel): the last 20
-symbols of a k-mer answered from ONE hashed line.  Checked against its numpy specification (oracle/final_step.py)
-line by line, and against the oracle's count_kmer (src/msbwt_core.rs:125-161) for the lengths that reach the step
-(k = table depth + 10 a + 20) and for some that do not.
-
-Written after the round's GPU budget was spent: NOT yet run on a GPU.  Needs a library compiled with
--DMSBWT_FINAL_STEP (`tools/build_variant.sh finalstep -DMSBWT_FINAL_STEP`, then
-`MSBWT_LIBRARY_PATH=build/variants/lib_finalstep.so MSBWT_EXPERIMENTAL=1 pytest -m gpu tests/test_gpu_final_step.py`);
-skipped otherwise."""
-import os
-
+"""Final-step image (layout.h, fin_builder.cu, the `is_fin` step of count_kmers_oct_kernel): the last 20 symbols of a
+k-mer answered from ONE hashed line.  Checked against its numpy specification (oracle/final_step.py) line by line, and
+against the oracle's count_kmer (src/msbwt_core.rs:125-161) for the lengths that reach the step
+(k = table depth + 10 a + 20) and for some that do not -- with the quad image kept beside it and dropped."""
 import numpy as np
 import pytest
 
@@ -17,21 +10,15 @@ from oracle import final_step as F
 from oracle import oracle as O
 from tests.test_oracle_final_step import decode
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MSBWT_EXPERIMENTAL", "0") in ("", "0"),
-                                 reason="the final-step image is unverified on a GPU: set MSBWT_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
 
 def make_index(rle, monkeypatch, shift=16, lb=12, **kw):
-    monkeypatch.setenv("MSBWT_FINAL_INDEX", "1")
-    monkeypatch.setenv("MSBWT_FINAL_BUCKET_SHIFT", str(shift))
-    monkeypatch.setenv("MSBWT_FINAL_LINES_LOG2", str(lb))
-    g = M.RleBWT(oct_index=1, **kw)
+    g = M.RleBWT(oct_index=1, final_index=1, final_bucket_shift=shift, final_lines_log2=lb, **kw)
     g.load_vector(rle)
-    if not g.final_index:
-        pytest.skip("library built without -DMSBWT_FINAL_STEP")
+    assert g.final_index and g.oct_index
     return g
 
 
@@ -59,11 +46,13 @@ def test_device_image_equals_the_specification(midsize, monkeypatch, shift, lb):
         assert F.line_groups(lines[i]) == F.line_groups(want[i]), i
 
 
+@pytest.mark.parametrize("keep_quad", [1, 0])
 @pytest.mark.parametrize("shift,lb,table_s", [(16, 12, -1), (12, 12, -1), (10, 13, 7), (16, 12, 0), (14, 12, 12)])
-def test_counts_are_bit_exact_with_the_final_step(midsize, monkeypatch, shift, lb, table_s):
+def test_counts_are_bit_exact_with_the_final_step(midsize, monkeypatch, shift, lb, table_s, keep_quad):
     from harness import synth
     reads, o = midsize
-    g = make_index(o.rle_bytes(), monkeypatch, shift, lb, suffix_table_s=table_s)
+    g = make_index(o.rle_bytes(), monkeypatch, shift, lb, suffix_table_s=table_s, keep_quad_index=keep_quad)
+    assert g.quad_index == bool(keep_quad)
     for k in (20, 21, 24, 30, 31, 32, 33, 40, 41, 42, 51, 61, 64, 71, 100):
         q = synth.make_queries(reads, k, 12001, 6000).cpu().numpy()
         q[5, 0] = 4
@@ -80,8 +69,29 @@ def test_overflowed_lines_fall_back(monkeypatch):
     rle = bwt_build.build_rle_bwt(reads)[0].cpu().numpy()
     o = O.RleBWT()
     o.load_vector(rle)
-    g = make_index(rle, monkeypatch)
-    assert g.final_image()[3] > 0
-    for k in (31, 41, 64):
-        q = synth.make_queries(reads, k, 20000, 5000).cpu().numpy()
-        assert (g.count_kmers_fixed(q, k) == o.count_kmers_fixed(q, k, threads=8)).all(), k
+    for keep_quad in (1, 0):
+        g = make_index(rle, monkeypatch, keep_quad_index=keep_quad)
+        assert g.final_image()[3] > 0 and g.oct_overflow_lines > 0
+        for k in (31, 37, 41, 64):
+            q = synth.make_queries(reads, k, 20000, 5000).cpu().numpy()
+            assert (g.count_kmers_fixed(q, k) == o.count_kmers_fixed(q, k, threads=8)).all(), (keep_quad, k)
+
+
+def test_automatic_policy_builds_it_with_the_oct_image_and_can_be_switched_off(midsize, monkeypatch):
+    from harness import synth
+    reads, o = midsize
+    g = M.RleBWT(oct_index=1)
+    g.load_vector(o.rle_bytes())
+    assert g.final_index and g.final_bucket_shift == 16
+    off = M.RleBWT(oct_index=1, final_index=0)
+    off.load_vector(o.rle_bytes())
+    assert not off.final_index and off.oct_index
+    monkeypatch.setenv("MSBWT_FINAL_INDEX", "0")
+    env_off = M.RleBWT(oct_index=1)
+    env_off.load_vector(o.rle_bytes())
+    assert not env_off.final_index
+    q = synth.make_queries(reads, 31, 50001, 20000).cpu().numpy()
+    want = o.count_kmers_fixed(q, 31, threads=8)
+    for b in (g, off, env_off):
+        assert (b.count_kmers_fixed(q, 31) == want).all()
+        assert (b.count_kmers_fixed(q, 31, counts32=True) == want).all()

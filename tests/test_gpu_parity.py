@@ -29,7 +29,7 @@ def from_strings(strings, **kw):
 
 def test_library_is_the_cuda_one_and_device_present():
     assert torch.cuda.is_available()
-    assert M.load_library().msbwt_abi_version() == 3
+    assert M.load_library().msbwt_abi_version() == 4
 
 
 # ---- test_data/two_string.npy (config 1): rle_bwt.rs:76-79, README.md:62-70 ----

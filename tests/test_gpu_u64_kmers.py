@@ -1,21 +1,13 @@
 """`count_kmers_u64` (msbwt_count_kmers_u64): BWT::count_kmer (src/msbwt_core.rs:125-161) for k-mers the caller holds
 as 2-bit-per-symbol integers, k <= 32 -- compared with the oracle's count_kmer on the same k-mers spelled out as
-symbol bytes, over every image a query can be served from and every suffix-table depth class.
-
-EXPERIMENTAL: written after the round's GPU budget was spent, so these tests have not run on a GPU yet; they are
-skipped unless MSBWT_EXPERIMENTAL=1 (first thing to run next round: `MSBWT_EXPERIMENTAL=1 pytest -m gpu
-tests/test_gpu_u64_kmers.py`)."""
-import os
-
+symbol bytes, over every image a query can be served from and every suffix-table depth class."""
 import numpy as np
 import pytest
 
 import rust_msbwt_b200 as M
 from oracle import oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MSBWT_EXPERIMENTAL", "0") in ("", "0"),
-                                 reason="count_kmers_u64 is unverified on a GPU: set MSBWT_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
@@ -88,6 +80,10 @@ def test_u64_kmers_many_chunks_and_argument_checks(midsize):
     assert (g.count_kmers_u64(encode(q), 31) == o.count_kmers_fixed(q, 31, threads=8)).all()
     h2d, d2h = M.last_transfer_bytes()
     assert h2d == 8 * len(q) and d2h == 8 * len(q)
+    got32 = g.count_kmers_u64(encode(q), 31, counts32=True)                # u32 counts: 4 bytes per query back
+    assert got32.dtype == np.uint32 and (got32 == o.count_kmers_fixed(q, 31, threads=8)).all()
+    h2d, d2h = M.last_transfer_bytes()
+    assert h2d == 8 * len(q) and d2h == 4 * len(q)
     assert g.count_kmers_u64(np.zeros(0, dtype=np.uint64), 31).size == 0
     for bad_k in (0, 33):
         with pytest.raises(M.MsbwtError):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/msbwt_gpu.h but not exported"
     assert declared == set(M.EXPORTED_SYMBOLS)
-    assert M.load_library().msbwt_abi_version() == 3
+    assert M.load_library().msbwt_abi_version() == 4
 
 
 CKPT_SLOT = {1: 0, 2: 1, 3: 2, 5: 3}  # layout.h: A,C in half 0 words 0,1; G,T in half 1 words 0,1; $ / N in aux
