@@ -1,14 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- 31-mer count_kmer throughput (queries/s) on B200, per the driver contract.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload default|cfg2|cfg3|cfg5|tiny]
 
-A "step" is one pass of the hot path (pack + backward-search kernels) over one batch of
-synthetic k-mer queries.  Default workload = BASELINE.json configs[1]: 1 M synthetic
-150-bp reads (151 Msymbol BWT), 5 M random + 5 M read-sampled 31-mers, one B200.
-With N > 1 (torchrun, one rank per GPU) every rank holds a replica of the index and its
-own batch of the same size (weak scaling, no data-path collective); the only
-torch.distributed traffic is the barrier and the max-over-ranks of the timings.
+A "step" is one pass of the hot path (pack/seed + backward-search kernels) over one batch of synthetic k-mer
+queries.  Headline workload = BASELINE.json configs[2]: 10 M synthetic 150-bp reads with 1 % errors (1.51 Gsymbol
+BWT), a FIXED batch of 100 M read-sampled 31-mers.  With N > 1 (torchrun, one rank per GPU) every rank holds a
+replica of the index and the rank's contiguous slice of that batch (strong scaling, no data-path collective); the
+only torch.distributed traffic is the barrier and the max-over-ranks of the timings.
+
+  value : kernel-only -- the batch resident in HBM as symbol bytes, pack/seed + search timed with CUDA events
+  e2e   : the drop-in C-ABI call (msbwt_count_kmers_fixed) on pinned HOST buffers, copies inside the timed region,
+          through ONE handle created with devices = [0..N-1] on rank 0 -- the library's own multi-GPU dispatcher
+          (the other ranks have released their replicas and sleep in a gloo barrier); the packed-integer entry
+          points (8 bytes in, 8 or 4 bytes out per query) are timed beside it
+
+Nested `other_workloads`: configs[1] (151 Msymbol BWT, N = 1 only) and configs[4] (3.02 Gsymbol BWT; one GPU's
+125 M-query share at N = 1, the full 10^9 queries over 8 replicas at N = 8).
 
 One JSON line on stdout (rank 0).  Everything else goes to stderr.
 """
@@ -21,7 +29,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -31,17 +38,22 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # BASELINE.json configs[1]
     "cfg2": dict(key="cfg2", reads=1_000_000, read_len=150, coverage=30.0, error=0.0, n_read=5_000_000, n_random=5_000_000, k=31,
+                 scaling="strong",
                  name="configs[1]: 1M synthetic 150bp reads (151 Msymbol BWT), 5M random + 5M read-sampled 31-mers"),
-    # BASELINE.json configs[2]
+    # BASELINE.json configs[2]: the headline
     "cfg3": dict(key="cfg3", reads=10_000_000, read_len=150, coverage=30.0, error=0.01, n_read=100_000_000, n_random=0, k=31,
+                 scaling="strong",
                  name="configs[2]: 10M synthetic 150bp reads with 1% errors (1.51 Gsymbol BWT), 100M read-sampled 31-mers"),
-    # BASELINE.json configs[4], one GPU's share: the 3.02 Gsymbol index is replicated, the 1 B queries are split 8 ways
+    # BASELINE.json configs[4]: the 3.02 Gsymbol index is replicated, every GPU answers 125 M of the 10^9 queries
     "cfg5": dict(key="cfg5", reads=20_000_000, read_len=150, coverage=30.0, error=0.01, n_read=125_000_000, n_random=0, k=31,
+                 scaling="weak",
                  name="configs[4]: 20M synthetic 150bp reads with 1% errors (3.02 Gsymbol BWT), 125M read-sampled 31-mers per GPU (1 B over 8)"),
     # small shape for plumbing checks
     "tiny": dict(key="tiny", reads=20_000, read_len=150, coverage=30.0, error=0.01, n_read=100_000, n_random=100_000, k=31,
+                 scaling="strong",
                  name="tiny: 20k reads, 200k 31-mers (plumbing check, not a bench line)"),
 }
+HEADLINE = "cfg3"
 METRIC = "count_kmer_31mer_queries_per_sec"
 UNIT = "queries/s"
 BLOCK_BYTES = 64      # layout.h: one 64-byte block per 128 symbols (one-step path)
@@ -57,15 +69,20 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def ncu_traffic(workload_key: str, lanes: int, table_s: int, pair: bool = False, quad: bool = False, oct_: bool = False):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel, per launch, from the committed
-    `ncu --set full` capture of this same workload/kernel configuration (profiles/ncu_traffic.json);
-    None when no capture matches."""
+def workload_config(cfg: dict, total: int | None, world: int) -> dict:
+    """The `config` object: names the workload.  Identical in both arms (`--impl ours` / `--impl reference`)."""
+    n = cfg["n_read"] + cfg["n_random"]
+    return {"workload": cfg["name"], "bwt_symbols": total, "k": cfg["k"],
+            "queries": n if cfg["scaling"] == "strong" else n * world,
+            "seeds": "torch Philox 0x5EED0001.. (harness/synth.py)"}
+
+
+def ncu_traffic(workload_key: str, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of this same workload / kernel (profiles/ncu_traffic.json); None when none matches."""
     try:
         for e in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["captures"]:
-            if (e["workload"] == workload_key and e["suffix_table_s"] == table_s and bool(e.get("pair", False)) == pair
-                    and bool(e.get("quad", False)) == quad and bool(e.get("oct", False)) == oct_
-                    and (pair or quad or e["lanes"] == lanes)):
+            if e["workload"] == workload_key and e.get("kernel") == kernel:
                 return e["dram_bytes_per_launch"], e["source"]
     except Exception:
         pass
@@ -135,14 +152,14 @@ class ClockSampler:
         return out
 
 
-def build_workload(cfg: dict, device, rank: int):
-    """Synthetic reads -> BWT -> RLE bytes (host) and this rank's query batch (device)."""
+def build_reads_and_bwt(cfg: dict, device, use_library: bool):
+    """Synthetic reads -> BWT -> RLE bytes (host).  `use_library`: the product's device-side builder
+    (bwt_build.cu; equals the harness builder and naive_bwt, tests/); otherwise the torch harness only, so that the
+    reference arm never maps our library."""
     import torch
     from harness import bwt_build, synth
-    t0 = time.time()
     reads = synth.make_reads(cfg["reads"], cfg["read_len"], cfg["coverage"], cfg["error"], device=device)
-    if device.type == "cuda":
-        # the library's own device-side builder (bwt_build.cu; equals the harness builder and naive_bwt, tests/)
+    if use_library and device.type == "cuda":
         import rust_msbwt_b200 as M
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
@@ -151,7 +168,18 @@ def build_workload(cfg: dict, device, rank: int):
         rle, total = bwt_build.build_rle_bwt(reads)
         rle_host = rle.cpu().numpy()
         del rle
-    queries = synth.make_queries(reads, cfg["k"], cfg["n_read"], cfg["n_random"], seed_offset=1000 * rank)
+    return reads, rle_host, total
+
+
+def build_workload(cfg: dict, device, rank: int, use_library: bool = True):
+    """RLE bytes (host) and a query batch (device).  A strong-scaling workload has ONE batch, the same on every rank
+    (the ranks then take slices of it); a weak-scaling one gives every rank its own batch (seed offset = rank)."""
+    import torch
+    from harness import synth
+    t0 = time.time()
+    reads, rle_host, total = build_reads_and_bwt(cfg, device, use_library)
+    seed_offset = 0 if cfg["scaling"] == "strong" else 1000 * rank
+    queries = synth.make_queries(reads, cfg["k"], cfg["n_read"], cfg["n_random"], seed_offset=seed_offset)
     reads_sample = reads[:100_000].cpu().numpy()   # for the pileup leg (count_read_kmers)
     del reads
     if device.type == "cuda":
@@ -160,6 +188,22 @@ def build_workload(cfg: dict, device, rank: int):
     log(f"[rank {rank}] workload built in {time.time() - t0:.1f}s: {total} symbols, {rle_host.size} RLE bytes, "
         f"{queries.shape[0]} queries")
     return rle_host, total, queries, reads_sample
+
+
+def encode_u64(q, k: int):
+    """[n, k] symbol bytes (all ACGT) on a torch device -> n int64: the k-mer as a 2k-bit integer, first symbol most
+    significant, A,C,G,T = 0..3 (msbwt_count_kmers_u64's input format)."""
+    import torch
+    lut = torch.tensor([0, 0, 1, 2, 0, 3], dtype=torch.int64, device=q.device)
+    out = torch.empty(q.shape[0], dtype=torch.int64, device=q.device)
+    step = 1 << 24
+    for a in range(0, q.shape[0], step):
+        blk = q[a:a + step]
+        acc = torch.zeros(blk.shape[0], dtype=torch.int64, device=q.device)
+        for j in range(k):
+            acc = (acc << 2) | lut[blk[:, j].long()]
+        out[a:a + step] = acc
+    return out
 
 
 def cpu_reference_leg(orc, q_host, k, threads, target_s, label):
@@ -178,12 +222,12 @@ def cpu_reference_leg(orc, q_host, k, threads, target_s, label):
 
 
 def reference_measure(args, cfg):
-    """The reference's own CPU algorithm (oracle port; the Rust crate cannot be built in this image)
-    on this box's host cores, all threads, bounded samples of the workload."""
+    """The reference's own CPU algorithm (oracle port; the Rust crate cannot be built in this image) on this box's
+    host cores, all threads, bounded samples of the workload.  Inputs come from the torch harness alone."""
     import torch
     from oracle import oracle as O
     dev = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")  # GPU only manufactures the inputs
-    rle_host, total, queries, _ = build_workload(cfg, dev, 0)
+    rle_host, total, queries, _ = build_workload(cfg, dev, 0, use_library=False)
     q_host = queries.cpu().numpy()
     del queries
     orc = O.RleBWT()
@@ -214,14 +258,15 @@ def run_reference(args, cfgs):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     r = reference_measure(args, cfgs[0])
     sample = f"{r['per_step']} of the workload's {r['n']} queries per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": cfgs[0]["name"], "bwt_symbols": r["total"], "k": r["k"],
-                   "queries_per_step": r["per_step"]},
+        "higher_is_better": True, "scaling": cfgs[0]["scaling"], "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(cfgs[0], r["total"], world),
+        "queries_per_step": r["per_step"],
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -229,32 +274,131 @@ def run_reference(args, cfgs):
     for extra in cfgs[1:]:
         x = reference_measure(args, extra)
         line.setdefault("other_workloads", []).append(
-            {"workload": extra["name"], "value": x["value"], "unit": UNIT, "cores": x["cores"],
+            {"config": workload_config(extra, x["total"], world), "value": x["value"], "unit": UNIT, "cores": x["cores"],
              "sample": f"{x['per_step']} of {x['n']} queries per step"})
     print(json.dumps(line), flush=True)
 
 
-def measure_ours(args, cfg, ctx, primary: bool):
-    """One workload on this rank's GPU: kernel-only `value`, end-to-end C-ABI figure, parity check,
-    CPU baseline and roofline accounting (rank 0)."""
+def time_host_calls(fn, steps: int, warm: int = 1) -> float:
+    """seconds per call of a blocking host-buffer entry point (results are in host memory when it returns)"""
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    return (time.perf_counter() - t0) / steps
+
+
+def e2e_legs(args, cfg, handle, lib, M, q_dev_list, k, reads_sample, n_devices, want_bytes_leg=True):
+    """End-to-end legs through ONE handle (`n_devices` replicas) on pinned host buffers.  `q_dev_list`: the batch as
+    device tensors (one per original rank for a weak workload) -- copied to pinned host memory here, outside the
+    timed regions.  Returns (dict of legs, host arrays needed for the parity check)."""
     import ctypes
 
     import numpy as np
     import torch
 
+    n = sum(int(q.shape[0]) for q in q_dev_list)
+    steps = max(1, min(args.steps, 5))
+    legs = {}
+    vp = ctypes.c_void_p
+
+    # the packed-integer batch: what a k-mer counter holds (8 bytes per 31-mer)
+    km_pinned = torch.empty(n, dtype=torch.int64, pin_memory=True)
+    at = 0
+    for q in q_dev_list:
+        km_pinned[at:at + q.shape[0]].copy_(encode_u64(q, k))
+        at += q.shape[0]
+    torch.cuda.synchronize()
+    km_np = km_pinned.numpy().view(np.uint64)
+    out64 = torch.empty(n, dtype=torch.int64, pin_memory=True)
+    out32 = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    o64, o32 = out64.numpy().view(np.uint64), out32.numpy().view(np.uint32)
+
+    def leg(name, what, fn, out_arr):
+        dt = time_host_calls(fn, steps)
+        h2d, d2h = M.last_transfer_bytes()
+        legs[name] = {"value": n / dt, "unit": UNIT, "ms_per_step": 1e3 * dt, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "entry": what, "steps": steps}
+        legs[name]["checksum"] = int(out_arr.astype(np.uint64).sum())
+        log(f"[e2e] {name}: {n / dt / 1e9:.2f} G q/s ({1e3 * dt:.2f} ms per {n} queries, {h2d / n:.1f} B in, {d2h / n:.1f} B out per query)")
+
+    def call(fn_name, *a):
+        rc = getattr(lib, fn_name)(handle, *a)
+        assert rc == 0, lib.msbwt_last_error()
+
+    leg("u64", "msbwt_count_kmers_u64: k-mers as 2-bit-per-symbol integers in, u64 counts out",
+        lambda: call("msbwt_count_kmers_u64", vp(km_np.ctypes.data), k, n, vp(o64.ctypes.data)), o64)
+    leg("u64_out32", "msbwt_count_kmers_u64_u32: the same with u32 counts (index below 2^32 symbols)",
+        lambda: call("msbwt_count_kmers_u64_u32", vp(km_np.ctypes.data), k, n, vp(o32.ctypes.data)), o32)
+    assert legs["u64"]["checksum"] == legs["u64_out32"]["checksum"], "u64 and u32 counts differ"
+
+    host = {"o64": o64, "q_np": None}
+    if want_bytes_leg:
+        q_pinned = torch.empty((n, k), dtype=torch.uint8, pin_memory=True)
+        at = 0
+        for q in q_dev_list:
+            q_pinned[at:at + q.shape[0]].copy_(q)
+            at += q.shape[0]
+        torch.cuda.synchronize()
+        q_np = q_pinned.numpy()
+        host["q_np"] = q_np
+        ob = torch.empty(n, dtype=torch.int64, pin_memory=True)
+        ob_np = ob.numpy().view(np.uint64)
+        leg("bytes", "msbwt_count_kmers_fixed: one symbol per byte in (the reference's &[u8] k-mers), u64 counts out",
+            lambda: call("msbwt_count_kmers_fixed", vp(q_np.ctypes.data), k, n, vp(ob_np.ctypes.data)), ob_np)
+        h2d = legs["bytes"]["h2d_bytes_per_step"]
+        legs["bytes"]["route"] = ("symbol bytes H2D -> pack + search kernels -> D2H" if h2d >= n * k else
+                                  "host threads pack 2 bit/symbol into pinned staging -> H2D -> seed + search kernels -> D2H"
+                                  if h2d <= 8 * -(-k // 32) * n + 4096 else
+                                  "hybrid: chunks packed 2 bit/symbol by the host pool, and raw symbol-byte chunks whenever the "
+                                  "copy engine is idle -> seed / pack + search kernels -> D2H")
+        legs["bytes"]["host_input_bytes_per_step"] = n * k
+        assert legs["bytes"]["checksum"] == legs["u64"]["checksum"], "byte and integer entry points differ"
+        host["o64"] = ob_np
+
+    # pileup: count_kmer of every window of whole reads (msbwt_count_read_kmers): only the reads cross PCIe
+    if reads_sample is not None:
+        nr, rl = reads_sample.shape
+        r_pinned = torch.empty((nr, rl), dtype=torch.uint8, pin_memory=True)
+        r_pinned.copy_(torch.from_numpy(reads_sample))
+        p_out = torch.empty((nr, rl - k + 1), dtype=torch.int64, pin_memory=True)
+        r_np, p_np = r_pinned.numpy(), p_out.numpy().view(np.uint64)
+        dt = time_host_calls(lambda: call("msbwt_count_read_kmers", vp(r_np.ctypes.data), rl, nr, k, 1, vp(p_np.ctypes.data)), steps)
+        legs["pileup"] = {"value": nr * (rl - k + 1) / dt, "unit": UNIT, "reads_per_step": nr, "windows_per_read": rl - k + 1,
+                          "h2d_bytes_per_step": nr * rl, "d2h_bytes_per_step": nr * (rl - k + 1) * 8, "ms_per_step": 1e3 * dt,
+                          "entry": "msbwt_count_read_kmers on pinned host reads: every 31-mer window of every read, forward strand"}
+        host["pile_counts"] = p_np[:64].copy()
+    legs["host_pack_threads"] = M.host_pack_threads()
+    legs["devices"] = n_devices
+    return legs, host
+
+
+def measure_ours(args, cfg, ctx, primary: bool):
+    """One workload: kernel-only `value` (one replica + one slice per rank), end-to-end legs through one handle
+    (rank 0), parity checks on every rank, CPU baseline and roofline accounting (rank 0)."""
+    import numpy as np
+    import torch
+
     import rust_msbwt_b200 as M
+    from harness.dist import shard_bounds
     from oracle import oracle as O
 
     rank, world, local, dev = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"]
-    barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
+    barrier, max_over_ranks, host_barrier = ctx["barrier"], ctx["max_over_ranks"], ctx["host_barrier"]
     k = cfg["k"]
-    rle_host, total, queries, reads_sample = build_workload(cfg, dev, rank)
+    strong = cfg["scaling"] == "strong"
+    rle_host, total, queries_all, reads_sample = build_workload(cfg, dev, rank)
+    n_batch = queries_all.shape[0]
+    lo, hi = shard_bounds(n_batch, rank, world) if strong else (0, n_batch)
+    queries = queries_all[lo:hi]
     n = queries.shape[0]
+    n_job = n_batch if strong else n_batch * world          # queries the whole job answers per step
     t0 = time.time()
     bwt = M.RleBWT.new(devices=[local])
     bwt.load_vector(rle_host)
-    log(f"[rank {rank}] index resident: {bwt.index_bytes / 1e6:.1f} MB (suffix table s={bwt.suffix_table_s}) "
-        f"in {time.time() - t0:.1f}s")
+    log(f"[rank {rank}] index resident: {bwt.index_bytes / 1e9:.2f} GB (suffix table s={bwt.suffix_table_s}, quad {bwt.quad_index}, "
+        f"oct {bwt.oct_index} b={bwt.oct_bucket_shift}, final {bwt.final_index}) in {time.time() - t0:.1f}s")
 
     stream = torch.cuda.current_stream().cuda_stream
     table_s = bwt.suffix_table_s
@@ -303,89 +447,123 @@ def measure_ours(args, cfg, ctx, primary: bool):
     total_ms = max_over_ranks(sum(step_ms))
     clocks = sampler.stop() if rank == 0 else None
     assert int(d_status.item()) == 0
-    value = world * n * args.steps / (total_ms / 1e3)
+    value = n_job * args.steps / (total_ms / 1e3)
     checksum = int(d_out.sum().item())
-    del flush
+    got = d_out.cpu().numpy().view(np.uint64)
 
-    # ---- e2e: the drop-in C-ABI call with HOST buffers (pinned), H2D + D2H inside ----
-    q_pinned = torch.empty((n, k), dtype=torch.uint8, pin_memory=True)
-    q_pinned.copy_(queries)
-    out_pinned = torch.empty(n, dtype=torch.int64, pin_memory=True)
-    q_np, out_np = q_pinned.numpy(), out_pinned.numpy().view(np.uint64)
-    lib = M.load_library()
+    # ---- exact index traffic of one step (outside any timing): what the pack stage's one-request path fetched and
+    #      left over (its own counters), and what the search then fetches (counting build of the oct kernel) ----
+    stats = None
+    pstats = None
+    if bwt.oct_index and not fused:
+        d_stats = torch.zeros(8, dtype=torch.int64, device=dev)
+        d_out_s = torch.empty(n, dtype=torch.int64, device=dev)
+        d_status.zero_()
+        bwt.pack_kmers_device(queries.data_ptr(), k, n, d_packed.data_ptr(), d_out_s.data_ptr(), d_status.data_ptr(), stream)
+        pstats = bwt.pack_stats(d_packed.data_ptr(), k, n)
+        bwt.count_kmers_packed_stats_device(d_packed.data_ptr(), k, n, d_out_s.data_ptr(), d_stats.data_ptr(), stream)
+        # (list B -- k-mers holding `$` / `N` -- is not walked by the counting build: compare where it has nothing to add)
+        torch.cuda.synchronize()
+        if pstats["live_b"] == 0:
+            assert (d_out_s == d_out).all(), "the counting build of the search kernel returns different counts"
+        stats = [int(v) for v in d_stats.cpu().tolist()]
+        del d_stats, d_out_s
+    del flush, d_packed
 
-    def e2e_step():
-        rc = lib.msbwt_count_kmers_fixed(bwt.handle, ctypes.c_void_p(q_np.ctypes.data), k, n,
-                                         ctypes.c_void_p(out_np.ctypes.data))
-        assert rc == 0, lib.msbwt_last_error()
-
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * n * args.steps / e2e_s
-    h2d_bytes, d2h_bytes = M.last_transfer_bytes()   # counted by the library from the copies it issued
-    assert int(out_np.astype(np.int64).sum()) == checksum, "host-path and device-path results differ"
-
-    # ---- pileup: count_kmer of every window of whole reads (msbwt_count_read_kmers): only the reads cross PCIe ----
-    nr, rl = reads_sample.shape
-    r_pinned = torch.empty((nr, rl), dtype=torch.uint8, pin_memory=True)
-    r_pinned.copy_(torch.from_numpy(reads_sample))
-    p_out = torch.empty((nr, rl - k + 1), dtype=torch.int64, pin_memory=True)
-    r_np, p_np = r_pinned.numpy(), p_out.numpy().view(np.uint64)
-
-    def pile_step():
-        rc = lib.msbwt_count_read_kmers(bwt.handle, ctypes.c_void_p(r_np.ctypes.data), rl, nr, k, 1,
-                                        ctypes.c_void_p(p_np.ctypes.data))
-        assert rc == 0, lib.msbwt_last_error()
-
-    pile_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        pile_step()
-    torch.cuda.synchronize()
-    pile_s = max_over_ranks(time.perf_counter() - t0)
-    pileup = {"value": world * nr * (rl - k + 1) * args.steps / pile_s, "unit": UNIT, "reads_per_step": nr,
-              "windows_per_read": rl - k + 1, "h2d_bytes_per_step": nr * rl, "d2h_bytes_per_step": nr * (rl - k + 1) * 8,
-              "ms_per_step": 1e3 * pile_s / args.steps,
-              "what": "msbwt_count_read_kmers on pinned host reads: every 31-mer window of every read, forward strand"}
-    pile_counts = p_np[:64].copy()
+    # ---- parity, every rank: a sample of this rank's slice against the CPU oracle ----
+    cores = os.cpu_count() or 1
+    my_threads = max(1, cores // world)
+    orc = O.RleBWT()
+    orc.load_vector(rle_host)
+    q_slice_host = None
+    if world > 1:
+        m = min(n, 200_000)
+        q_slice_host = queries[:m].cpu().numpy()
+        assert (got[:m] == orc.count_kmers_fixed(q_slice_host, k, threads=my_threads)).all(), \
+            f"rank {rank}: GPU counts differ from the CPU oracle"
+        log(f"[rank {rank}] parity: {m} queries of slice [{lo}, {hi}) equal the oracle's counts")
 
     res = {
         "value": value, "ms_per_step": total_ms / args.steps,
-        "config": {"workload": cfg["name"], "bwt_symbols": total, "index_bytes": bwt.index_bytes, "k": k,
-                   "suffix_table_s": table_s, "pair_index": bwt.pair_index, "quad_index": bwt.quad_index, "oct_index": bwt.oct_index,
-                   "kernel_lanes_per_query": 1 if bwt.quad_index else (4 if bwt.pair_index else bwt.kernel_lanes),
+        "config": workload_config(cfg, total, world),
+        "engine": {"index_bytes": bwt.index_bytes, "suffix_table_s": table_s, "pair_index": bwt.pair_index,
+                   "quad_index": bwt.quad_index, "oct_index": bwt.oct_index, "oct_bucket_shift": bwt.oct_bucket_shift,
+                   "final_index": bwt.final_index, "final_bucket_shift": bwt.final_bucket_shift,
                    "queries_per_gpu_per_step": n,
-                   "parallelism": f"replica x{world}, query batch sharded",
-                   "l2": "L2 flushed (512 MB fill) between timed iterations; query batch (n*k bytes) exceeds L2",
-                   "seeds": "torch Philox 0x5EED0001.. (harness/synth.py)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "host_input_bytes_per_step": n * k,
-                "route": ("symbol bytes H2D -> pack + search kernels -> D2H" if h2d_bytes >= n * k else
-                          "host threads pack 2 bit/symbol into pinned staging -> H2D -> seed + search kernels -> D2H"
-                          if h2d_bytes <= 8 * -(-k // 32) * n + 4096 else
-                          "hybrid: chunks packed 2 bit/symbol by the host pool, and raw symbol-byte chunks whenever the "
-                          "copy engine is idle -> seed / pack + search kernels -> D2H"),
-                "host_pack_threads": M.host_pack_threads()},
-        "e2e_pileup": pileup,
+                   "parallelism": f"index replicated on {world} GPU(s), the batch cut into {world} contiguous slice(s), no collective",
+                   "l2": "L2 flushed (512 MB fill) between timed iterations; the query batch (n*k bytes) exceeds L2"},
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "checksum": checksum,
+        "parity": {"every_rank_checked_its_slice": world > 1},
     }
 
-    # ---- parity + CPU baseline + algorithmic bytes (rank 0, bounded samples) ----
+    # ---- e2e: the drop-in C-ABI calls with HOST buffers (pinned), H2D + D2H inside, ONE handle over all the GPUs ----
+    lib = M.load_library()
+    want_bytes = True
+    q_dev_list = [queries_all]
+    if not strong and world > 1:
+        # configs[4] at N GPUs: rank 0 regenerates every rank's share (same seeds) for the one-handle run; the batch
+        # travels as packed integers only (a 10^9-query byte batch would be 31 GB of pinned host memory)
+        want_bytes = False
+    if world == 1:
+        legs, host = e2e_legs(args, cfg, bwt.handle, lib, M, q_dev_list, k, reads_sample, 1, want_bytes)
+        assert legs["u64"]["checksum"] == checksum, "host-path and device-path results differ"
+        del bwt
+    else:
+        # every rank releases its replica; rank 0 alone then drives devices 0..N-1 through one handle while the
+        # others sleep in a gloo barrier (an NCCL barrier would keep a kernel spinning on their GPUs)
+        del bwt, d_out
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        host_barrier()
+        legs, host = None, None
+        if rank == 0:
+            os.environ["MSBWT_HOST_THREADS"] = str(min(64, cores))
+            if not strong:
+                from harness import synth
+                reads, _, _ = build_reads_and_bwt(cfg, dev, True)
+                q_dev_list = [synth.make_queries(reads, k, cfg["n_read"], cfg["n_random"], seed_offset=1000 * r) for r in range(world)]
+                del reads
+                torch.cuda.empty_cache()
+            t0 = time.time()
+            multi = M.RleBWT.new(devices=list(range(world)))
+            multi.load_vector(rle_host)
+            log(f"[rank 0] one handle over devices {multi.device_ordinals}: replicas built in {time.time() - t0:.1f}s")
+            legs, host = e2e_legs(args, cfg, multi.handle, lib, M, q_dev_list, k, reads_sample, world, want_bytes)
+            # parity of the dispatcher: this rank's slice equals what its own replica computed, and an evenly spread
+            # sample of the whole batch equals the oracle
+            if strong:
+                assert (host["o64"][lo:hi] == got).all(), "one-handle dispatcher and per-rank replica differ on rank 0's slice"
+            nq = host["o64"].shape[0]
+            idx = np.linspace(0, nq - 1, 200_000).astype(np.int64)
+            if host["q_np"] is not None:
+                qs = host["q_np"][idx]
+            else:
+                allq = torch.cat([q[torch.from_numpy(idx[(idx >= o) & (idx < o + q.shape[0])] - o).to(q.device)]
+                                  for o, q in zip(np.cumsum([0] + [int(q.shape[0]) for q in q_dev_list[:-1]]), q_dev_list)])
+                qs = allq.cpu().numpy()
+            assert (host["o64"][idx] == orc.count_kmers_fixed(qs, k, threads=cores)).all(), "dispatcher counts differ from the CPU oracle"
+            res["parity"]["dispatcher_sample"] = int(idx.size)
+            del multi
+            os.environ.pop("MSBWT_HOST_THREADS", None)
+        del q_dev_list
+        torch.cuda.empty_cache()
+        host_barrier()
     if rank == 0:
-        q_host = q_np
-        orc = O.RleBWT()
-        orc.load_vector(rle_host)
-        cores = os.cpu_count() or 1
-        got = d_out.cpu().numpy().view(np.uint64)
-        pw = np.ascontiguousarray(np.lib.stride_tricks.sliding_window_view(reads_sample[:64], k, axis=1)).reshape(-1, k)
-        assert (pile_counts.reshape(-1) == orc.count_kmers_fixed(pw, k, threads=cores)).all(), "pileup counts differ from the CPU oracle"
+        main_leg = legs["bytes"] if "bytes" in legs else legs["u64"]
+        res["e2e"] = {"value": main_leg["value"], "unit": UNIT, "h2d_bytes_per_step": main_leg["h2d_bytes_per_step"],
+                      "d2h_bytes_per_step": main_leg["d2h_bytes_per_step"], "ms_per_step": main_leg["ms_per_step"],
+                      "entry": main_leg["entry"], "route": main_leg.get("route"),
+                      "handle": f"one msbwt_index over devices [0..{world - 1}] on rank 0 (the library's dispatcher: one host thread per device, host-side gather)",
+                      "host_pack_threads": legs["host_pack_threads"],
+                      "u64": legs["u64"], "u64_out32": legs["u64_out32"], "pileup": legs.get("pileup"),
+                      "bytes": legs.get("bytes")}
+
+    # ---- parity (full), CPU baseline and algorithmic bytes (rank 0, bounded samples) ----
+    if rank == 0:
+        q_host = host["q_np"] if host["q_np"] is not None else queries[: min(n, 2_000_000)].cpu().numpy()
+        if "pile_counts" in host:
+            pw = np.ascontiguousarray(np.lib.stride_tricks.sliding_window_view(reads_sample[:64], k, axis=1)).reshape(-1, k)
+            assert (host["pile_counts"].reshape(-1) == orc.count_kmers_fixed(pw, k, threads=cores)).all(), "pileup counts differ from the CPU oracle"
         if world == 1:
             tgt = 8.0 if primary else 4.0
             v1, m1, c1 = cpu_reference_leg(orc, q_host, k, 1, tgt, "single thread")
@@ -396,98 +574,110 @@ def measure_ours(args, cfg, ctx, primary: bool):
                                    "sample": f"first {m1} of {n} queries, single thread (the reference's loop)",
                                    "allcore": {"value": vN, "cores": cores, "sample": f"first {mN} of {n} queries"},
                                    "parity_checked_queries": max(m1, mN)}
+            res["parity"]["oracle_checked_queries"] = max(m1, mN)
         else:
-            m = min(n, 200_000)
-            assert (got[:m] == orc.count_kmers_fixed(q_host[:m], k, threads=cores)).all()
             res["cpu_baseline"] = None
-        # algorithmic bytes: the index lines the implemented algorithm must touch -- per executed
-        # step the distinct 64-B blocks (one-step path) or 128-B lines (pair path: two of the reference's
-        # constrain_range calls per line) holding l and h, one 32-B sector per suffix-table lookup, the packed
-        # query and the result.  The no-table / one-step figure (what the reference's 31 steps would cost on
-        # 64-B blocks) is reported beside it.  All counted by replaying the batch through the oracle.
-        ms = min(n, 1_000_000)
-        steps0, two0 = orc.count_kmers_stats(q_host[:ms], k, BLOCK_SHIFT)
+        # algorithmic bytes: the index lines the implemented algorithm must touch -- counted EXACTLY by
+        # the counting build of the search kernel on the first `ms` queries when the index has an oct image, else by
+        # replaying the batch through the oracle -- plus the packed query and the result.  The no-table / one-step
+        # figure (what the reference's 31 steps would cost on 64-B blocks) is reported beside it.
+        mo = min(n, 1_000_000, q_host.shape[0])
+        steps0, two0 = orc.count_kmers_stats(q_host[:mo], k, BLOCK_SHIFT)
         packed_q = 8 * (-(-k // 21) + 1) + 4   # symbol words + seed + index of the compacted live list
-        bytes_per_query_no_table = (steps0 + two0) * BLOCK_BYTES / ms + packed_q + 8
-        pair, quad = bwt.pair_index, bwt.quad_index
-        quad_lines = quad_sectors = oct_lines = final_lines = 0
-        if quad:
-            # quad path: four of the reference's constrain_range calls per 32-B sector.  An L2 miss fills the
-            # whole 128-B line, so the bytes HBM must move are counted per distinct LINE (l and h share one
-            # 97 % of the time); the sector-granular figure is reported beside it.
-            # with the oct image on top: M.oct_symbols() (ten) calls per 128-B line while that many symbols are left
-            st = orc.count_kmers_stats_quad(q_host[:ms], k, table_s, QUAD_SYMS, LINE_BYTES // QUAD_SECTOR_BYTES, BLOCK_SHIFT,
-                                            bwt.oct_bucket_shift if bwt.oct_index else 0, M.oct_symbols(),
-                                            bwt.final_bucket_shift)   # experimental final-step image: 0 without one
-            hits = st["table_hits"]
-            final_lines = st["final_steps"]   # one 128-B line for the last 20 symbols (0 unless that image exists)
-            oct_lines = st["oct_steps"] + final_lines   # (a range over two buckets takes its symbols as quad / one-symbol steps: counted there)
+        bytes_per_query_no_table = (steps0 + two0) * BLOCK_BYTES / mo + packed_q + 8
+        pair, quad, octi = res["engine"]["pair_index"], res["engine"]["quad_index"], res["engine"]["oct_index"]
+        oct_lines = final_lines = final_overflowed = quad_steps = quad_lines = one_steps = one_blocks = pair_lines = 0
+        hits = mo
+        if stats is not None:
+            oct_lines, final_lines, final_overflowed, quad_steps, quad_lines, one_steps, one_blocks, walked = stats
+            denom = n
+            ref_steps = M.oct_symbols() * oct_lines + 20 * (final_lines - final_overflowed) + 4 * quad_steps + one_steps
+            source = f"counting build of the search kernel on this rank's {n} queries ({walked} reached the search)"
+        elif quad:
+            st = orc.count_kmers_stats_quad(q_host[:mo], k, table_s, QUAD_SYMS, LINE_BYTES // QUAD_SECTOR_BYTES, BLOCK_SHIFT, 0, M.oct_symbols(), 0)
+            hits, quad_steps = st["table_hits"], st["quad_steps"]
             quad_lines = st["quad_steps"] + st["two_line_quad_steps"]
-            quad_sectors = st["quad_steps"] + st["two_sector_quad_steps"]
-            pair_lines = 0
-            one_blocks = st["one_steps"] + st["two_block_one_steps"]
-            ref_steps = M.oct_symbols() * st["oct_steps"] + 20 * final_lines + 4 * st["quad_steps"] + st["one_steps"]
-            two_share = st["two_line_quad_steps"] / max(1, st["quad_steps"] + st["oct_steps"])
+            one_steps, one_blocks = st["one_steps"], st["one_steps"] + st["two_block_one_steps"]
+            denom, ref_steps = mo, 4 * st["quad_steps"] + st["one_steps"]
+            source = f"oracle replay of the first {mo} of {n} queries"
         elif pair:
-            st = orc.count_kmers_stats_pair(q_host[:ms], k, table_s, PAIR_SYMS, BLOCK_SHIFT)
+            st = orc.count_kmers_stats_pair(q_host[:mo], k, table_s, PAIR_SYMS, BLOCK_SHIFT)
             hits = st["table_hits"]
             pair_lines = st["pair_steps"] + st["two_line_pair_steps"]
-            one_blocks = st["one_steps"] + st["two_block_one_steps"]
-            ref_steps = 2 * st["pair_steps"] + st["one_steps"]
-            two_share = st["two_line_pair_steps"] / max(1, st["pair_steps"])
+            one_steps, one_blocks = st["one_steps"], st["one_steps"] + st["two_block_one_steps"]
+            denom, ref_steps = mo, 2 * st["pair_steps"] + st["one_steps"]
+            source = f"oracle replay of the first {mo} of {n} queries"
         else:
-            steps, two, hits = orc.count_kmers_stats_skip(q_host[:ms], k, BLOCK_SHIFT, table_s)
-            pair_lines, one_blocks, ref_steps = 0, steps + two, steps
-            two_share = two / max(1, steps)
-        # the dominant kernel is the SEARCH kernel: it reads the index lines, the packed query (symbol word, seed
-        # range, index) and writes the result; the suffix-table lookup (one line fill per query) belongs to the
-        # pack/seed kernel and is accounted in `step` below, next to the whole step's time
-        index_bytes_q = (oct_lines * LINE_BYTES + quad_lines * LINE_BYTES + pair_lines * PAIR_BYTES + one_blocks * BLOCK_BYTES) / ms
-        bytes_per_query = index_bytes_q + packed_q + 8
-        if fused:   # the fused kernel reads the k symbol bytes itself and one 16-byte piece of the (L2-resident) table level
-            bytes_per_query = index_bytes_q + hits / ms * 16 + k + 8
-        sector_bytes_per_query = (oct_lines * LINE_BYTES + quad_sectors * QUAD_SECTOR_BYTES + pair_lines * PAIR_BYTES + one_blocks * BLOCK_BYTES) / ms + packed_q + 8
-        accesses_per_query = (oct_lines + quad_lines + pair_lines + one_blocks) / ms
-        # a suffix-table lookup fills a 128-B line from HBM unless the level it reads is L2-resident (depth 11 under
-        # the oct image: 4^11 entries of 8 B = 33 MB), where it costs its 8 bytes
-        depth = bwt.table_depth_for_k(k)
-        table_level_bytes = (4 ** depth) * 8
-        table_hit_bytes = 8 if table_level_bytes <= 64 << 20 else LINE_BYTES
+            steps, two, hits = orc.count_kmers_stats_skip(q_host[:mo], k, BLOCK_SHIFT, table_s)
+            one_steps, one_blocks, denom, ref_steps = steps, steps + two, mo, steps
+            source = f"oracle replay of the first {mo} of {n} queries"
+        depth = M.load_library().msbwt_debug_table_depth(k, table_s, M.oct_symbols() if octi else (4 if quad else 2 if pair else 1))
+        table_level_bytes = (4 ** depth) * 8 if depth > 0 else 0
+        table_hit_bytes = 8 if table_level_bytes <= 64 << 20 else LINE_BYTES   # an L2-resident level costs its 8 bytes
+        table_hits_q = (hits / mo) if depth > 0 else 0.0
         peak, peak_src = measured_peak_gbs()
-        kern_s = statistics.mean(kern_ms) / 1e3
-        achieved = bytes_per_query * n / kern_s / 1e9
-        traffic, traffic_src = ncu_traffic(cfg["key"], bwt.kernel_lanes, table_s, pair, quad, bwt.oct_index)
+        pack_s = statistics.mean(step_ms) / 1e3 - statistics.mean(kern_ms) / 1e3
+        search_s = statistics.mean(kern_ms) / 1e3
+        step_s = statistics.mean(step_ms) / 1e3
+        # the two kernels of a step.  SEARCH: the index lines it fetches, the packed query (symbol word, seed range,
+        # index) of every query that reaches it, the result.  PACK/SEED: k symbol bytes in, one suffix-table entry, and
+        # either the packed query out (20 B) or -- on the one-request path (pack_seed_final_kernel: k = 31 / 32 with a
+        # final-step image) -- one 128-B final-step line and the 8-B result, with only the leftovers written out.
+        search_lines128 = oct_lines + final_lines + quad_lines + pair_lines
+        search_queries = (pstats["live_a"] + pstats["live_b"]) if pstats else n
+        search_bytes = search_lines128 * LINE_BYTES * (n / denom) + one_blocks * BLOCK_BYTES * (n / denom) + search_queries * (packed_q + 8)
+        one_request = bool(pstats and pstats["final_lines"] > 0)
+        if one_request:
+            answered = n - pstats["live_a"] - pstats["live_b"]
+            pack_bytes = n * (k + table_hit_bytes) + pstats["final_lines"] * LINE_BYTES + answered * 8 + (pstats["live_a"] + pstats["live_b"]) * packed_q
+            pack_lines = pstats["final_lines"]
+            pack_kernel = "pack_seed_final_kernel (pack + suffix-table entry + ONE final-step line per 31-mer)"
+        else:
+            pack_bytes = n * (k + table_hits_q * table_hit_bytes) + search_queries * packed_q + (n - search_queries) * 8
+            pack_lines = 0
+            pack_kernel = "pack_seed_kernel"
+        search_kernel = ("count_kmers_oct_kernel<RAW> (fused: pack + table + search)" if fused else "count_kmers_oct_kernel" if octi
+                         else "count_kmers_quad_kernel" if quad else ("count_kmers_pair_kernel" if pair else "count_kmers_packed_kernel"))
+        if fused:   # the fused kernel reads the k symbol bytes itself and one 16-byte piece of the (L2-resident) table level
+            search_bytes = search_lines128 * LINE_BYTES * (n / denom) + one_blocks * BLOCK_BYTES * (n / denom) + n * (16 + k + 8)
+        dominant_is_pack = one_request and pack_s >= search_s
+        dom_bytes, dom_s, dom_kernel = (pack_bytes, pack_s, pack_kernel) if dominant_is_pack else (search_bytes, search_s, search_kernel)
+        achieved = dom_bytes / dom_s / 1e9
+        hbm_requests = pack_lines + (search_lines128 + one_blocks) * (n / denom)   # line fills a step asks HBM for (table entries come from L2)
+        if table_hit_bytes == LINE_BYTES:
+            hbm_requests += table_hits_q * n
+        traffic, traffic_src = ncu_traffic(cfg["key"], dom_kernel.split(" ")[0])
         res["roofline"] = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "traffic_source": traffic_src,
-            "kernel": "count_kmers_oct_kernel<RAW> (fused: pack + table + search)" if fused else "count_kmers_oct_kernel" if bwt.oct_index else "count_kmers_quad_kernel" if quad else ("count_kmers_pair_kernel" if pair else "count_kmers_packed_kernel"),
-            "fused": bool(fused), "kernel_ms": 1e3 * kern_s, "algorithmic_bytes_per_launch": bytes_per_query * n,
-            "algorithmic_bytes_per_query": bytes_per_query, "mean_steps_per_query": ref_steps / ms,
-            "oct_lines_per_query": oct_lines / ms, "final_step_lines_per_query": final_lines / ms,
-            "oct_overflow_lines": bwt.oct_overflow_lines,
-            "oct_overflow_position_share": bwt.oct_overflow_occurrences / max(1, total), "oct_bucket_shift": bwt.oct_bucket_shift, "oct_symbols_per_line": M.oct_symbols(),
-            "quad_lines_per_query": quad_lines / ms, "quad_sectors_per_query": quad_sectors / ms,
-            "achieved_sector_granular": sector_bytes_per_query * n / kern_s / 1e9,
-            "pair_lines_per_query": pair_lines / ms, "one_step_blocks_per_query": one_blocks / ms,
-            "two_block_step_share": two_share, "suffix_table_s": table_s,
-            "table_hits_per_query": hits / ms, "index_accesses_per_query": accesses_per_query,
-            "index_accesses_per_s": accesses_per_query * n / kern_s,
-            "no_table": {"algorithmic_bytes_per_query": bytes_per_query_no_table,
-                         "mean_steps_per_query": steps0 / ms,
-                         "achieved_if_counted_without_table": bytes_per_query_no_table * n / kern_s / 1e9},
-            "step": {"what": "pack/seed kernel + search kernel (value's timed region): index lines + one suffix-table line per "
-                             "lookup + query bytes in + packed query out and in + result",
-                     "index_accesses_per_query": accesses_per_query + hits / ms,
-                     "index_accesses_per_s": (accesses_per_query + hits / ms) * n / (statistics.mean(step_ms) / 1e3),
-                     "achieved": (index_bytes_q + hits / ms * table_hit_bytes + k + 2 * packed_q + 8) * n / (statistics.mean(step_ms) / 1e3) / 1e9,
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": dom_kernel,
+            "fused": bool(fused), "kernel_ms": 1e3 * dom_s, "algorithmic_bytes_per_launch": dom_bytes,
+            "algorithmic_bytes_per_query": dom_bytes / n,
+            "one_request_path": one_request, "pack_stage": pstats,
+            "kernels": {"pack": {"kernel": pack_kernel, "ms": 1e3 * pack_s, "algorithmic_bytes": pack_bytes,
+                                 "achieved": pack_bytes / max(pack_s, 1e-9) / 1e9, "hbm_line_requests": pack_lines},
+                        "search": {"kernel": search_kernel, "ms": 1e3 * search_s, "algorithmic_bytes": search_bytes,
+                                   "achieved": search_bytes / max(search_s, 1e-9) / 1e9, "queries": search_queries,
+                                   "oct_lines": oct_lines * (n / denom), "final_step_lines": final_lines * (n / denom),
+                                   "final_step_overflowed": final_overflowed * (n / denom), "quad_lines": quad_lines * (n / denom),
+                                   "pair_lines": pair_lines * (n / denom), "one_step_blocks": one_blocks * (n / denom),
+                                   "mean_reference_steps_per_query": ref_steps / max(1, denom), "accounting_source": source}},
+            "hbm_line_requests_per_query": hbm_requests / n,
+            "index_accesses_per_query": hbm_requests / n,
+            "index_accesses_per_s": hbm_requests / step_s,
+            "no_table": {"algorithmic_bytes_per_query": bytes_per_query_no_table, "mean_steps_per_query": steps0 / mo,
+                         "achieved_if_counted_without_table": bytes_per_query_no_table * n / step_s / 1e9},
+            "step": {"what": "pack/seed kernel + search kernel = value's timed region",
+                     "ms": 1e3 * step_s, "algorithmic_bytes": pack_bytes + search_bytes,
+                     "achieved": (pack_bytes + search_bytes) / step_s / 1e9, "frac": (pack_bytes + search_bytes) / step_s / 1e9 / peak,
                      "suffix_table_depth_used": depth, "suffix_table_level_bytes": table_level_bytes,
-                     "hbm_requests_per_query": accesses_per_query + (hits / ms if table_hit_bytes == LINE_BYTES else 0.0)},
-            "note": ("achieved counts every index line as a 128-B HBM line fill; where part of the image stays in L2 "
-                     "(oct image of the 151 Msym index: 300 MB against 126 MB of L2) the kernel runs above the HBM "
-                     "random-request rate and frac can exceed what DRAM alone would allow -- `traffic` is the DRAM side"),
-            "peak_source": peak_src, "stats_sample": f"first {ms} of {n} queries (oracle replay)"}
+                     "hbm_line_requests_per_s": hbm_requests / step_s},
+            "note": ("achieved counts every index line as a 128-B HBM line fill; where part of an image stays in L2 "
+                     "the kernel runs above the HBM random-request rate and frac can exceed what DRAM alone would allow -- "
+                     "`traffic` is the DRAM side.  The physical ceiling of this path is the random-read REQUEST rate "
+                     "(gather_reads_per_s, K4 in the same run), not the copy bandwidth `peak`: see frac_of_gather128_request_rate"),
+            "peak_source": peak_src}
         res["kernel_share_of_step"] = statistics.mean(kern_ms) / statistics.mean(step_ms)
-    del bwt, d_packed, d_out, queries, q_pinned, out_pinned
+    del queries, queries_all
     torch.cuda.empty_cache()
     return res
 
@@ -517,7 +707,36 @@ def gather_roofline(local, dev):
     return res
 
 
-def run_ours(args, cfgs):
+def host_memory_bandwidth():
+    """What the end-to-end path is bound by on the host side: one large memcpy per thread count (numpy releases the
+    GIL), GB/s of bytes read + written."""
+    import threading
+
+    import numpy as np
+    out = {}
+    try:
+        cores = os.cpu_count() or 1
+        size = 256 << 20
+        for th in sorted({1, min(8, cores), cores}):
+            src = [np.ones(size, dtype=np.uint8) for _ in range(th)]
+            dst = [np.empty(size, dtype=np.uint8) for _ in range(th)]
+            def work(i):
+                np.copyto(dst[i], src[i])
+            for rep in range(2):
+                ts = [threading.Thread(target=work, args=(i,)) for i in range(th)]
+                t0 = time.perf_counter()
+                for t in ts:
+                    t.start()
+                for t in ts:
+                    t.join()
+                dt = time.perf_counter() - t0
+            out[str(th)] = 2 * size * th / dt / 1e9
+    except Exception as e:  # measurement aid only
+        out["error"] = str(e)
+    return out
+
+
+def run_ours(args, cfg_keys):
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -528,6 +747,7 @@ def run_ours(args, cfgs):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     dist = None
+    gloo = None
     if world > 1:
         import torch.distributed as dist
         # NCCL prints its version banner on stdout at first use; stdout carries only the JSON line
@@ -537,6 +757,7 @@ def run_ours(args, cfgs):
             dist.init_process_group("nccl", device_id=dev)
             dist.barrier()
             torch.cuda.synchronize()
+            gloo = dist.new_group(backend="gloo")
         finally:
             sys.stdout.flush()
             os.dup2(saved, 1)
@@ -548,6 +769,11 @@ def run_ours(args, cfgs):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def host_barrier():   # CPU-side only: the waiting ranks leave their GPUs idle
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(group=gloo)
+
     def max_over_ranks(x: float) -> float:
         if dist is None:
             return x
@@ -555,7 +781,9 @@ def run_ours(args, cfgs):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ctx = dict(rank=rank, world=world, local=local, dev=dev, barrier=barrier, max_over_ranks=max_over_ranks)
+    ctx = dict(rank=rank, world=world, local=local, dev=dev, barrier=barrier, max_over_ranks=max_over_ranks,
+               host_barrier=host_barrier)
+    cfgs = [WORKLOADS[key] for key in cfg_keys]
     main_res = measure_ours(args, cfgs[0], ctx, primary=True)
     others = [measure_ours(args, c, ctx, primary=False) for c in cfgs[1:]]
     if rank == 0:
@@ -569,19 +797,28 @@ def run_ours(args, cfgs):
             if rf and gather:
                 rf["gather_gbs"] = {g: v["gb_per_s"] for g, v in gather.items()}
                 rf["gather_reads_per_s"] = {g: v["reads_per_s"] for g, v in gather.items()}
-                rf["frac_of_gather64_access_rate"] = rf["index_accesses_per_s"] / gather["64"]["reads_per_s"]
+                rf["frac_of_gather128_request_rate"] = rf["index_accesses_per_s"] / gather["128"]["reads_per_s"]
+                for kn in ("pack", "search"):
+                    kk = rf["kernels"][kn]
+                    if kn == "pack":
+                        kk["line_requests_per_s"] = kk["hbm_line_requests"] / max(kk["ms"] / 1e3, 1e-9)
+                    else:
+                        kk["line_requests_per_s"] = (kk["oct_lines"] + kk["final_step_lines"] + kk["quad_lines"] + kk["pair_lines"] + kk["one_step_blocks"]) / max(kk["ms"] / 1e3, 1e-9)
+                    kk["frac_of_gather128_request_rate"] = kk["line_requests_per_s"] / gather["128"]["reads_per_s"]
         line = {
             "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "scaling": cfgs[0]["scaling"], "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         }
-        for key in ("config", "e2e", "e2e_pileup", "gpu_launches", "clocks", "roofline", "cpu_baseline", "wall_s_timed_region",
-                    "checksum", "kernel_share_of_step"):
+        for key in ("config", "engine", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "parity",
+                    "wall_s_timed_region", "checksum", "kernel_share_of_step"):
             line[key] = main_res.get(key)
+        line["host_memory_gbs_by_threads"] = host_memory_bandwidth()
         if others:
             line["other_workloads"] = [
-                {key: r.get(key) for key in ("value", "ms_per_step", "config", "e2e", "e2e_pileup", "gpu_launches", "roofline",
-                                             "cpu_baseline", "checksum")} for r in others]
+                {key: r.get(key) for key in ("value", "ms_per_step", "config", "engine", "e2e", "gpu_launches", "roofline",
+                                             "cpu_baseline", "parity", "checksum")} | {"scaling": c["scaling"]}
+                for r, c in zip(others, cfgs[1:])]
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -596,15 +833,24 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["default"],
                     default=os.environ.get("MSBWT_BENCH_WORKLOAD", "default"),
-                    help="default = configs[1] as the bench line, configs[2] (HBM-resident index) nested beside it")
+                    help="default = configs[2] as the bench line; configs[1] (N = 1) and configs[4] (N = 1 and 8) nested beside it")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)
-    cfgs = [WORKLOADS["cfg2"], WORKLOADS["cfg3"]] if args.workload == "default" else [WORKLOADS[args.workload]]
-    if args.impl == "reference":
-        run_reference(args, cfgs)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "default":
+        keys = [HEADLINE]
+        if args.impl == "ours":
+            if world == 1:
+                keys.append("cfg2")
+            if world in (1, 8) and os.environ.get("MSBWT_BENCH_SKIP_CFG5", "0") in ("", "0"):
+                keys.append("cfg5")
     else:
-        run_ours(args, cfgs)
+        keys = [args.workload]
+    if args.impl == "reference":
+        run_reference(args, [WORKLOADS[key] for key in keys])
+    else:
+        run_ours(args, keys)
 
 
 if __name__ == "__main__":

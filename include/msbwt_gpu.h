@@ -218,7 +218,9 @@ int msbwt_constrain_ranges_device(const msbwt_index *idx, int slot, const uint8_
 /* The two stages of msbwt_count_kmers_fixed_device as separate calls, for callers that want to
  * time or overlap them (n <= 2^30 per pair; d_packed = msbwt_packed_bytes(idx,k,n) bytes of device
  * scratch, opaque):
- *   pack : validates the n*k symbol bytes, looks each k-mer's last symbols up in the suffix table,
+ *   pack : validates the n*k symbol bytes, looks each k-mer's last symbols up in the suffix table -- and, when the
+ *          index has a final-step image and the k-mer is a table entry + exactly 20 symbols (k = 31, 32), answers
+ *          it right there from ONE 128-byte line (pack_seed_final_kernel) --,
  *          packs the remaining symbols 3 bits each (the k-mer's LAST symbol first, because backward
  *          search consumes it first), writes d_out[q] directly for k-mers that need no further
  *          search step (e.g. the table says "absent") and appends the rest to a compacted list;
@@ -229,6 +231,11 @@ int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const uint8_t *d_s
                             void *stream);
 int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot, const uint64_t *d_packed,
                                     uint32_t k, uint64_t n, uint64_t *d_out, void *stream);
+/* Measurement aid: what the last msbwt_pack_kmers_device on this scratch left for the search (out6[0] live list A,
+ * [1] live list B) and what its one-request path did ([2] final-step lines fetched, [3] of which had overflowed,
+ * [4] ranges over two buckets, [5] k-mers the suffix table answered with an empty range).  Synchronises the device. */
+int msbwt_debug_pack_stats(const msbwt_index *idx, int slot, const uint64_t *d_packed, uint32_t k, uint64_t n,
+                           uint64_t *out6);
 /* Measurement aid (bench.py's roofline accounting): the search over the oct image with a counting build of the
  * kernel.  d_stats = 8 u64 on the device: oct lines fetched, final-step lines fetched, of which had overflowed,
  * quad steps, distinct 128-byte lines those read, one-symbol steps, distinct 64-byte blocks those read, queries

@@ -735,6 +735,24 @@ extern "C" int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot,
     return MSBWT_OK;
 }
 
+// Measurement aid: what the last msbwt_pack_kmers_device call on this scratch left for the search kernels and what
+// its one-request path did (synchronises the device).  out[0] = live list A, [1] = live list B, [2] = final-step
+// lines fetched by the pack stage, [3] = of which had overflowed, [4] = ranges over two buckets, [5] = k-mers the
+// suffix table already answered with an empty range ([2..5] are zero when the one-request path did not apply).
+extern "C" int msbwt_debug_pack_stats(const msbwt_index *idx, int slot, const uint64_t *d_packed, uint32_t k, uint64_t n,
+                                      uint64_t *out6) {
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size() || !d_packed || !out6) return fail(MSBWT_EINVAL, "bad handle, slot or buffer");
+    Replica &rep = *idx->reps[slot];
+    DeviceGuard guard(rep.device);
+    const PackedLayout lay = packed_layout(rep.view, k, n);
+    uint64_t tmp[8];
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(tmp, d_packed + lay.live(), sizeof(tmp), cudaMemcpyDeviceToHost));
+    out6[0] = tmp[0]; out6[1] = tmp[1];
+    for (int i = 0; i < 4; i++) out6[2 + i] = tmp[4 + i];
+    return MSBWT_OK;
+}
+
 // Measurement aid: msbwt_count_kmers_packed_device over list A with the counting instantiation of the oct kernel
 // (stats_kernels.cu).  d_stats: 8 u64 on the device -- oct lines, final-step lines, of which overflowed, quad steps,
 // 128-byte lines those read, one-symbol steps, 64-byte blocks those read, queries walked.  EINVAL without an oct image.

@@ -142,6 +142,9 @@ bool index_is_wide(const IndexView &ix);
 //   [.., + (words-1)*n)         WX    symbol words 1.. of query q, word-major, by ORIGINAL index
 //   [.., + 2)                   LIVE  number of live queries in list A, list B (u64 counters)
 //   [.., + 2)                   WORK  the oct kernel's chunk dispenser over list A (u32 counter; + padding)
+//   [.., + 4)                   FSTAT counters of pack_seed_final_kernel (final_kernels.cu): final-step lines fetched,
+//                                     of which had overflowed, ranges over two buckets, k-mers the suffix table
+//                                     already answered (empty range)
 // Queries that need no search step (empty seed range, or the suffix table answered every symbol)
 // are finished by the pack kernel itself and never reach the search kernels.
 constexpr uint32_t kQidxMask = (1u << 30) - 1u;
@@ -154,7 +157,8 @@ struct PackedLayout {
     __host__ __device__ uint64_t wx() const { return qidx() + (n + 1) / 2; }
     __host__ __device__ uint64_t live() const { return wx() + (uint64_t)(words - 1) * n; }
     __host__ __device__ uint64_t work() const { return live() + 2; }
-    __host__ __device__ uint64_t total() const { return live() + 4; }
+    __host__ __device__ uint64_t fstat() const { return live() + 4; }
+    __host__ __device__ uint64_t total() const { return live() + 8; }
 };
 inline PackedLayout packed_layout(const IndexView &ix, uint32_t k, uint64_t n) {
     return PackedLayout{n, words_for_k(k), index_is_wide(ix) ? 2u : 1u};
@@ -170,6 +174,14 @@ cudaError_t launch_seed_packed(const IndexView &ix, const uint64_t *d_words, uin
 // caller-packed batches, k <= 32: kmers[q] = the k-mer as a 2k-bit integer, first symbol most significant -> live list A
 cudaError_t launch_seed_u64(const IndexView &ix, const uint64_t *d_kmers, uint32_t k, uint64_t n,
                             uint64_t *d_packed, uint64_t *d_out, cudaStream_t st);
+// final_kernels.cu: the one-request path of k-mers that are a suffix-table entry + exactly kFinSyms symbols
+// (k = 31 / 32 with table levels 11 / 12): pack (or take the packed word), seed and answer from ONE final-step line
+// in one regular kernel; what it cannot answer (range over two buckets, overflowed line, `$` / `N`) goes to the live
+// lists for launch_count_packed.  `src_kind`: 0 = symbol bytes (n * k, 16-byte aligned), 1 = caller-packed integers
+// (msbwt_count_kmers_u64's format), 2 = host-packed words (word 0 of hostpack.cpp's format).
+bool final_fast_path_applies(const IndexView &ix, uint32_t k, const void *d_src, int src_kind);
+cudaError_t launch_pack_seed_final(int device, const IndexView &ix, const void *d_src, int src_kind, uint32_t k, uint64_t n,
+                                   uint64_t *d_packed, uint64_t *d_out, uint32_t *d_status, cudaStream_t st);
 // quad_kernels.cu: live list A over the quad (and oct) image
 cudaError_t launch_count_quad(int device, const IndexView &ix, const uint64_t *d_packed, const PackedLayout &lay,
                               uint32_t k, uint64_t *d_out, cudaStream_t st);

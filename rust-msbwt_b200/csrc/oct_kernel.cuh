@@ -265,7 +265,9 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                     } else {
                         word = *reinterpret_cast<const volatile uint64_t *>(p + 8u * slot);
                         const uint64_t lo = *reinterpret_cast<const volatile uint64_t *>(p + 256u + 8u * slot);
-                        q = *reinterpret_cast<const volatile uint32_t *>(p + 512u + 4u * slot) & kQidxMask;
+                        const uint32_t qraw = *reinterpret_cast<const volatile uint32_t *>(p + 512u + 4u * slot);
+                        q = qraw & kQidxMask;
+                        no_fin = ((qraw >> 30) & 1u) != 0u;  // pack_seed_final_kernel already found this query's line overflowed
                         l = (uint32_t)lo;
                         h = (uint32_t)(lo >> 32);
                         rem = rem0;

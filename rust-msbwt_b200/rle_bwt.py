@@ -144,6 +144,7 @@ def load_library():
         "msbwt_pack_kmers_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp, vp]),
         "msbwt_count_kmers_packed_device": (i32, [vp, i32, vp, u32, u64, vp, vp]),
         "msbwt_count_kmers_packed_stats_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
+        "msbwt_debug_pack_stats": (i32, [vp, i32, vp, u32, u64, vp]),
         "msbwt_launch_count": (u64, []),
         "msbwt_gather_bench": (i32, [i32, vp, u64, u32, u64, u64, vp, vp]),
         "msbwt_l2_fetch_granularity": (i32, [i32, i32]),
@@ -165,7 +166,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
-    "msbwt_index_create_from_npy_opts", "msbwt_count_kmers_packed_stats_device", "msbwt_count_kmers_fixed_u32", "msbwt_count_kmers_u64_u32",
+    "msbwt_index_create_from_npy_opts", "msbwt_count_kmers_packed_stats_device", "msbwt_debug_pack_stats", "msbwt_count_kmers_fixed_u32", "msbwt_count_kmers_u64_u32",
     "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_oct_index", "msbwt_oct_overflow_lines",
     "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift", "msbwt_oct_symbols", "msbwt_table_depth_for_k", "msbwt_debug_table_depth", "msbwt_count_kmers_u64", "msbwt_final_index", "msbwt_debug_copy_final_image",
     "msbwt_debug_copy_oct_image", "msbwt_constrain_ranges_fanout", "msbwt_constrain_ranges_fanout_device",
@@ -426,6 +427,13 @@ class RleBWT:
                                   slot: int = 0) -> None:
         _check(load_library().msbwt_count_kmers_packed_device(self.handle, slot, d_packed, k, n, d_out,
                                                               stream or None), "count_kmers_packed_device")
+
+    def pack_stats(self, d_packed: int, k: int, n: int, slot: int = 0) -> dict:
+        """what the last pack_kmers_device call on this scratch left for the search and what its one-request path did"""
+        out = np.zeros(6, dtype=np.uint64)
+        _check(load_library().msbwt_debug_pack_stats(self.handle, slot, d_packed, k, n, _p(out)), "debug_pack_stats")
+        keys = ("live_a", "live_b", "final_lines", "final_overflowed", "two_buckets", "table_empty")
+        return dict(zip(keys, (int(v) for v in out)))
 
     def count_kmers_packed_stats_device(self, d_packed: int, k: int, n: int, d_out: int, d_stats: int, stream: int = 0,
                                         slot: int = 0) -> None:

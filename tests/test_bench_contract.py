@@ -27,7 +27,7 @@ def test_reference_arm_line_has_the_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference"
     assert d["metric"] == "count_kmer_31mer_queries_per_sec" and d["unit"] == "queries/s"
-    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["vs_baseline"] is None
     assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
     assert d["dtype"] == "u64" and d["data"] == "synthetic" and d["gpu_launches"] == 0
     assert d["value"] > 0 and d["ms_per_step"] > 0
