@@ -321,10 +321,27 @@ int msbwt_debug_host_pack(const uint8_t *syms, uint32_t k, uint64_t n, int threa
  * insertion (src/bin/msbwt2-build.rs:19-114, src/dynamic_bwt.rs:305-381), i.e. naive_bwt's order
  * (src/bwt_util.rs:154-171).  `reads` is host memory, or device memory on `device` when reads_on_device != 0.
  * *rle is a buffer of *rle_len bytes owned by the caller: release it with msbwt_buffer_free.
- * *total = n_reads * (read_len + 1).  Equal-length reads only. */
+ * *total = n_reads * (read_len + 1). */
 int msbwt_build_rle_bwt(const uint8_t *reads, uint64_t n_reads, uint32_t read_len, int reads_on_device,
                         int device, uint8_t **rle, uint64_t *rle_len, uint64_t *total);
+/* The same for reads of ANY lengths (create_from_fastx takes them as they come, src/dynamic_bwt.rs:453-473): read r is
+ * syms[offsets[r] .. offsets[r+1]) (host memory, n_reads + 1 offsets; an empty read contributes its `$` alone).
+ * Order = naive_bwt's (src/bwt_util.rs:154-171): a suffix that ends sooner sorts first (`$` is the smallest symbol),
+ * equal suffixes by the lexicographic rank of their whole reads.  *total = sum of (length + 1). */
+int msbwt_build_rle_bwt_ragged(const uint8_t *syms, const uint64_t *offsets, uint64_t n_reads, int device,
+                               uint8_t **rle, uint64_t *rle_len, uint64_t *total);
 void msbwt_buffer_free(uint8_t *p);
+
+/* ---- the data format either side of the path: src/bwt_converter.rs ----
+ * convert_to_vec (:26-80): a text BWT over `$ACGNT` (newlines are skipped and do not end a run) -> msbwt RLE bytes
+ * (malloc'd: release with msbwt_buffer_free).  Any other byte -> MSBWT_EFORMAT (the reference panics, :43-46). */
+int msbwt_convert_to_rle(const uint8_t *text, uint64_t n, uint8_t **rle, uint64_t *rle_len);
+/* save_bwt_numpy (:102-130): the 96-byte npy-v1 header msbwt2 writes -- `{'descr': '|u1', 'fortran_order': False,
+ * 'shape': (<len>, ), }` padded with spaces, newline-terminated -- followed by the RLE bytes, byte for byte what the
+ * reference writes and what msbwt_index_create_from_npy / load_numpy_file read.  MSBWT_EIO on any file error. */
+int msbwt_save_rle_npy(const uint8_t *rle, uint64_t len, const char *path);
+/* save_bwt_runs_numpy (:152-184): the same container from (symbol, count) runs; a zero count writes nothing */
+int msbwt_save_runs_npy(const uint8_t *syms, const uint64_t *counts, uint64_t nruns, const char *path);
 
 /* ---- pinned host buffers for callers that want full copy/compute overlap ---- */
 void *msbwt_host_alloc(size_t bytes);

@@ -11,10 +11,14 @@ of that name at the repo root loads this package).
 from .rle_bwt import (  # noqa: F401
     BWTRange,
     build_rle_bwt,
+    build_rle_bwt_ragged,
     MsbwtError,
     RleBWT,
     convert_itos,
     convert_stoi,
+    convert_to_vec,
+    save_bwt_numpy,
+    save_bwt_runs_numpy,
     debug_build_image,
     debug_host_pack,
     gather_bench,

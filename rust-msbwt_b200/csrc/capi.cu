@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "handle.h"
 #include "kernel_common.cuh"
@@ -20,6 +21,7 @@ namespace msbwt {
 thread_local std::string g_last_error;
 thread_local int g_call_launches = 0;
 std::atomic<uint64_t> g_launches{0};
+int codec_fail(int code, const std::string &msg) { return fail(code, msg); }  // codec.cpp reports through the same thread-local
 }  // namespace msbwt
 
 namespace {
@@ -42,7 +44,31 @@ int resolve_devices(const int *devices, int ndev, std::vector<int> &devs) {
     return MSBWT_OK;
 }
 
-int finish_replica(msbwt_index *idx, std::unique_ptr<Replica> rep, uint64_t total, uint64_t nblocks, uint32_t n_super,
+// Runs body(i) for i in [0, n): on the calling thread when n == 1, else one thread per replica (every replica lives on
+// its own device, so the builds of a multi-GPU handle overlap).  A thread's failure text (thread-local) is carried back
+// to the caller; the first failure by slot order is returned.
+template <class F>
+int for_each_replica_slot(size_t n, F &&body) {
+    std::vector<int> rc(n, MSBWT_OK);
+    std::vector<std::string> err(n);
+    auto run = [&](size_t i) {
+        rc[i] = body(i);
+        if (rc[i] != MSBWT_OK) err[i] = g_last_error;
+    };
+    if (n == 1) {
+        run(0);
+    } else {
+        std::vector<std::thread> workers;
+        for (size_t i = 1; i < n; i++) workers.emplace_back(run, i);
+        run(0);
+        for (auto &w : workers) w.join();
+    }
+    for (size_t i = 0; i < n; i++)
+        if (rc[i] != MSBWT_OK) return fail(rc[i], err[i]);
+    return MSBWT_OK;
+}
+
+int finish_replica(msbwt_index *idx, size_t slot, std::unique_ptr<Replica> rep, uint64_t total, uint64_t nblocks, uint32_t n_super,
                    uint32_t sb_shift) {
     CU_TRY(cudaMalloc((void **)&rep->d_status, kStatusWords * sizeof(uint32_t)));
     CU_TRY(cudaMemset(rep->d_status, 0, kStatusWords * sizeof(uint32_t)));
@@ -59,8 +85,8 @@ int finish_replica(msbwt_index *idx, std::unique_ptr<Replica> rep, uint64_t tota
     rep->view.nblocks = nblocks;
     rep->view.n_super = n_super;
     rep->view.sb_shift = sb_shift;
-    idx->bytes_per_replica = nblocks * kBlockBytes + nblocks * 2 * sizeof(uint32_t) + (uint64_t)n_super * 8 * sizeof(uint64_t);
-    idx->reps.push_back(std::move(rep));
+    if (slot == 0) idx->bytes_per_replica = nblocks * kBlockBytes + nblocks * 2 * sizeof(uint32_t) + (uint64_t)n_super * 8 * sizeof(uint64_t);
+    idx->reps[slot] = std::move(rep);
     return MSBWT_OK;
 }
 
@@ -69,23 +95,26 @@ int build_replicas_on_device(msbwt_index *idx, const uint8_t *rle, uint64_t len,
                              int ndev) {
     std::vector<int> devs;
     if (int rc = resolve_devices(devices, ndev, devs); rc != MSBWT_OK) return rc;
-    for (int d : devs) {
-        DeviceGuard guard(d);
+    idx->reps.resize(devs.size());
+    int rc = for_each_replica_slot(devs.size(), [&](size_t i) -> int {
+        DeviceGuard guard(devs[i]);
         DeviceImage img;
         std::string why;
-        int rc = build_image_on_device(rle, len, sb_shift, img, why);
-        if (rc != MSBWT_OK) { free_device_image(img); return fail(rc, why); }
+        int r = build_image_on_device(rle, len, sb_shift, img, why);
+        if (r != MSBWT_OK) { free_device_image(img); return fail(r, why); }
         auto rep = std::make_unique<Replica>();
-        rep->device = d;
+        rep->device = devs[i];
         rep->d_blocks = img.blocks;
         rep->d_aux = img.aux;
         rep->d_cbase = img.cbase;
-        idx->total = img.total;
-        for (int s = 0; s < kAlphabet; s++) { idx->counts[s] = img.counts[s]; idx->start[s] = img.start[s]; }
-        rc = finish_replica(idx, std::move(rep), img.total, img.nblocks, img.n_super, img.sb_shift);
-        if (rc != MSBWT_OK) return rc;
-    }
-    return MSBWT_OK;
+        if (i == 0) {
+            idx->total = img.total;
+            for (int s = 0; s < kAlphabet; s++) { idx->counts[s] = img.counts[s]; idx->start[s] = img.start[s]; }
+        }
+        return finish_replica(idx, i, std::move(rep), img.total, img.nblocks, img.n_super, img.sb_shift);
+    });
+    if (rc != MSBWT_OK) idx->reps.clear();
+    return rc;
 }
 
 // MSBWT_HOST_BUILD=1: build the image with the serial host builder (loader.cu) and copy it up.
@@ -97,7 +126,9 @@ int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev)
     const size_t block_bytes = img.blocks.size() * sizeof(uint32_t);
     const size_t cbase_bytes = img.cbase.size() * sizeof(uint64_t);
     const size_t aux_bytes = img.aux.size() * sizeof(uint32_t);
-    for (int d : devs) {
+    idx->reps.resize(devs.size());
+    for (size_t slot = 0; slot < devs.size(); slot++) {
+        const int d = devs[slot];
         DeviceGuard guard(d);
         auto rep = std::make_unique<Replica>();
         rep->device = d;
@@ -107,8 +138,8 @@ int upload(msbwt_index *idx, const HostImage &img, const int *devices, int ndev)
         CU_TRY(cudaMemcpy(rep->d_aux, img.aux.data(), aux_bytes, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(rep->d_blocks, img.blocks.data(), block_bytes, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(rep->d_cbase, img.cbase.data(), cbase_bytes, cudaMemcpyHostToDevice));
-        int rc = finish_replica(idx, std::move(rep), img.total, img.nblocks, img.n_super, img.sb_shift);
-        if (rc != MSBWT_OK) return rc;
+        int rc = finish_replica(idx, slot, std::move(rep), img.total, img.nblocks, img.n_super, img.sb_shift);
+        if (rc != MSBWT_OK) { idx->reps.clear(); return rc; }
     }
     return MSBWT_OK;
 }
@@ -435,7 +466,7 @@ int build_suffix_table(msbwt_index *idx, Replica &rep, int s) {
         bytes += (1ull << (2 * j)) * eb;
     }
     rep.view.table_s = (uint32_t)s;
-    idx->table_s = (uint32_t)s;
+    if (idx->reps[0].get() == &rep) idx->table_s = (uint32_t)s;
     if (idx->reps[0].get() == &rep) idx->bytes_per_replica += bytes;
     return MSBWT_OK;
 }
@@ -464,7 +495,8 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
         const int s0 = pick_table_s(idx->total, table_s, &explicit_s);
         const bool wide = index_is_wide(idx->reps[0]->view);
         const uint64_t one_step_bytes = idx->bytes_per_replica + (s0 > 0 ? (1ull << (2 * s0)) * (wide ? 16 : 8) : 0);
-        for (auto &rep : idx->reps) {
+        rc = for_each_replica_slot(idx->reps.size(), [&](size_t slot) -> int {
+            auto &rep = idx->reps[slot];
             int s = s0;
             bool quad;
             {
@@ -475,7 +507,7 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
                 quad = opt.oct == 1 || pick_quad(rep->device, one_step_bytes, idx->total, opt.quad, opt.pair, with_oct);
             }
             if (quad || pick_pair(rep->device, one_step_bytes, opt.pair)) {
-                if ((rc = quad ? build_multi_step(idx.get(), *rep, opt) : build_pair(idx.get(), *rep)) != MSBWT_OK) break;
+                if (int r = quad ? build_multi_step(idx.get(), *rep, opt) : build_pair(idx.get(), *rep); r != MSBWT_OK) return r;
                 if (!explicit_s && (quad || lives_in_hbm(rep->device, one_step_bytes))) {
                     DeviceGuard guard(rep->device);
                     const uint64_t multi = quad ? quad_image_bytes(idx->total) : rep->view.npair * kPairBytes;
@@ -485,10 +517,10 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
                     if (rep->view.oct) s = std::min(s, kOctAutoTableS);
                 }
             }
-            rc = build_suffix_table(idx.get(), *rep, s);
-            if (rc != MSBWT_OK) break;
+            if (int r = build_suffix_table(idx.get(), *rep, s); r != MSBWT_OK) return r;
             rep->lanes = pick_lanes(rep->device, one_step_bytes, opt.lanes);
-        }
+            return MSBWT_OK;
+        });
     }
     if (err) *err = rc;
     if (rc != MSBWT_OK) return nullptr;
@@ -906,6 +938,51 @@ extern "C" int msbwt_constrain_ranges_fanout_device(const msbwt_index *idx, int 
 
 // ================================================================ construction of the BWT itself
 
+namespace {
+// reads (and, for reads of different lengths, their n_reads + 1 offsets) on the host or already on `device` ->
+// RLE bytes of their multi-string BWT in a malloc'd host buffer
+int build_rle_bwt_common(const uint8_t *reads, const uint64_t *offsets, uint64_t n_reads, uint32_t read_len, uint64_t n_syms,
+                         int on_device, int device, uint8_t **rle, uint64_t *rle_len, uint64_t *total) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(MSBWT_ENODEV, "no usable CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= count) return fail(MSBWT_ENODEV, "device ordinal out of range");
+    DeviceGuard guard(device);
+    struct DevPtr { void *p = nullptr; ~DevPtr() { if (p) cudaFree(p); } };
+    DevPtr reads_copy, offsets_copy, d_rle_owner;
+    const uint8_t *d_reads = reads;
+    const uint64_t *d_offsets = offsets;
+    if (!on_device && n_reads) {
+        if (n_syms) {
+            CU_TRY(cudaMalloc(&reads_copy.p, n_syms));
+            CU_TRY(cudaMemcpy(reads_copy.p, reads, n_syms, cudaMemcpyHostToDevice));
+        }
+        d_reads = (const uint8_t *)reads_copy.p;
+        if (offsets) {
+            CU_TRY(cudaMalloc(&offsets_copy.p, (n_reads + 1) * sizeof(uint64_t)));
+            CU_TRY(cudaMemcpy(offsets_copy.p, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+            d_offsets = (const uint64_t *)offsets_copy.p;
+        }
+    }
+    uint8_t *d_rle = nullptr;
+    std::string why;
+    int n = 0;
+    int rc = build_rle_bwt_on_device(d_reads, d_offsets, n_reads, read_len, &d_rle, rle_len, total, why, &n);
+    g_launches += (uint64_t)n;
+    d_rle_owner.p = d_rle;
+    if (rc != MSBWT_OK) return fail(rc, why);
+    uint8_t *host = (uint8_t *)malloc(*rle_len ? *rle_len : 1);
+    if (!host) return fail(MSBWT_ENOMEM, "host buffer for the RLE bytes");
+    if (*rle_len) {
+        if (cudaError_t e = cudaMemcpy(host, d_rle, *rle_len, cudaMemcpyDeviceToHost); e != cudaSuccess) {
+            free(host);
+            return fail(MSBWT_ECUDA, std::string("copying the RLE bytes: ") + cudaGetErrorString(e));
+        }
+    }
+    *rle = host;
+    return MSBWT_OK;
+}
+}  // namespace
+
 extern "C" int msbwt_build_rle_bwt(const uint8_t *reads, uint64_t n_reads, uint32_t read_len, int reads_on_device,
                                    int device, uint8_t **rle, uint64_t *rle_len, uint64_t *total) {
     g_last_error.clear();
@@ -914,39 +991,33 @@ extern "C" int msbwt_build_rle_bwt(const uint8_t *reads, uint64_t n_reads, uint3
     *rle_len = 0;
     *total = 0;
     if (n_reads && (!reads || !read_len)) return fail(MSBWT_EINVAL, "NULL reads or read_len == 0");
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(MSBWT_ENODEV, "no usable CUDA device (there is no CPU fallback)");
-    if (device < 0 || device >= count) return fail(MSBWT_ENODEV, "device ordinal out of range");
-    DeviceGuard guard(device);
-    const uint8_t *d_reads = reads;
-    uint8_t *d_copy = nullptr;
-    if (!reads_on_device && n_reads) {
-        CU_TRY(cudaMalloc((void **)&d_copy, n_reads * read_len));
-        if (cudaError_t e = cudaMemcpy(d_copy, reads, n_reads * read_len, cudaMemcpyHostToDevice); e != cudaSuccess) {
-            cudaFree(d_copy);
-            return fail(MSBWT_ECUDA, std::string("copying the reads: ") + cudaGetErrorString(e));
-        }
-        d_reads = d_copy;
+    return build_rle_bwt_common(reads, nullptr, n_reads, read_len, n_reads * read_len, reads_on_device, device, rle, rle_len, total);
+}
+
+extern "C" int msbwt_build_rle_bwt_ragged(const uint8_t *syms, const uint64_t *offsets, uint64_t n_reads, int device,
+                                          uint8_t **rle, uint64_t *rle_len, uint64_t *total) {
+    g_last_error.clear();
+    if (!rle || !rle_len || !total) return fail(MSBWT_EINVAL, "NULL output pointer");
+    *rle = nullptr;
+    *rle_len = 0;
+    *total = 0;
+    if (!n_reads) return MSBWT_OK;
+    if (!offsets) return fail(MSBWT_EINVAL, "NULL offsets");
+    uint64_t longest = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        if (offsets[r + 1] < offsets[r]) return fail(MSBWT_EINVAL, "offsets must be non-decreasing");
+        longest = std::max(longest, offsets[r + 1] - offsets[r]);
     }
-    uint8_t *d_rle = nullptr;
-    std::string why;
-    int n = 0;
-    int rc = build_rle_bwt_on_device(d_reads, n_reads, read_len, &d_rle, rle_len, total, why, &n);
-    g_launches += (uint64_t)n;
-    if (d_copy) cudaFree(d_copy);
-    if (rc != MSBWT_OK) return fail(rc, why);
-    uint8_t *host = (uint8_t *)malloc(*rle_len ? *rle_len : 1);
-    if (!host) { cudaFree(d_rle); return fail(MSBWT_ENOMEM, "host buffer for the RLE bytes"); }
-    if (*rle_len) {
-        if (cudaError_t e = cudaMemcpy(host, d_rle, *rle_len, cudaMemcpyDeviceToHost); e != cudaSuccess) {
-            cudaFree(d_rle);
-            free(host);
-            return fail(MSBWT_ECUDA, std::string("copying the RLE bytes: ") + cudaGetErrorString(e));
-        }
-    }
-    if (d_rle) cudaFree(d_rle);
-    *rle = host;
-    return MSBWT_OK;
+    if (longest >= 0xFFFFFFFFull) return fail(MSBWT_EINVAL, "a read is longer than 2^32 - 2 symbols");
+    const uint64_t n_syms = offsets[n_reads] - offsets[0];
+    if (n_syms && !syms) return fail(MSBWT_EINVAL, "NULL symbols");
+    // the kernels index the symbols with the caller's absolute offsets: copy from the first read's first symbol and
+    // bias the device pointer instead of rewriting the offsets
+    if (offsets[0] == 0)
+        return build_rle_bwt_common(syms, offsets, n_reads, (uint32_t)longest, n_syms, 0, device, rle, rle_len, total);
+    std::vector<uint64_t> rebased(offsets, offsets + n_reads + 1);
+    for (auto &o : rebased) o -= offsets[0];
+    return build_rle_bwt_common(syms + offsets[0], rebased.data(), n_reads, (uint32_t)longest, n_syms, 0, device, rle, rle_len, total);
 }
 
 extern "C" void msbwt_buffer_free(uint8_t *p) { free(p); }

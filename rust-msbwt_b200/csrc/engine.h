@@ -115,9 +115,10 @@ int build_fin_lines_on_device(int device, uint64_t total, uint64_t *d_codes20, i
                               std::string &why, int *launches);
 void free_fin_image(FinImage &img);
 
-// ---- bwt_build.cu: equal-length reads (device) -> RLE bytes of their multi-string BWT (device) ----
-int build_rle_bwt_on_device(const uint8_t *d_reads, uint64_t n_reads, uint32_t read_len, uint8_t **d_rle_out,
-                            uint64_t *rle_len, uint64_t *total, std::string &why, int *launches);
+// ---- bwt_build.cu: reads (device) -> RLE bytes of their multi-string BWT (device).  d_offsets == nullptr: n_reads reads
+// of read_len symbols each; otherwise read r = d_reads[d_offsets[r] .. d_offsets[r + 1]) and read_len = the longest ----
+int build_rle_bwt_on_device(const uint8_t *d_reads, const uint64_t *d_offsets, uint64_t n_reads, uint32_t read_len,
+                            uint8_t **d_rle_out, uint64_t *rle_len, uint64_t *total, std::string &why, int *launches);
 
 // return an msbwt_status; on failure `why` explains
 int validate_rle(const uint8_t *rle, uint64_t len, std::string &why);

@@ -16,11 +16,12 @@
 //                    line: one 128-byte request per line)
 //     A  batch i+3 : the batch's 32 k symbol bytes -> byte buffer (i+3) & 1 (coalesced 16-byte cp.async)     } G_i
 //     -- cp.async.wait_group 1: G_{i-1} has landed = the lines of batch i and the bytes of batch i+2
+//     B  batch i+2 : every lane packs its k-mer from the byte buffer (SWAR, four symbols per step), and requests
+//                    its table entry (ld.global.nc: an L2 hit, consumed by C in the next iteration -- D below is
+//                    what hides its latency)
 //     D  batch i   : every lane scans its own line (groups `tag | nruns` + runs, layout.h), writes its count to
 //                    out[32 * batch + lane] (one coalesced 256-byte store per warp), or queues the query for the
 //                    general kernel: overflowed line, range over two buckets
-//     B  batch i+2 : every lane packs its k-mer from the byte buffer (SWAR, four symbols per step), and requests
-//                    its table entry (ld.global.nc: an L2 hit, consumed in the next iteration)
 //
 // What the pipeline cannot answer goes where pack_seed_kernel would have put it, in the same scratch layout
 // (engine.h PackedLayout), for launch_count_packed to finish: live list A (all-ACGT: the remaining 20 symbols + the
@@ -208,9 +209,14 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
         bool to_queue = kind == kKindTwoBuckets;
         uint32_t nofin = 0;
         uint32_t cnt = 0;
+        // Phase 1, per lane: hop from group header to group header (`tag << 4 | nruns`, then nruns run words) and note
+        // where this query's code sits -- a line holds a few groups, so this is a handful of 4-byte shared-memory reads.
+        // A code with more than 15 runs in the bucket has a second group (a 31-mer seen 30 times is ~13 runs of
+        // consecutive positions); a third one is rare enough to leave to the general kernel.
+        const uint32_t *roww = reinterpret_cast<const uint32_t *>(rows + (s & 1u) * (32 * kFinRowBytes) + lane * kFinRowBytes);
+        uint32_t i1 = 0, n1 = 0, i2 = 0, n2 = 0;
         if (kind == kKindLine) {
-            const uint4 *my_row = reinterpret_cast<const uint4 *>(rows + (s & 1u) * (32 * kFinRowBytes) + lane * kFinRowBytes);
-            const uint4 first = my_row[0];
+            const uint2 first = *reinterpret_cast<const uint2 *>(roww);
             const uint32_t used = first.x;
             st_lines++;
             if (used == kFinOverflow) {
@@ -218,33 +224,39 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
                 nofin = 1u;
                 st_over++;
             } else {
-                const int pl = (int)(l & fmask), ph = (int)(h & fmask);
-                int acc = 0;
-                uint32_t left = 0;
-                bool match = false;
-                auto eat = [&](uint32_t w, uint32_t idx) {  // word `idx` of the line: a group header or one of its runs
-                    if (idx > used) return;
-                    if (left == 0u) {
-                        match = (w >> 4) == tag;
-                        left = w & 15u;
-                    } else {
-                        const int off = (int)(w & 0xFFFFu), len = (int)(w >> 16);
-                        if (match) acc += min(max(ph - off, 0), len) - min(max(pl - off, 0), len);
-                        left--;
+                uint32_t hw = first.y, matches = 0;  // word 1: the first header (meaningless when used == 0)
+                for (uint32_t idx = 1u; idx <= used;) {
+                    const uint32_t nr = hw & 15u;
+                    if ((hw >> 4) == tag) {
+                        if (matches == 0u) { i1 = idx; n1 = nr; }
+                        else if (matches == 1u) { i2 = idx; n2 = nr; }
+                        matches++;
                     }
-                };
-                eat(first.y, 1u);
-                eat(first.z, 2u);
-                eat(first.w, 3u);
-                for (uint32_t v = 1; v < 8u && 4u * v <= used; v++) {
-                    const uint4 r = my_row[v];
-                    eat(r.x, 4u * v);
-                    eat(r.y, 4u * v + 1u);
-                    eat(r.z, 4u * v + 2u);
-                    eat(r.w, 4u * v + 3u);
+                    idx += 1u + nr;
+                    if (idx <= used) hw = roww[idx];
                 }
-                cnt = (uint32_t)acc;
+                if (matches > 2u) {  // three groups of one code: the general kernel's scan takes any number
+                    to_queue = true;
+                    n1 = n2 = 0;
+                }
             }
+        }
+        // Phase 2, the warp in step: every lane adds up the runs of its one or two groups -- the same loop for all
+        // lanes (trip count = the longest list in the warp), instead of one divergent inner loop per header hop
+        {
+            const int pl = (int)(l & fmask), ph = (int)(h & fmask);
+            const uint32_t total_runs = n1 + n2;
+            const uint32_t trips = __reduce_max_sync(kFull, total_runs);
+            int acc = 0;
+#pragma unroll 2
+            for (uint32_t r = 0; r < trips; r++) {
+                if (r < total_runs) {
+                    const uint32_t w = roww[r < n1 ? i1 + 1u + r : i2 + 1u + (r - n1)];
+                    const int off = (int)(w & 0xFFFFu), len = (int)(w >> 16);
+                    acc += min(max(ph - off, 0), len) - min(max(pl - off, 0), len);
+                }
+            }
+            cnt = (uint32_t)acc;
         }
         st_two += kind == kKindTwoBuckets;
         st_zero += kind == kKindZero;
@@ -304,11 +316,17 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
         asm volatile("cp.async.commit_group;" ::: "memory");   // G_s = lines(s+1) + bytes(s+3)
         asm volatile("cp.async.wait_group 1;" ::: "memory");   // G_{s-1} (or the prologue's group) landed: lines(s), bytes(s+2)
         __syncwarp();
-        stage_d(s, d_word, d_kind, d_l, d_h, d_tag);
-        // rotate: s+1 becomes the D batch
-        d_word = c_word; d_kind = c_kind; d_l = n_l; d_h = n_h; d_tag = n_tag;
-        stage_b(s + 2, b_wordreg, c_word, c_entry, c_kind);    // B(s+2)
+        // B(s+2) BEFORE D(s): the table entry it requests is consumed by C(s+2) at the top of the next iteration, and
+        // D(s)'s line scan in between is what hides that (L2) latency
+        uint64_t b_word;
+        uint2 b_entry;
+        uint32_t b_kind;
+        stage_b(s + 2, b_wordreg, b_word, b_entry, b_kind);
         b_wordreg = a_word;
+        stage_d(s, d_word, d_kind, d_l, d_h, d_tag);
+        // rotate: s+1 becomes the D batch, s+2 the C batch
+        d_word = c_word; d_kind = c_kind; d_l = n_l; d_h = n_h; d_tag = n_tag;
+        c_word = b_word; c_entry = b_entry; c_kind = b_kind;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     flush_queue();

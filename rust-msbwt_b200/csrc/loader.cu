@@ -85,6 +85,7 @@ int validate_rle(const uint8_t *rle, uint64_t len, std::string &why) {
     if (len && !rle) { why = "rle is NULL"; return MSBWT_EINVAL; }
     uint8_t prev = 255;
     int digits = 0;
+    uint64_t total = 0;  // every addend is below 2^60 and the sum is checked after each: it cannot wrap unnoticed
     for (uint64_t i = 0; i < len; i++) {
         const uint8_t c = rle[i] & 7u;
         if (c >= kAlphabet) {
@@ -94,6 +95,8 @@ int validate_rle(const uint8_t *rle, uint64_t len, std::string &why) {
         digits = (c == prev) ? digits + 1 : 0;
         prev = c;
         if (digits >= 12) { why = "run longer than 2^60 symbols"; return MSBWT_EFORMAT; }
+        total += (uint64_t)(rle[i] >> 3) << (5 * digits);
+        if (total >> 62) { why = "BWT longer than 2^62 symbols"; return MSBWT_EFORMAT; }  // (the device builder's u64 prefix sums stay exact)
     }
     return MSBWT_OK;
 }

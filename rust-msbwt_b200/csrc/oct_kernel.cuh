@@ -364,31 +364,23 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                 no_fin = true;  // the same symbols through two oct steps
                 if constexpr (STATS) st_cnt[2]++;
             } else {
+                // hop from group header to group header (layout.h): a handful of 4-byte reads, not a scan of 31 words
                 const uint32_t tag = (uint32_t)(fin_mixed >> flb);
                 const int pl = (int)(l & fmask), ph = (int)(h & fmask);
+                const uint32_t *roww = reinterpret_cast<const uint32_t *>(my_row);
                 int cnt = 0;
-                uint32_t left = 0;
-                bool match = false;
-                auto eat = [&](uint32_t w, uint32_t idx) {  // word `idx` of the line: a group header or one of its runs
-                    if (idx > used) return;
-                    if (left == 0u) {
-                        match = (w >> 4) == tag;
-                        left = w & 15u;
-                    } else {
-                        const int off = (int)(w & 0xFFFFu), len = (int)(w >> 16);
-                        if (match) cnt += min(max(ph - off, 0), len) - min(max(pl - off, 0), len);
-                        left--;
+                uint32_t hw = first.y;
+                for (uint32_t idx = 1u; idx <= used;) {
+                    const uint32_t nr = hw & 15u;
+                    if ((hw >> 4) == tag) {
+                        for (uint32_t r = 1u; r <= nr; r++) {
+                            const uint32_t w = roww[idx + r];
+                            const int off = (int)(w & 0xFFFFu), len = (int)(w >> 16);
+                            cnt += min(max(ph - off, 0), len) - min(max(pl - off, 0), len);
+                        }
                     }
-                };
-                eat(first.y, 1u);
-                eat(first.z, 2u);
-                eat(first.w, 3u);
-                for (uint32_t v = 1; v < 8u && 4u * v <= used; v++) {
-                    const uint4 r = my_row[v];
-                    eat(r.x, 4u * v);
-                    eat(r.y, 4u * v + 1u);
-                    eat(r.z, 4u * v + 2u);
-                    eat(r.w, 4u * v + 3u);
+                    idx += 1u + nr;
+                    if (idx <= used) hw = roww[idx];
                 }
                 l = 0;
                 h = (uint32_t)cnt;  // only h - l is read from here on

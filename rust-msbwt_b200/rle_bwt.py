@@ -151,7 +151,11 @@ def load_library():
         "msbwt_debug_build_image": (i32, [vp, u64, u32, C.POINTER(u64), C.POINTER(u32), vp, vp, vp]),
         "msbwt_debug_copy_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp, vp]),
         "msbwt_build_rle_bwt": (i32, [vp, u64, u32, i32, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]),
+        "msbwt_build_rle_bwt_ragged": (i32, [vp, vp, u64, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]),
         "msbwt_buffer_free": (None, [vp]),
+        "msbwt_convert_to_rle": (i32, [vp, u64, C.POINTER(vp), C.POINTER(u64)]),
+        "msbwt_save_rle_npy": (i32, [vp, u64, C.c_char_p]),
+        "msbwt_save_runs_npy": (i32, [vp, vp, u64, C.c_char_p]),
         "msbwt_host_alloc": (vp, [C.c_size_t]),
         "msbwt_host_free": (None, [vp]),
         "msbwt_last_error": (C.c_char_p, []),
@@ -177,7 +181,8 @@ EXPORTED_SYMBOLS = (
     "msbwt_count_kmers_fixed", "msbwt_constrain_ranges", "msbwt_count_kmers_fixed_device",
     "msbwt_constrain_ranges_device", "msbwt_packed_bytes", "msbwt_pack_kmers_device",
     "msbwt_count_kmers_packed_device", "msbwt_launch_count", "msbwt_gather_bench", "msbwt_l2_fetch_granularity", "msbwt_debug_build_image", "msbwt_debug_copy_image",
-    "msbwt_host_alloc", "msbwt_build_rle_bwt", "msbwt_buffer_free",
+    "msbwt_host_alloc", "msbwt_build_rle_bwt", "msbwt_build_rle_bwt_ragged", "msbwt_buffer_free", "msbwt_convert_to_rle", "msbwt_save_rle_npy",
+    "msbwt_save_runs_npy",
     "msbwt_host_free", "msbwt_last_error", "msbwt_abi_version",
 )
 
@@ -580,6 +585,53 @@ def build_rle_bwt(reads, device: int = 0, n_reads: int | None = None, read_len: 
     finally:
         L.msbwt_buffer_free(out)
     return rle, int(total.value)
+
+
+def build_rle_bwt_ragged(reads, device: int = 0) -> tuple[np.ndarray, int]:
+    """The same for reads of any lengths (`reads`: a sequence of uint8 symbol arrays / strings over ACGNT), in
+    naive_bwt's order (src/bwt_util.rs:154-171).  Returns (rle bytes, total symbols = sum of length + 1)."""
+    L = load_library()
+    arrs = [convert_stoi(r) if isinstance(r, (str, bytes)) else _u8(r).reshape(-1) for r in reads]
+    offs = np.zeros(len(arrs) + 1, dtype=np.uint64)
+    if arrs:
+        np.cumsum([a.size for a in arrs], out=offs[1:])
+    flat = _u8(np.concatenate(arrs)) if arrs and offs[-1] else np.zeros(1, np.uint8)
+    out, nbytes, total = C.c_void_p(0), C.c_uint64(0), C.c_uint64(0)
+    _check(L.msbwt_build_rle_bwt_ragged(_p(flat), _p(offs), len(arrs), device, C.byref(out), C.byref(nbytes), C.byref(total)),
+           "build_rle_bwt_ragged")
+    try:
+        rle = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(nbytes.value,)).copy() if nbytes.value else np.zeros(0, np.uint8)
+    finally:
+        L.msbwt_buffer_free(out)
+    return rle, int(total.value)
+
+
+def convert_to_vec(text) -> np.ndarray:
+    """bwt_converter.rs:26-80: a text BWT over `$ACGNT` (newlines skipped) -> msbwt RLE bytes"""
+    raw = text.encode() if isinstance(text, str) else bytes(text)
+    a = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(0, dtype=np.uint8)
+    L = load_library()
+    out, n = C.c_void_p(0), C.c_uint64(0)
+    _check(L.msbwt_convert_to_rle(_p(a) if a.size else None, a.size, C.byref(out), C.byref(n)), "convert_to_vec")
+    try:
+        return np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint8)
+    finally:
+        L.msbwt_buffer_free(out)
+
+
+def save_bwt_numpy(rle, filename: str) -> None:
+    """bwt_converter.rs:102-130: the 96-byte header msbwt2 writes + the RLE bytes"""
+    a = _u8(rle).reshape(-1)
+    _check(load_library().msbwt_save_rle_npy(_p(a) if a.size else None, a.size, os.fsencode(filename)), "save_bwt_numpy")
+
+
+def save_bwt_runs_numpy(runs, filename: str) -> None:
+    """bwt_converter.rs:152-184: the same container from an iterable of (symbol, count) runs"""
+    runs = list(runs)
+    s = np.array([r[0] for r in runs], dtype=np.uint8)
+    c = np.array([r[1] for r in runs], dtype=np.uint64)
+    _check(load_library().msbwt_save_runs_npy(_p(s) if s.size else None, _p(c) if c.size else None, s.size, os.fsencode(filename)),
+           "save_bwt_runs_numpy")
 
 
 def l2_fetch_granularity(device: int, nbytes: int = 0) -> int:

@@ -70,6 +70,41 @@ def test_long_runs_and_midsize_equal_the_harness_builder():
     assert (got2 == got).all()
 
 
+def test_reads_of_different_lengths_match_naive_bwt():
+    """N2: create_from_fastx takes reads as they come (src/dynamic_bwt.rs:453-473); `msbwt_build_rle_bwt_ragged` must
+    order their suffixes as naive_bwt does (src/bwt_util.rs:154-171: doubled rotations, '$' smallest)"""
+    # the reference's own mixed-length examples: bwt_util.rs doc-test and dynamic_bwt.rs tests
+    for data, want in ((["CCGT", "N", "ACG"], "GTN$$ACCC$G"), (["ACA", "CA"], "AACC$A$")):
+        rle, total = M.build_rle_bwt_ragged(data)
+        assert total == sum(len(s) + 1 for s in data)
+        assert (rle == O.convert_to_vec(want)).all(), data
+    rng = np.random.default_rng(9)
+    for trial in range(6):
+        lens = rng.integers(0, 70, 80)                  # empty reads, lengths around the 21-symbol key word, prefixes
+        reads = [rng.choice(np.array([1, 2, 3, 4, 5], dtype=np.uint8), size=int(n), p=[0.3, 0.2, 0.2, 0.05, 0.25]) for n in lens]
+        reads[5] = reads[9][: len(reads[9]) // 2].copy()   # a read that is a prefix of another
+        reads[6] = reads[9].copy()                         # a duplicate
+        reads[7] = reads[9][len(reads[9]) // 3:].copy()    # a read that is a suffix of another
+        rle, total = M.build_rle_bwt_ragged(reads)
+        assert total == sum(len(r) + 1 for r in reads)
+        assert (rle == O.convert_to_vec(naive.naive_bwt(_as_strings(reads)))).all(), trial
+    # equal lengths through the ragged entry = the fixed-length builder
+    same = rng.choice(np.array([1, 2, 3, 5], dtype=np.uint8), size=(300, 37))
+    assert (M.build_rle_bwt_ragged(list(same))[0] == M.build_rle_bwt(same)[0]).all()
+    assert M.build_rle_bwt_ragged([])[1] == 0
+    # the index built from it answers like the oracle on the same bytes
+    reads = [rng.choice(np.array([1, 2, 3, 5], dtype=np.uint8), size=int(n)) for n in rng.integers(20, 120, 3000)]
+    rle, total = M.build_rle_bwt_ragged(reads)
+    o = O.RleBWT()
+    o.load_vector(rle)
+    g = M.RleBWT.new()
+    g.load_vector(rle)
+    assert g.get_total_size() == o.get_total_size() == total
+    q = np.stack([r[:12] for r in reads if len(r) >= 12][:2000])
+    assert (g.count_kmers_fixed(q, 12) == o.count_kmers_fixed(q, 12)).all()
+    assert int((g.count_kmers_fixed(q, 12) > 0).all())
+
+
 def test_bad_symbols_are_refused():
     reads = np.full((10, 8), 2, dtype=np.uint8)
     reads[3, 4] = 0
@@ -79,3 +114,5 @@ def test_bad_symbols_are_refused():
     reads[3, 4] = 6
     with pytest.raises(M.MsbwtError):
         M.build_rle_bwt(reads)
+    with pytest.raises(M.MsbwtError):
+        M.build_rle_bwt_ragged([np.array([1, 2, 0, 3], dtype=np.uint8), np.array([1], dtype=np.uint8)])

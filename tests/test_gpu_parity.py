@@ -262,6 +262,30 @@ def test_golden_fixture(golden_dir):
     assert (g.count_kmers_fixed(z["queries_k12"], 12) == z["counts_k12"]).all()
 
 
+def test_built_bwt_saved_as_npy_loads_back_with_the_requested_layout(midsize, tmp_path):
+    """N1: the product writes msbwt2's container itself (codec.cpp, src/bwt_converter.rs:102-130) and
+    load_numpy_file honours the layout knobs (msbwt_index_create_from_npy_opts)"""
+    from harness import synth
+    reads, g, o = midsize
+    p = str(tmp_path / "built.npy")
+    M.save_bwt_numpy(o.rle_bytes(), p)
+    o2 = O.RleBWT()
+    o2.load_numpy_file(p)                      # the oracle's reader accepts the file
+    assert o2.get_total_size() == o.get_total_size()
+    q = synth.make_queries(reads, 31, 20001, 10000).cpu().numpy()
+    want = o.count_kmers_fixed(q, 31, threads=8)
+    for opts in (dict(), dict(pair_index=1, suffix_table_s=5), dict(oct_index=1, final_index=0), dict(oct_index=1, keep_quad_index=0)):
+        b = M.RleBWT(**opts)
+        b.load_numpy_file(p)
+        assert b.get_total_size() == o.get_total_size()
+        if "pair_index" in opts:
+            assert b.pair_index and b.suffix_table_s == 5
+        if "oct_index" in opts:
+            assert b.oct_index and b.final_index == (opts.get("final_index", -1) != 0)
+            assert b.quad_index == (opts.get("keep_quad_index", 1) != 0)
+        assert (b.count_kmers_fixed(q, 31) == want).all(), opts
+
+
 def test_multi_device_split_matches_single(midsize):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

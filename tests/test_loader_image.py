@@ -96,6 +96,21 @@ def test_bad_rle_symbol_is_eformat():
     assert e.value.code == 3
 
 
+def test_rle_whose_runs_add_up_past_2_pow_62_is_refused_before_any_device_work():
+    """the total is accumulated with a check after every byte (validate_rle): five runs of 31 * 32^11 ~ 2^60 symbols
+    each must be refused as EFORMAT, not wrap a u64 prefix sum on the device"""
+    run_a = np.full(12, 1 | (31 << 3), dtype=np.uint8)   # twelve base-32 digits of symbol A
+    run_c = np.full(12, 2 | (31 << 3), dtype=np.uint8)
+    rle = np.concatenate([run_a, run_c, run_a, run_c, run_a])
+    b = M.RleBWT.new()
+    with pytest.raises(M.MsbwtError) as e:
+        b.load_vector(rle)
+    assert e.value.code == 3 and "2^62" in str(e.value)
+    with pytest.raises(M.MsbwtError) as e:                # a thirteenth digit: one run beyond 2^60
+        b.load_vector(np.full(13, 1 | (31 << 3), dtype=np.uint8))
+    assert e.value.code == 3
+
+
 def test_string_util_mirror():
     assert list(M.convert_stoi("ACGTN$acgtnx")) == [1, 2, 3, 5, 4, 0, 1, 2, 3, 5, 4, 4]
     assert M.convert_itos([0, 1, 2, 3, 4, 5]) == "$ACGNT"
