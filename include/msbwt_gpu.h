@@ -109,7 +109,7 @@ msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *
  * ONE line fill.  -1 = automatic (built whenever the oct image is; MSBWT_FINAL_INDEX=0|1 overrides), 0 = never,
  * 1 = always (create fails if it cannot be built).  A line whose groups do not fit, or a range over two buckets,
  * takes the two oct steps instead, so results are identical on any input.  `final_bucket_shift` (8..16, 0 = 16) and
- * `final_lines_log2` (12..20 lines per bucket; 0 = automatic: 13 = 16 bytes per symbol when that fits a quarter of
+ * `final_lines_log2` (12..20 lines per bucket; 0 = automatic: 13 = 16 bytes per symbol when that fits 30 % of
  * the device memory, else 12 = 8 bytes per symbol). */
 typedef struct msbwt_options {
     uint32_t struct_size;
@@ -229,6 +229,10 @@ uint64_t msbwt_packed_bytes(const msbwt_index *idx, uint32_t k, uint64_t n);
 int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const uint8_t *d_syms, uint32_t k,
                             uint64_t n, uint64_t *d_packed, uint64_t *d_out, uint32_t *d_status,
                             void *stream);
+/* the pack stage for k-mers already on the device as 2-bit-per-symbol integers (msbwt_count_kmers_u64's format, k <= 32):
+ * nothing to validate; followed by msbwt_count_kmers_packed_device like msbwt_pack_kmers_device */
+int msbwt_seed_kmers_u64_device(const msbwt_index *idx, int slot, const uint64_t *d_kmers, uint32_t k, uint64_t n,
+                                uint64_t *d_packed, uint64_t *d_out, void *stream);
 int msbwt_count_kmers_packed_device(const msbwt_index *idx, int slot, const uint64_t *d_packed,
                                     uint32_t k, uint64_t n, uint64_t *d_out, void *stream);
 /* Measurement aid: what the last msbwt_pack_kmers_device on this scratch left for the search (out6[0] live list A,

@@ -16,7 +16,8 @@ a tag fits 28 bits for m = 20).  A code goes to line `(bucket << lb) | (mix40(c)
   then groups : header `(tag << 4) | nruns` (nruns 1..15) followed by nruns words `(len << 16) | offset` -- a run of
                 `len` consecutive positions with that code starting at `offset` inside the bucket.  A code with more
                 than 15 runs in a bucket simply has several groups; a run never crosses a bucket boundary.
-Group order inside a line is unspecified (the device builder appends with atomics): compare lines as sets of groups.
+The groups of one code are adjacent (both builders write a line's groups in (tag, start) order); the order of different
+codes inside a line is otherwise unspecified: compare lines as sets of groups.
 """
 from __future__ import annotations
 

@@ -354,7 +354,9 @@ int build_multi_step(msbwt_index *idx, Replica &rep, const Options &opt) {
     int fshift = opt.fin_shift ? opt.fin_shift : env_int("MSBWT_FINAL_BUCKET_SHIFT", 16);
     int flb = opt.fin_lb ? opt.fin_lb : env_int("MSBWT_FINAL_LINES_LOG2", 0);
     if (want_fin) {
-        if (!flb) flb = fin_image_bytes(N, fshift, 13) <= (uint64_t)total_b / 4 ? 13 : 12;  // 16 or 8 bytes per symbol
+        // 16 bytes per symbol (0.8 % of the read-sampled 31-mers find their line overflowed and take the oct steps) when
+        // that fits 30 % of the device (48 GB at 3.02 Gsymbols), else 8 bytes per symbol (6.5 %)
+        if (!flb) flb = fin_image_bytes(N, fshift, 13) <= (uint64_t)total_b / 10 * 3 ? 13 : 12;
         n = 0;
         rc = build_fin_codes_on_device(rep.device, rep.view, codes10, &codes20, why, &n);
         g_launches += (uint64_t)n;
@@ -750,6 +752,21 @@ extern "C" int msbwt_pack_kmers_device(const msbwt_index *idx, int slot, const u
     Replica &rep = *idx->reps[slot];
     DeviceGuard guard(rep.device);
     CU_TRY(launch_pack_seed(rep.view, d_syms, k, n, d_packed, d_out, d_status, (cudaStream_t)stream));
+    g_launches++;
+    return MSBWT_OK;
+}
+
+// the pack stage for k-mers the caller holds on the device as 2-bit-per-symbol integers (msbwt_count_kmers_u64's format)
+extern "C" int msbwt_seed_kmers_u64_device(const msbwt_index *idx, int slot, const uint64_t *d_kmers, uint32_t k, uint64_t n,
+                                           uint64_t *d_packed, uint64_t *d_out, void *stream) {
+    if (!idx || slot < 0 || slot >= (int)idx->reps.size()) return fail(MSBWT_EINVAL, "bad handle or slot");
+    if (n && (!d_packed || !d_out || !d_kmers)) return fail(MSBWT_EINVAL, "NULL device buffer");
+    if (k == 0 || k > 32) return fail(MSBWT_EINVAL, "k must be 1..32 (one 2-bit-per-symbol word per k-mer)");
+    if (n > kMaxPerLaunch) return fail(MSBWT_EINVAL, "more than 2^30 queries per pack/count pair: split the batch");
+    if (!n) return MSBWT_OK;
+    Replica &rep = *idx->reps[slot];
+    DeviceGuard guard(rep.device);
+    CU_TRY(launch_seed_u64(rep.view, d_kmers, k, n, d_packed, d_out, (cudaStream_t)stream));
     g_launches++;
     return MSBWT_OK;
 }

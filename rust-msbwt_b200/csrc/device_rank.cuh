@@ -18,6 +18,19 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     return p;
 }
 
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// a suffix-table entry {l, h}: the table level a batch reads is small (33 MB at depth 11) and every entry is read many
+// times per batch, while the index lines around it are read once -- keep it in L2 against that stream
+__device__ __forceinline__ uint2 ldg_table_entry(const uint2 *p, uint64_t pol_last) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol_last));
+    return r;
+}
+
 struct Half { uint32_t w[8]; };  // 32 bytes = one sector of a block
 
 // half an index block: read-only path, no L1 allocation, evict-last in L2 (256-bit load)

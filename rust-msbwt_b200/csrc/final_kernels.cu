@@ -41,16 +41,27 @@ constexpr int kFinWarps = 8;                 // warps per CTA
 constexpr int kFinThreads = 32 * kFinWarps;
 constexpr int kFinRowBytes = 144;            // a 128-byte line + 16: the rows of consecutive lanes start 4 banks apart
 constexpr int kFinByteBuf = 32 * 32 + 16;    // 32 k-mers of k <= 32 symbol bytes, + the slack an unaligned 4-byte read needs
-constexpr int kFinQueue = 64;                // list-A entries a warp stages before it flushes
-constexpr int kFinWarpSmem = 2 * 32 * kFinRowBytes + 2 * kFinByteBuf + kFinQueue * 20;
-constexpr int kFinSmem = kFinWarps * kFinWarpSmem;
+// Two shapes of the same pipeline (template parameter DEEP), chosen by measurement (launch_t):
+//   DEEP = true : two row buffers and two byte buffers per warp -- a warp keeps the lines of batch s+1 in flight while
+//                 it scans those of batch s; 12.3 KB of shared memory per warp, 2 CTAs of 8 warps per SM (16 warps)
+//   DEEP = false: one of each -- a warp waits for its own lines, the OTHER warps of the SM hide that: 6.3 KB per warp
+//                 and 64 registers per thread, 4 CTAs per SM (32 warps).  The loop is bound by the latency of its own
+//                 dependent instructions (ncu, profiles/r2g_*: 640 instructions per batch issue in 5600 cycles per
+//                 warp at 4 warps per scheduler), which only more resident warps can hide.
+template <bool DEEP> struct FinShape {
+    static constexpr int kBufs = DEEP ? 2 : 1;
+    static constexpr int kQueue = DEEP ? 64 : 32;  // list-A entries a warp stages before it flushes
+    static constexpr int kWarpSmem = kBufs * 32 * kFinRowBytes + kBufs * kFinByteBuf + kQueue * 20;
+    static constexpr int kSmem = kFinWarps * kWarpSmem;
+    static constexpr int kCtasPerSm = DEEP ? 2 : 4;
+};
 
 enum : uint32_t { kKindNone = 0, kKindZero = 1, kKindLine = 2, kKindTwoBuckets = 3 };
 
 // SRC 0: symbol bytes; 1: caller-packed integers (first symbol most significant); 2: host-packed words (last symbol
 // in the top bits).  K = 31: every shift, mask and copy count a constant; K = 0: k_rt (k <= 32).
-template <int SRC, uint32_t K>
-__global__ void __launch_bounds__(kFinThreads, 2)
+template <int SRC, uint32_t K, bool DEEP>
+__global__ void __launch_bounds__(kFinThreads, FinShape<DEEP>::kCtasPerSm)
 pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_rt, SeedPlan plan, PackedLayout lay,
                        uint64_t *__restrict__ packed, uint64_t *__restrict__ out, uint32_t *__restrict__ status) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -58,17 +69,20 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
     const uint32_t k = K ? K : k_rt;
     const uint32_t depth = plan.depth;  // k - depth == kFinSyms (the host checked)
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint64_t n = lay.n;
-    const uint64_t n_batches = (n + 31) / 32;
-    const uint64_t warps_total = (uint64_t)gridDim.x * kFinWarps;
-    const uint64_t warp_gid = (uint64_t)blockIdx.x * kFinWarps + warp;
+    const uint32_t n = (uint32_t)lay.n;  // <= 2^30 per launch (kMaxPerLaunch): query and batch numbers are 32-bit
+    const uint32_t n_batches = (n + 31u) / 32u;
+    const uint32_t warps_total = gridDim.x * kFinWarps;
+    const uint32_t warp_gid = blockIdx.x * kFinWarps + warp;
     if (warp_gid >= n_batches) return;
-    const uint64_t my_batches = (n_batches - warp_gid + warps_total - 1) / warps_total;  // batches warp_gid + s * warps_total
+    const uint32_t my_batches = (n_batches - warp_gid + warps_total - 1u) / warps_total;  // batches warp_gid + s * warps_total
 
-    uint8_t *const wsm = smem + warp * kFinWarpSmem;
-    uint8_t *const rows = wsm;                                   // 2 x 32 rows
-    uint8_t *const bytes = wsm + 2 * 32 * kFinRowBytes;          // 2 byte buffers (SRC 0)
-    uint8_t *const queue = bytes + 2 * kFinByteBuf;              // kFinQueue x {u64 word, u64 seed, u32 index}
+    using Shape = FinShape<DEEP>;
+    constexpr uint32_t kBufMask = DEEP ? 1u : 0u;  // buffer of batch s: s & kBufMask
+    constexpr int kFinQueue = Shape::kQueue;
+    uint8_t *const wsm = smem + warp * Shape::kWarpSmem;
+    uint8_t *const rows = wsm;                                              // kBufs x 32 rows
+    uint8_t *const bytes = wsm + Shape::kBufs * 32 * kFinRowBytes;          // kBufs byte buffers (SRC 0)
+    uint8_t *const queue = bytes + Shape::kBufs * kFinByteBuf;              // kQueue x {u64 word, u64 seed, u32 index}
     uint64_t *const q_word = reinterpret_cast<uint64_t *>(queue);
     uint64_t *const q_seed = q_word + kFinQueue;
     uint32_t *const q_idx = reinterpret_cast<uint32_t *>(q_seed + kFinQueue);
@@ -77,28 +91,34 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
     const uint2 *const table = reinterpret_cast<const uint2 *>(plan.tab);
     const char *const fin_base = reinterpret_cast<const char *>(ix.fin);
     const uint32_t fshift = ix.fin_shift, fmask = (1u << fshift) - 1u, flb = ix.fin_lb;
-    const uint64_t stream_pol = policy_evict_first();
+    const uint64_t stream_pol = policy_evict_first();  // query bytes, final-step lines, results: read or written once
+    const uint64_t table_pol = policy_evict_last();    // the suffix-table level: 33 MB read a hundred million times
     unsigned long long *const live = reinterpret_cast<unsigned long long *>(packed + lay.live());
     uint32_t *const qidx_arr = reinterpret_cast<uint32_t *>(packed + lay.qidx());
     uint32_t st_lines = 0, st_over = 0, st_two = 0, st_zero = 0;
 
-    auto batch_of = [&](uint64_t s) { return warp_gid + s * warps_total; };
+    auto first_query = [&](uint32_t s) { return (warp_gid + s * warps_total) * 32u; };
 
     // ---- A: symbol bytes of batch sequence number s -> byte buffer s & 1 (SRC 0), or this lane's word (SRC 1, 2)
-    auto stage_a = [&](uint64_t s, uint64_t &word_reg) {
+    auto stage_a = [&](uint32_t s, uint64_t &word_reg) {
         if (s >= my_batches) return;
-        const uint64_t q0 = batch_of(s) * 32u;
+        const uint32_t q0 = first_query(s);
         if constexpr (SRC == 0) {
-            const uint8_t *g = reinterpret_cast<const uint8_t *>(src_v) + q0 * k;  // 16-byte aligned: 32 k bytes per batch
-            const uint32_t cnt = (uint32_t)min((uint64_t)32u, n - q0), nbytes = cnt * k;
-            uint8_t *dst = bytes + (s & 1u) * kFinByteBuf;
+            const uint8_t *g = reinterpret_cast<const uint8_t *>(src_v) + (size_t)q0 * k;  // 16-byte aligned: 32 k bytes per batch
+            uint8_t *dst = bytes + (s & kBufMask) * kFinByteBuf;
+            if (q0 + 32u <= n) {  // a whole batch: 2 k pieces of 16 bytes, every one of them full
+                cp_async16_hint(dst + 16u * lane, g + 16u * lane, true, stream_pol);
+                if (lane + 32u < 2u * k) cp_async16_hint(dst + 16u * (lane + 32u), g + 16u * (lane + 32u), true, stream_pol);
+            } else {              // the batch's tail: the pieces past the last query are zero-filled, not read
+                const uint32_t nbytes = (n - q0) * k;
 #pragma unroll
-            for (uint32_t c = lane; c < 64u; c += 32u) {  // 32 k <= 1024 bytes: at most 64 pieces of 16
-                const uint32_t at = 16u * c;
-                if (K == 0 || at < 32u * K) cp_async16_partial(dst + at, g + at, at < nbytes ? min(16u, nbytes - at) : 0u);
+                for (uint32_t c = lane; c < 64u; c += 32u) {
+                    const uint32_t at = 16u * c;
+                    if (at < 32u * k) cp_async16_partial(dst + at, g + at, at < nbytes ? min(16u, nbytes - at) : 0u);
+                }
             }
         } else {
-            const uint64_t q = q0 + lane;
+            const uint32_t q = q0 + lane;
             word_reg = q < n ? ldg_stream(reinterpret_cast<const uint64_t *>(src_v) + q, stream_pol) : 0ull;
         }
     };
@@ -106,15 +126,15 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
     // ---- B: pack (SRC 0) / normalise (SRC 1, 2) the k-mer of batch s: `word` = its symbols 2 bits each, the LAST
     //         symbol in the top bits; request the table entry.  A k-mer holding `$` / `N` is seeded one symbol at a
     //         time (seed_general) and goes to live list B here and now; kind = what stage C has to do with the query.
-    auto stage_b = [&](uint64_t s, uint64_t word_reg, uint64_t &word, uint2 &entry, uint32_t &kind) {
+    auto stage_b = [&](uint32_t s, uint64_t word_reg, uint64_t &word, uint2 &entry, uint32_t &kind) {
         kind = kKindNone;
         word = 0;
         entry = make_uint2(0u, 0u);
         if (s >= my_batches) return;
-        const uint64_t q = batch_of(s) * 32u + lane;
+        const uint32_t q = first_query(s) + lane;
         if (q >= n) return;
         if constexpr (SRC == 0) {
-            const uint8_t *buf = bytes + (s & 1u) * kFinByteBuf;
+            const uint8_t *buf = bytes + (s & kBufMask) * kFinByteBuf;
             const uint32_t o = lane * k;
             const volatile uint32_t *p = reinterpret_cast<const volatile uint32_t *>(buf + (o & ~3u));
             const uint32_t sh = (o & 3u) * 8u;
@@ -140,10 +160,10 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
                 if (finished) {
                     out[q] = hi - lo;
                 } else {
-                    const uint64_t pos = n - 1 - atomicAdd(live + 1, 1ull);
+                    const uint64_t pos = (uint64_t)n - 1 - atomicAdd(live + 1, 1ull);
                     packed[lay.w0() + pos] = word0;
                     packed[lay.seed() + pos] = lo | (hi << 32);
-                    qidx_arr[pos] = (uint32_t)q | (flag << 30);
+                    qidx_arr[pos] = q | (flag << 30);
                 }
                 return;
             }
@@ -154,12 +174,12 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
         } else {
             word = word_reg;
         }
-        entry = __ldg(table + (word >> (64u - 2u * depth)));
+        entry = ldg_table_entry(table + (word >> (64u - 2u * depth)), table_pol);
         kind = kKindLine;  // refined in stage C, once the entry has arrived
     };
 
     // ---- C: batch s: the range, the line, and the warp's copy of the 32 lines into row buffer s & 1
-    auto stage_c = [&](uint64_t s, uint64_t word, uint2 entry, uint32_t &kind, uint32_t &l, uint32_t &h, uint32_t &tag) {
+    auto stage_c = [&](uint32_t s, uint64_t word, uint2 entry, uint32_t &kind, uint32_t &l, uint32_t &h, uint32_t &tag) {
         l = entry.x;
         h = entry.y;
         uint32_t line = 0;
@@ -176,14 +196,15 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
             }
         }
         if (s >= my_batches) return;  // (warp-uniform)
-        const uint32_t pub = line | (kind == kKindLine ? 0x80000000u : 0u);  // a line index is below 2^29
-        uint8_t *const dst_rows = rows + (s & 1u) * (32 * kFinRowBytes);
+        const uint32_t pub = line | (kind == kKindLine ? 0x80000000u : 0u);  // a line index is below 2^31 (checked by the host)
+        uint8_t *const dst_rows = rows + (s & kBufMask) * (32 * kFinRowBytes);
         const uint32_t j = lane & 7u;
 #pragma unroll
         for (uint32_t c = 0; c < 8u; c++) {
             const uint32_t o = 4u * c + (lane >> 3);  // the lane whose line this is
             const uint32_t v = __shfl_sync(kFull, pub, o);
-            cp_async16(dst_rows + o * kFinRowBytes + 16u * j, fin_base + (size_t)(v & 0x7fffffffu) * kFinLineBytes + 16u * j, (v >> 31) != 0u);
+            cp_async16_hint(dst_rows + o * kFinRowBytes + 16u * j, fin_base + (size_t)(v & 0x7fffffffu) * kFinLineBytes + 16u * j,
+                            (v >> 31) != 0u, stream_pol);
         }
     };
 
@@ -202,65 +223,71 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
         q_fill = 0;
     };
 
+    // occurrences inside [pl, ph) of the runs `(len << 16) | offset` at words first .. first + nruns - 1 of a row: the
+    // same loop for every lane of the warp (trip count = the longest list among them), four runs per trip
+    auto add_runs = [&](const uint32_t *roww, uint32_t first, uint32_t nruns, int pl, int ph, int &acc) {
+        const uint32_t trips = __reduce_max_sync(kFull, nruns);
+        for (uint32_t r = 0; r < trips; r += 4u) {
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; u++) {
+                if (r + u < nruns) {
+                    const uint32_t w = roww[first + r + u];
+                    const int off = (int)(w & 0xFFFFu), len = (int)(w >> 16);
+                    acc += min(max(ph - off, 0), len) - min(max(pl - off, 0), len);
+                }
+            }
+        }
+    };
+
     // ---- D: batch s: scan the line, write the count, or queue the query for the general kernel
-    auto stage_d = [&](uint64_t s, uint64_t word, uint32_t kind, uint32_t l, uint32_t h, uint32_t tag) {
+    auto stage_d = [&](uint32_t s, uint64_t word, uint32_t kind, uint32_t l, uint32_t h, uint32_t tag) {
         if (s >= my_batches) return;  // (warp-uniform)
-        const uint64_t q = batch_of(s) * 32u + lane;
+        const uint32_t q = first_query(s) + lane;
         bool to_queue = kind == kKindTwoBuckets;
         uint32_t nofin = 0;
-        uint32_t cnt = 0;
-        // Phase 1, per lane: hop from group header to group header (`tag << 4 | nruns`, then nruns run words) and note
-        // where this query's code sits -- a line holds a few groups, so this is a handful of 4-byte shared-memory reads.
-        // A code with more than 15 runs in the bucket has a second group (a 31-mer seen 30 times is ~13 runs of
-        // consecutive positions); a third one is rare enough to leave to the general kernel.
-        const uint32_t *roww = reinterpret_cast<const uint32_t *>(rows + (s & 1u) * (32 * kFinRowBytes) + lane * kFinRowBytes);
-        uint32_t i1 = 0, n1 = 0, i2 = 0, n2 = 0;
+        // Phase 1, per lane: hop from group header to group header (`tag << 4 | nruns`, then nruns run words) to the
+        // FIRST group of this query's code -- a line holds a few groups, so this is a handful of 4-byte shared-memory
+        // reads.  A code with more than 15 runs in the bucket (a 31-mer seen 30 times is ~13 runs of consecutive
+        // positions) continues in the groups right behind (layout.h: the groups of one code are adjacent).
+        const uint32_t *roww = reinterpret_cast<const uint32_t *>(rows + (s & kBufMask) * (32 * kFinRowBytes) + lane * kFinRowBytes);
+        uint32_t i1 = 0, matches = 0, used = 0;
         if (kind == kKindLine) {
             const uint2 first = *reinterpret_cast<const uint2 *>(roww);
-            const uint32_t used = first.x;
+            used = first.x;
             st_lines++;
             if (used == kFinOverflow) {
                 to_queue = true;
                 nofin = 1u;
                 st_over++;
+                used = 0;
             } else {
-                uint32_t hw = first.y, matches = 0;  // word 1: the first header (meaningless when used == 0)
+                uint32_t hw = first.y;  // word 1: the first header (meaningless when used == 0)
                 for (uint32_t idx = 1u; idx <= used;) {
-                    const uint32_t nr = hw & 15u;
-                    if ((hw >> 4) == tag) {
-                        if (matches == 0u) { i1 = idx; n1 = nr; }
-                        else if (matches == 1u) { i2 = idx; n2 = nr; }
-                        matches++;
-                    }
-                    idx += 1u + nr;
+                    const bool eq = (hw >> 4) == tag;
+                    if (eq && matches == 0u) i1 = idx;
+                    matches += eq ? 1u : 0u;
+                    idx += 1u + (hw & 15u);
                     if (idx <= used) hw = roww[idx];
-                }
-                if (matches > 2u) {  // three groups of one code: the general kernel's scan takes any number
-                    to_queue = true;
-                    n1 = n2 = 0;
                 }
             }
         }
-        // Phase 2, the warp in step: every lane adds up the runs of its one or two groups -- the same loop for all
-        // lanes (trip count = the longest list in the warp), instead of one divergent inner loop per header hop
+        // Phase 2, the warp in step: every lane adds up the runs of its group (and, when some lane's code has one, of
+        // the group behind it); a third group of one code is rare enough to leave to the general kernel
+        int acc = 0;
         {
             const int pl = (int)(l & fmask), ph = (int)(h & fmask);
-            const uint32_t total_runs = n1 + n2;
-            const uint32_t trips = __reduce_max_sync(kFull, total_runs);
-            int acc = 0;
-#pragma unroll 2
-            for (uint32_t r = 0; r < trips; r++) {
-                if (r < total_runs) {
-                    const uint32_t w = roww[r < n1 ? i1 + 1u + r : i2 + 1u + (r - n1)];
-                    const int off = (int)(w & 0xFFFFu), len = (int)(w >> 16);
-                    acc += min(max(ph - off, 0), len) - min(max(pl - off, 0), len);
-                }
+            const uint32_t n1 = matches ? (roww[i1] & 15u) : 0u;
+            add_runs(roww, i1 + 1u, n1, pl, ph, acc);
+            if (__any_sync(kFull, matches > 1u)) {
+                const uint32_t i2 = i1 + 1u + n1;
+                const uint32_t n2 = matches > 1u ? (roww[i2] & 15u) : 0u;
+                add_runs(roww, i2 + 1u, n2, pl, ph, acc);
+                if (matches > 2u) to_queue = true;
             }
-            cnt = (uint32_t)acc;
         }
         st_two += kind == kKindTwoBuckets;
         st_zero += kind == kKindZero;
-        if ((kind == kKindLine && !to_queue) || kind == kKindZero) stg_stream(out + q, (uint64_t)cnt, stream_pol);
+        if ((kind == kKindLine && !to_queue) || kind == kKindZero) stg_stream(out + q, (uint64_t)(uint32_t)acc, stream_pol);
         const uint32_t qm = __ballot_sync(kFull, to_queue);
         if (qm) {
             if (q_fill + (uint32_t)__popc(qm) > (uint32_t)kFinQueue) flush_queue();
@@ -268,65 +295,108 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
                 const uint32_t at = q_fill + __popc(qm & ((1u << lane) - 1u));
                 q_word[at] = word << (2u * depth);  // the kFinSyms symbols still to consume, first in the top bits
                 q_seed[at] = (uint64_t)l | ((uint64_t)h << 32);
-                q_idx[at] = (uint32_t)q | (nofin << 30);
+                q_idx[at] = q | (nofin << 30);
             }
             q_fill += (uint32_t)__popc(qm);
             __syncwarp();
         }
     };
 
-    // ---- the pipeline.  Register state: batch s in D (d_*), s+1 in C (c_*), s+2 in B; the word of s+3 in flight (SRC 1, 2)
-    uint64_t a_word = 0, b_wordreg = 0;
-    uint64_t c_word = 0, d_word = 0;
-    uint2 c_entry = make_uint2(0u, 0u);
-    uint32_t c_kind = kKindNone, d_kind = kKindNone, d_l = 0, d_h = 0, d_tag = 0;
-
-    // prologue: bytes of batches 0 and 1 (and 2), B for batch 0 and 1, C for batch 0
-    stage_a(0, b_wordreg);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    uint64_t w1 = 0;
-    stage_a(1, w1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();
-    {   // B(0)
-        uint64_t word;
-        uint2 entry;
-        uint32_t kind;
-        stage_b(0, b_wordreg, word, entry, kind);
-        d_word = word;
-        uint32_t l, h, tag;
-        stage_c(0, word, entry, kind, l, h, tag);  // C(0): lines of batch 0 -> rows 0
-        d_kind = kind; d_l = l; d_h = h; d_tag = tag;
-    }
-    __syncwarp();        // byte buffer 0 was read by B(0)
-    stage_a(2, a_word);  // bytes(2) -> byte buffer 0
-    asm volatile("cp.async.commit_group;" ::: "memory");   // group: lines(0) + bytes(2)
-    asm volatile("cp.async.wait_group 1;" ::: "memory");   // bytes(1) landed
-    __syncwarp();
-    stage_b(1, w1, c_word, c_entry, c_kind);                // B(1)
-    b_wordreg = a_word;                                     // the word of batch 2 (SRC 1, 2)
-
-    for (uint64_t s = 0; s < my_batches; s++) {
-        // C(s+1): needs the entry requested by B(s+1)
-        uint32_t n_l, n_h, n_tag;
-        __syncwarp();  // rows (s+1) & 1 were read by D(s-1); byte buffer (s+3) & 1 by B(s+1)
-        stage_c(s + 1, c_word, c_entry, c_kind, n_l, n_h, n_tag);
-        stage_a(s + 3, a_word);
-        asm volatile("cp.async.commit_group;" ::: "memory");   // G_s = lines(s+1) + bytes(s+3)
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // G_{s-1} (or the prologue's group) landed: lines(s), bytes(s+2)
+    if constexpr (!DEEP) {
+        // ---- the shallow pipeline (one row buffer, one byte buffer).  Iteration s: everything issued so far has landed
+        //      (lines of batch s, bytes of batch s+2) -> D(s) -> B(s+2) -> C(s+1) (its table entry was requested an
+        //      iteration ago) -> A(s+3) -> commit.  Register state: batch s in D (d_*), s+1 in C (c_*).
+        uint64_t a_word = 0, b_wordreg = 0, w1 = 0;
+        uint64_t c_word = 0, d_word = 0;
+        uint2 c_entry = make_uint2(0u, 0u);
+        uint32_t c_kind = kKindNone, d_kind = kKindNone, d_l = 0, d_h = 0, d_tag = 0;
+        auto land = [&]() {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+        };
+        stage_a(0, b_wordreg);
+        land();
+        uint2 e0;
+        uint32_t k0;
+        stage_b(0, b_wordreg, d_word, e0, k0);                  // B(0)
         __syncwarp();
-        // B(s+2) BEFORE D(s): the table entry it requests is consumed by C(s+2) at the top of the next iteration, and
-        // D(s)'s line scan in between is what hides that (L2) latency
-        uint64_t b_word;
-        uint2 b_entry;
-        uint32_t b_kind;
-        stage_b(s + 2, b_wordreg, b_word, b_entry, b_kind);
-        b_wordreg = a_word;
-        stage_d(s, d_word, d_kind, d_l, d_h, d_tag);
-        // rotate: s+1 becomes the D batch, s+2 the C batch
-        d_word = c_word; d_kind = c_kind; d_l = n_l; d_h = n_h; d_tag = n_tag;
-        c_word = b_word; c_entry = b_entry; c_kind = b_kind;
+        stage_a(1, w1);
+        land();
+        stage_b(1, w1, c_word, c_entry, c_kind);                // B(1)
+        __syncwarp();
+        stage_c(0, d_word, e0, k0, d_l, d_h, d_tag);            // C(0)
+        d_kind = k0;
+        stage_a(2, b_wordreg);                                  // A(2)
+        for (uint32_t s = 0; s < my_batches; s++) {
+            land();                                             // lines(s), bytes(s+2)
+            stage_d(s, d_word, d_kind, d_l, d_h, d_tag);
+            uint64_t b_word;
+            uint2 b_entry;
+            uint32_t b_kind;
+            stage_b(s + 2, b_wordreg, b_word, b_entry, b_kind); // requests the table entry C(s+2) reads next iteration
+            __syncwarp();                                       // rows were read by D(s), the byte buffer by B(s+2)
+            uint32_t n_l, n_h, n_tag;
+            stage_c(s + 1, c_word, c_entry, c_kind, n_l, n_h, n_tag);
+            stage_a(s + 3, a_word);
+            b_wordreg = a_word;
+            d_word = c_word; d_kind = c_kind; d_l = n_l; d_h = n_h; d_tag = n_tag;
+            c_word = b_word; c_entry = b_entry; c_kind = b_kind;
+        }
+    } else {
+        // ---- the pipeline.  Register state: batch s in D (d_*), s+1 in C (c_*), s+2 in B; the word of s+3 in flight (SRC 1, 2)
+        uint64_t a_word = 0, b_wordreg = 0;
+        uint64_t c_word = 0, d_word = 0;
+        uint2 c_entry = make_uint2(0u, 0u);
+        uint32_t c_kind = kKindNone, d_kind = kKindNone, d_l = 0, d_h = 0, d_tag = 0;
+
+        // prologue: bytes of batches 0 and 1 (and 2), B for batch 0 and 1, C for batch 0
+        stage_a(0, b_wordreg);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        uint64_t w1 = 0;
+        stage_a(1, w1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        {   // B(0)
+            uint64_t word;
+            uint2 entry;
+            uint32_t kind;
+            stage_b(0, b_wordreg, word, entry, kind);
+            d_word = word;
+            uint32_t l, h, tag;
+            stage_c(0, word, entry, kind, l, h, tag);  // C(0): lines of batch 0 -> rows 0
+            d_kind = kind; d_l = l; d_h = h; d_tag = tag;
+        }
+        __syncwarp();        // byte buffer 0 was read by B(0)
+        stage_a(2, a_word);  // bytes(2) -> byte buffer 0
+        asm volatile("cp.async.commit_group;" ::: "memory");   // group: lines(0) + bytes(2)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // bytes(1) landed
+        __syncwarp();
+        stage_b(1, w1, c_word, c_entry, c_kind);                // B(1)
+        b_wordreg = a_word;                                     // the word of batch 2 (SRC 1, 2)
+
+        for (uint32_t s = 0; s < my_batches; s++) {
+            // C(s+1): needs the entry requested by B(s+1)
+            uint32_t n_l, n_h, n_tag;
+            __syncwarp();  // rows (s+1) & 1 were read by D(s-1); byte buffer (s+3) & 1 by B(s+1)
+            stage_c(s + 1, c_word, c_entry, c_kind, n_l, n_h, n_tag);
+            stage_a(s + 3, a_word);
+            asm volatile("cp.async.commit_group;" ::: "memory");   // G_s = lines(s+1) + bytes(s+3)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // G_{s-1} (or the prologue's group) landed: lines(s), bytes(s+2)
+            __syncwarp();
+            // B(s+2) BEFORE D(s): the table entry it requests is consumed by C(s+2) at the top of the next iteration, and
+            // D(s)'s line scan in between is what hides that (L2) latency
+            uint64_t b_word;
+            uint2 b_entry;
+            uint32_t b_kind;
+            stage_b(s + 2, b_wordreg, b_word, b_entry, b_kind);
+            b_wordreg = a_word;
+            stage_d(s, d_word, d_kind, d_l, d_h, d_tag);
+            // rotate: s+1 becomes the D batch, s+2 the C batch
+            d_word = c_word; d_kind = c_kind; d_l = n_l; d_h = n_h; d_tag = n_tag;
+            c_word = b_word; c_entry = b_entry; c_kind = b_kind;
+        }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     flush_queue();
@@ -341,11 +411,12 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
     }
 }
 
-template <int SRC, uint32_t K>
-cudaError_t launch_t(int device, const IndexView &ix, const void *d_src, uint32_t k, const SeedPlan &plan, const PackedLayout &lay,
+template <int SRC, uint32_t K, bool DEEP>
+cudaError_t launch_shape(int device, const IndexView &ix, const void *d_src, uint32_t k, const SeedPlan &plan, const PackedLayout &lay,
                      uint64_t *d_packed, uint64_t *d_out, uint32_t *d_status, cudaStream_t st) {
     static bool prepared[64] = {};
-    const void *fn = (const void *)pack_seed_final_kernel<SRC, K>;
+    constexpr int kFinSmem = FinShape<DEEP>::kSmem;
+    const void *fn = (const void *)pack_seed_final_kernel<SRC, K, DEEP>;
     if (device < 0 || device >= 64 || !prepared[device]) {
         if (cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinSmem); e != cudaSuccess) return e;
         cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -356,8 +427,16 @@ cudaError_t launch_t(int device, const IndexView &ix, const void *d_src, uint32_
     const uint64_t full = (uint64_t)sm_count(device) * (uint64_t)per_sm;
     const uint64_t need = ((lay.n + 31) / 32 + kFinWarps - 1) / kFinWarps;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(need, full));
-    pack_seed_final_kernel<SRC, K><<<grid, kFinThreads, kFinSmem, st>>>(ix, d_src, k, plan, lay, d_packed, d_out, d_status);
+    pack_seed_final_kernel<SRC, K, DEEP><<<grid, kFinThreads, kFinSmem, st>>>(ix, d_src, k, plan, lay, d_packed, d_out, d_status);
     return cudaGetLastError();
+}
+
+template <int SRC, uint32_t K>
+cudaError_t launch_t(int device, const IndexView &ix, const void *d_src, uint32_t k, const SeedPlan &plan, const PackedLayout &lay,
+                     uint64_t *d_packed, uint64_t *d_out, uint32_t *d_status, cudaStream_t st) {
+    const char *env = getenv("MSBWT_FINAL_DEEP");  // =1: the two-buffer shape (A/B measurements)
+    if (env && atoi(env) != 0) return launch_shape<SRC, K, true>(device, ix, d_src, k, plan, lay, d_packed, d_out, d_status, st);
+    return launch_shape<SRC, K, false>(device, ix, d_src, k, plan, lay, d_packed, d_out, d_status, st);
 }
 
 }  // namespace

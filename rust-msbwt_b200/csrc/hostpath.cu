@@ -9,6 +9,7 @@
 // overlap), and the results land in disjoint slices of the caller's output -- a host-side gather, no collective.
 // There is no CPU fallback: every route ends in kernel launches.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -292,17 +293,64 @@ int u64_route(Replica &rep, const uint64_t *kmers, uint32_t k, Slice sl, CountsO
         if (int rc = reserve_search_buffers(rep, ln, k, chunk, out); rc != MSBWT_OK) return rc;
     }
     const bool with_b = packed_batch_needs_list_b(rep.view, k);
+    // MSBWT_TRACE_PIPE=1: per-chunk timeline of the lanes (copy-in, kernels, copy-out) on stderr -- a measurement aid
+    const bool trace = getenv("MSBWT_TRACE_PIPE") != nullptr;
+    struct Marks { cudaEvent_t e[4]; int lane; };
+    std::vector<Marks> marks;
+    cudaEvent_t t0 = nullptr;
+    if (trace) {
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, rep.lane[0].stream);
+    }
     uint64_t c = 0;
     for (uint64_t b = sl.begin; b < sl.end; b += chunk, c++) {
         const uint64_t m = std::min(chunk, sl.end - b);
         Lane &ln = rep.lane[c % kLanes];
+        Marks mk{};
+        if (trace) {
+            for (auto &e : mk.e) cudaEventCreate(&e);
+            mk.lane = (int)(c % kLanes);
+            cudaEventRecord(mk.e[0], ln.stream);
+        }
         CU_TRY(cudaMemcpyAsync(ln.in_b.p, kmers + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
+        if (trace) cudaEventRecord(mk.e[1], ln.stream);
         CU_TRY(launch_seed_u64(rep.view, ln.in_b.as<uint64_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(), ln.stream));
         g_launches++;
         x.h2d += m * sizeof(uint64_t);
-        if (int rc = search_and_copy_out(rep, ln, k, b, m, out, with_b, x); rc != MSBWT_OK) return rc;
+        // (search + copy-out; with tracing the boundary between them is marked inside by the extra event below)
+        CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
+                                   ln.stream, &g_call_launches, with_b));
+        flush_launches();
+        if (out.o32) {
+            CU_TRY(launch_narrow_counts(rep.device, ln.out_a.as<uint64_t>(), m, ln.out_b.as<uint32_t>(), ln.stream));
+            g_launches++;
+        }
+        if (trace) cudaEventRecord(mk.e[2], ln.stream);
+        if (out.o32) {
+            CU_TRY(cudaMemcpyAsync(out.o32 + b, ln.out_b.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ln.stream));
+            x.d2h += m * sizeof(uint32_t);
+        } else {
+            CU_TRY(cudaMemcpyAsync(out.o64 + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
+            x.d2h += m * sizeof(uint64_t);
+        }
+        if (trace) {
+            cudaEventRecord(mk.e[3], ln.stream);
+            marks.push_back(mk);
+        }
     }
-    return drain(rep);
+    if (int rc = drain(rep); rc != MSBWT_OK) return rc;
+    if (trace) {
+        fprintf(stderr, "[msbwt] u64 route on device %d: %zu chunks of %llu queries\n  chunk lane  h2d_start  h2d_end  kernels_end  d2h_end (ms)\n",
+                rep.device, marks.size(), (unsigned long long)chunk);
+        for (size_t i = 0; i < marks.size(); i++) {
+            float t[4];
+            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], t0, marks[i].e[j]);
+            fprintf(stderr, "  %5zu %4d  %9.3f %8.3f %12.3f %8.3f\n", i, marks[i].lane, t[0], t[1], t[2], t[3]);
+            for (auto &e : marks[i].e) cudaEventDestroy(e);
+        }
+        cudaEventDestroy(t0);
+    }
+    return MSBWT_OK;
 }
 
 struct AllLocks {

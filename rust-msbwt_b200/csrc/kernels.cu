@@ -492,6 +492,56 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint4 *__restrict__ b
     if (acc == 0x9E3779B9u) atomicAdd((unsigned long long *)sink, 1ull);  // practically never; defeats DCE
 }
 
+// The same measurement with the Hopper / Blackwell bulk copy: every LANE asks for its own 128-byte line with ONE
+// cp.async.bulk into its shared-memory row (completion counted in bytes by an mbarrier per warp and stage), two
+// stages per warp in flight -- against eight lanes x cp.async 16 B per line in the search kernels.  `granule` 129.
+__global__ void __launch_bounds__(256) gather_bulk_kernel(const uint4 *__restrict__ buf, uint32_t line_mask, uint32_t n_gathers,
+                                                          uint32_t seed, uint64_t *__restrict__ sink) {
+    extern __shared__ __align__(128) uint8_t gather_smem[];  // rows[8 warps][2 stages][32 x 128 B], then bars[8][2]
+    uint8_t(*rows)[2][32 * 128] = reinterpret_cast<uint8_t(*)[2][32 * 128]>(gather_smem);
+    uint64_t(*bars)[2] = reinterpret_cast<uint64_t(*)[2]>(gather_smem + 8 * 2 * 32 * 128);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t warps = gridDim.x * 8u, wg = blockIdx.x * 8u + warp;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[warp][0]), bar1 = (uint32_t)__cvta_generic_to_shared(&bars[warp][1]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const uint32_t batches = (n_gathers + 31u) / 32u;
+    uint32_t acc = 0;
+    auto issue = [&](uint32_t b, uint32_t stage) {
+        const uint32_t bar = stage ? bar1 : bar0;
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32u * 128u) : "memory");
+        __syncwarp();
+        const uint32_t gi = mix32((b * 32u + lane) ^ seed) & line_mask;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&rows[warp][stage][lane * 128u]);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];" ::"r"(dst),
+                     "l"(buf + (size_t)gi * 8u), "r"(bar)
+                     : "memory");
+    };
+    auto wait = [&](uint32_t stage, uint32_t parity) {
+        const uint32_t bar = stage ? bar1 : bar0;
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        }
+    };
+    uint32_t it = 0;
+    uint32_t b = wg;
+    if (b < batches) issue(b, 0);
+    for (; b < batches; b += warps, it++) {
+        const uint32_t stage = it & 1u;
+        if (b + warps < batches) issue(b + warps, stage ^ 1u);
+        wait(stage, (it >> 1) & 1u);
+        acc ^= *reinterpret_cast<const uint32_t *>(&rows[warp][stage][lane * 128u + 4u * (lane & 31u)]);
+        __syncwarp();
+    }
+    if (acc == 0x9E3779B9u) atomicAdd((unsigned long long *)sink, 1ull);
+}
+
 // ---------------------------------------------------------------- launch wrappers
 
 static bool is_wide(const IndexView &ix) { return ix.n_super > 1 || (ix.total >> 32) != 0; }
@@ -670,7 +720,7 @@ cudaError_t launch_constrain_ranges(int device, const IndexView &ix, const uint8
 
 cudaError_t launch_gather(int device, const void *d_buf, uint64_t buf_bytes, uint32_t granule,
                           uint64_t n_gathers, uint64_t seed, uint64_t *d_sink, cudaStream_t st) {
-    uint64_t n_granules = buf_bytes / granule;
+    uint64_t n_granules = buf_bytes / (granule == 129 ? 128 : granule);
     if (!n_granules || !n_gathers || n_gathers >= (1ull << 31)) return cudaErrorInvalidValue;
     while (n_granules & (n_granules - 1)) n_granules &= n_granules - 1;  // round down to a power of two
     if (n_granules > (1ull << 31)) n_granules = 1ull << 31;
@@ -681,6 +731,13 @@ cudaError_t launch_gather(int device, const void *d_buf, uint64_t buf_bytes, uin
         case 32: gather_kernel<2><<<grid, 256, 0, st>>>(buf, mask, (uint32_t)n_gathers, (uint32_t)seed, d_sink); break;
         case 64: gather_kernel<4><<<grid, 256, 0, st>>>(buf, mask, (uint32_t)n_gathers, (uint32_t)seed, d_sink); break;
         case 128: gather_kernel<8><<<grid, 256, 0, st>>>(buf, mask, (uint32_t)n_gathers, (uint32_t)seed, d_sink); break;
+        case 129:  // 128-byte lines, one cp.async.bulk per lane (64 KB of shared memory per CTA: 3 CTAs per SM)
+        {
+            constexpr int kBulkSmem = 8 * 2 * 32 * 128 + 8 * 2 * 8;
+            if (cudaError_t e = cudaFuncSetAttribute((const void *)gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSmem); e != cudaSuccess) return e;
+            gather_bulk_kernel<<<(unsigned)sm_count(device) * 3u, 256, kBulkSmem, st>>>(buf, mask, (uint32_t)n_gathers, (uint32_t)seed, d_sink);
+            break;
+        }
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -181,7 +181,9 @@ __host__ __device__ constexpr int oct_chunk_shift(int b) {  // cs = min(31 - b, 
 // positions (b <= 16); code c lives in line `(bucket << lb) | (fin_mix40(c) & (2^lb - 1))` under the tag
 // `fin_mix40(c) >> lb` (fin_mix40 is a bijection of the 40-bit codes, lb >= 12 so that a tag fits kFinTagBits):
 //     word 0      words in use after it (0..31), or kFinOverflow: the query takes the oct steps instead
-//     then groups `(tag << 4) | nruns` (1..15) followed by nruns words `(len << 16) | offset in the bucket`
+//     then groups `(tag << 4) | nruns` (1..15) followed by nruns words `(len << 16) | offset in the bucket`; a code
+//     with more than 15 runs in the bucket has several groups, ADJACENT to one another (the builder writes a line's
+//     groups in key order), so a reader that has found a code's first group finds the others right behind it
 // A range over two buckets also takes the oct steps.  A 31-mer = an L2-resident depth-11 table entry + ONE line.
 constexpr int kFinSyms = 20;
 constexpr int kFinCodeBits = 2 * kFinSyms;

@@ -43,6 +43,12 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool on
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(on ? 16u : 0u) : "memory");
 }
+// the same with an L2 eviction policy (createpolicy): index lines and query bytes are read once -- evict first
+__device__ __forceinline__ void cp_async16_hint(void *smem, const void *gmem, bool on, uint64_t policy) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(gmem), "r"(on ? 16u : 0u), "l"(policy)
+                 : "memory");
+}
 // `bytes` (0..16) from gmem, the rest of the 16 zero-filled
 __device__ __forceinline__ void cp_async16_partial(void *smem, const void *gmem, uint32_t bytes) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);

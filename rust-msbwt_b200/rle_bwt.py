@@ -143,6 +143,7 @@ def load_library():
         "msbwt_debug_copy_pair_image": (i32, [vp, i32, C.POINTER(u64), C.POINTER(u32), vp, vp]),
         "msbwt_pack_kmers_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp, vp]),
         "msbwt_count_kmers_packed_device": (i32, [vp, i32, vp, u32, u64, vp, vp]),
+        "msbwt_seed_kmers_u64_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
         "msbwt_count_kmers_packed_stats_device": (i32, [vp, i32, vp, u32, u64, vp, vp, vp]),
         "msbwt_debug_pack_stats": (i32, [vp, i32, vp, u32, u64, vp]),
         "msbwt_launch_count": (u64, []),
@@ -170,7 +171,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "msbwt_index_create_from_rle", "msbwt_index_create_from_npy", "msbwt_index_create_ex", "msbwt_index_create_opts",
-    "msbwt_index_create_from_npy_opts", "msbwt_count_kmers_packed_stats_device", "msbwt_debug_pack_stats", "msbwt_count_kmers_fixed_u32", "msbwt_count_kmers_u64_u32",
+    "msbwt_index_create_from_npy_opts", "msbwt_count_kmers_packed_stats_device", "msbwt_seed_kmers_u64_device", "msbwt_debug_pack_stats", "msbwt_count_kmers_fixed_u32", "msbwt_count_kmers_u64_u32",
     "msbwt_pair_index", "msbwt_debug_copy_pair_image", "msbwt_quad_index", "msbwt_debug_copy_quad_image", "msbwt_oct_index", "msbwt_oct_overflow_lines",
     "msbwt_oct_overflow_occurrences", "msbwt_oct_runs", "msbwt_oct_bucket_shift", "msbwt_oct_symbols", "msbwt_table_depth_for_k", "msbwt_debug_table_depth", "msbwt_count_kmers_u64", "msbwt_final_index", "msbwt_debug_copy_final_image",
     "msbwt_debug_copy_oct_image", "msbwt_constrain_ranges_fanout", "msbwt_constrain_ranges_fanout_device",
@@ -427,6 +428,11 @@ class RleBWT:
                           stream: int = 0, slot: int = 0) -> None:
         _check(load_library().msbwt_pack_kmers_device(self.handle, slot, d_syms, k, n, d_packed, d_out, d_status,
                                                       stream or None), "pack_kmers_device")
+
+    def seed_kmers_u64_device(self, d_kmers: int, k: int, n: int, d_packed: int, d_out: int, stream: int = 0, slot: int = 0) -> None:
+        """pack stage for device-resident k-mers held as 2-bit-per-symbol integers (k <= 32)"""
+        _check(load_library().msbwt_seed_kmers_u64_device(self.handle, slot, d_kmers, k, n, d_packed, d_out, stream),
+               "seed_kmers_u64_device")
 
     def count_kmers_packed_device(self, d_packed: int, k: int, n: int, d_out: int, stream: int = 0,
                                   slot: int = 0) -> None:

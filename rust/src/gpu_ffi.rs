@@ -18,6 +18,10 @@ pub struct msbwt_options {
     pub quad_index: i32,
     pub oct_index: i32,
     pub oct_bucket_shift: i32,
+    pub keep_quad_index: i32,     // ABI 4: -1 automatic
+    pub final_index: i32,         // ABI 4: -1 automatic
+    pub final_bucket_shift: i32,  // ABI 4: 0 default
+    pub final_lines_log2: i32,    // ABI 4: 0 automatic
 }
 
 pub const MSBWT_OK: c_int = 0;
@@ -33,6 +37,7 @@ extern "C" {
     pub fn msbwt_index_create_from_npy(path: *const c_char, devices: *const c_int, ndev: c_int, err: *mut c_int) -> *mut msbwt_index;
     pub fn msbwt_index_create_ex(rle: *const u8, len: u64, devices: *const c_int, ndev: c_int, superblock_shift: u32, suffix_table_s: c_int, err: *mut c_int) -> *mut msbwt_index;
     pub fn msbwt_index_create_opts(rle: *const u8, len: u64, devices: *const c_int, ndev: c_int, opts: *const msbwt_options, err: *mut c_int) -> *mut msbwt_index;
+    pub fn msbwt_index_create_from_npy_opts(path: *const c_char, devices: *const c_int, ndev: c_int, opts: *const msbwt_options, err: *mut c_int) -> *mut msbwt_index;
     pub fn msbwt_index_destroy(idx: *mut msbwt_index);
     pub fn msbwt_total_size(idx: *const msbwt_index) -> u64;
     pub fn msbwt_symbol_count(idx: *const msbwt_index, sym: u8) -> u64;
@@ -57,6 +62,17 @@ extern "C" {
     pub fn msbwt_final_index(idx: *const msbwt_index) -> c_int;
     pub fn msbwt_debug_copy_final_image(idx: *const msbwt_index, slot: c_int, nlines: *mut u64, bucket_shift: *mut u32, lines_log2: *mut u32, overflow_lines: *mut u64, lines: *mut u32) -> c_int;
     pub fn msbwt_count_kmers_u64(idx: *const msbwt_index, kmers: *const u64, k: u32, n: u64, out: *mut u64) -> c_int;
+    pub fn msbwt_count_kmers_fixed_u32(idx: *const msbwt_index, syms: *const u8, k: u32, n: u64, out: *mut u32) -> c_int;
+    pub fn msbwt_count_kmers_u64_u32(idx: *const msbwt_index, kmers: *const u64, k: u32, n: u64, out: *mut u32) -> c_int;
+    pub fn msbwt_seed_kmers_u64_device(idx: *const msbwt_index, slot: c_int, d_kmers: *const u64, k: u32, n: u64, d_packed: *mut u64, d_out: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn msbwt_debug_pack_stats(idx: *const msbwt_index, slot: c_int, d_packed: *const u64, k: u32, n: u64, out6: *mut u64) -> c_int;
+    pub fn msbwt_count_kmers_packed_stats_device(idx: *const msbwt_index, slot: c_int, d_packed: *const u64, k: u32, n: u64, d_out: *mut u64, d_stats: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn msbwt_build_rle_bwt(reads: *const u8, n_reads: u64, read_len: u32, reads_on_device: c_int, device: c_int, rle: *mut *mut u8, rle_len: *mut u64, total: *mut u64) -> c_int;
+    pub fn msbwt_build_rle_bwt_ragged(syms: *const u8, offsets: *const u64, n_reads: u64, device: c_int, rle: *mut *mut u8, rle_len: *mut u64, total: *mut u64) -> c_int;
+    pub fn msbwt_buffer_free(p: *mut u8);
+    pub fn msbwt_convert_to_rle(text: *const u8, n: u64, rle: *mut *mut u8, rle_len: *mut u64) -> c_int;
+    pub fn msbwt_save_rle_npy(rle: *const u8, len: u64, path: *const c_char) -> c_int;
+    pub fn msbwt_save_runs_npy(syms: *const u8, counts: *const u64, nruns: u64, path: *const c_char) -> c_int;
     pub fn msbwt_oct_runs(idx: *const msbwt_index) -> u64;
     pub fn msbwt_oct_overflow_lines(idx: *const msbwt_index) -> u64;
     pub fn msbwt_oct_overflow_occurrences(idx: *const msbwt_index) -> u64;

@@ -65,6 +65,21 @@ impl GpuRleBWT {
         assert!(rc == ffi::MSBWT_OK, "count_kmers_fixed failed: {}", last_error());
         out
     }
+    /// K-mers the caller holds as 2-bit-per-symbol integers (k <= 32, first symbol most significant, A,C,G,T = 0..3):
+    /// 8 bytes per query over the link instead of k.
+    pub fn count_kmers_u64(&self, kmers: &[u64], k: usize) -> Vec<u64> {
+        let mut out = vec![0u64; kmers.len()];
+        let rc = unsafe { ffi::msbwt_count_kmers_u64(self.handle, kmers.as_ptr(), k as u32, kmers.len() as u64, out.as_mut_ptr()) };
+        assert!(rc == ffi::MSBWT_OK, "count_kmers_u64 failed: {}", last_error());
+        out
+    }
+    /// The same with 32-bit counts (index below 2^32 symbols): 4 bytes per query on the way back.
+    pub fn count_kmers_u64_u32(&self, kmers: &[u64], k: usize) -> Vec<u32> {
+        let mut out = vec![0u32; kmers.len()];
+        let rc = unsafe { ffi::msbwt_count_kmers_u64_u32(self.handle, kmers.as_ptr(), k as u32, kmers.len() as u64, out.as_mut_ptr()) };
+        assert!(rc == ffi::MSBWT_OK, "count_kmers_u64_u32 failed: {}", last_error());
+        out
+    }
 }
 
 impl Default for GpuRleBWT {

@@ -180,3 +180,25 @@ def test_npy_reader_error_classes_match_oracle(tmp_path, two_string_npy):
         except M.MsbwtError as e:
             got = {3: "panic", 6: "ok"}.get(e.code, f"code{e.code}")  # ENODEV == parsed fine, no device here
         assert got == want, name
+
+
+def test_rust_shim_sources_stay_in_sync_with_the_library():
+    """rust/ cannot be compiled here (no cargo): at least its file list and its `extern "C"` block must follow the
+    library -- build.rs compiles exactly the translation units build.py does, and gpu_ffi.rs binds only symbols
+    include/msbwt_gpu.h declares, every query / construction / codec entry point among them."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("msbwt_build", os.path.join(root, "rust-msbwt_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    build_rs = open(os.path.join(root, "rust", "build.rs")).read()
+    assert set(re.findall(r'"(\w+\.cu)"', build_rs)) == set(b.SOURCES)
+    assert set(re.findall(r'"(\w+\.cpp)"', build_rs)) == set(b.HOST_SOURCES)
+    header = open(os.path.join(root, "include", "msbwt_gpu.h")).read()
+    declared = set(re.findall(r"\b(msbwt_\w+)\s*\(", header))
+    bound = set(re.findall(r"pub fn (msbwt_\w+)\(", open(os.path.join(root, "rust", "src", "gpu_ffi.rs")).read()))
+    assert bound <= declared, bound - declared
+    must = {n for n in declared if not n.startswith("msbwt_debug_") and n not in (
+        "msbwt_gather_bench", "msbwt_host_pack_threads", "msbwt_last_transfer_bytes")}
+    assert must <= bound, must - bound

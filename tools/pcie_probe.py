@@ -38,6 +38,23 @@ def main():
                 torch.cuda.synchronize()
                 best = min(best, time.perf_counter() - t0)
             res[f"{name}_chunk{chunk >> 20}MB_GBps_each_direction"] = nbytes / best / 1e9
+    # the library's lane pattern: L streams, each chunk = H2D -> a kernel -> D2H on ONE stream, chunks round-robin
+    for lanes in (2, 5, 8):
+        for chunk in (1 << 22, 1 << 24):
+            streams = [torch.cuda.Stream() for _ in range(lanes)]
+            best = 1e9
+            nb = 800_000_000 // chunk * chunk
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for c, a in enumerate(range(0, nb, chunk)):
+                    with torch.cuda.stream(streams[c % lanes]):
+                        d_in[a:a + chunk].copy_(h_in[a:a + chunk], non_blocking=True)
+                        d_out[a:a + chunk].copy_(d_in[a:a + chunk])          # stands in for the kernels
+                        h_out[a:a + chunk].copy_(d_out[a:a + chunk], non_blocking=True)
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            res[f"lanes{lanes}_chunk{chunk >> 20}MB_GBps_each_direction"] = nb / best / 1e9
     print(json.dumps(res), flush=True)
 
 
