@@ -113,7 +113,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -520,7 +520,7 @@ def measure_ours(args, cfg, ctx, primary: bool):
             os.environ["MSBWT_HOST_THREADS"] = str(min(64, cores))
             if not strong:
                 from harness import synth
-                reads, _, _ = build_reads_and_bwt(cfg, dev, True)
+                reads = synth.make_reads(cfg["reads"], cfg["read_len"], cfg["coverage"], cfg["error"], device=dev)   # same seeds: same reads
                 q_dev_list = [synth.make_queries(reads, k, cfg["n_read"], cfg["n_random"], seed_offset=1000 * r) for r in range(world)]
                 del reads
                 torch.cuda.empty_cache()

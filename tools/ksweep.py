@@ -1,9 +1,8 @@
 """BASELINE.json configs[3]: k-sweep (k = 15 / 31 / 63 / 101) over the 1.51 Gsymbol BWT of configs[2],
 10 M read-sampled queries per k, kernel-only (queries resident in HBM), each k checked against the CPU
-oracle on a sample.  Also measures what exact-duplicate grouping of a batch would buy: the batch is
-sorted + uniqued with torch on the device (harness-level stand-in for the planned native co-lex
-sort/group stage), the engine runs on the unique k-mers, and the time of both variants is reported
-(sort time included and shown separately).
+oracle on a sample, with the index traffic of every k counted by the counting build of the search kernel.
+(What grouping equal k-mers of a batch would buy is measured on the full 100 M batch by tools/group_bench.py:
+profiles/r2_group_cfg3.json.)
 
     python tools/ksweep.py [--reads 10000000] [--queries 10000000] > gpurun_out/ksweep.json
 """
@@ -54,7 +53,8 @@ def main():
           f"lanes={bwt.kernel_lanes}, built in {time.time() - t0:.1f}s", file=sys.stderr)
     stream = torch.cuda.current_stream().cuda_stream
     out = {"bwt_symbols": total, "suffix_table_s": bwt.suffix_table_s, "kernel_lanes": bwt.kernel_lanes,
-           "quad_index": bwt.quad_index, "pair_index": bwt.pair_index,
+           "quad_index": bwt.quad_index, "pair_index": bwt.pair_index, "oct_index": bwt.oct_index, "oct_bucket_shift": bwt.oct_bucket_shift,
+           "final_index": bwt.final_index, "index_bytes": bwt.index_bytes,
            "queries_per_k": args.queries, "results": []}
     for k in (15, 31, 63, 101):
         q = synth.make_queries(reads, k, args.queries, 0, seed_offset=k)
@@ -65,23 +65,29 @@ def main():
         want = orc.count_kmers_fixed(q[:m].cpu().numpy(), k, threads=os.cpu_count() or 1)
         assert (d_out[:m].cpu().numpy().astype(np.uint64) == want).all(), f"parity failed at k={k}"
         steps, two, hits = orc.count_kmers_stats_skip(q[:m].cpu().numpy(), k, 7, bwt.suffix_table_s)
-        # grouped variant: exact duplicates collapse (co-lex sort + group; torch stand-in)
-        t_sort = timed(lambda: torch.unique(q, dim=0, return_inverse=True), reps=2)
-        uq, inv = torch.unique(q, dim=0, return_inverse=True)
-        nu = uq.shape[0]
-        u_out = torch.zeros(nu, dtype=torch.int64, device=dev)
-        ms_u = timed(lambda: bwt.count_kmers_fixed_device(uq.data_ptr(), k, nu, u_out.data_ptr(), 0, stream))
-        assert (u_out[inv] == d_out).all()
+        # what the two stages fetch: the pack stage's own counters + the counting build of the search kernel
+        d_packed = torch.empty(bwt.packed_bytes(k, n) // 8, dtype=torch.int64, device=dev)
+        d_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        d_stats = torch.zeros(8, dtype=torch.int64, device=dev)
+        d_out2 = torch.zeros(n, dtype=torch.int64, device=dev)
+        ms_pack = timed(lambda: bwt.pack_kmers_device(q.data_ptr(), k, n, d_packed.data_ptr(), d_out2.data_ptr(), d_status.data_ptr(), stream))
+        ps = bwt.pack_stats(d_packed.data_ptr(), k, n)
+        bwt.count_kmers_packed_stats_device(d_packed.data_ptr(), k, n, d_out2.data_ptr(), d_stats.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert (d_out2 == d_out).all()
+        st = [int(v) for v in d_stats.cpu().tolist()]
+        lines = ps["final_lines"] + st[0] + st[1] + st[4]
         out["results"].append({
-            "k": k, "queries": n, "ms_ungrouped": ms, "queries_per_s_ungrouped": n / (ms / 1e3),
-            "mean_steps_after_table": steps / m, "two_block_share": two / max(1, steps),
-            "ns_per_step_per_query_chain": 1e6 * ms / (steps / m) / 1.0 if steps else None,
-            "unique_queries": nu, "ms_search_on_unique": ms_u, "ms_torch_sort_unique": t_sort,
-            "queries_per_s_grouped_excl_sort": n / (ms_u / 1e3),
-            "queries_per_s_grouped_incl_torch_sort": n / ((ms_u + t_sort) / 1e3),
+            "k": k, "queries": n, "suffix_table_depth_used": bwt.table_depth_for_k(k), "ms": ms, "ms_pack_stage": ms_pack,
+            "queries_per_s": n / (ms / 1e3),
+            "reference_steps_after_table": steps / m,
+            "line_fills_per_query": lines / n, "one_step_blocks_per_query": st[6] / n,
+            "pack_stage": ps, "search_oct_lines": st[0], "search_final_lines": st[1], "search_quad_lines": st[4],
+            "ns_per_query": 1e6 * ms / n, "line_fills_per_s": lines / (ms / 1e3),
             "parity_checked": m})
+        del d_packed, d_status, d_stats, d_out2
         print(out["results"][-1], file=sys.stderr)
-        del q, d_out, uq, inv, u_out
+        del q, d_out
     print(json.dumps(out))
 
 
