@@ -51,3 +51,26 @@ def test_our_arm_refuses_to_run_without_a_device():
     res = run_bench("--workload", "tiny", "--steps", "1", "--warmup", "1")
     assert res.returncode != 0
     assert "no CPU fallback" in (res.stderr + res.stdout)
+
+
+def test_bench_helpers_on_cpu():
+    """encode_u64 (the packed-integer input format of msbwt_count_kmers_u64: first symbol most significant, A,C,G,T =
+    0..3) and the `config` object, which must be identical in both arms"""
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    q = torch.tensor([[1, 2, 3, 5], [5, 5, 5, 5], [1, 1, 1, 1]], dtype=torch.uint8)
+    assert bench.encode_u64(q, 4).tolist() == [0b00011011, 0b11111111, 0]
+    rng = np.random.default_rng(0)
+    q = rng.choice(np.array([1, 2, 3, 5], dtype=np.uint8), size=(1000, 31))
+    want = np.zeros(1000, dtype=np.uint64)
+    code = np.zeros(6, dtype=np.uint64)
+    code[[1, 2, 3, 5]] = [0, 1, 2, 3]
+    for j in range(31):
+        want = (want << np.uint64(2)) | code[q[:, j]]
+    assert (bench.encode_u64(torch.from_numpy(q), 31).numpy().view(np.uint64) == want).all()
+    c = bench.workload_config(bench.WORKLOADS["cfg3"], 1_510_000_000, 4)
+    assert c["workload"].startswith("configs[2]") and c["queries"] == 100_000_000 and c["k"] == 31
+    assert bench.workload_config(bench.WORKLOADS["cfg5"], 3_020_000_000, 8)["queries"] == 1_000_000_000
+    assert bench.HEADLINE == "cfg3" and bench.WORKLOADS["cfg3"]["scaling"] == "strong"
