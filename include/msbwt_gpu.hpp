@@ -40,6 +40,22 @@ inline std::vector<uint8_t> convert_stoi(const std::string &s) {
     return v;
 }
 
+// bwt_converter.rs:26-80 / 102-130: text BWT -> RLE bytes; RLE bytes -> msbwt2's .npy container
+inline std::vector<uint8_t> convert_to_vec(const std::string &text) {
+    uint8_t *rle = nullptr;
+    uint64_t n = 0;
+    const int rc = msbwt_convert_to_rle(reinterpret_cast<const uint8_t *>(text.data()), text.size(), &rle, &n);
+    if (rc != MSBWT_OK) throw Panic(rc, msbwt_last_error());
+    std::vector<uint8_t> out(rle, rle + n);
+    msbwt_buffer_free(rle);
+    return out;
+}
+inline void save_bwt_numpy(const std::vector<uint8_t> &rle, const std::string &filename) {
+    const int rc = msbwt_save_rle_npy(rle.data(), rle.size(), filename.c_str());
+    if (rc == MSBWT_EIO) throw IoError(msbwt_last_error());
+    if (rc != MSBWT_OK) throw Panic(rc, msbwt_last_error());
+}
+
 class RleBWT {
   public:
     RleBWT() = default;                                            // RleBWT::new()
@@ -93,10 +109,16 @@ class RleBWT {
         check(msbwt_count_kmers_fixed(h_, syms.data(), k, out.size(), out.data()));
         return out;
     }
-    // k-mers held as integers (k <= 32, first symbol in the most significant of the 2k bits; A,C,G,T = 0..3) -- experimental
+    // k-mers held as integers (k <= 32, first symbol in the most significant of the 2k bits; A,C,G,T = 0..3)
     std::vector<uint64_t> count_kmers_u64(const std::vector<uint64_t> &kmers, uint32_t k) const {
         std::vector<uint64_t> out(kmers.size());
         check(msbwt_count_kmers_u64(h_, kmers.data(), k, kmers.size(), out.data()));
+        return out;
+    }
+    // the same with 32-bit counts (index below 2^32 symbols): 4 bytes per query on the way back
+    std::vector<uint32_t> count_kmers_u64_u32(const std::vector<uint64_t> &kmers, uint32_t k) const {
+        std::vector<uint32_t> out(kmers.size());
+        check(msbwt_count_kmers_u64_u32(h_, kmers.data(), k, kmers.size(), out.data()));
         return out;
     }
     // the four constrain_range calls (A, C, G, T) of one extension step, from one fetch of the index blocks

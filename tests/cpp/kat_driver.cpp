@@ -61,6 +61,16 @@ int main(int argc, char **argv) {
     threw = false;
     try { msbwt::RleBWT x; x.load_numpy_file("/nonexistent/file.npy"); } catch (const msbwt::IoError &) { threw = true; }
     EXPECT(threw);
+    // bwt_converter.rs:246-256 (convert_to_vec KAT), then the same index through the packed-integer entry points
+    EXPECT(msbwt::convert_to_vec("GTN$$ACCC$G") == rle);
+    threw = false;
+    try { msbwt::convert_to_vec("ACGX"); } catch (const msbwt::Panic &) { threw = true; }
+    EXPECT(threw);
+    // ACG = 0b000110, CC = 0b0101, T = 0b11 (first symbol most significant): counts in "CCGT$ N$ ACG$"
+    const std::vector<uint64_t> km3 = {0b000110u};
+    EXPECT(b.count_kmers_u64(km3, 3)[0] == b.count_kmer(convert_stoi("ACG")));
+    EXPECT(b.count_kmers_u64({0b0101u}, 2)[0] == b.count_kmer(convert_stoi("CC")));
+    EXPECT(b.count_kmers_u64_u32({0b11u, 0b00u}, 1)[0] == 1 && b.count_kmers_u64_u32({0b11u, 0b00u}, 1)[1] == 1);
     printf(failures ? "kat_driver: %d failure(s)\n" : "kat_driver: all passed (%d)\n", failures);
     return failures ? 1 : 0;
 }
