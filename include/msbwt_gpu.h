@@ -179,7 +179,9 @@ int msbwt_count_kmers(const msbwt_index *idx, const uint8_t *syms, const uint64_
  * k-mers 2 bits per symbol into pinned staging while earlier chunks are copied and searched, so the
  * link carries 8*ceil(k/32) bytes per query instead of k; k-mers holding any other symbol, and every
  * batch when the pool is off, are copied as bytes and packed / validated on the device.  Counts
- * are identical either way.  `syms` and `out` may be pageable or pinned (msbwt_host_alloc). */
+ * are identical either way.  `syms` and `out` may be pageable or pinned (msbwt_host_alloc): pinned buffers are read
+ * and written by the copy engines directly; pageable ones are staged chunk by chunk through pinned buffers of the
+ * library by its worker threads (about half the throughput of pinned memory, host-memory-bound). */
 int msbwt_count_kmers_fixed(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_t n,
                             uint64_t *out);
 /* The same counts for k-mers the caller already holds as integers, 2 bits per symbol -- what k-mer counting

@@ -77,6 +77,7 @@ int finish_replica(msbwt_index *idx, size_t slot, std::unique_ptr<Replica> rep, 
     for (auto &ln : rep->lane) {
         CU_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
         CU_TRY(cudaEventCreateWithFlags(&ln.h2d_done, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&ln.d2h_done, cudaEventDisableTiming));
     }
     rep->view.blocks = rep->d_blocks;
     rep->view.cbase = rep->d_cbase;

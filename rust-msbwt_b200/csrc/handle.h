@@ -75,8 +75,11 @@ constexpr int kLanes = kPackLanes + kRawLanes;
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t h2d_done = nullptr;  // the lane's pinned staging buffer may be rewritten after this
+    cudaEvent_t d2h_done = nullptr;  // the lane's pinned result buffer holds the counts of its last chunk after this
     DevBuf in_a, in_b, in_c, packed, out_a, out_b;
-    PinnedBuf h_stage;
+    PinnedBuf h_stage;               // input staging: host-packed words, or a copy of a PAGEABLE caller buffer's chunk
+    PinnedBuf h_out;                 // result staging when the caller's output buffer is pageable
+    uint64_t pend_first = 0, pend_count = 0;  // queries whose counts wait in h_out to be copied to the caller (0 = none)
 };
 
 struct Replica {
@@ -112,7 +115,9 @@ struct Replica {
         for (auto &ln : lane) {
             if (ln.stream) cudaStreamDestroy(ln.stream);
             if (ln.h2d_done) cudaEventDestroy(ln.h2d_done);
+            if (ln.d2h_done) cudaEventDestroy(ln.d2h_done);
             ln.h_stage.release();
+            ln.h_out.release();
             ln.in_a.release(); ln.in_b.release(); ln.in_c.release();
             ln.packed.release(); ln.out_a.release(); ln.out_b.release();
         }

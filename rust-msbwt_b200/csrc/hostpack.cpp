@@ -141,6 +141,7 @@ struct HostPool::Impl {
     std::atomic<int> pending{0};
     std::atomic<int> sleepers{0};
     std::atomic<bool> in_session{false};
+    int session_depth = 0;  // begin_session / end_session nest (guarded by mu)
     bool stop = false;
     int nthreads = 1;
 
@@ -218,12 +219,19 @@ void HostPool::begin_session() {
     if (impl_->nthreads == 1) return;
     {
         std::lock_guard<std::mutex> lk(impl_->mu);
+        if (impl_->session_depth++ > 0) return;  // nested: the workers are awake already
         impl_->in_session.store(true, std::memory_order_release);
     }
     impl_->cv_go.notify_all();
 }
 
-void HostPool::end_session() { impl_->in_session.store(false, std::memory_order_release); }
+void HostPool::end_session() {
+    if (impl_->nthreads == 1) return;
+    std::lock_guard<std::mutex> lk(impl_->mu);
+    if (--impl_->session_depth > 0) return;
+    impl_->session_depth = 0;
+    impl_->in_session.store(false, std::memory_order_release);
+}
 
 // inside a session only
 void HostPool::run(const std::function<void(int, int)> &fn) {

@@ -19,8 +19,8 @@ void host_pack_range(const uint8_t *syms, uint32_t k, uint64_t n_total, uint64_t
 int host_threads_available();
 
 // fork-join pool: between begin_session() and end_session() the workers spin, and run(fn) calls
-// fn(tid, nthreads) on every worker (the caller is worker 0) and returns when all are done.  One session
-// and one run at a time; outside a session the workers sleep.
+// fn(tid, nthreads) on every worker (the caller is worker 0) and returns when all are done.  Sessions nest
+// (the workers park when the outermost one ends); one run at a time; outside a session the workers sleep.
 class HostPool {
   public:
     explicit HostPool(int nthreads);

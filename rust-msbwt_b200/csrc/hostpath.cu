@@ -111,70 +111,12 @@ int drain(Replica &rep) {
     return MSBWT_OK;
 }
 
-// search the lane's packed scratch and send the counts of queries [b, b + m) home
-int search_and_copy_out(Replica &rep, Lane &ln, uint32_t k, uint64_t b, uint64_t m, CountsOut out, bool with_b, Xfer &x) {
-    CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
-                               ln.stream, &g_call_launches, with_b));
-    flush_launches();
-    if (out.o32) {
-        CU_TRY(launch_narrow_counts(rep.device, ln.out_a.as<uint64_t>(), m, ln.out_b.as<uint32_t>(), ln.stream));
-        g_launches++;
-        CU_TRY(cudaMemcpyAsync(out.o32 + b, ln.out_b.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ln.stream));
-        x.d2h += m * sizeof(uint32_t);
-    } else {
-        CU_TRY(cudaMemcpyAsync(out.o64 + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-        x.d2h += m * sizeof(uint64_t);
-    }
-    return MSBWT_OK;
-}
-
-int reserve_search_buffers(Replica &rep, Lane &ln, uint32_t k, uint64_t chunk, CountsOut out) {
-    CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, std::max<uint64_t>(1, chunk)).total() * sizeof(uint64_t)));
-    CU_TRY(ln.out_a.reserve(std::max<uint64_t>(1, chunk) * sizeof(uint64_t)));
-    if (out.o32) CU_TRY(ln.out_b.reserve(std::max<uint64_t>(1, chunk) * sizeof(uint32_t)));
-    return MSBWT_OK;
-}
-
-// The byte route: the caller's symbol bytes are copied to the device as they are and packed + validated there
-// (pack_seed_kernel).  PCIe carries k bytes per query.
-int bytes_route(Replica &rep, const uint8_t *syms, uint32_t k, Slice sl, CountsOut out, Xfer &x) {
-    const uint64_t chunk = pick_chunk(sl.len(), kChunkQueries, k);
-    for (auto &ln : rep.lane) {
-        CU_TRY(cudaStreamSynchronize(ln.stream));
-        CU_TRY(ln.in_a.reserve(std::max<uint64_t>(1, chunk * k)));
-        if (int rc = reserve_search_buffers(rep, ln, k, chunk, out); rc != MSBWT_OK) return rc;
-    }
-    if (int rc = reset_status(rep); rc != MSBWT_OK) return rc;
-    uint64_t c = 0;
-    for (uint64_t b = sl.begin; b < sl.end; b += chunk, c++) {
-        const uint64_t m = std::min(chunk, sl.end - b);
-        const int li = (int)(c % kLanes);
-        Lane &ln = rep.lane[li];
-        if (k) CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + b * k, m * k, cudaMemcpyHostToDevice, ln.stream));
-        CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
-                                rep.d_status + li, ln.stream));
-        g_launches++;
-        x.h2d += m * k;
-        if (int rc = search_and_copy_out(rep, ln, k, b, m, out, true, x); rc != MSBWT_OK) return rc;
-    }
-    if (int rc = drain(rep); rc != MSBWT_OK) return rc;
-    return check_status(rep, "count_kmers_fixed");
-}
-
 // Host threads a replica's packers may use: the process's share of the host (hostpack.cpp) divided by the
 // handle's devices, each of which is fed by its own thread.
 int replica_pack_threads(size_t ndev) { return std::max(1, host_threads_available() / (int)std::max<size_t>(1, ndev)); }
 
-// Host-side 2-bit packing pays off when enough host threads can feed it: the byte route moves k bytes per query
-// over PCIe (~55 GB/s), the packed route 8 * ceil(k/32) but needs the CPU to read the k bytes.
-bool use_host_pack(uint32_t k, uint64_t n, size_t ndev) {
-    if (!k || k > max_host_packed_k() || n < 4096) return false;
-    if (const char *env = getenv("MSBWT_HOST_PACK")) return atoi(env) != 0;
-    return replica_pack_threads(ndev) >= 8;
-}
-
-// true when `p` is page-locked host memory the copy engine can read while the host does something else
-// (cudaMemcpyAsync from pageable memory stages through the driver and holds the calling thread)
+// true when `p` is page-locked host memory the copy engine can read / write while the host does something else
+// (cudaMemcpyAsync on pageable memory stages through the driver and holds the calling thread)
 bool is_pinned_host(const void *p) {
     cudaPointerAttributes a{};
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -182,6 +124,155 @@ bool is_pinned_host(const void *p) {
         return false;
     }
     return a.type == cudaMemoryTypeHost;
+}
+
+HostPool &replica_pool(Replica &rep, size_t ndev) {
+    const int want = replica_pack_threads(ndev);
+    if (!rep.pool || rep.pool->size() != want) rep.pool = std::make_unique<HostPool>(want);
+    return *rep.pool;
+}
+
+struct PoolSession {  // the workers stay hot for the duration of one call only
+    HostPool &p;
+    explicit PoolSession(HostPool &pool) : p(pool) { p.begin_session(); }
+    ~PoolSession() { p.end_session(); }
+};
+
+// PAGEABLE caller buffers (a Rust Vec, a numpy array): the copy engine cannot touch them asynchronously -- measured
+// on B200, 117 ms per 100 M packed 31-mers through cudaMemcpyAsync on pageable memory against 18.8 ms on pinned
+// memory (profiles/r2p_e2e_probe.log).  So a pageable input chunk is first copied into the lane's pinned staging
+// buffer by the replica's worker threads, and a pageable output receives its counts from the lane's pinned result
+// buffer the same way once the lane's copy-out has completed; the copy engines keep running underneath.
+struct HostStage {
+    HostPool *pool = nullptr;
+    bool in = false, out = false;
+    CountsOut dst;
+    size_t out_elem = sizeof(uint64_t);
+};
+
+void parallel_copy(HostPool *pool, void *dst, const void *src, size_t bytes) {
+    if (!pool || pool->size() == 1 || bytes < (1u << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    pool->run([&](int tid, int nt) {
+        const size_t a = bytes * (size_t)tid / (size_t)nt, b = bytes * (size_t)(tid + 1) / (size_t)nt;
+        memcpy((char *)dst + a, (const char *)src + a, b - a);
+    });
+}
+
+HostStage make_stage(Replica &rep, size_t ndev, const void *in_ptr, CountsOut out) {
+    HostStage hs;
+    hs.dst = out;
+    hs.out_elem = out.o32 ? sizeof(uint32_t) : sizeof(uint64_t);
+    hs.in = in_ptr && !is_pinned_host(in_ptr);
+    hs.out = !is_pinned_host(out.o32 ? (const void *)out.o32 : (const void *)out.o64);
+    if (hs.in || hs.out) hs.pool = &replica_pool(rep, ndev);
+    for (auto &ln : rep.lane) ln.pend_count = 0;
+    return hs;
+}
+
+// the counts of the lane's last chunk, waiting in its pinned result buffer -> the caller's (pageable) output
+int flush_lane_output(Lane &ln, HostStage &hs) {
+    if (!ln.pend_count) return MSBWT_OK;
+    CU_TRY(cudaEventSynchronize(ln.d2h_done));
+    char *dst = hs.dst.o32 ? (char *)(hs.dst.o32 + ln.pend_first) : (char *)(hs.dst.o64 + ln.pend_first);
+    parallel_copy(hs.pool, dst, ln.h_out.p, ln.pend_count * hs.out_elem);
+    ln.pend_count = 0;
+    return MSBWT_OK;
+}
+
+int flush_all_outputs(Replica &rep, HostStage &hs) {
+    for (auto &ln : rep.lane)
+        if (int rc = flush_lane_output(ln, hs); rc != MSBWT_OK) return rc;
+    return MSBWT_OK;
+}
+
+// `bytes` of the caller's input for this chunk, where the copy engine may read them: the caller's own (pinned)
+// memory, or the lane's staging buffer after a copy (the previous copy-in from that buffer has completed)
+int stage_input(Lane &ln, HostStage &hs, const void *src, size_t bytes, const void **where) {
+    *where = src;
+    if (!hs.in || !bytes) return MSBWT_OK;
+    CU_TRY(cudaEventSynchronize(ln.h2d_done));
+    parallel_copy(hs.pool, ln.h_stage.p, src, bytes);
+    *where = ln.h_stage.p;
+    return MSBWT_OK;
+}
+
+// search the lane's packed scratch and send the counts of queries [b, b + m) home
+int search_and_copy_out(Replica &rep, Lane &ln, uint32_t k, uint64_t b, uint64_t m, HostStage &hs, bool with_b, Xfer &x) {
+    CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
+                               ln.stream, &g_call_launches, with_b));
+    flush_launches();
+    const void *d_res = ln.out_a.p;
+    if (hs.dst.o32) {
+        CU_TRY(launch_narrow_counts(rep.device, ln.out_a.as<uint64_t>(), m, ln.out_b.as<uint32_t>(), ln.stream));
+        g_launches++;
+        d_res = ln.out_b.p;
+    }
+    void *h_res = hs.dst.o32 ? (void *)(hs.dst.o32 + b) : (void *)(hs.dst.o64 + b);
+    if (hs.out) h_res = ln.h_out.p;
+    CU_TRY(cudaMemcpyAsync(h_res, d_res, m * hs.out_elem, cudaMemcpyDeviceToHost, ln.stream));
+    x.d2h += m * hs.out_elem;
+    if (hs.out) {
+        CU_TRY(cudaEventRecord(ln.d2h_done, ln.stream));
+        ln.pend_first = b;
+        ln.pend_count = m;
+    }
+    return MSBWT_OK;
+}
+
+int reserve_search_buffers(Replica &rep, Lane &ln, uint32_t k, uint64_t chunk, const HostStage &hs) {
+    CU_TRY(ln.packed.reserve(packed_layout(rep.view, k, std::max<uint64_t>(1, chunk)).total() * sizeof(uint64_t)));
+    CU_TRY(ln.out_a.reserve(std::max<uint64_t>(1, chunk) * sizeof(uint64_t)));
+    if (hs.dst.o32) CU_TRY(ln.out_b.reserve(std::max<uint64_t>(1, chunk) * sizeof(uint32_t)));
+    if (hs.out) CU_TRY(ln.h_out.reserve(std::max<uint64_t>(1, chunk) * hs.out_elem));
+    return MSBWT_OK;
+}
+
+// The byte route: the caller's symbol bytes are copied to the device as they are and packed + validated there
+// (pack_seed_kernel / pack_seed_final_kernel).  PCIe carries k bytes per query.
+int bytes_route(Replica &rep, size_t ndev, const uint8_t *syms, uint32_t k, Slice sl, CountsOut out, Xfer &x) {
+    const uint64_t chunk = pick_chunk(sl.len(), kChunkQueries, k);
+    HostStage hs = make_stage(rep, ndev, k ? syms : nullptr, out);
+    std::unique_ptr<PoolSession> session;
+    if (hs.pool) session = std::make_unique<PoolSession>(*hs.pool);
+    for (auto &ln : rep.lane) {
+        CU_TRY(cudaStreamSynchronize(ln.stream));
+        CU_TRY(ln.in_a.reserve(std::max<uint64_t>(1, chunk * k)));
+        if (hs.in) CU_TRY(ln.h_stage.reserve(std::max<uint64_t>(1, chunk * k)));
+        if (int rc = reserve_search_buffers(rep, ln, k, chunk, hs); rc != MSBWT_OK) return rc;
+    }
+    if (int rc = reset_status(rep); rc != MSBWT_OK) return rc;
+    uint64_t c = 0;
+    for (uint64_t b = sl.begin; b < sl.end; b += chunk, c++) {
+        const uint64_t m = std::min(chunk, sl.end - b);
+        const int li = (int)(c % kLanes);
+        Lane &ln = rep.lane[li];
+        if (int rc = flush_lane_output(ln, hs); rc != MSBWT_OK) return rc;
+        if (k) {
+            const void *src = nullptr;
+            if (int rc = stage_input(ln, hs, syms + b * k, m * k, &src); rc != MSBWT_OK) return rc;
+            CU_TRY(cudaMemcpyAsync(ln.in_a.p, src, m * k, cudaMemcpyHostToDevice, ln.stream));
+            if (hs.in) CU_TRY(cudaEventRecord(ln.h2d_done, ln.stream));
+        }
+        CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
+                                rep.d_status + li, ln.stream));
+        g_launches++;
+        x.h2d += m * k;
+        if (int rc = search_and_copy_out(rep, ln, k, b, m, hs, true, x); rc != MSBWT_OK) return rc;
+    }
+    if (int rc = drain(rep); rc != MSBWT_OK) return rc;
+    if (int rc = flush_all_outputs(rep, hs); rc != MSBWT_OK) return rc;
+    return check_status(rep, "count_kmers_fixed");
+}
+
+// Host-side 2-bit packing pays off when enough host threads can feed it: the byte route moves k bytes per query
+// over PCIe (~55 GB/s), the packed route 8 * ceil(k/32) but needs the CPU to read the k bytes.
+bool use_host_pack(uint32_t k, uint64_t n, size_t ndev) {
+    if (!k || k > max_host_packed_k() || n < 4096) return false;
+    if (const char *env = getenv("MSBWT_HOST_PACK")) return atoi(env) != 0;
+    return replica_pack_threads(ndev) >= 8;
 }
 
 // The packed / hybrid route (hostpack.cpp): the replica's worker threads pack all-ACGT k-mers 2 bits per symbol
@@ -198,14 +289,11 @@ int packed_route(Replica &rep, size_t ndev, const uint8_t *syms, uint32_t k, uin
     const uint64_t chunk = pick_chunk(sl.len(), kPackedChunkQueries, 8ull * nw);
     bool hybrid = is_pinned_host(syms);
     if (const char *env = getenv("MSBWT_HYBRID")) hybrid = hybrid && atoi(env) != 0;
-    const int want_threads = replica_pack_threads(ndev);
-    if (!rep.pool || rep.pool->size() != want_threads) rep.pool = std::make_unique<HostPool>(want_threads);
-    HostPool &pool = *rep.pool;
-    struct Session {  // the workers stay hot for the duration of this call only
-        HostPool &p;
-        explicit Session(HostPool &pool_) : p(pool_) { p.begin_session(); }
-        ~Session() { p.end_session(); }
-    } session(pool);
+    HostPool &pool = replica_pool(rep, ndev);
+    PoolSession session(pool);
+    // (the packers read the caller's symbol bytes themselves, pageable or not: only the OUTPUT may need staging)
+    HostStage hs = make_stage(rep, ndev, nullptr, out);
+    hs.pool = &pool;
     std::vector<std::vector<uint64_t>> exc_by_thread((size_t)pool.size());
 
     for (int li = 0; li < kLanes; li++) {
@@ -219,7 +307,7 @@ int packed_route(Replica &rep, size_t ndev, const uint8_t *syms, uint32_t k, uin
         } else {
             continue;
         }
-        if (int rc = reserve_search_buffers(rep, ln, k, chunk, out); rc != MSBWT_OK) return rc;
+        if (int rc = reserve_search_buffers(rep, ln, k, chunk, hs); rc != MSBWT_OK) return rc;
     }
     if (int rc = reset_status(rep); rc != MSBWT_OK) return rc;
     const bool with_b = packed_batch_needs_list_b(rep.view, k);
@@ -232,16 +320,18 @@ int packed_route(Replica &rep, size_t ndev, const uint8_t *syms, uint32_t k, uin
                 if (cudaEventQuery(rep.lane[kPackLanes + r].h2d_done) == cudaSuccess) raw_lane = kPackLanes + r;
         if (raw_lane >= 0) {  // the link is idle: this chunk travels as symbol bytes
             Lane &ln = rep.lane[raw_lane];
+            if (int rc = flush_lane_output(ln, hs); rc != MSBWT_OK) return rc;
             CU_TRY(cudaMemcpyAsync(ln.in_a.p, syms + b * k, m * k, cudaMemcpyHostToDevice, ln.stream));
             CU_TRY(cudaEventRecord(ln.h2d_done, ln.stream));
             CU_TRY(launch_pack_seed(rep.view, ln.in_a.as<uint8_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(),
                                     rep.d_status + raw_lane, ln.stream));
             g_launches++;
             x.h2d += m * k;
-            if (int rc = search_and_copy_out(rep, ln, k, b, m, out, true, x); rc != MSBWT_OK) return rc;
+            if (int rc = search_and_copy_out(rep, ln, k, b, m, hs, true, x); rc != MSBWT_OK) return rc;
             continue;
         }
         Lane &ln = rep.lane[packed_turn++ % kPackLanes];
+        if (int rc = flush_lane_output(ln, hs); rc != MSBWT_OK) return rc;
         CU_TRY(cudaEventSynchronize(ln.h2d_done));  // the lane's staging buffer is free again
         uint64_t *stage = (uint64_t *)ln.h_stage.p;
         pool.run([&](int tid, int nthreads) {
@@ -253,9 +343,10 @@ int packed_route(Replica &rep, size_t ndev, const uint8_t *syms, uint32_t k, uin
         CU_TRY(launch_seed_packed(rep.view, ln.in_b.as<uint64_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(), ln.stream));
         g_launches++;
         x.h2d += m * nw * sizeof(uint64_t);
-        if (int rc = search_and_copy_out(rep, ln, k, b, m, out, with_b, x); rc != MSBWT_OK) return rc;
+        if (int rc = search_and_copy_out(rep, ln, k, b, m, hs, with_b, x); rc != MSBWT_OK) return rc;
     }
     if (int rc = drain(rep); rc != MSBWT_OK) return rc;
+    if (int rc = flush_all_outputs(rep, hs); rc != MSBWT_OK) return rc;
     if (int rc = check_status(rep, "count_kmers_fixed"); rc != MSBWT_OK) return rc;  // raw chunks validate on the device
     // exceptions: k-mers with a symbol outside ACGT go through the byte route (device-side validation)
     std::vector<uint64_t> exc;
@@ -266,7 +357,7 @@ int packed_route(Replica &rep, size_t ndev, const uint8_t *syms, uint32_t k, uin
     for (size_t i = 0; i < exc.size(); i++) memcpy(esyms.data() + i * k, syms + exc[i] * k, k);
     CountsOut tmp;
     tmp.o64 = eout.data();
-    if (int rc = bytes_route(rep, esyms.data(), k, Slice{0, exc.size()}, tmp, x); rc != MSBWT_OK) return rc;
+    if (int rc = bytes_route(rep, ndev, esyms.data(), k, Slice{0, exc.size()}, tmp, x); rc != MSBWT_OK) return rc;
     for (size_t i = 0; i < exc.size(); i++) {
         if (out.o32) out.o32[exc[i]] = (uint32_t)eout[i];
         else out.o64[exc[i]] = eout[i];
@@ -278,24 +369,28 @@ int fixed_route(const msbwt_index *idx, const uint8_t *syms, uint32_t k, uint64_
     const size_t ndev = idx->reps.size();
     const bool packed = use_host_pack(k, n, ndev);
     return run_on_replicas(idx, n, [&](Replica &rep, Slice sl, Xfer &x) {
-        return packed ? packed_route(rep, ndev, syms, k, n, sl, out, x) : bytes_route(rep, syms, k, sl, out, x);
+        return packed ? packed_route(rep, ndev, syms, k, n, sl, out, x) : bytes_route(rep, ndev, syms, k, sl, out, x);
     });
 }
 
 // K-mers the caller already holds as integers (k <= 32): nothing to do on the host, 8 bytes per query over the
 // link on the way in and 8 (u64 counts) or 4 (u32 counts) on the way back.  A lane's stream orders copy-in, seed,
 // search and copy-out, so its buffers are reused safely by its next chunk.
-int u64_route(Replica &rep, const uint64_t *kmers, uint32_t k, Slice sl, CountsOut out, Xfer &x) {
+int u64_route(Replica &rep, size_t ndev, const uint64_t *kmers, uint32_t k, Slice sl, CountsOut out, Xfer &x) {
     const uint64_t chunk = pick_chunk(sl.len(), 1ull << 21, sizeof(uint64_t));
+    HostStage hs = make_stage(rep, ndev, kmers, out);
+    std::unique_ptr<PoolSession> session;
+    if (hs.pool) session = std::make_unique<PoolSession>(*hs.pool);
     for (auto &ln : rep.lane) {
         CU_TRY(cudaStreamSynchronize(ln.stream));
         CU_TRY(ln.in_b.reserve(chunk * sizeof(uint64_t)));
-        if (int rc = reserve_search_buffers(rep, ln, k, chunk, out); rc != MSBWT_OK) return rc;
+        if (hs.in) CU_TRY(ln.h_stage.reserve(chunk * sizeof(uint64_t)));
+        if (int rc = reserve_search_buffers(rep, ln, k, chunk, hs); rc != MSBWT_OK) return rc;
     }
     const bool with_b = packed_batch_needs_list_b(rep.view, k);
     // MSBWT_TRACE_PIPE=1: per-chunk timeline of the lanes (copy-in, kernels, copy-out) on stderr -- a measurement aid
     const bool trace = getenv("MSBWT_TRACE_PIPE") != nullptr;
-    struct Marks { cudaEvent_t e[4]; int lane; };
+    struct Marks { cudaEvent_t e[3]; int lane; };
     std::vector<Marks> marks;
     cudaEvent_t t0 = nullptr;
     if (trace) {
@@ -306,46 +401,36 @@ int u64_route(Replica &rep, const uint64_t *kmers, uint32_t k, Slice sl, CountsO
     for (uint64_t b = sl.begin; b < sl.end; b += chunk, c++) {
         const uint64_t m = std::min(chunk, sl.end - b);
         Lane &ln = rep.lane[c % kLanes];
+        if (int rc = flush_lane_output(ln, hs); rc != MSBWT_OK) return rc;
+        const void *src = nullptr;
+        if (int rc = stage_input(ln, hs, kmers + b, m * sizeof(uint64_t), &src); rc != MSBWT_OK) return rc;
         Marks mk{};
         if (trace) {
             for (auto &e : mk.e) cudaEventCreate(&e);
             mk.lane = (int)(c % kLanes);
             cudaEventRecord(mk.e[0], ln.stream);
         }
-        CU_TRY(cudaMemcpyAsync(ln.in_b.p, kmers + b, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
+        CU_TRY(cudaMemcpyAsync(ln.in_b.p, src, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ln.stream));
+        if (hs.in) CU_TRY(cudaEventRecord(ln.h2d_done, ln.stream));
         if (trace) cudaEventRecord(mk.e[1], ln.stream);
         CU_TRY(launch_seed_u64(rep.view, ln.in_b.as<uint64_t>(), k, m, ln.packed.as<uint64_t>(), ln.out_a.as<uint64_t>(), ln.stream));
         g_launches++;
         x.h2d += m * sizeof(uint64_t);
-        // (search + copy-out; with tracing the boundary between them is marked inside by the extra event below)
-        CU_TRY(launch_count_packed(rep.device, rep.view, rep.lanes, ln.packed.as<uint64_t>(), k, m, ln.out_a.as<uint64_t>(),
-                                   ln.stream, &g_call_launches, with_b));
-        flush_launches();
-        if (out.o32) {
-            CU_TRY(launch_narrow_counts(rep.device, ln.out_a.as<uint64_t>(), m, ln.out_b.as<uint32_t>(), ln.stream));
-            g_launches++;
-        }
-        if (trace) cudaEventRecord(mk.e[2], ln.stream);
-        if (out.o32) {
-            CU_TRY(cudaMemcpyAsync(out.o32 + b, ln.out_b.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ln.stream));
-            x.d2h += m * sizeof(uint32_t);
-        } else {
-            CU_TRY(cudaMemcpyAsync(out.o64 + b, ln.out_a.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ln.stream));
-            x.d2h += m * sizeof(uint64_t);
-        }
+        if (int rc = search_and_copy_out(rep, ln, k, b, m, hs, with_b, x); rc != MSBWT_OK) return rc;
         if (trace) {
-            cudaEventRecord(mk.e[3], ln.stream);
+            cudaEventRecord(mk.e[2], ln.stream);
             marks.push_back(mk);
         }
     }
     if (int rc = drain(rep); rc != MSBWT_OK) return rc;
+    if (int rc = flush_all_outputs(rep, hs); rc != MSBWT_OK) return rc;
     if (trace) {
-        fprintf(stderr, "[msbwt] u64 route on device %d: %zu chunks of %llu queries\n  chunk lane  h2d_start  h2d_end  kernels_end  d2h_end (ms)\n",
+        fprintf(stderr, "[msbwt] u64 route on device %d: %zu chunks of %llu queries\n  chunk lane  h2d_start  h2d_end  d2h_end (ms)\n",
                 rep.device, marks.size(), (unsigned long long)chunk);
         for (size_t i = 0; i < marks.size(); i++) {
-            float t[4];
-            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], t0, marks[i].e[j]);
-            fprintf(stderr, "  %5zu %4d  %9.3f %8.3f %12.3f %8.3f\n", i, marks[i].lane, t[0], t[1], t[2], t[3]);
+            float t[3];
+            for (int j = 0; j < 3; j++) cudaEventElapsedTime(&t[j], t0, marks[i].e[j]);
+            fprintf(stderr, "  %5zu %4d  %9.3f %8.3f %8.3f\n", i, marks[i].lane, t[0], t[1], t[2]);
             for (auto &e : marks[i].e) cudaEventDestroy(e);
         }
         cudaEventDestroy(t0);
@@ -401,7 +486,7 @@ extern "C" int msbwt_count_kmers_u64(const msbwt_index *idx, const uint64_t *kme
     AllLocks locks(idx);
     CountsOut o;
     o.o64 = out;
-    return run_on_replicas(idx, n, [&](Replica &rep, Slice sl, Xfer &x) { return u64_route(rep, kmers, k, sl, o, x); });
+    return run_on_replicas(idx, n, [&](Replica &rep, Slice sl, Xfer &x) { return u64_route(rep, idx->reps.size(), kmers, k, sl, o, x); });
 }
 
 extern "C" int msbwt_count_kmers_u64_u32(const msbwt_index *idx, const uint64_t *kmers, uint32_t k, uint64_t n, uint32_t *out) {
@@ -413,7 +498,7 @@ extern "C" int msbwt_count_kmers_u64_u32(const msbwt_index *idx, const uint64_t 
     AllLocks locks(idx);
     CountsOut o;
     o.o32 = out;
-    return run_on_replicas(idx, n, [&](Replica &rep, Slice sl, Xfer &x) { return u64_route(rep, kmers, k, sl, o, x); });
+    return run_on_replicas(idx, n, [&](Replica &rep, Slice sl, Xfer &x) { return u64_route(rep, idx->reps.size(), kmers, k, sl, o, x); });
 }
 
 extern "C" void msbwt_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h) {

@@ -38,6 +38,21 @@ def main():
         t0 = time.perf_counter()
         call()
         print(f"wall {1e3 * (time.perf_counter() - t0):.2f} ms for {n} queries", file=sys.stderr, flush=True)
+    # the same call on PAGEABLE host memory (what a caller's Vec<u64> / numpy array is): cudaMemcpyAsync then stages
+    # through the driver and holds the calling thread
+    km_pg, out_pg = km_np.copy(), np.zeros(n, dtype=np.uint64)
+
+    def call_pageable():
+        rc = lib.msbwt_count_kmers_u64(bwt.handle, ctypes.c_void_p(km_pg.ctypes.data), k, n, ctypes.c_void_p(out_pg.ctypes.data))
+        assert rc == 0
+    call_pageable()
+    for _ in range(3):
+        t0 = time.perf_counter()
+        call_pageable()
+        print(f"pageable wall {1e3 * (time.perf_counter() - t0):.2f} ms for {n} queries", file=sys.stderr, flush=True)
+    assert (out_pg == out_np).all()
+    if len(sys.argv) > 2 and sys.argv[2] == "bytes":
+        q_pg = None
     os.environ["MSBWT_TRACE_PIPE"] = "1"
     call()
 
