@@ -36,7 +36,7 @@ namespace msbwt {
 #endif
 constexpr int kOctRowBytes = 144;    // a 128-byte line + 16: rows of consecutive lanes start 4 banks apart (conflict-free LDS.128)
 constexpr int kOctPoolBytes = 640;   // 32 x (u64 symbol word, u64 seed range, u32 original index)
-constexpr int kOctChunk = 512;       // queries a warp takes from the live list at a time
+constexpr int kOctChunk = 512;       // queries a warp takes from the live list at a time (fewer when the list is short)
 constexpr int kOctRawPoolBytes = 1072;  // fused path: 32 queries x k <= 32 symbol bytes, + the slack an unaligned 36-byte read needs
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool on) {
@@ -132,7 +132,12 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     uint8_t *const pools = rows + 32 * kOctRowBytes;               // 2 pools of 32 queries
     const uint4 *const my_row = reinterpret_cast<const uint4 *>(rows + lane * kOctRowBytes);
 
-    // The queries are handed out in chunks of kOctChunk (an atomic counter: a warp whose queries die early
+    // A SHORT list (the leftovers of the one-request kernel: a percent of the batch) is cut into smaller chunks so that
+    // every resident warp gets one: a warp walks its chunk 32 queries at a time, each a chain of dependent line fetches,
+    // and 512 queries per warp would leave most of the grid idle behind sixteen such rounds.
+    const uint32_t warps_in_grid = gridDim.x * (kCountThreads / 32);
+    const uint32_t chunk_size = min((uint32_t)kOctChunk, max(32u, ((n / warps_in_grid) + 31u) & ~31u));
+    // The queries are handed out in chunks of `chunk_size` (an atomic counter: a warp whose queries die early
     // simply comes back sooner, whatever the order of the batch) and staged pool by pool: pool A (sequence
     // number `seq`, buffer seq & 1) is being handed to the lanes, pool B (the other buffer) is already staged
     // or on its way.
@@ -140,10 +145,10 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     auto next_pool = [&](uint32_t &base, uint32_t &cnt) {
         if (chunk_next >= chunk_end) {
             uint32_t c = 0;
-            if (lane == 0) c = atomicAdd(work, (uint32_t)kOctChunk);
+            if (lane == 0) c = atomicAdd(work, chunk_size);
             c = __shfl_sync(kFull, c, 0);
             chunk_next = min(c, n);
-            chunk_end = min(c + (uint32_t)kOctChunk, n);
+            chunk_end = min(c + chunk_size, n);
         }
         base = chunk_next;
         cnt = min(32u, chunk_end - chunk_next);

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--k", type=int, default=0, help="query length (default: the workload's)")
+    ap.add_argument("--n", type=int, default=0, help="use only the first n queries of the batch (a rank's slice under strong scaling)")
     args = ap.parse_args()
 
     import torch
@@ -36,6 +37,8 @@ def main():
         cfg["k"] = args.k
     k = cfg["k"]
     rle_host, total, queries, _ = bench.build_workload(cfg, dev, 0)
+    if args.n:
+        queries = queries[: args.n].contiguous()
     n = queries.shape[0]
     bwt = M.RleBWT.new(devices=[0])
     bwt.load_vector(rle_host)
