@@ -418,6 +418,104 @@ int build_multi_step(msbwt_index *idx, Replica &rep, const Options &opt) {
     return MSBWT_OK;
 }
 
+// The same two images for an index whose positions need 64 bits (N >= 2^32: the reference is u64 throughout,
+// src/msbwt_core.rs:18-24, src/rle_bwt.rs:14-24; or several superblocks).  A quad image of such an index (36.6 B per
+// position: 157 GB at 2^32) has no room, so nothing is built on the way: the builders walk LF through the one-step
+// blocks (oct_builder.cu build_oct_codes_by_walk, fin_builder.cu build_fin_codes_by_walk), and the search kernel
+// (wide_kernels.cu) takes remainders and fallbacks as one-symbol steps.
+//   10-symbol codes -> oct lines -> 20-symbol codes (10-symbol codes dropped) -> final-step lines.
+// `required` false (automatic choice): running out of device memory leaves the index without these images
+// (*built = false, MSBWT_OK) and the caller falls back to the pair image.
+int build_multi_step_wide(msbwt_index *idx, Replica &rep, const Options &opt, bool required, bool *built) {
+    *built = false;
+    DeviceGuard guard(rep.device);
+    struct DevPtr { void *p = nullptr; ~DevPtr() { if (p) cudaFree(p); } void reset() { if (p) cudaFree(p); p = nullptr; } };
+    const uint64_t N = rep.view.total;
+    const int fin_req = opt.fin != -1 ? opt.fin : env_int("MSBWT_FINAL_INDEX", -1);
+    std::string why;
+    int n = 0;
+    auto soft = [&](int rc) {  // out of memory on an automatic build: the index works without these images
+        if (rc == MSBWT_ENOMEM && !required) { cudaGetLastError(); return true; }
+        return false;
+    };
+
+    DevPtr codes10_owner;
+    uint32_t *codes10 = nullptr;
+    build_trace("10-symbol codes (walk)");
+    int rc = build_oct_codes_by_walk(rep.device, rep.view, &codes10, why, &n);
+    g_launches += (uint64_t)n;
+    if (rc != MSBWT_OK) return soft(rc) ? MSBWT_OK : fail(rc, why);
+    codes10_owner.p = codes10;
+
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { free_b = 0; total_b = 0; }
+    const int fshift = opt.fin_shift ? opt.fin_shift : env_int("MSBWT_FINAL_BUCKET_SHIFT", 16);
+    int flb = opt.fin_lb ? opt.fin_lb : env_int("MSBWT_FINAL_LINES_LOG2", 0);
+    if (!flb) flb = fin_image_bytes(N, fshift, 13) <= (uint64_t)total_b / 10 * 3 ? 13 : 12;
+    // what the final-step image will need after the oct lines exist: its lines, the 20-symbol codes (8 B per
+    // position) and the run records + sort scratch (4 B per position once the codes are gone)
+    const uint64_t fin_need = fin_req != 0 ? fin_image_bytes(N, fshift, flb) + 12 * N : 0;
+    const uint64_t reserve = fin_need + (opt.oct == 1 ? 0 : (8ull << 30));
+    const uint64_t budget = free_b > reserve ? free_b - reserve : 0;
+    const int oct_shift = opt.oct_shift ? opt.oct_shift : env_int("MSBWT_OCT_BUCKET_SHIFT", 0);
+    n = 0;
+    build_trace("oct lines");
+    rc = build_oct_lines_on_device(rep.device, rep.view, codes10, oct_shift, budget, rep.oct, why, &n);
+    g_launches += (uint64_t)n;
+    if (rc != MSBWT_OK) {
+        free_oct_image(rep.oct);
+        rep.oct = OctImage{};
+        return soft(rc) ? MSBWT_OK : fail(rc, why);
+    }
+    if (!rep.oct.lines) {
+        if (required) return fail(MSBWT_ENOMEM, "no room for the oct image of this index");
+        return MSBWT_OK;
+    }
+    rep.view.oct = rep.oct.lines;
+    rep.view.nbuck8 = rep.oct.nbuck8;
+    rep.view.oct_shift = (uint32_t)rep.oct.shift;
+    if (idx->reps[0].get() == &rep) idx->bytes_per_replica += (uint64_t)kOctCodes * rep.oct.nbuck8 * kOctLineBytes;
+    *built = true;
+    if (fin_req == 0) return MSBWT_OK;
+
+    uint64_t *codes20 = nullptr;
+    n = 0;
+    rc = build_fin_codes_by_walk(rep.device, rep.view, codes10, &codes20, why, &n);
+    g_launches += (uint64_t)n;
+    codes10_owner.reset();
+    if (rc != MSBWT_OK) {
+        if (rc == MSBWT_ENOMEM && fin_req != 1) { cudaGetLastError(); return MSBWT_OK; }
+        return fail(rc, why);
+    }
+    n = 0;
+    rc = build_fin_lines_on_device(rep.device, N, codes20, fshift, flb, rep.fin, why, &n);  // owns codes20
+    g_launches += (uint64_t)n;
+    if (rc != MSBWT_OK) {
+        free_fin_image(rep.fin);
+        rep.fin = FinImage{};
+        if (rc == MSBWT_ENOMEM && fin_req != 1) { cudaGetLastError(); return MSBWT_OK; }
+        return fail(rc, why);
+    }
+    rep.view.fin = rep.fin.lines;
+    rep.view.fin_shift = (uint32_t)rep.fin.shift;
+    rep.view.fin_lb = (uint32_t)rep.fin.lb;
+    if (idx->reps[0].get() == &rep) idx->bytes_per_replica += rep.fin.nlines * (uint64_t)kFinLineBytes;
+    build_trace("multi-step images done");
+    return MSBWT_OK;
+}
+
+// Automatic choice for an index with 64-bit positions: it lives in HBM, the caller pinned no other layout, and the
+// two images at their coarsest settings plus the builders' scratch fit the free device memory.
+bool pick_wide_oct(int device, uint64_t index_bytes, uint64_t total, const Options &opt) {
+    if (opt.oct == 0 || opt.oct == 1) return opt.oct == 1;
+    if (const char *env = getenv("MSBWT_OCT_INDEX")) { if (atoi(env) == 0) return false; }
+    if (opt.pair != -1 || opt.quad != -1 || getenv("MSBWT_PAIR_INDEX") || getenv("MSBWT_QUAD_INDEX")) return false;
+    if (!lives_in_hbm(device, index_bytes) || (total >> 40) != 0) return false;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+    return oct_image_bytes(total, kOctMaxShift) + fin_image_bytes(total, 16, 12) + 12 * total + (8ull << 30) <= free_b;
+}
+
 int build_suffix_table(msbwt_index *idx, Replica &rep, int s) {
     if (s <= 0) return MSBWT_OK;
     DeviceGuard guard(rep.device);
@@ -502,14 +600,23 @@ msbwt_index *create_common(const uint8_t *rle, uint64_t len, const int *devices,
             auto &rep = idx->reps[slot];
             int s = s0;
             bool quad;
+            bool wide_oct = false;
             {
                 DeviceGuard guard(rep->device);
+                if (wide && pick_wide_oct(rep->device, one_step_bytes, idx->total, opt)) {
+                    if (int r = build_multi_step_wide(idx.get(), *rep, opt, opt.oct == 1, &wide_oct); r != MSBWT_OK) return r;
+                }
                 const char *oct_env = getenv("MSBWT_OCT_INDEX");
                 const bool with_oct = idx->total < (1ull << 32) && !index_is_wide(rep->view) && opt.oct != 0 &&
                                       (opt.oct == 1 || !oct_env || atoi(oct_env) != 0);
-                quad = opt.oct == 1 || pick_quad(rep->device, one_step_bytes, idx->total, opt.quad, opt.pair, with_oct);
+                quad = !wide_oct && (opt.oct == 1 || pick_quad(rep->device, one_step_bytes, idx->total, opt.quad, opt.pair, with_oct));
             }
-            if (quad || pick_pair(rep->device, one_step_bytes, opt.pair)) {
+            if (wide_oct) {
+                if (!explicit_s) {
+                    DeviceGuard guard(rep->device);
+                    s = std::min(deepen_table_for_hbm(s0, idx->reps[0]->view.nblocks * kBlockBytes + oct_image_bytes(idx->total, rep->oct.shift), 16), kOctAutoTableS);
+                }
+            } else if (quad || pick_pair(rep->device, one_step_bytes, opt.pair)) {
                 if (int r = quad ? build_multi_step(idx.get(), *rep, opt) : build_pair(idx.get(), *rep); r != MSBWT_OK) return r;
                 if (!explicit_s && (quad || lives_in_hbm(rep->device, one_step_bytes))) {
                     DeviceGuard guard(rep->device);
@@ -813,6 +920,7 @@ extern "C" int msbwt_count_kmers_packed_stats_device(const msbwt_index *idx, int
     if (n > kMaxPerLaunch) return fail(MSBWT_EINVAL, "more than 2^30 queries per pack/count pair: split the batch");
     Replica &rep = *idx->reps[slot];
     if (!rep.view.oct) return fail(MSBWT_EINVAL, "this index has no oct image");
+    if (index_is_wide(rep.view)) return fail(MSBWT_EINVAL, "the counting build of the oct kernel exists for 32-bit positions only");
     if (!n) return MSBWT_OK;
     DeviceGuard guard(rep.device);
     CU_TRY(launch_count_oct_stats(rep.device, rep.view, d_packed, k, n, d_out, (unsigned long long *)d_stats, (cudaStream_t)stream));

@@ -180,6 +180,23 @@ __device__ __forceinline__ void rank_step(const IndexView &ix, const CBase<WIDE>
     h = cb.at(bh, sym) + ckh + ch;
 }
 
+// The symbol stored at BWT position p < N (one 4-byte read per bit-plane of the half that holds it, layout.h), and
+// LF(p) = C[B[p]] + rank(B[p], p): what the image builders that walk the one-step blocks use (oct_builder.cu,
+// fin_builder.cu: the indexes too large for a quad image to walk LF^4 with).
+__device__ __forceinline__ uint32_t symbol_at(const IndexView &ix, uint64_t p) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blocks) + (p >> kBlockShift) * (uint64_t)kWordsPerBlock +
+                        (((uint32_t)p >> 6) & 1u) * 8u + (((uint32_t)p >> 5) & 1u);
+    const uint32_t b = (uint32_t)p & 31u;
+    return ((__ldg(w + 2) >> b) & 1u) | (((__ldg(w + 4) >> b) & 1u) << 1) | (((__ldg(w + 6) >> b) & 1u) << 2);
+}
+template <bool WIDE>
+__device__ __forceinline__ typename Pos<WIDE>::type lf_step(const IndexView &ix, const CBase<WIDE> &cb, uint32_t sym,
+                                                            typename Pos<WIDE>::type p) {
+    typename Pos<WIDE>::type l = p, h = p;
+    rank_step<WIDE, 1>(ix, cb, sym, l, h);
+    return l;
+}
+
 // The four constrain_range calls of a backward-search extension at once: the block(s) holding
 // l and h are fetched ONCE and ranked for A, C, G and T.  out_l[j], out_h[j] = constrain_range(ACGT[j], [l,h)).
 template <bool WIDE>

@@ -91,6 +91,9 @@ uint64_t oct_image_bytes(uint64_t total, int shift);
 // keep_codes, OWNED by this call; `d_codes2` = the pair builder's keep_codes (borrowed).  N < 2^32 only.
 int build_oct_codes_on_device(int device, const IndexView &ix, uint16_t *d_codes4, const uint8_t *d_codes2,
                               uint32_t **d_codes10, std::string &why, int *launches);
+// stage 1 without a quad image: the same codes by walking LF through the one-step blocks (any index; the only way when
+// N >= 2^32, whose quad image has no room)
+int build_oct_codes_by_walk(int device, const IndexView &ix, uint32_t **d_codes10, std::string &why, int *launches);
 // stage 2 (needs only the one-step blocks and the codes): the lines.  `requested_shift` 0 = automatic (layout.h).
 // When even the coarsest buckets exceed `max_bytes` nothing is built (img.lines stays null) and MSBWT_OK is returned.
 int build_oct_lines_on_device(int device, const IndexView &ix, const uint32_t *d_codes10, int requested_shift,
@@ -110,6 +113,8 @@ uint64_t fin_image_bytes(uint64_t total, int shift, int lb);
 // `1 << kFinCodeBits | code` or 0 (8 bytes per position, device memory OWNED by stage 2)
 int build_fin_codes_on_device(int device, const IndexView &ix, const uint32_t *d_codes10, uint64_t **d_codes20,
                               std::string &why, int *launches);
+int build_fin_codes_by_walk(int device, const IndexView &ix, const uint32_t *d_codes10, uint64_t **d_codes20,
+                            std::string &why, int *launches);
 // stage 2 (needs only the codes, which it frees as soon as the run records exist): the lines
 int build_fin_lines_on_device(int device, uint64_t total, uint64_t *d_codes20, int shift, int lb, FinImage &img,
                               std::string &why, int *launches);
@@ -186,6 +191,9 @@ cudaError_t launch_pack_seed_final(int device, const IndexView &ix, const void *
 // quad_kernels.cu: live list A over the quad (and oct) image
 cudaError_t launch_count_quad(int device, const IndexView &ix, const uint64_t *d_packed, const PackedLayout &lay,
                               uint32_t k, uint64_t *d_out, cudaStream_t st);
+// wide_kernels.cu: live list A over the oct (and final-step) image of an index with 64-bit positions
+cudaError_t launch_count_oct_wide(int device, const IndexView &ix, const uint64_t *d_packed, const PackedLayout &lay,
+                                  uint32_t k, uint64_t *d_out, cudaStream_t st);
 // stats_kernels.cu: live list A over the oct image with the counting instantiation -- d_stats[8] (oct_kernel.cuh)
 cudaError_t launch_count_oct_stats(int device, const IndexView &ix, const uint64_t *d_packed, uint32_t k, uint64_t n,
                                    uint64_t *d_out, unsigned long long *d_stats, cudaStream_t st);

@@ -57,6 +57,29 @@ __global__ void __launch_bounds__(256) fin_code20_kernel(IndexView ix, const uin
     }
 }
 
+// The same codes without a quad image (indexes of 2^32 positions and more): ten one-symbol steps through the one-step
+// blocks -- the symbols are the digits of the position's own 10-symbol code -- then the code found there.
+template <bool WIDE>
+__global__ void __launch_bounds__(256) fin_code_walk_kernel(IndexView ix, const uint32_t *__restrict__ codes10,
+                                                            uint64_t *__restrict__ codes20) {
+    using P = typename Pos<WIDE>::type;
+    __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
+    const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < ix.total; j += step) {
+        const uint32_t a = codes10[j];
+        uint64_t v = 0;
+        if (a & kValid10) {
+            P p = (P)j;
+#pragma unroll 1
+            for (int r = kOctSyms - 1; r >= 0; r--) p = lf_step<WIDE>(ix, cb, (0x5321u >> (4u * ((a >> (2 * r)) & 3u))) & 7u, p);  // A,C,G,T = 1,2,3,5
+            const uint32_t b = codes10[p];
+            if (b & kValid10) v = kValid20 | ((uint64_t)(a & kMask10) << kOctCodeBits) | (uint64_t)(b & kMask10);
+        }
+        codes20[j] = v;
+    }
+}
+
 __device__ __forceinline__ bool fin_is_head(const uint64_t *codes20, uint64_t j, uint64_t bmask) {
     const uint64_t v = codes20[j];
     return (v & kValid20) && (j == 0 || (j & bmask) == 0 || codes20[j - 1] != v);
@@ -191,12 +214,39 @@ int build_fin_codes_on_device(int device, const IndexView &ix, const uint32_t *d
     return MSBWT_OK;
 }
 
+// Stage 1 without a quad image (any index; the only way for one of 2^32 positions and more): `ix` needs only the one-step
+// blocks
+int build_fin_codes_by_walk(int device, const IndexView &ix, const uint32_t *d_codes10, uint64_t **d_codes20_out,
+                            std::string &why, int *launches) {
+    *d_codes20_out = nullptr;
+    if (!d_codes10) { why = "final-step image: needs the 10-symbol codes"; return MSBWT_EINVAL; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((ix.total + 255) / 256, (uint64_t)sms * 32));
+    uint64_t *d_codes20 = nullptr;
+    F_TRY(cudaMalloc((void **)&d_codes20, std::max<uint64_t>(1, ix.total) * sizeof(uint64_t)));
+    fin_trace("codes (walk)");
+    if (index_is_wide(ix)) fin_code_walk_kernel<true><<<grid, 256>>>(ix, d_codes10, d_codes20);
+    else fin_code_walk_kernel<false><<<grid, 256>>>(ix, d_codes10, d_codes20);
+    if (launches) (*launches)++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(d_codes20);
+        why = std::string("final-step image: code walk kernel: ") + cudaGetErrorString(e);
+        return MSBWT_ECUDA;
+    }
+    *d_codes20_out = d_codes20;
+    return MSBWT_OK;
+}
+
 // Stage 2 (needs nothing but the codes, which it OWNS and frees as soon as the run records exist): the lines
 int build_fin_lines_on_device(int device, uint64_t total, uint64_t *d_codes20_in, int shift, int lb, FinImage &img,
                               std::string &why, int *launches) {
     struct Owned { uint64_t *p; ~Owned() { if (p) cudaFree(p); } } codes20{d_codes20_in};
     if (!d_codes20_in) { why = "final-step image: no position codes"; return MSBWT_EINVAL; }
     if (shift < 8 || shift > 16 || lb < kFinCodeBits - kFinTagBits || lb > 20) { why = "final-step image: bucket shift 8..16, lines per bucket 2^12..2^20"; return MSBWT_EINVAL; }
+    if (((((total >> shift) + 1) << lb) >> (64 - kFinTagBits)) != 0) { why = "final-step image: line index and tag do not fit one 64-bit sort key"; return MSBWT_EINVAL; }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * 32));
@@ -239,7 +289,9 @@ int build_fin_lines_on_device(int device, uint64_t total, uint64_t *d_codes20_in
         cub::DoubleBuffer<uint64_t> keys(k0, k1);
         cub::DoubleBuffer<uint32_t> vals(v0, v1);
         size_t temp_bytes = 0;
-        const int end_bit = std::min(64, kFinTagBits + (32 - shift) + lb + 1);
+        int line_bits = 1;  // bits of a line index
+        while (line_bits < 64 && (nlines >> line_bits) != 0) line_bits++;
+        const int end_bit = std::min(64, kFinTagBits + line_bits);
         F_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, vals, (int64_t)n_runs, 0, end_bit));
         void *d_temp = nullptr;
         F_TRY(tmp.alloc((uint8_t **)&d_temp, temp_bytes));

@@ -152,8 +152,16 @@ constexpr int kQuadMaxSuperInSmem = 8;  // rows of 256 u64 staged in shared memo
 // low-complexity text) the kernel falls back to quad / one-step ranks for that query-step, so the result is
 // exact on any input.  128 * 4^m * (N / 2^b + 1) bytes; b is the largest shift that keeps the mean number of
 // runs per line <= kOctTargetRuns (b = 24, 8 B/symbol, on 30x reads with 1 % errors), never below one bucket
-// (128 MB).  Built only next to a quad image (which also serves remainders of 4..m-1 symbols) and only when
-// N < 2^32.
+// (128 MB).  N < 2^32: built through the pair and quad images (LF^4 per step of the code builder); the quad image
+// may stay beside it and then serves remainders of 4..m-1 symbols.
+//
+// 64-bit positions (N >= 2^32 -- the reference is u64 throughout, src/msbwt_core.rs:18-24 -- or several
+// superblocks): the same lines with a 40-bit checkpoint,
+//     word 0      low 32 bits of the checkpoint
+//     word 1      min(number of runs, kOctCapacity + 1) | (checkpoint >> 32) << 8
+// everything else is bucket-relative and unchanged.  A quad image of such an index has no room (36.6 B per
+// position), so the code builder walks LF through the one-step blocks instead and the kernel
+// (count_kmers_oct_kernel<.., WIDE = true>) takes remainders and fallbacks as one-symbol steps.  N < 2^40.
 //
 // Why ten: a 31-mer then is a suffix-table entry at depth 11 -- 4^11 entries of 8 bytes = 33 MB, resident in
 // L2 -- plus TWO lines: two HBM requests per query instead of three with eight symbols per line and a
@@ -174,7 +182,7 @@ __host__ __device__ constexpr int oct_chunk_shift(int b) {  // cs = min(31 - b, 
     return c;
 }
 
-// ---- final-step lines (EXPERIMENTAL, only with -DMSBWT_FINAL_STEP; specification: oracle/final_step.py) ----
+// ---- final-step lines (specification: oracle/final_step.py; holds no positions, so the same for any N) ----
 //
 // The LAST kFinSyms symbols a count_kmer consumes need no rank, only #{ j in [l, h) : code_20(j) == c }: no
 // checkpoints, nothing stored for codes that do not occur.  `1 << lb` lines of 128 bytes per bucket of `1 << b`

@@ -61,6 +61,28 @@ __global__ void __launch_bounds__(256) oct_code8_kernel(IndexView ix, const uint
     }
 }
 
+// The same codes without a quad image: every position walks LF through the one-step blocks, kOctSyms symbols, one
+// 64-byte block per step (indexes of 2^32 positions and more, whose quad image -- 36.6 B per position -- has no room).
+template <bool WIDE>
+__global__ void __launch_bounds__(256) oct_code_walk_kernel(IndexView ix, uint32_t *__restrict__ codes) {
+    using P = typename Pos<WIDE>::type;
+    __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
+    const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < ix.total; j += step) {
+        P p = (P)j;
+        uint32_t code = 0;
+        bool ok = true;
+        for (int r = 0; r < kOctSyms; r++) {
+            const uint32_t s = symbol_at(ix, p);
+            if (!((0x2Eu >> s) & 1u)) { ok = false; break; }  // not one of A,C,G,T = 1,2,3,5
+            code = (code << 2) | ((s - 1u - (s >> 2)) & 3u);
+            if (r + 1 < kOctSyms) p = lf_step<WIDE>(ix, cb, s, p);
+        }
+        codes[j] = ok ? (kValid8 | code) : 0u;
+    }
+}
+
 __global__ void __launch_bounds__(256) oct_count_runs_kernel(const uint32_t *__restrict__ codes8, uint64_t total,
                                                              unsigned long long *__restrict__ runs) {
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
@@ -92,27 +114,36 @@ __global__ void __launch_bounds__(256) oct_emit_kernel(const uint32_t *__restric
     }
 }
 
-// one warp per code: occurrence counts of its buckets (word 0) -> checkpoints
+// one warp per code: occurrence counts of its buckets (word 0) -> checkpoints.  WIDE (positions of 2^32 and more):
+// word 0 = the low 32 bits of the checkpoint, word 1 = min(runs, 31) | (the bits above them) << 8 (layout.h).
+template <bool WIDE>
 __global__ void __launch_bounds__(256) oct_stamp_kernel(const uint64_t *__restrict__ c8, uint64_t nbuck8,
                                                         uint32_t *__restrict__ lines, unsigned long long *__restrict__ overflow) {
+    using P = typename Pos<WIDE>::type;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t code = blockIdx.x * 8u + (threadIdx.x >> 5);
     if (code >= (uint32_t)kOctCodes) return;
     uint32_t *base = lines + (uint64_t)code * nbuck8 * kOctLineWords;
-    uint32_t run = (uint32_t)c8[code];
-    uint32_t over = 0, over_occ = 0;
+    P run = (P)c8[code];
+    uint32_t over = 0;
+    unsigned long long over_occ = 0;
     for (uint64_t b0 = 0; b0 < nbuck8; b0 += 32) {
         const uint64_t b = b0 + lane;
         const uint32_t cnt = b < nbuck8 ? base[b * kOctLineWords] : 0u;
-        if (b < nbuck8 && base[b * kOctLineWords + 1] > (uint32_t)kOctCapacity) { over++; over_occ += cnt; }
+        const uint32_t nruns = b < nbuck8 ? base[b * kOctLineWords + 1] : 0u;
+        if (nruns > (uint32_t)kOctCapacity) { over++; over_occ += cnt; }
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= (uint32_t)d) incl += t;
         }
-        if (b < nbuck8) base[b * kOctLineWords] = run + incl - cnt;
-        run += __shfl_sync(0xffffffffu, incl, 31);
+        if (b < nbuck8) {
+            const P ck = run + (P)(incl - cnt);
+            base[b * kOctLineWords] = (uint32_t)ck;
+            if constexpr (WIDE) base[b * kOctLineWords + 1] = min(nruns, (uint32_t)kOctCapacity + 1u) | ((uint32_t)(ck >> 32) << 8);
+        }
+        run += (P)__shfl_sync(0xffffffffu, incl, 31);
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -121,7 +152,7 @@ __global__ void __launch_bounds__(256) oct_stamp_kernel(const uint64_t *__restri
     }
     if (lane == 0 && over) {
         atomicAdd(overflow, (unsigned long long)over);
-        atomicAdd(overflow + 1, (unsigned long long)over_occ);
+        atomicAdd(overflow + 1, over_occ);
     }
 }
 
@@ -177,12 +208,37 @@ int build_oct_codes_on_device(int device, const IndexView &ix, uint16_t *d_codes
     return MSBWT_OK;
 }
 
+// Stage 1 without a quad image (any index; the only way for one of 2^32 positions and more): the codes by walking LF
+// through the one-step blocks -- `ix` needs nothing else.
+int build_oct_codes_by_walk(int device, const IndexView &ix, uint32_t **d_codes10, std::string &why, int *launches) {
+    *d_codes10 = nullptr;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((ix.total + 255) / 256, (uint64_t)sms * 32));
+    uint32_t *d_codes = nullptr;
+    O_TRY(cudaMalloc((void **)&d_codes, std::max<uint64_t>(1, ix.total) * sizeof(uint32_t)));
+    if (index_is_wide(ix)) oct_code_walk_kernel<true><<<grid, 256>>>(ix, d_codes);
+    else oct_code_walk_kernel<false><<<grid, 256>>>(ix, d_codes);
+    if (launches) (*launches)++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(d_codes);
+        why = std::string("oct image: code walk kernel: ") + cudaGetErrorString(e);
+        return MSBWT_ECUDA;
+    }
+    *d_codes10 = d_codes;
+    return MSBWT_OK;
+}
+
 // Stage 2: the lines, from the codes alone (plus the one-step blocks for Cm[c]): the quad image is not read, so
 // the caller may already have dropped it.  `requested_shift` 0 = automatic (layout.h).  When even the coarsest
 // buckets exceed `max_bytes` nothing is built (img.lines stays null) and MSBWT_OK is returned.
 int build_oct_lines_on_device(int device, const IndexView &ix, const uint32_t *d_codes8, int requested_shift,
                               uint64_t max_bytes, OctImage &img, std::string &why, int *launches) {
-    if (!d_codes8 || index_is_wide(ix)) { why = "oct image: needs the position codes and 32-bit positions"; return MSBWT_EINVAL; }
+    if (!d_codes8) { why = "oct image: needs the position codes"; return MSBWT_EINVAL; }
+    if ((ix.total >> 40) != 0) { why = "oct image: a line's checkpoint holds 40 bits (N < 2^40)"; return MSBWT_EINVAL; }
+    const bool wide = index_is_wide(ix);
     if (requested_shift && (requested_shift < kOctMinShift || requested_shift > kOctMaxShift)) {
         why = "oct image: bucket shift out of range"; return MSBWT_EINVAL;
     }
@@ -242,7 +298,8 @@ int build_oct_lines_on_device(int device, const IndexView &ix, const uint32_t *d
         if (launches) (*launches)++;
     }
     // stamp
-    oct_stamp_kernel<<<kOctCodes / 8, 256>>>(cur, nbuck8, reinterpret_cast<uint32_t *>(img.lines), d_stat + 1);
+    if (wide) oct_stamp_kernel<true><<<kOctCodes / 8, 256>>>(cur, nbuck8, reinterpret_cast<uint32_t *>(img.lines), d_stat + 1);
+    else oct_stamp_kernel<false><<<kOctCodes / 8, 256>>>(cur, nbuck8, reinterpret_cast<uint32_t *>(img.lines), d_stat + 1);
     O_TRY(cudaGetLastError());
     if (launches) (*launches)++;
     unsigned long long over[2] = {0, 0};

@@ -36,6 +36,7 @@ namespace msbwt {
 #endif
 constexpr int kOctRowBytes = 144;    // a 128-byte line + 16: rows of consecutive lanes start 4 banks apart (conflict-free LDS.128)
 constexpr int kOctPoolBytes = 640;   // 32 x (u64 symbol word, u64 seed range, u32 original index)
+constexpr int kOctWidePoolBytes = 896;  // WIDE: 32 x (u64 symbol word, u64 l, u64 h, u32 original index)
 constexpr int kOctChunk = 512;       // queries a warp takes from the live list at a time (fewer when the list is short)
 constexpr int kOctRawPoolBytes = 1072;  // fused path: 32 queries x k <= 32 symbol bytes, + the slack an unaligned 36-byte read needs
 
@@ -70,6 +71,12 @@ static __device__ __noinline__ uint2 oct_remainder_step(const IndexView &ix, con
     rank_step<false, 1>(ix, cb, sym, l, h);
     return make_uint2(l, h);
 }
+static __device__ __noinline__ ulonglong2 oct_remainder_step_wide(const IndexView &ix, const uint64_t *cbase, uint32_t sb_shift, uint32_t sym,
+                                                                  uint64_t l, uint64_t h) {
+    const CBase<true> cb{cbase, sb_shift};
+    rank_step<true, 1>(ix, cb, sym, l, h);
+    return make_ulonglong2(l, h);
+}
 
 // occurrences below bucket offsets pl / ph contributed by one stored run `(len << b) | off` (0 = empty slot)
 __device__ __forceinline__ void oct_add_run(uint32_t e, uint32_t b, uint32_t mask, int pl, int ph, int &sl, int &sh) {
@@ -101,18 +108,24 @@ __device__ __forceinline__ uint32_t staged_sector_rank(const uint4 &a, const uin
 // [3] quad steps, [4] distinct 128-byte lines those read, [5] one-symbol steps, [6] distinct 64-byte blocks those
 // read, [7] queries walked: the exact index traffic of the implemented algorithm on a batch, for the roofline
 // accounting of bench.py.
+// WIDE = true (wide_kernels.cu): positions of 64 bits -- an index of 2^32 symbols and more, or one cut into several
+// superblocks.  The seeds come as two words per query, a line's checkpoint is word 0 | (word 1 >> 8) << 32 and its run
+// count the low byte of word 1 (layout.h); such an index has no quad image beside the oct image (36.6 B per position
+// have no room), so remainders, overflowed lines and ranges over two buckets take one-symbol steps.
 constexpr int kOctStatWords = 8;
-template <bool RAW, bool STATS = false>
-__global__ void __launch_bounds__(kCountThreads, MSBWT_OCT_CTAS)
+template <bool RAW, bool STATS = false, bool WIDE = false>
+__global__ void __launch_bounds__(kCountThreads, WIDE ? 3 : MSBWT_OCT_CTAS)
 count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, PackedLayout lay, uint32_t k,
                        uint64_t *__restrict__ out, uint32_t *__restrict__ work, const uint8_t *__restrict__ syms,
                        uint32_t n_raw, uint32_t *__restrict__ exc, unsigned long long *__restrict__ stats = nullptr) {
+    static_assert(!(RAW && WIDE), "the fused path is compiled for 32-bit positions only");
+    using P = typename Pos<WIDE>::type;
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint64_t cb_smem[4];
-    const CBase<false> cb = stage_cbase<false>(ix, cb_smem);
+    __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
+    const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
     const uint64_t stream = policy_evict_first();
     constexpr uint32_t kFull = 0xffffffffu;
-    constexpr uint32_t kPool = RAW ? kOctRawPoolBytes : kOctPoolBytes;
+    constexpr uint32_t kPool = RAW ? kOctRawPoolBytes : (WIDE ? kOctWidePoolBytes : kOctPoolBytes);
     constexpr uint32_t kWarpSmem = 32 * kOctRowBytes + 2 * kPool;
 
     const uint32_t n = RAW ? n_raw : (uint32_t)packed[lay.live()];  // queries to walk (live list A)
@@ -132,11 +145,12 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     uint8_t *const pools = rows + 32 * kOctRowBytes;               // 2 pools of 32 queries
     const uint4 *const my_row = reinterpret_cast<const uint4 *>(rows + lane * kOctRowBytes);
 
-    // A SHORT list (the leftovers of the one-request kernel: a percent of the batch) is cut into smaller chunks so that
-    // every resident warp gets one: a warp walks its chunk 32 queries at a time, each a chain of dependent line fetches,
-    // and 512 queries per warp would leave most of the grid idle behind sixteen such rounds.
+    // A list that is not long against the grid (the leftovers of the one-request kernel: a percent of the batch; a
+    // 10 M-query batch of long k-mers) is cut into smaller chunks, about sixteen per resident warp: a warp walks its
+    // chunk 32 queries at a time, each a chain of dependent line fetches, and with 512-query chunks the last round
+    // of chunks would keep a fraction of the grid busy for a fifth of the run (10 M queries = 4.1 chunks per warp).
     const uint32_t warps_in_grid = gridDim.x * (kCountThreads / 32);
-    const uint32_t chunk_size = min((uint32_t)kOctChunk, max(32u, ((n / warps_in_grid) + 31u) & ~31u));
+    const uint32_t chunk_size = min((uint32_t)kOctChunk, max(32u, ((n / (warps_in_grid * 16u)) + 31u) & ~31u));
     // The queries are handed out in chunks of `chunk_size` (an atomic counter: a warp whose queries die early
     // simply comes back sooner, whatever the order of the batch) and staged pool by pool: pool A (sequence
     // number `seq`, buffer seq & 1) is being handed to the lanes, pool B (the other buffer) is already staged
@@ -169,7 +183,12 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             const bool on = lane < cnt;
             cp_async8(p + 8u * lane, w0 + idx, on);
             cp_async8(p + 256u + 8u * lane, seeds + idx, on);
-            cp_async4(p + 512u + 4u * lane, qidx + idx, on);
+            if constexpr (WIDE) {
+                cp_async8(p + 512u + 8u * lane, seeds + lay.n + idx, on);
+                cp_async4(p + 768u + 4u * lane, qidx + idx, on);
+            } else {
+                cp_async4(p + 512u + 4u * lane, qidx + idx, on);
+            }
         }
     };
     uint32_t seq = 0, a_pos = 0, a_cnt, b_cnt, a_base, b_base;
@@ -195,7 +214,7 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     };
     bool active = false;
     bool need_table = false;  // RAW: the next step is the suffix-table lookup
-    uint32_t l = 0, h = 0;
+    P l = 0, h = 0;
     uint64_t word = 0, pend = 0;
     uint32_t q = 0;
     uint32_t rem = 0;     // symbols still to consume
@@ -276,11 +295,16 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                     } else {
                         word = *reinterpret_cast<const volatile uint64_t *>(p + 8u * slot);
                         const uint64_t lo = *reinterpret_cast<const volatile uint64_t *>(p + 256u + 8u * slot);
-                        const uint32_t qraw = *reinterpret_cast<const volatile uint32_t *>(p + 512u + 4u * slot);
+                        const uint32_t qraw = *reinterpret_cast<const volatile uint32_t *>(p + (WIDE ? 768u : 512u) + 4u * slot);
                         q = qraw & kQidxMask;
                         no_fin = ((qraw >> 30) & 1u) != 0u;  // pack_seed_final_kernel already found this query's line overflowed
-                        l = (uint32_t)lo;
-                        h = (uint32_t)(lo >> 32);
+                        if constexpr (WIDE) {
+                            l = lo;
+                            h = *reinterpret_cast<const volatile uint64_t *>(p + 512u + 8u * slot);
+                        } else {
+                            l = (uint32_t)lo;
+                            h = (uint32_t)(lo >> 32);
+                        }
                         rem = rem0;
                         if (rem > (uint32_t)kPairSymsPerWord) pend = ldg_stream(wx + q, stream);
                     }
@@ -314,7 +338,7 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         // the last two of ten, one-symbol steps)
         const bool is_table = RAW && active && need_table;
         const bool live = active && !is_table && rem != 0 && l != h;
-        const uint32_t bl = l >> bshift, bh = h >> bshift;
+        const P bl = l >> bshift, bh = h >> bshift;
         // exactly kFinSyms symbols left: ONE final-step line answers the count (no rank needed for the last step)
         const bool is_fin = live && fin_base != nullptr && rem == (uint32_t)kFinSyms && forced == 0u && !no_fin &&
                             (l >> fshift) == (h >> fshift);
@@ -322,10 +346,10 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         const bool want_oct = live && !is_fin && rem >= (uint32_t)kOctSyms && forced == 0u;
         const bool is_oct = want_oct && bl == bh;
         if (want_oct && !is_oct) forced = (uint32_t)kOctSyms;  // symbols to take without the oct image
-        const bool is_quad = live && quad_base != nullptr && !is_oct && !is_fin && rem >= 4u && (forced == 0u || forced >= 4u);
+        const bool is_quad = !WIDE && live && quad_base != nullptr && !is_oct && !is_fin && rem >= 4u && (forced == 0u || forced >= 4u);
         const uint32_t codem = peek((uint32_t)kOctSyms);
         const uint32_t code8 = peek(4u);
-        const uint32_t sl = l / (uint32_t)kQuadSyms, sh = h / (uint32_t)kQuadSyms;
+        const uint32_t sl = WIDE ? 0u : (uint32_t)l / (uint32_t)kQuadSyms, sh = WIDE ? 0u : (uint32_t)h / (uint32_t)kQuadSyms;
         const uint64_t entry = RAW ? (word >> (64u - 2u * (depth0 ? depth0 : 1u))) : 0ull;  // suffix-table index
         const char *p0 = is_oct ? oct_base + ((size_t)codem * ix.nbuck8 + bl) * kOctLineBytes
                                 : quad_base + ((size_t)code8 * ix.nsec4 + sl) * kQuadSectorBytes;
@@ -377,7 +401,7 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             } else {
                 // hop from group header to group header (layout.h): a handful of 4-byte reads, not a scan of 31 words
                 const uint32_t tag = (uint32_t)(fin_mixed >> flb);
-                const int pl = (int)(l & fmask), ph = (int)(h & fmask);
+                const int pl = (int)((uint32_t)l & fmask), ph = (int)((uint32_t)h & fmask);
                 const uint32_t *roww = reinterpret_cast<const uint32_t *>(my_row);
                 int cnt = 0;
                 uint32_t hw = first.y;
@@ -399,34 +423,36 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             }
         } else if (is_oct) {
             const uint4 a = my_row[0], b = my_row[1];
-            if (a.y > (uint32_t)kOctCapacity) {
+            const uint32_t nruns = WIDE ? (a.y & 255u) : a.y;
+            if (nruns > (uint32_t)kOctCapacity) {
                 forced = (uint32_t)kOctSyms;  // this line cannot hold its runs: the same symbols without the oct image
             } else {
-                const int pl = (int)(l & bmask), ph = (int)(h & bmask);
+                const int pl = (int)((uint32_t)l & bmask), ph = (int)((uint32_t)h & bmask);
                 int cl = 0, ch = 0;
                 oct_add_run(a.z, bshift, bmask, pl, ph, cl, ch);
                 oct_add_run(a.w, bshift, bmask, pl, ph, cl, ch);
                 oct_add_runs(b, bshift, bmask, pl, ph, cl, ch);
-                if (a.y > 6u) {
+                if (nruns > 6u) {
                     oct_add_runs(my_row[2], bshift, bmask, pl, ph, cl, ch);
                     oct_add_runs(my_row[3], bshift, bmask, pl, ph, cl, ch);
-                    if (a.y > 14u) {
+                    if (nruns > 14u) {
                         oct_add_runs(my_row[4], bshift, bmask, pl, ph, cl, ch);
                         oct_add_runs(my_row[5], bshift, bmask, pl, ph, cl, ch);
-                        if (a.y > 22u) {
+                        if (nruns > 22u) {
                             oct_add_runs(my_row[6], bshift, bmask, pl, ph, cl, ch);
                             oct_add_runs(my_row[7], bshift, bmask, pl, ph, cl, ch);
                         }
                     }
                 }
-                l = a.x + (uint32_t)cl;
-                h = a.x + (uint32_t)ch;
+                const P ck = WIDE ? (P)(((uint64_t)(a.y >> 8) << 32) | a.x) : (P)a.x;
+                l = ck + (uint32_t)cl;
+                h = ck + (uint32_t)ch;
                 rem -= (uint32_t)kOctSyms;
                 shift -= 2 * kOctSyms;
             }
         } else if (is_quad) {
-            const uint32_t nl = staged_sector_rank(my_row[0], my_row[1], (int)(l - sl * (uint32_t)kQuadSyms));
-            const uint32_t nh = staged_sector_rank(my_row[2], my_row[3], (int)(h - sh * (uint32_t)kQuadSyms));
+            const uint32_t nl = staged_sector_rank(my_row[0], my_row[1], (int)((uint32_t)l - sl * (uint32_t)kQuadSyms));
+            const uint32_t nh = staged_sector_rank(my_row[2], my_row[3], (int)((uint32_t)h - sh * (uint32_t)kQuadSyms));
             l = nl;
             h = nh;
             rem -= 4;
@@ -438,9 +464,15 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                 st_cnt[5]++;
                 st_cnt[6] += (l >> kBlockShift) == (h >> kBlockShift) ? 1u : 2u;
             }
-            const uint2 r = oct_remainder_step(ix, cb.c, sym, l, h);
-            l = r.x;
-            h = r.y;
+            if constexpr (WIDE) {
+                const ulonglong2 r = oct_remainder_step_wide(ix, cb.c, cb.sb_shift, sym, l, h);
+                l = r.x;
+                h = r.y;
+            } else {
+                const uint2 r = oct_remainder_step(ix, cb.c, sym, l, h);
+                l = r.x;
+                h = r.y;
+            }
             rem--;
             shift -= 2;
             forced = forced ? forced - 1u : 0u;
@@ -452,6 +484,7 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
 // dynamic shared memory per CTA
 constexpr int kOctSmemPacked = (kCountThreads / 32) * (32 * kOctRowBytes + 2 * kOctPoolBytes);
 constexpr int kOctSmemRaw = (kCountThreads / 32) * (32 * kOctRowBytes + 2 * kOctRawPoolBytes);
+constexpr int kOctSmemWide = (kCountThreads / 32) * (32 * kOctRowBytes + 2 * kOctWidePoolBytes);
 
 // one full wave of CTAs for a kernel with `smem` bytes of dynamic shared memory, fewer if there is less work
 inline unsigned oct_grid(int device, const void *kernel, int smem, uint64_t n) {

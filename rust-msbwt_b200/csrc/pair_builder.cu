@@ -30,14 +30,7 @@ namespace {
 __device__ __forceinline__ bool is_acgt(uint32_t sy) { return ((0x2Eu >> sy) & 1u) != 0; }  // sy < 8
 __device__ __forceinline__ uint32_t acgt_idx(uint32_t sy) { return (sy - 1u - (sy >> 2)) & 3u; }
 
-// B[pos] from the one-step block planes (layout.h)
-__device__ __forceinline__ uint32_t symbol_at(const IndexView &ix, uint64_t pos) {
-    const uint32_t off = (uint32_t)pos & (kBlockSyms - 1);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blocks) + (pos >> kBlockShift) * kWordsPerBlock +
-                        (off >> 6) * 8 + ((off >> 5) & 1u);
-    const uint32_t bit = off & 31u;
-    return ((__ldg(w + 2) >> bit) & 1u) | (((__ldg(w + 4) >> bit) & 1u) << 1) | (((__ldg(w + 6) >> bit) & 1u) << 2);
-}
+// (symbol_at: B[pos] from the one-step block planes, device_rank.cuh)
 
 template <bool WIDE>
 __global__ void __launch_bounds__(kCountThreads) pair_codes_kernel(IndexView ix, uint8_t *__restrict__ codes) {

@@ -115,7 +115,9 @@ static cudaError_t launch_count_quad_t(int device, const IndexView &ix, const ui
 
 cudaError_t launch_count_quad(int device, const IndexView &ix, const uint64_t *d_packed, const PackedLayout &lay,
                               uint32_t k, uint64_t *d_out, cudaStream_t st) {
-    if (index_is_wide(ix)) return launch_count_quad_t<true>(device, ix, d_packed, lay, k, d_out, st);
+    if (index_is_wide(ix))
+        return ix.oct ? launch_count_oct_wide(device, ix, d_packed, lay, k, d_out, st)
+                      : launch_count_quad_t<true>(device, ix, d_packed, lay, k, d_out, st);
     if (ix.oct) {
         static bool prepared[64] = {};  // per device: 4 CTAs x 47 KB of staging per SM need the large shared-memory configuration
         if (device < 0 || device >= 64 || !prepared[device]) {

@@ -9,7 +9,7 @@ fn main() {
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let mut objs = vec![];
     // the same list as rust-msbwt_b200/build.py SOURCES
-    for f in ["capi.cu", "hostpath.cu", "kernels.cu", "quad_kernels.cu", "fused_kernels.cu", "stats_kernels.cu", "final_kernels.cu", "ext_kernels.cu",
+    for f in ["capi.cu", "hostpath.cu", "kernels.cu", "quad_kernels.cu", "fused_kernels.cu", "stats_kernels.cu", "wide_kernels.cu", "final_kernels.cu", "ext_kernels.cu",
               "loader.cu", "builder.cu", "pair_builder.cu", "quad_builder.cu", "oct_builder.cu", "fin_builder.cu", "bwt_build.cu"] {
         let obj = out.join(f).with_extension("o");
         let ok = Command::new(&nvcc)

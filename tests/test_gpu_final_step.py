@@ -46,6 +46,22 @@ def test_device_image_equals_the_specification(midsize, monkeypatch, shift, lb):
         assert F.line_groups(lines[i]) == F.line_groups(want[i]), i
 
 
+@pytest.mark.parametrize("shift,lb", [(16, 12), (11, 13)])
+def test_device_image_of_a_wide_index_equals_the_specification(midsize, monkeypatch, shift, lb):
+    """64-bit positions: the 20-symbol codes come from walking LF through the one-step blocks (fin_builder.cu
+    build_fin_codes_by_walk); the image has no positions in it, so it must equal the same specification"""
+    reads, o = midsize
+    g = make_index(o.rle_bytes(), monkeypatch, shift, lb, superblock_shift=4)
+    assert not g.quad_index
+    lines, b, l2, over = g.final_image()
+    assert (b, l2) == (shift, lb)
+    want, stats = F.build_final_image(decode(o.rle_bytes()), b=shift, lb=lb)
+    assert lines.shape == want.shape and over == stats["overflowed_lines"]
+    assert ((lines[:, 0] == F.OVERFLOW) == (want[:, 0] == F.OVERFLOW)).all()
+    for i in np.flatnonzero((want[:, 0] != 0) | (lines[:, 0] != 0)):
+        assert F.line_groups(lines[i]) == F.line_groups(want[i]), i
+
+
 @pytest.mark.parametrize("keep_quad", [1, 0])
 @pytest.mark.parametrize("shift,lb,table_s", [(16, 12, -1), (12, 12, -1), (10, 13, 7), (16, 12, 0), (14, 12, 12)])
 def test_counts_are_bit_exact_with_the_final_step(midsize, monkeypatch, shift, lb, table_s, keep_quad):

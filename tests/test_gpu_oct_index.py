@@ -70,7 +70,8 @@ def auto_shift(runs: int, n: int) -> int:
     return s
 
 
-def check_oct_image(g, bwt):
+def check_oct_image(g, bwt, wide=False):
+    """wide: the index has 64-bit positions -- word 1 of a line = min(runs, 31) | (checkpoint >> 32) << 8 (layout.h)"""
     lines = g.oct_image()
     n = bwt.size
     shift = g.oct_bucket_shift
@@ -95,7 +96,7 @@ def check_oct_image(g, bwt):
     np.add.at(per, (rc, rb), lens)
     np.add.at(nruns, (rc, rb), 1)
     before = np.cumsum(per, axis=1) - per
-    assert (lines[:, :, 1] == nruns).all()
+    assert (lines[:, :, 1] == (np.minimum(nruns, CAP + 1) if wide else nruns)).all()  # (checkpoints below 2^32 here)
     assert (lines[:, :, 0] == (before + c8[:, None]).astype(np.uint32)).all()
     over = nruns > CAP
     assert g.oct_overflow_lines == int(over.sum())
@@ -203,15 +204,93 @@ def test_oct_path_on_low_complexity_reads_where_lines_overflow(monkeypatch):
     assert (g.count_kmers_fixed(q, 31) == o.count_kmers_fixed(q, 31, threads=8)).all()
 
 
-def test_oct_on_golden_fixture_and_wide_indexes_refuse_it(golden_dir):
+@pytest.mark.parametrize("shift", [0, 17])
+def test_wide_oct_image_equals_brute_force(shift):
+    """64-bit positions (here: superblocks of 1024 symbols): the codes come from walking LF through the one-step
+    blocks (no pair / quad image on the way), the lines carry 40-bit checkpoints"""
+    rng = np.random.default_rng(2021)
+    from harness import bwt_build, synth
+    reads = synth.make_reads(400, 60, 15.0, 0.02, device="cuda")
+    reads[3, 10:12] = 4
+    low = synth.make_reads(3000, 50, 600.0, 0.03, device="cuda")
+    streams = [
+        O.convert_to_vec(naive.naive_bwt(["CCGTACGTA", "GGTACAGTA", "ACGACGACG", "ANNT"])),
+        _random_rle(rng, 3000, [1, 1, 1, 2, 3, 5, 9, 31, 32, 33, 95, 96, 97, 223, 224, 225, 255]),
+        bwt_build.build_rle_bwt(reads)[0].cpu().numpy(),
+        bwt_build.build_rle_bwt(low)[0].cpu().numpy(),
+    ]
+    for rle in streams:
+        g = M.RleBWT(oct_index=1, oct_bucket_shift=shift, superblock_shift=3)
+        g.load_vector(rle)
+        wide = (g.get_total_size() >> 7) + 1 > 8  # more than one superblock of 8 blocks (the 4-string BWT is not)
+        assert g.oct_index and g.quad_index == (not wide) and not g.pair_index
+        assert g.oct_bucket_shift == (shift or auto_shift(g.oct_runs, g.get_total_size()))
+        bwt = decode(np.asarray(rle, dtype=np.uint8))
+        check_oct_image(g, bwt, wide=wide)
+
+
+@pytest.mark.parametrize("table_s,shift,final", [(-1, 0, -1), (0, 18, 0), (3, 19, 1), (7, 18, 0), (11, 19, -1), (12, 20, 0), (14, 17, 1)])
+def test_wide_oct_path_is_bit_exact(midsize, table_s, shift, final):
+    """the WIDE instantiation of the oct kernel (wide_kernels.cu) against the reference's algorithm, with and
+    without final-step lines, every table depth / remainder combination, `$` / N inside the k-mers"""
+    from harness import synth
+    reads, o = midsize
+    g = M.RleBWT(suffix_table_s=table_s, oct_index=1, oct_bucket_shift=shift, final_index=final, superblock_shift=4)
+    g.load_vector(o.rle_bytes())
+    assert g.oct_index and not g.quad_index and g.final_index == (final != 0)
+    rng = np.random.default_rng(12 + 10 * (table_s + 1))
+    for k in (1, 2, 3, 9, 10, 11, 13, 20, 21, 24, 25, 30, 31, 32, 33, 34, 35, 40, 41, 44, 45, 51, 54, 63, 64, 65, 71, 100):
+        q = synth.make_queries(reads, k, 12001, 8000).cpu().numpy()
+        q[5, 0] = 4
+        q[7, k - 1] = 0
+        q[11, k // 2] = 4
+        got = g.count_kmers_fixed(q, k)
+        want = o.count_kmers_fixed(q, k, threads=8)
+        assert (got == want).all(), (table_s, k, np.flatnonzero(got != want)[:5])
+        if k >= 29:
+            assert int((got > 0).sum()) >= 11990
+        if k <= 32:
+            packed = np.zeros(q.shape[0], dtype=np.uint64)
+            ok = np.isin(q, ACGT).all(axis=1)
+            idx = np.zeros(8, dtype=np.uint64)
+            idx[ACGT] = np.arange(4, dtype=np.uint64)
+            for i in range(k):
+                packed = (packed << np.uint64(2)) | idx[q[:, i]]
+            assert (g.count_kmers_u64(packed[ok], k) == want[ok]).all(), (table_s, k)
+    ragged = [rng.integers(0, 6, int(rng.integers(0, 40))).astype(np.uint8) for _ in range(3000)]
+    assert (g.count_kmers(ragged) == o.count_kmers(ragged)).all()
+
+
+def test_wide_oct_path_on_low_complexity_reads_where_lines_overflow():
+    """most lines in use overflow: the WIDE kernel answers them with one-symbol steps (no quad image beside it)"""
+    from harness import bwt_build, synth
+    reads = synth.make_reads(30000, read_len=100, coverage=1500.0, error_rate=0.01, device="cuda")
+    rle = bwt_build.build_rle_bwt(reads)[0].cpu().numpy()
+    o = O.RleBWT()
+    o.load_vector(rle)
+    g = M.RleBWT(oct_index=1, superblock_shift=5)
+    g.load_vector(rle)
+    assert g.oct_index and g.final_index and g.oct_overflow_lines > 1000
+    for k in (8, 16, 31, 32, 41, 64):
+        q = synth.make_queries(reads, k, 20000, 5000).cpu().numpy()
+        assert (g.count_kmers_fixed(q, k) == o.count_kmers_fixed(q, k, threads=8)).all(), k
+
+
+def test_oct_on_golden_fixture_also_with_64_bit_positions(golden_dir):
     z = np.load(f"{golden_dir}/reads30x_k31.npz")
     g = M.RleBWT(oct_index=1)
     g.load_vector(z["rle"])
     assert g.oct_index
     assert (g.count_kmers_fixed(z["queries"], int(z["k"])) == z["counts"]).all()
     assert (g.count_kmers_fixed(z["queries_k12"], 12) == z["counts_k12"]).all()
-    # 64-bit positions (several superblocks): the oct image is not built, the quad image serves alone
+    # 64-bit positions (several superblocks): oct and final-step lines built by the LF walk, no quad image
     w = M.RleBWT(oct_index=1, superblock_shift=3)
     w.load_vector(z["rle"])
-    assert w.quad_index and not w.oct_index
+    assert w.oct_index and w.final_index and not w.quad_index
     assert (w.count_kmers_fixed(z["queries"], int(z["k"])) == z["counts"]).all()
+    assert (w.count_kmers_fixed(z["queries_k12"], 12) == z["counts_k12"]).all()
+    # ... and with the oct image switched off the quad image serves alone, as before
+    w4 = M.RleBWT(oct_index=0, quad_index=1, superblock_shift=3)
+    w4.load_vector(z["rle"])
+    assert w4.quad_index and not w4.oct_index
+    assert (w4.count_kmers_fixed(z["queries"], int(z["k"])) == z["counts"]).all()

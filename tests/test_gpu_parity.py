@@ -337,10 +337,33 @@ def test_full_size_config1_properties():
         assert g.get_symbol_count(s) == o.get_symbol_count(s)
 
 
+def _kmers_that_occur(o, syms, ends, rng, k, m):
+    """m k-mers with count >= 1 in ANY symbol stream: the symbols B[j], B[LF j], .. of a walk from a random position j
+    are what count_kmer consumes, last symbol first (src/msbwt_core.rs:148-155), so reversed they are a k-mer whose
+    range still holds the walk's end.  LF from the oracle's constrain_range; walks that meet `$` / N are dropped."""
+    n = int(ends[-1])
+    out = []
+    while len(out) < m:
+        p = int(rng.integers(0, n))
+        walk = []
+        for _ in range(k):
+            s = int(syms[np.searchsorted(ends, np.int64(p), side="right")])  # (`ends` is int64: no per-call conversion)
+            if s in (0, 4):
+                break
+            walk.append(s)
+            p = o.constrain_range(s, p, p)[0]
+        if len(walk) == k:
+            out.append(walk[::-1])
+    return np.array(out, dtype=np.uint8)
+
+
 def test_wide_index_beyond_2_pow_32_symbols():
     """Maximum-size edge: N > 2^32 (u64 positions, two default-size superblocks).  Any RLE stream is a legal
     index, so a 4.6 Gsymbol one is made from ~4.6 M long runs; ranges and k-mer counts must match the
-    oracle at positions on both sides of 2^32."""
+    oracle at positions on both sides of 2^32.  The index lives in HBM, so the automatic layout is the oct and
+    final-step images with 40-bit checkpoints, built by walking LF through the one-step blocks and searched by the
+    WIDE instantiation of the oct kernel; the pair image it replaced is checked beside it."""
+    torch.cuda.empty_cache()
     rng = np.random.default_rng(2032)
     nruns = 4_600_000
     syms = rng.choice(np.array([0, 1, 2, 3, 4, 5], dtype=np.uint8), size=nruns, p=[0.02, 0.26, 0.24, 0.24, 0.02, 0.22])
@@ -352,6 +375,7 @@ def test_wide_index_beyond_2_pow_32_symbols():
     g, o = both(rle)
     n = o.get_total_size()
     assert n > (1 << 32) and g.get_total_size() == n
+    assert g.oct_index and g.final_index and not g.quad_index and not g.pair_index and g.suffix_table_s == 14
     m = 200_000
     sym = rng.integers(0, 6, m).astype(np.uint8)
     lo = rng.integers(0, n + 1, m).astype(np.uint64)
@@ -363,12 +387,30 @@ def test_wide_index_beyond_2_pow_32_symbols():
         assert (int(gl[i]), int(gh[i])) == o.constrain_range(int(sym[i]), int(lo[i]), int(hi[i])), i
     for i in range(4):
         assert (int(gl[i]), int(gh[i])) == o.constrain_range(int(sym[i]), int(lo[i]), int(hi[i])), i
+    pair = M.RleBWT(oct_index=0)  # the layout of such an index before the wide oct image existed
+    pair.load_vector(rle)
+    assert pair.pair_index and not pair.oct_index
     for k in (3, 9, 24):
         q = rng.choice(np.array([1, 2, 3, 5], dtype=np.uint8), size=(100_000, k))
         q[::97, 0] = 4
-        assert (g.count_kmers_fixed(q, k) == o.count_kmers_fixed(q, k, threads=8)).all(), k
+        want = o.count_kmers_fixed(q, k, threads=8)
+        assert (g.count_kmers_fixed(q, k) == want).all(), k
+        assert (pair.count_kmers_fixed(q, k) == want).all(), k
+    # k-mers that occur (walks of LF from random positions: half of them start beyond 2^32), through every kind of
+    # step of the wide kernel: oct lines (k = 24, 44), a final-step line (31..34), both (45, 63, 70), remainders
+    ends = np.cumsum(counts.astype(np.int64))
+    for k in (24, 31, 32, 34, 44, 45, 63, 70):
+        q = np.concatenate([_kmers_that_occur(o, syms, ends, rng, k, 600),
+                            rng.choice(np.array([1, 2, 3, 5], dtype=np.uint8), size=(500, k))])
+        want = o.count_kmers_fixed(q, k, threads=8)
+        assert int((want[:600] > 0).sum()) == 600
+        got = g.count_kmers_fixed(q, k)
+        assert (got == want).all(), (k, np.flatnonzero(got != want)[:5])
+        assert (pair.count_kmers_fixed(q, k) == want).all(), k
     ragged = [rng.integers(0, 6, int(rng.integers(0, 9))).astype(np.uint8) for _ in range(3000)]
     assert (g.count_kmers(ragged) == o.count_kmers(ragged)).all()
+    del g, pair
+    torch.cuda.empty_cache()
 
 
 @pytest.mark.parametrize("sb_shift", [0, 2])
