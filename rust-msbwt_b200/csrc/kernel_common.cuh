@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdio>
+
 #include "engine.h"
 
 namespace msbwt {
@@ -85,6 +87,16 @@ __device__ __forceinline__ uint32_t swar_lut_pack4_top(uint32_t x, uint32_t &acc
 // top bytes of four words -> one word, word i at byte i
 __device__ __forceinline__ uint32_t swar_gather4(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
     return prmt_b32(prmt_b32(m0, m1, 0x0073u), prmt_b32(m2, m3, 0x0073u), 0x5410u);
+}
+
+// CONVERGENCE GUARD for kernels whose lanes exchange data (shuffles, ballots, shared memory + __syncwarp) after
+// divergent code.  ptxas 12.9 may "prove" such a warp converged, drop every __syncwarp() and issue the collectives
+// without a WARPSYNC; on B200 that assumption failed under load in the oct search kernel (oct_kernel.cuh has the
+// story, profiles/r2t_convergence.md the evidence).  A call ptxas cannot see through -- a printf that never runs: the
+// bits of a launch's query count above 2^40 are never set -- makes it compile the kernel conservatively, with
+// WARPSYNC.COLLECTIVE before every collective.  tests/test_sass_contract.py checks the SASS for it.
+__device__ __forceinline__ void warp_sync_guard(const PackedLayout &lay) {
+    if ((uint32_t)(lay.n >> 40) == 0x5EEDu) printf("%u", (uint32_t)lay.n);
 }
 
 inline int sm_count(int device) {

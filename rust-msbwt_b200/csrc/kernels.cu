@@ -239,6 +239,7 @@ count_kmers_packed_kernel(IndexView ix, const uint64_t *__restrict__ packed, Pac
     __shared__ uint64_t cb_smem[WIDE ? kMaxSuperInSmem * 8 : 4];
     const CBase<WIDE> cb = stage_cbase<WIDE>(ix, cb_smem);
     const uint64_t stream = policy_evict_first();
+    if constexpr (LANES == 2) warp_sync_guard(lay);  // the lanes of a pair exchange their halves through shuffles
 
     constexpr uint32_t kPerWord = BITS == 3 ? kSymsPerWord : kPairSymsPerWord;
     constexpr int kTop = 64 - BITS - (BITS == 3 ? 1 : 0);  // bit offset of a word's first symbol: 60 / 62
@@ -322,6 +323,7 @@ count_kmers_pair_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packe
     __shared__ uint64_t c2_smem[WIDE ? kMaxSuperInSmem * 16 : 1];
     const C2Base<WIDE> c2 = stage_c2base<WIDE>(ix, c2_smem);
     const uint64_t stream = policy_evict_first();
+    warp_sync_guard(lay);  // the lanes of a quad exchange their quarters through shuffles
 
     const uint32_t n = (uint32_t)packed[lay.live()];  // live queries of list A
     const uint32_t tid = blockIdx.x * kCountThreads + threadIdx.x;

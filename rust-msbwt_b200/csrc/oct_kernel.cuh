@@ -129,6 +129,17 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     constexpr uint32_t kWarpSmem = 32 * kOctRowBytes + 2 * kPool;
 
     const uint32_t n = RAW ? n_raw : (uint32_t)packed[lay.live()];  // queries to walk (live list A)
+    // CONVERGENCE.  The warp protocol below (24 shuffles, a ballot and three __syncwarp() per iteration) needs the 32
+    // lanes together at every one of those points.  Left alone, ptxas 12.9 "proves" that they are (the divergent
+    // regions all close with BSYNC.RECONVERGENT), drops every __syncwarp() and issues the shuffles / votes without a
+    // WARPSYNC -- and on B200 that assumption does not hold under load: on batches of 50-100 M k-mers that take oct
+    // steps AND a final-step line (k = 43, 53, 63) about every other launch left a few hundred queries unanswered and
+    // some warps never finished, while every build whose SASS carries WARPSYNC.COLLECTIVE ran clean (profiles/
+    // r2t_convergence.md).  warp_sync_guard (kernel_common.cuh) makes ptxas compile the kernel conservatively:
+    // WARPSYNC.COLLECTIVE before every collective, which is what the source asks for.  tests/test_sass_contract.py
+    // checks the SASS of every instantiation for it, so that a toolchain that changes its mind cannot silently take
+    // it away again.
+    warp_sync_guard(lay);
     const uint32_t lane = threadIdx.x & 31u;
     if ((blockIdx.x * (kCountThreads / 32) + (threadIdx.x >> 5)) * 32u >= n) return;  // more warps than pools of work
     const uint64_t *w0 = packed + lay.w0(), *seeds = packed + lay.seed(), *wx = packed + lay.wx();
@@ -222,6 +233,9 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     uint32_t widx = 0;
     uint32_t forced = 0;  // symbols to take without the oct image (overflowed line / two buckets)
     bool no_fin = false;  // this query's final-step line overflowed: its last kFinSyms symbols go through the oct steps
+#ifdef MSBWT_OCT_WATCHDOG
+    uint32_t wd_age = 0;  // debug build: iterations this lane has spent on its current query
+#endif
     const char *const fin_base = reinterpret_cast<const char *>(ix.fin);
     const uint32_t fshift = ix.fin_shift, fmask = (1u << fshift) - 1u, flb = ix.fin_lb;
 
@@ -261,6 +275,9 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                     forced = 0;
                     no_fin = false;
                     active = true;
+#ifdef MSBWT_OCT_WATCHDOG
+                    wd_age = 0;
+#endif
                     if constexpr (STATS) st_cnt[7]++;
                     if constexpr (RAW) {
                         q = (from_a ? a_base : b_base) + slot;
@@ -333,6 +350,14 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             if (2u * rem > (uint32_t)(shift + 2)) pend = ldg_stream(wx + (uint64_t)widx * lay.n + q, stream);
         }
 
+#ifdef MSBWT_OCT_WATCHDOG
+        if (active && ++wd_age > 4096u) {  // no k-mer needs more than k iterations: say what this one is doing and drop it
+            printf("[oct watchdog] q %u rem %u l %llu h %llu shift %d widx %u forced %u no_fin %d word %016llx pend %016llx k %u n %u\n", q, rem,
+                   (unsigned long long)l, (unsigned long long)h, shift, widx, forced, (int)no_fin, (unsigned long long)word,
+                   (unsigned long long)pend, k, n);
+            rem = 0;
+        }
+#endif
         // ---- ISSUE (branch-free): every lane publishes what its query needs, the warp fetches it
         // (a range over two buckets, like an overflowed line, takes its kOctSyms symbols as quad steps and, for
         // the last two of ten, one-symbol steps)
@@ -365,6 +390,21 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             st_cnt[3] += is_quad;
             if (is_quad) st_cnt[4] += (((size_t)code8 * ix.nsec4 + sl) >> 2) == (((size_t)code8 * ix.nsec4 + sh) >> 2) ? 1u : 2u;
         }
+#ifdef MSBWT_OCT_WATCHDOG
+        {   // debug build: every address a live lane is about to ask for must lie inside its image
+            const uint64_t fin_lines = ((ix.total >> fshift) + 1ull) << flb;
+            const uint64_t fin_line = (((uint64_t)(l >> fshift)) << flb) | (fin_mixed & ((1ull << flb) - 1ull));
+            const bool bad = (live && ((uint64_t)l > (uint64_t)h || (uint64_t)h > ix.total)) || (active && q >= (uint32_t)lay.n) ||
+                             (is_fin && fin_line >= fin_lines) || (is_oct && ((uint64_t)bl >= ix.nbuck8 || codem >= (uint32_t)kOctCodes)) ||
+                             (is_quad && ((uint64_t)sl >= ix.nsec4 || (uint64_t)sh >= ix.nsec4 || code8 >= 256u));
+            if (bad) {
+                printf("[oct watchdog] BAD STATE q %u rem %u l %llu h %llu shift %d widx %u forced %u no_fin %d word %016llx pend %016llx fin %d oct %d quad %d "
+                       "codem %u code8 %u age %u total %llu\n", q, rem, (unsigned long long)l, (unsigned long long)h, shift, widx, forced, (int)no_fin,
+                       (unsigned long long)word, (unsigned long long)pend, (int)is_fin, (int)is_oct, (int)is_quad, codem, code8, wd_age,
+                       (unsigned long long)ix.total);
+            }
+        }
+#endif
         const uint32_t p0_lo = (uint32_t)(uintptr_t)p0, p0_hi = (uint32_t)((uintptr_t)p0 >> 32);
         {
             const uint32_t j = lane & 7u;  // this lane's 16 bytes of a line
@@ -394,7 +434,7 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             need_table = false;
         } else if (is_fin) {
             const uint4 first = my_row[0];
-            const uint32_t used = first.x;
+            const uint32_t used = first.x;  // <= 31 in any line the builder wrote
             if (used == kFinOverflow) {
                 no_fin = true;  // the same symbols through two oct steps
                 if constexpr (STATS) st_cnt[2]++;
@@ -405,7 +445,10 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                 const uint32_t *roww = reinterpret_cast<const uint32_t *>(my_row);
                 int cnt = 0;
                 uint32_t hw = first.y;
-                for (uint32_t idx = 1u; idx <= used;) {
+#ifdef MSBWT_OCT_WATCHDOG
+                if (used > 31u) printf("[oct watchdog] final-step line of q %u says %u words in use (l %llu h %llu)\n", q, used, (unsigned long long)l, (unsigned long long)h);
+#endif
+                for (uint32_t idx = 1u; idx <= min(used, (uint32_t)kFinLineWords - 1u);) {  // (bounded whatever the row holds)
                     const uint32_t nr = hw & 15u;
                     if ((hw >> 4) == tag) {
                         for (uint32_t r = 1u; r <= nr; r++) {

@@ -8,7 +8,9 @@ src/rle_bwt.rs:202-287 -- answers a sample in seconds; the whole batch is covere
     the counts of the packed-integer entry (a third pack stage);
   * partition: count(Q) == sum over the six symbols c of count(cQ)   (constrain_range splits a range);
   * counts are permutation-equivariant (nothing depends on where a query sits in the batch);
-  * host-buffer entry == device-buffer entry.
+  * host-buffer entry == device-buffer entry;
+  * configs[2] only: 100 M 43-mers and 70 M 63-mers in ONE launch of the general search kernel, repeated -- the shape that
+    exposed the dropped warp synchronisations of round 2 (profiles/r2t_convergence.md).
 
 Both workloads are bench.py's own (same generator, same seeds), so what is tested here is what the bench line times."""
 import numpy as np
@@ -42,7 +44,7 @@ def _device_counts(g, q, k, fast: bool | None, monkeypatch):
     return d_out, stats
 
 
-def _check_workload(key: str, monkeypatch, expect_quad: bool):
+def _check_workload(key: str, monkeypatch, expect_quad: bool, long_kmers: bool = False):
     import bench
     cfg = bench.WORKLOADS[key]
     dev = torch.device("cuda:0")
@@ -105,12 +107,42 @@ def _check_workload(key: str, monkeypatch, expect_quad: bool):
     assert (got[:s] == o.count_kmers_fixed(q_host[:s], k, threads=16)).all()
     for sym in range(6):
         assert g.get_symbol_count(sym) == o.get_symbol_count(sym)
+    if long_kmers:
+        del fast, queries
+        torch.cuda.empty_cache()
+        _check_long_kmers(g, o, cfg, dev, monkeypatch)
     return checksum
+
+
+def _check_long_kmers(g, o, cfg, dev, monkeypatch):
+    """REGRESSION (round 2): very large launches of the general search kernel with k-mers that take oct steps AND a
+    final-step line.  ptxas had dropped every warp synchronisation of that kernel and on 50-100 M-query launches about
+    every other one came back with a few hundred unanswered queries (and warps that never ended); never on the first
+    launch of a process, hence the repetitions.  Counts must be equal launch after launch, every read-sampled k-mer
+    must occur, and a sample must equal the oracle's."""
+    from harness import synth
+    reads = synth.make_reads(cfg["reads"], cfg["read_len"], cfg["coverage"], cfg["error"], device=dev)
+    for k, n, reps in ((43, 100_000_000, 6), (63, 70_000_000, 4)):
+        q = synth.make_queries(reads, k, n, 0, seed_offset=k)
+        first = None
+        for _ in range(reps):
+            got, st = _device_counts(g, q, k, None, monkeypatch)
+            assert st["live_a"] == n and st["final_lines"] == 0      # the general kernels, one launch of n queries
+            assert int((got >= 1).sum().item()) == n, k
+            if first is None:
+                first = got
+                s = 200_000
+                want = o.count_kmers_fixed(q[-s:].cpu().numpy(), k, threads=16)   # the END of the list: where it went wrong
+                assert (got[-s:].cpu().numpy().view(np.uint64) == want).all(), k
+            else:
+                assert torch.equal(got, first), k
+        del q, first, got
+        torch.cuda.empty_cache()
 
 
 def test_config3_full_size_properties(monkeypatch):
     """configs[2]: 10 M reads x 150 bp with 1 % errors, 1.51 Gsymbol BWT, 100 M read-sampled 31-mers"""
-    assert _check_workload("cfg3", monkeypatch, expect_quad=True) >= 100_000_000
+    assert _check_workload("cfg3", monkeypatch, expect_quad=True, long_kmers=True) >= 100_000_000
 
 
 def test_config5_full_size_properties(monkeypatch):
