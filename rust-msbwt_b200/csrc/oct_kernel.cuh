@@ -425,6 +425,8 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
         __syncwarp();
 
         // ---- CONSUME (each lane ranks in its own staged line)
+        bool fin_scan = false;                 // this lane's final-step line is good: its runs are summed in phase 2
+        uint32_t fin_at = 0, fin_left = 0;     // header word of the first group of its code, groups of that code
         if (is_table) {
             const uint4 e = my_row[0];
             l = (entry & 1ull) ? e.z : e.x;
@@ -439,30 +441,25 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                 no_fin = true;  // the same symbols through two oct steps
                 if constexpr (STATS) st_cnt[2]++;
             } else {
-                // hop from group header to group header (layout.h): a handful of 4-byte reads, not a scan of 31 words
+                // Phase 1, per lane: hop from group header to group header (layout.h) to the FIRST group of this query's
+                // code and count its groups (they are adjacent: the builder writes a line's groups in key order) -- a
+                // handful of 4-byte reads with nothing nested inside, so the lanes differ only in their trip counts.
+                // The runs are summed by the warp in step, below the branches (phase 2).
                 const uint32_t tag = (uint32_t)(fin_mixed >> flb);
-                const int pl = (int)((uint32_t)l & fmask), ph = (int)((uint32_t)h & fmask);
                 const uint32_t *roww = reinterpret_cast<const uint32_t *>(my_row);
-                int cnt = 0;
+                const uint32_t lim = min(used, (uint32_t)kFinLineWords - 1u);  // (bounded whatever the row holds)
                 uint32_t hw = first.y;
 #ifdef MSBWT_OCT_WATCHDOG
                 if (used > 31u) printf("[oct watchdog] final-step line of q %u says %u words in use (l %llu h %llu)\n", q, used, (unsigned long long)l, (unsigned long long)h);
 #endif
-                for (uint32_t idx = 1u; idx <= min(used, (uint32_t)kFinLineWords - 1u);) {  // (bounded whatever the row holds)
-                    const uint32_t nr = hw & 15u;
-                    if ((hw >> 4) == tag) {
-                        for (uint32_t r = 1u; r <= nr; r++) {
-                            const uint32_t w = roww[idx + r];
-                            const int off = (int)(w & 0xFFFFu), len = (int)(w >> 16);
-                            cnt += min(max(ph - off, 0), len) - min(max(pl - off, 0), len);
-                        }
-                    }
-                    idx += 1u + nr;
-                    if (idx <= used) hw = roww[idx];
+                fin_scan = true;
+                for (uint32_t idx = 1u; idx <= lim;) {
+                    const bool eq = (hw >> 4) == tag;
+                    if (eq && fin_left == 0u) fin_at = idx;
+                    fin_left += eq ? 1u : 0u;
+                    idx += 1u + (hw & 15u);
+                    if (idx <= lim) hw = roww[idx];
                 }
-                l = 0;
-                h = (uint32_t)cnt;  // only h - l is read from here on
-                rem = 0;
             }
         } else if (is_oct) {
             const uint4 a = my_row[0], b = my_row[1];
@@ -519,6 +516,38 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             rem--;
             shift -= 2;
             forced = forced ? forced - 1u : 0u;
+        }
+        // Phase 2 of the final-step lines, the warp in step: every lane adds up the runs of its group, four words per
+        // trip, as many trips as the longest group among the lanes needs; a code with more than 15 runs in the bucket
+        // continues in the group right behind.  (One lane after the other, inside the branch above, this scan was a
+        // quarter of all the warp instructions of a 63-mer batch: profiles/r2w_oct_k63_ncu_summary.txt.)
+        if (__any_sync(kFull, fin_scan)) {
+            const uint32_t *roww = reinterpret_cast<const uint32_t *>(my_row);
+            const int pl = (int)((uint32_t)l & fmask), ph = (int)((uint32_t)h & fmask);
+            int acc = 0;
+            do {
+                const uint32_t n1 = fin_left ? (roww[fin_at] & 15u) : 0u;
+                const uint32_t trips = __reduce_max_sync(kFull, n1);
+                for (uint32_t r = 0; r < trips; r += 4u) {
+#pragma unroll
+                    for (uint32_t u = 0; u < 4u; u++) {
+                        if (r + u < n1) {
+                            const uint32_t w = roww[fin_at + 1u + r + u];
+                            const int off = (int)(w & 0xFFFFu), len = (int)(w >> 16);
+                            acc += min(max(ph - off, 0), len) - min(max(pl - off, 0), len);
+                        }
+                    }
+                }
+                if (fin_left) {
+                    fin_at += 1u + n1;
+                    fin_left--;
+                }
+            } while (__any_sync(kFull, fin_left != 0u));
+            if (fin_scan) {
+                l = 0;
+                h = (uint32_t)acc;  // only h - l is read from here on
+                rem = 0;
+            }
         }
         __syncwarp();  // the rows are rewritten by the next ISSUE
     }
