@@ -92,10 +92,13 @@ msbwt_index *msbwt_index_create_ex(const uint8_t *rle, uint64_t len, const int *
  * device memory; MSBWT_QUAD_INDEX=0|1 overrides), 0 = never, 1 = always.  Results are identical.
  * `oct_index`: the OCT image -- one 128-byte line of explicit occurrence RUNS per (m-symbol code, 2^b-position
  * bucket), m = msbwt_oct_symbols() = 10 constrain_range steps per line fill, 128 * 4^m * (N / 2^b + 1) bytes --
- * is built next to the quad image when positions are 32-bit (-1 = automatic: whenever the quad image is built
- * and the oct image fits a quarter of the device memory left; MSBWT_OCT_INDEX=0|1 overrides), 0 = never,
- * 1 = always (implies quad_index).  Lines that cannot hold their bucket's runs are answered through the quad
- * image, so results are identical on any input.  `oct_bucket_shift`: b, 8..24 (0 = automatic: the largest b
+ * is built next to the quad image (-1 = automatic: whenever the quad image is built and the oct image fits a quarter
+ * of the device memory left; MSBWT_OCT_INDEX=0|1 overrides), 0 = never, 1 = always (implies quad_index).  An index
+ * whose positions need 64 bits (2^32 symbols and more -- the reference is u64 throughout, src/msbwt_core.rs:18-24 --
+ * or several superblocks) gets the same lines with 40-bit checkpoints, built by walking LF through the one-step
+ * blocks, and no quad image (36.6 bytes per position have no room): automatic when it lives in HBM and the images
+ * fit.  Lines that cannot hold their bucket's runs are answered through the quad image or one-symbol ranks, so
+ * results are identical on any input.  `oct_bucket_shift`: b, 8..24 (0 = automatic: the largest b
  * that keeps the mean number of runs per line <= 6).  Under an oct image the automatic suffix-table depth is
  * 14 with levels 11..13 kept: a 31-mer is one L2-resident table entry (depth 11) + two oct lines.
  * `keep_quad_index` (under an oct image): the quad image is what the builders walk LF^4 with; afterwards it only
