@@ -31,6 +31,12 @@ __device__ __forceinline__ uint2 ldg_table_entry(const uint2 *p, uint64_t pol_la
     return r;
 }
 
+__device__ __forceinline__ ulonglong2 ldg_table_entry(const ulonglong2 *p, uint64_t pol_last) {  // 64-bit positions
+    ulonglong2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(r.x), "=l"(r.y) : "l"(p), "l"(pol_last));
+    return r;
+}
+
 struct Half { uint32_t w[8]; };  // 32 bytes = one sector of a block
 
 // half an index block: read-only path, no L1 allocation, evict-last in L2 (256-bit load)

@@ -29,6 +29,7 @@
 // live list B (k-mers holding `$` / `N`: seed_general, one symbol at a time -- rare).  Appends to list A are staged
 // per warp in shared memory and flushed 32+ at a time: one atomic per flush, not per query.
 #include <cstdlib>
+#include <type_traits>
 
 #include "oct_kernel.cuh"
 #include "pack_common.cuh"
@@ -48,20 +49,24 @@ constexpr int kFinByteBuf = 32 * 32 + 16;    // 32 k-mers of k <= 32 symbol byte
 //                 and 64 registers per thread, 4 CTAs per SM (32 warps).  The loop is bound by the latency of its own
 //                 dependent instructions (ncu, profiles/r2g_*: 640 instructions per batch issue in 5600 cycles per
 //                 warp at 4 warps per scheduler), which only more resident warps can hide.
-template <bool DEEP> struct FinShape {
+// WIDE (64-bit positions: an index of 2^32 symbols and more, or one cut into several superblocks): 16-byte table
+// entries, two seed words per queued query, 3 CTAs per SM for the registers the wider ranges take.
+template <bool DEEP, bool WIDE = false> struct FinShape {
     static constexpr int kBufs = DEEP ? 2 : 1;
     static constexpr int kQueue = DEEP ? 64 : 32;  // list-A entries a warp stages before it flushes
-    static constexpr int kWarpSmem = kBufs * 32 * kFinRowBytes + kBufs * kFinByteBuf + kQueue * 20;
+    static constexpr int kWarpSmem = kBufs * 32 * kFinRowBytes + kBufs * kFinByteBuf + kQueue * (WIDE ? 28 : 20);
     static constexpr int kSmem = kFinWarps * kWarpSmem;
-    static constexpr int kCtasPerSm = DEEP ? 2 : 4;
+    static constexpr int kCtasPerSm = DEEP ? 2 : (WIDE ? 3 : 4);
 };
+
+
 
 enum : uint32_t { kKindNone = 0, kKindZero = 1, kKindLine = 2, kKindTwoBuckets = 3 };
 
 // SRC 0: symbol bytes; 1: caller-packed integers (first symbol most significant); 2: host-packed words (last symbol
 // in the top bits).  K = 31: every shift, mask and copy count a constant; K = 0: k_rt (k <= 32).
-template <int SRC, uint32_t K, bool DEEP>
-__global__ void __launch_bounds__(kFinThreads, FinShape<DEEP>::kCtasPerSm)
+template <int SRC, uint32_t K, bool DEEP, bool WIDE = false>
+__global__ void __launch_bounds__(kFinThreads, FinShape<DEEP, WIDE>::kCtasPerSm)
 pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_rt, SeedPlan plan, PackedLayout lay,
                        uint64_t *__restrict__ packed, uint64_t *__restrict__ out, uint32_t *__restrict__ status) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -76,7 +81,9 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
     if (warp_gid >= n_batches) return;
     const uint32_t my_batches = (n_batches - warp_gid + warps_total - 1u) / warps_total;  // batches warp_gid + s * warps_total
 
-    using Shape = FinShape<DEEP>;
+    using Shape = FinShape<DEEP, WIDE>;
+    using P = typename Pos<WIDE>::type;                                       // a BWT position
+    using E = typename std::conditional<WIDE, ulonglong2, uint2>::type;       // a suffix-table entry {l, h}
     constexpr uint32_t kBufMask = DEEP ? 1u : 0u;  // buffer of batch s: s & kBufMask
     constexpr int kFinQueue = Shape::kQueue;
     uint8_t *const wsm = smem + warp * Shape::kWarpSmem;
@@ -84,11 +91,12 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
     uint8_t *const bytes = wsm + Shape::kBufs * 32 * kFinRowBytes;          // kBufs byte buffers (SRC 0)
     uint8_t *const queue = bytes + Shape::kBufs * kFinByteBuf;              // kQueue x {u64 word, u64 seed, u32 index}
     uint64_t *const q_word = reinterpret_cast<uint64_t *>(queue);
-    uint64_t *const q_seed = q_word + kFinQueue;
-    uint32_t *const q_idx = reinterpret_cast<uint32_t *>(q_seed + kFinQueue);
+    uint64_t *const q_seed = q_word + kFinQueue;                             // l | h << 32; WIDE: l, and h in q_seed_hi
+    [[maybe_unused]] uint64_t *const q_seed_hi = q_seed + kFinQueue;
+    uint32_t *const q_idx = reinterpret_cast<uint32_t *>(q_seed + (WIDE ? 2 : 1) * kFinQueue);
     uint32_t q_fill = 0;  // warp-uniform
 
-    const uint2 *const table = reinterpret_cast<const uint2 *>(plan.tab);
+    const E *const table = reinterpret_cast<const E *>(plan.tab);
     const char *const fin_base = reinterpret_cast<const char *>(ix.fin);
     const uint32_t fshift = ix.fin_shift, fmask = (1u << fshift) - 1u, flb = ix.fin_lb;
     const uint64_t stream_pol = policy_evict_first();  // query bytes, final-step lines, results: read or written once
@@ -126,10 +134,11 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
     // ---- B: pack (SRC 0) / normalise (SRC 1, 2) the k-mer of batch s: `word` = its symbols 2 bits each, the LAST
     //         symbol in the top bits; request the table entry.  A k-mer holding `$` / `N` is seeded one symbol at a
     //         time (seed_general) and goes to live list B here and now; kind = what stage C has to do with the query.
-    auto stage_b = [&](uint32_t s, uint64_t word_reg, uint64_t &word, uint2 &entry, uint32_t &kind) {
+    auto stage_b = [&](uint32_t s, uint64_t word_reg, uint64_t &word, E &entry, uint32_t &kind) {
         kind = kKindNone;
         word = 0;
-        entry = make_uint2(0u, 0u);
+        entry.x = 0;
+        entry.y = 0;
         if (s >= my_batches) return;
         const uint32_t q = first_query(s) + lane;
         if (q >= n) return;
@@ -155,14 +164,19 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
                 uint64_t lo = 0, hi = 0, word0 = 0;
                 uint32_t flag = 0;
                 bool finished = false, bad = false;
-                seed_general<false>(ix, const_cast<const uint8_t *>(buf) + o, k, lay, q, packed, lo, hi, flag, finished, word0, bad);
+                seed_general<WIDE>(ix, const_cast<const uint8_t *>(buf) + o, k, lay, q, packed, lo, hi, flag, finished, word0, bad);
                 if (bad) atomicOr(status, 1u);
                 if (finished) {
                     out[q] = hi - lo;
                 } else {
                     const uint64_t pos = (uint64_t)n - 1 - atomicAdd(live + 1, 1ull);
                     packed[lay.w0() + pos] = word0;
-                    packed[lay.seed() + pos] = lo | (hi << 32);
+                    if constexpr (WIDE) {
+                        packed[lay.seed() + pos] = lo;
+                        packed[lay.seed() + lay.n + pos] = hi;
+                    } else {
+                        packed[lay.seed() + pos] = lo | (hi << 32);
+                    }
                     qidx_arr[pos] = q | (flag << 30);
                 }
                 return;
@@ -179,7 +193,7 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
     };
 
     // ---- C: batch s: the range, the line, and the warp's copy of the 32 lines into row buffer s & 1
-    auto stage_c = [&](uint32_t s, uint64_t word, uint2 entry, uint32_t &kind, uint32_t &l, uint32_t &h, uint32_t &tag) {
+    auto stage_c = [&](uint32_t s, uint64_t word, E entry, uint32_t &kind, P &l, P &h, uint32_t &tag) {
         l = entry.x;
         h = entry.y;
         uint32_t line = 0;
@@ -191,7 +205,7 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
                 kind = kKindTwoBuckets;
             } else {
                 const uint64_t mixed = fin_mix40((word << (2u * depth)) >> (64 - kFinCodeBits));
-                line = ((l >> fshift) << flb) | (uint32_t)(mixed & ((1ull << flb) - 1ull));
+                line = ((uint32_t)(l >> fshift) << flb) | (uint32_t)(mixed & ((1ull << flb) - 1ull));
                 tag = (uint32_t)(mixed >> flb);
             }
         }
@@ -217,6 +231,7 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
         for (uint32_t i = lane; i < q_fill; i += 32u) {
             packed[lay.w0() + base + i] = q_word[i];
             packed[lay.seed() + base + i] = q_seed[i];
+            if constexpr (WIDE) packed[lay.seed() + lay.n + base + i] = q_seed_hi[i];
             qidx_arr[base + i] = q_idx[i];
         }
         __syncwarp();
@@ -240,7 +255,7 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
     };
 
     // ---- D: batch s: scan the line, write the count, or queue the query for the general kernel
-    auto stage_d = [&](uint32_t s, uint64_t word, uint32_t kind, uint32_t l, uint32_t h, uint32_t tag) {
+    auto stage_d = [&](uint32_t s, uint64_t word, uint32_t kind, P l, P h, uint32_t tag) {
         if (s >= my_batches) return;  // (warp-uniform)
         const uint32_t q = first_query(s) + lane;
         bool to_queue = kind == kKindTwoBuckets;
@@ -275,7 +290,7 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
         // the group behind it); a third group of one code is rare enough to leave to the general kernel
         int acc = 0;
         {
-            const int pl = (int)(l & fmask), ph = (int)(h & fmask);
+            const int pl = (int)((uint32_t)l & fmask), ph = (int)((uint32_t)h & fmask);
             const uint32_t n1 = matches ? (roww[i1] & 15u) : 0u;
             add_runs(roww, i1 + 1u, n1, pl, ph, acc);
             if (__any_sync(kFull, matches > 1u)) {
@@ -294,7 +309,12 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
             if (to_queue) {
                 const uint32_t at = q_fill + __popc(qm & ((1u << lane) - 1u));
                 q_word[at] = word << (2u * depth);  // the kFinSyms symbols still to consume, first in the top bits
-                q_seed[at] = (uint64_t)l | ((uint64_t)h << 32);
+                if constexpr (WIDE) {
+                    q_seed[at] = l;
+                    q_seed_hi[at] = h;
+                } else {
+                    q_seed[at] = (uint64_t)l | ((uint64_t)h << 32);
+                }
                 q_idx[at] = q | (nofin << 30);
             }
             q_fill += (uint32_t)__popc(qm);
@@ -308,8 +328,9 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
         //      iteration ago) -> A(s+3) -> commit.  Register state: batch s in D (d_*), s+1 in C (c_*).
         uint64_t a_word = 0, b_wordreg = 0, w1 = 0;
         uint64_t c_word = 0, d_word = 0;
-        uint2 c_entry = make_uint2(0u, 0u);
-        uint32_t c_kind = kKindNone, d_kind = kKindNone, d_l = 0, d_h = 0, d_tag = 0;
+        E c_entry{};
+        uint32_t c_kind = kKindNone, d_kind = kKindNone, d_tag = 0;
+        P d_l = 0, d_h = 0;
         auto land = [&]() {
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_all;" ::: "memory");
@@ -317,7 +338,7 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
         };
         stage_a(0, b_wordreg);
         land();
-        uint2 e0;
+        E e0;
         uint32_t k0;
         stage_b(0, b_wordreg, d_word, e0, k0);                  // B(0)
         __syncwarp();
@@ -332,11 +353,12 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
             land();                                             // lines(s), bytes(s+2)
             stage_d(s, d_word, d_kind, d_l, d_h, d_tag);
             uint64_t b_word;
-            uint2 b_entry;
+            E b_entry;
             uint32_t b_kind;
             stage_b(s + 2, b_wordreg, b_word, b_entry, b_kind); // requests the table entry C(s+2) reads next iteration
             __syncwarp();                                       // rows were read by D(s), the byte buffer by B(s+2)
-            uint32_t n_l, n_h, n_tag;
+            P n_l, n_h;
+            uint32_t n_tag;
             stage_c(s + 1, c_word, c_entry, c_kind, n_l, n_h, n_tag);
             stage_a(s + 3, a_word);
             b_wordreg = a_word;
@@ -347,8 +369,9 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
         // ---- the pipeline.  Register state: batch s in D (d_*), s+1 in C (c_*), s+2 in B; the word of s+3 in flight (SRC 1, 2)
         uint64_t a_word = 0, b_wordreg = 0;
         uint64_t c_word = 0, d_word = 0;
-        uint2 c_entry = make_uint2(0u, 0u);
-        uint32_t c_kind = kKindNone, d_kind = kKindNone, d_l = 0, d_h = 0, d_tag = 0;
+        E c_entry{};
+        uint32_t c_kind = kKindNone, d_kind = kKindNone, d_tag = 0;
+        P d_l = 0, d_h = 0;
 
         // prologue: bytes of batches 0 and 1 (and 2), B for batch 0 and 1, C for batch 0
         stage_a(0, b_wordreg);
@@ -360,11 +383,12 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
         __syncwarp();
         {   // B(0)
             uint64_t word;
-            uint2 entry;
+            E entry;
             uint32_t kind;
             stage_b(0, b_wordreg, word, entry, kind);
             d_word = word;
-            uint32_t l, h, tag;
+            P l, h;
+            uint32_t tag;
             stage_c(0, word, entry, kind, l, h, tag);  // C(0): lines of batch 0 -> rows 0
             d_kind = kind; d_l = l; d_h = h; d_tag = tag;
         }
@@ -378,7 +402,8 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
 
         for (uint32_t s = 0; s < my_batches; s++) {
             // C(s+1): needs the entry requested by B(s+1)
-            uint32_t n_l, n_h, n_tag;
+            P n_l, n_h;
+            uint32_t n_tag;
             __syncwarp();  // rows (s+1) & 1 were read by D(s-1); byte buffer (s+3) & 1 by B(s+1)
             stage_c(s + 1, c_word, c_entry, c_kind, n_l, n_h, n_tag);
             stage_a(s + 3, a_word);
@@ -388,7 +413,7 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
             // B(s+2) BEFORE D(s): the table entry it requests is consumed by C(s+2) at the top of the next iteration, and
             // D(s)'s line scan in between is what hides that (L2) latency
             uint64_t b_word;
-            uint2 b_entry;
+            E b_entry;
             uint32_t b_kind;
             stage_b(s + 2, b_wordreg, b_word, b_entry, b_kind);
             b_wordreg = a_word;
@@ -411,12 +436,12 @@ pack_seed_final_kernel(IndexView ix, const void *__restrict__ src_v, uint32_t k_
     }
 }
 
-template <int SRC, uint32_t K, bool DEEP>
+template <int SRC, uint32_t K, bool DEEP, bool WIDE = false>
 cudaError_t launch_shape(int device, const IndexView &ix, const void *d_src, uint32_t k, const SeedPlan &plan, const PackedLayout &lay,
                      uint64_t *d_packed, uint64_t *d_out, uint32_t *d_status, cudaStream_t st) {
     static bool prepared[64] = {};
-    constexpr int kFinSmem = FinShape<DEEP>::kSmem;
-    const void *fn = (const void *)pack_seed_final_kernel<SRC, K, DEEP>;
+    constexpr int kFinSmem = FinShape<DEEP, WIDE>::kSmem;
+    const void *fn = (const void *)pack_seed_final_kernel<SRC, K, DEEP, WIDE>;
     if (device < 0 || device >= 64 || !prepared[device]) {
         if (cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinSmem); e != cudaSuccess) return e;
         cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -427,13 +452,14 @@ cudaError_t launch_shape(int device, const IndexView &ix, const void *d_src, uin
     const uint64_t full = (uint64_t)sm_count(device) * (uint64_t)per_sm;
     const uint64_t need = ((lay.n + 31) / 32 + kFinWarps - 1) / kFinWarps;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(need, full));
-    pack_seed_final_kernel<SRC, K, DEEP><<<grid, kFinThreads, kFinSmem, st>>>(ix, d_src, k, plan, lay, d_packed, d_out, d_status);
+    pack_seed_final_kernel<SRC, K, DEEP, WIDE><<<grid, kFinThreads, kFinSmem, st>>>(ix, d_src, k, plan, lay, d_packed, d_out, d_status);
     return cudaGetLastError();
 }
 
 template <int SRC, uint32_t K>
 cudaError_t launch_t(int device, const IndexView &ix, const void *d_src, uint32_t k, const SeedPlan &plan, const PackedLayout &lay,
                      uint64_t *d_packed, uint64_t *d_out, uint32_t *d_status, cudaStream_t st) {
+    if (index_is_wide(ix)) return launch_shape<SRC, 0, false, true>(device, ix, d_src, k, plan, lay, d_packed, d_out, d_status, st);  // 64-bit positions: runtime k, shallow shape
     const char *env = getenv("MSBWT_FINAL_DEEP");  // =1: the two-buffer shape (A/B measurements)
     if (env && atoi(env) != 0) return launch_shape<SRC, K, true>(device, ix, d_src, k, plan, lay, d_packed, d_out, d_status, st);
     return launch_shape<SRC, K, false>(device, ix, d_src, k, plan, lay, d_packed, d_out, d_status, st);
@@ -443,7 +469,7 @@ cudaError_t launch_t(int device, const IndexView &ix, const void *d_src, uint32_
 
 bool final_fast_path_applies(const IndexView &ix, uint32_t k, const void *d_src, int src_kind) {
     const char *env = getenv("MSBWT_FINAL_FAST");  // =0: the general kernels only (A/B measurements, tests)
-    if ((env && atoi(env) == 0) || !ix.fin || !ix.oct || index_is_wide(ix) || k > 32u || k <= (uint32_t)kFinSyms) return false;
+    if ((env && atoi(env) == 0) || !ix.fin || !ix.oct || k > 32u || k <= (uint32_t)kFinSyms) return false;
     const uint32_t depth = list_a_table_depth(ix, k);
     if (depth == 0 || k - depth != (uint32_t)kFinSyms) return false;
     if ((((ix.total >> ix.fin_shift) + 1) << ix.fin_lb) >= (1ull << 31)) return false;  // line indices travel as 31 bits

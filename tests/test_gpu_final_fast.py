@@ -55,6 +55,8 @@ def pack_stats_of(g, q, k):
     dict(final_bucket_shift=8),                           # 256-position buckets: many ranges span two
     dict(final_bucket_shift=10, final_lines_log2=12, keep_quad_index=0),
     dict(final_bucket_shift=12, suffix_table_s=12),       # deepest table level 12: k = 32 starts from it, k = 31 from 11
+    dict(superblock_shift=4),                             # 64-bit positions (superblocks of 2048 symbols): the WIDE
+    dict(superblock_shift=4, final_bucket_shift=8),       # instantiation -- 16-byte table entries, two seed words
 ])
 def test_one_request_path_is_bit_exact(midsize, monkeypatch, opts):
     from harness import synth
@@ -115,8 +117,8 @@ def test_one_request_path_with_overflowed_lines():
     rle = bwt_build.build_rle_bwt(reads)[0].cpu().numpy()
     o = O.RleBWT()
     o.load_vector(rle)
-    for keep_quad in (1, 0):
-        g = M.RleBWT(oct_index=1, final_index=1, keep_quad_index=keep_quad)
+    for keep_quad, sb in ((1, 0), (0, 0), (-1, 5)):   # (sb = 5: 64-bit positions, the WIDE kernels, no quad image)
+        g = M.RleBWT(oct_index=1, final_index=1, keep_quad_index=keep_quad, superblock_shift=sb)
         g.load_vector(rle)
         for k in (31, 32):
             q = synth.make_queries(reads, k, 60_000, 5_000).cpu().numpy()
