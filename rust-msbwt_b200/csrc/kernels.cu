@@ -162,6 +162,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(256)
 seed_packed_kernel(IndexView ix, const uint64_t *__restrict__ words, uint32_t k, SeedPlan plan, PackedLayout lay,
                    uint64_t *__restrict__ packed, uint64_t *__restrict__ out) {
+    warp_sync_guard(lay);  // append_live's ballots follow a divergent table lookup
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = q < lay.n;
     const uint32_t nw = (k + kPairSymsPerWord - 1) / kPairSymsPerWord;  // <= kPackMaxWords (the host checks)
@@ -195,6 +196,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(256)
 seed_u64_kernel(IndexView ix, const uint64_t *__restrict__ kmers, uint32_t k, SeedPlan plan, PackedLayout lay,
                 uint64_t *__restrict__ packed, uint64_t *__restrict__ out) {
+    warp_sync_guard(lay);  // append_live's ballots follow a divergent table lookup
     const uint64_t q = (uint64_t)blockIdx.x * kPackThreads + threadIdx.x;
     const bool valid = q < lay.n;
     uint64_t lo = 0, hi = 0, word0 = 0;

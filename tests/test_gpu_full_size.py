@@ -122,7 +122,8 @@ def _check_long_kmers(g, o, cfg, dev, monkeypatch):
     must occur, and a sample must equal the oracle's."""
     from harness import synth
     reads = synth.make_reads(cfg["reads"], cfg["read_len"], cfg["coverage"], cfg["error"], device=dev)
-    for k, n, reps in ((43, 100_000_000, 6), (63, 70_000_000, 4)):
+    # (k = 15 and 101: the other two lengths of configs[3]'s k-sweep, at its own size of 10 M queries)
+    for k, n, reps in ((43, 100_000_000, 6), (63, 70_000_000, 4), (15, 10_000_000, 2), (101, 10_000_000, 2)):
         q = synth.make_queries(reads, k, n, 0, seed_offset=k)
         first = None
         for _ in range(reps):

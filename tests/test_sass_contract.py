@@ -61,6 +61,9 @@ def test_every_warp_cooperative_search_kernel_keeps_its_warp_syncs(sass_counts):
         assert c["SHFL"] >= 4 and c["WARPSYNC"] >= 1, (name, c)
     for name, c in pick(lambda k: re.search(r"count_kmers_packed_kernel<\(bool\)[01], \(int\)2,", k) is not None).items():
         assert c["SHFL"] >= 3 and c["WARPSYNC"] >= 1, (name, c)
+    # the pack / seed kernels: append_live's ballots (one atomic per CTA and list) follow a divergent table lookup
+    for name, c in pick(lambda k: re.search(r"(pack_seed_kernel|seed_packed_kernel|seed_u64_kernel)<", k) is not None).items():
+        assert c["VOTE"] >= 2 and c["WARPSYNC"] >= 1, (name, c)
     # the one-request kernel (ptxas keeps these on its own; pinned all the same)
     for name, c in pick(lambda k: "pack_seed_final_kernel<" in k).items():
         assert c["WARPSYNC"] >= 24, (name, c)
