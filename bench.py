@@ -98,8 +98,11 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  nvidia-smi needs a few hundred
+    milliseconds before its first line and the timed region of the headline workload is ~40 ms, so the sampler is
+    started before the warm-up, the warm-up is extended until its first line is there (`has_sample`), it samples every
+    20 ms, and `stop` keeps the samples whose own time stamps fall inside the timed region."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -118,37 +121,55 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self) -> dict:
+    def has_sample(self) -> bool:
+        try:
+            return self.proc is None or os.path.getsize(self.path) > 0
+        except OSError:
+            return True
+
+    @staticmethod
+    def _epoch(stamp: str):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0: float | None = None, t1: float | None = None) -> dict:
+        """t0, t1: time.time() around the timed region; without them every sample counts"""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    rows.append((self._epoch(f[0]), float(f[2]), float(f[3]), [nm for nm, v in zip(names, f[6:10]) if v.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for nm, v in zip(names, f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+        window = "timed region"
+        inside = [r for r in rows if t0 is not None and r[0] is not None and t0 <= r[0] <= t1]
+        if not inside and t0 is not None:   # (a region shorter than the sampling period can fall between two samples)
+            inside = [r for r in rows if r[0] is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+            window = "timed region +- 50 ms"
+        if not inside:
+            inside, window = rows, "warm-up + timed region"
+        if inside:
+            out = {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside),
+                   "reasons": sorted({nm for r in inside for nm in r[3]}), "samples": len(inside), "window": window}
         return out
 
 
@@ -424,28 +445,36 @@ def measure_ours(args, cfg, ctx, primary: bool):
             ev[1].record()
 
     # ---- value: kernel-only, inputs resident in HBM ----
-    for _ in range(args.warmup):
-        flush.fill_(1)
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step()
+    if rank == 0:   # further untimed steps (the GPU stays under load) until nvidia-smi has printed its first line
+        t_wait = time.time()
+        while not sampler.has_sample() and time.time() - t_wait < 3.0:
+            flush.fill_(1)
+            step()
+            torch.cuda.synchronize()
+    barrier()
     launches0 = M.launch_count()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
+    t_epoch0 = time.time()
     for s in range(args.steps):
         flush.fill_(s & 1)               # L2 flush between timed iterations (not inside the event spans)
         ev[s][0].record()
         step((ev[s][1], ev[s][2]))
     barrier()
+    t_epoch1 = time.time()
     wall = time.perf_counter() - t_wall0
     launches = M.launch_count() - launches0
     step_ms = [ev[s][0].elapsed_time(ev[s][2]) for s in range(args.steps)]
     kern_ms = [ev[s][1].elapsed_time(ev[s][2]) for s in range(args.steps)]
     total_ms = max_over_ranks(sum(step_ms))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_epoch0, t_epoch1) if rank == 0 else None
     assert int(d_status.item()) == 0
     value = n_job * args.steps / (total_ms / 1e3)
     checksum = int(d_out.sum().item())
