@@ -405,14 +405,20 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             }
         }
 #endif
-        const uint32_t p0_lo = (uint32_t)(uintptr_t)p0, p0_hi = (uint32_t)((uintptr_t)p0 >> 32);
+        // every lane leaves {address, meta} in the 16 spare bytes at the end of its own row (a row is 128 + 16 bytes and
+        // the copies only write the first 128): one 16-byte store and eight 16-byte reads per lane instead of the 24
+        // shuffles that used to carry the same three words (a tenth of the kernel's instructions on long k-mers)
+        *reinterpret_cast<uint4 *>(rows + lane * kOctRowBytes + kOctLineBytes) =
+            make_uint4((uint32_t)(uintptr_t)p0, (uint32_t)((uintptr_t)p0 >> 32), meta, 0u);
+        __syncwarp();
         {
             const uint32_t j = lane & 7u;  // this lane's 16 bytes of a line
 #pragma unroll
             for (uint32_t c = 0; c < 8u; c++) {
                 const uint32_t o = 4u * c + (lane >> 3);  // the lane whose line this is
-                const uint32_t m = __shfl_sync(kFull, meta, o);
-                const uint64_t a = ((uint64_t)__shfl_sync(kFull, p0_hi, o) << 32) | __shfl_sync(kFull, p0_lo, o);
+                const uint4 want_o = *reinterpret_cast<const uint4 *>(rows + o * kOctRowBytes + kOctLineBytes);
+                const uint32_t m = want_o.z;
+                const uint64_t a = ((uint64_t)want_o.y << 32) | want_o.x;
                 // oct: bytes 16j.. of the line; quad: the sector of l into bytes 0..31, the sector of h into 32..63;
                 // table: the 16 bytes that hold the entry into bytes 0..15
                 const uint64_t src = a + 16u * j + (((m & 3u) == 2u && j >= 2u) ? (uint64_t)(m & ~31u) - 32u : 0u);
