@@ -8,19 +8,20 @@
 
 namespace msbwt {
 
-// ---------------------------------------------------------------- oct image on top of the quad image
+// ---------------------------------------------------------------- oct image (with or without the quad image beside it)
 //
-// 32-bit positions only.  While kOctSyms (ten) or more symbols are left a step reads one 128-byte line of the
-// oct image (layout.h); the quad image (and one-symbol ranks) serve remainders, ranges that straddle two oct
-// buckets and the lines that overflowed (two quad steps + two one-symbol steps instead of one oct step).
+// While kOctSyms (ten) or more symbols are left a step reads one 128-byte line of the oct image (layout.h); when
+// exactly kFinSyms (twenty) are left, one final-step line answers the count; the quad image (if it was kept) and
+// one-symbol ranks serve remainders, ranges that straddle two buckets and the lines that overflowed.  32-bit
+// positions, or 64-bit ones in the WIDE instantiation (wide_kernels.cu), which has no quad image.
 //
 // What HBM random access is bound by is the number of L2 requests that miss -- about 40 G/s whatever their
 // size (profiles/r1_gather_*.json) -- and what reaches that bound is the number of them in flight.  So:
 //
 //  * one thread per query (1024 queries in flight per SM), but the index lines are fetched by the WARP:
-//    every lane publishes the address of the line (or the two quad sectors) its query needs next, and in
-//    eight rounds the warp copies the 32 lines into shared memory with cp.async, eight lanes x 16 bytes per
-//    line, i.e. ONE 128-byte request per line and no load registers.  (A thread that read its own line with
+//    every lane publishes the address of the line (or the two quad sectors) its query needs next (in the 16
+//    spare bytes of its shared-memory row), and in eight rounds the warp copies the 32 lines into shared memory
+//    with cp.async, eight lanes x 16 bytes per line, i.e. ONE 128-byte request per line and no load registers.  (A thread that read its own line with
 //    four 256-bit loads paid four requests per line and ran at a quarter of the line rate; a quad of lanes
 //    per query kept only 384 queries per SM in flight: profiles/r1_o2_*, r1_o6_* summaries.)
 //  * every iteration is ISSUE (branch-free, whatever kind of step each lane needs), one wait, CONSUME (each
@@ -129,14 +130,16 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     constexpr uint32_t kWarpSmem = 32 * kOctRowBytes + 2 * kPool;
 
     const uint32_t n = RAW ? n_raw : (uint32_t)packed[lay.live()];  // queries to walk (live list A)
-    // CONVERGENCE.  The warp protocol below (24 shuffles, a ballot and three __syncwarp() per iteration) needs the 32
+    // CONVERGENCE.  The warp protocol below (a ballot, requests and lines other lanes read from shared memory, four
+    // __syncwarp(), a warp-wide scan -- and, when the trouble was found, 24 shuffles per iteration) needs the 32
     // lanes together at every one of those points.  Left alone, ptxas 12.9 "proves" that they are (the divergent
     // regions all close with BSYNC.RECONVERGENT), drops every __syncwarp() and issues the shuffles / votes without a
     // WARPSYNC -- and on B200 that assumption does not hold under load: on batches of 50-100 M k-mers that take oct
     // steps AND a final-step line (k = 43, 53, 63) about every other launch left a few hundred queries unanswered and
     // some warps never finished, while every build whose SASS carries WARPSYNC.COLLECTIVE ran clean (profiles/
     // r2t_convergence.md).  warp_sync_guard (kernel_common.cuh) makes ptxas compile the kernel conservatively:
-    // WARPSYNC.COLLECTIVE before every collective, which is what the source asks for.  tests/test_sass_contract.py
+    // a path with WARPSYNC.COLLECTIVE before every collective for a warp that is not all there, which is what the
+    // source asks for.  tests/test_sass_contract.py
     // checks the SASS of every instantiation for it, so that a toolchain that changes its mind cannot silently take
     // it away again.
     warp_sync_guard(lay);
