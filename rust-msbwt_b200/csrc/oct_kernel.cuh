@@ -51,6 +51,11 @@ __device__ __forceinline__ void cp_async16_hint(void *smem, const void *gmem, bo
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(gmem), "r"(on ? 16u : 0u), "l"(policy)
                  : "memory");
 }
+// 16 bytes when `bytes` is 16, sixteen zero bytes (and no read) when it is 0
+__device__ __forceinline__ void cp_async16_bytes(void *smem, const void *gmem, uint32_t bytes) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
 // `bytes` (0..16) from gmem, the rest of the 16 zero-filled
 __device__ __forceinline__ void cp_async16_partial(void *smem, const void *gmem, uint32_t bytes) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
@@ -158,6 +163,11 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
     uint8_t *const rows = smem + (threadIdx.x >> 5) * kWarpSmem;  // 32 rows of kOctRowBytes
     uint8_t *const pools = rows + 32 * kOctRowBytes;               // 2 pools of 32 queries
     const uint4 *const my_row = reinterpret_cast<const uint4 *>(rows + lane * kOctRowBytes);
+    // this lane copies bytes [16 j, 16 j + 16) of the lines of rows 4 c + (lane >> 3): of every oct / final-step line
+    // (kind 1), of a quad request (kind 2) when j < 4, of a table entry (kind 3) when j == 0 -- bit `kind` of piece_on
+    const uint32_t piece_off = 16u * (lane & 7u);
+    const uint32_t piece_on = 2u | ((lane & 7u) < 4u ? 4u : 0u) | ((lane & 7u) == 0u ? 8u : 0u);
+    const uint32_t piece_hmask = (lane & 7u) >= 2u ? ~0u : 0u;  // pieces 2, 3 of a quad request: the sector of h
 
     // A list that is not long against the grid (the leftovers of the one-request kernel: a percent of the batch; a
     // 10 M-query batch of long k-mers) is cut into smaller chunks, about sixteen per resident warp: a warp walks its
@@ -383,10 +393,12 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
                                 : quad_base + ((size_t)code8 * ix.nsec4 + sl) * kQuadSectorBytes;
         if (is_table) p0 = table_base + ((entry * 8u) & ~15ull);
         if (is_fin) p0 = fin_base + ((((size_t)(l >> fshift)) << flb) | (size_t)(fin_mixed & ((1ull << flb) - 1ull))) * kFinLineBytes;
-        // low two bits: kind (1 oct, 2 quad, 3 table entry, 0 nothing); the rest (quad): byte distance from the
-        // sector of l to the sector of h
-        // a final-step line is fetched like an oct line (kind 1: all eight 16-byte pieces)
-        const uint32_t meta = is_table ? 3u : ((is_oct || is_fin) ? 1u : (is_quad ? (2u | ((sh - sl) * (uint32_t)kQuadSectorBytes)) : 0u));
+        // kind: 1 oct line or final-step line (all eight 16-byte pieces), 2 quad (the sector of l into bytes 0..31 of the
+        // row, the sector of h into 32..63), 3 table entry (its 16 bytes into bytes 0..15), 0 nothing.  h_adj (quad): what
+        // pieces 2 and 3 add to `p0 + 16 j` to land in the sector of h -- its byte distance from the sector of l, less the 32
+        // bytes the two pieces already skipped (mod 2^32: 16 j >= 32 there, the sum is never negative)
+        const uint32_t kind = is_table ? 3u : ((is_oct || is_fin) ? 1u : (is_quad ? 2u : 0u));
+        const uint32_t h_adj = is_quad ? (sh - sl) * (uint32_t)kQuadSectorBytes - 32u : 0u;
         if constexpr (STATS) {
             st_cnt[0] += is_oct;
             st_cnt[1] += is_fin;
@@ -408,26 +420,20 @@ count_kmers_oct_kernel(IndexView ix, const uint64_t *__restrict__ packed, Packed
             }
         }
 #endif
-        // every lane leaves {address, meta} in the 16 spare bytes at the end of its own row (a row is 128 + 16 bytes and
-        // the copies only write the first 128): one 16-byte store and eight 16-byte reads per lane instead of the 24
-        // shuffles that used to carry the same three words (a tenth of the kernel's instructions on long k-mers)
+        // every lane leaves {address, kind, h_adj} in the 16 spare bytes at the end of its own row (a row is 128 + 16 bytes
+        // and the copies only write the first 128): one 16-byte store and eight 16-byte reads per lane instead of the 24
+        // shuffles that used to carry the same words; what depends only on the lane (which pieces of which kind it copies)
+        // is in piece_on / piece_hmask, computed once
         *reinterpret_cast<uint4 *>(rows + lane * kOctRowBytes + kOctLineBytes) =
-            make_uint4((uint32_t)(uintptr_t)p0, (uint32_t)((uintptr_t)p0 >> 32), meta, 0u);
+            make_uint4((uint32_t)(uintptr_t)p0, (uint32_t)((uintptr_t)p0 >> 32), kind, h_adj);
         __syncwarp();
-        {
-            const uint32_t j = lane & 7u;  // this lane's 16 bytes of a line
 #pragma unroll
-            for (uint32_t c = 0; c < 8u; c++) {
-                const uint32_t o = 4u * c + (lane >> 3);  // the lane whose line this is
-                const uint4 want_o = *reinterpret_cast<const uint4 *>(rows + o * kOctRowBytes + kOctLineBytes);
-                const uint32_t m = want_o.z;
-                const uint64_t a = ((uint64_t)want_o.y << 32) | want_o.x;
-                // oct: bytes 16j.. of the line; quad: the sector of l into bytes 0..31, the sector of h into 32..63;
-                // table: the 16 bytes that hold the entry into bytes 0..15
-                const uint64_t src = a + 16u * j + (((m & 3u) == 2u && j >= 2u) ? (uint64_t)(m & ~31u) - 32u : 0u);
-                cp_async16(rows + o * kOctRowBytes + 16u * j, reinterpret_cast<const void *>(src),
-                           (m & 3u) == 1u || ((m & 3u) == 2u && j < 4u) || ((m & 3u) == 3u && j == 0u));
-            }
+        for (uint32_t c = 0; c < 8u; c++) {
+            const uint32_t o = 4u * c + (lane >> 3);  // the lane whose line this is
+            const uint4 want_o = *reinterpret_cast<const uint4 *>(rows + o * kOctRowBytes + kOctLineBytes);
+            const uint64_t a = ((uint64_t)want_o.y << 32) | want_o.x;
+            const uint64_t src = a + (uint64_t)(piece_off + (want_o.w & piece_hmask));
+            cp_async16_bytes(rows + o * kOctRowBytes + piece_off, reinterpret_cast<const void *>(src), ((piece_on >> want_o.z) & 1u) << 4);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_all;" ::: "memory");
