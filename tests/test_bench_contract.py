@@ -74,3 +74,40 @@ def test_bench_helpers_on_cpu():
     assert c["workload"].startswith("configs[2]") and c["queries"] == 100_000_000 and c["k"] == 31
     assert bench.workload_config(bench.WORKLOADS["cfg5"], 3_020_000_000, 8)["queries"] == 1_000_000_000
     assert bench.HEADLINE == "cfg3" and bench.WORKLOADS["cfg3"]["scaling"] == "strong"
+
+
+def test_clock_sampler_keeps_the_samples_inside_the_timed_region(tmp_path):
+    """bench.py's `clocks` object: nvidia-smi lines carry their own time stamps; only those inside the timed region count
+    (the region is ~40 ms on the headline workload), with explicit fallbacks when none falls inside"""
+    import datetime
+    import time
+
+    import bench
+
+    def stamp(t):
+        return datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+
+    class Done:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=0):
+            pass
+
+    now = time.time()
+
+    def sampler(lines):
+        c = bench.ClockSampler(0)
+        p = tmp_path / f"s{len(lines)}_{lines[0][0]}.csv"
+        p.write_text("".join(f"{stamp(now + dt)}, 0, {mhz}, 1965, 512.3, 0x0, Not Active, Not Active, Not Active, {cap}\n" for dt, mhz, cap in lines))
+        c.proc, c.path = Done(), str(p)
+        return c
+
+    lines = [(-0.30, 1200, "Not Active"), (0.010, 1965, "Not Active"), (0.030, 1950, "Active"), (0.200, 900, "Not Active")]
+    got = sampler(lines).stop(now, now + 0.040)
+    assert got == {"sm_mhz": 1957.5, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 2, "window": "timed region"}
+    near = sampler([(-0.02, 1965, "Not Active"), (0.5, 900, "Not Active")]).stop(now, now + 0.010)
+    assert near["samples"] == 1 and near["sm_mhz"] == 1965.0 and near["window"] == "timed region +- 50 ms"
+    far = sampler([(-1.0, 1800, "Not Active")]).stop(now, now + 0.010)
+    assert far["samples"] == 1 and far["window"] == "warm-up + timed region"
+    assert bench.ClockSampler(0).stop(now, now + 1)["sm_mhz"] is None   # never started: no clocks, no crash

@@ -4,6 +4,14 @@ CUDA events on the launching stream (L2 flushed between iterations) and prints o
 of the counts, so that two builds can be compared for speed AND for equality of their results.
 
     MSBWT_LIBRARY_PATH=build/variants/lib_x.so python tools/pack_ab.py [--workload cfg2] [--iters 20] [--k 31]
+
+Also the stress / post-mortem harness of profiles/r2t_convergence.md:
+    --also k:n,k:n      further (k, n) runs on the same index;  --superblock-shift s: 64-bit positions (the WIDE kernels)
+    --postmortem T      prefill the outputs (--prefill v) before every iteration; when one does not end within T seconds,
+                        read the outputs and the dispenser counter from ANOTHER stream and list the unanswered queries
+    --verify-pack       check after every pack stage that live list A is a permutation of the batch with the words / seeds
+                        of the first iteration;  --trace: synchronise and report after every launch
+    --watchdog T        dump the Python stack and exit when a (k, n) run takes longer than T seconds
 """
 from __future__ import annotations
 
